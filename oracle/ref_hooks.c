@@ -22,6 +22,7 @@
  */
 #include "common/common.h"
 #include "encoder/me.h"
+#include "encoder/macroblock.h"
 #include <time.h>
 
 void x264_me_search_ref_real( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
@@ -81,10 +82,6 @@ WRAP7(WRAPX3, sad_x3, sad)
 WRAP7(WRAPX4, sad_x4, sad)
 WRAP7(WRAPX3, satd_x3, satd)
 WRAP7(WRAPX4, satd_x4, satd)
-
-#define INSTALL7(tab) do { \
-    x264_pixel_cmp_t tmp[7] = { w_##tab##_0, w_##tab##_1, w_##tab##_2, w_##tab##_3, w_##tab##_4, w_##tab##_5, w_##tab##_6 }; \
-    memcpy( h->pixf.tab, tmp, sizeof(tmp) ); } while(0)
 
 static void install_count_wrappers( x264_t *h )
 {
@@ -224,10 +221,24 @@ void pcamv_hook_slice_begin( x264_t *h )
 }
 
 /* ---- slice end: final per-MB decisions as stored in the frame arrays -------------------------- */
+extern int16_t *g_cost_mv[52];            /* reference encoder/analyse.c:189 (malloc base, centre at +2*4*2048) */
+extern uint16_t x264_cost_ref[52][3][33]; /* reference encoder/analyse.c:188 */
+static int g_cmv_dumped[52];
+
 void pcamv_hook_slice_end( x264_t *h )
 {
     if( !dump_on( h ) || !g_pslice )
         return;
+    if( g_cost_mv[h->sh.i_qp] && !g_cmv_dumped[h->sh.i_qp] )
+    {
+        /* 'CMV0': int32 qp, lambda; int16 cost_mv[32769] (index 0 <-> mv delta -16384); uint16 cost_ref[3][33] */
+        int32_t hd[2] = { h->sh.i_qp, x264_lambda_tab[h->sh.i_qp] };
+        g_cmv_dumped[h->sh.i_qp] = 1;
+        rec_begin( "CMV0", sizeof(hd) + 32769*2 + 3*33*2 );
+        fwrite( hd, 1, sizeof(hd), g_dump );
+        fwrite( g_cost_mv[h->sh.i_qp], 2, 32769, g_dump );
+        fwrite( x264_cost_ref[h->sh.i_qp], 2, 3*33, g_dump );
+    }
     {
         /* 'SLCE': int32 frame, pass, n_mb; then int8 type[n_mb]; int8 ref[4*n_mb] in b8 raster;
          * int16 mv[16*n_mb][2] in b4 raster (frame layout, stride i_b4_stride); int16 mvr0[n_mb][2]. */
@@ -340,6 +351,14 @@ static void fill_common( x264_t *h, x264_me_t *m, pcamv_call_rec_t *r )
     memset( r, 0, sizeof(*r) );
     r->frame = h->i_frame; r->pass = g_pass; r->mb_xy = h->mb.i_mb_xy; r->mb_x = h->mb.i_mb_x; r->mb_y = h->mb.i_mb_y;
     r->i_pixel = m->i_pixel; r->i_ref = m->i_ref; r->xoff = off % FENC_STRIDE; r->yoff = off / FENC_STRIDE;
+    {
+        /* sub-8x8 searches leave m->i_ref unset (reference encoder/analyse.c:1569-1693): recover the
+         * reference index from the plane pointer instead */
+        int k;
+        for( k = 0; k < h->mb.pic.i_fref[0]; k++ )
+            if( m->p_fref[0] == &h->mb.pic.p_fref[0][k][0][r->xoff + r->yoff*m->i_stride[0]] )
+                r->i_ref = k;
+    }
     r->i_ref_cost = m->i_ref_cost;
     r->me_method = h->mb.i_me_method; r->me_range = h->param.analyse.i_me_range; r->subme = h->mb.i_subpel_refine;
     r->b_chroma_me = h->mb.b_chroma_me; r->qp = h->mb.i_qp;

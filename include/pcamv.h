@@ -1,0 +1,160 @@
+/* pcamv.h — C ABI of libpcamv_cuda.so: the B200 (sm_100a) implementation of the PCAMV encoder's
+ * motion-estimation hot path.  Plain C, plain pointers and sizes; no CUDA or torch types.
+ *
+ * The reference (x264 build 66 + PCAMV, /root/reference) has no FFI layer; the seams this library
+ * replaces are (file:line in the reference):
+ *
+ *   leaf seam     x264_pixel_function_t   common/pixel.h:63-103   filled by x264_pixel_init (pixel.c:565)
+ *                 x264_mc_functions_t     common/mc.h:31-77       filled by x264_mc_init   (mc.c:406)
+ *   search seam   x264_me_search_ref      encoder/me.h:58  (me.c:158)
+ *                 x264_me_refine_qpel     encoder/me.h:62  (me.c:669)
+ *                 x264_ih_get_mv_cost     encoder/analyse.c:2391 (static; the stego cost table)
+ *   frame seam    x264_frame_filter       common/mc.c:453  (+ x264_frame_expand_border[_filtered],
+ *                                         common/frame.c:246,275), called from x264_fdec_filter_row
+ *                 P-slice body of x264_macroblock_analyse   encoder/analyse.c:2613-3172,3518-3689
+ *
+ * Conventions follow the reference: every entry point returns 0 on success and -1 on failure
+ * (the reference's `int` + x264_log convention, common/common.h:39-47); the message is available
+ * from pcamv_last_error().  The caller owns all host memory; the context owns device memory, its
+ * CUDA stream and pinned staging.  A context is thread-compatible (one encoder thread per context,
+ * like one x264_t), not thread-safe.  There is NO CPU fallback: without a usable CUDA device
+ * pcamv_open fails.  CUDA errors are sticky: after the first failure every call returns -1.
+ */
+#ifndef PCAMV_H
+#define PCAMV_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCAMV_ABI_VERSION 1
+#define PCAMV_MAX_REFS 16
+#define PCAMV_MAX_MVC 10
+
+/* block sizes: same numbering as the reference's PIXEL_WxH enum (common/pixel.h:30-42) */
+enum { PCAMV_PIXEL_16x16 = 0, PCAMV_PIXEL_16x8, PCAMV_PIXEL_8x16, PCAMV_PIXEL_8x8,
+       PCAMV_PIXEL_8x4, PCAMV_PIXEL_4x8, PCAMV_PIXEL_4x4 };
+/* search methods: X264_ME_* (x264.h) */
+enum { PCAMV_ME_DIA = 0, PCAMV_ME_HEX, PCAMV_ME_UMH, PCAMV_ME_ESA, PCAMV_ME_TESA };
+/* macroblock types / partitions as numbered by the reference (common/macroblock.h:29-60) */
+enum { PCAMV_P_L0 = 4, PCAMV_P_8x8 = 5, PCAMV_P_SKIP = 6 };
+enum { PCAMV_D_L0_4x4 = 0, PCAMV_D_L0_8x4 = 1, PCAMV_D_L0_4x8 = 2, PCAMV_D_L0_8x8 = 3,
+       PCAMV_D_8x8 = 13, PCAMV_D_16x8 = 14, PCAMV_D_8x16 = 15, PCAMV_D_16x16 = 16 };
+
+typedef struct pcamv_ctx pcamv_ctx;
+
+/* Encoder-wide configuration: the x264_param_t fields the path reads (x264.h:154-311) plus geometry. */
+typedef struct pcamv_cfg
+{
+    int abi_version;        /* PCAMV_ABI_VERSION */
+    int device;             /* CUDA device ordinal */
+    int width, height;      /* luma size in pixels, already rounded up to multiples of 16 */
+    int me_method;          /* param.analyse.i_me_method */
+    int me_range;           /* param.analyse.i_me_range (after validation) */
+    int subpel_refine;      /* param.analyse.i_subpel_refine; this build supports 1..5 for frame analysis */
+    int chroma_me;          /* param.analyse.b_chroma_me */
+    int max_refs;           /* param.i_frame_reference */
+    int mv_range;           /* param.analyse.i_mv_range in pixels (level default, encoder/encoder.c:558-561) */
+    int b_cabac;            /* param.b_cabac */
+    int b_fast_pskip;       /* param.analyse.b_fast_pskip */
+    int b_dct_decimate;     /* param.analyse.b_dct_decimate */
+    int analyse_inter;      /* param.analyse.inter flag word (X264_ANALYSE_PSUB16x16 = 0x10, PSUB8x8 = 0x20) */
+    int chroma_qp_offset;   /* pps chroma_qp_index_offset */
+    int reserved[8];
+} pcamv_cfg;
+
+/* Per-QP tables.  They are built on the host because the reference builds cost_mv with float
+ * log under -ffast-math (encoder/analyse.c:46,193-229); the device only ever reads them. */
+typedef struct pcamv_qp_tables
+{
+    int qp;                          /* luma QP the tables are for */
+    int lambda;                      /* x264_lambda_tab[qp]  (analyse.c:148) */
+    int lambda2_chroma;              /* x264_lambda2_tab[chroma qp], for the P_SKIP chroma SSD gate */
+    int chroma_qp;                   /* h->chroma_qp_table[qp] */
+    const int16_t *cost_mv;          /* 32769 entries, entry 16384 <-> mv difference 0 */
+    const uint16_t *cost_ref;        /* 3*33 entries: x264_cost_ref[qp] */
+    const uint16_t *quant4_mf[2];    /* [0]=CQM_4PY(inter luma) [1]=CQM_4PC(inter chroma): 16 entries for this qp / chroma qp */
+    const uint16_t *quant4_bias[2];  /* same indexing */
+    const int32_t *dequant4_mf[2];   /* 6*16 entries each: h->dequant4_mf[CQM_4PY / CQM_4PC] */
+} pcamv_qp_tables;
+
+/* One x264_me_search_ref (mode 0) or x264_me_refine_qpel (mode 1) call: the x264_me_t inputs
+ * (encoder/me.h:30-51) plus the h->mb.* state those functions read. */
+typedef struct pcamv_me_call
+{
+    int32_t mode;                    /* 0 = search, 1 = refine_qpel */
+    int32_t mb_x, mb_y;              /* macroblock position */
+    int32_t xoff, yoff;              /* block offset inside the macroblock, pixels */
+    int32_t i_pixel;                 /* PCAMV_PIXEL_* */
+    int32_t ref_slot;                /* reference slot uploaded with pcamv_put_ref* */
+    int32_t i_ref_cost;
+    int32_t mv_min_fpel[2], mv_max_fpel[2], mv_min_spel[2], mv_max_spel[2];
+    int32_t i_mvc, has_thresh, thresh_in;
+    int16_t mvp[2];
+    int16_t mvc[PCAMV_MAX_MVC][2];
+    int16_t mv_in[2];                /* refine only */
+    int32_t cost_in, cost_mv_in;     /* refine only */
+} pcamv_me_call;
+
+typedef struct pcamv_me_result
+{
+    int16_t mv[2];
+    int32_t cost, cost_mv, thresh_out;
+} pcamv_me_result;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+/* replaces: nothing in the reference; called from x264_encoder_open after mbcmp_init (encoder/encoder.c:766) */
+int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg);
+/* called from x264_encoder_close (encoder/encoder.c:2670) */
+void pcamv_close(pcamv_ctx *ctx);
+const char *pcamv_last_error(const pcamv_ctx *ctx);   /* ctx may be NULL: error of the last failed pcamv_open */
+int pcamv_abi_version(void);
+
+/* ---- tables -------------------------------------------------------------------------------------- */
+/* called when x264_mb_analyse_load_costs first sees a QP (encoder/analyse.c:198) */
+int pcamv_set_qp_tables(pcamv_ctx *ctx, const pcamv_qp_tables *t);
+
+/* ---- frames -------------------------------------------------------------------------------------- */
+/* Source frame after x264_frame_copy_picture + mod16 expansion (encoder/encoder.c:2163-2167).
+ * y/u/v point at pixel (0,0); strides in bytes. */
+int pcamv_put_fenc(pcamv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c);
+
+/* Reconstructed + deblocked reference frame (end of x264_fdec_filter_row for a kept frame,
+ * encoder/encoder.c:2030).  The GPU replicates the borders (common/frame.c:224-273), builds the H, V
+ * and HV half-pel planes (common/mc.c:134-190,453-475), replicates their borders (frame.c:275-301) and,
+ * for --me esa, the integral image (mc.c:311-345,477-511). */
+int pcamv_put_ref(pcamv_ctx *ctx, int slot, int poc, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                  int stride_y, int stride_c);
+/* Test/debug: upload the six planes of a reference exactly as the host holds them (padded buffers:
+ * luma planes start 32 rows / 32 columns before pixel (0,0), chroma 16/16), bypassing the GPU filter. */
+int pcamv_put_ref_planes(pcamv_ctx *ctx, int slot, int poc, const uint8_t *const luma_padded[4],
+                         const uint8_t *u_padded, const uint8_t *v_padded);
+/* Copy one device plane of a slot back (padded buffer, same layout as above).  plane: 0..3 luma
+ * (integer, H, V, HV), 4 = U, 5 = V.  dst must hold pcamv_plane_bytes(). */
+int pcamv_get_ref_plane(pcamv_ctx *ctx, int slot, int plane, uint8_t *dst);
+size_t pcamv_plane_bytes(const pcamv_ctx *ctx, int plane);
+int pcamv_plane_stride(const pcamv_ctx *ctx, int plane);
+
+/* ---- search seam ---------------------------------------------------------------------------------- */
+/* n independent x264_me_search_ref / x264_me_refine_qpel evaluations against the current fenc and
+ * the uploaded reference slots (1:1 stand-in for encoder/me.h:58,62; used by the parity tests and
+ * by the stateless throughput benchmark). */
+int pcamv_me_search_batch(pcamv_ctx *ctx, const pcamv_me_call *calls, int n, pcamv_me_result *results);
+
+/* Benchmark support: keep the batch resident on the device and time repeated launches with CUDA
+ * events on the context's stream.  pcamv_me_batch_upload stages calls once; pcamv_me_batch_run
+ * launches the search kernel `iters` times and returns the mean kernel time in milliseconds. */
+int pcamv_me_batch_upload(pcamv_ctx *ctx, const pcamv_me_call *calls, int n);
+int pcamv_me_batch_run(pcamv_ctx *ctx, int iters, float *ms_per_launch);
+int pcamv_me_batch_download(pcamv_ctx *ctx, pcamv_me_result *results, int n);
+
+/* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
+long long pcamv_launch_count(const pcamv_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCAMV_H */

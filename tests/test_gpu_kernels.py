@@ -1,0 +1,102 @@
+"""GPU parity tests proper: every call goes through the C-ABI of libpcamv_cuda.so (ctypes)."""
+import os
+
+import numpy as np
+import pytest
+
+import refrun
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"]
+
+
+def open_ctx(pcamv, dump, slice_):
+    c = dump.cfg
+    ctx = pcamv.PcamvContext(slice_.width, slice_.lines_y, me_method=c["me_method"], me_range=c["me_range"],
+                             subpel_refine=c["subme"], chroma_me=c["chroma_me"], max_refs=max(c["refs"], 1),
+                             mv_range=c["mv_range"], b_cabac=c["b_cabac"], b_fast_pskip=c["fast_pskip"],
+                             b_dct_decimate=c["dct_decimate"], analyse_inter=c["inter"])
+    assert ctx.plane_stride(0) == slice_.stride_y and ctx.plane_stride(4) == slice_.stride_c
+    return ctx
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_frame_filter_matches_reference_planes(pcamv, cuda_lib, name, tmp_path):
+    """A6/A7: borders + H/V/HV planes built on the GPU from the integer reconstruction are byte-identical,
+    padding included, to the planes the reference encoder held (x264_frame_filter + expand_border*)."""
+    dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path(name, str(tmp_path)))
+    checked = 0
+    for s in dump.slices():
+        if not s.with_planes:
+            continue
+        ctx = open_ctx(pcamv, dump, s)
+        for slot, r in enumerate(s.refs):
+            H, W = s.lines_y, s.width
+            y = r["luma"][0][32:32 + H, 32:32 + W]
+            u = r["u"][16:16 + H // 2, 16:16 + W // 2]
+            v = r["v"][16:16 + H // 2, 16:16 + W // 2]
+            ctx.put_ref(slot, r["poc"], y, u, v)
+            for k in range(4):
+                got = ctx.get_ref_plane(slot, k)
+                assert np.array_equal(got, r["luma"][k]), "luma plane %d of slot %d differs" % (k, slot)
+            assert np.array_equal(ctx.get_ref_plane(slot, 4), r["u"])
+            assert np.array_equal(ctx.get_ref_plane(slot, 5), r["v"])
+            checked += 1
+        ctx.close()
+    assert checked >= 1
+
+
+def run_calls(pcamv, dump, use_gpu_filter):
+    calls, refine = dump.calls()
+    tables = dump.cost_tables
+    total = bad = 0
+    for s in dump.slices():
+        if not s.with_planes or s.pass_ == 2:
+            continue
+        ctx = open_ctx(pcamv, dump, s)
+        t = tables[s.qp]
+        ctx.set_qp_tables(s.qp, t["lambda"], t["cost_mv"], t["cost_ref"])
+        ctx.put_fenc(s.fenc[0][:, :s.width], s.fenc[1][:, :s.width // 2], s.fenc[2][:, :s.width // 2])
+        for slot, r in enumerate(s.refs):
+            if use_gpu_filter:
+                H, W = s.lines_y, s.width
+                ctx.put_ref(slot, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2],
+                            r["v"][16:16 + H // 2, 16:16 + W // 2])
+            else:
+                ctx.put_ref_planes(slot, r["poc"], r["luma"], r["u"], r["v"])
+        sel = calls["frame"] == s.frame          # both passes read the same planes
+        rc, rf = calls[sel], refine[sel]
+        res = ctx.me_search_batch(pcamv.dumpfmt.calls_to_abi(rc, rf))
+        ok = (res["mv"] == rc["mv"]).all(axis=1) & (res["cost"] == rc["cost"])
+        thr = (rc["has_thresh"] != 0) & ~rf
+        ok &= np.where(thr, res["thresh_out"] == rc["thresh_out"], res["cost_mv"] == rc["cost_mv"])
+        total += len(rc)
+        bad += int((~ok).sum())
+        ctx.close()
+    return total, bad
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_search_calls_match_reference(pcamv, cuda_lib, name, tmp_path):
+    """A1-A5, A8: every recorded x264_me_search_ref / x264_me_refine_qpel call reproduces mv, cost, cost_mv and
+    the multi-ref half-pel threshold bit-exactly, reading planes the GPU filtered itself."""
+    dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path(name, str(tmp_path)))
+    total, bad = run_calls(pcamv, dump, use_gpu_filter=True)
+    assert total > 1000 and bad == 0, (total, bad)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/x264_dump not built")
+@pytest.mark.parametrize("args,frames,size", [
+    ("--me umh --subme 5 --ref 1", "1:3", (352, 288)),
+    ("--me hex --subme 5 --ref 3 --partitions all --mixed-refs", "3:5", (352, 288)),
+    ("--me umh --subme 5 --ref 1", "1:2", (1280, 720)),
+])
+def test_search_calls_live_reference(pcamv, cuda_lib, args, frames, size, tmp_path):
+    w, h = size
+    clip = refrun.synth_clip(pcamv, w, h, 5 if w < 1000 else 2, config=2, stream=1, workdir=str(tmp_path))
+    dumpf = str(tmp_path / "d.bin")
+    refrun.run_ref(clip, w, h, ("--qp 26 --keyint 250 --emrate 0.2 " + args).split(), dump=dumpf, frames=frames)
+    dump = pcamv.dumpfmt.Dump(dumpf)
+    total, bad = run_calls(pcamv, dump, use_gpu_filter=True)
+    assert total > 5000 and bad == 0, (total, bad)

@@ -1,0 +1,153 @@
+"""Parser for the tagged binary dumps written by the instrumented reference (oracle/ref_hooks.c).
+
+Record stream: 4-byte tag, uint32 size, payload.  Used by tests/ and bench.py to turn recorded
+x264_me_search_ref / x264_me_refine_qpel calls and frame planes into C-ABI inputs and expected outputs.
+"""
+import numpy as np
+
+from .host import ME_CALL_DTYPE
+
+CALL_REC_DTYPE = np.dtype([
+    ("frame", "<i4"), ("pass_", "<i4"), ("mb_xy", "<i4"), ("mb_x", "<i4"), ("mb_y", "<i4"),
+    ("i_pixel", "<i4"), ("i_ref", "<i4"), ("xoff", "<i4"), ("yoff", "<i4"), ("i_ref_cost", "<i4"),
+    ("me_method", "<i4"), ("me_range", "<i4"), ("subme", "<i4"), ("b_chroma_me", "<i4"), ("qp", "<i4"),
+    ("mv_min_fpel", "<i4", 2), ("mv_max_fpel", "<i4", 2), ("mv_min_spel", "<i4", 2), ("mv_max_spel", "<i4", 2),
+    ("i_mvc", "<i4"), ("has_thresh", "<i4"), ("thresh_in", "<i4"), ("thresh_out", "<i4"),
+    ("mvp", "<i2", 2), ("mvc", "<i2", (10, 2)), ("mv_in", "<i2", 2), ("cost_in", "<i4"), ("cost_mv_in", "<i4"),
+    ("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4")], align=True)
+assert CALL_REC_DTYPE.itemsize == 176
+
+MBAN_DTYPE = np.dtype([
+    ("frame", "<i4"), ("pass_", "<i4"), ("mb_xy", "<i4"), ("type", "<i4"), ("partition", "<i4"),
+    ("sub", "<i4", 4), ("b_skip_mc", "<i4"), ("qp", "<i4"),
+    ("mv", "<i2", (16, 2)), ("ref", "i1", 4), ("pskip_mv", "<i2", 2)])
+assert MBAN_DTYPE.itemsize == 44 + 64 + 4 + 4
+
+EMBD_MB_DTYPE = np.dtype([
+    ("type", "<i4"), ("qp", "<i4"), ("partition", "<i4"), ("used", "u1"), ("sub", "u1", 4), ("pad", "u1", 3),
+    ("mv_stego", "<i2", (16, 2)), ("inter_stego_cost", "<i4", 16), ("ref", "i1", 16), ("mv", "<i2", (16, 2)),
+    ("pskip_mv", "<i2", 2)])
+assert EMBD_MB_DTYPE.itemsize == 232
+
+CFG_NAMES = ["width", "height", "mb_w", "mb_h", "me_method", "me_range", "subme", "refs", "chroma_me", "mv_range",
+             "qp", "b_cabac", "inter", "mixed_refs", "fast_pskip", "dct_decimate", "keyint", "transform_8x8",
+             "trellis", "threads", "b4_stride", "b8_stride", "mb_stride", "emrate_x1e6"]
+
+
+class Slice:
+    """One 'SLCB' record: header + (optionally) fenc and reference planes as numpy views."""
+
+    def __init__(self, payload):
+        hd = np.frombuffer(payload, dtype="<i4", count=16)
+        (self.frame, self.pass_, self.type, self.qp, self.nref, self.with_planes, self.stride_y, self.stride_c,
+         self.lines_y, self.lines_c, self.width, self.fenc_frame, self.poc, self.first_mb, self.last_mb, _) = [int(x) for x in hd]
+        self.refs = []
+        self.fenc = None
+        if not self.with_planes:
+            return
+        buf = np.frombuffer(payload, dtype=np.uint8)
+        p = 64
+        sy, sc, ly, lc = self.stride_y, self.stride_c, self.lines_y, self.lines_c
+
+        def take(n, shape):
+            nonlocal p
+            a = buf[p:p + n].reshape(shape)
+            p += n
+            return a
+
+        self.fenc = (take(sy * ly, (ly, sy)), take(sc * lc, (lc, sc)), take(sc * lc, (lc, sc)))
+        for _ in range(self.nref):
+            poc, frame = [int(x) for x in np.frombuffer(payload, dtype="<i4", count=2, offset=p)]
+            p += 8
+            luma = [take(sy * (ly + 64), (ly + 64, sy)) for _ in range(4)]
+            u = take(sc * (lc + 32), (lc + 32, sc))
+            v = take(sc * (lc + 32), (lc + 32, sc))
+            self.refs.append({"poc": poc, "frame": frame, "luma": luma, "u": u, "v": v})
+
+
+class Dump:
+    def __init__(self, path_or_bytes):
+        if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
+            self.raw = bytes(path_or_bytes)
+        else:
+            with open(path_or_bytes, "rb") as f:
+                self.raw = f.read()
+        self.records = []           # (tag, offset, size)
+        p, n = 0, len(self.raw)
+        while p + 8 <= n:
+            tag = self.raw[p:p + 4].decode("latin-1")
+            size = int.from_bytes(self.raw[p + 4:p + 8], "little")
+            if p + 8 + size > n:
+                break
+            self.records.append((tag, p + 8, size))
+            p += 8 + size
+        self.cfg = {}
+        self.cost_tables = {}       # qp -> dict(lambda, cost_mv[32769], cost_ref[3,33])
+        for tag, off, size in self.records:
+            if tag == "CFG0":
+                vals = np.frombuffer(self.raw, dtype="<i4", count=24, offset=off)
+                self.cfg = {k: int(v) for k, v in zip(CFG_NAMES, vals)}
+            elif tag == "CMV0":
+                qp, lam = [int(x) for x in np.frombuffer(self.raw, dtype="<i4", count=2, offset=off)]
+                cm = np.frombuffer(self.raw, dtype="<i2", count=32769, offset=off + 8)
+                cr = np.frombuffer(self.raw, dtype="<u2", count=99, offset=off + 8 + 32769 * 2).reshape(3, 33)
+                self.cost_tables[qp] = {"lambda": lam, "cost_mv": cm, "cost_ref": cr}
+
+    def payload(self, rec):
+        _, off, size = rec
+        return memoryview(self.raw)[off:off + size]
+
+    def slices(self):
+        for rec in self.records:
+            if rec[0] == "SLCB":
+                yield Slice(self.payload(rec))
+
+    def _stack(self, tag, dtype):
+        recs = [r for r in self.records if r[0] == tag]
+        out = np.zeros(len(recs), dtype=dtype)
+        for i, r in enumerate(recs):
+            out[i] = np.frombuffer(self.raw, dtype=dtype, count=1, offset=r[1])[0]
+        return out
+
+    def calls(self):
+        """All MESR / MERQ records in file order -> (structured array, is_refine bool array)."""
+        recs = [r for r in self.records if r[0] in ("MESR", "MERQ")]
+        out = np.zeros(len(recs), dtype=CALL_REC_DTYPE)
+        refine = np.zeros(len(recs), dtype=bool)
+        for i, r in enumerate(recs):
+            out[i] = np.frombuffer(self.raw, dtype=CALL_REC_DTYPE, count=1, offset=r[1])[0]
+            refine[i] = r[0] == "MERQ"
+        return out, refine
+
+    def mb_decisions(self):
+        return self._stack("MBAN", MBAN_DTYPE)
+
+    def embeds(self):
+        """List of dicts, one per 'EMBD' record (end of pass 1 of a P frame)."""
+        out = []
+        for tag, off, size in self.records:
+            if tag != "EMBD":
+                continue
+            frame, n_mb, length, an, num_filp = [int(x) for x in np.frombuffer(self.raw, dtype="<i4", count=5, offset=off)]
+            p = off + 20
+            mbs = np.frombuffer(self.raw, dtype=EMBD_MB_DTYPE, count=n_mb, offset=p); p += 232 * n_mb
+            cover = np.frombuffer(self.raw, dtype=np.uint8, count=length, offset=p); p += length
+            rho = np.frombuffer(self.raw, dtype="<f4", count=length, offset=p); p += 4 * length
+            msg = np.frombuffer(self.raw, dtype=np.uint8, count=max(an, 0), offset=p); p += max(an, 0)
+            stego = np.frombuffer(self.raw, dtype=np.uint8, count=length, offset=p); p += length
+            filp = np.frombuffer(self.raw, dtype=np.int8, count=length, offset=p); p += length
+            out.append({"frame": frame, "n_mb": n_mb, "length": length, "an": an, "num_filp": num_filp, "mbs": mbs,
+                        "cover": cover, "rho": rho, "message": msg, "stego": stego, "filp": filp})
+        return out
+
+
+def calls_to_abi(recs, refine, slot_of_ref=None):
+    """Convert recorded calls into pcamv_me_call records (include/pcamv.h)."""
+    out = np.zeros(len(recs), dtype=ME_CALL_DTYPE)
+    out["mode"] = refine.astype(np.int32)
+    for k in ("mb_x", "mb_y", "xoff", "yoff", "i_pixel", "i_ref_cost", "mv_min_fpel", "mv_max_fpel", "mv_min_spel",
+              "mv_max_spel", "has_thresh", "thresh_in", "mvp", "mvc", "mv_in", "cost_in", "cost_mv_in"):
+        out[k] = recs[k]
+    out["i_mvc"] = np.minimum(recs["i_mvc"], 10)
+    out["ref_slot"] = recs["i_ref"] if slot_of_ref is None else np.asarray(slot_of_ref)[recs["i_ref"]]
+    return out

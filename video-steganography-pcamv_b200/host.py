@@ -1,0 +1,199 @@
+"""ctypes mirror of include/pcamv.h.
+
+Python stands in for the reference's C host here only because the parity tests and bench.py are
+Python; the reference encoder binds the very same C symbols.  Nothing in this file
+computes anything: every method is one C-ABI call.  If the CUDA library is missing or no GPU is
+present the calls raise — there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build
+
+MAX_MVC = 10
+
+
+class PcamvError(RuntimeError):
+    pass
+
+
+class Cfg(C.Structure):
+    _fields_ = [("abi_version", C.c_int), ("device", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("me_method", C.c_int), ("me_range", C.c_int), ("subpel_refine", C.c_int), ("chroma_me", C.c_int),
+                ("max_refs", C.c_int), ("mv_range", C.c_int), ("b_cabac", C.c_int), ("b_fast_pskip", C.c_int),
+                ("b_dct_decimate", C.c_int), ("analyse_inter", C.c_int), ("chroma_qp_offset", C.c_int),
+                ("reserved", C.c_int * 8)]
+
+
+class QpTables(C.Structure):
+    _fields_ = [("qp", C.c_int), ("lambda_", C.c_int), ("lambda2_chroma", C.c_int), ("chroma_qp", C.c_int),
+                ("cost_mv", C.c_void_p), ("cost_ref", C.c_void_p),
+                ("quant4_mf", C.c_void_p * 2), ("quant4_bias", C.c_void_p * 2), ("dequant4_mf", C.c_void_p * 2)]
+
+
+# numpy views of the POD records (layout checked against sizeof in load_library)
+ME_CALL_DTYPE = np.dtype([
+    ("mode", "<i4"), ("mb_x", "<i4"), ("mb_y", "<i4"), ("xoff", "<i4"), ("yoff", "<i4"), ("i_pixel", "<i4"),
+    ("ref_slot", "<i4"), ("i_ref_cost", "<i4"),
+    ("mv_min_fpel", "<i4", 2), ("mv_max_fpel", "<i4", 2), ("mv_min_spel", "<i4", 2), ("mv_max_spel", "<i4", 2),
+    ("i_mvc", "<i4"), ("has_thresh", "<i4"), ("thresh_in", "<i4"),
+    ("mvp", "<i2", 2), ("mvc", "<i2", (MAX_MVC, 2)), ("mv_in", "<i2", 2),
+    ("cost_in", "<i4"), ("cost_mv_in", "<i4")], align=True)
+ME_RESULT_DTYPE = np.dtype([("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4"), ("thresh_out", "<i4")], align=True)
+
+EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version", "pcamv_set_qp_tables",
+           "pcamv_put_fenc", "pcamv_put_ref", "pcamv_put_ref_planes", "pcamv_get_ref_plane", "pcamv_plane_bytes",
+           "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
+           "pcamv_me_batch_download", "pcamv_launch_count"]
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libpcamv_cuda.so (built in-tree by build.build_cuda) and declare the prototypes."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or build.LIB
+    if not os.path.exists(path):
+        raise PcamvError("libpcamv_cuda.so is not built (%s); run __graft_entry__.build()" % path)
+    lib = C.CDLL(path)
+    vp, ip = C.c_void_p, C.c_int
+    lib.pcamv_open.argtypes = [C.POINTER(vp), C.POINTER(Cfg)]; lib.pcamv_open.restype = ip
+    lib.pcamv_close.argtypes = [vp]; lib.pcamv_close.restype = None
+    lib.pcamv_last_error.argtypes = [vp]; lib.pcamv_last_error.restype = C.c_char_p
+    lib.pcamv_abi_version.argtypes = []; lib.pcamv_abi_version.restype = ip
+    lib.pcamv_set_qp_tables.argtypes = [vp, C.POINTER(QpTables)]; lib.pcamv_set_qp_tables.restype = ip
+    lib.pcamv_put_fenc.argtypes = [vp, vp, vp, vp, ip, ip]; lib.pcamv_put_fenc.restype = ip
+    lib.pcamv_put_ref.argtypes = [vp, ip, ip, vp, vp, vp, ip, ip]; lib.pcamv_put_ref.restype = ip
+    lib.pcamv_put_ref_planes.argtypes = [vp, ip, ip, C.POINTER(vp), vp, vp]; lib.pcamv_put_ref_planes.restype = ip
+    lib.pcamv_get_ref_plane.argtypes = [vp, ip, ip, vp]; lib.pcamv_get_ref_plane.restype = ip
+    lib.pcamv_plane_bytes.argtypes = [vp, ip]; lib.pcamv_plane_bytes.restype = C.c_size_t
+    lib.pcamv_plane_stride.argtypes = [vp, ip]; lib.pcamv_plane_stride.restype = ip
+    lib.pcamv_me_search_batch.argtypes = [vp, vp, ip, vp]; lib.pcamv_me_search_batch.restype = ip
+    lib.pcamv_me_batch_upload.argtypes = [vp, vp, ip]; lib.pcamv_me_batch_upload.restype = ip
+    lib.pcamv_me_batch_run.argtypes = [vp, ip, C.POINTER(C.c_float)]; lib.pcamv_me_batch_run.restype = ip
+    lib.pcamv_me_batch_download.argtypes = [vp, vp, ip]; lib.pcamv_me_batch_download.restype = ip
+    lib.pcamv_launch_count.argtypes = [vp]; lib.pcamv_launch_count.restype = C.c_longlong
+    if path == build.LIB:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PcamvContext:
+    """One encoder's GPU context (mirrors one x264_t)."""
+
+    def __init__(self, width, height, me_method=1, me_range=16, subpel_refine=5, chroma_me=1, max_refs=1,
+                 mv_range=512, b_cabac=1, b_fast_pskip=1, b_dct_decimate=1, analyse_inter=0x113, device=0):
+        self.lib = load_library()
+        cfg = Cfg()
+        cfg.abi_version = self.lib.pcamv_abi_version()
+        cfg.device = device
+        cfg.width, cfg.height = width, height
+        cfg.me_method, cfg.me_range, cfg.subpel_refine, cfg.chroma_me = me_method, me_range, subpel_refine, chroma_me
+        cfg.max_refs, cfg.mv_range, cfg.b_cabac, cfg.b_fast_pskip = max_refs, mv_range, b_cabac, b_fast_pskip
+        cfg.b_dct_decimate, cfg.analyse_inter = b_dct_decimate, analyse_inter
+        self.cfg = cfg
+        self.handle = C.c_void_p()
+        if self.lib.pcamv_open(C.byref(self.handle), C.byref(cfg)) != 0:
+            raise PcamvError(self.lib.pcamv_last_error(None).decode())
+        self.width, self.height = width, height
+        self._keep = []
+
+    def close(self):
+        if self.handle:
+            self.lib.pcamv_close(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PcamvError(self.lib.pcamv_last_error(self.handle).decode())
+
+    # -- tables ---------------------------------------------------------------------------------
+    def set_qp_tables(self, qp, lam, cost_mv, cost_ref=None, lambda2_chroma=0, chroma_qp=0,
+                      quant4_mf=(None, None), quant4_bias=(None, None), dequant4_mf=(None, None)):
+        t = QpTables()
+        t.qp, t.lambda_, t.lambda2_chroma, t.chroma_qp = qp, lam, lambda2_chroma, chroma_qp
+        keep = []
+
+        def arr(a, dt, n):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt)
+            assert a.size == n, (a.size, n)
+            keep.append(a)
+            return a.ctypes.data
+
+        t.cost_mv = arr(cost_mv, np.int16, 32769)
+        t.cost_ref = arr(cost_ref, np.uint16, 99)
+        for i in range(2):
+            t.quant4_mf[i] = arr(quant4_mf[i], np.uint16, 16)
+            t.quant4_bias[i] = arr(quant4_bias[i], np.uint16, 16)
+            t.dequant4_mf[i] = arr(dequant4_mf[i], np.int32, 96)
+        self._check(self.lib.pcamv_set_qp_tables(self.handle, C.byref(t)))
+
+    # -- frames ---------------------------------------------------------------------------------
+    def put_fenc(self, y, u, v):
+        y, u, v = (np.ascontiguousarray(p, dtype=np.uint8) for p in (y, u, v))
+        self._check(self.lib.pcamv_put_fenc(self.handle, _ptr(y), _ptr(u), _ptr(v), y.strides[0], u.strides[0]))
+
+    def put_ref(self, slot, poc, y, u, v):
+        y, u, v = (np.ascontiguousarray(p, dtype=np.uint8) for p in (y, u, v))
+        self._check(self.lib.pcamv_put_ref(self.handle, slot, poc, _ptr(y), _ptr(u), _ptr(v), y.strides[0], u.strides[0]))
+
+    def put_ref_planes(self, slot, poc, luma4, u, v):
+        luma4 = [np.ascontiguousarray(p, dtype=np.uint8) for p in luma4]
+        u, v = np.ascontiguousarray(u, dtype=np.uint8), np.ascontiguousarray(v, dtype=np.uint8)
+        for p in luma4:
+            assert p.nbytes == self.plane_bytes(0), (p.nbytes, self.plane_bytes(0))
+        assert u.nbytes == self.plane_bytes(4) and v.nbytes == self.plane_bytes(4)
+        ptrs = (C.c_void_p * 4)(*[p.ctypes.data for p in luma4])
+        self._check(self.lib.pcamv_put_ref_planes(self.handle, slot, poc, ptrs, _ptr(u), _ptr(v)))
+
+    def plane_bytes(self, plane):
+        return int(self.lib.pcamv_plane_bytes(self.handle, plane))
+
+    def plane_stride(self, plane):
+        return int(self.lib.pcamv_plane_stride(self.handle, plane))
+
+    def get_ref_plane(self, slot, plane):
+        out = np.empty(self.plane_bytes(plane), dtype=np.uint8)
+        self._check(self.lib.pcamv_get_ref_plane(self.handle, slot, plane, _ptr(out)))
+        return out.reshape(-1, self.plane_stride(plane))
+
+    # -- search seam ------------------------------------------------------------------------------
+    def me_search_batch(self, calls):
+        calls = np.ascontiguousarray(calls, dtype=ME_CALL_DTYPE)
+        res = np.zeros(len(calls), dtype=ME_RESULT_DTYPE)
+        self._check(self.lib.pcamv_me_search_batch(self.handle, _ptr(calls), len(calls), _ptr(res)))
+        return res
+
+    def me_batch_upload(self, calls):
+        calls = np.ascontiguousarray(calls, dtype=ME_CALL_DTYPE)
+        self._check(self.lib.pcamv_me_batch_upload(self.handle, _ptr(calls), len(calls)))
+        self._batch_n = len(calls)
+
+    def me_batch_run(self, iters=1):
+        ms = C.c_float()
+        self._check(self.lib.pcamv_me_batch_run(self.handle, iters, C.byref(ms)))
+        return float(ms.value)
+
+    def me_batch_download(self):
+        res = np.zeros(self._batch_n, dtype=ME_RESULT_DTYPE)
+        self._check(self.lib.pcamv_me_batch_download(self.handle, _ptr(res), self._batch_n))
+        return res
+
+    def launch_count(self):
+        return int(self.lib.pcamv_launch_count(self.handle))

@@ -151,6 +151,10 @@ int pcamv_me_batch_upload(pcamv_ctx *ctx, const pcamv_me_call *calls, int n);
 int pcamv_me_batch_run(pcamv_ctx *ctx, int iters, float *ms_per_launch);
 int pcamv_me_batch_download(pcamv_ctx *ctx, pcamv_me_result *results, int n);
 
+/* Measured integer-pipe issue peak of the device, in giga lane-operations/s: a microbenchmark of the
+ * VABSDIFF4 / IADD3 / LOP3 mix the SAD and SATD loops consist of.  Roofline denominator for the search kernels. */
+int pcamv_int_peak(pcamv_ctx *ctx, double *gops);
+
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 long long pcamv_launch_count(const pcamv_ctx *ctx);
 

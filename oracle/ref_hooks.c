@@ -343,6 +343,8 @@ typedef struct
     int16_t mv_in[2]; int32_t cost_in, cost_mv_in;
     /* out */
     int16_t mv[2]; int32_t cost, cost_mv;
+    /* accounting: block-distortion evaluations made by this call (PCAMV_COUNT=1) and its wall time */
+    int32_t n_cand, t_ns, pix_sad, pix_satd;
 } pcamv_call_rec_t;
 
 static void fill_common( x264_t *h, x264_me_t *m, pcamv_call_rec_t *r )
@@ -383,6 +385,7 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
         r.has_thresh = p_halfpel_thresh != NULL;
         r.thresh_in = p_halfpel_thresh ? *p_halfpel_thresh : 0;
     }
+    uint64_t c0 = g_cnt_sad + g_cnt_satd, ps0 = g_pix_sad, pt0 = g_pix_satd;
     clock_gettime( CLOCK_MONOTONIC, &t0 );
     g_in_me++;
     x264_me_search_ref_real( h, m, mvc, i_mvc, p_halfpel_thresh );
@@ -392,6 +395,9 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
     g_cnt_search++;
     if( rec )
     {
+        r.n_cand = (int32_t)(g_cnt_sad + g_cnt_satd - c0);
+        r.pix_sad = (int32_t)(g_pix_sad - ps0); r.pix_satd = (int32_t)(g_pix_satd - pt0);
+        r.t_ns = (int32_t)((t1.tv_sec - t0.tv_sec)*1000000000LL + (t1.tv_nsec - t0.tv_nsec));
         r.thresh_out = p_halfpel_thresh ? *p_halfpel_thresh : 0;
         r.mv[0] = m->mv[0]; r.mv[1] = m->mv[1]; r.cost = m->cost; r.cost_mv = m->cost_mv;
         rec_begin( "MESR", sizeof(r) );
@@ -409,6 +415,7 @@ void x264_me_refine_qpel( x264_t *h, x264_me_t *m )
         fill_common( h, m, &r );
         r.mv_in[0] = m->mv[0]; r.mv_in[1] = m->mv[1]; r.cost_in = m->cost; r.cost_mv_in = m->cost_mv;
     }
+    uint64_t c0 = g_cnt_sad + g_cnt_satd, ps0 = g_pix_sad, pt0 = g_pix_satd;
     clock_gettime( CLOCK_MONOTONIC, &t0 );
     g_in_me++;
     x264_me_refine_qpel_real( h, m );
@@ -418,6 +425,9 @@ void x264_me_refine_qpel( x264_t *h, x264_me_t *m )
     g_cnt_refine++;
     if( rec )
     {
+        r.n_cand = (int32_t)(g_cnt_sad + g_cnt_satd - c0);
+        r.pix_sad = (int32_t)(g_pix_sad - ps0); r.pix_satd = (int32_t)(g_pix_satd - pt0);
+        r.t_ns = (int32_t)((t1.tv_sec - t0.tv_sec)*1000000000LL + (t1.tv_nsec - t0.tv_nsec));
         r.mv[0] = m->mv[0]; r.mv[1] = m->mv[1]; r.cost = m->cost; r.cost_mv = m->cost_mv;
         rec_begin( "MERQ", sizeof(r) );
         fwrite( &r, 1, sizeof(r), g_dump );

@@ -20,6 +20,7 @@ struct CallRec      // mirrors pcamv_call_rec_t in oracle/ref_hooks.c
     int16_t mvc[10][2];
     int16_t mv_in[2]; int32_t cost_in, cost_mv_in;
     int16_t mv[2]; int32_t cost, cost_mv;
+    int32_t n_cand, t_ns, pix_sad, pix_satd;
 };
 
 struct SliceHdr

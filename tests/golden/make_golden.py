@@ -33,7 +33,7 @@ def main():
     for name, (w, h, n, noise, rng, args) in CASES.items():
         clip = refrun.synth_clip(pcamv, w, h, n, config=9, stream=len(name), noise16=noise, workdir=work)
         dump = os.path.join(work, name + ".bin")
-        refrun.run_ref(clip, w, h, args.split(), dump=dump, frames=rng)
+        refrun.run_ref(clip, w, h, args.split(), dump=dump, frames=rng, count=True)
         raw = open(dump, "rb").read()
         with lzma.open(os.path.join(HERE, name + ".bin.xz"), "wb", preset=9) as f:
             f.write(raw)

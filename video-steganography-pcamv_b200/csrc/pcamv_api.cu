@@ -154,11 +154,11 @@ extern "C" int pcamv_set_qp_tables(pcamv_ctx *ctx, const pcamv_qp_tables *t)
     GUARD();
     if (!t || !t->cost_mv) return fail(ctx, "pcamv_set_qp_tables: null table", cudaSuccess);
     // stage everything in one pinned block: cost_mv | cost_ref | mf0 mf1 | bias0 bias1 | dq0 dq1
-    const size_t need = 32769 * 2 + 2 + 3 * 33 * 2 + 4 * 16 * 2 + 2 * 96 * 4;
+    const size_t need = 65540 + 3 * 33 * 2 + 4 + 4 * 16 * 2 + 2 * 96 * 4;
     if (ensure_stage(ctx, need + 64)) return -1;
     uint8_t *h = ctx->h_stage;
     memcpy(h, t->cost_mv, 32769 * 2);
-    uint8_t *ht = h + 32770;        // 2-byte aligned table block
+    uint8_t *ht = h + 65540;        // 4-byte aligned table block behind the 32769 int16 entries
     size_t o = 0;
     auto put = [&](const void *src, size_t n) { if (src) memcpy(ht + o, src, n); else memset(ht + o, 0, n); size_t at = o; o += n; return at; };
     const size_t o_ref = put(t->cost_ref, 3 * 33 * 2);
@@ -347,4 +347,34 @@ extern "C" int pcamv_me_search_batch(pcamv_ctx *ctx, const pcamv_me_call *calls,
     ctx->launches += 1;
     CK(cudaGetLastError());
     return pcamv_me_batch_download(ctx, results, n);
+}
+
+// Integer-pipe issue peak, in giga lane-operations per second (32 lanes x instructions retired).
+extern "C" int pcamv_int_peak(pcamv_ctx *ctx, double *gops)
+{
+    GUARD();
+    if (!gops) return fail(ctx, "pcamv_int_peak: null argument", cudaSuccess);
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
+    const int blocks = sms * 8, iters = 4096;
+    uint32_t *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * 256 * 4));
+    launch_int_peak(d, blocks, 64, ctx->stream);                    // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++)
+    {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        launch_int_peak(d, blocks, iters, ctx->stream);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (ms < best) best = ms;
+    }
+    ctx->launches += 6;
+    cudaFree(d);
+    // per thread and iteration: 8 chains x 5 integer instructions (VABSDIFF4.ACC, IADD3 x2, LOP3, SHF)
+    const double ops = (double)blocks * 256 * iters * 8 * 5;
+    *gops = ops / (best * 1e-3) / 1e9;
+    return 0;
 }

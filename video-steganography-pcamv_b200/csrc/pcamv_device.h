@@ -52,4 +52,6 @@ void launch_hpel_filter(const uint8_t *src, uint8_t *dsth, uint8_t *dstv, uint8_
                         int stride, int width, int height, void *stream);
 void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int n, pcamv_me_result *results, void *stream);
 
+void launch_int_peak(uint32_t *out, int blocks, int iters, void *stream);
+
 } // namespace pcamv

@@ -285,4 +285,37 @@ void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int 
     k_search_batch<<<(n + SB_WARPS - 1) / SB_WARPS, SB_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, calls, n, results);
 }
 
+// =====================================================================================================
+// Integer issue-rate microbenchmark: the roofline denominator for the search kernels (SURVEY.md 8(d):
+// "measure the int32 issue peak with a micro-benchmark on the box").  Every thread runs `iters` rounds
+// of 8 independent chains of the instruction mix the SAD/SATD inner loops are made of
+// (VABSDIFF4.ACC, IADD3, LOP3); the result is written so nothing is optimised away.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = seed * (threadIdx.x + 1) + k; b[k] = seed ^ (0x9E3779B9u * (k + 1)); }
+    for (int i = 0; i < iters; i++)
+    {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            a[k] = __vsadu4(a[k], b[k]) + a[k];       // VABSDIFF4.U8.ACC
+            b[k] = (b[k] + a[k]) + 0x01010101u;       // IADD3
+            a[k] = (a[k] ^ b[k]) & 0x7f7f7f7fu;       // LOP3
+            b[k] = b[k] - (a[k] >> 1);                // SHF/IADD
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r += a[k] ^ b[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+void launch_int_peak(uint32_t *out, int blocks, int iters, void *stream)
+{
+    k_int_peak<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 12345u);
+}
+
 } // namespace pcamv

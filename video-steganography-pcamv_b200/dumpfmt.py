@@ -14,8 +14,9 @@ CALL_REC_DTYPE = np.dtype([
     ("mv_min_fpel", "<i4", 2), ("mv_max_fpel", "<i4", 2), ("mv_min_spel", "<i4", 2), ("mv_max_spel", "<i4", 2),
     ("i_mvc", "<i4"), ("has_thresh", "<i4"), ("thresh_in", "<i4"), ("thresh_out", "<i4"),
     ("mvp", "<i2", 2), ("mvc", "<i2", (10, 2)), ("mv_in", "<i2", 2), ("cost_in", "<i4"), ("cost_mv_in", "<i4"),
-    ("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4")], align=True)
-assert CALL_REC_DTYPE.itemsize == 176
+    ("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4"), ("n_cand", "<i4"), ("t_ns", "<i4"),
+    ("pix_sad", "<i4"), ("pix_satd", "<i4")], align=True)
+assert CALL_REC_DTYPE.itemsize == 192
 
 MBAN_DTYPE = np.dtype([
     ("frame", "<i4"), ("pass_", "<i4"), ("mb_xy", "<i4"), ("type", "<i4"), ("partition", "<i4"),

@@ -46,7 +46,7 @@ ME_RESULT_DTYPE = np.dtype([("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4"
 EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version", "pcamv_set_qp_tables",
            "pcamv_put_fenc", "pcamv_put_ref", "pcamv_put_ref_planes", "pcamv_get_ref_plane", "pcamv_plane_bytes",
            "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
-           "pcamv_me_batch_download", "pcamv_launch_count"]
+           "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak"]
 
 _lib = None
 
@@ -77,6 +77,7 @@ def load_library(path=None):
     lib.pcamv_me_batch_run.argtypes = [vp, ip, C.POINTER(C.c_float)]; lib.pcamv_me_batch_run.restype = ip
     lib.pcamv_me_batch_download.argtypes = [vp, vp, ip]; lib.pcamv_me_batch_download.restype = ip
     lib.pcamv_launch_count.argtypes = [vp]; lib.pcamv_launch_count.restype = C.c_longlong
+    lib.pcamv_int_peak.argtypes = [vp, C.POINTER(C.c_double)]; lib.pcamv_int_peak.restype = ip
     if path == build.LIB:
         _lib = lib
     return lib
@@ -194,6 +195,11 @@ class PcamvContext:
         res = np.zeros(self._batch_n, dtype=ME_RESULT_DTYPE)
         self._check(self.lib.pcamv_me_batch_download(self.handle, _ptr(res), self._batch_n))
         return res
+
+    def int_peak_gops(self):
+        g = C.c_double()
+        self._check(self.lib.pcamv_int_peak(self.handle, C.byref(g)))
+        return float(g.value)
 
     def launch_count(self):
         return int(self.lib.pcamv_launch_count(self.handle))

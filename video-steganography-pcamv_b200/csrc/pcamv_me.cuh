@@ -103,7 +103,7 @@ PCAMV_DEV uint32_t chroma4(const uint8_t *src, int stride, int qmx, int qmy, int
 // ---- distortion of up to N candidates, concurrently -----------------------------------------------
 // SAD at quarter-pel candidates (integer/half positions take the single-plane path).
 // out[i] = SAD only; the caller adds the MV cost.
-PCAMV_DEV void sad_cands(const MeBlock &b, int n, const int *qmx, const int *qmy, int *out)
+PCAMV_FN void sad_cands(const MeBlock &b, int n, const int *qmx, const int *qmy, int *out)
 {
     const int grp = team_grp(), sub = team_sub();
     const int w4 = b.bw >> 2, words = w4 * b.bh;
@@ -130,7 +130,7 @@ PCAMV_DEV void sad_cands(const MeBlock &b, int n, const int *qmx, const int *qmy
 }
 
 // SAD at full-pel candidates (mx,my in pixels): integer plane only.
-PCAMV_DEV void sad_fpel_cands(const MeBlock &b, int n, const int *mx, const int *my, int *out)
+PCAMV_FN void sad_fpel_cands(const MeBlock &b, int n, const int *mx, const int *my, int *out)
 {
     const int grp = team_grp(), sub = team_sub();
     const int w4 = b.bw >> 2, words = w4 * b.bh;
@@ -245,7 +245,7 @@ PCAMV_DEV int satd_chroma_part(const uint8_t *fenc, int fstride, int cw, int ch,
 // out[i] = luma SATD + U SATD + V SATD (each already halved like the reference's functions).
 // The reference adds chroma only while the running cost is still below the best (encoder/me.c:689-713);
 // chroma terms are non-negative, so adding them unconditionally gives the same decisions.
-PCAMV_DEV void satd_cands(const MeBlock &b, int n, const int *qmx, const int *qmy, int chroma, int *out,
+PCAMV_FN void satd_cands(const MeBlock &b, int n, const int *qmx, const int *qmy, int chroma, int *out,
                           const uint8_t *fenc_y, const uint8_t *fenc_u, const uint8_t *fenc_v, int use_satd = 1)
 {
     const int grp = team_grp(), sub = team_sub();
@@ -330,7 +330,7 @@ struct MeSearch
     PCAMV_MEM void dia1(int ox, int oy) { try_x4(ox, oy, 0, -1, 0, 1, -1, 0, 1, 0); }
 
     // symmetric cross around (ox,oy)  (reference encoder/me.c:131-155)
-    PCAMV_MEM void cross(int ox, int oy, int start, int x_max, int y_max)
+    PCAMV_MEMFN void cross(int ox, int oy, int start, int x_max, int y_max)
     {
         int i = start;
         if (x_max <= imin(mv_x_max - ox, ox - mv_x_min))
@@ -353,7 +353,7 @@ struct MeSearch
     }
 
     // hexagon (radius 2) walk followed by the 8-point square  (reference encoder/me.c:263-341)
-    PCAMV_MEM void hex_then_square(int me_range)
+    PCAMV_MEMFN void hex_then_square(int me_range)
     {
         // hexagon corner k (k = 0..5), walking order matches the reference's direction indices
         const int hx[6] = { -2, -1, 1, 2, 1, -1 };
@@ -416,7 +416,7 @@ struct MeSearch
     }
 
     // uneven-cross multi-hexagon-grid search (reference encoder/me.c:342-482)
-    PCAMV_MEM void search_umh(int pmx, int pmy, const int (*mvc)[2], int i_mvc)
+    PCAMV_MEMFN void search_umh(int pmx, int pmy, const int (*mvc)[2], int i_mvc)
     {
         int me_range = env.me_range;
         const int shift = b.i_pixel == PIX_16x16 ? 0 : b.i_pixel <= PIX_8x16 ? 1 : b.i_pixel == PIX_8x8 ? 2
@@ -519,7 +519,7 @@ struct MeSearch
 };
 
 // half-pel / quarter-pel refinement (reference encoder/me.c:715-843)
-PCAMV_DEV void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int hpel_iters, int qpel_iters,
+PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int hpel_iters, int qpel_iters,
                              int *p_halfpel_thresh, int b_refine_qpel)
 {
     const int chroma = env.chroma_me && b.i_pixel <= PIX_8x8;
@@ -630,7 +630,7 @@ PCAMV_DEV void subpel_iters(int subme, int out[4])
 // both are pure accelerations of a raster scan (y outer, x inner) with strict-< updates, which is
 // what is restated here.  The scanned width is rounded to a multiple of 4 exactly as the reference
 // rounds it (me.c:491), so up to 3 columns right of max_x are visited and the last one may be cut.
-PCAMV_DEV void esa_search(MeSearch &s)
+PCAMV_FN void esa_search(MeSearch &s)
 {
     const int range = s.env.me_range;
     const int min_x = imax(s.bmx - range, s.mv_x_min), min_y = imax(s.bmy - range, s.mv_y_min);
@@ -641,7 +641,7 @@ PCAMV_DEV void esa_search(MeSearch &s)
             s.try_x4(min_x + x, my, 0, 0, 1, 0, 2, 0, 3, 0);
 }
 
-PCAMV_DEV void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)[2], int i_mvc,
+PCAMV_FN void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)[2], int i_mvc,
                              int *p_halfpel_thresh, MeResult &m)
 {
     MeSearch s(env, b);
@@ -741,7 +741,7 @@ PCAMV_DEV void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc
 }
 
 // x264_me_refine_qpel (reference encoder/me.c:669-678); i_ref_cost is removed first for P blocks <= 8x8
-PCAMV_DEV void me_refine_qpel(const MeEnv &env, const MeBlock &b, MeResult &m, int i_ref_cost)
+PCAMV_FN void me_refine_qpel(const MeEnv &env, const MeBlock &b, MeResult &m, int i_ref_cost)
 {
     int it[4];
     subpel_iters(env.subme, it);

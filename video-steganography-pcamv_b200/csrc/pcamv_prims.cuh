@@ -18,12 +18,19 @@
   #include <stdlib.h>
   #define PCAMV_DEV static inline
   #define PCAMV_MEM inline
+  #define PCAMV_FN static
+  #define PCAMV_MEMFN inline
   #define PCAMV_NGRP 1
   #define PCAMV_LPG  1
 #else
   #include <cuda_runtime.h>
   #define PCAMV_DEV __device__ __forceinline__
   #define PCAMV_MEM __device__ __forceinline__
+  // out-of-line device functions: the search code is far larger than the instruction cache when everything
+  // is inlined (first profile: 678 KB of SASS, warps stalled on instruction fetch), so the block-cost
+  // evaluators and the pattern walkers exist exactly once.
+  #define PCAMV_FN __device__ __noinline__
+  #define PCAMV_MEMFN __device__ __noinline__
   #define PCAMV_NGRP 4
   #define PCAMV_LPG  8
 #endif

@@ -218,6 +218,44 @@ void pcamv_hook_slice_begin( x264_t *h )
             }
         }
     }
+    if( g_pslice )
+    {
+        /* 'SLCX': what the P-slice analysis reads besides pixels: int32 cur_poc, n_ref, ref_poc[16], col_n_ref,
+         * col_inv_ref_poc[16], n_mb; then the co-located frame's (fref0[0]) int8 ref[4*n_mb] and int16 mv[16*n_mb][2]
+         * (temporal MV candidates, common/macroblock.c:444-467); then 'QNT0' once per QP with the quantiser tables. */
+        x264_frame_t *l0 = h->fref0[0];
+        int n_mb = h->mb.i_mb_count, i;
+        int32_t hd[36];
+        memset( hd, 0, sizeof(hd) );
+        hd[0] = h->fdec->i_poc; hd[1] = h->i_ref0;
+        for( i = 0; i < h->i_ref0 && i < 16; i++ ) hd[2+i] = h->fref0[i]->i_poc;
+        hd[18] = l0->i_ref[0];
+        for( i = 0; i < 16; i++ ) hd[19+i] = l0->inv_ref_poc[i];
+        hd[35] = n_mb;
+        rec_begin( "SLCX", (uint32_t)(sizeof(hd) + 4*n_mb + 64*n_mb) );
+        fwrite( hd, 1, sizeof(hd), g_dump );
+        fwrite( l0->ref[0], 1, 4*n_mb, g_dump );
+        fwrite( l0->mv[0], 1, 64*n_mb, g_dump );
+        {
+            static int done[52];
+            int qp = h->sh.i_qp, qpc = h->chroma_qp_table[qp];
+            if( !done[qp] )
+            {
+                /* 'QNT0': int32 qp, chroma_qp, lambda2[chroma_qp]; uint16 mf_y[16], bias_y[16], mf_c[16], bias_c[16];
+                 * int32 dequant_y[6][16], dequant_c[6][16]  (CQM_4PY / CQM_4PC) */
+                int32_t q[3] = { qp, qpc, x264_lambda2_tab[qpc] };
+                done[qp] = 1;
+                rec_begin( "QNT0", sizeof(q) + 4*32 + 2*96*4 );
+                fwrite( q, 1, sizeof(q), g_dump );
+                fwrite( h->quant4_mf[CQM_4PY][qp], 2, 16, g_dump );
+                fwrite( h->quant4_bias[CQM_4PY][qp], 2, 16, g_dump );
+                fwrite( h->quant4_mf[CQM_4PC][qpc], 2, 16, g_dump );
+                fwrite( h->quant4_bias[CQM_4PC][qpc], 2, 16, g_dump );
+                fwrite( h->dequant4_mf[CQM_4PY], 4, 96, g_dump );
+                fwrite( h->dequant4_mf[CQM_4PC], 4, 96, g_dump );
+            }
+        }
+    }
 }
 
 /* ---- slice end: final per-MB decisions as stored in the frame arrays -------------------------- */

@@ -1,0 +1,828 @@
+// pcamv_frame.cuh — per-macroblock P-slice analysis: neighbour cache, MV prediction, P_SKIP probe,
+// partition search order + mode decision, and the PCAMV candidate-MV cost table.
+//
+// Behavioural contract (bit-exact), reference file:line —
+//   neighbour load            common/macroblock.c:914-1224 (x264_macroblock_cache_load, P part)
+//   MV prediction             common/macroblock.c:28-163 (x264_mb_predict_mv, _16x16, _pskip)
+//   extra 16x16 candidates    common/macroblock.c:388-470 (x264_mb_predict_mv_ref16x16)
+//   MV limits                 encoder/analyse.c:271-318
+//   P_SKIP probe              encoder/macroblock.c:809-895 (x264_macroblock_probe_skip)
+//   search order / decision   encoder/analyse.c:1122-1205 (p16x16), :1371-1426 (p8x8), :1428-1533 (p16x8/p8x16),
+//                             :2613-2810 (x264_macroblock_analyse, non-RD P path), :2658-2676 (pass-2 overrides)
+//   MB reconstruction         encoder/macroblock.c:605-755 (inter luma), :277-372 (chroma), common/dct.c:122-262,364,
+//                             common/quant.c:33-75,203-252, common/macroblock.c:483-508,630-650 (x264_mb_mc)
+//   cost table                encoder/analyse.c:2364-2550 (MV_SATD_FDEC_IH, x264_ih_get_mv_cost), :3518-3689
+// Every x264_me_search_ref / x264_me_refine_qpel / x264_ih_get_mv_cost result is appended to a per-MB
+// log in call order; the host encoder replays that log instead of searching.
+#pragma once
+#include "pcamv_me.cuh"
+
+namespace pcamv {
+
+enum { MB_P_L0 = 4, MB_P_8x8 = 5, MB_P_SKIP = 6 };
+enum { PART_8x8 = 13, PART_16x8 = 14, PART_8x16 = 15, PART_16x16 = 16 };
+enum { LOG_SEARCH = 0, LOG_REFINE = 1, LOG_IHCOST = 2 };
+#define PCAMV_LOG_MAX 48
+
+struct LogEntry              // 16 bytes
+{
+    int8_t kind, i_pixel, i_ref, pad;
+    int16_t mv[2];           // search/refine: resulting mv; ih-cost: chosen delta (m_x, m_y)
+    int32_t cost;            // search/refine: m->cost; ih-cost: cost_opt
+    int32_t cost_mv;         // search/refine: m->cost_mv (thresh_out in the upper use is not needed by the host)
+};
+
+struct ForcedMb              // pass-2 input per MB: the pass-1 decision with the STC flips applied (host glue)
+{
+    int8_t type, used, partition, pad;
+    int8_t ref[4];           // per 8x8 block
+    uint32_t mv[16];         // packed (x & 0xffff) | (y << 16), block_idx order
+};
+
+struct PartInfo { int16_t mv[2]; int16_t mvp[2]; int8_t ref, i_pixel, xoff, yoff; };
+
+struct MbResult              // what the analysis leaves for the cost-table kernel and the tests
+{
+    int8_t type, partition, n_part, early_skip;
+    int8_t ref[4];
+    uint32_t mv[16];         // final cache MVs, block_idx order
+    PartInfo part[4];        // partitions of the final mode that carry an MV
+    int32_t n_log;
+    int16_t pskip_mv[2];
+};
+
+struct FrameArrays           // per-frame motion state in HBM (h->mb.type / ref / mv / mvr of the reference)
+{
+    int8_t *type;            // [mb_h * mb_w]
+    int8_t *ref8;            // [2*mb_h][2*mb_w]
+    uint32_t *mv4;           // [4*mb_h][4*mb_w] packed
+    uint32_t *mvr;           // [max_refs][mb_h*mb_w] packed: 16x16 search result per reference
+};
+
+struct FrameParams
+{
+    int pass;                // 0 = no embedding, 1 = pre-encode, 2 = final encode (decisions forced from pass 1)
+    int n_ref;
+    int ref_slot[PCAMV_MAX_REFS];
+    int ref_poc[PCAMV_MAX_REFS];
+    int cur_poc;
+    int col_n_ref;           // fref0[0]->i_ref[0]; > 0 enables the temporal candidates
+    int col_inv_ref_poc[PCAMV_MAX_REFS];
+    const int8_t *col_ref8;
+    const uint32_t *col_mv4;
+    const ForcedMb *forced;  // pass 2 only
+    uint32_t stale_mv[16];   // what the MV cache held before MB 0 of this pass (quirk q2)
+    FrameArrays cur;
+    LogEntry *log;           // [n_mb][PCAMV_LOG_MAX]
+    MbResult *results;       // [n_mb]
+    int *row_progress;       // [mb_h] wavefront counters
+};
+
+// team-shared scratch of one macroblock
+struct MbWork
+{
+    int8_t ref[48];          // scan8-indexed neighbour cache, list 0
+    uint32_t mv[48];
+    uint8_t fenc_y[256], fenc_u[64], fenc_v[64];
+    uint8_t pred_y[256], pred_u[64], pred_v[64];     // MC / reconstruction staging
+    int32_t scratch[32];
+};
+
+PCAMV_DEV int scan8(int idx)
+{
+    const int x = (idx & 1) | ((idx >> 1) & 2);
+    const int y = ((idx >> 1) & 1) | ((idx >> 2) & 2);
+    return 4 + x + 8 * (1 + y);
+}
+PCAMV_DEV uint32_t pack_mv(int x, int y) { return ((uint32_t)x & 0xffffu) | ((uint32_t)y << 16); }
+PCAMV_DEV int mv_x(uint32_t p) { return (int)(int16_t)(p & 0xffffu); }
+PCAMV_DEV int mv_y(uint32_t p) { return (int)(int16_t)(p >> 16); }
+
+// everything the per-MB code needs, by reference
+struct MbCtx
+{
+    const DevFrameCtx &fc;
+    const FrameParams &fp;
+    MbWork &w;
+    int mb_x, mb_y, mb_xy;
+    int type_left, type_top, type_topleft, type_topright;
+    int partition;                        // h->mb.i_partition as seen by x264_mb_predict_mv
+    int mv_min[2], mv_max[2];             // full-range qpel limits (MC clipping)
+    MeEnv env;
+    int n_log;
+    int pskip_mv[2];
+    PCAMV_MEM MbCtx(const DevFrameCtx &f, const FrameParams &p, MbWork &wk) : fc(f), fp(p), w(wk) {}
+};
+
+PCAMV_DEV void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int mvy, int cost, int cost_mv)
+{
+    if (c.n_log < PCAMV_LOG_MAX && team_lane() == 0)
+    {
+        LogEntry e;
+        e.kind = (int8_t)kind; e.i_pixel = (int8_t)i_pixel; e.i_ref = (int8_t)i_ref; e.pad = 0;
+        e.mv[0] = (int16_t)mvx; e.mv[1] = (int16_t)mvy; e.cost = cost; e.cost_mv = cost_mv;
+        c.fp.log[(size_t)c.mb_xy * PCAMV_LOG_MAX + c.n_log] = e;
+    }
+    c.n_log++;
+}
+
+// ---- neighbour cache -------------------------------------------------------------------------------
+PCAMV_DEV void cache_fill_rect(MbCtx &c, int x, int y, int wd, int ht, int ref, uint32_t mv, int set_ref, int set_mv)
+{
+    for (int j = 0; j < ht; j++)
+        for (int i = 0; i < wd; i++)
+        {
+            const int k = 12 + x + i + 8 * (y + j);
+            if (set_ref) c.w.ref[k] = (int8_t)ref;
+            if (set_mv) c.w.mv[k] = mv;
+        }
+}
+
+PCAMV_DEV void cache_load(MbCtx &c)
+{
+    const int mb_w = c.fc.mb_w, s8 = 2 * mb_w, s4 = 4 * mb_w;
+    const int mb_x = c.mb_x, mb_y = c.mb_y;
+    const FrameArrays &a = c.fp.cur;
+    const bool top = mb_y > 0, left = mb_x > 0, topright = top && mb_x < mb_w - 1, topleft = top && left;
+    const int top_xy = (mb_y - 1) * mb_w + mb_x;
+    const int top8 = (2 * (mb_y - 1) + 1) * s8 + 2 * mb_x, top4 = (4 * (mb_y - 1) + 3) * s4 + 4 * mb_x;
+    const int cur8 = 2 * mb_y * s8 + 2 * mb_x, cur4 = 4 * mb_y * s4 + 4 * mb_x;
+    c.type_top = top ? a.type[top_xy] : -1;
+    c.type_left = left ? a.type[c.mb_xy - 1] : -1;
+    c.type_topright = topright ? a.type[top_xy + 1] : -1;
+    c.type_topleft = topleft ? a.type[top_xy - 1] : -1;
+    // positions never written for the current MB keep "unavailable" (the reference memsets the cache to -2 once)
+    for (int k = 0; k < 48; k++) { c.w.ref[k] = -2; c.w.mv[k] = 0; }
+    if (topleft) { c.w.ref[3] = a.ref8[top8 - 1]; c.w.mv[3] = a.mv4[top4 - 1]; }
+    if (top)
+    {
+        c.w.ref[4] = c.w.ref[5] = a.ref8[top8]; c.w.ref[6] = c.w.ref[7] = a.ref8[top8 + 1];
+        for (int k = 0; k < 4; k++) c.w.mv[4 + k] = a.mv4[top4 + k];
+    }
+    if (topright) { c.w.ref[8] = a.ref8[top8 + 2]; c.w.mv[8] = a.mv4[top4 + 4]; }
+    if (left)
+    {
+        c.w.ref[11] = c.w.ref[19] = a.ref8[cur8 - 1];
+        c.w.ref[27] = c.w.ref[35] = a.ref8[cur8 - 1 + s8];
+        for (int k = 0; k < 4; k++) c.w.mv[11 + 8 * k] = a.mv4[cur4 - 1 + k * s4];
+    }
+}
+
+PCAMV_DEV uint32_t median_mv(uint32_t a, uint32_t b, uint32_t cc)
+{
+    return pack_mv(median3(mv_x(a), mv_x(b), mv_x(cc)), median3(mv_y(a), mv_y(b), mv_y(cc)));
+}
+
+PCAMV_DEV uint32_t predict_from(int i_ref, int refa, uint32_t mva, int refb, uint32_t mvb, int refc, uint32_t mvc)
+{
+    const int count = (refa == i_ref) + (refb == i_ref) + (refc == i_ref);
+    if (count > 1) return median_mv(mva, mvb, mvc);
+    if (count == 1) return refa == i_ref ? mva : refb == i_ref ? mvb : mvc;
+    if (refb == -2 && refc == -2 && refa != -2) return mva;
+    return median_mv(mva, mvb, mvc);
+}
+
+PCAMV_DEV uint32_t predict_mv_16x16(const MbCtx &c, int i_ref)
+{
+    int refc = c.w.ref[8]; uint32_t mvc = c.w.mv[8];
+    if (refc == -2) { refc = c.w.ref[3]; mvc = c.w.mv[3]; }
+    return predict_from(i_ref, c.w.ref[11], c.w.mv[11], c.w.ref[4], c.w.mv[4], refc, mvc);
+}
+
+PCAMV_DEV uint32_t predict_mv(const MbCtx &c, int idx, int width)
+{
+    const int i8 = scan8(idx);
+    const int i_ref = c.w.ref[i8];
+    const int refa = c.w.ref[i8 - 1], refb = c.w.ref[i8 - 8];
+    const uint32_t mva = c.w.mv[i8 - 1], mvb = c.w.mv[i8 - 8];
+    int refc = c.w.ref[i8 - 8 + width]; uint32_t mvc = c.w.mv[i8 - 8 + width];
+    if ((idx & 3) == 3 || (width == 2 && (idx & 3) == 2) || refc == -2)
+    {
+        refc = c.w.ref[i8 - 8 - 1]; mvc = c.w.mv[i8 - 8 - 1];
+    }
+    if (c.partition == PART_16x8)
+    {
+        if (idx == 0 && refb == i_ref) return mvb;
+        if (idx != 0 && refa == i_ref) return mva;
+    }
+    else if (c.partition == PART_8x16)
+    {
+        if (idx == 0 && refa == i_ref) return mva;
+        if (idx != 0 && refc == i_ref) return mvc;
+    }
+    return predict_from(i_ref, refa, mva, refb, mvb, refc, mvc);
+}
+
+PCAMV_DEV uint32_t predict_mv_pskip(const MbCtx &c)
+{
+    const int refa = c.w.ref[11], refb = c.w.ref[4];
+    const uint32_t mva = c.w.mv[11], mvb = c.w.mv[4];
+    if (refa == -2 || refb == -2 || !(refa | (int)mva) || !(refb | (int)mvb))
+        return 0;
+    return predict_mv_16x16(c, 0);
+}
+
+// candidate list of the 16x16 search: neighbours' 16x16 search results + temporally scaled co-located MVs
+PCAMV_DEV int predict_mv_ref16x16(const MbCtx &c, int i_ref, int (*mvc)[2])
+{
+    const int mb_w = c.fc.mb_w, n_mb = mb_w * c.fc.mb_h;
+    const uint32_t *mvr = c.fp.cur.mvr + (size_t)i_ref * n_mb;
+    const int8_t *type = c.fp.cur.type;
+    int n = 0;
+#define PCAMV_SET(p) { const uint32_t v_ = (p); mvc[n][0] = mv_x(v_); mvc[n][1] = mv_y(v_); n++; }
+    if (c.mb_x > 0 && type[c.mb_xy - 1] != MB_P_SKIP) PCAMV_SET(mvr[c.mb_xy - 1]);
+    if (c.mb_y > 0)
+    {
+        const int t = c.mb_xy - mb_w;
+        if (type[t] != MB_P_SKIP) PCAMV_SET(mvr[t]);
+        if (c.mb_x > 0 && type[t - 1] != MB_P_SKIP) PCAMV_SET(mvr[t - 1]);
+        if (c.mb_x < mb_w - 1 && type[t + 1] != MB_P_SKIP) PCAMV_SET(mvr[t + 1]);
+    }
+#undef PCAMV_SET
+    if (c.fp.col_n_ref > 0)
+    {
+        const int s8 = 2 * mb_w, s4 = 4 * mb_w;
+        const int cur8 = 2 * c.mb_y * s8 + 2 * c.mb_x, cur4 = 4 * c.mb_y * s4 + 4 * c.mb_x;
+        for (int k = 0; k < 3; k++)
+        {
+            const int dx = k == 1, dy = k == 2;
+            if (k == 1 && !(c.mb_x < mb_w - 1)) continue;
+            if (k == 2 && !(c.mb_y < c.fc.mb_h - 1)) continue;
+            const int ref_col = c.fp.col_ref8[cur8 + dx * 2 + dy * 2 * s8];
+            if (ref_col >= 0)
+            {
+                const int scale = (c.fp.cur_poc - c.fp.ref_poc[i_ref]) * c.fp.col_inv_ref_poc[ref_col];
+                const uint32_t m = c.fp.col_mv4[cur4 + dx * 4 + dy * 4 * s4];
+                mvc[n][0] = (int16_t)((mv_x(m) * scale + 128) >> 8);
+                mvc[n][1] = (int16_t)((mv_y(m) * scale + 128) >> 8);
+                n++;
+            }
+        }
+    }
+    return n;
+}
+
+// ---- MV limits (reference encoder/analyse.c:271-318; single thread, progressive) -------------------
+PCAMV_DEV void init_limits(MbCtx &c)
+{
+    const int fmv = 4 * c.fc.mv_range;
+    c.mv_min[0] = 4 * (-16 * c.mb_x - 24);
+    c.mv_max[0] = 4 * (16 * (c.fc.mb_w - c.mb_x - 1) + 24);
+    c.mv_min[1] = 4 * (-16 * c.mb_y - 24);
+    c.mv_max[1] = 4 * (16 * (c.fc.mb_h - c.mb_y - 1) + 24);
+    c.env.mv_min_spel[0] = clip3(c.mv_min[0], -fmv, fmv - 1);
+    c.env.mv_max_spel[0] = clip3(c.mv_max[0], -fmv, fmv - 1);
+    c.env.mv_min_spel[1] = clip3(c.mv_min[1], imax(4 * (-512 + 8), -fmv), fmv);
+    c.env.mv_max_spel[1] = imin(clip3(c.mv_max[1], -fmv, fmv - 1), fmv * 4);
+    for (int k = 0; k < 2; k++)
+    {
+        c.env.mv_min_fpel[k] = (c.env.mv_min_spel[k] >> 2) + 5;
+        c.env.mv_max_fpel[k] = (c.env.mv_max_spel[k] >> 2) - 5;
+    }
+}
+
+// ---- 4x4 transform / quantisation (one 4x4 block per lane) -----------------------------------------
+// d[] = fenc - pred residual in raster order (d[4*y+x]); out = coefficients in the reference's dct[i][j] layout
+PCAMV_DEV void dct4x4(const int d[16], int out[16])
+{
+    int tmp[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int s03 = d[4 * i] + d[4 * i + 3], s12 = d[4 * i + 1] + d[4 * i + 2];
+        const int d03 = d[4 * i] - d[4 * i + 3], d12 = d[4 * i + 1] - d[4 * i + 2];
+        tmp[0 * 4 + i] = s03 + s12; tmp[1 * 4 + i] = 2 * d03 + d12; tmp[2 * 4 + i] = s03 - s12; tmp[3 * 4 + i] = d03 - 2 * d12;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int s03 = tmp[4 * i] + tmp[4 * i + 3], s12 = tmp[4 * i + 1] + tmp[4 * i + 2];
+        const int d03 = tmp[4 * i] - tmp[4 * i + 3], d12 = tmp[4 * i + 1] - tmp[4 * i + 2];
+        out[4 * i] = (int16_t)(s03 + s12); out[4 * i + 1] = (int16_t)(2 * d03 + d12);
+        out[4 * i + 2] = (int16_t)(s03 - s12); out[4 * i + 3] = (int16_t)(d03 - 2 * d12);
+    }
+}
+// in-place quantisation with dead-zone bias; returns nonzero flag
+PCAMV_DEV int quant4x4(int coef[16], const uint16_t *mf, const uint16_t *bias)
+{
+    int nz = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+    {
+        const int v = coef[i];
+        const int q = v > 0 ? ((bias[i] + v) * mf[i]) >> 16 : -(((bias[i] - v) * mf[i]) >> 16);
+        coef[i] = (int16_t)q;
+        nz |= q;
+    }
+    return nz != 0;
+}
+PCAMV_DEV int quant_one(int v, int mf, int bias)
+{
+    return (int16_t)(v > 0 ? ((bias + v) * mf) >> 16 : -(((bias - v) * mf) >> 16));
+}
+// decimation score of a quantised 4x4 block; first = 0 (all 16 coefficients) or 1 (AC only)
+PCAMV_DEV int decimate_score(const int coef[16], int first)
+{
+    // coefficient i of the frame zigzag scan lives at dct[x][y] (flattened 4*x+y) of these positions
+    const int zz[16] = { 0, 4, 1, 2, 5, 8, 12, 9, 6, 3, 7, 10, 13, 14, 11, 15 };
+    const int tab[16] = { 3, 2, 2, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    int idx = 15;
+    while (idx >= first && coef[zz[idx]] == 0) idx--;
+    int score = 0;
+    while (idx >= first)
+    {
+        const int v = coef[zz[idx--]];
+        if ((unsigned)(v + 1) > 2) return 9;
+        int run = 0;
+        while (idx >= first && coef[zz[idx]] == 0) { idx--; run++; }
+        score += tab[run];
+    }
+    return score;
+}
+PCAMV_DEV void dequant4x4(int coef[16], const int32_t *dequant_mf, int qp)
+{
+    const int32_t *dm = dequant_mf + (qp % 6) * 16;
+    const int qbits = qp / 6 - 4;
+    if (qbits >= 0)
+    {
+#pragma unroll
+        for (int i = 0; i < 16; i++) coef[i] = (int16_t)((coef[i] * dm[i]) << qbits);
+    }
+    else
+    {
+        const int f = 1 << (-qbits - 1);
+#pragma unroll
+        for (int i = 0; i < 16; i++) coef[i] = (int16_t)((coef[i] * dm[i] + f) >> (-qbits));
+    }
+}
+// residual block r[4*y+x] to add to the prediction
+PCAMV_DEV void idct4x4(const int coef[16], int r[16])
+{
+    int tmp[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int s02 = coef[0 * 4 + i] + coef[2 * 4 + i], d02 = coef[0 * 4 + i] - coef[2 * 4 + i];
+        const int s13 = coef[1 * 4 + i] + (coef[3 * 4 + i] >> 1), d13 = (coef[1 * 4 + i] >> 1) - coef[3 * 4 + i];
+        tmp[4 * i] = (int16_t)(s02 + s13); tmp[4 * i + 1] = (int16_t)(d02 + d13);
+        tmp[4 * i + 2] = (int16_t)(d02 - d13); tmp[4 * i + 3] = (int16_t)(s02 - s13);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int s02 = tmp[0 * 4 + i] + tmp[2 * 4 + i], d02 = tmp[0 * 4 + i] - tmp[2 * 4 + i];
+        const int s13 = tmp[1 * 4 + i] + (tmp[3 * 4 + i] >> 1), d13 = (tmp[1 * 4 + i] >> 1) - tmp[3 * 4 + i];
+        r[0 * 4 + i] = (int16_t)((s02 + s13 + 32) >> 6); r[1 * 4 + i] = (int16_t)((d02 + d13 + 32) >> 6);
+        r[2 * 4 + i] = (int16_t)((d02 - d13 + 32) >> 6); r[3 * 4 + i] = (int16_t)((s02 - s13 + 32) >> 6);
+    }
+}
+
+PCAMV_DEV void load_residual(const uint8_t *fenc, int fs, const uint8_t *pred, int ps, int d[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+    {
+        const uint32_t f = ld4a(fenc + y * fs), p = ld4a(pred + y * ps);
+#pragma unroll
+        for (int x = 0; x < 4; x++) d[4 * y + x] = px(f, x) - px(p, x);
+    }
+}
+PCAMV_DEV void add_residual(uint8_t *pred, int ps, const int r[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+    {
+        const uint32_t p = ld4a(pred + y * ps);
+        uint32_t o = 0;
+#pragma unroll
+        for (int x = 0; x < 4; x++) o |= (uint32_t)clip_u8(px(p, x) + r[4 * y + x]) << (8 * x);
+#if defined(PCAMV_EMU)
+        memcpy(pred + y * ps, &o, 4);
+#else
+        *(uint32_t *)(pred + y * ps) = o;
+#endif
+    }
+}
+PCAMV_DEV void st4a(uint8_t *p, uint32_t v)
+{
+#if defined(PCAMV_EMU)
+    memcpy(p, &v, 4);
+#else
+    *(uint32_t *)p = v;
+#endif
+}
+
+PCAMV_DEV int team_any(int v)
+{
+#if defined(PCAMV_EMU)
+    return v != 0;
+#else
+    return __any_sync(0xffffffffu, v != 0);
+#endif
+}
+// generic team work split: on the GPU lane l does item l; in emulation the single lane loops over all items
+#if defined(PCAMV_EMU)
+  #define PCAMV_FOR_ITEMS(it, n) for (int it = 0; it < (n); it++)
+#else
+  #define PCAMV_FOR_ITEMS(it, n) for (int it = team_lane(); it < (n); it += 32)
+#endif
+
+// ---- motion compensation of a rectangle into the staging buffers -------------------------------------
+// luma w x h at block-relative (x0,y0) with quarter-pel MV (already clipped); chroma analogously.
+PCAMV_FN void mc_rect(MbCtx &c, int ref_slot, int x0, int y0, int wd, int ht, int qmx, int qmy)
+{
+    const DevRef &rf = c.fc.ref[ref_slot];
+    MeBlock b;
+    b.stride = c.fc.stride_y; b.stride_c = c.fc.stride_c;
+    const ptrdiff_t off = (ptrdiff_t)(16 * c.mb_y + y0) * b.stride + 16 * c.mb_x + x0;
+    for (int k = 0; k < 4; k++) b.ref[k] = rf.y[k] + off;
+    const uint8_t *s1, *s2;
+    qpel_sources(b, qmx, qmy, s1, s2);
+    const int w4 = wd >> 2;
+    PCAMV_FOR_ITEMS(it, w4 * ht)
+    {
+        const int y = it / w4, x = (it - y * w4) << 2;
+        st4a(c.w.pred_y + (y0 + y) * 16 + x0 + x, pred4(s1, s2, b.stride, x, y));
+    }
+    const int cw4 = wd >> 3, chh = ht >> 1;      // chroma words per row / rows
+    const ptrdiff_t offc = (ptrdiff_t)(8 * c.mb_y + (y0 >> 1)) * b.stride_c + 8 * c.mb_x + (x0 >> 1);
+    PCAMV_FOR_ITEMS(it, 2 * cw4 * chh)
+    {
+        const int pl = it / (cw4 * chh), r = it - pl * cw4 * chh;
+        const int y = r / cw4, x = (r - y * cw4) << 2;
+        const uint8_t *src = (pl ? rf.v : rf.u) + offc;
+        uint8_t *dst = (pl ? c.w.pred_v : c.w.pred_u) + ((y0 >> 1) + y) * 8 + (x0 >> 1) + x;
+        st4a(dst, chroma4(src, b.stride_c, qmx, qmy, x, y));
+    }
+    team_sync();
+}
+
+// ---- P_SKIP probe -----------------------------------------------------------------------------------------
+PCAMV_FN int probe_pskip(MbCtx &c)
+{
+    const int mvx = clip3(c.pskip_mv[0], c.mv_min[0], c.mv_max[0]);
+    const int mvy = clip3(c.pskip_mv[1], c.mv_min[1], c.mv_max[1]);
+    mc_rect(c, c.fp.ref_slot[0], 0, 0, 16, 16, mvx, mvy);
+    const DevTables &t = c.fc.tab;
+    int fail = 0;
+    // luma: 16 blocks, total decimate score must stay below 6
+    int score = 0;
+    PCAMV_FOR_ITEMS(blk, 16)
+    {
+        const int bx = (blk & 1) | ((blk >> 1) & 2), by = ((blk >> 1) & 1) | ((blk >> 2) & 2);
+        int d[16], co[16];
+        load_residual(c.w.fenc_y + 64 * by + 4 * bx, 16, c.w.pred_y + 64 * by + 4 * bx, 16, d);
+        dct4x4(d, co);
+        if (quant4x4(co, t.quant4_mf[0], t.quant4_bias[0]))
+            score += decimate_score(co, 0);
+    }
+    score = team_sum(score);
+    if (score >= 6) fail = 1;
+    // chroma: SSD gate, then DC must quantise to zero and the AC decimate score must stay below 7, per plane
+    const int thresh = (t.lambda2_chroma + 32) >> 6;
+    for (int pl = 0; pl < 2 && !fail; pl++)
+    {
+        const uint8_t *fe = pl ? c.w.fenc_v : c.w.fenc_u, *pr = pl ? c.w.pred_v : c.w.pred_u;
+        int ssd = 0;
+        PCAMV_FOR_ITEMS(it, 16)
+        {
+            const uint32_t f = ld4a(fe + 4 * it), p = ld4a(pr + 4 * it);
+            for (int k = 0; k < 4; k++) { const int dd = px(f, k) - px(p, k); ssd += dd * dd; }
+        }
+        ssd = team_sum(ssd);
+        if (ssd < thresh) continue;
+        int dcv = 0, sc = 0;
+        int dcs[4] = { 0, 0, 0, 0 };
+        PCAMV_FOR_ITEMS(blk, 4)
+        {
+            int d[16], co[16];
+            load_residual(fe + 32 * (blk >> 1) + 4 * (blk & 1), 8, pr + 32 * (blk >> 1) + 4 * (blk & 1), 8, d);
+            dct4x4(d, co);
+            dcv = co[0];
+            dcs[blk] = co[0];
+            co[0] = 0;
+            if (quant4x4(co, t.quant4_mf[1], t.quant4_bias[1]))
+                sc += decimate_score(co, 1);
+        }
+#if !defined(PCAMV_EMU)
+        for (int k = 0; k < 4; k++) dcs[k] = lane_bcast(dcv, k);     // lane k transformed block k
+#endif
+        (void)dcv;
+        const int d0 = dcs[0] + dcs[1], d1 = dcs[2] + dcs[3], d2 = dcs[0] - dcs[1], d3 = dcs[2] - dcs[3];
+        const int mf = t.quant4_mf[1][0] >> 1, bias = t.quant4_bias[1][0] << 1;
+        if (quant_one((int16_t)(d0 + d1), mf, bias) | quant_one((int16_t)(d2 + d3), mf, bias) |
+            quant_one((int16_t)(d0 - d1), mf, bias) | quant_one((int16_t)(d2 - d3), mf, bias))
+        { fail = 1; break; }
+        sc = team_sum(sc);
+        if (sc >= 7) { fail = 1; break; }
+    }
+    return !fail;
+}
+
+// =======================================================================================================
+// Search drivers
+// =======================================================================================================
+struct MeSlot            // the fields of x264_me_t that survive a search (per partition)
+{
+    MeResult r;
+    int mvp[2];
+    int i_ref, i_ref_cost, i_pixel, xoff, yoff;
+};
+
+PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, int xoff, int yoff)
+{
+    const DevRef &rf = c.fc.ref[c.fp.ref_slot[i_ref]];
+    b.i_pixel = i_pixel; b.bw = pix_w(i_pixel); b.bh = pix_h(i_pixel);
+    b.fenc = c.w.fenc_y + yoff * 16 + xoff;
+    b.fenc_u = c.w.fenc_u + (yoff >> 1) * 8 + (xoff >> 1);
+    b.fenc_v = c.w.fenc_v + (yoff >> 1) * 8 + (xoff >> 1);
+    b.stride = c.fc.stride_y; b.stride_c = c.fc.stride_c;
+    const ptrdiff_t off = (ptrdiff_t)(16 * c.mb_y + yoff) * b.stride + 16 * c.mb_x + xoff;
+    for (int k = 0; k < 4; k++) b.ref[k] = rf.y[k] + off;
+    const ptrdiff_t offc = (ptrdiff_t)(8 * c.mb_y + (yoff >> 1)) * b.stride_c + 8 * c.mb_x + (xoff >> 1);
+    b.ref_u = rf.u + offc; b.ref_v = rf.v + offc;
+    b.integral = nullptr;
+}
+
+PCAMV_DEV void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
+{
+    MeBlock b;
+    setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
+    s.mvp[0] = mv_x(mvp); s.mvp[1] = mv_y(mvp);
+    block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
+    s.r.mv[0] = s.r.mv[1] = 0; s.r.cost = 0; s.r.cost_mv = 0;
+    me_search_ref(c.env, b, mvc, i_mvc, thresh, s.r);
+    log_push(c, LOG_SEARCH, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
+}
+
+PCAMV_DEV void run_refine(MbCtx &c, MeSlot &s)
+{
+    MeBlock b;
+    setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
+    block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
+    me_refine_qpel(c.env, b, s.r, s.i_ref_cost);
+    log_push(c, LOG_REFINE, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
+}
+
+PCAMV_DEV int ref_cost(const MbCtx &c, int i_ref)
+{
+    return c.fc.tab.cost_ref[clip3(c.fp.n_ref - 1, 0, 2) * 33 + i_ref];
+}
+
+struct MbAnalysis
+{
+    MeSlot me16x16, me8x8[4], me16x8[2], me8x16[2];
+    int mvc[PCAMV_MAX_REFS][5][2];        // [ref][0] = 16x16 result, [ref][1..4] = 8x8 results
+    int cost8x8, cost16x8, cost8x16;
+};
+
+// 16x16 search over all references; returns 1 when the early P_SKIP termination fired
+PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_pskip)
+{
+    const int lambda = c.fc.tab.lambda;
+    int halfpel_thresh = 0x7fffffff;
+    int *p_thresh = c.fp.n_ref > 1 ? &halfpel_thresh : nullptr;
+    a.me16x16.r.cost = 0x7fffffff;
+    for (int i_ref = 0; i_ref < c.fp.n_ref; i_ref++)
+    {
+        MeSlot m;
+        const int rc = ref_cost(c, i_ref);
+        halfpel_thresh -= rc;
+        m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_16x16; m.xoff = 0; m.yoff = 0;
+        int mvc[PCAMV_MAX_MVC][2];
+        const uint32_t mvp = predict_mv_16x16(c, i_ref);
+        const int i_mvc = predict_mv_ref16x16(c, i_ref, mvc);
+        run_search(c, m, mvp, mvc, i_mvc, p_thresh);
+        if (allow_skip && i_ref == 0 && b_try_pskip && m.r.cost - m.r.cost_mv < 300 * lambda &&
+            iabs(m.r.mv[0] - c.pskip_mv[0]) + iabs(m.r.mv[1] - c.pskip_mv[1]) <= 1 && probe_pskip(c))
+            return 1;
+        m.r.cost += rc;
+        halfpel_thresh += rc;
+        if (m.r.cost < a.me16x16.r.cost)
+            a.me16x16 = m;
+        a.mvc[i_ref][0][0] = m.r.mv[0]; a.mvc[i_ref][0][1] = m.r.mv[1];
+        if (team_lane() == 0)
+            c.fp.cur.mvr[(size_t)i_ref * c.fc.mb_w * c.fc.mb_h + c.mb_xy] = pack_mv(m.r.mv[0], m.r.mv[1]);
+    }
+    cache_fill_rect(c, 0, 0, 4, 4, a.me16x16.i_ref, 0, 1, 0);
+    return 0;
+}
+
+PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
+{
+    const int i_ref = a.me16x16.i_ref;
+    const int rc = (c.fc.b_cabac || i_ref) ? ref_cost(c, i_ref) : 0;
+    int (*mvc)[2] = a.mvc[i_ref];
+    c.partition = PART_8x8;
+    int i_mvc = 1;
+    mvc[0][0] = a.me16x16.r.mv[0]; mvc[0][1] = a.me16x16.r.mv[1];
+    for (int i = 0; i < 4; i++)
+    {
+        MeSlot &m = a.me8x8[i];
+        const int x8 = i & 1, y8 = i >> 1;
+        m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_8x8; m.xoff = 8 * x8; m.yoff = 8 * y8;
+        run_search(c, m, predict_mv(c, 4 * i, 2), mvc, i_mvc, nullptr);
+        cache_fill_rect(c, 2 * x8, 2 * y8, 2, 2, 0, pack_mv(m.r.mv[0], m.r.mv[1]), 0, 1);
+        mvc[i_mvc][0] = m.r.mv[0]; mvc[i_mvc][1] = m.r.mv[1];
+        i_mvc++;
+        m.r.cost += rc;
+        m.r.cost += c.fc.tab.lambda * 1;          // sub-partition type cost of an unsplit 8x8
+    }
+    a.cost8x8 = a.me8x8[0].r.cost + a.me8x8[1].r.cost + a.me8x8[2].r.cost + a.me8x8[3].r.cost;
+    if (c.fc.b_cabac)
+        a.cost8x8 -= rc;
+}
+
+// 16x8 (dir = 0) or 8x16 (dir = 1)
+PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
+{
+    c.partition = dir ? PART_8x16 : PART_16x8;
+    int total = 0;
+    for (int i = 0; i < 2; i++)
+    {
+        MeSlot &best = dir ? a.me8x16[i] : a.me16x8[i];
+        const int r0 = dir ? a.me8x8[i].i_ref : a.me8x8[2 * i].i_ref;
+        const int r1 = dir ? a.me8x8[i + 2].i_ref : a.me8x8[2 * i + 1].i_ref;
+        const int nrefs = r0 == r1 ? 1 : 2;
+        best.r.cost = 0x7fffffff;
+        for (int j = 0; j < nrefs; j++)
+        {
+            const int i_ref = j ? r1 : r0;
+            MeSlot m;
+            m.i_ref = i_ref; m.i_ref_cost = ref_cost(c, i_ref);
+            m.i_pixel = dir ? PIX_8x16 : PIX_16x8;
+            m.xoff = dir ? 8 * i : 0; m.yoff = dir ? 0 : 8 * i;
+            int mvc[3][2];
+            const int k1 = dir ? i + 1 : 2 * i + 1, k2 = dir ? i + 3 : 2 * i + 2;
+            mvc[0][0] = a.mvc[i_ref][0][0]; mvc[0][1] = a.mvc[i_ref][0][1];
+            mvc[1][0] = a.mvc[i_ref][k1][0]; mvc[1][1] = a.mvc[i_ref][k1][1];
+            mvc[2][0] = a.mvc[i_ref][k2][0]; mvc[2][1] = a.mvc[i_ref][k2][1];
+            if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, i_ref, 0, 1, 0);
+            else     cache_fill_rect(c, 0, 2 * i, 4, 2, i_ref, 0, 1, 0);
+            run_search(c, m, dir ? predict_mv(c, 4 * i, 2) : predict_mv(c, 8 * i, 4), mvc, 3, nullptr);
+            m.r.cost += m.i_ref_cost;
+            if (m.r.cost < best.r.cost)
+                best = m;
+        }
+        const uint32_t mv = pack_mv(best.r.mv[0], best.r.mv[1]);
+        if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, best.i_ref, mv, 1, 1);
+        else     cache_fill_rect(c, 0, 2 * i, 4, 2, best.i_ref, mv, 1, 1);
+        total += best.r.cost;
+    }
+    if (dir) a.cost8x16 = total; else a.cost16x8 = total;
+}
+
+// write the decided mode into the neighbour cache (x264_analyse_update_cache, P part)
+PCAMV_DEV void update_cache(MbCtx &c, const MbAnalysis &a, int type, int partition)
+{
+    if (type == MB_P_SKIP)
+    {
+        cache_fill_rect(c, 0, 0, 4, 4, 0, pack_mv(c.pskip_mv[0], c.pskip_mv[1]), 1, 1);
+        return;
+    }
+    if (partition == PART_16x16)
+        cache_fill_rect(c, 0, 0, 4, 4, a.me16x16.i_ref, pack_mv(a.me16x16.r.mv[0], a.me16x16.r.mv[1]), 1, 1);
+    else if (partition == PART_16x8)
+        for (int i = 0; i < 2; i++)
+            cache_fill_rect(c, 0, 2 * i, 4, 2, a.me16x8[i].i_ref, pack_mv(a.me16x8[i].r.mv[0], a.me16x8[i].r.mv[1]), 1, 1);
+    else if (partition == PART_8x16)
+        for (int i = 0; i < 2; i++)
+            cache_fill_rect(c, 2 * i, 0, 2, 4, a.me8x16[i].i_ref, pack_mv(a.me8x16[i].r.mv[0], a.me8x16[i].r.mv[1]), 1, 1);
+    else
+        for (int i = 0; i < 4; i++)
+            cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, a.me8x8[i].i_ref, pack_mv(a.me8x8[i].r.mv[0], a.me8x8[i].r.mv[1]), 1, 1);
+}
+
+// store the MB's final state to the frame arrays (x264_macroblock_cache_save, inter part) and the result record
+PCAMV_DEV void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition, int early_skip)
+{
+    const int mb_w = c.fc.mb_w, s8 = 2 * mb_w, s4 = 4 * mb_w;
+    const int cur8 = 2 * c.mb_y * s8 + 2 * c.mb_x, cur4 = 4 * c.mb_y * s4 + 4 * c.mb_x;
+    if (team_lane() == 0)
+    {
+        const FrameArrays &fa = c.fp.cur;
+        fa.type[c.mb_xy] = (int8_t)type;
+        fa.ref8[cur8] = c.w.ref[12]; fa.ref8[cur8 + 1] = c.w.ref[14];
+        fa.ref8[cur8 + s8] = c.w.ref[28]; fa.ref8[cur8 + s8 + 1] = c.w.ref[30];
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++)
+                fa.mv4[cur4 + y * s4 + x] = c.w.mv[12 + x + 8 * y];
+        MbResult r;
+        r.type = (int8_t)type; r.partition = (int8_t)partition; r.early_skip = (int8_t)early_skip;
+        r.ref[0] = c.w.ref[12]; r.ref[1] = c.w.ref[14]; r.ref[2] = c.w.ref[28]; r.ref[3] = c.w.ref[30];
+        for (int i = 0; i < 16; i++) r.mv[i] = c.w.mv[scan8(i)];
+        r.n_part = 0;
+        if (type != MB_P_SKIP)
+        {
+            const int np = partition == PART_16x16 ? 1 : partition == PART_8x8 ? 4 : 2;
+            r.n_part = (int8_t)np;
+            for (int i = 0; i < np; i++)
+            {
+                const MeSlot &m = partition == PART_16x16 ? a.me16x16 : partition == PART_16x8 ? a.me16x8[i]
+                                : partition == PART_8x16 ? a.me8x16[i] : a.me8x8[i];
+                r.part[i].mv[0] = (int16_t)m.r.mv[0]; r.part[i].mv[1] = (int16_t)m.r.mv[1];
+                r.part[i].mvp[0] = (int16_t)m.mvp[0]; r.part[i].mvp[1] = (int16_t)m.mvp[1];
+                r.part[i].ref = (int8_t)m.i_ref; r.part[i].i_pixel = (int8_t)m.i_pixel;
+                r.part[i].xoff = (int8_t)m.xoff; r.part[i].yoff = (int8_t)m.yoff;
+            }
+        }
+        r.n_log = c.n_log;
+        r.pskip_mv[0] = (int16_t)c.pskip_mv[0]; r.pskip_mv[1] = (int16_t)c.pskip_mv[1];
+        c.fp.results[c.mb_xy] = r;
+    }
+}
+
+// One macroblock of a P slice.  `prev_mv` = the 16 cache MVs left behind by the previous MB in raster order
+// (needed only for the pass-2 "forced skip without cache update" quirk, analyse.c:2668-2676).
+PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
+{
+    const DevFrameCtx &fc = c.fc;
+    MbAnalysis a;
+    c.n_log = 0;
+    c.partition = PART_16x16;
+    cache_load(c);
+    const uint32_t ps = predict_mv_pskip(c);
+    c.pskip_mv[0] = mv_x(ps); c.pskip_mv[1] = mv_y(ps);
+    init_limits(c);
+    c.env.cost_mv = fc.tab.cost_mv;
+    c.env.me_method = fc.me_method; c.env.me_range = fc.me_range; c.env.subme = fc.subme;
+    c.env.chroma_me = fc.chroma_me && fc.subme >= 5;
+    c.env.mbcmp_satd = fc.subme > 1;
+
+    int b_try_pskip = 0, b_skip = 0;
+    if (fc.b_fast_pskip)
+    {
+        if (fc.subme >= 3) b_try_pskip = 1;
+        else if (c.type_left == MB_P_SKIP || c.type_top == MB_P_SKIP || c.type_topleft == MB_P_SKIP || c.type_topright == MB_P_SKIP)
+            b_skip = probe_pskip(c);
+    }
+    const ForcedMb *forced = c.fp.pass == 2 ? &c.fp.forced[c.mb_xy] : nullptr;
+    int type = MB_P_L0, partition = PART_16x16, early_skip = 0;
+    if (b_skip)
+    {
+        // (subme < 3 only) the reference takes this MB as P_SKIP before any search; pass 2 cannot override it
+        update_cache(c, a, MB_P_SKIP, PART_16x16);
+        finalize_mb(c, a, MB_P_SKIP, PART_16x16, 1);
+        return;
+    }
+    early_skip = analyse_p16x16(c, a, 1, b_try_pskip);
+    if (early_skip)
+    {
+        type = MB_P_SKIP;
+        update_cache(c, a, MB_P_SKIP, PART_16x16);
+    }
+    if (forced)
+    {
+        if (forced->type != MB_P_SKIP && type == MB_P_SKIP)
+            analyse_p16x16(c, a, 0, b_try_pskip);       // the reference re-runs the 16x16 search without the skip exit
+        type = forced->type;
+    }
+    if (type == MB_P_SKIP)
+    {
+        if (!early_skip)
+        {
+            // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
+            // and the refs are what the 16x16 search left (its best reference)
+            for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = prev_mv[i];
+        }
+        finalize_mb(c, a, MB_P_SKIP, PART_16x16, early_skip);
+        return;
+    }
+
+    const int flags = fc.analyse_inter;
+    const int psub16 = (flags & 0x10) != 0;
+    if (psub16)
+        analyse_p8x8(c, a);
+    int i_cost = a.me16x16.r.cost;
+    // (with X264_ANALYSE_PSUB8x8 the reference would go on to P_8x8 / sub-partitions here; pcamv_open rejects that flag)
+    if (psub16)
+    {
+        const int thresh16x8 = a.me8x8[1].r.cost_mv + a.me8x8[2].r.cost_mv;
+        if (a.cost8x8 < a.me16x16.r.cost + thresh16x8)
+        {
+            analyse_p16x8_8x16(c, a, 0);
+            if (a.cost16x8 < i_cost) { i_cost = a.cost16x8; partition = PART_16x8; }
+            analyse_p16x8_8x16(c, a, 1);
+            if (a.cost8x16 < i_cost) { i_cost = a.cost8x16; partition = PART_8x16; }
+        }
+    }
+    c.partition = partition;
+    if (partition == PART_16x16) run_refine(c, a.me16x16);
+    else if (partition == PART_16x8) { run_refine(c, a.me16x8[0]); run_refine(c, a.me16x8[1]); }
+    else { run_refine(c, a.me8x16[0]); run_refine(c, a.me8x16[1]); }
+
+    if (forced && forced->used)
+    {
+        // pass 2: type / partition / refs / MVs come from pass 1 with the embedding flips applied
+        type = forced->type; partition = forced->partition;
+        for (int i = 0; i < 4; i++)
+            cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
+        for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
+        // the analysis slots keep the searched values; neighbours only ever see the cache
+    }
+    else
+        update_cache(c, a, type, partition);
+    finalize_mb(c, a, type, partition, 0);
+}
+
+} // namespace pcamv

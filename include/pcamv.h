@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PCAMV_ABI_VERSION 1
+#define PCAMV_ABI_VERSION 2
 #define PCAMV_MAX_REFS 16
 #define PCAMV_MAX_MVC 10
 
@@ -150,6 +150,76 @@ int pcamv_me_search_batch(pcamv_ctx *ctx, const pcamv_me_call *calls, int n, pca
 int pcamv_me_batch_upload(pcamv_ctx *ctx, const pcamv_me_call *calls, int n);
 int pcamv_me_batch_run(pcamv_ctx *ctx, int iters, float *ms_per_launch);
 int pcamv_me_batch_download(pcamv_ctx *ctx, pcamv_me_result *results, int n);
+
+/* ---- frame seam: the P-slice body of x264_macroblock_analyse ------------------------------------------------ */
+#define PCAMV_LOG_MAX 48
+
+/* One entry of a macroblock's result log.  The analysis of a macroblock calls x264_me_search_ref,
+ * x264_me_refine_qpel and (pass 1) x264_ih_get_mv_cost in a data-dependent order (encoder/analyse.c:2646-2810,
+ * 3518-3689); the GPU appends one entry per call, in that order, and the host encoder replays them instead of
+ * searching. */
+enum { PCAMV_LOG_SEARCH = 0, PCAMV_LOG_REFINE = 1, PCAMV_LOG_IHCOST = 2 };
+typedef struct pcamv_log_entry
+{
+    int8_t kind, i_pixel, i_ref, pad;
+    int16_t mv[2];      /* search / refine: m->mv;  ih-cost: the chosen replacement delta (m_x, m_y) */
+    int32_t cost;       /* search / refine: m->cost;  ih-cost: cost_opt (the embedding cost) */
+    int32_t cost_mv;    /* search / refine: m->cost_mv */
+} pcamv_log_entry;
+
+/* Per-macroblock outcome of the analysis (what x264_macroblock_analyse leaves in h->mb for a P macroblock). */
+typedef struct pcamv_mb_out
+{
+    int8_t type, partition, n_part, early_skip;   /* PCAMV_P_*, PCAMV_D_*, MV-carrying partitions, early P_SKIP exit */
+    int8_t ref[4];                                /* reference index per 8x8 block */
+    int16_t mv[16][2];                            /* h->mb.cache.mv[0][x264_scan8[i]], block_idx order */
+    struct { int16_t mv[2]; int16_t mvp[2]; int8_t ref, i_pixel, xoff, yoff; } part[4];
+    int32_t n_log;                                /* entries used in this macroblock's log */
+    int16_t pskip_mv[2];
+} pcamv_mb_out;
+
+/* The fields of the reference's h->info.cache[mb] (common/common.h:585-603) that pass 2 reads, verbatim —
+ * including how analyse.c:3526-3632 fills them (ref[] raster, mv[] through the unsequenced idx++ copy). */
+typedef struct pcamv_pass1_mb
+{
+    int32_t type;            /* PCAMV_P_L0 / PCAMV_P_8x8 / PCAMV_P_SKIP */
+    int32_t partition;       /* PCAMV_D_16x8 / 8x16 / 16x16 */
+    uint8_t used;
+    uint8_t sub[4];
+    int8_t ref[16];
+    int16_t mv[16][2];
+    int16_t mv_stego[16][2];
+} pcamv_pass1_mb;
+
+typedef struct pcamv_frame_in
+{
+    int32_t pass;                       /* 0 = embedding off, 1 = pre-encode, 2 = final encode (info.firstTime == 0) */
+    int32_t n_ref;                      /* h->i_ref0 */
+    int32_t ref_slot[PCAMV_MAX_REFS];   /* slot of h->fref0[i] as uploaded with pcamv_put_ref */
+    int32_t ref_poc[PCAMV_MAX_REFS];    /* h->fref0[i]->i_poc */
+    int32_t cur_poc;                    /* h->fdec->i_poc */
+    int32_t col_n_ref;                  /* h->fref0[0]->i_ref[0]; <= 0 disables the temporal candidates */
+    int32_t col_inv_ref_poc[PCAMV_MAX_REFS];   /* h->fref0[0]->inv_ref_poc[] */
+    const int8_t *col_ref8;             /* h->fref0[0]->ref[0]: [2*mb_h][2*mb_w] */
+    const int16_t *col_mv4;             /* h->fref0[0]->mv[0]:  [4*mb_h][4*mb_w][2] */
+    const pcamv_pass1_mb *pass1;        /* pass 2: h->info.cache[0..n_mb) */
+    const int8_t *filp;                 /* pass 2: h->info.filp[0..n_filp) */
+    int32_t n_filp;
+    int32_t cost_table;                 /* pass 1: also build the candidate-MV cost table (emrate != 0) */
+    int16_t stale_mv[16][2];            /* h->mb.cache.mv[0][x264_scan8[i]] as left by the previous slice pass */
+} pcamv_frame_in;
+
+/* Analyse every macroblock of a P slice against the current fenc and the uploaded references.
+ * mbs: n_mb records; log: n_mb * PCAMV_LOG_MAX entries (may be NULL).  Replaces, per macroblock, the searches of
+ * x264_macroblock_analyse (encoder/encoder.c:1273 -> encoder/analyse.c:2555) for P slices with subme <= 5. */
+int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log);
+
+/* Benchmark / pipelining support: the three stages of pcamv_analyse_p separately.  _upload stages the frame
+ * inputs in HBM; _run launches the wavefront (+ cost table) `iters` times and returns the mean device time of one
+ * analysis in milliseconds (CUDA events on the context's stream); _download copies results back. */
+int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in);
+int pcamv_frame_run(pcamv_ctx *ctx, int iters, float *ms_per_frame);
+int pcamv_frame_download(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log);
 
 /* Measured integer-pipe issue peak of the device, in giga lane-operations/s: a microbenchmark of the
  * VABSDIFF4 / IADD3 / LOP3 mix the SAD and SATD loops consist of.  Roofline denominator for the search kernels. */

@@ -27,7 +27,7 @@ def test_host_mirror_lists_every_export(pcamv):
 
 
 def test_abi_version_and_record_layout(pcamv, cuda_lib):
-    assert cuda_lib.pcamv_abi_version() == 1
+    assert cuda_lib.pcamv_abi_version() == 2
     # sizes of the POD records as laid out by the C compiler (see include/pcamv.h)
     assert pcamv.host.ME_CALL_DTYPE.itemsize == 132
     assert pcamv.host.ME_RESULT_DTYPE.itemsize == 16
@@ -39,7 +39,7 @@ def test_open_fails_loudly_without_gpu(pcamv, cuda_lib):
     if torch.cuda.is_available():
         return
     cfg = pcamv.host.Cfg()
-    cfg.abi_version = 1
+    cfg.abi_version = 2
     cfg.width, cfg.height, cfg.max_refs = 176, 144, 1
     h = ctypes.c_void_p()
     assert cuda_lib.pcamv_open(ctypes.byref(h), ctypes.byref(cfg)) == -1
@@ -52,6 +52,6 @@ def test_open_rejects_bad_arguments(pcamv, cuda_lib):
     h = ctypes.c_void_p()
     assert cuda_lib.pcamv_open(ctypes.byref(h), ctypes.byref(cfg)) == -1
     assert b"ABI" in cuda_lib.pcamv_last_error(None)
-    cfg.abi_version = 1
+    cfg.abi_version = 2
     cfg.width, cfg.height, cfg.max_refs = 100, 100, 1       # not multiples of 16
     assert cuda_lib.pcamv_open(ctypes.byref(h), ctypes.byref(cfg)) == -1

@@ -1,0 +1,49 @@
+"""Frame-level device code (neighbour cache, MV prediction, P_SKIP probe, partition decision, pass-2 forcing,
+PCAMV cost table) checked on the CPU with a lane team of one (-DPCAMV_EMU) against the reference encoder's
+records: committed golden fixtures always, live runs of oracle/_ref/x264_dump when that binary is present."""
+import os
+import subprocess
+
+import pytest
+
+import refrun
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def checker(pcamv):
+    return pcamv.build.build_tool("emu_frame_check", os.path.join(ROOT, "tests", "emu", "emu_frame_check.cpp"))
+
+
+def run_checker(checker, dump):
+    p = subprocess.run([checker, dump], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = dict(kv.split("=") for kv in p.stdout.split())
+    assert out["bad_mb_logs"] == "0" and out["bad_decisions"] == "0" and out["bad_ih"] == "0", p.stdout
+    return {k: int(v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"])
+def test_golden_frames(checker, name, tmp_path):
+    n = run_checker(checker, refrun.golden_dump_path(name, str(tmp_path)))
+    assert n["passes"] >= 2 and n["calls"] > 1000 and n["ih"] > 100
+
+
+LIVE = [
+    ("--me hex --subme 5 --ref 1", "1:4", 32),
+    ("--me umh --subme 5 --ref 3", "3:5", 32),
+    ("--me hex --subme 4 --ref 2 --no-fast-pskip", "2:4", 32),
+    ("--me dia --subme 2 --ref 1 --qp 32", "1:4", 4),          # low noise: P_SKIP-heavy, exercises the pass-2 quirks
+    ("--me hex --subme 5 --ref 1 --no-cabac", "1:3", 16),
+]
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/x264_dump not built")
+@pytest.mark.parametrize("args,frames,noise", LIVE)
+def test_live_reference_frames(pcamv, checker, args, frames, noise, tmp_path):
+    clip = refrun.synth_clip(pcamv, 352, 288, 5, config=1, stream=5, noise16=noise, workdir=str(tmp_path))
+    dump = str(tmp_path / "d.bin")
+    refrun.run_ref(clip, 352, 288, ("--qp 26 --keyint 250 --emrate 0.2 " + args).split(), dump=dump, frames=frames)
+    n = run_checker(checker, dump)
+    assert n["passes"] >= 2 and n["calls"] > 5000

@@ -6,36 +6,13 @@
 #include <string.h>
 #include <string>
 #include <vector>
-#include "pcamv_device.h"
+#include "pcamv_ctx.h"
 
 using namespace pcamv;
 
 static thread_local std::string g_open_error;
 
-struct pcamv_ctx
-{
-    pcamv_cfg cfg;
-    DevFrameCtx fc;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
-    bool failed = false;
-    long long launches = 0;
-
-    // HBM
-    uint8_t *d_fenc = nullptr;                 // Y | U | V, strides = stride_y / stride_c
-    uint8_t *d_ref[PCAMV_SLOTS] = {};          // per slot: 4 luma planes | U | V (+slack)
-    uint16_t *d_integral[PCAMV_SLOTS] = {};
-    size_t luma_bytes = 0, chroma_bytes = 0, ref_bytes = 0;
-    int16_t *d_cost_mv = nullptr;              // 32769
-    uint8_t *d_tables = nullptr;               // cost_ref | quant mf/bias | dequant
-    // batch staging
-    pcamv_me_call *d_calls = nullptr; pcamv_me_result *d_results = nullptr; int batch_cap = 0, batch_n = 0;
-    pcamv_me_call *h_calls = nullptr; pcamv_me_result *h_results = nullptr;     // pinned
-    uint8_t *h_stage = nullptr; size_t h_stage_bytes = 0;                       // pinned frame staging
-};
-
-static int fail(pcamv_ctx *c, const char *what, cudaError_t e)
+int pcamv::ctx_fail(pcamv_ctx *c, const char *what, cudaError_t e)
 {
     char buf[512];
     snprintf(buf, sizeof(buf), "pcamv: %s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
@@ -43,6 +20,7 @@ static int fail(pcamv_ctx *c, const char *what, cudaError_t e)
     else g_open_error = buf;
     return -1;
 }
+static int fail(pcamv_ctx *c, const char *what, cudaError_t e) { return ctx_fail(c, what, e); }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, #call, e_); } while (0)
 #define GUARD() do { if (!ctx) return -1; if (ctx->failed) return -1; } while (0)
 
@@ -140,6 +118,10 @@ extern "C" void pcamv_close(pcamv_ctx *ctx)
     for (int s = 0; s < PCAMV_SLOTS; s++) { cudaFree(ctx->d_ref[s]); cudaFree(ctx->d_integral[s]); }
     cudaFree(ctx->d_cost_mv); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_calls); cudaFree(ctx->d_results);
+    cudaFree(ctx->fa.type); cudaFree(ctx->fa.ref8); cudaFree(ctx->fa.mv4); cudaFree(ctx->fa.mvr);
+    cudaFree(ctx->d_col_ref8); cudaFree(ctx->d_col_mv4); cudaFree(ctx->d_forced); cudaFree(ctx->d_log);
+    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress);
+    if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
     if (ctx->h_calls) cudaFreeHost(ctx->h_calls);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);

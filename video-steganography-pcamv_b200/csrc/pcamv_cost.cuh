@@ -11,10 +11,10 @@
 namespace pcamv {
 
 #if defined(PCAMV_EMU)
-  #define PCAMV_SLOTS 24
+  #define PCAMV_COEF_SLOTS 24
   #define PCAMV_SLOT(it) (it)
 #else
-  #define PCAMV_SLOTS 1
+  #define PCAMV_COEF_SLOTS 1
   #define PCAMV_SLOT(it) 0
 #endif
 
@@ -31,7 +31,7 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
         const int my = clip3(p == k_over ? omy : pi.mv[1], c.mv_min[1], c.mv_max[1]);
         mc_rect(c, c.fp.ref_slot[pi.ref], pi.xoff, pi.yoff, pix_w(pi.i_pixel), pix_h(pi.i_pixel), mx, my);
     }
-    int coef[PCAMV_SLOTS][16];
+    int coef[PCAMV_COEF_SLOTS][16];
     // scratch layout: [0..23] decimate score, bits: score | nz << 8 ; chroma DC terms in dcs
     int *sc = c.w.scratch;
     int16_t *dcs = (int16_t *)(c.w.scratch + 24);           // 8 x int16

@@ -1,0 +1,44 @@
+// pcamv_ctx.h — the context object behind the opaque pcamv_ctx handle (private to csrc/).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "pcamv_device.h"
+#include "pcamv_frame_types.h"
+
+struct pcamv_ctx
+{
+    pcamv_cfg cfg;
+    pcamv::DevFrameCtx fc;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    bool failed = false;
+    long long launches = 0;
+
+    // HBM
+    uint8_t *d_fenc = nullptr;                 // Y | U | V, strides = stride_y / stride_c
+    uint8_t *d_ref[PCAMV_SLOTS] = {};          // per slot: 4 luma planes | U | V (+slack)
+    uint16_t *d_integral[PCAMV_SLOTS] = {};
+    size_t luma_bytes = 0, chroma_bytes = 0, ref_bytes = 0;
+    int16_t *d_cost_mv = nullptr;              // 32769
+    uint8_t *d_tables = nullptr;               // cost_ref | quant mf/bias | dequant
+    // batch staging (stateless search seam)
+    pcamv_me_call *d_calls = nullptr; pcamv_me_result *d_results = nullptr; int batch_cap = 0, batch_n = 0;
+    pcamv_me_call *h_calls = nullptr; pcamv_me_result *h_results = nullptr;     // pinned
+    uint8_t *h_stage = nullptr; size_t h_stage_bytes = 0;                       // pinned frame staging
+
+    // frame-level analysis (pcamv_frame_api.cu): per-frame motion state and per-MB outputs, all in HBM
+    pcamv::FrameArrays fa = {};                // type / ref8 / mv4 / mvr of the frame being analysed
+    int8_t *d_col_ref8 = nullptr; uint32_t *d_col_mv4 = nullptr;      // co-located frame's ref / mv (temporal candidates)
+    pcamv::ForcedMb *d_forced = nullptr;       // pass-2 forced decisions
+    pcamv::LogEntry *d_log = nullptr;          // [n_mb][PCAMV_LOG_MAX]
+    pcamv::MbResult *d_mb_results = nullptr;   // [n_mb]
+    int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter
+    uint8_t *h_frame = nullptr; size_t h_frame_bytes = 0;             // pinned staging for frame inputs / outputs
+    pcamv::FrameParams fp = {};                // parameters of the last uploaded frame
+    bool frame_ready = false, frame_cost_table = false;
+};
+
+namespace pcamv {
+int ctx_fail(pcamv_ctx *c, const char *what, cudaError_t e);
+}

@@ -16,70 +16,13 @@
 // log in call order; the host encoder replays that log instead of searching.
 #pragma once
 #include "pcamv_me.cuh"
+#include "pcamv_device.h"
+#include "pcamv_frame_types.h"
 
 namespace pcamv {
 
-enum { MB_P_L0 = 4, MB_P_8x8 = 5, MB_P_SKIP = 6 };
-enum { PART_8x8 = 13, PART_16x8 = 14, PART_8x16 = 15, PART_16x16 = 16 };
-enum { LOG_SEARCH = 0, LOG_REFINE = 1, LOG_IHCOST = 2 };
-#define PCAMV_LOG_MAX 48
-
-struct LogEntry              // 16 bytes
-{
-    int8_t kind, i_pixel, i_ref, pad;
-    int16_t mv[2];           // search/refine: resulting mv; ih-cost: chosen delta (m_x, m_y)
-    int32_t cost;            // search/refine: m->cost; ih-cost: cost_opt
-    int32_t cost_mv;         // search/refine: m->cost_mv (thresh_out in the upper use is not needed by the host)
-};
-
-struct ForcedMb              // pass-2 input per MB: the pass-1 decision with the STC flips applied (host glue)
-{
-    int8_t type, used, partition, pad;
-    int8_t ref[4];           // per 8x8 block
-    uint32_t mv[16];         // packed (x & 0xffff) | (y << 16), block_idx order
-};
-
-struct PartInfo { int16_t mv[2]; int16_t mvp[2]; int8_t ref, i_pixel, xoff, yoff; };
-
-struct MbResult              // what the analysis leaves for the cost-table kernel and the tests
-{
-    int8_t type, partition, n_part, early_skip;
-    int8_t ref[4];
-    uint32_t mv[16];         // final cache MVs, block_idx order
-    PartInfo part[4];        // partitions of the final mode that carry an MV
-    int32_t n_log;
-    int16_t pskip_mv[2];
-};
-
-struct FrameArrays           // per-frame motion state in HBM (h->mb.type / ref / mv / mvr of the reference)
-{
-    int8_t *type;            // [mb_h * mb_w]
-    int8_t *ref8;            // [2*mb_h][2*mb_w]
-    uint32_t *mv4;           // [4*mb_h][4*mb_w] packed
-    uint32_t *mvr;           // [max_refs][mb_h*mb_w] packed: 16x16 search result per reference
-};
-
-struct FrameParams
-{
-    int pass;                // 0 = no embedding, 1 = pre-encode, 2 = final encode (decisions forced from pass 1)
-    int n_ref;
-    int ref_slot[PCAMV_MAX_REFS];
-    int ref_poc[PCAMV_MAX_REFS];
-    int cur_poc;
-    int col_n_ref;           // fref0[0]->i_ref[0]; > 0 enables the temporal candidates
-    int col_inv_ref_poc[PCAMV_MAX_REFS];
-    const int8_t *col_ref8;
-    const uint32_t *col_mv4;
-    const ForcedMb *forced;  // pass 2 only
-    uint32_t stale_mv[16];   // what the MV cache held before MB 0 of this pass (quirk q2)
-    FrameArrays cur;
-    LogEntry *log;           // [n_mb][PCAMV_LOG_MAX]
-    MbResult *results;       // [n_mb]
-    int *row_progress;       // [mb_h] wavefront counters
-};
-
 // team-shared scratch of one macroblock
-struct MbWork
+struct alignas(16) MbWork
 {
     int8_t ref[48];          // scan8-indexed neighbour cache, list 0
     uint32_t mv[48];
@@ -87,6 +30,15 @@ struct MbWork
     uint8_t pred_y[256], pred_u[64], pred_v[64];     // MC / reconstruction staging
     int32_t scratch[32];
 };
+
+// Loads of per-frame motion state written by OTHER macroblocks of the running wavefront (possibly on another SM):
+// they bypass the non-coherent L1 (ld.global.cg).  Ordering against the writer is the row-progress flag
+// (release/acquire, pcamv_frame_kernels.cu).
+#if defined(PCAMV_EMU)
+  #define PCAMV_LDV(p) (*(p))
+#else
+  #define PCAMV_LDV(p) __ldcg(p)
+#endif
 
 PCAMV_DEV int scan8(int idx)
 {
@@ -147,24 +99,24 @@ PCAMV_DEV void cache_load(MbCtx &c)
     const int top_xy = (mb_y - 1) * mb_w + mb_x;
     const int top8 = (2 * (mb_y - 1) + 1) * s8 + 2 * mb_x, top4 = (4 * (mb_y - 1) + 3) * s4 + 4 * mb_x;
     const int cur8 = 2 * mb_y * s8 + 2 * mb_x, cur4 = 4 * mb_y * s4 + 4 * mb_x;
-    c.type_top = top ? a.type[top_xy] : -1;
-    c.type_left = left ? a.type[c.mb_xy - 1] : -1;
-    c.type_topright = topright ? a.type[top_xy + 1] : -1;
-    c.type_topleft = topleft ? a.type[top_xy - 1] : -1;
+    c.type_top = top ? PCAMV_LDV(a.type + top_xy) : -1;
+    c.type_left = left ? PCAMV_LDV(a.type + c.mb_xy - 1) : -1;
+    c.type_topright = topright ? PCAMV_LDV(a.type + top_xy + 1) : -1;
+    c.type_topleft = topleft ? PCAMV_LDV(a.type + top_xy - 1) : -1;
     // positions never written for the current MB keep "unavailable" (the reference memsets the cache to -2 once)
     for (int k = 0; k < 48; k++) { c.w.ref[k] = -2; c.w.mv[k] = 0; }
-    if (topleft) { c.w.ref[3] = a.ref8[top8 - 1]; c.w.mv[3] = a.mv4[top4 - 1]; }
+    if (topleft) { c.w.ref[3] = PCAMV_LDV(a.ref8 + top8 - 1); c.w.mv[3] = PCAMV_LDV(a.mv4 + top4 - 1); }
     if (top)
     {
-        c.w.ref[4] = c.w.ref[5] = a.ref8[top8]; c.w.ref[6] = c.w.ref[7] = a.ref8[top8 + 1];
-        for (int k = 0; k < 4; k++) c.w.mv[4 + k] = a.mv4[top4 + k];
+        c.w.ref[4] = c.w.ref[5] = PCAMV_LDV(a.ref8 + top8); c.w.ref[6] = c.w.ref[7] = PCAMV_LDV(a.ref8 + top8 + 1);
+        for (int k = 0; k < 4; k++) c.w.mv[4 + k] = PCAMV_LDV(a.mv4 + top4 + k);
     }
-    if (topright) { c.w.ref[8] = a.ref8[top8 + 2]; c.w.mv[8] = a.mv4[top4 + 4]; }
+    if (topright) { c.w.ref[8] = PCAMV_LDV(a.ref8 + top8 + 2); c.w.mv[8] = PCAMV_LDV(a.mv4 + top4 + 4); }
     if (left)
     {
-        c.w.ref[11] = c.w.ref[19] = a.ref8[cur8 - 1];
-        c.w.ref[27] = c.w.ref[35] = a.ref8[cur8 - 1 + s8];
-        for (int k = 0; k < 4; k++) c.w.mv[11 + 8 * k] = a.mv4[cur4 - 1 + k * s4];
+        c.w.ref[11] = c.w.ref[19] = PCAMV_LDV(a.ref8 + cur8 - 1);
+        c.w.ref[27] = c.w.ref[35] = PCAMV_LDV(a.ref8 + cur8 - 1 + s8);
+        for (int k = 0; k < 4; k++) c.w.mv[11 + 8 * k] = PCAMV_LDV(a.mv4 + cur4 - 1 + k * s4);
     }
 }
 
@@ -230,13 +182,13 @@ PCAMV_DEV int predict_mv_ref16x16(const MbCtx &c, int i_ref, int (*mvc)[2])
     const int8_t *type = c.fp.cur.type;
     int n = 0;
 #define PCAMV_SET(p) { const uint32_t v_ = (p); mvc[n][0] = mv_x(v_); mvc[n][1] = mv_y(v_); n++; }
-    if (c.mb_x > 0 && type[c.mb_xy - 1] != MB_P_SKIP) PCAMV_SET(mvr[c.mb_xy - 1]);
+    if (c.mb_x > 0 && PCAMV_LDV(type + c.mb_xy - 1) != MB_P_SKIP) PCAMV_SET(PCAMV_LDV(mvr + c.mb_xy - 1));
     if (c.mb_y > 0)
     {
         const int t = c.mb_xy - mb_w;
-        if (type[t] != MB_P_SKIP) PCAMV_SET(mvr[t]);
-        if (c.mb_x > 0 && type[t - 1] != MB_P_SKIP) PCAMV_SET(mvr[t - 1]);
-        if (c.mb_x < mb_w - 1 && type[t + 1] != MB_P_SKIP) PCAMV_SET(mvr[t + 1]);
+        if (PCAMV_LDV(type + t) != MB_P_SKIP) PCAMV_SET(PCAMV_LDV(mvr + t));
+        if (c.mb_x > 0 && PCAMV_LDV(type + t - 1) != MB_P_SKIP) PCAMV_SET(PCAMV_LDV(mvr + t - 1));
+        if (c.mb_x < mb_w - 1 && PCAMV_LDV(type + t + 1) != MB_P_SKIP) PCAMV_SET(PCAMV_LDV(mvr + t + 1));
     }
 #undef PCAMV_SET
     if (c.fp.col_n_ref > 0)
@@ -732,6 +684,23 @@ PCAMV_DEV void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partitio
     }
 }
 
+// Quirk q2 support: the wavefront only orders a macroblock after its left / top / top-right neighbours, but the
+// stale cache of a forced skip is what the previous MB IN RASTER ORDER left behind; for mb_x == 0 that is the last
+// MB of the row above, so wait for that whole row (it never depends on this one, hence no deadlock).
+PCAMV_DEV void wait_prev_raster(const MbCtx &c)
+{
+#if !defined(PCAMV_EMU)
+    if (c.mb_x == 0 && c.mb_y > 0)
+    {
+        const int *flag = c.fp.row_progress + c.mb_y - 1;
+        int v;
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); } while (v < c.fc.mb_w);
+    }
+#else
+    (void)c;
+#endif
+}
+
 // One macroblock of a P slice.  `prev_mv` = the 16 cache MVs left behind by the previous MB in raster order
 // (needed only for the pass-2 "forced skip without cache update" quirk, analyse.c:2668-2676).
 PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
@@ -783,7 +752,8 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
         {
             // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
             // and the refs are what the 16x16 search left (its best reference)
-            for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = prev_mv[i];
+            wait_prev_raster(c);
+            for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = PCAMV_LDV(prev_mv + i);
         }
         finalize_mb(c, a, MB_P_SKIP, PART_16x16, early_skip);
         return;

@@ -1,0 +1,176 @@
+// pcamv_frame_api.cu — C-ABI of the frame seam (include/pcamv.h: pcamv_analyse_p and its three stages).
+// Host-side only: argument checks, the pass-2 glue (pcamv_glue.h), staging, launches.
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "pcamv_ctx.h"
+#include "pcamv_glue.h"
+
+using namespace pcamv;
+
+namespace pcamv {
+void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_ctas, void *stream);
+void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream);
+}
+
+// the ABI records are the device records
+static_assert(sizeof(pcamv_log_entry) == sizeof(LogEntry) && sizeof(LogEntry) == 16, "log entry layout");
+static_assert(sizeof(pcamv_mb_out) == sizeof(MbResult) && sizeof(MbResult) == 128, "mb_out layout");
+static_assert(offsetof(pcamv_mb_out, part) == offsetof(MbResult, part) && offsetof(pcamv_mb_out, n_log) == offsetof(MbResult, n_log), "mb_out layout");
+static_assert(sizeof(pcamv_pass1_mb) == sizeof(Pass1Mb) && offsetof(pcamv_pass1_mb, mv_stego) == offsetof(Pass1Mb, mv_stego), "pass1 layout");
+static_assert(sizeof(ForcedOut) == sizeof(ForcedMb), "forced layout");
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(ctx, #call, e_); } while (0)
+#define GUARD() do { if (!ctx) return -1; if (ctx->failed) return -1; } while (0)
+
+static int ensure_frame_buffers(pcamv_ctx *ctx)
+{
+    if (ctx->d_log) return 0;
+    const DevFrameCtx &fc = ctx->fc;
+    const size_t n_mb = (size_t)fc.mb_w * fc.mb_h;
+    CK(cudaMalloc(&ctx->fa.type, n_mb));
+    CK(cudaMalloc(&ctx->fa.ref8, 4 * n_mb));
+    CK(cudaMalloc(&ctx->fa.mv4, 16 * n_mb * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->fa.mvr, (size_t)PCAMV_MAX_REFS * n_mb * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->d_col_ref8, 4 * n_mb));
+    CK(cudaMalloc(&ctx->d_col_mv4, 16 * n_mb * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->d_forced, n_mb * sizeof(ForcedMb)));
+    CK(cudaMalloc(&ctx->d_mb_results, n_mb * sizeof(MbResult)));
+    CK(cudaMalloc(&ctx->d_progress, (fc.mb_h + 1) * sizeof(int)));
+    CK(cudaMemsetAsync(ctx->fa.type, 0, n_mb, ctx->stream));
+    CK(cudaMemsetAsync(ctx->fa.ref8, 0, 4 * n_mb, ctx->stream));
+    CK(cudaMemsetAsync(ctx->fa.mv4, 0, 16 * n_mb * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->fa.mvr, 0, (size_t)PCAMV_MAX_REFS * n_mb * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_mb_results, 0, n_mb * sizeof(MbResult), ctx->stream));
+    // pinned staging: inputs (col ref/mv + forced) and outputs (results + log)
+    ctx->h_frame_bytes = n_mb * (4 + 64 + sizeof(ForcedMb) + sizeof(MbResult) + PCAMV_LOG_MAX * sizeof(LogEntry)) + 1024;
+    CK(cudaMallocHost(&ctx->h_frame, ctx->h_frame_bytes));
+    CK(cudaMalloc(&ctx->d_log, n_mb * PCAMV_LOG_MAX * sizeof(LogEntry)));
+    CK(cudaMemsetAsync(ctx->d_log, 0, n_mb * PCAMV_LOG_MAX * sizeof(LogEntry), ctx->stream));
+    return 0;
+}
+
+extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
+{
+    GUARD();
+    ctx->frame_ready = false;
+    if (!in) return ctx_fail(ctx, "pcamv_frame_upload: null argument", cudaSuccess);
+    const DevFrameCtx &fc = ctx->fc;
+    if (!fc.tab.cost_mv || !fc.tab.quant4_mf[0]) return ctx_fail(ctx, "pcamv_frame_upload: pcamv_set_qp_tables has not been called", cudaSuccess);
+    if (fc.subme < 1 || fc.subme > 5)
+        return ctx_fail(ctx, "pcamv_frame_upload: frame analysis supports subpel_refine 1..5 (RD mode decision is raster-serial)", cudaSuccess);
+    if (fc.analyse_inter & 0x20)
+        return ctx_fail(ctx, "pcamv_frame_upload: sub-8x8 partitions (X264_ANALYSE_PSUB8x8) are not supported", cudaSuccess);
+    if (fc.me_method < PCAMV_ME_DIA || fc.me_method > PCAMV_ME_ESA)
+        return ctx_fail(ctx, "pcamv_frame_upload: me_method must be dia/hex/umh/esa", cudaSuccess);
+    if (in->pass < 0 || in->pass > 2 || in->n_ref < 1 || in->n_ref > ctx->cfg.max_refs)
+        return ctx_fail(ctx, "pcamv_frame_upload: bad pass / n_ref", cudaSuccess);
+    for (int i = 0; i < in->n_ref; i++)
+        if (in->ref_slot[i] < 0 || in->ref_slot[i] >= ctx->cfg.max_refs + 2 || !fc.ref[in->ref_slot[i]].valid)
+            return ctx_fail(ctx, "pcamv_frame_upload: reference slot was never uploaded", cudaSuccess);
+    if (in->col_n_ref > 0 && (!in->col_ref8 || !in->col_mv4))
+        return ctx_fail(ctx, "pcamv_frame_upload: co-located ref/mv arrays missing", cudaSuccess);
+    if (in->pass == 2 && (!in->pass1 || (in->n_filp > 0 && !in->filp)))
+        return ctx_fail(ctx, "pcamv_frame_upload: pass 2 needs the pass-1 records and filp[]", cudaSuccess);
+    if (ensure_frame_buffers(ctx)) return -1;
+
+    const size_t n_mb = (size_t)fc.mb_w * fc.mb_h;
+    FrameParams &fp = ctx->fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.pass = in->pass; fp.n_ref = in->n_ref; fp.cur_poc = in->cur_poc;
+    for (int i = 0; i < PCAMV_MAX_REFS; i++)
+    {
+        fp.ref_slot[i] = in->ref_slot[i]; fp.ref_poc[i] = in->ref_poc[i];
+        fp.col_inv_ref_poc[i] = in->col_inv_ref_poc[i];
+    }
+    fp.col_n_ref = in->col_n_ref;
+    uint8_t *h = ctx->h_frame;
+    if (in->col_n_ref > 0)
+    {
+        memcpy(h, in->col_ref8, 4 * n_mb);
+        memcpy(h + 4 * n_mb, in->col_mv4, 64 * n_mb);
+        CK(cudaMemcpyAsync(ctx->d_col_ref8, h, 4 * n_mb, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_col_mv4, h + 4 * n_mb, 64 * n_mb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    fp.col_ref8 = ctx->d_col_ref8; fp.col_mv4 = ctx->d_col_mv4;
+    if (in->pass == 2)
+    {
+        ForcedOut *fo = (ForcedOut *)(h + 68 * n_mb);
+        // filp[] is consumed in cover order; build_forced walks the macroblocks in the same order
+        std::vector<int8_t> flips((size_t)(in->n_filp > 0 ? in->n_filp : 0) + 16 * n_mb, 0);
+        if (in->n_filp > 0) memcpy(flips.data(), in->filp, in->n_filp);
+        const int used = build_forced((int)n_mb, (const Pass1Mb *)in->pass1, flips.data(), fo);
+        if (used != in->n_filp)
+        {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "pcamv_frame_upload: pass-1 records carry %d motion vectors but n_filp is %d", used, in->n_filp);
+            return ctx_fail(ctx, msg, cudaSuccess);
+        }
+        CK(cudaMemcpyAsync(ctx->d_forced, fo, n_mb * sizeof(ForcedMb), cudaMemcpyHostToDevice, ctx->stream));
+        fp.forced = ctx->d_forced;
+    }
+    for (int i = 0; i < 16; i++)
+        fp.stale_mv[i] = ((uint32_t)(uint16_t)in->stale_mv[i][0]) | ((uint32_t)(uint16_t)in->stale_mv[i][1] << 16);
+    fp.cur = ctx->fa;
+    fp.log = ctx->d_log; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
+    CK(cudaStreamSynchronize(ctx->stream));        // the caller may reuse its buffers; pinned staging is free again
+    ctx->frame_cost_table = in->pass == 1 && in->cost_table;
+    ctx->frame_ready = true;
+    return 0;
+}
+
+static int launch_frame(pcamv_ctx *ctx)
+{
+    const DevFrameCtx &fc = ctx->fc;
+    CK(cudaMemsetAsync(ctx->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
+    launch_analyse_p(fc, ctx->fp, ctx->d_progress + fc.mb_h, fc.mb_h, ctx->stream);
+    ctx->launches += 1;
+    if (ctx->frame_cost_table)
+    {
+        launch_cost_table(fc, ctx->fp, fc.mb_w * fc.mb_h, ctx->stream);
+        ctx->launches += 1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pcamv_frame_run(pcamv_ctx *ctx, int iters, float *ms_per_frame)
+{
+    GUARD();
+    if (iters <= 0 || !ctx->frame_ready) return ctx_fail(ctx, "pcamv_frame_run: no frame uploaded", cudaSuccess);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i < iters; i++)
+        if (launch_frame(ctx)) return -1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ms_per_frame) *ms_per_frame = ms / iters;
+    return 0;
+}
+
+extern "C" int pcamv_frame_download(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    GUARD();
+    if (!ctx->frame_ready) return ctx_fail(ctx, "pcamv_frame_download: no frame uploaded", cudaSuccess);
+    const size_t n_mb = (size_t)ctx->fc.mb_w * ctx->fc.mb_h;
+    uint8_t *h = ctx->h_frame;
+    const size_t res_bytes = n_mb * sizeof(MbResult), log_bytes = n_mb * PCAMV_LOG_MAX * sizeof(LogEntry);
+    if (mbs) CK(cudaMemcpyAsync(h, ctx->d_mb_results, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (log) CK(cudaMemcpyAsync(h + res_bytes, ctx->d_log, log_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (mbs) memcpy(mbs, h, res_bytes);
+    if (log) memcpy(log, h + res_bytes, log_bytes);
+    return 0;
+}
+
+extern "C" int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    GUARD();
+    if (!mbs) return ctx_fail(ctx, "pcamv_analyse_p: null output", cudaSuccess);
+    if (pcamv_frame_upload(ctx, in)) return -1;
+    if (launch_frame(ctx)) return -1;
+    return pcamv_frame_download(ctx, mbs, log);
+}

@@ -1,0 +1,124 @@
+// pcamv_frame_kernels.cu — frame-level kernels of the P-slice analysis.
+//
+//   k_analyse_p     macroblock wavefront over one P slice: neighbour cache, MV prediction, P_SKIP probe,
+//                   16x16 / 8x8 / 16x8 / 8x16 searches, mode decision, qpel refinement, pass-2 forcing
+//                   (reference encoder/analyse.c:2613-3172 non-RD P path; device code in pcamv_frame.cuh)
+//   k_cost_table    the PCAMV candidate-MV cost table of every non-skip macroblock
+//                   (reference encoder/analyse.c:2391-2550, 3518-3689; device code in pcamv_cost.cuh)
+//
+// Wavefront: a macroblock needs its left, top-left, top and top-right neighbours (MV prediction,
+// common/macroblock.c:28-163,388-470,1085-1224).  One lane team (warp) owns one macroblock ROW and walks it
+// left to right; before macroblock x it waits until the row above has finished x+1 (its top-right).  Rows are
+// claimed from an atomic counter in increasing order, so every row a claimed row waits on is owned by a team
+// that is already running: the scheme cannot deadlock for any grid size.  Progress is published with
+// st.release.gpu after the macroblock's state is in HBM and consumed with ld.acquire.gpu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pcamv_device.h"
+#include "pcamv_cost.cuh"
+
+namespace pcamv {
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// source pixels of one macroblock -> team scratch (Y 16x16 stride 16, U/V 8x8 stride 8)
+__device__ __forceinline__ void stage_fenc(const DevFrameCtx &fc, int mb_x, int mb_y, MbWork &w)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane < 16)
+        *(uint4 *)(w.fenc_y + 16 * lane) = *(const uint4 *)(fc.fenc_y + (size_t)(16 * mb_y + lane) * fc.stride_y + 16 * mb_x);
+    else if (lane < 24)
+        *(uint2 *)(w.fenc_u + 8 * (lane - 16)) = *(const uint2 *)(fc.fenc_u + (size_t)(8 * mb_y + lane - 16) * fc.stride_c + 8 * mb_x);
+    else
+        *(uint2 *)(w.fenc_v + 8 * (lane - 24)) = *(const uint2 *)(fc.fenc_v + (size_t)(8 * mb_y + lane - 24) * fc.stride_c + 8 * mb_x);
+    __syncwarp();
+}
+
+#define AP_WARPS 1
+
+__global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_constant__ DevFrameCtx fc,
+                                                            const __grid_constant__ FrameParams fp, int *row_claim)
+{
+    __shared__ MbWork s_work[AP_WARPS];
+    MbWork &work = s_work[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int mb_w = fc.mb_w, mb_h = fc.mb_h;
+    for (;;)
+    {
+        int row = 0;
+        if (lane == 0)
+            row = atomicAdd(row_claim, 1);
+        row = __shfl_sync(0xffffffffu, row, 0);
+        if (row >= mb_h)
+            return;
+        for (int x = 0; x < mb_w; x++)
+        {
+            if (row > 0)
+            {
+                const int need = min(x + 2, mb_w);
+                while (ld_acquire(fp.row_progress + row - 1) < need)
+                    __nanosleep(64);
+            }
+            MbCtx c(fc, fp, work);
+            c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;
+            stage_fenc(fc, x, row, work);
+            analyse_p_mb(c, c.mb_xy ? fp.results[c.mb_xy - 1].mv : fp.stale_mv);
+            __syncwarp();
+            if (lane == 0)
+            {
+                __threadfence();
+                st_release(fp.row_progress + row, x + 1);
+            }
+        }
+    }
+}
+
+void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_ctas, void *stream)
+{
+    k_analyse_p<<<n_ctas, AP_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
+}
+
+// ---- cost table: one lane team per macroblock; macroblocks are independent -------------------------------
+#define CT_WARPS 4
+
+__global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_constant__ DevFrameCtx fc,
+                                                             const __grid_constant__ FrameParams fp, int n_mb)
+{
+    __shared__ MbWork s_work[CT_WARPS];
+    __shared__ MbResult s_res[CT_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * CT_WARPS + warp;
+    if (mb >= n_mb)
+        return;
+    MbWork &work = s_work[warp];
+    MbResult &res = s_res[warp];
+    {
+        const uint32_t *src = (const uint32_t *)(fp.results + mb);
+        uint32_t *dst = (uint32_t *)&res;
+        for (int i = lane; i < (int)(sizeof(MbResult) / 4); i += 32) dst[i] = src[i];
+        __syncwarp();
+    }
+    if (res.type == MB_P_SKIP)
+        return;
+    MbCtx c(fc, fp, work);
+    c.mb_x = mb % fc.mb_w; c.mb_y = mb / fc.mb_w; c.mb_xy = mb;
+    c.partition = res.partition;
+    stage_fenc(fc, c.mb_x, c.mb_y, work);
+    cost_table_mb(c, res);
+}
+
+void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream)
+{
+    k_cost_table<<<(n_mb + CT_WARPS - 1) / CT_WARPS, CT_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, fp, n_mb);
+}
+
+} // namespace pcamv

@@ -29,7 +29,7 @@
   // out-of-line device functions: the search code is far larger than the instruction cache when everything
   // is inlined (first profile: 678 KB of SASS, warps stalled on instruction fetch), so the block-cost
   // evaluators and the pattern walkers exist exactly once.
-  #define PCAMV_FN __device__ __noinline__
+  #define PCAMV_FN static __device__ __noinline__
   #define PCAMV_MEMFN __device__ __noinline__
   #define PCAMV_NGRP 4
   #define PCAMV_LPG  8

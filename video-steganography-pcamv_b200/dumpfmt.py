@@ -120,6 +120,58 @@ class Dump:
             refine[i] = r[0] == "MERQ"
         return out, refine
 
+    def slice_units(self):
+        """Per P-slice pass with planes, in file order: dict(slice, ctx (SLCX fields), calls, refine, mban, embd).
+        `embd` is the EMBD record written at the end of that pass (pass 1 only) or None."""
+        units, cur = [], None
+        embeds = iter(self.embeds())
+        for rec in self.records:
+            tag, off, size = rec
+            if tag == "SLCB":
+                s = Slice(self.payload(rec))
+                cur = None
+                if s.type == 0:
+                    cur = {"slice": s, "ctx": None, "calls": [], "refine": [], "mban": [], "embd": None}
+                    units.append(cur)
+            elif cur is None:
+                if tag == "EMBD":
+                    next(embeds)
+                continue
+            elif tag == "SLCX":
+                hd = np.frombuffer(self.raw, dtype="<i4", count=36, offset=off)
+                n_mb = int(hd[35])
+                cur["ctx"] = {"cur_poc": int(hd[0]), "n_ref": int(hd[1]), "ref_poc": [int(x) for x in hd[2:18]],
+                              "col_n_ref": int(hd[18]), "col_inv_ref_poc": [int(x) for x in hd[19:35]], "n_mb": n_mb,
+                              "col_ref8": np.frombuffer(self.raw, dtype=np.int8, count=4 * n_mb, offset=off + 144),
+                              "col_mv4": np.frombuffer(self.raw, dtype="<i2", count=32 * n_mb, offset=off + 144 + 4 * n_mb)}
+            elif tag in ("MESR", "MERQ"):
+                cur["calls"].append(np.frombuffer(self.raw, dtype=CALL_REC_DTYPE, count=1, offset=off)[0])
+                cur["refine"].append(tag == "MERQ")
+            elif tag == "MBAN":
+                cur["mban"].append(np.frombuffer(self.raw, dtype=MBAN_DTYPE, count=1, offset=off)[0])
+            elif tag == "EMBD":
+                cur["embd"] = next(embeds)
+            elif tag == "SLCE":
+                cur = None
+        for u in units:
+            u["calls"] = np.array(u["calls"], dtype=CALL_REC_DTYPE)
+            u["refine"] = np.array(u["refine"], dtype=bool)
+            u["mban"] = np.array(u["mban"], dtype=MBAN_DTYPE)
+        return units
+
+    def quant_tables(self):
+        """qp -> dict of the 'QNT0' record (quantiser tables of the P slices)."""
+        out = {}
+        for tag, off, size in self.records:
+            if tag != "QNT0":
+                continue
+            qp, qpc, lam2 = [int(x) for x in np.frombuffer(self.raw, dtype="<i4", count=3, offset=off)]
+            u16 = np.frombuffer(self.raw, dtype="<u2", count=64, offset=off + 12)
+            dq = np.frombuffer(self.raw, dtype="<i4", count=192, offset=off + 12 + 128)
+            out[qp] = {"chroma_qp": qpc, "lambda2_chroma": lam2, "quant4_mf": (u16[0:16], u16[32:48]),
+                       "quant4_bias": (u16[16:32], u16[48:64]), "dequant4_mf": (dq[:96], dq[96:])}
+        return out
+
     def mb_decisions(self):
         return self._stack("MBAN", MBAN_DTYPE)
 

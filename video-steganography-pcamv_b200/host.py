@@ -43,10 +43,30 @@ ME_CALL_DTYPE = np.dtype([
     ("cost_in", "<i4"), ("cost_mv_in", "<i4")], align=True)
 ME_RESULT_DTYPE = np.dtype([("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4"), ("thresh_out", "<i4")], align=True)
 
+LOG_MAX = 48
+LOG_ENTRY_DTYPE = np.dtype([("kind", "i1"), ("i_pixel", "i1"), ("i_ref", "i1"), ("pad", "i1"), ("mv", "<i2", 2),
+                            ("cost", "<i4"), ("cost_mv", "<i4")], align=True)
+MB_OUT_DTYPE = np.dtype([("type", "i1"), ("partition", "i1"), ("n_part", "i1"), ("early_skip", "i1"), ("ref", "i1", 4),
+                         ("mv", "<i2", (16, 2)),
+                         ("part", [("mv", "<i2", 2), ("mvp", "<i2", 2), ("ref", "i1"), ("i_pixel", "i1"), ("xoff", "i1"),
+                                   ("yoff", "i1")], 4),
+                         ("n_log", "<i4"), ("pskip_mv", "<i2", 2)], align=True)
+PASS1_MB_DTYPE = np.dtype([("type", "<i4"), ("partition", "<i4"), ("used", "u1"), ("sub", "u1", 4), ("ref", "i1", 16),
+                           ("mv", "<i2", (16, 2)), ("mv_stego", "<i2", (16, 2))], align=True)
+
+
+class FrameIn(C.Structure):
+    _fields_ = [("pass_", C.c_int32), ("n_ref", C.c_int32), ("ref_slot", C.c_int32 * 16), ("ref_poc", C.c_int32 * 16),
+                ("cur_poc", C.c_int32), ("col_n_ref", C.c_int32), ("col_inv_ref_poc", C.c_int32 * 16),
+                ("col_ref8", C.c_void_p), ("col_mv4", C.c_void_p), ("pass1", C.c_void_p), ("filp", C.c_void_p),
+                ("n_filp", C.c_int32), ("cost_table", C.c_int32), ("stale_mv", (C.c_int16 * 2) * 16)]
+
+
 EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version", "pcamv_set_qp_tables",
            "pcamv_put_fenc", "pcamv_put_ref", "pcamv_put_ref_planes", "pcamv_get_ref_plane", "pcamv_plane_bytes",
            "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
-           "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak"]
+           "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
+           "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download"]
 
 _lib = None
 
@@ -78,6 +98,10 @@ def load_library(path=None):
     lib.pcamv_me_batch_download.argtypes = [vp, vp, ip]; lib.pcamv_me_batch_download.restype = ip
     lib.pcamv_launch_count.argtypes = [vp]; lib.pcamv_launch_count.restype = C.c_longlong
     lib.pcamv_int_peak.argtypes = [vp, C.POINTER(C.c_double)]; lib.pcamv_int_peak.restype = ip
+    lib.pcamv_analyse_p.argtypes = [vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_analyse_p.restype = ip
+    lib.pcamv_frame_upload.argtypes = [vp, C.POINTER(FrameIn)]; lib.pcamv_frame_upload.restype = ip
+    lib.pcamv_frame_run.argtypes = [vp, ip, C.POINTER(C.c_float)]; lib.pcamv_frame_run.restype = ip
+    lib.pcamv_frame_download.argtypes = [vp, vp, vp]; lib.pcamv_frame_download.restype = ip
     if path == build.LIB:
         _lib = lib
     return lib
@@ -195,6 +219,58 @@ class PcamvContext:
         res = np.zeros(self._batch_n, dtype=ME_RESULT_DTYPE)
         self._check(self.lib.pcamv_me_batch_download(self.handle, _ptr(res), self._batch_n))
         return res
+
+    # -- frame seam --------------------------------------------------------------------------------
+    def _frame_in(self, pass_, ref_slots, ref_pocs, cur_poc, col_n_ref=0, col_inv_ref_poc=None, col_ref8=None,
+                  col_mv4=None, pass1=None, filp=None, cost_table=True, stale_mv=None):
+        fi = FrameIn()
+        keep = []
+        fi.pass_, fi.n_ref, fi.cur_poc, fi.col_n_ref = pass_, len(ref_slots), cur_poc, col_n_ref
+        for i, (s, p) in enumerate(zip(ref_slots, ref_pocs)):
+            fi.ref_slot[i], fi.ref_poc[i] = int(s), int(p)
+        for i, v in enumerate(col_inv_ref_poc if col_inv_ref_poc is not None else []):
+            fi.col_inv_ref_poc[i] = int(v)
+        if col_n_ref > 0:
+            a = np.ascontiguousarray(col_ref8, dtype=np.int8); b = np.ascontiguousarray(col_mv4, dtype=np.int16)
+            n_mb = (self.width // 16) * (self.height // 16)
+            assert a.size == 4 * n_mb and b.size == 32 * n_mb, (a.size, b.size, n_mb)
+            keep += [a, b]
+            fi.col_ref8, fi.col_mv4 = a.ctypes.data, b.ctypes.data
+        if pass1 is not None:
+            a = np.ascontiguousarray(pass1, dtype=PASS1_MB_DTYPE)
+            f = np.ascontiguousarray(filp if filp is not None else [], dtype=np.int8)
+            keep += [a, f]
+            fi.pass1, fi.filp, fi.n_filp = a.ctypes.data, f.ctypes.data, len(f)
+        fi.cost_table = int(bool(cost_table))
+        if stale_mv is not None:
+            for i in range(16):
+                fi.stale_mv[i][0], fi.stale_mv[i][1] = int(stale_mv[i][0]), int(stale_mv[i][1])
+        return fi, keep
+
+    def analyse_p(self, pass_, ref_slots, ref_pocs, cur_poc, **kw):
+        """pcamv_analyse_p: returns (mb records [n_mb], log [n_mb, LOG_MAX])."""
+        fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
+        n_mb = (self.width // 16) * (self.height // 16)
+        mbs = np.zeros(n_mb, dtype=MB_OUT_DTYPE)
+        log = np.zeros((n_mb, LOG_MAX), dtype=LOG_ENTRY_DTYPE)
+        self._check(self.lib.pcamv_analyse_p(self.handle, C.byref(fi), _ptr(mbs), _ptr(log)))
+        return mbs, log
+
+    def frame_upload(self, pass_, ref_slots, ref_pocs, cur_poc, **kw):
+        fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
+        self._check(self.lib.pcamv_frame_upload(self.handle, C.byref(fi)))
+
+    def frame_run(self, iters=1):
+        ms = C.c_float()
+        self._check(self.lib.pcamv_frame_run(self.handle, iters, C.byref(ms)))
+        return float(ms.value)
+
+    def frame_download(self, want_log=True):
+        n_mb = (self.width // 16) * (self.height // 16)
+        mbs = np.zeros(n_mb, dtype=MB_OUT_DTYPE)
+        log = np.zeros((n_mb, LOG_MAX), dtype=LOG_ENTRY_DTYPE) if want_log else None
+        self._check(self.lib.pcamv_frame_download(self.handle, _ptr(mbs), _ptr(log) if want_log else None))
+        return mbs, log
 
     def int_peak_gops(self):
         g = C.c_double()

@@ -215,10 +215,12 @@ typedef struct pcamv_frame_in
 int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log);
 
 /* Benchmark / pipelining support: the three stages of pcamv_analyse_p separately.  _upload stages the frame
- * inputs in HBM; _run launches the wavefront (+ cost table) `iters` times and returns the mean device time of one
- * analysis in milliseconds (CUDA events on the context's stream); _download copies results back. */
+ * inputs of in->pass in HBM (one set per pass is kept, so pass 1 and pass 2 of a frame can both be resident);
+ * _run launches the wavefront (+ cost table) of `pass` (-1: the last uploaded) `iters` times and returns the mean
+ * device time of one analysis in milliseconds (CUDA events on the context's stream); _download copies the
+ * results of the last run back. */
 int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in);
-int pcamv_frame_run(pcamv_ctx *ctx, int iters, float *ms_per_frame);
+int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_per_frame);
 int pcamv_frame_download(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log);
 
 /* Measured integer-pipe issue peak of the device, in giga lane-operations/s: a microbenchmark of the

@@ -79,7 +79,8 @@ def instrument(tree):
     hook_decl = ("void pcamv_hook_open( x264_t *h ); void pcamv_hook_close( x264_t *h );\n"
                  "void pcamv_hook_slice_begin( x264_t *h ); void pcamv_hook_slice_end( x264_t *h );\n"
                  "void pcamv_hook_analyse_begin( x264_t *h ); void pcamv_hook_analyse_end( x264_t *h );\n"
-                 "void pcamv_hook_embed( x264_t *h, int an ); void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me );\n")
+                 "void pcamv_hook_embed( x264_t *h, int an ); void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me );\n"
+                 "void pcamv_hook_ih_begin( void ); void pcamv_hook_ih_end( void );\n")
     p = os.path.join(tree, "encoder/encoder.c")
     t = read(p)
     t = sub_exact(t, r'(#include "common/common.h"\n)', r"\1" + hook_decl.replace("\\", "\\\\"), 1, "encoder.c include")
@@ -109,6 +110,15 @@ def instrument(tree):
     t = read(p)
     t = sub_exact(t, r'(#include "common/common.h"\n)', r"\1" + hook_decl.replace("\\", "\\\\"), 1, "analyse.c include")
     t = sub_exact(t, r"(#define MV_SATD_FDEC_IH\(mx, my\)\\\n\{\\\n)", r"\1\tpcamv_hook_ih_satd( m->i_pixel, h->mb.b_chroma_me && m->i_pixel <= PIXEL_8x8 );\\\n", 1, "MV_SATD_FDEC_IH")
+    # time spent inside x264_ih_get_mv_cost (encoder/analyse.c:2391): rename the definition and put a timing wrapper
+    # of the same name in front of x264_macroblock_analyse (its only caller, encoder/analyse.c:3557-3673)
+    t = sub_exact(t, r"\nstatic inline int x264_ih_get_mv_cost\(", "\nstatic inline int x264_ih_get_mv_cost_real(", 1, "ih_get_mv_cost def")
+    wrapper = ("static int x264_ih_get_mv_cost( x264_t *h, x264_mb_analysis_t *analysis, x264_me_t *m, int16_t *m_x, int16_t *m_y,\n"
+               "    int8_t d_mv[][2], int8_t d_mv_1_neighborhood[][2], int mb_xy )\n"
+               "{ int r; pcamv_hook_ih_begin(); r = x264_ih_get_mv_cost_real( h, analysis, m, m_x, m_y, d_mv, d_mv_1_neighborhood, mb_xy );\n"
+               "  pcamv_hook_ih_end(); return r; }\n")
+    idx = t.index("\nvoid x264_macroblock_analyse( x264_t *h )\n")
+    t = t[:idx] + "\n" + wrapper + t[idx:]
     write(p, t)
 
 

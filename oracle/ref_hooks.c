@@ -39,8 +39,9 @@ static int g_pslice;
 static uint64_t g_cnt_sad, g_cnt_satd, g_cnt_ih_luma, g_cnt_ih_chroma;
 static uint64_t g_cnt_search, g_cnt_refine, g_cnt_mb_p, g_cnt_pframes, g_cnt_ads;
 static uint64_t g_pix_sad, g_pix_satd;  /* pixel-normalised (w*h) */
-static double g_t_analyse_p, g_t_me, g_t_total0;
-static struct timespec g_ts_an, g_ts_me;
+static double g_t_analyse_p, g_t_me, g_t_ih, g_t_total0;
+static uint64_t g_cnt_ih_calls;
+static struct timespec g_ts_an, g_ts_me, g_ts_ih;
 
 static double now_s( void )
 {
@@ -156,12 +157,14 @@ void pcamv_hook_close( x264_t *h )
             fprintf( f, "{\"sad\": %llu, \"satd\": %llu, \"ih_luma\": %llu, \"ih_chroma\": %llu, "
                         "\"pix_sad\": %llu, \"pix_satd\": %llu, "
                         "\"searches\": %llu, \"refines\": %llu, \"p_mb_passes\": %llu, \"p_frames\": %llu, "
+                        "\"ih_calls\": %llu, \"t_ih\": %.6f, "
                         "\"t_analyse_p\": %.6f, \"t_me\": %.6f, \"t_total\": %.6f}\n",
                      (unsigned long long)g_cnt_sad, (unsigned long long)g_cnt_satd,
                      (unsigned long long)g_cnt_ih_luma, (unsigned long long)g_cnt_ih_chroma,
                      (unsigned long long)g_pix_sad, (unsigned long long)g_pix_satd,
                      (unsigned long long)g_cnt_search, (unsigned long long)g_cnt_refine,
                      (unsigned long long)g_cnt_mb_p, (unsigned long long)g_cnt_pframes,
+                     (unsigned long long)g_cnt_ih_calls, g_t_ih,
                      g_t_analyse_p, g_t_me, now_s() - g_t_total0 );
             fclose( f );
         }
@@ -276,6 +279,17 @@ void pcamv_hook_slice_end( x264_t *h )
         fwrite( hd, 1, sizeof(hd), g_dump );
         fwrite( g_cost_mv[h->sh.i_qp], 2, 32769, g_dump );
         fwrite( x264_cost_ref[h->sh.i_qp], 2, 3*33, g_dump );
+    }
+    {
+        /* 'CNT0': cumulative counters at the end of this slice pass (uint64 each): sad, satd, ih_luma, ih_chroma,
+         * pix_sad, pix_satd, searches, refines, ih_calls; then double t_me, t_ih, t_analyse_p.  Per-pass work =
+         * difference of consecutive records. */
+        uint64_t c[9] = { g_cnt_sad, g_cnt_satd, g_cnt_ih_luma, g_cnt_ih_chroma, g_pix_sad, g_pix_satd,
+                          g_cnt_search, g_cnt_refine, g_cnt_ih_calls };
+        double t[3] = { g_t_me, g_t_ih, g_t_analyse_p };
+        rec_begin( "CNT0", sizeof(c) + sizeof(t) );
+        fwrite( c, 1, sizeof(c), g_dump );
+        fwrite( t, 1, sizeof(t), g_dump );
     }
     {
         /* 'SLCE': int32 frame, pass, n_mb; then int8 type[n_mb]; int8 ref[4*n_mb] in b8 raster;
@@ -470,6 +484,13 @@ void x264_me_refine_qpel( x264_t *h, x264_me_t *m )
         rec_begin( "MERQ", sizeof(r) );
         fwrite( &r, 1, sizeof(r), g_dump );
     }
+}
+
+void pcamv_hook_ih_begin( void ) { clock_gettime( CLOCK_MONOTONIC, &g_ts_ih ); g_cnt_ih_calls++; }
+void pcamv_hook_ih_end( void )
+{
+    struct timespec t; clock_gettime( CLOCK_MONOTONIC, &t );
+    g_t_ih += (t.tv_sec - g_ts_ih.tv_sec) + 1e-9*(t.tv_nsec - g_ts_ih.tv_nsec);
 }
 
 /* one MV_SATD_FDEC_IH evaluation (encoder/analyse.c:2364-2385): +1 luma SATD, +2 chroma when chroma ME */

@@ -35,8 +35,9 @@ struct pcamv_ctx
     pcamv::MbResult *d_mb_results = nullptr;   // [n_mb]
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter
     uint8_t *h_frame = nullptr; size_t h_frame_bytes = 0;             // pinned staging for frame inputs / outputs
-    pcamv::FrameParams fp = {};                // parameters of the last uploaded frame
-    bool frame_ready = false, frame_cost_table = false;
+    pcamv::FrameParams fp[3] = {};             // parameters of the last uploaded frame, per pass (0 / 1 / 2)
+    bool frame_ready[3] = { false, false, false }, frame_cost_table = false;
+    int frame_last = -1;
 };
 
 namespace pcamv {

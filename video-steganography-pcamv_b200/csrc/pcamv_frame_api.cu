@@ -55,7 +55,6 @@ static int ensure_frame_buffers(pcamv_ctx *ctx)
 extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
 {
     GUARD();
-    ctx->frame_ready = false;
     if (!in) return ctx_fail(ctx, "pcamv_frame_upload: null argument", cudaSuccess);
     const DevFrameCtx &fc = ctx->fc;
     if (!fc.tab.cost_mv || !fc.tab.quant4_mf[0]) return ctx_fail(ctx, "pcamv_frame_upload: pcamv_set_qp_tables has not been called", cudaSuccess);
@@ -77,7 +76,8 @@ extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
     if (ensure_frame_buffers(ctx)) return -1;
 
     const size_t n_mb = (size_t)fc.mb_w * fc.mb_h;
-    FrameParams &fp = ctx->fp;
+    ctx->frame_ready[in->pass] = false;
+    FrameParams &fp = ctx->fp[in->pass];
     memset(&fp, 0, sizeof(fp));
     fp.pass = in->pass; fp.n_ref = in->n_ref; fp.cur_poc = in->cur_poc;
     for (int i = 0; i < PCAMV_MAX_REFS; i++)
@@ -117,32 +117,35 @@ extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
     fp.log = ctx->d_log; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
     CK(cudaStreamSynchronize(ctx->stream));        // the caller may reuse its buffers; pinned staging is free again
     ctx->frame_cost_table = in->pass == 1 && in->cost_table;
-    ctx->frame_ready = true;
+    ctx->frame_ready[in->pass] = true;
+    ctx->frame_last = in->pass;
     return 0;
 }
 
-static int launch_frame(pcamv_ctx *ctx)
+static int launch_frame(pcamv_ctx *ctx, int pass)
 {
     const DevFrameCtx &fc = ctx->fc;
     CK(cudaMemsetAsync(ctx->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
-    launch_analyse_p(fc, ctx->fp, ctx->d_progress + fc.mb_h, fc.mb_h, ctx->stream);
+    launch_analyse_p(fc, ctx->fp[pass], ctx->d_progress + fc.mb_h, fc.mb_h, ctx->stream);
     ctx->launches += 1;
-    if (ctx->frame_cost_table)
+    if (pass == 1 && ctx->frame_cost_table)
     {
-        launch_cost_table(fc, ctx->fp, fc.mb_w * fc.mb_h, ctx->stream);
+        launch_cost_table(fc, ctx->fp[pass], fc.mb_w * fc.mb_h, ctx->stream);
         ctx->launches += 1;
     }
     CK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int pcamv_frame_run(pcamv_ctx *ctx, int iters, float *ms_per_frame)
+extern "C" int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_per_frame)
 {
     GUARD();
-    if (iters <= 0 || !ctx->frame_ready) return ctx_fail(ctx, "pcamv_frame_run: no frame uploaded", cudaSuccess);
+    if (pass < 0) pass = ctx->frame_last;
+    if (iters <= 0 || pass < 0 || pass > 2 || !ctx->frame_ready[pass])
+        return ctx_fail(ctx, "pcamv_frame_run: no frame uploaded for that pass", cudaSuccess);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int i = 0; i < iters; i++)
-        if (launch_frame(ctx)) return -1;
+        if (launch_frame(ctx, pass)) return -1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
     float ms = 0;
@@ -154,7 +157,7 @@ extern "C" int pcamv_frame_run(pcamv_ctx *ctx, int iters, float *ms_per_frame)
 extern "C" int pcamv_frame_download(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log)
 {
     GUARD();
-    if (!ctx->frame_ready) return ctx_fail(ctx, "pcamv_frame_download: no frame uploaded", cudaSuccess);
+    if (ctx->frame_last < 0) return ctx_fail(ctx, "pcamv_frame_download: no frame uploaded", cudaSuccess);
     const size_t n_mb = (size_t)ctx->fc.mb_w * ctx->fc.mb_h;
     uint8_t *h = ctx->h_frame;
     const size_t res_bytes = n_mb * sizeof(MbResult), log_bytes = n_mb * PCAMV_LOG_MAX * sizeof(LogEntry);
@@ -171,6 +174,6 @@ extern "C" int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_m
     GUARD();
     if (!mbs) return ctx_fail(ctx, "pcamv_analyse_p: null output", cudaSuccess);
     if (pcamv_frame_upload(ctx, in)) return -1;
-    if (launch_frame(ctx)) return -1;
+    if (launch_frame(ctx, in->pass)) return -1;
     return pcamv_frame_download(ctx, mbs, log);
 }

@@ -159,6 +159,20 @@ class Dump:
             u["mban"] = np.array(u["mban"], dtype=MBAN_DTYPE)
         return units
 
+    def counters(self):
+        """'CNT0' records in file order (one per dumped P-slice pass): cumulative work counters of the reference."""
+        names = ["sad", "satd", "ih_luma", "ih_chroma", "pix_sad", "pix_satd", "searches", "refines", "ih_calls"]
+        out = []
+        for tag, off, size in self.records:
+            if tag != "CNT0":
+                continue
+            c = np.frombuffer(self.raw, dtype="<u8", count=9, offset=off)
+            t = np.frombuffer(self.raw, dtype="<f8", count=3, offset=off + 72)
+            d = {k: int(v) for k, v in zip(names, c)}
+            d.update(t_me=float(t[0]), t_ih=float(t[1]), t_analyse_p=float(t[2]))
+            out.append(d)
+        return out
+
     def quant_tables(self):
         """qp -> dict of the 'QNT0' record (quantiser tables of the P slices)."""
         out = {}

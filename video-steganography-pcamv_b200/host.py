@@ -100,7 +100,7 @@ def load_library(path=None):
     lib.pcamv_int_peak.argtypes = [vp, C.POINTER(C.c_double)]; lib.pcamv_int_peak.restype = ip
     lib.pcamv_analyse_p.argtypes = [vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_analyse_p.restype = ip
     lib.pcamv_frame_upload.argtypes = [vp, C.POINTER(FrameIn)]; lib.pcamv_frame_upload.restype = ip
-    lib.pcamv_frame_run.argtypes = [vp, ip, C.POINTER(C.c_float)]; lib.pcamv_frame_run.restype = ip
+    lib.pcamv_frame_run.argtypes = [vp, ip, ip, C.POINTER(C.c_float)]; lib.pcamv_frame_run.restype = ip
     lib.pcamv_frame_download.argtypes = [vp, vp, vp]; lib.pcamv_frame_download.restype = ip
     if path == build.LIB:
         _lib = lib
@@ -260,9 +260,9 @@ class PcamvContext:
         fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
         self._check(self.lib.pcamv_frame_upload(self.handle, C.byref(fi)))
 
-    def frame_run(self, iters=1):
+    def frame_run(self, pass_=-1, iters=1):
         ms = C.c_float()
-        self._check(self.lib.pcamv_frame_run(self.handle, iters, C.byref(ms)))
+        self._check(self.lib.pcamv_frame_run(self.handle, pass_, iters, C.byref(ms)))
         return float(ms.value)
 
     def frame_download(self, want_log=True):

@@ -1,19 +1,27 @@
 #!/usr/bin/env python3
-"""bench.py — ME Mcandidates/s of the PCAMV motion-estimation hot path on B200 (BASELINE.json metric).
+"""bench.py — ME Mcandidates/s (and analysed P-frames/s) of the PCAMV motion-estimation hot path on B200.
 
-One "step" = one pass of the hot path over one batch: every x264_me_search_ref / x264_me_refine_qpel
-evaluation the reference encoder makes for one 1080p P-frame (both PCAMV passes) of the synthetic clip,
-against that frame's reference planes.  Candidates are credited as the REFERENCE executes them
-(per-call counters of the instrumented reference), never as the GPU happens to evaluate them.
+One "step" = the hot path over one 1080p P-frame exactly as the encoder needs it (BASELINE.json config 2):
+  pass 1  macroblock-wavefront analysis (every x264_me_search_ref / x264_me_refine_qpel of the frame, P_SKIP probes,
+          mode decision) + the PCAMV candidate-MV cost table of every motion vector (x264_ih_get_mv_cost)
+  pass 2  the wavefront analysis again with the pass-1 decisions and the STC flips forced
+Candidates (block-distortion evaluations at one MV) are credited as the REFERENCE executes them for the same
+frame — per-pass counters of the instrumented reference (oracle/ref_hooks.c: sad/satd +1, sad_x3 +3, sad_x4 +4,
+MV_SATD_FDEC_IH +1 luma +2 chroma) — never as the GPU happens to evaluate them.
 
-  value   device-resident: planes, fenc and the call batch already in HBM; CUDA-event time of the search kernel
-  e2e     through the C-ABI with HOST buffers: upload fenc + reconstructed reference (H2D), GPU border/half-pel
-          filter, upload calls, search, download results (D2H) — everything inside the timed region
-  --impl reference   the reference's own CPU implementation (oracle/_ref/x264_dump, C-only as built from
-          /root/reference) on the box's host cores, same clip/flags, candidates / time spent in the same calls
+  value   device-resident: frame inputs already in HBM; CUDA-event time of the three kernels on the context's stream
+  e2e     through the C-ABI with HOST buffers: pcamv_put_fenc + pcamv_put_ref (H2D, GPU border + half-pel filter),
+          pcamv_analyse_p pass 1 (H2D co-located MVs, D2H records + log), pcamv_analyse_p pass 2 (H2D pass-1
+          records + flips, D2H records + log) — wall clock around the calls, copies inside the timed region
+  --impl reference   the reference's own CPU implementation (oracle/_ref/x264_dump, built from /root/reference's C
+          sources) on the box's host cores, same clip and flags: reference-counted candidates / seconds spent
+          inside x264_macroblock_analyse of the P slices
 
-Launch: python bench.py [--gpus N --steps K --warmup W]   (N>1 via torch.distributed.run, one rank per GPU;
-ranks take independent clips = independent GOP shards; no data-path collective, weak scaling).
+A parity gate runs before any timing: records, search logs and cost table of both passes must equal the
+reference's bit for bit (tests/frame_parity.py), otherwise bench.py exits non-zero.
+
+Launch: python bench.py [--gpus N --steps K --warmup W]   (N>1 via torch.distributed.run, one rank per GPU; every
+rank analyses its own clip = an independent GOP shard; no data-path collective, weak scaling).
 """
 import argparse
 import json
@@ -34,31 +42,37 @@ WIDTH, HEIGHT = 1920, 1080
 REF_ARGS = "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"
 WORKLOAD = ("1080p synthetic YUV420 (synth/pcamv_synth.c config 2), --me umh --subme 5 --ref 1 --qp 26 --emrate 0.2; "
             "subme 5 instead of 7: RD mode decision is raster-serial on CABAC state (DESIGN.md)")
-CLIP_FRAMES = 3            # I P P ; the batch is P-frame #1 (both passes)
-BATCH_FRAME = 1
+CLIP_FRAMES = 3            # I P P
+BATCH_FRAME = 2            # the second P frame: spatial + temporal MV candidates are both live
+METRIC = "me_mcandidates_per_sec"
 
 
-def metric_name():
-    return "me_mcandidates_per_sec"
-
-
-def prepare_inputs(pcamv, rank, workdir, want_dump=True):
-    """Synthetic clip + instrumented reference run (candidate counts, call records, planes)."""
+def prepare_inputs(pcamv, rank, workdir):
+    """Synthetic clip + instrumented reference run for BATCH_FRAME: planes, expected records, candidate counters."""
     import refrun
     clip = refrun.synth_clip(pcamv, WIDTH, HEIGHT, CLIP_FRAMES, config=2, stream=rank, workdir=workdir)
-    dump = os.path.join(workdir, "dump.bin") if want_dump else None
-    t0 = time.time()
-    refrun.run_ref(clip, WIDTH, HEIGHT, REF_ARGS.split(), dump=dump, frames="%d:%d" % (BATCH_FRAME, BATCH_FRAME + 1),
-                   count=True, stats=os.path.join(workdir, "stats_count.json"))
-    return clip, dump, time.time() - t0
+    dump = os.path.join(workdir, "dump.bin")
+    refrun.run_ref(clip, WIDTH, HEIGHT, REF_ARGS.split(), dump=dump, frames="%d:%d" % (BATCH_FRAME, BATCH_FRAME + 1), count=True)
+    return clip, dump
 
 
-def cpu_reference_timing(pcamv, clip, workdir, frames=CLIP_FRAMES):
-    """Clean timing run of the reference (no counting wrappers, no dump): seconds inside the search calls."""
+def cpu_reference_timing(pcamv, clip, workdir):
+    """Clean timing run of the reference (no counting wrappers, no dump)."""
     import refrun
     stats = os.path.join(workdir, "stats_time.json")
-    refrun.run_ref(clip, WIDTH, HEIGHT, REF_ARGS.split() + ["--frames", str(frames)], stats=stats)
+    refrun.run_ref(clip, WIDTH, HEIGHT, REF_ARGS.split(), stats=stats)
     return json.load(open(stats))
+
+
+def cpu_reference_counts(pcamv, clip, workdir):
+    import refrun
+    stats = os.path.join(workdir, "stats_count.json")
+    refrun.run_ref(clip, WIDTH, HEIGHT, REF_ARGS.split(), stats=stats, count=True)
+    return json.load(open(stats))
+
+
+def candidates_of(c):
+    return c["sad"] + c["satd"] + c["ih_luma"] + c["ih_chroma"]
 
 
 class ClockSampler(threading.Thread):
@@ -93,27 +107,46 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def cpu_baseline_block(pcamv, clip, workdir):
+    """The reference's CPU path on this box: candidates of the clip's P frames / time inside x264_macroblock_analyse."""
+    counts = cpu_reference_counts(pcamv, clip, workdir)
+    st = cpu_reference_timing(pcamv, clip, workdir)
+    cand = candidates_of(counts)
+    return {"value": cand / st["t_analyse_p"] / 1e6, "unit": "Mcandidates/s", "cores": 1, "kind": "reference",
+            "sample": "oracle/_ref/x264_dump (reference C sources, gcc -O4 -ffast-math, no asm; the encoder is single-threaded "
+                      "with embedding on), %d-frame 1080p clip, %d candidates in %.2f s inside x264_macroblock_analyse of the "
+                      "P slices (search %.2f s, cost table %.2f s); whole encode %.2f s = %.2f frames/s"
+                      % (CLIP_FRAMES, cand, st["t_analyse_p"], st["t_me"], st["t_ih"], st["t_total"], CLIP_FRAMES / st["t_total"]),
+            "analysed_p_frames_per_sec": counts["p_frames"] / st["t_analyse_p"],
+            "encode_frames_per_sec": CLIP_FRAMES / st["t_total"]}
+
+
 def run_reference_arm(args, pcamv, rank, world):
     if rank != 0:
         return
+    import refrun
     workdir = tempfile.mkdtemp(prefix="pcamv_bench_ref_")
-    clip, _, _ = prepare_inputs(pcamv, 0, workdir, want_dump=False)
-    counts = json.load(open(os.path.join(workdir, "stats_count.json")))
-    cand = counts["sad"] + counts["satd"]
-    times = []
+    clip = refrun.synth_clip(pcamv, WIDTH, HEIGHT, CLIP_FRAMES, config=2, stream=0, workdir=workdir)
+    counts = cpu_reference_counts(pcamv, clip, workdir)
+    cand = candidates_of(counts)
+    times, totals = [], []
     for i in range(args.warmup + args.steps):
         st = cpu_reference_timing(pcamv, clip, workdir)
         if i >= args.warmup:
-            times.append(st["t_me"])
+            times.append(st["t_analyse_p"]); totals.append(st["t_total"])
     t = float(np.mean(times))
     v = cand / t / 1e6
-    line = {"impl": "reference", "metric": metric_name(), "value": v, "unit": "Mcandidates/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames": CLIP_FRAMES, "sample": "whole %d-frame clip, all P-frame passes" % CLIP_FRAMES},
+    sample = ("whole %d-frame clip per step (%d P frames, both passes each): %d reference-counted candidates, time inside "
+              "x264_macroblock_analyse of the P slices" % (CLIP_FRAMES, counts["p_frames"], cand))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mcandidates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 / counts["p_frames"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames": CLIP_FRAMES, "sample": sample},
             "cpu_baseline": {"value": v, "unit": "Mcandidates/s", "cores": 1, "kind": "reference",
-                             "sample": "oracle/_ref/x264_dump (reference C sources, gcc -O4 -ffast-math, no asm), %d frames 1080p, "
-                                       "time inside x264_me_search_ref + x264_me_refine_qpel" % CLIP_FRAMES},
+                             "sample": "oracle/_ref/x264_dump (reference C sources, gcc -O4 -ffast-math, no asm, single encoder thread: "
+                                       "frame threads crash with embedding on), " + sample},
+            "analysed_p_frames_per_sec": counts["p_frames"] / t,
+            "encode_frames_per_sec": CLIP_FRAMES / float(np.mean(totals)),
             "e2e": {"value": v, "unit": "Mcandidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -124,6 +157,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (profiling runs)")
     args = ap.parse_args()
 
     import pcamv_loader
@@ -144,23 +178,27 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    import frame_parity
     workdir = tempfile.mkdtemp(prefix="pcamv_bench_%d_" % rank)
-    clip, dumpf, t_prep = prepare_inputs(pcamv, rank, workdir)
+    clip, dumpf = prepare_inputs(pcamv, rank, workdir)
     dump = pcamv.dumpfmt.Dump(dumpf)
-    calls, refine = dump.calls()
-    s = next(x for x in dump.slices() if x.with_planes and x.frame == BATCH_FRAME)
-    c = dump.cfg
-    sel = calls["frame"] == BATCH_FRAME
-    rc, rf = calls[sel], refine[sel]
-    abi_calls = pcamv.dumpfmt.calls_to_abi(rc, rf)
-    cand_per_step = int(rc["n_cand"].sum())
-    # integer-op count per step, reference-counted: SAD 2 ops/pixel, SATD 7 ops/pixel (SURVEY.md 8(d))
-    ops_per_step = 2.0 * float(rc["pix_sad"].sum()) + 7.0 * float(rc["pix_satd"].sum())
+    units = [u for u in dump.slice_units() if u["slice"].frame == BATCH_FRAME and u["slice"].with_planes]
+    assert [u["slice"].pass_ for u in units] == [1, 2], "dump does not hold both passes of frame %d" % BATCH_FRAME
+    s = units[0]["slice"]
 
-    ctx = pcamv.PcamvContext(s.width, s.lines_y, me_method=c["me_method"], me_range=c["me_range"], subpel_refine=c["subme"],
-                             chroma_me=c["chroma_me"], max_refs=c["refs"], mv_range=c["mv_range"], device=local_rank)
-    t = dump.cost_tables[s.qp]
-    ctx.set_qp_tables(s.qp, t["lambda"], t["cost_mv"], t["cost_ref"])
+    # reference-counted work of this frame: the per-pass counters of the two dumped passes
+    cnt = dump.counters()
+    assert len(cnt) == 2, "expected the counters of two passes, got %d" % len(cnt)
+    work = {k: cnt[0][k] + cnt[1][k] for k in ("sad", "satd", "ih_luma", "ih_chroma", "pix_sad", "pix_satd")}
+    cand_per_step = candidates_of(work)
+    # integer-op count per step, reference-counted: SAD 2 ops/pixel, SATD 7 ops/pixel (SURVEY.md 8(d))
+    ops_per_step = 2.0 * work["pix_sad"] + 7.0 * work["pix_satd"]
+
+    # ---- parity gate before any number ---------------------------------------------------------------------------
+    ctx = frame_parity.open_ctx(pcamv, dump, s, device=local_rank)
+    par = frame_parity.check_dump(pcamv, dump, units=units, ctx=ctx, keep_ctx=True)       # raises on the first mismatch
+
+    x = units[0]["ctx"]
     H, W = s.lines_y, s.width
     fy, fu, fv = (np.ascontiguousarray(s.fenc[0][:, :W]), np.ascontiguousarray(s.fenc[1][:, :W // 2]),
                   np.ascontiguousarray(s.fenc[2][:, :W // 2]))
@@ -168,14 +206,10 @@ def main():
     ry = np.ascontiguousarray(r["luma"][0][32:32 + H, 32:32 + W])
     ru = np.ascontiguousarray(r["u"][16:16 + H // 2, 16:16 + W // 2])
     rv = np.ascontiguousarray(r["v"][16:16 + H // 2, 16:16 + W // 2])
-
-    # ---- parity gate before any number: the batch must reproduce the reference bit-exactly ----------------
-    ctx.put_fenc(fy, fu, fv)
-    ctx.put_ref(0, r["poc"], ry, ru, rv)
-    res = ctx.me_search_batch(abi_calls)
-    ok = (res["mv"] == rc["mv"]).all(axis=1) & (res["cost"] == rc["cost"])
-    if not ok.all():
-        raise SystemExit("bench.py: parity gate failed: %d of %d searches differ from the reference" % ((~ok).sum(), len(ok)))
+    col = dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"])
+    e = units[0]["embd"]
+    pass1 = frame_parity.pass1_records(pcamv, e)
+    refs, pocs, cur_poc = list(range(x["n_ref"])), x["ref_poc"][:x["n_ref"]], x["cur_poc"]
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
@@ -184,28 +218,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ------------------------------------------------------------------------------
-    ctx.me_batch_upload(abi_calls)
-    for _ in range(args.warmup):
+    # ---- device-resident arm ---------------------------------------------------------------------------------------
+    ctx.put_fenc(fy, fu, fv)
+    ctx.put_ref(0, r["poc"], ry, ru, rv)
+    ctx.frame_upload(1, refs, pocs, cur_poc, cost_table=True, **col)
+    mbs1, _ = ctx.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
+    stale = mbs1["mv"][-1]
+    ctx.frame_upload(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=stale, **col)
+
+    def dev_step():
         flush.zero_(); torch.cuda.synchronize()
-        ctx.me_batch_run(1)
+        _, w1, ct = ctx.frame_run(1, 1, per_kernel=True)
+        flush.zero_(); torch.cuda.synchronize()
+        _, w2, _ = ctx.frame_run(2, 1, per_kernel=True)
+        return w1, ct, w2
+
+    for _ in range(args.warmup):
+        dev_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     launches0 = ctx.launch_count()
-    kernel_ms = []
+    k_ms = []
     for _ in range(args.steps):
-        flush.zero_(); torch.cuda.synchronize()
-        kernel_ms.append(ctx.me_batch_run(1))           # CUDA events on the context's stream
+        k_ms.append(dev_step())                  # CUDA events around each kernel on the context's stream
     barrier()
-    dev_s = float(np.sum(kernel_ms)) * 1e-3
+    k_ms = np.array(k_ms)
+    dev_s = float(k_ms.sum()) * 1e-3
     n_launch = ctx.launch_count() - launches0
 
-    # ---- end-to-end arm: host buffers in, host results out ----------------------------------------------------
+    # ---- end-to-end arm: host buffers in, host records out ------------------------------------------------------------
     def e2e_step():
         ctx.put_fenc(fy, fu, fv)
         ctx.put_ref(0, r["poc"], ry, ru, rv)
-        return ctx.me_search_batch(abi_calls)
+        m1, l1 = ctx.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
+        m2, l2 = ctx.analyse_p(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], **col)
+        return m1, l1, m2, l2
     for _ in range(args.warmup):
         e2e_step()
     barrier()
@@ -217,19 +265,19 @@ def main():
     barrier()
     clocks = sampler.result()
     n_launch_e2e = ctx.launch_count() - launches0 - n_launch
-    assert (out["mv"] == rc["mv"]).all()
-    h2d = fy.nbytes + fu.nbytes + fv.nbytes + ry.nbytes + ru.nbytes + rv.nbytes + abi_calls.nbytes
-    d2h = res.nbytes
+    n_mb = len(out[0])
+    h2d = 2 * (fy.nbytes + fu.nbytes + fv.nbytes) + 2 * 68 * n_mb + n_mb * pcamv.host.PASS1_MB_DTYPE.itemsize + len(e["filp"])
+    d2h = out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes
 
     int_peak = ctx.int_peak_gops()
 
-    # ---- aggregate over ranks (max time, summed work) ------------------------------------------------------------
+    # ---- aggregate over ranks (max time, summed work) ----------------------------------------------------------------
     tt = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
     ww = torch.tensor([float(cand_per_step)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-    dev_s_max, e2e_s_max = [float(x) for x in tt.tolist()]
+    dev_s_max, e2e_s_max = [float(v) for v in tt.tolist()]
     cand_all = float(ww.item())
 
     if rank == 0:
@@ -241,36 +289,43 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # algorithmic HBM bytes of one launch: fenc once, 4 luma + 2 chroma reference planes once, call records in, results out
+        ms_w1, ms_ct, ms_w2 = [float(v) for v in k_ms.mean(axis=0)]
+        kernels = {"k_analyse_p(pass1)": ms_w1, "k_cost_table": ms_ct, "k_analyse_p(pass2)": ms_w2}
+        dom = max(kernels, key=kernels.get)
+        # algorithmic HBM bytes of one launch of either kernel: fenc once, 4 luma + 2 chroma reference planes once,
+        # per-MB records in/out (DESIGN.md "HBM traffic")
         plane_y = ctx.plane_bytes(0); plane_c = ctx.plane_bytes(4)
-        alg_bytes = fy.nbytes + fu.nbytes + fv.nbytes + 4 * plane_y + 2 * plane_c + abi_calls.nbytes + res.nbytes
-        ms_launch = float(np.mean(kernel_ms))
-        achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
-        # CPU baseline on this box (rank 0 only, bounded sample: the same 3-frame clip)
-        st = cpu_reference_timing(pcamv, clip, workdir)
-        counts = json.load(open(os.path.join(workdir, "stats_count.json")))
-        cpu_v = (counts["sad"] + counts["satd"]) / st["t_me"] / 1e6
+        alg_bytes = fy.nbytes + fu.nbytes + fv.nbytes + 4 * plane_y + 2 * plane_c + n_mb * (128 + 48 * 16 + 68)
+        achieved = alg_bytes / (kernels[dom] * 1e-3) / 1e9
+        step_ms = ms_w1 + ms_ct + ms_w2
         line = {
-            "metric": metric_name(), "value": value, "unit": "Mcandidates/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": "Mcandidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "step": "all %d search/refine calls of one 1080p P-frame (both passes), stateless batch" % len(rc),
-                       "candidates_per_step": cand_per_step, "l2": "flushed between timed iterations (256 MiB write)",
-                       "parity_gate": "passed (%d/%d searches bit-exact vs reference)" % (int(ok.sum()), len(ok))},
+            "config": {"workload": WORKLOAD,
+                       "step": "one 1080p P frame through the frame seam: wavefront analysis pass 1 + candidate-MV cost table + "
+                               "wavefront analysis pass 2 (%d searches/refines, %d cost-table entries)" % (par["calls"], par["ih"]),
+                       "candidates_per_step": int(cand_per_step), "l2": "flushed before every timed kernel sequence (256 MiB write)",
+                       "parity_gate": "passed: %d searches, %d macroblock decisions, %d cost-table entries bit-exact vs reference"
+                                      % (par["calls"], par["mbs"], par["ih"])},
+            "analysed_p_frames_per_sec": world * args.steps / dev_s_max,
+            "kernel_ms": kernels,
             "e2e": {"value": e2e_v, "unit": "Mcandidates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s_max / args.steps * 1e3},
+                    "ms_per_step": e2e_s_max / args.steps * 1e3, "analysed_p_frames_per_sec": world * args.steps / e2e_s_max},
             "gpu_launches": int(n_launch + n_launch_e2e),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "k_search_batch", "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
-                         "note": "the search kernel is integer-issue/latency bound, not HBM bound (SURVEY.md 8(d)); see int_issue"},
-            "int_issue": {"achieved_gops": ops_per_step / (ms_launch * 1e-3) / 1e9, "peak_gops": int_peak,
-                          "frac": ops_per_step / (ms_launch * 1e-3) / 1e9 / int_peak,
-                          "ops": "reference-counted: 2/pixel SAD, 7/pixel SATD", "peak_source": "pcamv_int_peak microbenchmark on this box"},
-            "cpu_baseline": {"value": cpu_v, "unit": "Mcandidates/s", "cores": 1, "kind": "reference",
-                             "sample": "oracle/_ref/x264_dump, %d frames 1080p, time inside x264_me_search_ref + x264_me_refine_qpel (%.2f s)"
-                                       % (CLIP_FRAMES, st["t_me"])},
+                         "traffic": None, "kernel": dom,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "note": "the analysis kernels are integer-issue / dependency-latency bound, not HBM bound (SURVEY.md 8(d)); "
+                                 "see int_issue"},
+            "int_issue": {"achieved_gops": ops_per_step / (step_ms * 1e-3) / 1e9, "peak_gops": int_peak,
+                          "frac": ops_per_step / (step_ms * 1e-3) / 1e9 / int_peak,
+                          "ops": "reference-counted: 2/pixel SAD, 7/pixel SATD over the whole step",
+                          "peak_source": "pcamv_int_peak microbenchmark on this box"},
         }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block(pcamv, clip, workdir)
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PCAMV_ABI_VERSION 2
+#define PCAMV_ABI_VERSION 3
 #define PCAMV_MAX_REFS 16
 #define PCAMV_MAX_MVC 10
 
@@ -217,11 +217,16 @@ int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs,
 /* Benchmark / pipelining support: the three stages of pcamv_analyse_p separately.  _upload stages the frame
  * inputs of in->pass in HBM (one set per pass is kept, so pass 1 and pass 2 of a frame can both be resident);
  * _run launches the wavefront (+ cost table) of `pass` (-1: the last uploaded) `iters` times and returns the mean
- * device time of one analysis in milliseconds (CUDA events on the context's stream); _download copies the
- * results of the last run back. */
+ * device time of one analysis in milliseconds (CUDA events on the context's stream) and, when ms_kernels is not
+ * NULL, the mean duration of its two kernels (ms_kernels[0] wavefront analysis, [1] cost table; events recorded
+ * around each launch on the same stream); _download copies the results of the last run back. */
 int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in);
-int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_per_frame);
+int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_per_frame, float *ms_kernels);
 int pcamv_frame_download(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log);
+
+/* Profiling aid: with enable != 0 the next wavefront launches record the device globaltimer (ns) at the start and end
+ * of every macroblock; out (may be NULL) receives the [n_mb][2] records of the last traced launch. */
+int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out);
 
 /* Measured integer-pipe issue peak of the device, in giga lane-operations/s: a microbenchmark of the
  * VABSDIFF4 / IADD3 / LOP3 mix the SAD and SATD loops consist of.  Roofline denominator for the search kernels. */

@@ -42,6 +42,8 @@ static uint64_t g_pix_sad, g_pix_satd;  /* pixel-normalised (w*h) */
 static double g_t_analyse_p, g_t_me, g_t_ih, g_t_total0;
 static uint64_t g_cnt_ih_calls;
 static struct timespec g_ts_an, g_ts_me, g_ts_ih;
+static uint64_t g_slice_c0[9];      /* counters at the start of the current slice pass */
+static double g_slice_t0[3];
 
 static double now_s( void )
 {
@@ -184,6 +186,13 @@ void pcamv_hook_slice_begin( x264_t *h )
     g_pass = !h->info.embed_flag ? 0 : h->info.firstTime ? 1 : 2;
     if( g_pslice && g_pass != 2 )
         g_cnt_pframes++;
+    {
+        uint64_t c[9] = { g_cnt_sad, g_cnt_satd, g_cnt_ih_luma, g_cnt_ih_chroma, g_pix_sad, g_pix_satd,
+                          g_cnt_search, g_cnt_refine, g_cnt_ih_calls };
+        double t[3] = { g_t_me, g_t_ih, g_t_analyse_p };
+        memcpy( g_slice_c0, c, sizeof(c) );
+        memcpy( g_slice_t0, t, sizeof(t) );
+    }
     if( !dump_on( h ) )
         return;
     {
@@ -281,12 +290,14 @@ void pcamv_hook_slice_end( x264_t *h )
         fwrite( x264_cost_ref[h->sh.i_qp], 2, 3*33, g_dump );
     }
     {
-        /* 'CNT0': cumulative counters at the end of this slice pass (uint64 each): sad, satd, ih_luma, ih_chroma,
-         * pix_sad, pix_satd, searches, refines, ih_calls; then double t_me, t_ih, t_analyse_p.  Per-pass work =
-         * difference of consecutive records. */
+        /* 'CNT0': work of THIS slice pass (uint64 each): sad, satd, ih_luma, ih_chroma, pix_sad, pix_satd, searches,
+         * refines, ih_calls; then double t_me, t_ih, t_analyse_p (seconds spent in this pass). */
         uint64_t c[9] = { g_cnt_sad, g_cnt_satd, g_cnt_ih_luma, g_cnt_ih_chroma, g_pix_sad, g_pix_satd,
                           g_cnt_search, g_cnt_refine, g_cnt_ih_calls };
         double t[3] = { g_t_me, g_t_ih, g_t_analyse_p };
+        int k;
+        for( k = 0; k < 9; k++ ) c[k] -= g_slice_c0[k];
+        for( k = 0; k < 3; k++ ) t[k] -= g_slice_t0[k];
         rec_begin( "CNT0", sizeof(c) + sizeof(t) );
         fwrite( c, 1, sizeof(c), g_dump );
         fwrite( t, 1, sizeof(t), g_dump );

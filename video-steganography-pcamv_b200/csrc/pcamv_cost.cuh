@@ -10,14 +10,6 @@
 
 namespace pcamv {
 
-#if defined(PCAMV_EMU)
-  #define PCAMV_COEF_SLOTS 24
-  #define PCAMV_SLOT(it) (it)
-#else
-  #define PCAMV_COEF_SLOTS 1
-  #define PCAMV_SLOT(it) 0
-#endif
-
 // x264_macroblock_encode for an inter MB whose partition k_over uses MV (omx, omy) instead of its own.
 // Leaves the reconstruction in c.w.pred_y / pred_u / pred_v.
 PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx, int omy)
@@ -31,55 +23,22 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
         const int my = clip3(p == k_over ? omy : pi.mv[1], c.mv_min[1], c.mv_max[1]);
         mc_rect(c, c.fp.ref_slot[pi.ref], pi.xoff, pi.yoff, pix_w(pi.i_pixel), pix_h(pi.i_pixel), mx, my);
     }
-    int coef[PCAMV_COEF_SLOTS][16];
-    // scratch layout: [0..23] decimate score, bits: score | nz << 8 ; chroma DC terms in dcs
+    // scratch layout: [0..23] decimate score | nz << 8 per block; raw chroma DC terms behind them
     int *sc = c.w.scratch;
     int16_t *dcs = (int16_t *)(c.w.scratch + 24);           // 8 x int16
     PCAMV_FOR_ITEMS(it, 24)
-    {
-        int *co = coef[PCAMV_SLOT(it)];
-        int d[16];
-        if (it < 16)
-        {
-            const int bx = (it & 1) | ((it >> 1) & 2), by = ((it >> 1) & 1) | ((it >> 2) & 2);
-            load_residual(c.w.fenc_y + 64 * by + 4 * bx, 16, c.w.pred_y + 64 * by + 4 * bx, 16, d);
-            dct4x4(d, co);
-            const int nz = quant4x4(co, t.quant4_mf[0], t.quant4_bias[0]);
-            int score = 0;
-            if (nz)
-            {
-                score = decimate_score(co, 0);
-                dequant4x4(co, t.dequant4_mf[0], t.qp);
-            }
-            sc[it] = score | (nz << 8);
-        }
-        else
-        {
-            const int pl = (it - 16) >> 2, blk = (it - 16) & 3;
-            const uint8_t *fe = pl ? c.w.fenc_v : c.w.fenc_u, *pr = pl ? c.w.pred_v : c.w.pred_u;
-            load_residual(fe + 32 * (blk >> 1) + 4 * (blk & 1), 8, pr + 32 * (blk >> 1) + 4 * (blk & 1), 8, d);
-            dct4x4(d, co);
-            dcs[it - 16] = (int16_t)co[0];
-            co[0] = 0;
-            const int nz = quant4x4(co, t.quant4_mf[1], t.quant4_bias[1]);
-            int score = 0;
-            if (nz)
-            {
-                score = decimate_score(co, 1);
-                dequant4x4(co, t.dequant4_mf[1], t.chroma_qp);
-            }
-            sc[it] = score | (nz << 8);
-        }
-    }
+        sc[it] = quant_block(c, it, dcs);
     team_sync();
 
     // ---- decisions (uniform) -------------------------------------------------------------------------------
     int add_luma8 = 0;          // bit i: 8x8 block i gets its residual added
     {
         int s8[4], any8[4], mb = 0;
+#pragma unroll
         for (int i = 0; i < 4; i++)
         {
             s8[i] = 0; any8[i] = 0;
+#pragma unroll
             for (int j = 0; j < 4; j++)
             {
                 const int v = sc[4 * i + j];
@@ -89,6 +48,7 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
             }
             mb += s8[i];
         }
+#pragma unroll
         for (int i = 0; i < 4; i++)
         {
             if (b_decimate) { if (mb >= 6 && s8[i] >= 4) add_luma8 |= 1 << i; }
@@ -97,9 +57,11 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
     }
     int chroma_mode[2];         // 0 = nothing, 1 = DC only, 2 = full
     int dcq[2][4];              // dequantised DC term per 4x4 block
+#pragma unroll
     for (int pl = 0; pl < 2; pl++)
     {
         int nz_ac = 0, score = 0;
+#pragma unroll
         for (int j = 0; j < 4; j++) { const int v = sc[16 + 4 * pl + j]; nz_ac |= v >> 8; score += v & 0xff; }
         const int b0 = dcs[4 * pl], b1 = dcs[4 * pl + 1], b2 = dcs[4 * pl + 2], b3 = dcs[4 * pl + 3];
         const int D0 = b0 + b1, D1 = b2 + b3, D2 = b0 - b1, D3 = b2 - b3;
@@ -125,81 +87,85 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
     // ---- reconstruction --------------------------------------------------------------------------------------
     PCAMV_FOR_ITEMS(it, 24)
     {
-        int *co = coef[PCAMV_SLOT(it)];
-        int r[16];
         if (it < 16)
         {
-            if (!((add_luma8 >> (it >> 2)) & 1)) continue;
-            const int bx = (it & 1) | ((it >> 1) & 2), by = ((it >> 1) & 1) | ((it >> 2) & 2);
-            idct4x4(co, r);
-            add_residual(c.w.pred_y + 64 * by + 4 * bx, 16, r);
+            // a block whose quantised coefficients are all zero adds nothing (its w.coef entry is stale)
+            if (((add_luma8 >> (it >> 2)) & 1) && (sc[it] >> 8))
+                recon_block(c, it, 0, 0);
         }
         else
         {
             const int pl = (it - 16) >> 2, blk = (it - 16) & 3;
-            uint8_t *pr = (pl ? c.w.pred_v : c.w.pred_u) + 32 * (blk >> 1) + 4 * (blk & 1);
-            if (chroma_mode[pl] == 0) continue;
-            if (chroma_mode[pl] == 1)
+            const int mode = pl ? chroma_mode[1] : chroma_mode[0];
+            const int dc = pl ? (blk == 0 ? dcq[1][0] : blk == 1 ? dcq[1][1] : blk == 2 ? dcq[1][2] : dcq[1][3])
+                              : (blk == 0 ? dcq[0][0] : blk == 1 ? dcq[0][1] : blk == 2 ? dcq[0][2] : dcq[0][3]);
+            if (mode == 1)
+                recon_block(c, it, 1, dc);
+            else if (mode == 2)
             {
-                const int dc = (int16_t)((dcq[pl][blk] + 32) >> 6);
-                for (int k = 0; k < 16; k++) r[k] = dc;
+                // AC part all zero: only the DC term contributes, through the full IDCT path
+                if (!(sc[it] >> 8))
+                {
+                    int16_t *co = c.w.coef[it];
+                    for (int i = 0; i < 16; i++) co[i] = 0;
+                }
+                recon_block(c, it, 2, dc);
             }
-            else
-            {
-                co[0] = dcq[pl][blk];
-                idct4x4(co, r);
-            }
-            add_residual(pr, 8, r);
         }
     }
     team_sync();
 }
 
-// costs of the 9-point ring around (cx, cy) for partition k against the current reconstruction
-PCAMV_FN void ring_costs(MbCtx &c, const MbResult &res, int k, int cx, int cy, int out[9])
-{
-    const PartInfo &pi = res.part[k];
-    MeBlock b;
-    setup_block(c, b, pi.ref, pi.i_pixel, pi.xoff, pi.yoff);
-    block_set_mvp(b, c.env, pi.mvp[0], pi.mvp[1]);
-    const int rx[9] = { 0, 1, 0, -1, -1, -1, 1, 1, 0 }, ry[9] = { -1, 0, 1, 0, -1, 1, -1, 1, 0 };
-    int qx[9], qy[9];
-    for (int i = 0; i < 9; i++) { qx[i] = cx + rx[i]; qy[i] = cy + ry[i]; }
-    const int chroma = c.env.chroma_me && pi.i_pixel <= PIX_8x8;
-    // the block being compared is the RECONSTRUCTION of this partition, not the source
-    b.fenc = c.w.pred_y + pi.yoff * 16 + pi.xoff;
-    b.fenc_u = c.w.pred_u + (pi.yoff >> 1) * 8 + (pi.xoff >> 1);
-    b.fenc_v = c.w.pred_v + (pi.yoff >> 1) * 8 + (pi.xoff >> 1);
-    satd_cands(b, 9, qx, qy, chroma, out, b.fenc, b.fenc_u, b.fenc_v, c.env.mbcmp_satd);
-    for (int i = 0; i < 9; i++) out[i] += b.cost_mvx[qx[i]] + b.cost_mvy[qy[i]];
-}
+// dx / dy of replacement candidate ii = 0..11 (four at distance 1, eight knight moves), one signed nibble each:
+//   dx = 0 1 0 -1 -2 -1 1 2 2 1 -1 -2      dy = -1 0 1 0 1 2 2 1 -1 -2 -2 -1
+PCAMV_DEV int cand_dx(int ii) { return (int)(((long long)(0xEF1221FEF010ull << (60 - 4 * ii))) >> 60); }
+PCAMV_DEV int cand_dy(int ii) { return (int)(((long long)(0xFEEF1221010Full << (60 - 4 * ii))) >> 60); }
 
 // x264_ih_get_mv_cost for partition k of macroblock `res`; returns cost_opt, writes the chosen delta
 PCAMV_FN int ih_get_mv_cost(MbCtx &c, const MbResult &res, int k, int &m_x, int &m_y)
 {
-    const int dmx[12] = { 0, 1, 0, -1, -2, -1, 1, 2, 2, 1, -1, -2 }, dmy[12] = { -1, 0, 1, 0, 1, 2, 2, 1, -1, -2, -2, -1 };
-    const int rx[4] = { 0, 1, 0, -1 }, ry[4] = { -1, 0, 1, 0 };
-    const int bmx = res.part[k].mv[0], bmy = res.part[k].mv[1];
-    int c1[9];
-    encode_mb_inter(c, res, -1, 0, 0);
-    ring_costs(c, res, k, bmx, bmy, c1);
-    int min_cost = PCAMV_COST_MAX;
-    for (int i = 0; i < 9; i++) if (c1[i] < min_cost) min_cost = c1[i];
-    const int orig = c1[8];
-    const int non_opt = min_cost < orig;        // the original vector is not a local optimum of its ring
+    const PartInfo &pi = res.part[k];
+    const int bmx = pi.mv[0], bmy = pi.mv[1];
+    MeBlock b;
+    setup_block(c, b, pi.ref, pi.i_pixel, pi.xoff, pi.yoff);
+    block_set_mvp(b, c.env, pi.mvp[0], pi.mvp[1]);
+    // the block being compared is the RECONSTRUCTION of this partition, not the source
+    b.fenc = c.w.pred_y + pi.yoff * 16 + pi.xoff;
+    b.fenc_u = c.w.pred_u + (pi.yoff >> 1) * 8 + (pi.xoff >> 1);
+    b.fenc_v = c.w.pred_v + (pi.yoff >> 1) * 8 + (pi.xoff >> 1);
+    const int kind = !c.env.mbcmp_satd ? COST_SAD : (c.env.chroma_me && pi.i_pixel <= PIX_8x8) ? COST_SATD_CHROMA : COST_SATD;
+
+    int orig = 0, non_opt = 0, fb_cost = PCAMV_COST_MAX, fb_idx = -1;
     int best = PCAMV_COST_MAX, ii_best = -1;
     m_x = 0; m_y = 0;
-    for (int ii = 0; ii < 12; ii++)
+    // ii = -1: the original vector; ii = 0..11: the replacement candidates (the first four decide whether the rest run)
+#pragma unroll 1
+    for (int ii = -1; ii < 12; ii++)
     {
-        const int cx = bmx + dmx[ii], cy = bmy + dmy[ii];
-        int c2[9];
-        encode_mb_inter(c, res, k, cx, cy);
-        ring_costs(c, res, k, cx, cy, c2);
-        int m1 = PCAMV_COST_MAX;
-        for (int i = 0; i < 9; i++) if (c2[i] < m1) m1 = c2[i];
-        const int cost = c2[8];
-        const int qualifies = non_opt ? (m1 != cost) : (m1 == cost);
-        if (qualifies && cost < best) { best = cost; m_x = dmx[ii]; m_y = dmy[ii]; ii_best = ii; }
+        const int cx = bmx + (ii < 0 ? 0 : cand_dx(ii)), cy = bmy + (ii < 0 ? 0 : cand_dy(ii));
+        encode_mb_inter(c, res, ii < 0 ? -1 : k, cx, cy);
+        // 9-point ring around (cx, cy) against the reconstruction: up, right, down, left, then the diagonals, then the centre
+        int r[4];
+        eval4(b, kind, 4, pk(cx, cy - 1), pk(cx + 1, cy), pk(cx, cy + 1), pk(cx - 1, cy), r);
+        int min9 = imin(imin(r[0], r[1]), imin(r[2], r[3]));
+        if (ii < 0)
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (r[i] < fb_cost) { fb_cost = r[i]; fb_idx = i; }
+        }
+        eval4(b, kind, 4, pk(cx - 1, cy - 1), pk(cx - 1, cy + 1), pk(cx + 1, cy - 1), pk(cx + 1, cy + 1), r);
+        min9 = imin(min9, imin(imin(r[0], r[1]), imin(r[2], r[3])));
+        const int centre = eval1(b, kind, pk(cx, cy));
+        min9 = imin(min9, centre);
+        if (ii < 0)
+        {
+            orig = centre;
+            non_opt = min9 < orig;          // the original vector is not a local optimum of its ring
+            continue;
+        }
+        const int qualifies = non_opt ? (min9 != centre) : (min9 == centre);
+        if (qualifies && centre < best) { best = centre; m_x = cand_dx(ii); m_y = cand_dy(ii); ii_best = ii; }
         if (ii == 3 && best != PCAMV_COST_MAX)
             break;
     }
@@ -208,8 +174,7 @@ PCAMV_FN int ih_get_mv_cost(MbCtx &c, const MbResult &res, int k, int &m_x, int 
     {
         b_error_pos = 1; b_1_neighbor = 1;
         m_x = 0; m_y = 0;
-        for (int i = 0; i < 4; i++)
-            if (c1[i] < best) { best = c1[i]; m_x = rx[i]; m_y = ry[i]; }
+        if (fb_idx >= 0) { best = fb_cost; m_x = cand_dx(fb_idx); m_y = cand_dy(fb_idx); }
     }
     else
         b_1_neighbor = ii_best <= 3;

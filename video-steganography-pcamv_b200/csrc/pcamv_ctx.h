@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 #include "pcamv_device.h"
 #include "pcamv_frame_types.h"
 
@@ -11,6 +12,7 @@ struct pcamv_ctx
     pcamv::DevFrameCtx fc;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;          // per-kernel timing of pcamv_frame_run
     std::string err;
     bool failed = false;
     long long launches = 0;
@@ -33,6 +35,8 @@ struct pcamv_ctx
     pcamv::ForcedMb *d_forced = nullptr;       // pass-2 forced decisions
     pcamv::LogEntry *d_log = nullptr;          // [n_mb][PCAMV_LOG_MAX]
     pcamv::MbResult *d_mb_results = nullptr;   // [n_mb]
+    unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
+    bool trace_on = false;
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter
     uint8_t *h_frame = nullptr; size_t h_frame_bytes = 0;             // pinned staging for frame inputs / outputs
     pcamv::FrameParams fp[3] = {};             // parameters of the last uploaded frame, per pass (0 / 1 / 2)

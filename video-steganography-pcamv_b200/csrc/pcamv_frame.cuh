@@ -29,6 +29,7 @@ struct alignas(16) MbWork
     uint8_t fenc_y[256], fenc_u[64], fenc_v[64];
     uint8_t pred_y[256], pred_u[64], pred_v[64];     // MC / reconstruction staging
     int32_t scratch[32];
+    int16_t coef[24][16];    // per 4x4 block (16 luma in block_idx order, 4 U, 4 V): quantised / dequantised coefficients
 };
 
 // Loads of per-frame motion state written by OTHER macroblocks of the running wavefront (possibly on another SM):
@@ -272,22 +273,22 @@ PCAMV_DEV int quant_one(int v, int mf, int bias)
 {
     return (int16_t)(v > 0 ? ((bias + v) * mf) >> 16 : -(((bias - v) * mf) >> 16));
 }
-// decimation score of a quantised 4x4 block; first = 0 (all 16 coefficients) or 1 (AC only)
-PCAMV_DEV int decimate_score(const int coef[16], int first)
+// decimation score of a quantised 4x4 block held in memory; first = 0 (all 16 coefficients) or 1 (AC only)
+PCAMV_DEV int decimate_score(const int16_t *coef, int first)
 {
-    // coefficient i of the frame zigzag scan lives at dct[x][y] (flattened 4*x+y) of these positions
-    const int zz[16] = { 0, 4, 1, 2, 5, 8, 12, 9, 6, 3, 7, 10, 13, 14, 11, 15 };
-    const int tab[16] = { 3, 2, 2, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    // coefficient i of the frame zigzag scan lives at dct[x][y] (flattened 4*x+y): 0 4 1 2 5 8 12 9 6 3 7 10 13 14 11 15
+    const unsigned long long zz = 0xfbeda7369c852140ull;
     int idx = 15;
-    while (idx >= first && coef[zz[idx]] == 0) idx--;
+    while (idx >= first && coef[(zz >> (4 * idx)) & 15] == 0) idx--;
     int score = 0;
     while (idx >= first)
     {
-        const int v = coef[zz[idx--]];
+        const int v = coef[(zz >> (4 * idx)) & 15];
+        idx--;
         if ((unsigned)(v + 1) > 2) return 9;
         int run = 0;
-        while (idx >= first && coef[zz[idx]] == 0) { idx--; run++; }
-        score += tab[run];
+        while (idx >= first && coef[(zz >> (4 * idx)) & 15] == 0) { idx--; run++; }
+        score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;        // x264_decimate_table4
     }
     return score;
 }
@@ -409,6 +410,81 @@ PCAMV_FN void mc_rect(MbCtx &c, int ref_slot, int x0, int y0, int wd, int ht, in
     team_sync();
 }
 
+// ---- transform / quantisation of one 4x4 block of the macroblock (the one expanded copy of the 16-coefficient code) ----
+// Block `it`: 0..15 luma (block_idx order), 16..19 U, 20..23 V.  Residual = fenc - staged prediction; DCT; for chroma
+// the DC term is set aside (raw, in dcs[]) and zeroed; quantise; decimate score; dequantise.  The coefficients end up
+// in w.coef[it] (dequantised when non-zero).  Returns score | nz << 8.
+// (reference encoder/macroblock.c:605-755 luma, :277-372 chroma, :809-895 probe; common/dct.c:122-162; quant.c:33-75,203-252)
+PCAMV_FN int quant_block(MbCtx &c, int it, int16_t *dcs)
+{
+    const DevTables &t = c.fc.tab;
+    const int ch = it >= 16;
+    int d[16], co[16];
+    if (!ch)
+    {
+        const int bx = (it & 1) | ((it >> 1) & 2), by = ((it >> 1) & 1) | ((it >> 2) & 2);
+        load_residual(c.w.fenc_y + 64 * by + 4 * bx, 16, c.w.pred_y + 64 * by + 4 * bx, 16, d);
+    }
+    else
+    {
+        const int pl = (it - 16) >> 2, blk = (it - 16) & 3;
+        const uint8_t *fe = pl ? c.w.fenc_v : c.w.fenc_u, *pr = pl ? c.w.pred_v : c.w.pred_u;
+        load_residual(fe + 32 * (blk >> 1) + 4 * (blk & 1), 8, pr + 32 * (blk >> 1) + 4 * (blk & 1), 8, d);
+    }
+    dct4x4(d, co);
+    if (ch)
+    {
+        dcs[it - 16] = (int16_t)co[0];
+        co[0] = 0;
+    }
+    const int nz = quant4x4(co, t.quant4_mf[ch], t.quant4_bias[ch]);
+    int16_t *out = c.w.coef[it];
+    int score = 0;
+    if (nz)
+    {
+#pragma unroll
+        for (int i = 0; i < 16; i++) out[i] = (int16_t)co[i];
+        score = decimate_score(out, ch);
+        dequant4x4(co, t.dequant4_mf[ch], ch ? t.chroma_qp : t.qp);
+#pragma unroll
+        for (int i = 0; i < 16; i++) out[i] = (int16_t)co[i];
+    }
+    return score | (nz << 8);
+}
+
+// Reconstruction of block `it` into the staged prediction: mode 0 = IDCT of w.coef[it]; 1 = chroma DC only;
+// 2 = chroma IDCT with the dequantised DC term `dc` put back  (common/dct.c:174-262,364-384)
+PCAMV_FN void recon_block(MbCtx &c, int it, int mode, int dc)
+{
+    int co[16], r[16];
+    uint8_t *pr; int ps;
+    if (it < 16)
+    {
+        const int bx = (it & 1) | ((it >> 1) & 2), by = ((it >> 1) & 1) | ((it >> 2) & 2);
+        pr = c.w.pred_y + 64 * by + 4 * bx; ps = 16;
+    }
+    else
+    {
+        const int pl = (it - 16) >> 2, blk = (it - 16) & 3;
+        pr = (pl ? c.w.pred_v : c.w.pred_u) + 32 * (blk >> 1) + 4 * (blk & 1); ps = 8;
+    }
+    if (mode == 1)
+    {
+        const int v = (int16_t)((dc + 32) >> 6);
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = v;
+    }
+    else
+    {
+        const int16_t *in = c.w.coef[it];
+#pragma unroll
+        for (int i = 0; i < 16; i++) co[i] = in[i];
+        if (mode == 2) co[0] = dc;
+        idct4x4(co, r);
+    }
+    add_residual(pr, ps, r);
+}
+
 // ---- P_SKIP probe -----------------------------------------------------------------------------------------
 PCAMV_FN int probe_pskip(MbCtx &c)
 {
@@ -416,23 +492,20 @@ PCAMV_FN int probe_pskip(MbCtx &c)
     const int mvy = clip3(c.pskip_mv[1], c.mv_min[1], c.mv_max[1]);
     mc_rect(c, c.fp.ref_slot[0], 0, 0, 16, 16, mvx, mvy);
     const DevTables &t = c.fc.tab;
-    int fail = 0;
+    int16_t *dcs = (int16_t *)(c.w.scratch + 24);           // 8 x int16: raw chroma DC terms
     // luma: 16 blocks, total decimate score must stay below 6
     int score = 0;
     PCAMV_FOR_ITEMS(blk, 16)
     {
-        const int bx = (blk & 1) | ((blk >> 1) & 2), by = ((blk >> 1) & 1) | ((blk >> 2) & 2);
-        int d[16], co[16];
-        load_residual(c.w.fenc_y + 64 * by + 4 * bx, 16, c.w.pred_y + 64 * by + 4 * bx, 16, d);
-        dct4x4(d, co);
-        if (quant4x4(co, t.quant4_mf[0], t.quant4_bias[0]))
-            score += decimate_score(co, 0);
+        const int v = quant_block(c, blk, dcs);
+        if (v >> 8) score += v & 0xff;
     }
     score = team_sum(score);
-    if (score >= 6) fail = 1;
+    if (score >= 6)
+        return 0;
     // chroma: SSD gate, then DC must quantise to zero and the AC decimate score must stay below 7, per plane
     const int thresh = (t.lambda2_chroma + 32) >> 6;
-    for (int pl = 0; pl < 2 && !fail; pl++)
+    for (int pl = 0; pl < 2; pl++)
     {
         const uint8_t *fe = pl ? c.w.fenc_v : c.w.fenc_u, *pr = pl ? c.w.pred_v : c.w.pred_u;
         int ssd = 0;
@@ -443,32 +516,25 @@ PCAMV_FN int probe_pskip(MbCtx &c)
         }
         ssd = team_sum(ssd);
         if (ssd < thresh) continue;
-        int dcv = 0, sc = 0;
-        int dcs[4] = { 0, 0, 0, 0 };
+        int sc = 0;
         PCAMV_FOR_ITEMS(blk, 4)
         {
-            int d[16], co[16];
-            load_residual(fe + 32 * (blk >> 1) + 4 * (blk & 1), 8, pr + 32 * (blk >> 1) + 4 * (blk & 1), 8, d);
-            dct4x4(d, co);
-            dcv = co[0];
-            dcs[blk] = co[0];
-            co[0] = 0;
-            if (quant4x4(co, t.quant4_mf[1], t.quant4_bias[1]))
-                sc += decimate_score(co, 1);
+            const int v = quant_block(c, 16 + 4 * pl + blk, dcs);
+            if (v >> 8) sc += v & 0xff;
         }
-#if !defined(PCAMV_EMU)
-        for (int k = 0; k < 4; k++) dcs[k] = lane_bcast(dcv, k);     // lane k transformed block k
-#endif
-        (void)dcv;
-        const int d0 = dcs[0] + dcs[1], d1 = dcs[2] + dcs[3], d2 = dcs[0] - dcs[1], d3 = dcs[2] - dcs[3];
+        team_sync();
+        const int b0 = dcs[4 * pl], b1 = dcs[4 * pl + 1], b2 = dcs[4 * pl + 2], b3 = dcs[4 * pl + 3];
+        const int d0 = b0 + b1, d1 = b2 + b3, d2 = b0 - b1, d3 = b2 - b3;
         const int mf = t.quant4_mf[1][0] >> 1, bias = t.quant4_bias[1][0] << 1;
         if (quant_one((int16_t)(d0 + d1), mf, bias) | quant_one((int16_t)(d2 + d3), mf, bias) |
             quant_one((int16_t)(d0 - d1), mf, bias) | quant_one((int16_t)(d2 - d3), mf, bias))
-        { fail = 1; break; }
+            return 0;
         sc = team_sum(sc);
-        if (sc >= 7) { fail = 1; break; }
+        if (sc >= 7)
+            return 0;
+        team_sync();
     }
-    return !fail;
+    return 1;
 }
 
 // =======================================================================================================

@@ -39,6 +39,7 @@ static int ensure_frame_buffers(pcamv_ctx *ctx)
     CK(cudaMalloc(&ctx->d_forced, n_mb * sizeof(ForcedMb)));
     CK(cudaMalloc(&ctx->d_mb_results, n_mb * sizeof(MbResult)));
     CK(cudaMalloc(&ctx->d_progress, (fc.mb_h + 1) * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_trace, 2 * n_mb * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ctx->fa.type, 0, n_mb, ctx->stream));
     CK(cudaMemsetAsync(ctx->fa.ref8, 0, 4 * n_mb, ctx->stream));
     CK(cudaMemsetAsync(ctx->fa.mv4, 0, 16 * n_mb * sizeof(uint32_t), ctx->stream));
@@ -116,41 +117,64 @@ extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
     fp.cur = ctx->fa;
     fp.log = ctx->d_log; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
     CK(cudaStreamSynchronize(ctx->stream));        // the caller may reuse its buffers; pinned staging is free again
-    ctx->frame_cost_table = in->pass == 1 && in->cost_table;
+    if (in->pass == 1) ctx->frame_cost_table = in->cost_table != 0;
     ctx->frame_ready[in->pass] = true;
     ctx->frame_last = in->pass;
     return 0;
 }
 
-static int launch_frame(pcamv_ctx *ctx, int pass)
+static int launch_frame(pcamv_ctx *ctx, int pass, cudaEvent_t *ev = nullptr)
 {
     const DevFrameCtx &fc = ctx->fc;
+    ctx->fp[pass].trace = ctx->trace_on ? ctx->d_trace : nullptr;
     CK(cudaMemsetAsync(ctx->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
+    if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
     launch_analyse_p(fc, ctx->fp[pass], ctx->d_progress + fc.mb_h, fc.mb_h, ctx->stream);
     ctx->launches += 1;
+    if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
     if (pass == 1 && ctx->frame_cost_table)
     {
         launch_cost_table(fc, ctx->fp[pass], fc.mb_w * fc.mb_h, ctx->stream);
         ctx->launches += 1;
     }
+    if (ev) CK(cudaEventRecord(ev[2], ctx->stream));
     CK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_per_frame)
+extern "C" int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_per_frame, float *ms_kernels)
 {
     GUARD();
     if (pass < 0) pass = ctx->frame_last;
     if (iters <= 0 || pass < 0 || pass > 2 || !ctx->frame_ready[pass])
         return ctx_fail(ctx, "pcamv_frame_run: no frame uploaded for that pass", cudaSuccess);
+    if (ms_kernels)
+        while ((int)ctx->ev_pool.size() < 3 * iters)
+        {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ctx->ev_pool.push_back(e);
+        }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int i = 0; i < iters; i++)
-        if (launch_frame(ctx, pass)) return -1;
+        if (launch_frame(ctx, pass, ms_kernels ? ctx->ev_pool.data() + 3 * i : nullptr)) return -1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (ms_per_frame) *ms_per_frame = ms / iters;
+    if (ms_kernels)
+    {
+        double a = 0, b = 0;
+        for (int i = 0; i < iters; i++)
+        {
+            float t0 = 0, t1 = 0;
+            CK(cudaEventElapsedTime(&t0, ctx->ev_pool[3 * i], ctx->ev_pool[3 * i + 1]));
+            CK(cudaEventElapsedTime(&t1, ctx->ev_pool[3 * i + 1], ctx->ev_pool[3 * i + 2]));
+            a += t0; b += t1;
+        }
+        ms_kernels[0] = (float)(a / iters); ms_kernels[1] = (float)(b / iters);
+    }
     return 0;
 }
 
@@ -176,4 +200,18 @@ extern "C" int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_m
     if (pcamv_frame_upload(ctx, in)) return -1;
     if (launch_frame(ctx, in->pass)) return -1;
     return pcamv_frame_download(ctx, mbs, log);
+}
+
+extern "C" int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out)
+{
+    GUARD();
+    if (ensure_frame_buffers(ctx)) return -1;
+    if (out)
+    {
+        const size_t n_mb = (size_t)ctx->fc.mb_w * ctx->fc.mb_h;
+        CK(cudaMemcpyAsync(out, ctx->d_trace, 2 * n_mb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->trace_on = enable != 0;
+    return 0;
 }

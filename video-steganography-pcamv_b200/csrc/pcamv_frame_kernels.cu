@@ -30,6 +30,13 @@ __device__ __forceinline__ void st_release(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // source pixels of one macroblock -> team scratch (Y 16x16 stride 16, U/V 8x8 stride 8)
 __device__ __forceinline__ void stage_fenc(const DevFrameCtx &fc, int mb_x, int mb_y, MbWork &w)
 {
@@ -70,11 +77,13 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
             }
             MbCtx c(fc, fp, work);
             c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;
+            if (fp.trace && lane == 0) fp.trace[2 * c.mb_xy] = globaltimer_ns();
             stage_fenc(fc, x, row, work);
             analyse_p_mb(c, c.mb_xy ? fp.results[c.mb_xy - 1].mv : fp.stale_mv);
             __syncwarp();
             if (lane == 0)
             {
+                if (fp.trace) fp.trace[2 * c.mb_xy + 1] = globaltimer_ns();
                 __threadfence();
                 st_release(fp.row_progress + row, x + 1);
             }

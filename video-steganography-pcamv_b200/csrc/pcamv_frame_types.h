@@ -63,6 +63,7 @@ struct FrameParams
     LogEntry *log;           // [n_mb][PCAMV_LOG_MAX]
     MbResult *results;       // [n_mb]
     int *row_progress;       // [mb_h] wavefront counters
+    unsigned long long *trace;   // optional [n_mb][2]: globaltimer ns at the start / end of each macroblock (profiling aid)
 };
 
 

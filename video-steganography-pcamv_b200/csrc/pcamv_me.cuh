@@ -74,457 +74,448 @@ PCAMV_DEV void qpel_sources(const MeBlock &b, int qmx, int qmy, const uint8_t *&
     const int h1 = (fy == 0) ? 0 : ((fx == 2) ? 3 : 2);
     const int off = (qmy >> 2) * b.stride + (qmx >> 2);
     s1 = b.ref[h0] + off + (fy == 3 ? b.stride : 0);
-    s2 = (idx & 5) ? b.ref[h1] + off + (fx == 3 ? 1 : 0) : (const uint8_t *)0;
+    s2 = (idx & 5) ? b.ref[h1] + off + (fx == 3 ? 1 : 0) : s1;      // (a + a + 1) >> 1 == a: no branch for the unaveraged positions
 }
 
 // 4 predicted luma pixels at block-relative (x, y) for sources prepared by qpel_sources
 PCAMV_DEV uint32_t pred4(const uint8_t *s1, const uint8_t *s2, int stride, int x, int y)
 {
-    uint32_t w = ld4(s1 + y * stride + x);
-    if (s2)
-        w = avg4(w, ld4(s2 + y * stride + x));
-    return w;
+    return avg4(ld4(s1 + y * stride + x), ld4(s2 + y * stride + x));
 }
 
-// 4 predicted chroma pixels (reference common/mc.c:246-277), src already at the block origin
+// =====================================================================================================
+// Candidate costs.  One out-of-line evaluator serves every caller (integer search, predictor test, half/quarter-
+// pel refinement, the cost-table rings): the instruction cache is the scarce resource of the per-macroblock
+// code, so there is exactly ONE copy of the SAD loop, the SATD unit loop and the 4x4 Hadamard in a kernel.
+// Candidates travel in registers (packed x | y << 16), never through local-memory arrays.
+// =====================================================================================================
+enum { COST_SAD = 0, COST_SATD = 1, COST_SATD_CHROMA = 2, COST_SAD_FPEL = 3 };
+
+PCAMV_DEV int pk(int x, int y) { return (int)(((uint32_t)x & 0xffffu) | ((uint32_t)y << 16)); }
+PCAMV_DEV int pk_x(int p) { return (int)(int16_t)(p & 0xffff); }
+PCAMV_DEV int pk_y(int p) { return p >> 16; }
+
+// 4 chroma pixels of the bilinear 1/8-pel interpolation (reference common/mc.c:246-277) from the two source rows
+// (t = top row words at s and s+1, u = bottom row), two pixels per 32-bit multiply-add: every 16-bit half stays
+// below 64*255+32, so the halves never interact and the result equals the scalar formula bit for bit.
+PCAMV_DEV uint32_t bilin4(uint32_t t0, uint32_t t1, uint32_t u0, uint32_t u1, int cA, int cB, int cC, int cD)
+{
+    const uint32_t m = 0x00ff00ffu;
+    const uint32_t e = (t0 & m) * cA + (t1 & m) * cB + (u0 & m) * cC + (u1 & m) * cD + 0x00200020u;
+    const uint32_t o = ((t0 >> 8) & m) * cA + ((t1 >> 8) & m) * cB + ((u0 >> 8) & m) * cC + ((u1 >> 8) & m) * cD + 0x00200020u;
+    return ((e >> 6) & m) | (((o >> 6) & m) << 8);
+}
+// words at p and p+1 (unaligned) from one pair of aligned loads
+PCAMV_DEV void ld4x2(const uint8_t *p, uint32_t &w0, uint32_t &w1)
+{
+#if defined(PCAMV_EMU)
+    memcpy(&w0, p, 4); memcpy(&w1, p + 1, 4);
+#else
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const unsigned long long v = (unsigned long long)__ldg(q) | ((unsigned long long)__ldg(q + 1) << 32);
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    w0 = (uint32_t)(v >> sh);
+    w1 = (uint32_t)(v >> (sh + 8));
+#endif
+}
+
+// 4 predicted chroma pixels at block-relative (x, y) (reference common/mc.c:246-277), src already at the block origin
 PCAMV_DEV uint32_t chroma4(const uint8_t *src, int stride, int qmx, int qmy, int x, int y)
 {
     const int dx = qmx & 7, dy = qmy & 7;
-    const int cA = (8 - dx) * (8 - dy), cB = dx * (8 - dy), cC = (8 - dx) * dy, cD = dx * dy;
     const uint8_t *s = src + ((qmy >> 3) + y) * stride + (qmx >> 3) + x;
-    const uint32_t t0 = ld4(s), t1 = ld4(s + 1), b0 = ld4(s + stride), b1 = ld4(s + stride + 1);
-    uint32_t r = 0;
+    uint32_t t0, t1, u0, u1;
+    ld4x2(s, t0, t1);
+    ld4x2(s + stride, u0, u1);
+    return bilin4(t0, t1, u0, u1, (8 - dx) * (8 - dy), dx * (8 - dy), (8 - dx) * dy, dx * dy);
+}
+
+// 16 pixels of the unaligned row at p as four words (five aligned loads + funnel shifts)
+PCAMV_DEV void ld_row16(const uint8_t *p, uint32_t w[4])
+{
+#if defined(PCAMV_EMU)
+    memcpy(w, p, 16);
+#else
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    uint32_t v[5];
 #pragma unroll
+    for (int j = 0; j < 5; j++) v[j] = __ldg(q + j);
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = __funnelshift_r(v[j], v[j + 1], sh);
+#endif
+}
+
+#if defined(PCAMV_EMU)
+  #define PCAMV_ROWS 16      // rows of a block handled by one lane
+#else
+  #define PCAMV_ROWS 2
+#endif
+
+// Cost of candidate `grp` of (c0..c3) — distortion of the block against the quarter-pel prediction at the packed MV
+// plus the MV bit cost — returned in every lane of that group; groups >= n return COST_MAX (they still compute, on
+// whatever valid candidate they were handed, so that the whole team runs one straight-line instruction stream:
+// a lone warp per macroblock pays ~25 cycles for every divergent branch and reconvergence).
+// kind: COST_SAD_FPEL (fpelcmp at integer positions: one source plane), COST_SAD (fpelcmp at any quarter-pel position),
+// COST_SATD (mbcmp, luma), COST_SATD_CHROMA (luma + both chroma planes, each halved separately as in the reference's
+// three calls; every 4x4 Hadamard sum is even, so halving per unit is exact).
+// SAD: a lane owns whole rows (sub, sub + 8) of up to 16 pixels; SATD: a lane owns 4x4 units.
+PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2, int c3)
+{
+    const int grp = team_grp(), sub = team_sub();
+    const int c = grp == 0 ? c0 : grp == 1 ? c1 : grp == 2 ? c2 : c3;
+    const int qx = pk_x(c), qy = pk_y(c);
+    int acc = 0;
+    const uint8_t *s1, *s2;
+    qpel_sources(b, qx, qy, s1, s2);
+    if (kind == COST_SAD_FPEL || kind == COST_SAD)
+    {
+        const int w4 = b.bw >> 2;
+#pragma unroll
+        for (int r = 0; r < PCAMV_ROWS; r++)
+        {
+            const int y = sub + PCAMV_LPG * r;
+            const int yy = imin(y, b.bh - 1);
+            uint32_t p[4];
+            ld_row16(s1 + yy * b.stride, p);
+            if (kind == COST_SAD)
+            {
+                uint32_t q[4];
+                ld_row16(s2 + yy * b.stride, q);
+#pragma unroll
+                for (int j = 0; j < 4; j++) p[j] = avg4(p[j], q[j]);
+            }
+            int s = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                s += j < w4 ? sad4(ld4a(b.fenc + yy * 16 + 4 * j), p[j]) : 0;
+            acc += y < b.bh ? s : 0;
+        }
+    }
+    else
+    {
+        const int llx = b.bw == 16 ? 2 : b.bw == 8 ? 1 : 0;         // log2(luma 4x4 units per row)
+        const int nl = (b.bh >> 2) << llx;
+#pragma unroll 1
+        for (int k = 0; k * PCAMV_LPG < nl; k++)
+        {
+            const int u = sub + PCAMV_LPG * k;
+            const int uu = u < nl ? u : 0;
+            const int x = (uu & ((1 << llx) - 1)) << 2, y = (uu >> llx) << 2;
+            uint32_t f[4], a[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                f[r] = ld4a(b.fenc + (y + r) * 16 + x);
+                a[r] = pred4(s1, s2, b.stride, x, y + r);
+            }
+            const int h = (int)(hadamard_4x4_sum(f, a) >> 1);
+            acc += u < nl ? h : 0;
+        }
+        if (kind == COST_SATD_CHROMA)
+        {
+            const int lcx = b.bw == 16 ? 1 : 0;                        // log2(chroma 4x4 units per row)
+            const int nc = (b.bh >> 3) << lcx;                         // units per chroma plane
+            const int dx = qx & 7, dy = qy & 7;
+            const int cA = (8 - dx) * (8 - dy), cB = dx * (8 - dy), cC = (8 - dx) * dy, cD = dx * dy;
+#pragma unroll 1
+            for (int k = 0; k * PCAMV_LPG < 2 * nc; k++)
+            {
+                const int u = sub + PCAMV_LPG * k;
+                int v = u < 2 * nc ? u : 0;
+                const int pl = v >= nc;
+                v -= pl ? nc : 0;
+                const int x = (v & ((1 << lcx) - 1)) << 2, y = (v >> lcx) << 2;
+                const uint8_t *fe = (pl ? b.fenc_v : b.fenc_u) + y * 8 + x;
+                const uint8_t *s = (pl ? b.ref_v : b.ref_u) + ((qy >> 3) + y) * b.stride_c + (qx >> 3) + x;
+                uint32_t f[4], a[4], t0, t1;
+                ld4x2(s, t0, t1);
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    uint32_t u0, u1;
+                    ld4x2(s + (r + 1) * b.stride_c, u0, u1);
+                    f[r] = ld4a(fe + r * 8);
+                    a[r] = bilin4(t0, t1, u0, u1, cA, cB, cC, cD);
+                    t0 = u0; t1 = u1;
+                }
+                const int h = (int)(hadamard_4x4_sum(f, a) >> 1);
+                acc += u < 2 * nc ? h : 0;
+            }
+        }
+    }
+    acc = grp_sum(acc);
+    return grp < n ? acc + b.cost_mvx[qx] + b.cost_mvy[qy] : PCAMV_COST_MAX;
+}
+
+// costs[i] = cost of candidate i (i < n <= 4) in EVERY lane
+PCAMV_DEV void eval4(const MeBlock &b, int kind, int n, int c0, int c1, int c2, int c3, int costs[4])
+{
+#if defined(PCAMV_EMU)
+    const int c[4] = { c0, c1, c2, c3 };
     for (int i = 0; i < 4; i++)
-        r |= (uint32_t)((cA * px(t0, i) + cB * px(t1, i) + cC * px(b0, i) + cD * px(b1, i) + 32) >> 6) << (8 * i);
-    return r;
+        costs[i] = i < n ? cand_cost(b, kind, 1, c[i], c[i], c[i], c[i]) : PCAMV_COST_MAX;
+#else
+    const int mine = cand_cost(b, kind, n, c0, c1, c2, c3);
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+        costs[g] = grp_bcast(mine, g);
+#endif
 }
-
-// ---- distortion of up to N candidates, concurrently -----------------------------------------------
-// SAD at quarter-pel candidates (integer/half positions take the single-plane path).
-// out[i] = SAD only; the caller adds the MV cost.
-PCAMV_FN void sad_cands(const MeBlock &b, int n, const int *qmx, const int *qmy, int *out)
+PCAMV_DEV int eval1(const MeBlock &b, int kind, int c)
 {
-    const int grp = team_grp(), sub = team_sub();
-    const int w4 = b.bw >> 2, words = w4 * b.bh;
-    for (int c0 = 0; c0 < n; c0 += PCAMV_NGRP)
-    {
-        const int c = c0 + grp;
-        int acc = 0;
-        if (c < n)
-        {
-            const uint8_t *s1, *s2;
-            qpel_sources(b, qmx[c], qmy[c], s1, s2);
-            for (int w = sub; w < words; w += PCAMV_LPG)
-            {
-                const int y = w / w4, x = (w - y * w4) << 2;
-                acc += sad4(ld4a(b.fenc + y * 16 + x), pred4(s1, s2, b.stride, x, y));
-            }
-        }
-        acc = grp_sum(acc);
-#pragma unroll
-        for (int g = 0; g < PCAMV_NGRP; g++)
-            if (c0 + g < n)
-                out[c0 + g] = grp_bcast(acc, g);
-    }
-}
-
-// SAD at full-pel candidates (mx,my in pixels): integer plane only.
-PCAMV_FN void sad_fpel_cands(const MeBlock &b, int n, const int *mx, const int *my, int *out)
-{
-    const int grp = team_grp(), sub = team_sub();
-    const int w4 = b.bw >> 2, words = w4 * b.bh;
-    for (int c0 = 0; c0 < n; c0 += PCAMV_NGRP)
-    {
-        const int c = c0 + grp;
-        int acc = 0;
-        if (c < n)
-        {
-            const uint8_t *s = b.ref[0] + my[c] * b.stride + mx[c];
-            for (int w = sub; w < words; w += PCAMV_LPG)
-            {
-                const int y = w / w4, x = (w - y * w4) << 2;
-                acc += sad4(ld4a(b.fenc + y * 16 + x), ld4(s + y * b.stride + x));
-            }
-        }
-        acc = grp_sum(acc);
-#pragma unroll
-        for (int g = 0; g < PCAMV_NGRP; g++)
-            if (c0 + g < n)
-                out[c0 + g] = grp_bcast(acc, g);
-    }
-}
-
-// SATD of a luma block against prepared sources; lanes of the group split the 8x4 / 4x4 units.
-PCAMV_DEV int satd_luma_part(const uint8_t *fenc, int fstride, int bw, int bh,
-                             const uint8_t *s1, const uint8_t *s2, int stride, int sub)
-{
-    uint32_t acc = 0;
-    if (bw >= 8)
-    {
-        const int ux = bw >> 3, units = ux * (bh >> 2);
-        for (int u = sub; u < units; u += PCAMV_LPG)
-        {
-            const int x = (u % ux) << 3, y = (u / ux) << 2;
-            uint32_t f[4], g[4], a[4], c[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                f[r] = ld4a(fenc + (y + r) * fstride + x);
-                g[r] = ld4a(fenc + (y + r) * fstride + x + 4);
-                a[r] = pred4(s1, s2, stride, x, y + r);
-                c[r] = pred4(s1, s2, stride, x + 4, y + r);
-            }
-            acc += hadamard_8x4_sum(f, g, a, c);
-        }
-    }
-    else
-    {
-        const int units = bh >> 2;
-        for (int u = sub; u < units; u += PCAMV_LPG)
-        {
-            const int y = u << 2;
-            uint32_t f[4], a[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                f[r] = ld4a(fenc + (y + r) * fstride);
-                a[r] = pred4(s1, s2, stride, 0, y + r);
-            }
-            acc += hadamard_4x4_sum(f, a);
-        }
-    }
-    return (int)acc;
-}
-
-// SATD of one chroma plane block (cw x ch, cw in {4,8}) against bilinear MC at (qmx,qmy)
-PCAMV_DEV int satd_chroma_part(const uint8_t *fenc, int fstride, int cw, int ch,
-                               const uint8_t *src, int stride, int qmx, int qmy, int sub, int sub_off)
-{
-    uint32_t acc = 0;
-    if (cw >= 8)
-    {
-        const int units = ch >> 2;
-        for (int u = 0; u < units; u++)
-        {
-            if (((u + sub_off) % PCAMV_LPG) != sub) continue;
-            const int y = u << 2;
-            uint32_t f[4], g[4], a[4], c[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                f[r] = ld4a(fenc + (y + r) * fstride);
-                g[r] = ld4a(fenc + (y + r) * fstride + 4);
-                a[r] = chroma4(src, stride, qmx, qmy, 0, y + r);
-                c[r] = chroma4(src, stride, qmx, qmy, 4, y + r);
-            }
-            acc += hadamard_8x4_sum(f, g, a, c);
-        }
-    }
-    else
-    {
-        const int units = ch >> 2;
-        for (int u = 0; u < units; u++)
-        {
-            if (((u + sub_off) % PCAMV_LPG) != sub) continue;
-            const int y = u << 2;
-            uint32_t f[4], a[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                f[r] = ld4a(fenc + (y + r) * fstride);
-                a[r] = chroma4(src, stride, qmx, qmy, 0, y + r);
-            }
-            acc += hadamard_4x4_sum(f, a);
-        }
-    }
-    return (int)acc;
-}
-
-// SATD (luma, plus both chroma planes when `chroma`) at quarter-pel candidates.
-// out[i] = luma SATD + U SATD + V SATD (each already halved like the reference's functions).
-// The reference adds chroma only while the running cost is still below the best (encoder/me.c:689-713);
-// chroma terms are non-negative, so adding them unconditionally gives the same decisions.
-PCAMV_FN void satd_cands(const MeBlock &b, int n, const int *qmx, const int *qmy, int chroma, int *out,
-                          const uint8_t *fenc_y, const uint8_t *fenc_u, const uint8_t *fenc_v, int use_satd = 1)
-{
-    const int grp = team_grp(), sub = team_sub();
-    if (!use_satd)
-    {
-        // --subme 1: mbcmp is plain SAD (chroma ME is never on below subme 5)
-        sad_cands(b, n, qmx, qmy, out);
-        return;
-    }
-    for (int c0 = 0; c0 < n; c0 += PCAMV_NGRP)
-    {
-        const int c = c0 + grp;
-        int accY = 0, accU = 0, accV = 0;
-        if (c < n)
-        {
-            const uint8_t *s1, *s2;
-            qpel_sources(b, qmx[c], qmy[c], s1, s2);
-            accY = satd_luma_part(fenc_y, 16, b.bw, b.bh, s1, s2, b.stride, sub);
-            if (chroma)
-            {
-                // spread the chroma units over the lanes that have the fewest luma units
-                accU = satd_chroma_part(fenc_u, 8, b.bw >> 1, b.bh >> 1, b.ref_u, b.stride_c, qmx[c], qmy[c], sub, PCAMV_LPG - 1);
-                accV = satd_chroma_part(fenc_v, 8, b.bw >> 1, b.bh >> 1, b.ref_v, b.stride_c, qmx[c], qmy[c], sub, PCAMV_LPG - 3);
-            }
-        }
-        // each plane's SATD is halved separately in the reference (three function calls)
-        accY = grp_sum(accY) >> 1;
-        if (chroma)
-        {
-            accU = grp_sum(accU) >> 1;
-            accV = grp_sum(accV) >> 1;
-        }
-        const int tot = accY + accU + accV;
-#pragma unroll
-        for (int g = 0; g < PCAMV_NGRP; g++)
-            if (c0 + g < n)
-                out[c0 + g] = grp_bcast(tot, g);
-    }
+    int costs[4];
+    eval4(b, kind, 1, c, c, c, c, costs);
+    return costs[0];
 }
 
 // =====================================================================================================
 // Integer-pel search + sub-pel refinement of one block
 // =====================================================================================================
-struct MeSearch
+// running best of the integer search, in registers: cost in the high word, packed full-pel MV in the low word
+typedef unsigned long long best_t;
+PCAMV_DEV best_t best_make(int cost, int mv) { return ((best_t)(uint32_t)cost << 32) | (uint32_t)mv; }
+PCAMV_DEV int best_cost(best_t s) { return (int)(s >> 32); }
+PCAMV_DEV int best_mv(best_t s) { return (int)(uint32_t)s; }
+
+// four signed byte offsets in one word
+#define PCAMV_OFF4(a, b, c, d) ((uint32_t)((a) & 0xff) | ((uint32_t)((b) & 0xff) << 8) | ((uint32_t)((c) & 0xff) << 16) | ((uint32_t)((d) & 0xff) << 24))
+PCAMV_DEV int off_at(uint32_t offs, int i) { return (int)(int8_t)(offs >> (8 * i)); }
+
+// Cost the full-pel candidates (ox + dx_i, oy + dy_i), i < n, and fold them into the best in order with the
+// reference's strict-< rule (COST_MV / COST_MV_X3_DIR / COST_MV_X4, encoder/me.c:57-120).
+PCAMV_FN best_t try4(const MeBlock &b, best_t best, int n, int ox, int oy, uint32_t dxs, uint32_t dys)
 {
-    const MeEnv &env;
-    const MeBlock &b;
-    int bmx, bmy, bcost;           // running best (full-pel units during the integer search)
-    int mv_x_min, mv_y_min, mv_x_max, mv_y_max;
-
-    PCAMV_MEM MeSearch(const MeEnv &e, const MeBlock &blk) : env(e), b(blk)
-    {
-        mv_x_min = e.mv_min_fpel[0]; mv_y_min = e.mv_min_fpel[1];
-        mv_x_max = e.mv_max_fpel[0]; mv_y_max = e.mv_max_fpel[1];
-    }
-    PCAMV_MEM int bits_fpel(int mx, int my) const { return b.cost_mvx[mx << 2] + b.cost_mvy[my << 2]; }
-    PCAMV_MEM bool in_range(int mx, int my) const
-    {
-        return mx >= mv_x_min && mx <= mv_x_max && my >= mv_y_min && my <= mv_y_max;
-    }
-    // cost n (<=4) full-pel candidates and fold them into the best in order (strict <)
-    PCAMV_MEM void try_fpel(int n, const int *mx, const int *my)
-    {
-        int sad[4];
-        sad_fpel_cands(b, n, mx, my, sad);
+    int mv[4], costs[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (i < n)
-            {
-                const int c = sad[i] + bits_fpel(mx[i], my[i]);
-                if (c < bcost) { bcost = c; bmx = mx[i]; bmy = my[i]; }
-            }
-    }
-    PCAMV_MEM void try_fpel1(int mx, int my) { try_fpel(1, &mx, &my); }
-    // four offsets around (ox,oy)  — the reference's COST_MV_X4
-    PCAMV_MEM void try_x4(int ox, int oy, int x0, int y0, int x1, int y1, int x2, int y2, int x3, int y3)
-    {
-        const int mx[4] = { ox + x0, ox + x1, ox + x2, ox + x3 };
-        const int my[4] = { oy + y0, oy + y1, oy + y2, oy + y3 };
-        try_fpel(4, mx, my);
-    }
-    PCAMV_MEM void dia1(int ox, int oy) { try_x4(ox, oy, 0, -1, 0, 1, -1, 0, 1, 0); }
+    for (int i = 0; i < 4; i++)
+        mv[i] = pk(ox + off_at(dxs, i), oy + off_at(dys, i));
+    eval4(b, COST_SAD_FPEL, n, pk(pk_x(mv[0]) << 2, pk_y(mv[0]) << 2), pk(pk_x(mv[1]) << 2, pk_y(mv[1]) << 2),
+          pk(pk_x(mv[2]) << 2, pk_y(mv[2]) << 2), pk(pk_x(mv[3]) << 2, pk_y(mv[3]) << 2), costs);
+    int bcost = best_cost(best), bmv = best_mv(best);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (i < n && costs[i] < bcost) { bcost = costs[i]; bmv = mv[i]; }
+    return best_make(bcost, bmv);
+}
+PCAMV_DEV best_t try1(const MeBlock &b, best_t best, int mx, int my) { return try4(b, best, 1, mx, my, 0, 0); }
+PCAMV_DEV best_t dia1(const MeBlock &b, best_t best, int ox, int oy)
+{
+    return try4(b, best, 4, ox, oy, PCAMV_OFF4(0, 0, -1, 1), PCAMV_OFF4(-1, 1, 0, 0));
+}
+PCAMV_DEV bool fpel_in_range(const MeEnv &e, int mx, int my)
+{
+    return mx >= e.mv_min_fpel[0] && mx <= e.mv_max_fpel[0] && my >= e.mv_min_fpel[1] && my <= e.mv_max_fpel[1];
+}
 
-    // symmetric cross around (ox,oy)  (reference encoder/me.c:131-155)
-    PCAMV_MEMFN void cross(int ox, int oy, int start, int x_max, int y_max)
+// symmetric cross around (ox,oy)  (reference encoder/me.c:131-155)
+PCAMV_FN best_t search_cross(const MeEnv &e, const MeBlock &b, best_t best, int ox, int oy, int start, int x_max, int y_max)
+{
+    int i = start;
+    if (x_max <= imin(e.mv_max_fpel[0] - ox, ox - e.mv_min_fpel[0]))
+        for (; i < x_max - 2; i += 4)
+            best = try4(b, best, 4, ox, oy, PCAMV_OFF4(i, -i, i + 2, -i - 2), 0);
+    for (; i < x_max; i += 2)
     {
-        int i = start;
-        if (x_max <= imin(mv_x_max - ox, ox - mv_x_min))
-            for (; i < x_max - 2; i += 4)
-                try_x4(ox, oy, i, 0, -i, 0, i + 2, 0, -i - 2, 0);
-        for (; i < x_max; i += 2)
+        if (ox + i <= e.mv_max_fpel[0]) best = try1(b, best, ox + i, oy);
+        if (ox - i >= e.mv_min_fpel[0]) best = try1(b, best, ox - i, oy);
+    }
+    i = start;
+    if (y_max <= imin(e.mv_max_fpel[1] - oy, oy - e.mv_min_fpel[1]))
+        for (; i < y_max - 2; i += 4)
+            best = try4(b, best, 4, ox, oy, 0, PCAMV_OFF4(i, -i, i + 2, -i - 2));
+    for (; i < y_max; i += 2)
+    {
+        if (oy + i <= e.mv_max_fpel[1]) best = try1(b, best, ox, oy + i);
+        if (oy - i >= e.mv_min_fpel[1]) best = try1(b, best, ox, oy - i);
+    }
+    return best;
+}
+
+// hexagon corner k = 0..5: (-2,0) (-1,2) (1,2) (2,0) (1,-2) (-1,-2), one signed nibble per corner
+PCAMV_DEV int hex_dx(int k) { return ((int)(0xF121FEu << (28 - 4 * k))) >> 28; }     // nibbles, k = 0 lowest: E F 1 2 1 F
+PCAMV_DEV int hex_dy(int k) { return ((int)(0xEE0220u << (28 - 4 * k))) >> 28; }      // 0 2 2 0 E E
+
+// hexagon (radius 2) walk followed by the 8-point square  (reference encoder/me.c:263-341)
+PCAMV_FN best_t search_hex(const MeEnv &e, const MeBlock &b, best_t best, int me_range)
+{
+    int cx = pk_x(best_mv(best)), cy = pk_y(best_mv(best));
+    // first step: all six corners in the order 0..5
+    const int cost0 = best_cost(best);
+    best = try4(b, best, 3, cx, cy, PCAMV_OFF4(-2, -1, 1, 0), PCAMV_OFF4(0, 2, 2, 0));
+    best = try4(b, best, 3, cx, cy, PCAMV_OFF4(2, 1, -1, 0), PCAMV_OFF4(0, -2, -2, 0));
+    if (best_cost(best) < cost0)
+    {
+        int nx = pk_x(best_mv(best)), ny = pk_y(best_mv(best));
+        // direction index of the winning corner
+        int dir = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (nx - cx == hex_dx(k) && ny - cy == hex_dy(k)) dir = k;
+        cx = nx; cy = ny;
+        // half hexagons: only the three corners not covered by the previous position
+        for (int i = 1; i < me_range / 2 && fpel_in_range(e, cx, cy); i++)
         {
-            if (ox + i <= mv_x_max) try_fpel1(ox + i, oy);
-            if (ox - i >= mv_x_min) try_fpel1(ox - i, oy);
+            const int d0 = dir == 0 ? 5 : dir - 1, d2 = dir == 5 ? 0 : dir + 1;
+            const int costi = best_cost(best);
+            best = try4(b, best, 3, cx, cy, PCAMV_OFF4(hex_dx(d0), hex_dx(dir), hex_dx(d2), 0),
+                        PCAMV_OFF4(hex_dy(d0), hex_dy(dir), hex_dy(d2), 0));
+            if (!(best_cost(best) < costi))
+                break;
+            nx = pk_x(best_mv(best)); ny = pk_y(best_mv(best));
+            dir = (nx - cx == hex_dx(d0) && ny - cy == hex_dy(d0)) ? d0 : (nx - cx == hex_dx(dir) && ny - cy == hex_dy(dir)) ? dir : d2;
+            cx = nx; cy = ny;
         }
-        i = start;
-        if (y_max <= imin(mv_y_max - oy, oy - mv_y_min))
-            for (; i < y_max - 2; i += 4)
-                try_x4(ox, oy, 0, i, 0, -i, 0, i + 2, 0, -i - 2);
-        for (; i < y_max; i += 2)
-        {
-            if (oy + i <= mv_y_max) try_fpel1(ox, oy + i);
-            if (oy - i >= mv_y_min) try_fpel1(ox, oy - i);
-        }
     }
+    // square refine around the final centre
+    best = try4(b, best, 4, cx, cy, PCAMV_OFF4(0, 0, -1, 1), PCAMV_OFF4(-1, 1, 0, 0));
+    best = try4(b, best, 4, cx, cy, PCAMV_OFF4(-1, -1, 1, 1), PCAMV_OFF4(-1, 1, -1, 1));
+    return best;
+}
 
-    // hexagon (radius 2) walk followed by the 8-point square  (reference encoder/me.c:263-341)
-    PCAMV_MEMFN void hex_then_square(int me_range)
+PCAMV_DEV best_t search_dia(const MeEnv &e, const MeBlock &b, best_t best, int me_range)
+{
+    int i = 0;
+    do
     {
-        // hexagon corner k (k = 0..5), walking order matches the reference's direction indices
-        const int hx[6] = { -2, -1, 1, 2, 1, -1 };
-        const int hy[6] = { 0, 2, 2, 0, -2, -2 };
-        int mx[4], my[4], sad[4];
-        int dir = -1;
-        // first step: all six corners, in the order 0..5
-        int best6 = bcost;
-        for (int half = 0; half < 2; half++)
-        {
-            for (int k = 0; k < 3; k++) { mx[k] = bmx + hx[3 * half + k]; my[k] = bmy + hy[3 * half + k]; }
-            sad_fpel_cands(b, 3, mx, my, sad);
-            for (int k = 0; k < 3; k++)
-            {
-                const int c = sad[k] + bits_fpel(mx[k], my[k]);
-                if (c < best6) { best6 = c; dir = 3 * half + k; }
-            }
-        }
-        bcost = best6;
-        if (dir >= 0)
-        {
-            bmx += hx[dir]; bmy += hy[dir];
-            // half hexagons: only the three corners not covered by the previous position
-            for (int i = 1; i < me_range / 2 && in_range(bmx, bmy); i++)
-            {
-                int nd = -1;
-                for (int k = 0; k < 3; k++)
-                {
-                    const int d = (dir + 5 + k) % 6;     // dir-1, dir, dir+1
-                    mx[k] = bmx + hx[d]; my[k] = bmy + hy[d];
-                }
-                sad_fpel_cands(b, 3, mx, my, sad);
-                for (int k = 0; k < 3; k++)
-                {
-                    const int c = sad[k] + bits_fpel(mx[k], my[k]);
-                    if (c < bcost) { bcost = c; nd = (dir + 5 + k) % 6; }
-                }
-                if (nd < 0)
-                    break;
-                dir = nd;
-                bmx += hx[dir]; bmy += hy[dir];
-            }
-        }
-        // square refine around the final centre
-        const int ox = bmx, oy = bmy;
-        try_x4(ox, oy, 0, -1, 0, 1, -1, 0, 1, 0);
-        try_x4(ox, oy, -1, -1, -1, 1, 1, -1, 1, 1);
-    }
+        const int omv = best_mv(best);
+        best = dia1(b, best, pk_x(omv), pk_y(omv));
+        if (best_mv(best) == omv) break;
+        if (!fpel_in_range(e, pk_x(best_mv(best)), pk_y(best_mv(best)))) break;
+    } while (++i < me_range);
+    return best;
+}
 
-    PCAMV_MEM void search_dia(int me_range)
+// uneven-cross multi-hexagon-grid search (reference encoder/me.c:342-482); returns with *run_hex = 1 when the
+// reference goes on to the hexagon refinement (executed by the caller, so that search_hex is expanded once)
+PCAMV_FN best_t search_umh(const MeEnv &e, const MeBlock &b, best_t best, int pmx, int pmy, const int (*mvc)[2], int i_mvc,
+                            int *run_hex, int *hex_range)
+{
+    int me_range = e.me_range;
+    const int shift = b.i_pixel == PIX_16x16 ? 0 : b.i_pixel <= PIX_8x16 ? 1 : b.i_pixel == PIX_8x8 ? 2
+                    : b.i_pixel <= PIX_4x8 ? 3 : 4;
+    int cross_start = 1;
+    *run_hex = 0; *hex_range = me_range;
+    const int ucost1 = best_cost(best);
+    best = dia1(b, best, pmx, pmy);
+    if (pmx | pmy)
+        best = dia1(b, best, 0, 0);
+    if (b.i_pixel == PIX_4x4) { *run_hex = 1; return best; }
+
+    const int ucost2 = best_cost(best);
     {
-        int i = 0;
-        do
-        {
-            const int ox = bmx, oy = bmy;
-            dia1(ox, oy);
-            if (bmx == ox && bmy == oy) break;
-            if (!in_range(bmx, bmy)) break;
-        } while (++i < me_range);
-    }
-
-    // uneven-cross multi-hexagon-grid search (reference encoder/me.c:342-482)
-    PCAMV_MEMFN void search_umh(int pmx, int pmy, const int (*mvc)[2], int i_mvc)
-    {
-        int me_range = env.me_range;
-        const int shift = b.i_pixel == PIX_16x16 ? 0 : b.i_pixel <= PIX_8x16 ? 1 : b.i_pixel == PIX_8x8 ? 2
-                        : b.i_pixel <= PIX_4x8 ? 3 : 4;
-        int cross_start = 1;
-        const int ucost1 = bcost;
-        dia1(pmx, pmy);
-        if (pmx | pmy)
-            dia1(0, 0);
-        if (b.i_pixel == PIX_4x4) { hex_then_square(me_range); return; }
-
-        const int ucost2 = bcost;
+        const int bmx = pk_x(best_mv(best)), bmy = pk_y(best_mv(best));
         if ((bmx | bmy) && ((bmx - pmx) | (bmy - pmy)))
-            dia1(bmx, bmy);
-        if (bcost == ucost2)
-            cross_start = 3;
-        int ox = bmx, oy = bmy;
-
-        if (bcost == ucost2 && bcost < (2000 >> shift))
-        {
-            try_x4(ox, oy, 0, -2, -1, -1, 1, -1, -2, 0);
-            try_x4(ox, oy, 2, 0, -1, 1, 1, 1, 0, 2);
-            if (bcost == ucost1 && bcost < (500 >> shift))
-                return;
-            if (bcost == ucost2)
-            {
-                const int range = (me_range >> 1) | 1;
-                cross(ox, oy, 3, range, range);
-                try_x4(ox, oy, -1, -2, 1, -2, -2, -1, 2, -1);
-                try_x4(ox, oy, -2, 1, 2, 1, -1, 2, 1, 2);
-                if (bcost == ucost2)
-                    return;
-                cross_start = range + 2;
-            }
-        }
-
-        // adaptive search range from predictor agreement
-        if (i_mvc)
-        {
-            int mvd, denom = 1;
-            if (i_mvc == 1)
-            {
-                if (b.i_pixel == PIX_16x16)
-                    mvd = 25;
-                else
-                    mvd = iabs(b.mvp[0] - mvc[0][0]) + iabs(b.mvp[1] - mvc[0][1]);
-            }
-            else
-            {
-                denom = i_mvc - 1;
-                mvd = 0;
-                if (b.i_pixel != PIX_16x16)
-                {
-                    mvd = iabs(b.mvp[0] - mvc[0][0]) + iabs(b.mvp[1] - mvc[0][1]);
-                    denom++;
-                }
-                for (int i = 0; i < i_mvc - 1; i++)
-                    mvd += iabs(mvc[i][0] - mvc[i + 1][0]) + iabs(mvc[i][1] - mvc[i + 1][1]);
-            }
-            const int sad_ctx = bcost < (1000 >> shift) ? 0 : bcost < (2000 >> shift) ? 1 : bcost < (4000 >> shift) ? 2 : 3;
-            const int mvd_ctx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
-            // multiplier table rows = mvd_ctx, cols = sad_ctx
-            const int mul = mvd_ctx == 0 ? (sad_ctx < 2 ? 3 : 4)
-                          : mvd_ctx == 1 ? (sad_ctx < 1 ? 3 : 4)
-                          : mvd_ctx == 2 ? (sad_ctx < 3 ? 4 : 5)
-                          : (sad_ctx < 2 ? 4 : sad_ctx == 2 ? 5 : 6);
-            me_range = me_range * mul / 4;
-        }
-
-        // still centred on (ox,oy) — the reference keeps the stale centre here on purpose
-        cross(ox, oy, cross_start, me_range, me_range / 2);
-        try_x4(ox, oy, -2, -2, -2, 2, 2, -2, 2, 2);
-
-        // 16-point hexagon grid, radius 4*i
-        ox = bmx; oy = bmy;
-        const int gx[16] = { -4, -4, -4, -4, -4, 4, 4, 4, 4, 4, 2, 0, -2, -2, 0, 2 };
-        const int gy[16] = { 2, 1, 0, -1, -2, -2, -1, 0, 1, 2, 3, 4, 3, -3, -4, -3 };
-        int i = 1;
-        do
-        {
-            if (4 * i > imin(imin(mv_x_max - ox, ox - mv_x_min), imin(mv_y_max - oy, oy - mv_y_min)))
-            {
-                for (int j = 0; j < 16; j++)
-                {
-                    const int mx = ox + gx[j] * i, my = oy + gy[j] * i;
-                    if (in_range(mx, my))
-                        try_fpel1(mx, my);
-                }
-            }
-            else
-            {
-                for (int j = 0; j < 16; j += 4)
-                    try_x4(ox, oy, gx[j] * i, gy[j] * i, gx[j + 1] * i, gy[j + 1] * i,
-                           gx[j + 2] * i, gy[j + 2] * i, gx[j + 3] * i, gy[j + 3] * i);
-            }
-        } while (++i <= me_range / 4);
-        if (bmy <= mv_y_max)
-            hex_then_square(me_range);
+            best = dia1(b, best, bmx, bmy);
     }
-};
+    if (best_cost(best) == ucost2)
+        cross_start = 3;
+    int ox = pk_x(best_mv(best)), oy = pk_y(best_mv(best));
+
+    if (best_cost(best) == ucost2 && best_cost(best) < (2000 >> shift))
+    {
+        best = try4(b, best, 4, ox, oy, PCAMV_OFF4(0, -1, 1, -2), PCAMV_OFF4(-2, -1, -1, 0));
+        best = try4(b, best, 4, ox, oy, PCAMV_OFF4(2, -1, 1, 0), PCAMV_OFF4(0, 1, 1, 2));
+        if (best_cost(best) == ucost1 && best_cost(best) < (500 >> shift))
+            return best;
+        if (best_cost(best) == ucost2)
+        {
+            const int range = (me_range >> 1) | 1;
+            best = search_cross(e, b, best, ox, oy, 3, range, range);
+            best = try4(b, best, 4, ox, oy, PCAMV_OFF4(-1, 1, -2, 2), PCAMV_OFF4(-2, -2, -1, -1));
+            best = try4(b, best, 4, ox, oy, PCAMV_OFF4(-2, 2, -1, 1), PCAMV_OFF4(1, 1, 2, 2));
+            if (best_cost(best) == ucost2)
+                return best;
+            cross_start = range + 2;
+        }
+    }
+
+    // adaptive search range from predictor agreement
+    if (i_mvc)
+    {
+        int mvd, denom = 1;
+        if (i_mvc == 1)
+        {
+            if (b.i_pixel == PIX_16x16)
+                mvd = 25;
+            else
+                mvd = iabs(b.mvp[0] - mvc[0][0]) + iabs(b.mvp[1] - mvc[0][1]);
+        }
+        else
+        {
+            denom = i_mvc - 1;
+            mvd = 0;
+            if (b.i_pixel != PIX_16x16)
+            {
+                mvd = iabs(b.mvp[0] - mvc[0][0]) + iabs(b.mvp[1] - mvc[0][1]);
+                denom++;
+            }
+            for (int i = 0; i < i_mvc - 1; i++)
+                mvd += iabs(mvc[i][0] - mvc[i + 1][0]) + iabs(mvc[i][1] - mvc[i + 1][1]);
+        }
+        const int bc = best_cost(best);
+        const int sad_ctx = bc < (1000 >> shift) ? 0 : bc < (2000 >> shift) ? 1 : bc < (4000 >> shift) ? 2 : 3;
+        const int mvd_ctx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
+        // multiplier table rows = mvd_ctx, cols = sad_ctx
+        const int mul = mvd_ctx == 0 ? (sad_ctx < 2 ? 3 : 4)
+                      : mvd_ctx == 1 ? (sad_ctx < 1 ? 3 : 4)
+                      : mvd_ctx == 2 ? (sad_ctx < 3 ? 4 : 5)
+                      : (sad_ctx < 2 ? 4 : sad_ctx == 2 ? 5 : 6);
+        me_range = me_range * mul / 4;
+    }
+
+    // still centred on (ox,oy) — the reference keeps the stale centre here on purpose
+    best = search_cross(e, b, best, ox, oy, cross_start, me_range, me_range / 2);
+    best = try4(b, best, 4, ox, oy, PCAMV_OFF4(-2, -2, 2, 2), PCAMV_OFF4(-2, 2, -2, 2));
+
+    // 16-point hexagon grid, radius 4*i; rows of the table = four consecutive points
+    ox = pk_x(best_mv(best)); oy = pk_y(best_mv(best));
+    int i = 1;
+    do
+    {
+        const bool near_edge = 4 * i > imin(imin(e.mv_max_fpel[0] - ox, ox - e.mv_min_fpel[0]),
+                                            imin(e.mv_max_fpel[1] - oy, oy - e.mv_min_fpel[1]));
+#pragma unroll 1
+        for (int j = 0; j < 4; j++)
+        {
+            // { -4,-4,-4,-4 | -4,4,4,4 | 4,4,2,0 | -2,-2,0,2 } and { 2,1,0,-1 | -2,-2,-1,0 | 1,2,3,4 | 3,-3,-4,-3 }
+            const uint32_t gx = j == 0 ? PCAMV_OFF4(-4, -4, -4, -4) : j == 1 ? PCAMV_OFF4(-4, 4, 4, 4)
+                              : j == 2 ? PCAMV_OFF4(4, 4, 2, 0) : PCAMV_OFF4(-2, -2, 0, 2);
+            const uint32_t gy = j == 0 ? PCAMV_OFF4(2, 1, 0, -1) : j == 1 ? PCAMV_OFF4(-2, -2, -1, 0)
+                              : j == 2 ? PCAMV_OFF4(1, 2, 3, 4) : PCAMV_OFF4(3, -3, -4, -3);
+            const uint32_t dxs = PCAMV_OFF4(off_at(gx, 0) * i, off_at(gx, 1) * i, off_at(gx, 2) * i, off_at(gx, 3) * i);
+            const uint32_t dys = PCAMV_OFF4(off_at(gy, 0) * i, off_at(gy, 1) * i, off_at(gy, 2) * i, off_at(gy, 3) * i);
+            if (!near_edge)
+                best = try4(b, best, 4, ox, oy, dxs, dys);
+            else
+            {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++)
+                {
+                    const int mx = ox + off_at(dxs, k), my = oy + off_at(dys, k);
+                    if (fpel_in_range(e, mx, my))
+                        best = try1(b, best, mx, my);
+                }
+            }
+        }
+    } while (++i <= me_range / 4);
+    if (pk_y(best_mv(best)) <= e.mv_max_fpel[1])
+    {
+        *run_hex = 1; *hex_range = me_range;
+    }
+    return best;
+}
 
 // half-pel / quarter-pel refinement (reference encoder/me.c:715-843)
 PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int hpel_iters, int qpel_iters,
                              int *p_halfpel_thresh, int b_refine_qpel)
 {
     const int chroma = env.chroma_me && b.i_pixel <= PIX_8x8;
+    const int mbcmp = !env.mbcmp_satd ? COST_SAD : chroma ? COST_SATD_CHROMA : COST_SATD;   // --subme 1: mbcmp is plain SAD
     int bmx = m.mv[0], bmy = m.mv[1], bcost = m.cost;
-    int odir = -1, bdir;
+    int costs[4];
 
     if (hpel_iters && env.subme < 3)
     {
@@ -532,9 +523,7 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
         const int my = clip3(b.mvp[1], env.mv_min_spel[1], env.mv_max_spel[1]);
         if ((mx - bmx) | (my - bmy))
         {
-            int s;
-            sad_cands(b, 1, &mx, &my, &s);
-            s += b.cost_mvx[mx] + b.cost_mvy[my];
+            const int s = eval1(b, COST_SAD, pk(mx, my));
             if (s < bcost) { bcost = s; bmx = mx; bmy = my; }
         }
     }
@@ -542,19 +531,12 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
     for (int i = hpel_iters; i > 0; i--)
     {
         const int omx = bmx, omy = bmy;
-        const int qx[4] = { omx, omx, omx - 2, omx + 2 };
-        const int qy[4] = { omy - 2, omy + 2, omy, omy };
-        int s[4];
-        sad_cands(b, 4, qx, qy, s);
+        eval4(b, COST_SAD, 4, pk(omx, omy - 2), pk(omx, omy + 2), pk(omx - 2, omy), pk(omx + 2, omy), costs);
         // the vertical pair only ever moves bmy (reference COPY2_IF_LT on bmy alone)
-        int c = s[0] + b.cost_mvx[omx] + b.cost_mvy[omy - 2];
-        if (c < bcost) { bcost = c; bmy = omy - 2; }
-        c = s[1] + b.cost_mvx[omx] + b.cost_mvy[omy + 2];
-        if (c < bcost) { bcost = c; bmy = omy + 2; }
-        c = s[2] + b.cost_mvx[omx - 2] + b.cost_mvy[omy];
-        if (c < bcost) { bcost = c; bmx = omx - 2; bmy = omy; }
-        c = s[3] + b.cost_mvx[omx + 2] + b.cost_mvy[omy];
-        if (c < bcost) { bcost = c; bmx = omx + 2; bmy = omy; }
+        if (costs[0] < bcost) { bcost = costs[0]; bmy = omy - 2; }
+        if (costs[1] < bcost) { bcost = costs[1]; bmy = omy + 2; }
+        if (costs[2] < bcost) { bcost = costs[2]; bmx = omx - 2; bmy = omy; }
+        if (costs[3] < bcost) { bcost = costs[3]; bmx = omx + 2; bmy = omy; }
         if (bmx == omx && bmy == omy)
             break;
     }
@@ -563,9 +545,7 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
     {
         if (bmy > env.mv_max_spel[1])
             bmy = env.mv_max_spel[1];
-        int s;
-        satd_cands(b, 1, &bmx, &bmy, chroma, &s, b.fenc, b.fenc_u, b.fenc_v, env.mbcmp_satd);
-        bcost = s + b.cost_mvx[bmx] + b.cost_mvy[bmy];     // bcost was reset to COST_MAX: always taken
+        bcost = eval1(b, mbcmp, pk(bmx, bmy));     // bcost was reset to COST_MAX: always taken
     }
 
     if (p_halfpel_thresh)
@@ -579,26 +559,33 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
             *p_halfpel_thresh = bcost;
     }
 
-    bdir = -1;
+    int bdir = -1;
     for (int i = qpel_iters; i > 0; i--)
     {
-        odir = bdir;
+        const int odir = bdir;
         const int omx = bmx, omy = bmy;
-        // direction d is skipped when it would step straight back (d^1 == odir), except in final refine
-        int qx[4], qy[4], dirs[4], n = 0;
-        const int dx[4] = { 0, 0, -1, 1 }, dy[4] = { -1, 1, 0, 0 };
+        // direction d (0 up, 1 down, 2 left, 3 right) is skipped when it would step straight back (d^1 == odir),
+        // except in the final refine
+        int c[4], dirs[4], n = 0;
+#pragma unroll
         for (int d = 0; d < 4; d++)
-            if (b_refine_qpel || (d ^ 1) != odir)
-            {
-                qx[n] = omx + dx[d]; qy[n] = omy + dy[d]; dirs[n] = d; n++;
-            }
-        int s[4];
-        satd_cands(b, n, qx, qy, chroma, s, b.fenc, b.fenc_u, b.fenc_v, env.mbcmp_satd);
-        for (int k = 0; k < n; k++)
         {
-            const int c = s[k] + b.cost_mvx[qx[k]] + b.cost_mvy[qy[k]];
-            if (c < bcost) { bcost = c; bmx = qx[k]; bmy = qy[k]; bdir = dirs[k]; }
+            const int ddx = d == 2 ? -1 : d == 3 ? 1 : 0, ddy = d == 0 ? -1 : d == 1 ? 1 : 0;
+            const bool take = b_refine_qpel || (d ^ 1) != odir;
+            // compact the taken directions to the front without local-memory indexing
+            if (take)
+            {
+                const int v = pk(omx + ddx, omy + ddy);
+                if (n == 0) { c[0] = v; dirs[0] = d; } else if (n == 1) { c[1] = v; dirs[1] = d; }
+                else if (n == 2) { c[2] = v; dirs[2] = d; } else { c[3] = v; dirs[3] = d; }
+                n++;
+            }
         }
+        if (n < 4) { c[3] = c[0]; dirs[3] = dirs[0]; }
+        eval4(b, mbcmp, n, c[0], c[1], c[2], c[3], costs);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < n && costs[k] < bcost) { bcost = costs[k]; bmx = pk_x(c[k]); bmy = pk_y(c[k]); bdir = dirs[k]; }
         if (bmx == omx && bmy == omy)
             break;
     }
@@ -606,9 +593,7 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
     if (bmy > env.mv_max_spel[1])
     {
         bmy = env.mv_max_spel[1];
-        int s;
-        satd_cands(b, 1, &bmx, &bmy, chroma, &s, b.fenc, b.fenc_u, b.fenc_v, env.mbcmp_satd);
-        bcost = s + b.cost_mvx[bmx] + b.cost_mvy[bmy];
+        bcost = eval1(b, mbcmp, pk(bmx, bmy));
     }
 
     m.cost = bcost;
@@ -619,10 +604,10 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
 
 PCAMV_DEV void subpel_iters(int subme, int out[4])
 {
-    // { refine_hpel, refine_qpel, me_hpel, me_qpel } per --subme level (reference encoder/me.c:34-44)
-    const int t[10][4] = { {0,0,0,0}, {1,1,0,0}, {0,1,1,0}, {0,2,1,0}, {0,2,1,1}, {0,2,1,2},
-                           {0,0,2,2}, {0,0,2,2}, {0,0,4,10}, {0,0,4,10} };
-    for (int i = 0; i < 4; i++) out[i] = t[subme][i];
+    // { refine_hpel, refine_qpel, me_hpel, me_qpel } per --subme level (reference encoder/me.c:34-44), one nibble each
+    const uint32_t t = subme == 1 ? 0x0011u : subme == 2 ? 0x0110u : subme == 3 ? 0x0120u : subme == 4 ? 0x1120u
+                     : subme == 5 ? 0x2120u : subme == 6 || subme == 7 ? 0x2200u : subme >= 8 ? 0xa400u : 0u;
+    out[0] = t & 15; out[1] = (t >> 4) & 15; out[2] = (t >> 8) & 15; out[3] = (t >> 12) & 15;
 }
 
 // Exhaustive search (reference encoder/me.c:483-634, --me esa).  The reference prunes with the
@@ -630,104 +615,104 @@ PCAMV_DEV void subpel_iters(int subme, int out[4])
 // both are pure accelerations of a raster scan (y outer, x inner) with strict-< updates, which is
 // what is restated here.  The scanned width is rounded to a multiple of 4 exactly as the reference
 // rounds it (me.c:491), so up to 3 columns right of max_x are visited and the last one may be cut.
-PCAMV_FN void esa_search(MeSearch &s)
+PCAMV_FN best_t search_esa(const MeEnv &e, const MeBlock &b, best_t best)
 {
-    const int range = s.env.me_range;
-    const int min_x = imax(s.bmx - range, s.mv_x_min), min_y = imax(s.bmy - range, s.mv_y_min);
-    const int max_x = imin(s.bmx + range, s.mv_x_max), max_y = imin(s.bmy + range, s.mv_y_max);
+    const int range = e.me_range;
+    const int bmx = pk_x(best_mv(best)), bmy = pk_y(best_mv(best));
+    const int min_x = imax(bmx - range, e.mv_min_fpel[0]), min_y = imax(bmy - range, e.mv_min_fpel[1]);
+    const int max_x = imin(bmx + range, e.mv_max_fpel[0]), max_y = imin(bmy + range, e.mv_max_fpel[1]);
     const int width = (max_x - min_x + 3) & ~3;
     for (int my = min_y; my <= max_y; my++)
         for (int x = 0; x < width; x += 4)
-            s.try_x4(min_x + x, my, 0, 0, 1, 0, 2, 0, 3, 0);
+            best = try4(b, best, 4, min_x + x, my, PCAMV_OFF4(0, 1, 2, 3), 0);
+    return best;
 }
 
 PCAMV_FN void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)[2], int i_mvc,
                              int *p_halfpel_thresh, MeResult &m)
 {
-    MeSearch s(env, b);
-    int bpred_mx = 0, bpred_my = 0, bpred_cost = PCAMV_COST_MAX;
-
-    s.bmx = clip3(b.mvp[0], s.mv_x_min * 4, s.mv_x_max * 4);
-    s.bmy = clip3(b.mvp[1], s.mv_y_min * 4, s.mv_y_max * 4);
-    const int pmx = (s.bmx + 2) >> 2, pmy = (s.bmy + 2) >> 2;
-    s.bcost = PCAMV_COST_MAX;
+    const int x_min = env.mv_min_fpel[0], y_min = env.mv_min_fpel[1], x_max = env.mv_max_fpel[0], y_max = env.mv_max_fpel[1];
+    int bpred_mv = 0, bpred_cost = PCAMV_COST_MAX;
+    int bmx = clip3(b.mvp[0], x_min * 4, x_max * 4);
+    int bmy = clip3(b.mvp[1], y_min * 4, y_max * 4);
+    const int pmx = (bmx + 2) >> 2, pmy = (bmy + 2) >> 2;
+    best_t best;
 
     if (env.subme >= 3)
     {
-        // predictors at quarter-pel precision: mvp first, then each distinct non-zero candidate
-        int qx[10], qy[10], n = 0;
-        qx[n] = s.bmx; qy[n] = s.bmy; n++;
-        for (int i = 0; i < i_mvc; i++)
+        // predictors at quarter-pel precision: mvp first, then each distinct non-zero candidate; costed four at a
+        // time and folded in order (strict <)
+        int c[4], n = 0;
+        c[0] = c[1] = c[2] = c[3] = pk(bmx, bmy);
+        n = 1;
+        for (int i = 0; i <= i_mvc; i++)
         {
-            const bool nonzero = (mvc[i][0] | mvc[i][1]) != 0;
-            const bool differs = ((mvc[i][0] & 0xffff) != (s.bmx & 0xffff)) || ((mvc[i][1] & 0xffff) != (s.bmy & 0xffff));
-            if (nonzero && differs)
+            bool have = false;
+            int v = 0;
+            if (i < i_mvc)
             {
-                qx[n] = clip3(mvc[i][0], s.mv_x_min * 4, s.mv_x_max * 4);
-                qy[n] = clip3(mvc[i][1], s.mv_y_min * 4, s.mv_y_max * 4);
+                const int cx = mvc[i][0], cy = mvc[i][1];
+                const bool nonzero = (cx | cy) != 0;
+                const bool differs = ((cx & 0xffff) != (bmx & 0xffff)) || ((cy & 0xffff) != (bmy & 0xffff));
+                have = nonzero && differs;
+                v = pk(clip3(cx, x_min * 4, x_max * 4), clip3(cy, y_min * 4, y_max * 4));
+            }
+            if (have)
+            {
+                if (n == 0) c[0] = v; else if (n == 1) c[1] = v; else if (n == 2) c[2] = v; else c[3] = v;
                 n++;
             }
-        }
-        for (int k0 = 0; k0 < n; k0 += 4)
-        {
-            const int nn = imin(4, n - k0);
-            int sad[4];
-            sad_cands(b, nn, qx + k0, qy + k0, sad);
-            for (int k = 0; k < nn; k++)
+            if (n == 4 || (i == i_mvc && n > 0))
             {
-                const int c = sad[k] + b.cost_mvx[qx[k0 + k]] + b.cost_mvy[qy[k0 + k]];
-                if (c < bpred_cost) { bpred_cost = c; bpred_mx = qx[k0 + k]; bpred_my = qy[k0 + k]; }
+                int costs[4];
+                eval4(b, COST_SAD, n, c[0], c[1], c[2], c[3], costs);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < n && costs[k] < bpred_cost) { bpred_cost = costs[k]; bpred_mv = c[k]; }
+                n = 0;
             }
         }
-        s.bmx = (bpred_mx + 2) >> 2;
-        s.bmy = (bpred_my + 2) >> 2;
-        {
-            // COST_MV(bmx,bmy) against bcost = COST_MAX: always taken
-            int sad;
-            const int mx = s.bmx, my = s.bmy;
-            sad_fpel_cands(b, 1, &mx, &my, &sad);
-            s.bcost = sad + s.bits_fpel(mx, my);
-        }
+        bmx = (pk_x(bpred_mv) + 2) >> 2;
+        bmy = (pk_y(bpred_mv) + 2) >> 2;
+        // COST_MV(bmx,bmy) against bcost = COST_MAX: always taken
+        best = try1(b, best_make(PCAMV_COST_MAX, 0), bmx, bmy);
     }
     else
     {
-        {
-            int sad;
-            sad_fpel_cands(b, 1, &pmx, &pmy, &sad);
-            s.bcost = sad;               // COST_MV then minus BITS_MVD(pmx,pmy)
-            s.bmx = pmx; s.bmy = pmy;
-        }
+        // COST_MV then minus BITS_MVD(pmx,pmy): the plain SAD at the rounded predictor
+        best = try1(b, best_make(PCAMV_COST_MAX, 0), pmx, pmy);
+        best = best_make(best_cost(best) - (b.cost_mvx[pmx << 2] + b.cost_mvy[pmy << 2]), pk(pmx, pmy));
         for (int i = 0; i < i_mvc; i++)
         {
             int mx = (mvc[i][0] + 2) >> 2, my = (mvc[i][1] + 2) >> 2;
-            if ((mx | my) && ((mx - s.bmx) | (my - s.bmy)))
+            if ((mx | my) && ((mx - pk_x(best_mv(best))) | (my - pk_y(best_mv(best)))))
             {
-                mx = clip3(mx, s.mv_x_min, s.mv_x_max);
-                my = clip3(my, s.mv_y_min, s.mv_y_max);
-                s.try_fpel1(mx, my);
+                mx = clip3(mx, x_min, x_max);
+                my = clip3(my, y_min, y_max);
+                best = try1(b, best, mx, my);
             }
         }
     }
-    s.try_fpel1(0, 0);
+    best = try1(b, best, 0, 0);
 
-    switch (env.me_method)
-    {
-    case ME_DIA: s.search_dia(env.me_range); break;
-    case ME_HEX: s.hex_then_square(env.me_range); break;
-    case ME_UMH: s.search_umh(pmx, pmy, mvc, i_mvc); break;
-    default:     esa_search(s); break;
-    }
+    int run_hex = env.me_method == ME_HEX, hex_range = env.me_range;
+    if (env.me_method == ME_DIA) best = search_dia(env, b, best, env.me_range);
+    else if (env.me_method == ME_UMH) best = search_umh(env, b, best, pmx, pmy, mvc, i_mvc, &run_hex, &hex_range);
+    else if (env.me_method != ME_HEX) best = search_esa(env, b, best);
+    if (run_hex)
+        best = search_hex(env, b, best, hex_range);
 
-    if (bpred_cost < s.bcost)
+    bmx = pk_x(best_mv(best)); bmy = pk_y(best_mv(best));
+    if (bpred_cost < best_cost(best))
     {
-        m.mv[0] = bpred_mx; m.mv[1] = bpred_my; m.cost = bpred_cost;
+        m.mv[0] = pk_x(bpred_mv); m.mv[1] = pk_y(bpred_mv); m.cost = bpred_cost;
     }
     else
     {
-        m.mv[0] = s.bmx << 2; m.mv[1] = s.bmy << 2; m.cost = s.bcost;
+        m.mv[0] = bmx << 2; m.mv[1] = bmy << 2; m.cost = best_cost(best);
     }
     m.cost_mv = b.cost_mvx[m.mv[0]] + b.cost_mvy[m.mv[1]];
-    if (s.bmx == pmx && s.bmy == pmy && env.subme < 3)
+    if (bmx == pmx && bmy == pmy && env.subme < 3)
         m.cost += m.cost_mv;
 
     if (env.subme >= 2)

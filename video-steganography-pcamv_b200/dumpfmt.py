@@ -160,7 +160,7 @@ class Dump:
         return units
 
     def counters(self):
-        """'CNT0' records in file order (one per dumped P-slice pass): cumulative work counters of the reference."""
+        """'CNT0' records in file order (one per dumped P-slice pass): the reference's work counters of that pass."""
         names = ["sad", "satd", "ih_luma", "ih_chroma", "pix_sad", "pix_satd", "searches", "refines", "ih_calls"]
         out = []
         for tag, off, size in self.records:

@@ -66,7 +66,7 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_put_fenc", "pcamv_put_ref", "pcamv_put_ref_planes", "pcamv_get_ref_plane", "pcamv_plane_bytes",
            "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
            "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
-           "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download"]
+           "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace"]
 
 _lib = None
 
@@ -100,8 +100,9 @@ def load_library(path=None):
     lib.pcamv_int_peak.argtypes = [vp, C.POINTER(C.c_double)]; lib.pcamv_int_peak.restype = ip
     lib.pcamv_analyse_p.argtypes = [vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_analyse_p.restype = ip
     lib.pcamv_frame_upload.argtypes = [vp, C.POINTER(FrameIn)]; lib.pcamv_frame_upload.restype = ip
-    lib.pcamv_frame_run.argtypes = [vp, ip, ip, C.POINTER(C.c_float)]; lib.pcamv_frame_run.restype = ip
+    lib.pcamv_frame_run.argtypes = [vp, ip, ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]; lib.pcamv_frame_run.restype = ip
     lib.pcamv_frame_download.argtypes = [vp, vp, vp]; lib.pcamv_frame_download.restype = ip
+    lib.pcamv_frame_trace.argtypes = [vp, ip, vp]; lib.pcamv_frame_trace.restype = ip
     if path == build.LIB:
         _lib = lib
     return lib
@@ -260,10 +261,12 @@ class PcamvContext:
         fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
         self._check(self.lib.pcamv_frame_upload(self.handle, C.byref(fi)))
 
-    def frame_run(self, pass_=-1, iters=1):
+    def frame_run(self, pass_=-1, iters=1, per_kernel=False):
+        """Mean device ms of one analysis; with per_kernel also (wavefront ms, cost-table ms)."""
         ms = C.c_float()
-        self._check(self.lib.pcamv_frame_run(self.handle, pass_, iters, C.byref(ms)))
-        return float(ms.value)
+        mk = (C.c_float * 2)()
+        self._check(self.lib.pcamv_frame_run(self.handle, pass_, iters, C.byref(ms), mk if per_kernel else None))
+        return (float(ms.value), float(mk[0]), float(mk[1])) if per_kernel else float(ms.value)
 
     def frame_download(self, want_log=True):
         n_mb = (self.width // 16) * (self.height // 16)
@@ -271,6 +274,13 @@ class PcamvContext:
         log = np.zeros((n_mb, LOG_MAX), dtype=LOG_ENTRY_DTYPE) if want_log else None
         self._check(self.lib.pcamv_frame_download(self.handle, _ptr(mbs), _ptr(log) if want_log else None))
         return mbs, log
+
+    def frame_trace(self, enable=True, fetch=False):
+        """Switch per-macroblock timestamps on/off; with fetch, return the [n_mb, 2] ns records of the last traced launch."""
+        n_mb = (self.width // 16) * (self.height // 16)
+        out = np.zeros((n_mb, 2), dtype=np.uint64) if fetch else None
+        self._check(self.lib.pcamv_frame_trace(self.handle, int(enable), _ptr(out) if fetch else None))
+        return out
 
     def int_peak_gops(self):
         g = C.c_double()

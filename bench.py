@@ -157,8 +157,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--streams", type=int, default=16,
+                    help="independent encoder contexts (GOP shards / streams) analysing concurrently on each GPU")
+    ap.add_argument("--rows-per-cta", type=int, default=4, help="wavefront layout used when --streams > 1 (pcamv_cfg.rows_per_cta)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (profiling runs)")
     args = ap.parse_args()
+
+    # one hardware work queue per context stream (the default of 8 would serialise contexts 9..S behind the first 8)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
     import pcamv_loader
     pcamv = pcamv_loader.load()
@@ -179,6 +185,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import frame_parity
+    S = max(1, args.streams)
     workdir = tempfile.mkdtemp(prefix="pcamv_bench_%d_" % rank)
     clip, dumpf = prepare_inputs(pcamv, rank, workdir)
     dump = pcamv.dumpfmt.Dump(dumpf)
@@ -190,13 +197,13 @@ def main():
     cnt = dump.counters()
     assert len(cnt) == 2, "expected the counters of two passes, got %d" % len(cnt)
     work = {k: cnt[0][k] + cnt[1][k] for k in ("sad", "satd", "ih_luma", "ih_chroma", "pix_sad", "pix_satd")}
-    cand_per_step = candidates_of(work)
-    # integer-op count per step, reference-counted: SAD 2 ops/pixel, SATD 7 ops/pixel
-    ops_per_step = 2.0 * work["pix_sad"] + 7.0 * work["pix_satd"]
+    cand_per_frame = candidates_of(work)
+    # integer-op count per frame, reference-counted: SAD 2 ops/pixel, SATD 7 ops/pixel
+    ops_per_frame = 2.0 * work["pix_sad"] + 7.0 * work["pix_satd"]
 
     # ---- parity gate before any number ---------------------------------------------------------------------------
-    ctx = frame_parity.open_ctx(pcamv, dump, s, device=local_rank)
-    par = frame_parity.check_dump(pcamv, dump, units=units, ctx=ctx, keep_ctx=True)       # raises on the first mismatch
+    ctxs = [frame_parity.open_ctx(pcamv, dump, s, device=local_rank, rows_per_cta=args.rows_per_cta if S > 1 else 1) for _ in range(S)]
+    par = frame_parity.check_dump(pcamv, dump, units=units, ctx=ctxs[0], keep_ctx=True)       # raises on the first mismatch
 
     x = units[0]["ctx"]
     H, W = s.lines_y, s.width
@@ -210,75 +217,89 @@ def main():
     e = units[0]["embd"]
     pass1 = frame_parity.pass1_records(pcamv, e)
     refs, pocs, cur_poc = list(range(x["n_ref"])), x["ref_poc"][:x["n_ref"]], x["cur_poc"]
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    n_mb = (W // 16) * (H // 16)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ---------------------------------------------------------------------------------------
-    ctx.put_fenc(fy, fu, fv)
-    ctx.put_ref(0, r["poc"], ry, ru, rv)
-    ctx.frame_upload(1, refs, pocs, cur_poc, cost_table=True, **col)
-    mbs1, _ = ctx.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
-    stale = mbs1["mv"][-1]
-    ctx.frame_upload(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=stale, **col)
+    def run_threads(fn):
+        """fn(i) on one host thread per context (the C-ABI calls release the GIL), all started together."""
+        out = [None] * S
+        def wrap(i):
+            out[i] = fn(i)
+        th = [threading.Thread(target=wrap, args=(i,)) for i in range(S)]
+        for t in th: t.start()
+        for t in th: t.join()
+        return out
 
-    def dev_step():
-        flush.zero_(); torch.cuda.synchronize()
-        _, w1, ct = ctx.frame_run(1, 1, per_kernel=True)
-        flush.zero_(); torch.cuda.synchronize()
-        _, w2, _ = ctx.frame_run(2, 1, per_kernel=True)
-        return w1, ct, w2
+    # ---- device-resident arm: every context holds its own copy of the frame inputs in HBM ---------------------------
+    def stage(i):
+        c = ctxs[i]
+        c.put_fenc(fy, fu, fv)
+        c.put_ref(0, r["poc"], ry, ru, rv)
+        c.frame_upload(1, refs, pocs, cur_poc, cost_table=True, **col)
+        m1, _ = c.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
+        c.frame_upload(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], **col)
+        return m1
+    staged = run_threads(stage)
+    assert all((m["mv"] == staged[0]["mv"]).all() for m in staged)
 
-    for _ in range(args.warmup):
-        dev_step()
+    def dev_steps(i, k):
+        c = ctxs[i]
+        acc = np.zeros(3)
+        for _ in range(k):
+            _, w1, ct = c.frame_run(1, 1, per_kernel=True)      # CUDA events around each kernel on the context's stream
+            _, w2, _ = c.frame_run(2, 1, per_kernel=True)
+            acc += (w1, ct, w2)
+        return acc
+    run_threads(lambda i: dev_steps(i, args.warmup))
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    launches0 = ctx.launch_count()
-    k_ms = []
-    for _ in range(args.steps):
-        k_ms.append(dev_step())                  # CUDA events around each kernel on the context's stream
+    launches0 = sum(c.launch_count() for c in ctxs)
+    t0 = time.perf_counter()
+    k_ms = run_threads(lambda i: dev_steps(i, args.steps))
+    torch.cuda.synchronize()
+    dev_s = time.perf_counter() - t0
     barrier()
-    k_ms = np.array(k_ms)
-    dev_s = float(k_ms.sum()) * 1e-3
-    n_launch = ctx.launch_count() - launches0
+    k_ms = np.array(k_ms) / args.steps            # [S, 3] mean kernel durations per context while all S run concurrently
+    n_launch = sum(c.launch_count() for c in ctxs) - launches0
 
-    # ---- end-to-end arm: host buffers in, host records out ------------------------------------------------------------
-    def e2e_step():
-        ctx.put_fenc(fy, fu, fv)
-        ctx.put_ref(0, r["poc"], ry, ru, rv)
-        m1, l1 = ctx.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
-        m2, l2 = ctx.analyse_p(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], **col)
+    # ---- end-to-end arm: host buffers in, host records out, S encoder threads ------------------------------------------
+    def e2e_steps(i, k):
+        c = ctxs[i]
+        for _ in range(k):
+            c.put_fenc(fy, fu, fv)
+            c.put_ref(0, r["poc"], ry, ru, rv)
+            m1, l1 = c.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
+            m2, l2 = c.analyse_p(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], **col)
         return m1, l1, m2, l2
-    for _ in range(args.warmup):
-        e2e_step()
+    run_threads(lambda i: e2e_steps(i, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = e2e_step()
+    outs = run_threads(lambda i: e2e_steps(i, args.steps))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.result()
-    n_launch_e2e = ctx.launch_count() - launches0 - n_launch
-    n_mb = len(out[0])
+    n_launch_e2e = sum(c.launch_count() for c in ctxs) - launches0 - n_launch
+    out = outs[0]
+    assert all((o[2]["mv"] == out[2]["mv"]).all() and (o[2]["type"] == out[2]["type"]).all() for o in outs)
     h2d = 2 * (fy.nbytes + fu.nbytes + fv.nbytes) + 2 * 68 * n_mb + n_mb * pcamv.host.PASS1_MB_DTYPE.itemsize + len(e["filp"])
     d2h = out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes
 
-    int_peak = ctx.int_peak_gops()
+    int_peak = ctxs[0].int_peak_gops()
 
     # ---- aggregate over ranks (max time, summed work) ----------------------------------------------------------------
     tt = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
-    ww = torch.tensor([float(cand_per_step)], dtype=torch.float64, device="cuda")
+    ww = torch.tensor([float(cand_per_frame) * S], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
     dev_s_max, e2e_s_max = [float(v) for v in tt.tolist()]
-    cand_all = float(ww.item())
+    cand_all = float(ww.item())           # candidates of one step over all ranks and contexts
 
     if rank == 0:
         value = cand_all * args.steps / dev_s_max / 1e6
@@ -288,46 +309,50 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_peak = peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6650.0))
         ms_w1, ms_ct, ms_w2 = [float(v) for v in k_ms.mean(axis=0)]
         kernels = {"k_analyse_p(pass1)": ms_w1, "k_cost_table": ms_ct, "k_analyse_p(pass2)": ms_w2}
         dom = max(kernels, key=kernels.get)
         # algorithmic HBM bytes of one launch of either kernel: fenc once, 4 luma + 2 chroma reference planes once,
-        # per-MB records in/out (DESIGN.md "HBM traffic")
-        plane_y = ctx.plane_bytes(0); plane_c = ctx.plane_bytes(4)
+        # per-MB records in/out (DESIGN.md "HBM traffic"); S launches of the dominant kernel overlap, so the achieved
+        # figure is S launches' bytes over the mean launch duration
+        plane_y = ctxs[0].plane_bytes(0); plane_c = ctxs[0].plane_bytes(4)
         alg_bytes = fy.nbytes + fu.nbytes + fv.nbytes + 4 * plane_y + 2 * plane_c + n_mb * (128 + 48 * 16 + 68)
-        achieved = alg_bytes / (kernels[dom] * 1e-3) / 1e9
-        step_ms = ms_w1 + ms_ct + ms_w2
+        achieved = S * alg_bytes / (kernels[dom] * 1e-3) / 1e9
+        frames_all = world * S * args.steps
         line = {
             "metric": METRIC, "value": value, "unit": "Mcandidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD,
-                       "step": "one 1080p P frame through the frame seam: wavefront analysis pass 1 + candidate-MV cost table + "
-                               "wavefront analysis pass 2 (%d searches/refines, %d cost-table entries)" % (par["calls"], par["ih"]),
-                       "candidates_per_step": int(cand_per_step), "l2": "flushed before every timed kernel sequence (256 MiB write)",
+                       "step": "one 1080p P frame through the frame seam in each of %d independent encoder contexts per GPU (GOP shards: own "
+                               "CUDA stream, own frame buffers): wavefront analysis pass 1 + candidate-MV cost table + wavefront analysis "
+                               "pass 2 (%d searches/refines, %d cost-table entries per frame)" % (S, par["calls"], par["ih"]),
+                       "contexts_per_gpu": S, "candidates_per_frame": int(cand_per_frame),
+                       "l2": "inputs larger than L2: %d contexts x %.1f MB of planes each, no flush" % (S, (alg_bytes) / 1e6),
                        "parity_gate": "passed: %d searches, %d macroblock decisions, %d cost-table entries bit-exact vs reference"
                                       % (par["calls"], par["mbs"], par["ih"])},
-            "analysed_p_frames_per_sec": world * args.steps / dev_s_max,
+            "analysed_p_frames_per_sec": frames_all / dev_s_max,
             "kernel_ms": kernels,
-            "e2e": {"value": e2e_v, "unit": "Mcandidates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s_max / args.steps * 1e3, "analysed_p_frames_per_sec": world * args.steps / e2e_s_max},
+            "e2e": {"value": e2e_v, "unit": "Mcandidates/s", "h2d_bytes_per_step": int(h2d) * S, "d2h_bytes_per_step": int(d2h) * S,
+                    "ms_per_step": e2e_s_max / args.steps * 1e3, "analysed_p_frames_per_sec": frames_all / e2e_s_max},
             "gpu_launches": int(n_launch + n_launch_e2e),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "kernel": dom,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "note": "the analysis kernels are integer-issue / dependency-latency bound, not HBM bound (SURVEY.md 8(d)); "
                                  "see int_issue"},
-            "int_issue": {"achieved_gops": ops_per_step / (step_ms * 1e-3) / 1e9, "peak_gops": int_peak,
-                          "frac": ops_per_step / (step_ms * 1e-3) / 1e9 / int_peak,
-                          "ops": "reference-counted: 2/pixel SAD, 7/pixel SATD over the whole step",
+            "int_issue": {"achieved_gops": ops_per_frame * frames_all / dev_s_max / 1e9 / world, "peak_gops": int_peak,
+                          "frac": ops_per_frame * frames_all / dev_s_max / 1e9 / world / int_peak,
+                          "ops": "reference-counted per GPU: 2/pixel SAD, 7/pixel SATD",
                           "peak_source": "pcamv_int_peak microbenchmark on this box"},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(pcamv, clip, workdir)
         print(json.dumps(line))
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -63,7 +63,9 @@ typedef struct pcamv_cfg
     int b_dct_decimate;     /* param.analyse.b_dct_decimate */
     int analyse_inter;      /* param.analyse.inter flag word (X264_ANALYSE_PSUB16x16 = 0x10, PSUB8x8 = 0x20) */
     int chroma_qp_offset;   /* pps chroma_qp_index_offset */
-    int reserved[8];
+    int rows_per_cta;       /* wavefront layout: 0/1 = one macroblock row per CTA (lowest latency, a single encoder);
+                               2 or 4 = consecutive rows share a CTA (throughput, many concurrent contexts per GPU) */
+    int reserved[7];
 } pcamv_cfg;
 
 /* Per-QP tables.  They are built on the host because the reference builds cost_mv with float

@@ -126,7 +126,7 @@ PCAMV_FN int ih_get_mv_cost(MbCtx &c, const MbResult &res, int k, int &m_x, int 
 {
     const PartInfo &pi = res.part[k];
     const int bmx = pi.mv[0], bmy = pi.mv[1];
-    MeBlock b;
+    MeBlock &b = c.w.blk;
     setup_block(c, b, pi.ref, pi.i_pixel, pi.xoff, pi.yoff);
     block_set_mvp(b, c.env, pi.mvp[0], pi.mvp[1]);
     // the block being compared is the RECONSTRUCTION of this partition, not the source

@@ -21,6 +21,24 @@
 
 namespace pcamv {
 
+// Per-macroblock state lives in SHARED memory, one copy per lane team: the control flow of the analysis is executed
+// redundantly by every lane (uniform values), and keeping that state in per-thread local memory costs 32 copies of it
+// in L1 per resident team (2 KB x 32 lanes) — with tens of encoder contexts resident the stacks alone evicted the
+// reference windows from L1.
+struct MeSlot            // the fields of x264_me_t that survive a search (per partition)
+{
+    MeResult r;
+    int mvp[2];
+    int i_ref, i_ref_cost, i_pixel, xoff, yoff;
+};
+
+struct MbAnalysis
+{
+    MeSlot me16x16, me8x8[4], me16x8[2], me8x16[2];
+    int mvc[PCAMV_MAX_REFS][5][2];        // [ref][0] = 16x16 result, [ref][1..4] = 8x8 results
+    int cost8x8, cost16x8, cost8x16;
+};
+
 // team-shared scratch of one macroblock
 struct alignas(16) MbWork
 {
@@ -30,6 +48,11 @@ struct alignas(16) MbWork
     uint8_t pred_y[256], pred_u[64], pred_v[64];     // MC / reconstruction staging
     int32_t scratch[32];
     int16_t coef[24][16];    // per 4x4 block (16 luma in block_idx order, 4 U, 4 V): quantised / dequantised coefficients
+    MbAnalysis an;           // search results of the partitions tried so far
+    MeSlot slot;             // the search in flight
+    MeBlock blk;             // its block descriptor
+    int mvc[PCAMV_MAX_MVC][2];
+    int halfpel_thresh;
 };
 
 // Loads of per-frame motion state written by OTHER macroblocks of the running wavefront (possibly on another SM):
@@ -67,7 +90,7 @@ struct MbCtx
     PCAMV_MEM MbCtx(const DevFrameCtx &f, const FrameParams &p, MbWork &wk) : fc(f), fp(p), w(wk) {}
 };
 
-PCAMV_DEV void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int mvy, int cost, int cost_mv)
+PCAMV_FN void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int mvy, int cost, int cost_mv)
 {
     if (c.n_log < PCAMV_LOG_MAX && team_lane() == 0)
     {
@@ -80,9 +103,11 @@ PCAMV_DEV void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int
 }
 
 // ---- neighbour cache -------------------------------------------------------------------------------
-PCAMV_DEV void cache_fill_rect(MbCtx &c, int x, int y, int wd, int ht, int ref, uint32_t mv, int set_ref, int set_mv)
+PCAMV_FN void cache_fill_rect(MbCtx &c, int x, int y, int wd, int ht, int ref, uint32_t mv, int set_ref, int set_mv)
 {
+#pragma unroll 1
     for (int j = 0; j < ht; j++)
+#pragma unroll 1
         for (int i = 0; i < wd; i++)
         {
             const int k = 12 + x + i + 8 * (y + j);
@@ -91,7 +116,7 @@ PCAMV_DEV void cache_fill_rect(MbCtx &c, int x, int y, int wd, int ht, int ref, 
         }
 }
 
-PCAMV_DEV void cache_load(MbCtx &c)
+PCAMV_FN void cache_load(MbCtx &c)
 {
     const int mb_w = c.fc.mb_w, s8 = 2 * mb_w, s4 = 4 * mb_w;
     const int mb_x = c.mb_x, mb_y = c.mb_y;
@@ -105,6 +130,7 @@ PCAMV_DEV void cache_load(MbCtx &c)
     c.type_topright = topright ? PCAMV_LDV(a.type + top_xy + 1) : -1;
     c.type_topleft = topleft ? PCAMV_LDV(a.type + top_xy - 1) : -1;
     // positions never written for the current MB keep "unavailable" (the reference memsets the cache to -2 once)
+#pragma unroll 1
     for (int k = 0; k < 48; k++) { c.w.ref[k] = -2; c.w.mv[k] = 0; }
     if (topleft) { c.w.ref[3] = PCAMV_LDV(a.ref8 + top8 - 1); c.w.mv[3] = PCAMV_LDV(a.mv4 + top4 - 1); }
     if (top)
@@ -135,14 +161,14 @@ PCAMV_DEV uint32_t predict_from(int i_ref, int refa, uint32_t mva, int refb, uin
     return median_mv(mva, mvb, mvc);
 }
 
-PCAMV_DEV uint32_t predict_mv_16x16(const MbCtx &c, int i_ref)
+PCAMV_FN uint32_t predict_mv_16x16(const MbCtx &c, int i_ref)
 {
     int refc = c.w.ref[8]; uint32_t mvc = c.w.mv[8];
     if (refc == -2) { refc = c.w.ref[3]; mvc = c.w.mv[3]; }
     return predict_from(i_ref, c.w.ref[11], c.w.mv[11], c.w.ref[4], c.w.mv[4], refc, mvc);
 }
 
-PCAMV_DEV uint32_t predict_mv(const MbCtx &c, int idx, int width)
+PCAMV_FN uint32_t predict_mv(const MbCtx &c, int idx, int width)
 {
     const int i8 = scan8(idx);
     const int i_ref = c.w.ref[i8];
@@ -176,7 +202,7 @@ PCAMV_DEV uint32_t predict_mv_pskip(const MbCtx &c)
 }
 
 // candidate list of the 16x16 search: neighbours' 16x16 search results + temporally scaled co-located MVs
-PCAMV_DEV int predict_mv_ref16x16(const MbCtx &c, int i_ref, int (*mvc)[2])
+PCAMV_FN int predict_mv_ref16x16(const MbCtx &c, int i_ref, int (*mvc)[2])
 {
     const int mb_w = c.fc.mb_w, n_mb = mb_w * c.fc.mb_h;
     const uint32_t *mvr = c.fp.cur.mvr + (size_t)i_ref * n_mb;
@@ -196,6 +222,7 @@ PCAMV_DEV int predict_mv_ref16x16(const MbCtx &c, int i_ref, int (*mvc)[2])
     {
         const int s8 = 2 * mb_w, s4 = 4 * mb_w;
         const int cur8 = 2 * c.mb_y * s8 + 2 * c.mb_x, cur4 = 4 * c.mb_y * s4 + 4 * c.mb_x;
+#pragma unroll 1
         for (int k = 0; k < 3; k++)
         {
             const int dx = k == 1, dy = k == 2;
@@ -216,7 +243,7 @@ PCAMV_DEV int predict_mv_ref16x16(const MbCtx &c, int i_ref, int (*mvc)[2])
 }
 
 // ---- MV limits (reference encoder/analyse.c:271-318; single thread, progressive) -------------------
-PCAMV_DEV void init_limits(MbCtx &c)
+PCAMV_FN void init_limits(MbCtx &c)
 {
     const int fmv = 4 * c.fc.mv_range;
     c.mv_min[0] = 4 * (-16 * c.mb_x - 24);
@@ -540,13 +567,6 @@ PCAMV_FN int probe_pskip(MbCtx &c)
 // =======================================================================================================
 // Search drivers
 // =======================================================================================================
-struct MeSlot            // the fields of x264_me_t that survive a search (per partition)
-{
-    MeResult r;
-    int mvp[2];
-    int i_ref, i_ref_cost, i_pixel, xoff, yoff;
-};
-
 PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, int xoff, int yoff)
 {
     const DevRef &rf = c.fc.ref[c.fp.ref_slot[i_ref]];
@@ -562,9 +582,9 @@ PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, i
     b.integral = nullptr;
 }
 
-PCAMV_DEV void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
+PCAMV_FN void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
 {
-    MeBlock b;
+    MeBlock &b = c.w.blk;
     setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
     s.mvp[0] = mv_x(mvp); s.mvp[1] = mv_y(mvp);
     block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
@@ -573,9 +593,9 @@ PCAMV_DEV void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2]
     log_push(c, LOG_SEARCH, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
 }
 
-PCAMV_DEV void run_refine(MbCtx &c, MeSlot &s)
+PCAMV_FN void run_refine(MbCtx &c, MeSlot &s)
 {
-    MeBlock b;
+    MeBlock &b = c.w.blk;
     setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
     block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
     me_refine_qpel(c.env, b, s.r, s.i_ref_cost);
@@ -587,27 +607,22 @@ PCAMV_DEV int ref_cost(const MbCtx &c, int i_ref)
     return c.fc.tab.cost_ref[clip3(c.fp.n_ref - 1, 0, 2) * 33 + i_ref];
 }
 
-struct MbAnalysis
-{
-    MeSlot me16x16, me8x8[4], me16x8[2], me8x16[2];
-    int mvc[PCAMV_MAX_REFS][5][2];        // [ref][0] = 16x16 result, [ref][1..4] = 8x8 results
-    int cost8x8, cost16x8, cost8x16;
-};
-
 // 16x16 search over all references; returns 1 when the early P_SKIP termination fired
 PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_pskip)
 {
     const int lambda = c.fc.tab.lambda;
-    int halfpel_thresh = 0x7fffffff;
+    int &halfpel_thresh = c.w.halfpel_thresh;
+    halfpel_thresh = 0x7fffffff;
     int *p_thresh = c.fp.n_ref > 1 ? &halfpel_thresh : nullptr;
     a.me16x16.r.cost = 0x7fffffff;
+#pragma unroll 1
     for (int i_ref = 0; i_ref < c.fp.n_ref; i_ref++)
     {
-        MeSlot m;
+        MeSlot &m = c.w.slot;
         const int rc = ref_cost(c, i_ref);
         halfpel_thresh -= rc;
         m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_16x16; m.xoff = 0; m.yoff = 0;
-        int mvc[PCAMV_MAX_MVC][2];
+        int (*mvc)[2] = c.w.mvc;
         const uint32_t mvp = predict_mv_16x16(c, i_ref);
         const int i_mvc = predict_mv_ref16x16(c, i_ref, mvc);
         run_search(c, m, mvp, mvc, i_mvc, p_thresh);
@@ -634,6 +649,7 @@ PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
     c.partition = PART_8x8;
     int i_mvc = 1;
     mvc[0][0] = a.me16x16.r.mv[0]; mvc[0][1] = a.me16x16.r.mv[1];
+#pragma unroll 1
     for (int i = 0; i < 4; i++)
     {
         MeSlot &m = a.me8x8[i];
@@ -656,6 +672,7 @@ PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
 {
     c.partition = dir ? PART_8x16 : PART_16x8;
     int total = 0;
+#pragma unroll 1
     for (int i = 0; i < 2; i++)
     {
         MeSlot &best = dir ? a.me8x16[i] : a.me16x8[i];
@@ -663,14 +680,15 @@ PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
         const int r1 = dir ? a.me8x8[i + 2].i_ref : a.me8x8[2 * i + 1].i_ref;
         const int nrefs = r0 == r1 ? 1 : 2;
         best.r.cost = 0x7fffffff;
+#pragma unroll 1
         for (int j = 0; j < nrefs; j++)
         {
             const int i_ref = j ? r1 : r0;
-            MeSlot m;
+            MeSlot &m = c.w.slot;
             m.i_ref = i_ref; m.i_ref_cost = ref_cost(c, i_ref);
             m.i_pixel = dir ? PIX_8x16 : PIX_16x8;
             m.xoff = dir ? 8 * i : 0; m.yoff = dir ? 0 : 8 * i;
-            int mvc[3][2];
+            int (*mvc)[2] = c.w.mvc;
             const int k1 = dir ? i + 1 : 2 * i + 1, k2 = dir ? i + 3 : 2 * i + 2;
             mvc[0][0] = a.mvc[i_ref][0][0]; mvc[0][1] = a.mvc[i_ref][0][1];
             mvc[1][0] = a.mvc[i_ref][k1][0]; mvc[1][1] = a.mvc[i_ref][k1][1];
@@ -691,7 +709,7 @@ PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
 }
 
 // write the decided mode into the neighbour cache (x264_analyse_update_cache, P part)
-PCAMV_DEV void update_cache(MbCtx &c, const MbAnalysis &a, int type, int partition)
+PCAMV_FN void update_cache(MbCtx &c, const MbAnalysis &a, int type, int partition)
 {
     if (type == MB_P_SKIP)
     {
@@ -701,18 +719,21 @@ PCAMV_DEV void update_cache(MbCtx &c, const MbAnalysis &a, int type, int partiti
     if (partition == PART_16x16)
         cache_fill_rect(c, 0, 0, 4, 4, a.me16x16.i_ref, pack_mv(a.me16x16.r.mv[0], a.me16x16.r.mv[1]), 1, 1);
     else if (partition == PART_16x8)
+#pragma unroll 1
         for (int i = 0; i < 2; i++)
             cache_fill_rect(c, 0, 2 * i, 4, 2, a.me16x8[i].i_ref, pack_mv(a.me16x8[i].r.mv[0], a.me16x8[i].r.mv[1]), 1, 1);
     else if (partition == PART_8x16)
+#pragma unroll 1
         for (int i = 0; i < 2; i++)
             cache_fill_rect(c, 2 * i, 0, 2, 4, a.me8x16[i].i_ref, pack_mv(a.me8x16[i].r.mv[0], a.me8x16[i].r.mv[1]), 1, 1);
     else
+#pragma unroll 1
         for (int i = 0; i < 4; i++)
             cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, a.me8x8[i].i_ref, pack_mv(a.me8x8[i].r.mv[0], a.me8x8[i].r.mv[1]), 1, 1);
 }
 
 // store the MB's final state to the frame arrays (x264_macroblock_cache_save, inter part) and the result record
-PCAMV_DEV void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition, int early_skip)
+PCAMV_FN void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition, int early_skip)
 {
     const int mb_w = c.fc.mb_w, s8 = 2 * mb_w, s4 = 4 * mb_w;
     const int cur8 = 2 * c.mb_y * s8 + 2 * c.mb_x, cur4 = 4 * c.mb_y * s4 + 4 * c.mb_x;
@@ -722,18 +743,21 @@ PCAMV_DEV void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partitio
         fa.type[c.mb_xy] = (int8_t)type;
         fa.ref8[cur8] = c.w.ref[12]; fa.ref8[cur8 + 1] = c.w.ref[14];
         fa.ref8[cur8 + s8] = c.w.ref[28]; fa.ref8[cur8 + s8 + 1] = c.w.ref[30];
+#pragma unroll 1
         for (int y = 0; y < 4; y++)
             for (int x = 0; x < 4; x++)
                 fa.mv4[cur4 + y * s4 + x] = c.w.mv[12 + x + 8 * y];
         MbResult r;
         r.type = (int8_t)type; r.partition = (int8_t)partition; r.early_skip = (int8_t)early_skip;
         r.ref[0] = c.w.ref[12]; r.ref[1] = c.w.ref[14]; r.ref[2] = c.w.ref[28]; r.ref[3] = c.w.ref[30];
+#pragma unroll 1
         for (int i = 0; i < 16; i++) r.mv[i] = c.w.mv[scan8(i)];
         r.n_part = 0;
         if (type != MB_P_SKIP)
         {
             const int np = partition == PART_16x16 ? 1 : partition == PART_8x8 ? 4 : 2;
             r.n_part = (int8_t)np;
+#pragma unroll 1
             for (int i = 0; i < np; i++)
             {
                 const MeSlot &m = partition == PART_16x16 ? a.me16x16 : partition == PART_16x8 ? a.me16x8[i]
@@ -772,7 +796,7 @@ PCAMV_DEV void wait_prev_raster(const MbCtx &c)
 PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
 {
     const DevFrameCtx &fc = c.fc;
-    MbAnalysis a;
+    MbAnalysis &a = c.w.an;
     c.n_log = 0;
     c.partition = PART_16x16;
     cache_load(c);
@@ -819,6 +843,7 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
             // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
             // and the refs are what the 16x16 search left (its best reference)
             wait_prev_raster(c);
+#pragma unroll 1
             for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = PCAMV_LDV(prev_mv + i);
         }
         finalize_mb(c, a, MB_P_SKIP, PART_16x16, early_skip);
@@ -851,8 +876,10 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     {
         // pass 2: type / partition / refs / MVs come from pass 1 with the embedding flips applied
         type = forced->type; partition = forced->partition;
+#pragma unroll 1
         for (int i = 0; i < 4; i++)
             cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
+#pragma unroll 1
         for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
         // the analysis slots keep the searched values; neighbours only ever see the cache
     }

@@ -11,7 +11,7 @@
 using namespace pcamv;
 
 namespace pcamv {
-void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_ctas, void *stream);
+void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_rows, int rows_per_cta, void *stream);
 void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream);
 }
 
@@ -129,7 +129,7 @@ static int launch_frame(pcamv_ctx *ctx, int pass, cudaEvent_t *ev = nullptr)
     ctx->fp[pass].trace = ctx->trace_on ? ctx->d_trace : nullptr;
     CK(cudaMemsetAsync(ctx->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
     if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
-    launch_analyse_p(fc, ctx->fp[pass], ctx->d_progress + fc.mb_h, fc.mb_h, ctx->stream);
+    launch_analyse_p(fc, ctx->fp[pass], ctx->d_progress + fc.mb_h, fc.mb_h, ctx->cfg.rows_per_cta, ctx->stream);
     ctx->launches += 1;
     if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
     if (pass == 1 && ctx->frame_cost_table)

@@ -8,12 +8,13 @@
 //
 // Wavefront: a macroblock needs its left, top-left, top and top-right neighbours (MV prediction,
 // common/macroblock.c:28-163,388-470,1085-1224).  One lane team (warp) owns one macroblock ROW and walks it
-// left to right; before macroblock x it waits until the row above has finished x+1 (its top-right).  Rows are
-// claimed from an atomic counter in increasing order, so every row a claimed row waits on is owned by a team
-// that is already running: the scheme cannot deadlock for any grid size.  Progress is published with
+// left to right; before macroblock x it waits until the row above has finished x+1 (its top-right).  Groups of
+// AP_WARPS consecutive rows are claimed by a CTA from an atomic counter in increasing order, so every row a claimed
+// row waits on is owned by a team that is already running: the scheme cannot deadlock for any grid size.  Progress is published with
 // st.release.gpu after the macroblock's state is in HBM and consumed with ld.acquire.gpu.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <new>
 #include "pcamv_device.h"
 #include "pcamv_cost.cuh"
 
@@ -50,32 +51,45 @@ __device__ __forceinline__ void stage_fenc(const DevFrameCtx &fc, int mb_x, int 
     __syncwarp();
 }
 
-#define AP_WARPS 1
 
+template <int AP_WARPS>
 __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_constant__ DevFrameCtx fc,
                                                             const __grid_constant__ FrameParams fp, int *row_claim)
 {
     __shared__ MbWork s_work[AP_WARPS];
+    __shared__ __align__(16) unsigned char s_ctx[AP_WARPS][sizeof(MbCtx)];
     MbWork &work = s_work[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
+    MbCtx &c = *new (s_ctx[threadIdx.x >> 5]) MbCtx(fc, fp, work);      // every lane writes the same values
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mb_w = fc.mb_w, mb_h = fc.mb_h;
+    __shared__ int s_group;
     for (;;)
     {
-        int row = 0;
-        if (lane == 0)
-            row = atomicAdd(row_claim, 1);
-        row = __shfl_sync(0xffffffffu, row, 0);
-        if (row >= mb_h)
+        // a CTA takes AP_WARPS consecutive rows: their reference windows overlap by 3/4 vertically and the rows run two
+        // macroblocks apart, so the warps of a CTA share most of their L1 lines
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_group = atomicAdd(row_claim, 1);
+        __syncthreads();
+        const int row = s_group * AP_WARPS + warp;
+        if (s_group * AP_WARPS >= mb_h)
             return;
+        if (row >= mb_h)
+            continue;
         for (int x = 0; x < mb_w; x++)
         {
             if (row > 0)
             {
                 const int need = min(x + 2, mb_w);
+                // back off while waiting: with many encoder contexts resident, spinning warps would otherwise take
+                // issue slots from the ones doing the work
+                unsigned ns = 32;
                 while (ld_acquire(fp.row_progress + row - 1) < need)
-                    __nanosleep(64);
+                {
+                    __nanosleep(ns);
+                    if (ns < 512) ns <<= 1;
+                }
             }
-            MbCtx c(fc, fp, work);
             c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;
             if (fp.trace && lane == 0) fp.trace[2 * c.mb_xy] = globaltimer_ns();
             stage_fenc(fc, x, row, work);
@@ -91,9 +105,16 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
     }
 }
 
-void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_ctas, void *stream)
+// rows_per_cta: 1 = every row on its own SM (lowest latency for a single encoder), 4 = four consecutive rows share a
+// CTA and its L1 (higher throughput when many encoder contexts run concurrently)
+void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_rows, int rows_per_cta, void *stream)
 {
-    k_analyse_p<<<n_ctas, AP_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
+    if (rows_per_cta >= 4)
+        k_analyse_p<4><<<(n_rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
+    else if (rows_per_cta >= 2)
+        k_analyse_p<2><<<(n_rows + 1) / 2, 64, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
+    else
+        k_analyse_p<1><<<n_rows, 32, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
 }
 
 // ---- cost table: one lane team per macroblock; macroblocks are independent -------------------------------
@@ -104,6 +125,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_const
 {
     __shared__ MbWork s_work[CT_WARPS];
     __shared__ MbResult s_res[CT_WARPS];
+    __shared__ __align__(16) unsigned char s_ctx[CT_WARPS][sizeof(MbCtx)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.x * CT_WARPS + warp;
     if (mb >= n_mb)
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_const
     }
     if (res.type == MB_P_SKIP)
         return;
-    MbCtx c(fc, fp, work);
+    MbCtx &c = *new (s_ctx[warp]) MbCtx(fc, fp, work);
     c.mb_x = mb % fc.mb_w; c.mb_y = mb / fc.mb_w; c.mb_xy = mb;
     c.partition = res.partition;
     stage_fenc(fc, c.mb_x, c.mb_y, work);

@@ -173,8 +173,8 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
     if (kind == COST_SAD_FPEL || kind == COST_SAD)
     {
         const int w4 = b.bw >> 2;
-#pragma unroll
-        for (int r = 0; r < PCAMV_ROWS; r++)
+#pragma unroll 1
+        for (int r = 0; r < PCAMV_ROWS && PCAMV_LPG * r < b.bh; r++)
         {
             const int y = sub + PCAMV_LPG * r;
             const int yy = imin(y, b.bh - 1);
@@ -315,8 +315,10 @@ PCAMV_FN best_t search_cross(const MeEnv &e, const MeBlock &b, best_t best, int 
 {
     int i = start;
     if (x_max <= imin(e.mv_max_fpel[0] - ox, ox - e.mv_min_fpel[0]))
+#pragma unroll 1
         for (; i < x_max - 2; i += 4)
             best = try4(b, best, 4, ox, oy, PCAMV_OFF4(i, -i, i + 2, -i - 2), 0);
+#pragma unroll 1
     for (; i < x_max; i += 2)
     {
         if (ox + i <= e.mv_max_fpel[0]) best = try1(b, best, ox + i, oy);
@@ -324,8 +326,10 @@ PCAMV_FN best_t search_cross(const MeEnv &e, const MeBlock &b, best_t best, int 
     }
     i = start;
     if (y_max <= imin(e.mv_max_fpel[1] - oy, oy - e.mv_min_fpel[1]))
+#pragma unroll 1
         for (; i < y_max - 2; i += 4)
             best = try4(b, best, 4, ox, oy, 0, PCAMV_OFF4(i, -i, i + 2, -i - 2));
+#pragma unroll 1
     for (; i < y_max; i += 2)
     {
         if (oy + i <= e.mv_max_fpel[1]) best = try1(b, best, ox, oy + i);
@@ -356,6 +360,7 @@ PCAMV_FN best_t search_hex(const MeEnv &e, const MeBlock &b, best_t best, int me
             if (nx - cx == hex_dx(k) && ny - cy == hex_dy(k)) dir = k;
         cx = nx; cy = ny;
         // half hexagons: only the three corners not covered by the previous position
+#pragma unroll 1
         for (int i = 1; i < me_range / 2 && fpel_in_range(e, cx, cy); i++)
         {
             const int d0 = dir == 0 ? 5 : dir - 1, d2 = dir == 5 ? 0 : dir + 1;
@@ -452,6 +457,7 @@ PCAMV_FN best_t search_umh(const MeEnv &e, const MeBlock &b, best_t best, int pm
                 mvd = iabs(b.mvp[0] - mvc[0][0]) + iabs(b.mvp[1] - mvc[0][1]);
                 denom++;
             }
+#pragma unroll 1
             for (int i = 0; i < i_mvc - 1; i++)
                 mvd += iabs(mvc[i][0] - mvc[i + 1][0]) + iabs(mvc[i][1] - mvc[i + 1][1]);
         }
@@ -528,6 +534,7 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
         }
     }
 
+#pragma unroll 1
     for (int i = hpel_iters; i > 0; i--)
     {
         const int omx = bmx, omy = bmy;
@@ -560,6 +567,7 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
     }
 
     int bdir = -1;
+#pragma unroll 1
     for (int i = qpel_iters; i > 0; i--)
     {
         const int odir = bdir;
@@ -622,6 +630,7 @@ PCAMV_FN best_t search_esa(const MeEnv &e, const MeBlock &b, best_t best)
     const int min_x = imax(bmx - range, e.mv_min_fpel[0]), min_y = imax(bmy - range, e.mv_min_fpel[1]);
     const int max_x = imin(bmx + range, e.mv_max_fpel[0]), max_y = imin(bmy + range, e.mv_max_fpel[1]);
     const int width = (max_x - min_x + 3) & ~3;
+#pragma unroll 1
     for (int my = min_y; my <= max_y; my++)
         for (int x = 0; x < width; x += 4)
             best = try4(b, best, 4, min_x + x, my, PCAMV_OFF4(0, 1, 2, 3), 0);
@@ -645,6 +654,7 @@ PCAMV_FN void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)
         int c[4], n = 0;
         c[0] = c[1] = c[2] = c[3] = pk(bmx, bmy);
         n = 1;
+#pragma unroll 1
         for (int i = 0; i <= i_mvc; i++)
         {
             bool have = false;
@@ -682,6 +692,7 @@ PCAMV_FN void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)
         // COST_MV then minus BITS_MVD(pmx,pmy): the plain SAD at the rounded predictor
         best = try1(b, best_make(PCAMV_COST_MAX, 0), pmx, pmy);
         best = best_make(best_cost(best) - (b.cost_mvx[pmx << 2] + b.cost_mvy[pmy << 2]), pk(pmx, pmy));
+#pragma unroll 1
         for (int i = 0; i < i_mvc; i++)
         {
             int mx = (mvc[i][0] + 2) >> 2, my = (mvc[i][1] + 2) >> 2;

@@ -24,7 +24,7 @@ class Cfg(C.Structure):
                 ("me_method", C.c_int), ("me_range", C.c_int), ("subpel_refine", C.c_int), ("chroma_me", C.c_int),
                 ("max_refs", C.c_int), ("mv_range", C.c_int), ("b_cabac", C.c_int), ("b_fast_pskip", C.c_int),
                 ("b_dct_decimate", C.c_int), ("analyse_inter", C.c_int), ("chroma_qp_offset", C.c_int),
-                ("reserved", C.c_int * 8)]
+                ("rows_per_cta", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class QpTables(C.Structure):
@@ -116,7 +116,7 @@ class PcamvContext:
     """One encoder's GPU context (mirrors one x264_t)."""
 
     def __init__(self, width, height, me_method=1, me_range=16, subpel_refine=5, chroma_me=1, max_refs=1,
-                 mv_range=512, b_cabac=1, b_fast_pskip=1, b_dct_decimate=1, analyse_inter=0x113, device=0):
+                 mv_range=512, b_cabac=1, b_fast_pskip=1, b_dct_decimate=1, analyse_inter=0x113, device=0, rows_per_cta=1):
         self.lib = load_library()
         cfg = Cfg()
         cfg.abi_version = self.lib.pcamv_abi_version()
@@ -125,6 +125,7 @@ class PcamvContext:
         cfg.me_method, cfg.me_range, cfg.subpel_refine, cfg.chroma_me = me_method, me_range, subpel_refine, chroma_me
         cfg.max_refs, cfg.mv_range, cfg.b_cabac, cfg.b_fast_pskip = max_refs, mv_range, b_cabac, b_fast_pskip
         cfg.b_dct_decimate, cfg.analyse_inter = b_dct_decimate, analyse_inter
+        cfg.rows_per_cta = rows_per_cta
         self.cfg = cfg
         self.handle = C.c_void_p()
         if self.lib.pcamv_open(C.byref(self.handle), C.byref(cfg)) != 0:

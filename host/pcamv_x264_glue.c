@@ -1,0 +1,342 @@
+/* pcamv_x264_glue.c — the reference's C host bound to libpcamv_cuda.so (include/pcamv.h).
+ *
+ * This is the binding INTEGRATION.md describes, compiled into the reference encoder by host/build_host.py (which
+ * inserts the hook calls at anchored lines of a scratch copy of the reference; no reference source lives in this
+ * repository).  The encoder keeps its x264_encoder_encode / --emrate interface and every line of its own control
+ * flow; what changes is where the motion-estimation results come from:
+ *
+ *   x264_encoder_open   (encoder/encoder.c:766)   -> pcamv_open
+ *   x264_slice_write    (encoder/encoder.c:1176)  -> per P-slice pass: pcamv_put_fenc, pcamv_put_ref for references not
+ *                                                    yet on the GPU, pcamv_set_qp_tables, ONE pcamv_analyse_p call
+ *   x264_me_search_ref  (encoder/me.c:158)        -> pops the next entry of the macroblock's result log
+ *   x264_me_refine_qpel (encoder/me.c:669)        -> same
+ *   x264_ih_get_mv_cost (encoder/analyse.c:2391)  -> same (replacement delta + embedding cost)
+ *   x264_encoder_close  (encoder/encoder.c:2670)  -> pcamv_close
+ *
+ * The host still walks x264_macroblock_analyse for every macroblock (MV prediction, candidate lists, P_SKIP probe,
+ * mode decision, pass-2 forcing, the unsequenced MV copy of SURVEY.md fact 3 ...), so its state evolves exactly as
+ * in the reference; each replayed call is checked against the log entry's kind / block size / reference, and any
+ * disagreement between the host's call sequence and the GPU's is fatal.  There is no CPU fallback: if the library
+ * cannot be opened or a call fails, the encoder exits.
+ */
+#include "common/common.h"
+#include "encoder/me.h"
+#include "encoder/macroblock.h"
+#include "pcamv.h"
+#include <time.h>
+
+void x264_me_search_ref_real( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
+void x264_me_refine_qpel_real( x264_t *h, x264_me_t *m );
+void pcamv_glue_load_costs( x264_t *h, int qp );      /* added to encoder/analyse.c by host/build_host.py */
+
+extern int16_t *g_cost_mv[52];            /* reference encoder/analyse.c:189 (malloc base, centre at +2*4*2048) */
+extern uint16_t x264_cost_ref[52][3][33]; /* reference encoder/analyse.c:188 */
+extern const int x264_lambda_tab[52];
+extern const int x264_lambda2_tab[52];
+
+typedef struct
+{
+    x264_t *h;
+    pcamv_ctx *ctx;
+    int n_mb;
+    pcamv_mb_out *mbs;              /* results of the running slice pass */
+    pcamv_log_entry *log;
+    pcamv_pass1_mb *pass1;          /* staging of h->info.cache[] for pass 2 */
+    int active;                     /* a P-slice pass with GPU results is being replayed */
+    int cur_mb, cur_pos;            /* replay cursor */
+    int qp_loaded;
+    int fenc_frame;                 /* h->fenc->i_frame currently on the GPU */
+    /* reference slots: which frame each GPU slot holds */
+    struct { x264_frame_t *fr; int i_frame, i_poc, age; } slot[PCAMV_MAX_REFS + 2];
+    int n_slots, tick;
+    /* accounting */
+    double t_gpu, t_total0;
+    long n_passes, n_replayed;
+} glue_t;
+
+static glue_t g;
+
+static double now_s( void )
+{
+    struct timespec ts; clock_gettime( CLOCK_MONOTONIC, &ts );
+    return ts.tv_sec + 1e-9*ts.tv_nsec;
+}
+
+static void die( const char *what )
+{
+    fprintf( stderr, "x264 [pcamv]: %s: %s\n", what, g.ctx ? pcamv_last_error( g.ctx ) : pcamv_last_error( NULL ) );
+    exit( 3 );
+}
+static void die_msg( const char *msg )
+{
+    fprintf( stderr, "x264 [pcamv]: %s\n", msg );
+    exit( 3 );
+}
+
+/* ---- open / close ---------------------------------------------------------------------------- */
+void pcamv_hook_open( x264_t *h )
+{
+    pcamv_cfg cfg;
+    const char *s;
+    memset( &g, 0, sizeof(g) );
+    g.h = h;
+    g.t_total0 = now_s();
+    g.fenc_frame = -1;
+    if( h->param.i_threads > 1 )
+        die_msg( "frame threads are not supported (the reference itself crashes with embedding on)" );
+    if( h->param.rc.i_rc_method != X264_RC_CQP || h->param.rc.i_aq_mode )
+        die_msg( "the GPU path needs constant QP (--qp N): one QP per slice" );
+    if( h->param.i_bframe )
+        die_msg( "B frames are not supported" );
+    if( h->param.analyse.i_subpel_refine > 5 )
+        die_msg( "--subme 6 and above (RD mode decision on live CABAC state) is raster-serial; use --subme 1..5" );
+    if( h->param.analyse.inter & X264_ANALYSE_PSUB8x8 )
+        die_msg( "sub-8x8 partitions (--partitions p4x4) are not supported" );
+    if( h->param.analyse.b_mixed_references )
+        die_msg( "--mixed-refs is not supported" );
+    if( h->param.analyse.i_me_method > X264_ME_ESA )
+        die_msg( "--me tesa is not supported" );
+    memset( &cfg, 0, sizeof(cfg) );
+    cfg.abi_version = PCAMV_ABI_VERSION;
+    cfg.device = (s = getenv( "PCAMV_DEVICE" )) ? atoi( s ) : 0;
+    cfg.width = 16 * h->sps->i_mb_width;
+    cfg.height = 16 * h->sps->i_mb_height;
+    cfg.me_method = h->param.analyse.i_me_method;
+    cfg.me_range = h->param.analyse.i_me_range;
+    cfg.subpel_refine = h->param.analyse.i_subpel_refine;
+    cfg.chroma_me = h->param.analyse.b_chroma_me;
+    cfg.max_refs = h->param.i_frame_reference;
+    cfg.mv_range = h->param.analyse.i_mv_range;
+    cfg.b_cabac = h->param.b_cabac;
+    cfg.b_fast_pskip = h->param.analyse.b_fast_pskip;
+    cfg.b_dct_decimate = h->param.analyse.b_dct_decimate;
+    cfg.analyse_inter = h->param.analyse.inter;
+    cfg.chroma_qp_offset = h->param.analyse.i_chroma_qp_offset;
+    cfg.rows_per_cta = (s = getenv( "PCAMV_ROWS_PER_CTA" )) ? atoi( s ) : 1;
+    if( pcamv_open( &g.ctx, &cfg ) )
+        die( "pcamv_open" );
+    g.n_mb = h->sps->i_mb_width * h->sps->i_mb_height;
+    g.n_slots = cfg.max_refs + 2;
+    g.mbs = calloc( g.n_mb, sizeof(*g.mbs) );
+    g.log = calloc( (size_t)g.n_mb * PCAMV_LOG_MAX, sizeof(*g.log) );
+    g.pass1 = calloc( g.n_mb, sizeof(*g.pass1) );
+    if( !g.mbs || !g.log || !g.pass1 )
+        die_msg( "out of memory" );
+    g.qp_loaded = -1;
+}
+
+void pcamv_hook_close( x264_t *h )
+{
+    const char *s = getenv( "PCAMV_STATS" );
+    (void)h;
+    if( s && *s )
+    {
+        FILE *f = fopen( s, "w" );
+        if( f )
+        {
+            fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_total\": %.6f}\n",
+                     g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, now_s() - g.t_total0 );
+            fclose( f );
+        }
+    }
+    if( g.ctx ) pcamv_close( g.ctx );
+    free( g.mbs ); free( g.log ); free( g.pass1 );
+    memset( &g, 0, sizeof(g) );
+}
+
+/* ---- slice begin: upload what is new, analyse the whole P slice on the GPU ---------------------- */
+static int slot_of( x264_frame_t *fr, const int *in_use, int n_in_use )
+{
+    int i, k, best = -1;
+    for( i = 0; i < g.n_slots; i++ )
+        if( g.slot[i].fr == fr && g.slot[i].i_frame == fr->i_frame && g.slot[i].i_poc == fr->i_poc )
+        {
+            g.slot[i].age = ++g.tick;
+            return i;
+        }
+    /* not resident: take the least recently used slot that no reference of this slice occupies */
+    for( i = 0; i < g.n_slots; i++ )
+    {
+        int busy = 0;
+        for( k = 0; k < n_in_use; k++ ) busy |= in_use[k] == i;
+        if( !busy && ( best < 0 || g.slot[i].age < g.slot[best].age ) )
+            best = i;
+    }
+    if( best < 0 )
+        die_msg( "no free reference slot" );
+    /* the integer plane as the host holds it after deblocking (filtered[0] == plane[0]); the GPU rebuilds borders,
+     * half-pel planes and integral image itself and must arrive at the host's own planes bit for bit */
+    if( pcamv_put_ref( g.ctx, best, fr->i_poc, fr->plane[0], fr->plane[1], fr->plane[2], fr->i_stride[0], fr->i_stride[1] ) )
+        die( "pcamv_put_ref" );
+    g.slot[best].fr = fr; g.slot[best].i_frame = fr->i_frame; g.slot[best].i_poc = fr->i_poc; g.slot[best].age = ++g.tick;
+    return best;
+}
+
+void pcamv_hook_slice_begin( x264_t *h )
+{
+    pcamv_frame_in in;
+    int qp = h->sh.i_qp, pass, i, n;
+    double t0;
+    g.active = 0;
+    if( h->sh.i_type != SLICE_TYPE_P )
+        return;
+    t0 = now_s();
+    pass = !h->info.embed_flag ? 0 : h->info.firstTime ? 1 : 2;
+    if( qp != g.qp_loaded )
+    {
+        pcamv_qp_tables t;
+        int qpc = h->chroma_qp_table[qp];
+        pcamv_glue_load_costs( h, qp );       /* the reference builds the table lazily at the first macroblock (analyse.c:198) */
+        memset( &t, 0, sizeof(t) );
+        t.qp = qp; t.lambda = x264_lambda_tab[qp]; t.lambda2_chroma = x264_lambda2_tab[qpc]; t.chroma_qp = qpc;
+        t.cost_mv = g_cost_mv[qp];
+        t.cost_ref = &x264_cost_ref[qp][0][0];
+        t.quant4_mf[0] = (const uint16_t *)h->quant4_mf[CQM_4PY][qp];   t.quant4_bias[0] = (const uint16_t *)h->quant4_bias[CQM_4PY][qp];
+        t.quant4_mf[1] = (const uint16_t *)h->quant4_mf[CQM_4PC][qpc];  t.quant4_bias[1] = (const uint16_t *)h->quant4_bias[CQM_4PC][qpc];
+        t.dequant4_mf[0] = (const int32_t *)h->dequant4_mf[CQM_4PY];
+        t.dequant4_mf[1] = (const int32_t *)h->dequant4_mf[CQM_4PC];
+        if( pcamv_set_qp_tables( g.ctx, &t ) )
+            die( "pcamv_set_qp_tables" );
+        g.qp_loaded = qp;
+    }
+    if( g.fenc_frame != h->fenc->i_frame )
+    {
+        if( pcamv_put_fenc( g.ctx, h->fenc->plane[0], h->fenc->plane[1], h->fenc->plane[2], h->fenc->i_stride[0], h->fenc->i_stride[1] ) )
+            die( "pcamv_put_fenc" );
+        g.fenc_frame = h->fenc->i_frame;
+    }
+    memset( &in, 0, sizeof(in) );
+    in.pass = pass;
+    in.n_ref = h->i_ref0;
+    for( i = 0; i < h->i_ref0; i++ )
+    {
+        in.ref_slot[i] = slot_of( h->fref0[i], in.ref_slot, i );
+        in.ref_poc[i] = h->fref0[i]->i_poc;
+    }
+    in.cur_poc = h->fdec->i_poc;
+    {
+        x264_frame_t *l0 = h->fref0[0];
+        in.col_n_ref = l0->i_ref[0];
+        for( i = 0; i < 16; i++ ) in.col_inv_ref_poc[i] = l0->inv_ref_poc[i];
+        in.col_ref8 = l0->ref[0];
+        in.col_mv4 = (const int16_t *)l0->mv[0];
+    }
+    in.cost_table = pass == 1;
+    if( pass == 2 )
+    {
+        n = 0;
+        for( i = 0; i < g.n_mb; i++ )
+        {
+            pcamv_pass1_mb *p = &g.pass1[i];
+            p->type = h->info.cache[i].i_type;
+            p->partition = h->info.cache[i].i_partition;
+            p->used = h->info.cache[i].used;
+            memcpy( p->sub, h->info.cache[i].i_sub_partition, 4 );
+            memcpy( p->ref, h->info.cache[i].ref, 16 );
+            memcpy( p->mv, h->info.cache[i].mv, 64 );
+            memcpy( p->mv_stego, h->info.cache[i].mv_stego, 64 );
+            if( p->used )
+                n += p->type == P_8x8 ? 4 : p->partition == D_16x16 ? 1 : 2;
+        }
+        in.pass1 = g.pass1;
+        in.filp = h->info.filp;
+        in.n_filp = n;
+    }
+    for( i = 0; i < 16; i++ )
+    {
+        /* what the MV cache holds before macroblock 0 (the pass-2 "forced skip without cache update" quirk reads it) */
+        in.stale_mv[i][0] = h->mb.cache.mv[0][x264_scan8[i]][0];
+        in.stale_mv[i][1] = h->mb.cache.mv[0][x264_scan8[i]][1];
+    }
+    if( pcamv_analyse_p( g.ctx, &in, g.mbs, g.log ) )
+        die( "pcamv_analyse_p" );
+    g.active = 1;
+    g.cur_mb = -1; g.cur_pos = 0;
+    g.n_passes++;
+    g.t_gpu += now_s() - t0;
+}
+
+void pcamv_hook_slice_end( x264_t *h ) { (void)h; g.active = 0; }
+
+/* ---- per-macroblock replay --------------------------------------------------------------------- */
+void pcamv_hook_analyse_begin( x264_t *h )
+{
+    if( g.active )
+    {
+        g.cur_mb = h->mb.i_mb_xy;
+        g.cur_pos = 0;
+    }
+}
+
+void pcamv_hook_analyse_end( x264_t *h )
+{
+    if( g.active )
+    {
+        /* every GPU entry of this macroblock must have been consumed, and the host must have arrived at the GPU's decision */
+        const pcamv_mb_out *r = &g.mbs[g.cur_mb];
+        if( g.cur_pos != r->n_log && !( r->n_log > PCAMV_LOG_MAX ) )
+        {
+            fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host made %d search calls, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, r->n_log );
+            exit( 4 );
+        }
+        if( h->mb.i_type != r->type || ( r->type != P_SKIP && h->mb.i_partition != r->partition ) )
+        {
+            fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host decided type %d partition %d, GPU %d / %d\n",
+                     h->i_frame, g.cur_mb, h->mb.i_type, h->mb.i_partition, r->type, r->partition );
+            exit( 4 );
+        }
+    }
+}
+
+static const pcamv_log_entry *next_entry( x264_t *h, x264_me_t *m, int kind )
+{
+    const pcamv_log_entry *e;
+    if( !g.active || g.cur_mb != h->mb.i_mb_xy )
+        die_msg( "motion search outside a GPU-analysed P slice (no CPU fallback)" );
+    if( g.cur_pos >= PCAMV_LOG_MAX || g.cur_pos >= g.mbs[g.cur_mb].n_log )
+    {
+        fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host asks for call %d, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, g.mbs[g.cur_mb].n_log );
+        exit( 4 );
+    }
+    e = &g.log[(size_t)g.cur_mb * PCAMV_LOG_MAX + g.cur_pos];
+    if( e->kind != kind || e->i_pixel != m->i_pixel )
+    {
+        fprintf( stderr, "x264 [pcamv]: frame %d mb %d call %d: host wants kind %d pixel %d, GPU logged kind %d pixel %d\n",
+                 h->i_frame, g.cur_mb, g.cur_pos, kind, m->i_pixel, e->kind, e->i_pixel );
+        exit( 4 );
+    }
+    g.cur_pos++;
+    g.n_replayed++;
+    return e;
+}
+
+void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh )
+{
+    const pcamv_log_entry *e = next_entry( h, m, PCAMV_LOG_SEARCH );
+    (void)mvc; (void)i_mvc;
+    /* the multi-reference half-pel threshold only ever feeds later searches, which are replayed too */
+    (void)p_halfpel_thresh;
+    m->mv[0] = e->mv[0]; m->mv[1] = e->mv[1];
+    m->cost = e->cost;
+    m->cost_mv = e->cost_mv;
+}
+
+void x264_me_refine_qpel( x264_t *h, x264_me_t *m )
+{
+    const pcamv_log_entry *e = next_entry( h, m, PCAMV_LOG_REFINE );
+    m->mv[0] = e->mv[0]; m->mv[1] = e->mv[1];
+    m->cost = e->cost;
+    m->cost_mv = e->cost_mv;
+}
+
+/* called by the x264_ih_get_mv_cost wrapper host/build_host.py puts into encoder/analyse.c */
+int pcamv_glue_ih_cost( x264_t *h, x264_me_t *m, int16_t *m_x, int16_t *m_y )
+{
+    const pcamv_log_entry *e = next_entry( h, m, PCAMV_LOG_IHCOST );
+    *m_x = e->mv[0]; *m_y = e->mv[1];
+    return e->cost;
+}
+
+/* hooks of the instrumented oracle twin that the GPU host does not need */
+void pcamv_hook_embed( x264_t *h, int an ) { (void)h; (void)an; }
+void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me ) { (void)i_pixel; (void)b_chroma_me; }

@@ -1,0 +1,52 @@
+"""Whole-encoder parity: the reference's C host with the CUDA shim bound in (host/_build/x264_pcamv, built by
+host/build_host.py) must emit a .264 bitstream that is byte-identical to the reference encoder's (oracle/_ref/x264_ref
+for CIF, the widened build otherwise) on the same synthetic clip and flags — both PCAMV passes, embedding on."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import refrun
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "host", "_build", "x264_pcamv")
+
+CASES = [
+    # BASELINE.json config 1: CIF 352x288, 30 frames, --me hex --subme 5, embed at 0.2 bits/MV; the UNMODIFIED reference
+    ("cif_hex5", 352, 288, 30, 1, 32, "x264_ref", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --emrate 0.2"),
+    ("cif_umh5_ref3", 352, 288, 12, 1, 32, "x264_wide", "--qp 26 --ref 3 --keyint 250 --me umh --subme 5 --emrate 0.2"),
+    ("cif_dia2_lownoise", 352, 288, 12, 1, 4, "x264_wide", "--qp 32 --ref 1 --keyint 250 --me dia --subme 2 --emrate 0.2"),
+    ("cif_hex4_idr", 352, 288, 14, 1, 16, "x264_wide", "--qp 24 --ref 2 --keyint 6 --min-keyint 6 --me hex --subme 4 --emrate 0.3"),
+    ("cif_noembed", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5"),
+    ("qcif_esa", 176, 144, 6, 9, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me esa --merange 16 --subme 5 --emrate 0.2"),
+    ("720p_umh5", 1280, 720, 4, 5, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
+]
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def encode_pair(pcamv, name, w, h, frames, config, noise, ref_bin, args, workdir):
+    clip = refrun.synth_clip(pcamv, w, h, frames, config=config, stream=1, noise16=noise, workdir=workdir)
+    ref_out, _ = refrun.run_ref(clip, w, h, args.split(), binary=ref_bin, out=os.path.join(workdir, name + "_ref.264"))
+    out = os.path.join(workdir, name + "_gpu.264")
+    stats = os.path.join(workdir, name + "_stats.json")
+    env = dict(os.environ, PCAMV_STATS=stats)
+    p = subprocess.run([HOST] + args.split() + ["-o", out, clip, "%dx%d" % (w, h)], env=env, capture_output=True, timeout=1800)
+    assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")      # (the reference prints GB18030 text)
+    return ref_out, out, json.load(open(stats))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_bitstream_identical(pcamv, cuda_lib, case, tmp_path):
+    if not os.path.exists(HOST):
+        pytest.fail("host/_build/x264_pcamv is not built (host/build_host.py)")
+    ref_out, out, stats = encode_pair(pcamv, *case, workdir=str(tmp_path))
+    assert os.path.getsize(out) > 1000
+    assert md5(out) == md5(ref_out), "bitstream differs from the reference (%d vs %d bytes)" % (os.path.getsize(out), os.path.getsize(ref_out))
+    assert stats["gpu_launches"] > 0 and stats["replayed_calls"] > 0

@@ -1,0 +1,146 @@
+"""Helpers shared by oracle/build_ref.py (the reference as checker) and host/build_host.py (the reference's C host
+with the CUDA shim bound in): make a scratch copy of the reference's C sources, apply anchored edits there, compile
+with the flags the reference's own `configure --disable-asm` produces.  No reference source is ever written into
+tracked files; the scratch tree is deleted after the build."""
+import os
+import re
+import shutil
+import subprocess
+
+REF = os.environ.get("PCAMV_REFERENCE", "/root/reference")
+MAX_MB = 32400          # 3840x2160 = 240x135 macroblocks
+
+SRCS = """common/mc.c common/predict.c common/pixel.c common/macroblock.c common/frame.c common/dct.c
+common/cpu.c common/cabac.c common/common.c common/mdate.c common/set.c common/quant.c common/vlc.c
+encoder/analyse.c encoder/me.c encoder/ratecontrol.c encoder/set.c encoder/macroblock.c encoder/cabac.c
+encoder/cavlc.c encoder/encoder.c""".split()
+SRCCLI = "x264.c matroska.c muxers.c".split()
+
+CFLAGS = ("-O4 -ffast-math -Wall -I. -DHAVE_MALLOC_H -DARCH_X86_64 -DSYS_LINUX -DHAVE_PTHREAD "
+          "-fomit-frame-pointer -Dsscanf_s=sscanf -D_strdup=strdup -w").split()
+LDFLAGS = "-lm -lpthread".split()
+
+CONFIG_H = '#define fseek fseeko\n#define ftell ftello\n#define X264_VERSION ""\n#define X264_POINTVER "0.66.x"\n'
+
+
+def sub_exact(text, pattern, repl, count, what, flags=0):
+    new, n = re.subn(pattern, repl, text, flags=flags)
+    if n != count:
+        raise SystemExit("reftree: anchor %r matched %d times, expected %d" % (what, n, count))
+    return new
+
+
+def read(path):
+    with open(path, "rb") as f:
+        # byte-transparent (sources are GB18030); CRLF -> LF so the anchors are uniform
+        return f.read().decode("latin-1").replace("\r\n", "\n")
+
+
+def write(path, text):
+    with open(path, "wb") as f:
+        f.write(text.encode("latin-1"))
+
+
+def widen(tree):
+    """CIF constants -> MAX_MB macroblocks; leaves the CIF bitstream unchanged."""
+    p = os.path.join(tree, "common/common.h")
+    t = read(p)
+    t = sub_exact(t, r"cache\[396\]", "cache[%d]" % MAX_MB, 1, "cache[396]")
+    t = sub_exact(t, r"\[6336\]", "[%d]" % (16 * MAX_MB), 8, "[6336]")
+    t = sub_exact(t, r"uint16_t i_mv_no", "uint32_t i_mv_no", 1, "i_mv_no")
+    t = sub_exact(t, r"uint16_t num_mv_modify_real", "uint32_t num_mv_modify_real", 1, "num_mv_modify_real")
+    write(p, t)
+    p = os.path.join(tree, "encoder/encoder.c")
+    t = read(p)
+    t = sub_exact(t, r"i < 396;", "i < %d;" % MAX_MB, 1, "i < 396")
+    t = sub_exact(t, r"\* 6336\)", "* %d)" % (16 * MAX_MB), 8, "* 6336)")
+    write(p, t)
+
+
+def copy_tree(dst):
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    for d in ("common", "encoder", "extras"):
+        os.makedirs(os.path.join(dst, d))
+    for f in os.listdir(REF):
+        if f.endswith((".c", ".h")):
+            shutil.copy(os.path.join(REF, f), os.path.join(dst, f))
+    for d in ("common", "encoder", "extras"):
+        for f in os.listdir(os.path.join(REF, d)):
+            if f.endswith((".c", ".h")):
+                shutil.copy(os.path.join(REF, d, f), os.path.join(dst, d, f))
+    for root, _, files in os.walk(dst):
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
+    write(os.path.join(dst, "config.h"), CONFIG_H)
+
+
+def compile_tree(tree, exe, extra_sources=(), extra_cflags=(), extra_ldflags=(), jobs=8, archive=None):
+    """gcc every reference source of `tree` plus extra_sources, link `exe`; optionally ar the library objects."""
+    objs, procs = [], []
+    srcs = SRCS + SRCCLI
+
+    def reap(s0, p0):
+        _, err = p0.communicate()
+        if p0.returncode:
+            raise SystemExit("reftree: %s failed:\n%s" % (s0, err.decode("latin-1")[-4000:]))
+
+    for s in srcs + list(extra_sources):
+        o = os.path.join(tree, os.path.basename(s).replace(".c", "") + "_" + str(len(objs)) + ".o")
+        objs.append(o)
+        cmd = ["gcc"] + CFLAGS + list(extra_cflags) + ["-c", s, "-o", o]
+        procs.append((s, subprocess.Popen(cmd, cwd=tree, stderr=subprocess.PIPE)))
+        if len(procs) >= jobs:
+            reap(*procs.pop(0))
+    for s0, p0 in procs:
+        reap(s0, p0)
+    subprocess.check_call(["gcc", "-o", exe] + objs + LDFLAGS + list(extra_ldflags), cwd=tree)
+    if archive:
+        if os.path.exists(archive):
+            os.remove(archive)
+        libobjs = objs[:len(SRCS)] + objs[len(srcs):len(srcs) + 1]
+        subprocess.check_call(["ar", "rcs", archive] + libobjs, cwd=tree)
+    return exe
+
+
+def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra=""):
+    """The anchored edits both instrumented builds share: calls to pcamv_hook_* at the frame-level points, the search
+    entry points renamed *_real (the hook file defines the originals' names), and a wrapper in front of
+    x264_ih_get_mv_cost.  (file:line of the reference in oracle/ref_hooks.c / host/pcamv_x264_glue.c.)"""
+    p = os.path.join(tree, "encoder/encoder.c")
+    t = read(p)
+    t = sub_exact(t, r'(#include "common/common.h"\n)', r"\1" + hook_decl.replace("\\", "\\\\"), 1, "encoder.c include")
+    # x264_encoder_open: the first mbcmp_init( h ) call (encoder/encoder.c:766); the second is reconfig
+    idx = t.index("    mbcmp_init( h );")
+    t = t[:idx] + "    mbcmp_init( h ); pcamv_hook_open( h );" + t[idx + len("    mbcmp_init( h );"):]
+    t = sub_exact(t, r"(    /\* init stats \*/\n    memset\( &h->stat\.frame, 0, sizeof\(h->stat\.frame\) \);)",
+                  r"\1 pcamv_hook_slice_begin( h );", 1, "slice begin")
+    t = sub_exact(t, r"\n(\t\tx264_macroblock_analyse\( h \);)",
+                  r"\n\t\tpcamv_hook_analyse_begin( h ); x264_macroblock_analyse( h ); pcamv_hook_analyse_end( h );", 1, "analyse call")
+    # after the filp loop of the embed stage (encoder/encoder.c:1848-1855): hook before the DEGUG print
+    t = sub_exact(t, r"(\t\t\t\t// [^\n]*\n\t\t\t\tif \(DEGUG_LIJUN\)\n\t\t\t\t\{\n\t\t\t\t\tprintf\(\"1)",
+                  r"\t\t\t\tpcamv_hook_embed( h, an );\n\1", 1, "embed end")
+    # end of x264_slice_write: the MB loop is followed by the cabac flush
+    t = sub_exact(t, r"(\n    if\( h->param\.b_cabac \)[^\n]*\n    \{\n        x264_cabac_encode_flush\( h, &h->cabac \);)",
+                  r"\n    pcamv_hook_slice_end( h );\1", 1, "slice end")
+    t = sub_exact(t, r"(void    x264_encoder_close  \( x264_t \*h \)\n\{)", r"\1 pcamv_hook_close( h );", 1, "close")
+    write(p, t)
+
+    p = os.path.join(tree, "encoder/me.c")
+    t = read(p)
+    t = sub_exact(t, r"\nvoid x264_me_search_ref\(", "\nvoid x264_me_search_ref_real(", 1, "me_search_ref def")
+    t = sub_exact(t, r"\nvoid x264_me_refine_qpel\(", "\nvoid x264_me_refine_qpel_real(", 1, "me_refine_qpel def")
+    write(p, t)
+
+    p = os.path.join(tree, "encoder/analyse.c")
+    t = read(p)
+    t = sub_exact(t, r'(#include "common/common.h"\n)', r"\1" + hook_decl.replace("\\", "\\\\"), 1, "analyse.c include")
+    t = sub_exact(t, r"(#define MV_SATD_FDEC_IH\(mx, my\)\\\n\{\\\n)", r"\1\tpcamv_hook_ih_satd( m->i_pixel, h->mb.b_chroma_me && m->i_pixel <= PIXEL_8x8 );\\\n", 1, "MV_SATD_FDEC_IH")
+    # x264_ih_get_mv_cost (encoder/analyse.c:2391): rename the definition and put a wrapper of the same name in front of
+    # x264_macroblock_analyse (its only caller, encoder/analyse.c:3557-3673)
+    t = sub_exact(t, r"\nstatic inline int x264_ih_get_mv_cost\(", "\nstatic inline int x264_ih_get_mv_cost_real(", 1, "ih_get_mv_cost def")
+    wrapper = ("static int x264_ih_get_mv_cost( x264_t *h, x264_mb_analysis_t *analysis, x264_me_t *m, int16_t *m_x, int16_t *m_y,\n"
+               "    int8_t d_mv[][2], int8_t d_mv_1_neighborhood[][2], int mb_xy )\n" + ih_wrapper_body)
+    idx = t.index("\nvoid x264_macroblock_analyse( x264_t *h )\n")
+    t = t[:idx] + "\n" + analyse_extra + wrapper + t[idx:]
+    write(p, t)

@@ -338,5 +338,22 @@ int pcamv_glue_ih_cost( x264_t *h, x264_me_t *m, int16_t *m_x, int16_t *m_y )
 }
 
 /* hooks of the instrumented oracle twin that the GPU host does not need */
-void pcamv_hook_embed( x264_t *h, int an ) { (void)h; (void)an; }
+/* end of the embed stage (encoder/encoder.c:1855): with PCAMV_PAYLOAD=<file> append what was hidden in this frame —
+ * int32 frame, length, an; uint8 message[an]; uint8 stego[length] — so that payload parity can be checked directly */
+void pcamv_hook_embed( x264_t *h, int an )
+{
+    const char *s = getenv( "PCAMV_PAYLOAD" );
+    if( s && *s )
+    {
+        FILE *f = fopen( s, "ab" );
+        if( f )
+        {
+            int32_t hd[3] = { h->i_frame, h->info.length, an };
+            fwrite( hd, 4, 3, f );
+            if( an > 0 ) fwrite( h->info.message, 1, an, f );
+            fwrite( h->info.stego, 1, h->info.length, f );
+            fclose( f );
+        }
+    }
+}
 void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me ) { (void)i_pixel; (void)b_chroma_me; }

@@ -50,3 +50,33 @@ def test_bitstream_identical(pcamv, cuda_lib, case, tmp_path):
     assert os.path.getsize(out) > 1000
     assert md5(out) == md5(ref_out), "bitstream differs from the reference (%d vs %d bytes)" % (os.path.getsize(out), os.path.getsize(ref_out))
     assert stats["gpu_launches"] > 0 and stats["replayed_calls"] > 0
+
+
+def test_payload_identical(pcamv, cuda_lib, tmp_path):
+    """The hidden payload: per P frame the message bits (glibc rand() & 1 stream, encoder/encoder.c:1838-1840) and the stego
+    LSB vector the STC embedder produced are identical to the reference's (EMBD records of the instrumented twin)."""
+    import numpy as np
+    w, h, frames, args = 352, 288, 10, "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --emrate 0.2"
+    workdir = str(tmp_path)
+    clip = refrun.synth_clip(pcamv, w, h, frames, config=1, stream=2, workdir=workdir)
+    dump = os.path.join(workdir, "d.bin")
+    refrun.run_ref(clip, w, h, args.split(), dump=dump, planes=False, calls=False)
+    ref = pcamv.dumpfmt.Dump(dump).embeds()
+    pay = os.path.join(workdir, "payload.bin")
+    p = subprocess.run([HOST] + args.split() + ["-o", os.path.join(workdir, "o.264"), clip, "%dx%d" % (w, h)],
+                       env=dict(os.environ, PCAMV_PAYLOAD=pay), capture_output=True, timeout=1800)
+    assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")
+    raw = open(pay, "rb").read()
+    pos, got = 0, []
+    while pos < len(raw):
+        frame, length, an = np.frombuffer(raw, dtype="<i4", count=3, offset=pos); pos += 12
+        msg = np.frombuffer(raw, dtype=np.uint8, count=max(int(an), 0), offset=pos); pos += max(int(an), 0)
+        stego = np.frombuffer(raw, dtype=np.uint8, count=int(length), offset=pos); pos += int(length)
+        got.append((int(frame), int(length), int(an), msg, stego))
+    assert len(got) == len(ref) and len(got) >= frames - 1
+    bits = 0
+    for (frame, length, an, msg, stego), e in zip(got, ref):
+        assert (frame, length, an) == (e["frame"], e["length"], e["an"])
+        assert np.array_equal(msg, e["message"]) and np.array_equal(stego, e["stego"])
+        bits += max(an, 0)
+    assert bits > 100

@@ -8,5 +8,5 @@ Contents: ``csrc/`` (CUDA kernels + the C-ABI of libpcamv_cuda.so, declared in i
 host is C and binds the same symbols directly), ``dumpfmt.py`` (parser for the
 instrumented-reference dumps used by tests and bench), ``build.py`` (nvcc recipes).
 """
-from . import build, dumpfmt, host  # noqa: F401
+from . import build, dumpfmt, host  # noqa: F401  (shard imports torch; load it on demand: from pcamv_b200 import shard)
 from .host import PcamvContext, PcamvError, load_library  # noqa: F401

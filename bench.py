@@ -203,6 +203,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=16,
                     help="independent encoder contexts (GOP shards / streams) analysing concurrently on each GPU")
+    ap.add_argument("--launch", choices=["batch", "streams"], default="batch",
+                    help="batch: all contexts' frames in ONE wavefront launch (pcamv_analyse_p_batch); streams: one launch per context on its own CUDA stream")
     ap.add_argument("--rows-per-cta", type=int, default=4, help="wavefront layout used when --streams > 1 (pcamv_cfg.rows_per_cta)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (profiling runs)")
     args = ap.parse_args()
@@ -257,6 +259,8 @@ def main():
     ry = np.ascontiguousarray(r["luma"][0][32:32 + H, 32:32 + W])
     ru = np.ascontiguousarray(r["u"][16:16 + H // 2, 16:16 + W // 2])
     rv = np.ascontiguousarray(r["v"][16:16 + H // 2, 16:16 + W // 2])
+    # the end-to-end arm copies from / to page-locked host memory (pcamv_host_alloc), as an encoder host would hold its frames
+    fy, fu, fv, ry, ru, rv = [pcamv.host.pinned_copy(a) for a in (fy, fu, fv, ry, ru, rv)]
     col = dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"])
     e = units[0]["embd"]
     pass1 = frame_parity.pass1_records(pcamv, e)
@@ -298,32 +302,56 @@ def main():
             _, w2, _ = c.frame_run(2, 1, per_kernel=True)
             acc += (w1, ct, w2)
         return acc
-    run_threads(lambda i: dev_steps(i, args.warmup))
+    def dev_steps_batch(k):
+        acc = np.zeros(3)
+        for _ in range(k):
+            _, w1, ct = pcamv.host.frame_run_batch(ctxs, 1)      # CUDA events around each kernel on the leader's stream
+            _, w2, _ = pcamv.host.frame_run_batch(ctxs, 2)
+            acc += (w1, ct, w2)
+        return [acc]
+    batch = args.launch == "batch" and S > 1
+    dev_run = (lambda k: dev_steps_batch(k)) if batch else (lambda k: run_threads(lambda i: dev_steps(i, k)))
+    dev_run(args.warmup)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     launches0 = sum(c.launch_count() for c in ctxs)
     t0 = time.perf_counter()
-    k_ms = run_threads(lambda i: dev_steps(i, args.steps))
+    k_ms = dev_run(args.steps)
     torch.cuda.synchronize()
     dev_s = time.perf_counter() - t0
     barrier()
-    k_ms = np.array(k_ms) / args.steps            # [S, 3] mean kernel durations per context while all S run concurrently
+    k_ms = np.array(k_ms) / args.steps            # mean kernel durations (per context while all S run concurrently, or of the batch launch)
     n_launch = sum(c.launch_count() for c in ctxs) - launches0
 
     # ---- end-to-end arm: host buffers in, host records out, S encoder threads ------------------------------------------
+    outs1 = [c.alloc_outputs(pinned=True) for c in ctxs]
+    outs2 = [c.alloc_outputs(pinned=True) for c in ctxs]
+
     def e2e_steps(i, k):
         c = ctxs[i]
         for _ in range(k):
             c.put_fenc(fy, fu, fv)
             c.put_ref(0, r["poc"], ry, ru, rv)
-            m1, l1 = c.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
-            m2, l2 = c.analyse_p(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], **col)
+            m1, l1 = c.analyse_p(1, refs, pocs, cur_poc, cost_table=True, out=outs1[i], **col)
+            m2, l2 = c.analyse_p(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], out=outs2[i], **col)
         return m1, l1, m2, l2
-    run_threads(lambda i: e2e_steps(i, args.warmup))
+    def e2e_steps_batch(k):
+        for _ in range(k):
+            def put(i):
+                ctxs[i].put_fenc(fy, fu, fv)
+                ctxs[i].put_ref(0, r["poc"], ry, ru, rv)
+            run_threads(put)
+            a1 = [(1, refs, pocs, cur_poc, dict(cost_table=True, **col)) for _ in ctxs]
+            o1 = pcamv.host.analyse_p_batch(ctxs, a1, outs=outs1)
+            a2 = [(2, refs, pocs, cur_poc, dict(pass1=pass1, filp=e["filp"], stale_mv=o[0]["mv"][-1], **col)) for o in o1]
+            o2 = pcamv.host.analyse_p_batch(ctxs, a2, outs=outs2)
+        return [(o1[i][0], o1[i][1], o2[i][0], o2[i][1]) for i in range(S)]
+    e2e_run = e2e_steps_batch if batch else (lambda k: run_threads(lambda i: e2e_steps(i, k)))
+    e2e_run(args.warmup)
     barrier()
     t0 = time.perf_counter()
-    outs = run_threads(lambda i: e2e_steps(i, args.steps))
+    outs = e2e_run(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -360,8 +388,8 @@ def main():
         # per-MB records in/out (DESIGN.md "HBM traffic"); S launches of the dominant kernel overlap, so the achieved
         # figure is S launches' bytes over the mean launch duration
         plane_y = ctxs[0].plane_bytes(0); plane_c = ctxs[0].plane_bytes(4)
-        alg_bytes = fy.nbytes + fu.nbytes + fv.nbytes + 4 * plane_y + 2 * plane_c + n_mb * (128 + 48 * 16 + 68)
-        achieved = S * alg_bytes / (kernels[dom] * 1e-3) / 1e9
+        alg_bytes = fy.nbytes + fu.nbytes + fv.nbytes + 4 * plane_y + 2 * plane_c + n_mb * (128 + ctxs[0].log_stride * 16 + 68)
+        achieved = S * alg_bytes / (kernels[dom] * 1e-3) / 1e9      # (batch: one launch covers S frames; streams: S overlapping launches)
         frames_all = world * S * args.steps
         line = {
             "metric": METRIC, "value": value, "unit": "Mcandidates/s", "n_gpus": world, "steps": args.steps,
@@ -371,7 +399,8 @@ def main():
                        "step": "one 1080p P frame through the frame seam in each of %d independent encoder contexts per GPU (GOP shards: own "
                                "CUDA stream, own frame buffers): wavefront analysis pass 1 + candidate-MV cost table + wavefront analysis "
                                "pass 2 (%d searches/refines, %d cost-table entries per frame)" % (S, par["calls"], par["ih"]),
-                       "contexts_per_gpu": S, "shards_gathered": len(shards), "candidates_per_frame": int(cand_per_frame),
+                       "contexts_per_gpu": S, "launch": ("one wavefront launch for all contexts (pcamv_analyse_p_batch)" if batch else
+                                                           "one launch per context, each on its own CUDA stream"), "shards_gathered": len(shards), "candidates_per_frame": int(cand_per_frame),
                        "l2": "inputs larger than L2: %d contexts x %.1f MB of planes each, no flush" % (S, (alg_bytes) / 1e6),
                        "parity_gate": "passed: %d searches, %d macroblock decisions, %d cost-table entries bit-exact vs reference"
                                       % (par["calls"], par["mbs"], par["ih"])},

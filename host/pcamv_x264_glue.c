@@ -38,7 +38,7 @@ typedef struct
 {
     x264_t *h;
     pcamv_ctx *ctx;
-    int n_mb;
+    int n_mb, log_stride;
     pcamv_mb_out *mbs;              /* results of the running slice pass */
     pcamv_log_entry *log;
     pcamv_pass1_mb *pass1;          /* staging of h->info.cache[] for pass 2 */
@@ -117,8 +117,9 @@ void pcamv_hook_open( x264_t *h )
         die( "pcamv_open" );
     g.n_mb = h->sps->i_mb_width * h->sps->i_mb_height;
     g.n_slots = cfg.max_refs + 2;
-    g.mbs = calloc( g.n_mb, sizeof(*g.mbs) );
-    g.log = calloc( (size_t)g.n_mb * PCAMV_LOG_MAX, sizeof(*g.log) );
+    g.mbs = pcamv_host_alloc( g.n_mb * sizeof(*g.mbs) );      /* page-locked: results arrive without a staging copy */
+    g.log_stride = pcamv_log_stride( g.ctx );
+    g.log = pcamv_host_alloc( (size_t)g.n_mb * g.log_stride * sizeof(*g.log) );
     g.pass1 = calloc( g.n_mb, sizeof(*g.pass1) );
     if( !g.mbs || !g.log || !g.pass1 )
         die_msg( "out of memory" );
@@ -140,7 +141,7 @@ void pcamv_hook_close( x264_t *h )
         }
     }
     if( g.ctx ) pcamv_close( g.ctx );
-    free( g.mbs ); free( g.log ); free( g.pass1 );
+    pcamv_host_free( g.mbs ); pcamv_host_free( g.log ); free( g.pass1 );
     memset( &g, 0, sizeof(g) );
 }
 
@@ -274,7 +275,7 @@ void pcamv_hook_analyse_end( x264_t *h )
     {
         /* every GPU entry of this macroblock must have been consumed, and the host must have arrived at the GPU's decision */
         const pcamv_mb_out *r = &g.mbs[g.cur_mb];
-        if( g.cur_pos != r->n_log && !( r->n_log > PCAMV_LOG_MAX ) )
+        if( g.cur_pos != r->n_log )
         {
             fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host made %d search calls, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, r->n_log );
             exit( 4 );
@@ -293,12 +294,12 @@ static const pcamv_log_entry *next_entry( x264_t *h, x264_me_t *m, int kind )
     const pcamv_log_entry *e;
     if( !g.active || g.cur_mb != h->mb.i_mb_xy )
         die_msg( "motion search outside a GPU-analysed P slice (no CPU fallback)" );
-    if( g.cur_pos >= PCAMV_LOG_MAX || g.cur_pos >= g.mbs[g.cur_mb].n_log )
+    if( g.cur_pos >= g.log_stride || g.cur_pos >= g.mbs[g.cur_mb].n_log )
     {
         fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host asks for call %d, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, g.mbs[g.cur_mb].n_log );
         exit( 4 );
     }
-    e = &g.log[(size_t)g.cur_mb * PCAMV_LOG_MAX + g.cur_pos];
+    e = &g.log[(size_t)g.cur_mb * g.log_stride + g.cur_pos];
     if( e->kind != kind || e->i_pixel != m->i_pixel )
     {
         fprintf( stderr, "x264 [pcamv]: frame %d mb %d call %d: host wants kind %d pixel %d, GPU logged kind %d pixel %d\n",

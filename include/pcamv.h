@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PCAMV_ABI_VERSION 3
+#define PCAMV_ABI_VERSION 4
 #define PCAMV_MAX_REFS 16
 #define PCAMV_MAX_MVC 10
 
@@ -114,6 +114,11 @@ int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg);
 void pcamv_close(pcamv_ctx *ctx);
 const char *pcamv_last_error(const pcamv_ctx *ctx);   /* ctx may be NULL: error of the last failed pcamv_open */
 int pcamv_abi_version(void);
+
+/* Page-locked host memory for frame planes and result arrays: copies to / from such buffers go straight over PCIe
+ * (pageable buffers work too, through the context's own pinned staging).  Zero-filled; NULL on failure. */
+void *pcamv_host_alloc(size_t bytes);
+void pcamv_host_free(void *p);
 
 /* ---- tables -------------------------------------------------------------------------------------- */
 /* called when x264_mb_analyse_load_costs first sees a QP (encoder/analyse.c:198) */
@@ -211,8 +216,12 @@ typedef struct pcamv_frame_in
     int16_t stale_mv[16][2];            /* h->mb.cache.mv[0][x264_scan8[i]] as left by the previous slice pass */
 } pcamv_frame_in;
 
+/* Entries per macroblock in the log arrays of this context: the most its configuration can produce (14 -> 16 for one
+ * reference frame), never more than PCAMV_LOG_MAX.  Entry k of macroblock mb is log[mb * pcamv_log_stride(ctx) + k]. */
+int pcamv_log_stride(const pcamv_ctx *ctx);
+
 /* Analyse every macroblock of a P slice against the current fenc and the uploaded references.
- * mbs: n_mb records; log: n_mb * PCAMV_LOG_MAX entries (may be NULL).  Replaces, per macroblock, the searches of
+ * mbs: n_mb records; log: n_mb * pcamv_log_stride(ctx) entries (may be NULL).  Replaces, per macroblock, the searches of
  * x264_macroblock_analyse (encoder/encoder.c:1273 -> encoder/analyse.c:2555) for P slices with subme <= 5. */
 int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log);
 
@@ -225,6 +234,16 @@ int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs,
 int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in);
 int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_per_frame, float *ms_kernels);
 int pcamv_frame_download(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log);
+
+/* Multi-context launches: n encoder contexts of equal geometry and search configuration on one device (GOP shards or
+ * independent streams) analysed by ONE wavefront kernel (+ one cost-table kernel), so that a B200 is
+ * filled by many frames' wavefronts at once without one stream per context.  ctxs[0] leads (its stream carries the
+ * launch); results land in each member's own buffers.  pcamv_analyse_p_batch = upload each, launch once, download
+ * each; pcamv_frame_run_batch re-launches frames already staged with pcamv_frame_upload (benchmark / pipelining),
+ * returning the mean device time of one launch pair and, in ms_kernels[2], of the wavefront and cost-table kernels. */
+int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *ins, int n,
+                          pcamv_mb_out *const *mbs, pcamv_log_entry *const *logs);
+int pcamv_frame_run_batch(pcamv_ctx *const *ctxs, int n, int pass, int iters, float *ms_per_step, float *ms_kernels);
 
 /* Profiling aid: with enable != 0 the next wavefront launches record the device globaltimer (ns) at the start and end
  * of every macroblock; out (may be NULL) receives the [n_mb][2] records of the last traced launch. */

@@ -80,7 +80,7 @@ int main(int argc, char **argv)
         fp.col_ref8 = (const int8_t *)(sx.data + sizeof(hx));
         fp.col_mv4 = (const uint32_t *)(sx.data + sizeof(hx) + 4 * n_mb);
         fp.cur.type = type.data(); fp.cur.ref8 = ref8.data(); fp.cur.mv4 = mv4.data(); fp.cur.mvr = mvr.data();
-        fp.log = log.data(); fp.results = results.data();
+        fp.log = log.data(); fp.log_stride = PCAMV_LOG_MAX; fp.results = results.data();
 
         // reference records of this frame/pass
         std::vector<std::vector<CallRec>> calls(n_mb);

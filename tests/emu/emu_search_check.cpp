@@ -85,6 +85,19 @@ int main(int argc, char **argv)
             bad++;
         }
     }
+    if (getenv("PCAMV_EMU_STATS"))
+    {
+        const char *kn[4] = { "sad_qpel", "satd", "satd_chroma", "sad_fpel" };
+        for (int k = 0; k < 4; k++)
+            for (int n = 1; n <= 4; n++)
+            {
+                long tot = 0;
+                for (int p = 0; p < 7; p++) tot += g_eval_calls[k][n][p];
+                if (tot)
+                    fprintf(stderr, "%-12s n=%d calls=%8ld  by pixel: %ld %ld %ld %ld %ld %ld %ld\n", kn[k], n, tot, g_eval_calls[k][n][0], g_eval_calls[k][n][1],
+                            g_eval_calls[k][n][2], g_eval_calls[k][n][3], g_eval_calls[k][n][4], g_eval_calls[k][n][5], g_eval_calls[k][n][6]);
+            }
+    }
     printf("calls=%ld mismatches=%ld skipped=%ld\n", calls, bad, skipped);
     return bad ? 1 : 0;
 }

@@ -53,3 +53,37 @@ def test_frame_seam_rejects_unsupported(pcamv, cuda_lib):
     with pytest.raises(pcamv.PcamvError, match="subpel_refine"):
         ctx.analyse_p(0, [0], [0], 2)
     ctx.close()
+
+
+def test_batch_launch_equals_single(pcamv, cuda_lib, tmp_path):
+    """pcamv_analyse_p_batch: several encoder contexts (different frames) analysed by ONE wavefront launch give exactly
+    the records and logs each context gets on its own."""
+    import frame_parity
+    dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path("qcif_hex5", str(tmp_path)))
+    units = [u for u in dump.slice_units() if u["slice"].with_planes and u["slice"].pass_ == 1][:3]
+    assert len(units) == 3
+    ctxs, args, single = [], [], []
+    for rpc, u in zip((1, 1, 1), units):
+        s, x = u["slice"], u["ctx"]
+        H, W = s.lines_y, s.width
+        c = frame_parity.open_ctx(pcamv, dump, s, rows_per_cta=4)
+        c.put_fenc(s.fenc[0][:, :W], s.fenc[1][:, :W // 2], s.fenc[2][:, :W // 2])
+        for slot, r in enumerate(s.refs):
+            c.put_ref(slot, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2],
+                      r["v"][16:16 + H // 2, 16:16 + W // 2])
+        kw = dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"],
+                  cost_table=True)
+        a = (1, list(range(x["n_ref"])), x["ref_poc"][:x["n_ref"]], x["cur_poc"], kw)
+        single.append(c.analyse_p(a[0], a[1], a[2], a[3], **kw))
+        ctxs.append(c); args.append(a)
+    outs = pcamv.host.analyse_p_batch(ctxs, args)
+    for (m0, l0), (m1, l1) in zip(single, outs):
+        assert m0.tobytes() == m1.tobytes()
+        for mb in range(len(m0)):
+            n = int(m0["n_log"][mb])
+            assert l0[mb, :n].tobytes() == l1[mb, :n].tobytes()
+    assert not (single[0][0]["mv"] == single[1][0]["mv"]).all()       # the frames really differ
+    ms, w, ct = pcamv.host.frame_run_batch(ctxs, 1, iters=2)
+    assert ms > 0 and w > 0 and ct > 0
+    for c in ctxs:
+        c.close()

@@ -25,7 +25,24 @@ def main():
     r = s.refs[0]
     col = dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"])
     refs, pocs, cur_poc = list(range(x["n_ref"])), x["ref_poc"][:x["n_ref"]], x["cur_poc"]
-    c = frame_parity.open_ctx(pcamv, dump, s)
+    S = int(sys.argv[1]) if len(sys.argv) > 1 else 1          # contexts running concurrently (context 0 is traced)
+    rpc = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    others = []
+    for i in range(S - 1):
+        o = frame_parity.open_ctx(pcamv, dump, s, rows_per_cta=rpc)
+        o.put_fenc(s.fenc[0][:, :W], s.fenc[1][:, :W // 2], s.fenc[2][:, :W // 2])
+        o.put_ref(0, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2], r["v"][16:16 + H // 2, 16:16 + W // 2])
+        o.frame_upload(1, refs, pocs, cur_poc, cost_table=False, **col)
+        others.append(o)
+    import threading
+    stop = []
+    def spin(o):
+        while not stop:
+            o.frame_run(1, 1)
+    th = [threading.Thread(target=spin, args=(o,)) for o in others]
+    for x_ in th: x_.start()
+    c = frame_parity.open_ctx(pcamv, dump, s, rows_per_cta=rpc)
     c.put_fenc(s.fenc[0][:, :W], s.fenc[1][:, :W // 2], s.fenc[2][:, :W // 2])
     c.put_ref(0, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2], r["v"][16:16 + H // 2, 16:16 + W // 2])
     c.frame_upload(1, refs, pocs, cur_poc, cost_table=False, **col)
@@ -33,6 +50,8 @@ def main():
     c.frame_trace(True)
     ms = c.frame_run(1, 1)
     tr = c.frame_trace(False, fetch=True).astype(np.int64)
+    stop.append(1)
+    for x_ in th: x_.join()
     mbs, log = c.frame_download()
     mb_w, mb_h = W // 16, H // 16
     t0 = tr[:, 0].min()
@@ -43,7 +62,7 @@ def main():
     gap[:, 1:] = st[:, 1:] - en[:, :-1]
     n_log = mbs["n_log"].reshape(mb_h, mb_w)
     typ = mbs["type"].reshape(mb_h, mb_w)
-    out = {"kernel_ms": ms, "span_us": float(en.max()), "busy_us_mean": float(busy.mean()), "busy_us_median": float(np.median(busy)),
+    out = {"contexts": S, "rows_per_cta": rpc, "kernel_ms": ms, "span_us": float(en.max()), "busy_us_mean": float(busy.mean()), "busy_us_median": float(np.median(busy)),
            "busy_us_p90": float(np.percentile(busy, 90)), "busy_us_max": float(busy.max()),
            "gap_us_mean": float(gap.mean()), "gap_us_median": float(np.median(gap)),
            "row0_total_us": float(en[0, -1]), "row0_busy_us": float(busy[0].sum()),

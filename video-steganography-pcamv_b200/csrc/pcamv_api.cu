@@ -33,6 +33,15 @@ extern "C" const char *pcamv_last_error(const pcamv_ctx *ctx)
     return ctx ? ctx->err.c_str() : g_open_error.c_str();
 }
 
+extern "C" void *pcamv_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    memset(p, 0, bytes);
+    return p;
+}
+extern "C" void pcamv_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" long long pcamv_launch_count(const pcamv_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 static int ensure_stage(pcamv_ctx *ctx, size_t bytes)
@@ -75,6 +84,15 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
     fc.chroma_me = cfg->chroma_me; fc.mv_range = cfg->mv_range; fc.max_refs = cfg->max_refs;
     fc.b_cabac = cfg->b_cabac; fc.b_fast_pskip = cfg->b_fast_pskip; fc.b_dct_decimate = cfg->b_dct_decimate;
     fc.analyse_inter = cfg->analyse_inter;
+    {
+        // most entries one macroblock can log: a 16x16 search per reference (twice in pass 2 when an early skip is
+        // overridden), four 8x8, two 16x8 + two 8x16 per candidate reference (<= 2 each), two refinements, two cost-table
+        // entries; rounded up to a multiple of 4 and capped by the ABI constant
+        const int r = cfg->max_refs, r2 = r < 2 ? r : 2;
+        int n = 2 * r + 4 + 4 * r2 + 2 + 2;
+        n = (n + 3) & ~3;
+        ctx->log_stride = n < PCAMV_LOG_MAX ? n : PCAMV_LOG_MAX;
+    }
     ctx->luma_bytes = (size_t)fc.stride_y * (cfg->height + 2 * PCAMV_PADV);
     ctx->chroma_bytes = (size_t)fc.stride_c * (cfg->height / 2 + PCAMV_PADV);
     ctx->ref_bytes = 4 * ctx->luma_bytes + 2 * ctx->chroma_bytes;
@@ -120,7 +138,8 @@ extern "C" void pcamv_close(pcamv_ctx *ctx)
     cudaFree(ctx->d_calls); cudaFree(ctx->d_results);
     cudaFree(ctx->fa.type); cudaFree(ctx->fa.ref8); cudaFree(ctx->fa.mv4); cudaFree(ctx->fa.mvr);
     cudaFree(ctx->d_col_ref8); cudaFree(ctx->d_col_mv4); cudaFree(ctx->d_forced); cudaFree(ctx->d_log);
-    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim);
+    if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
     if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
     if (ctx->h_calls) cudaFreeHost(ctx->h_calls);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);

@@ -33,12 +33,17 @@ struct pcamv_ctx
     pcamv::FrameArrays fa = {};                // type / ref8 / mv4 / mvr of the frame being analysed
     int8_t *d_col_ref8 = nullptr; uint32_t *d_col_mv4 = nullptr;      // co-located frame's ref / mv (temporal candidates)
     pcamv::ForcedMb *d_forced = nullptr;       // pass-2 forced decisions
-    pcamv::LogEntry *d_log = nullptr;          // [n_mb][PCAMV_LOG_MAX]
+    pcamv::LogEntry *d_log = nullptr;          // [n_mb][log_stride]
+    int log_stride = PCAMV_LOG_MAX;            // entries per macroblock: what the configured search can produce at most
     pcamv::MbResult *d_mb_results = nullptr;   // [n_mb]
+    pcamv::BatchItem *d_batch = nullptr, *h_batch = nullptr; int batch_items_cap = 0;   // leader of a multi-context launch
+    int *d_batch_claim = nullptr;
+    int batch_max_ctas = 0;                    // 0 = one CTA per row group of every frame
     unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
     bool trace_on = false;
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter
-    uint8_t *h_frame = nullptr; size_t h_frame_bytes = 0;             // pinned staging for frame inputs / outputs
+    uint8_t *h_frame = nullptr; size_t h_frame_bytes = 0, h_frame_in_bytes = 0;
+    bool dl_mbs_direct = false, dl_log_direct = false;             // pinned staging for frame inputs / outputs
     pcamv::FrameParams fp[3] = {};             // parameters of the last uploaded frame, per pass (0 / 1 / 2)
     bool frame_ready[3] = { false, false, false }, frame_cost_table = false;
     int frame_last = -1;

@@ -92,12 +92,12 @@ struct MbCtx
 
 PCAMV_FN void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int mvy, int cost, int cost_mv)
 {
-    if (c.n_log < PCAMV_LOG_MAX && team_lane() == 0)
+    if (c.n_log < c.fp.log_stride && team_lane() == 0)
     {
         LogEntry e;
         e.kind = (int8_t)kind; e.i_pixel = (int8_t)i_pixel; e.i_ref = (int8_t)i_ref; e.pad = 0;
         e.mv[0] = (int16_t)mvx; e.mv[1] = (int16_t)mvy; e.cost = cost; e.cost_mv = cost_mv;
-        c.fp.log[(size_t)c.mb_xy * PCAMV_LOG_MAX + c.n_log] = e;
+        c.fp.log[(size_t)c.mb_xy * c.fp.log_stride + c.n_log] = e;
     }
     c.n_log++;
 }
@@ -747,7 +747,7 @@ PCAMV_FN void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition
         for (int y = 0; y < 4; y++)
             for (int x = 0; x < 4; x++)
                 fa.mv4[cur4 + y * s4 + x] = c.w.mv[12 + x + 8 * y];
-        MbResult r;
+        MbResult r = MbResult();      // unused partition slots stay zero: records are comparable byte for byte
         r.type = (int8_t)type; r.partition = (int8_t)partition; r.early_skip = (int8_t)early_skip;
         r.ref[0] = c.w.ref[12]; r.ref[1] = c.w.ref[14]; r.ref[2] = c.w.ref[28]; r.ref[3] = c.w.ref[30];
 #pragma unroll 1

@@ -13,6 +13,8 @@ using namespace pcamv;
 namespace pcamv {
 void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_rows, int rows_per_cta, void *stream);
 void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream);
+void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, void *stream);
+void launch_cost_table_batch(const BatchItem *items, int n_items, int n_mb, void *stream);
 }
 
 // the ABI records are the device records
@@ -46,14 +48,16 @@ static int ensure_frame_buffers(pcamv_ctx *ctx)
     CK(cudaMemsetAsync(ctx->fa.mvr, 0, (size_t)PCAMV_MAX_REFS * n_mb * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_mb_results, 0, n_mb * sizeof(MbResult), ctx->stream));
     // pinned staging: inputs (col ref/mv + forced) and outputs (results + log)
-    ctx->h_frame_bytes = n_mb * (4 + 64 + sizeof(ForcedMb) + sizeof(MbResult) + PCAMV_LOG_MAX * sizeof(LogEntry)) + 1024;
+    ctx->h_frame_in_bytes = (n_mb * (4 + 64 + sizeof(ForcedMb)) + 255) & ~(size_t)255;
+    ctx->h_frame_bytes = ctx->h_frame_in_bytes + n_mb * (sizeof(MbResult) + ctx->log_stride * sizeof(LogEntry)) + 1024;
     CK(cudaMallocHost(&ctx->h_frame, ctx->h_frame_bytes));
-    CK(cudaMalloc(&ctx->d_log, n_mb * PCAMV_LOG_MAX * sizeof(LogEntry)));
-    CK(cudaMemsetAsync(ctx->d_log, 0, n_mb * PCAMV_LOG_MAX * sizeof(LogEntry), ctx->stream));
+    CK(cudaMalloc(&ctx->d_log, n_mb * ctx->log_stride * sizeof(LogEntry)));
+    CK(cudaMemsetAsync(ctx->d_log, 0, n_mb * ctx->log_stride * sizeof(LogEntry), ctx->stream));
     return 0;
 }
 
-extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
+// stages the frame inputs and issues the copies on the context's stream; the caller synchronises
+static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
 {
     GUARD();
     if (!in) return ctx_fail(ctx, "pcamv_frame_upload: null argument", cudaSuccess);
@@ -115,11 +119,18 @@ extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
     for (int i = 0; i < 16; i++)
         fp.stale_mv[i] = ((uint32_t)(uint16_t)in->stale_mv[i][0]) | ((uint32_t)(uint16_t)in->stale_mv[i][1] << 16);
     fp.cur = ctx->fa;
-    fp.log = ctx->d_log; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
-    CK(cudaStreamSynchronize(ctx->stream));        // the caller may reuse its buffers; pinned staging is free again
+    fp.log = ctx->d_log; fp.log_stride = ctx->log_stride; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
     if (in->pass == 1) ctx->frame_cost_table = in->cost_table != 0;
-    ctx->frame_ready[in->pass] = true;
     ctx->frame_last = in->pass;
+    return 0;
+}
+
+extern "C" int pcamv_frame_upload(pcamv_ctx *ctx, const pcamv_frame_in *in)
+{
+    GUARD();
+    if (frame_upload_async(ctx, in)) return -1;
+    CK(cudaStreamSynchronize(ctx->stream));        // the caller may reuse its buffers; pinned staging is free again
+    ctx->frame_ready[in->pass] = true;
     return 0;
 }
 
@@ -178,19 +189,44 @@ extern "C" int pcamv_frame_run(pcamv_ctx *ctx, int pass, int iters, float *ms_pe
     return 0;
 }
 
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// issues the result copies on the context's stream: straight into the caller's buffers when those are page-locked
+// (cudaHostAlloc / cudaHostRegister), else into the context's pinned staging
+static int frame_download_async(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    if (ctx->frame_last < 0) return ctx_fail(ctx, "pcamv_frame_download: no frame uploaded", cudaSuccess);
+    const size_t n_mb = (size_t)ctx->fc.mb_w * ctx->fc.mb_h;
+    uint8_t *h = ctx->h_frame + ctx->h_frame_in_bytes;
+    const size_t res_bytes = n_mb * sizeof(MbResult), log_bytes = n_mb * ctx->log_stride * sizeof(LogEntry);
+    ctx->dl_mbs_direct = mbs && is_pinned(mbs);
+    ctx->dl_log_direct = log && is_pinned(log);
+    if (mbs) CK(cudaMemcpyAsync(ctx->dl_mbs_direct ? (void *)mbs : (void *)h, ctx->d_mb_results, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (log) CK(cudaMemcpyAsync(ctx->dl_log_direct ? (void *)log : (void *)(h + res_bytes), ctx->d_log, log_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+static int frame_download_finish(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    const size_t n_mb = (size_t)ctx->fc.mb_w * ctx->fc.mb_h;
+    uint8_t *h = ctx->h_frame + ctx->h_frame_in_bytes;
+    const size_t res_bytes = n_mb * sizeof(MbResult), log_bytes = n_mb * ctx->log_stride * sizeof(LogEntry);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (mbs && !ctx->dl_mbs_direct) memcpy(mbs, h, res_bytes);
+    if (log && !ctx->dl_log_direct) memcpy(log, h + res_bytes, log_bytes);
+    return 0;
+}
+
 extern "C" int pcamv_frame_download(pcamv_ctx *ctx, pcamv_mb_out *mbs, pcamv_log_entry *log)
 {
     GUARD();
-    if (ctx->frame_last < 0) return ctx_fail(ctx, "pcamv_frame_download: no frame uploaded", cudaSuccess);
-    const size_t n_mb = (size_t)ctx->fc.mb_w * ctx->fc.mb_h;
-    uint8_t *h = ctx->h_frame;
-    const size_t res_bytes = n_mb * sizeof(MbResult), log_bytes = n_mb * PCAMV_LOG_MAX * sizeof(LogEntry);
-    if (mbs) CK(cudaMemcpyAsync(h, ctx->d_mb_results, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (log) CK(cudaMemcpyAsync(h + res_bytes, ctx->d_log, log_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (mbs) memcpy(mbs, h, res_bytes);
-    if (log) memcpy(log, h + res_bytes, log_bytes);
-    return 0;
+    if (frame_download_async(ctx, mbs, log)) return -1;
+    return frame_download_finish(ctx, mbs, log);
 }
 
 extern "C" int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log)
@@ -201,6 +237,8 @@ extern "C" int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_m
     if (launch_frame(ctx, in->pass)) return -1;
     return pcamv_frame_download(ctx, mbs, log);
 }
+
+extern "C" int pcamv_log_stride(const pcamv_ctx *ctx) { return ctx ? ctx->log_stride : 0; }
 
 extern "C" int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out)
 {
@@ -213,5 +251,136 @@ extern "C" int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long 
         CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->trace_on = enable != 0;
+    return 0;
+}
+
+// ---- multi-context launches: n encoder contexts (GOP shards / streams of equal geometry) analysed by ONE wavefront kernel ----
+static int batch_check(pcamv_ctx *const *ctxs, int n, int pass)
+{
+    if (!ctxs || n <= 0 || !ctxs[0]) return -1;
+    pcamv_ctx *ctx = ctxs[0];
+    GUARD();
+    if (pass < 0 || pass > 2) return ctx_fail(ctx, "batch: bad pass", cudaSuccess);
+    for (int i = 0; i < n; i++)
+    {
+        pcamv_ctx *c = ctxs[i];
+        if (!c || c->failed) return ctx_fail(ctx, "batch: a member context is null or failed", cudaSuccess);
+        if (c->cfg.device != ctx->cfg.device || c->fc.mb_w != ctx->fc.mb_w || c->fc.mb_h != ctx->fc.mb_h ||
+            c->fc.me_method != ctx->fc.me_method || c->fc.subme != ctx->fc.subme)
+            return ctx_fail(ctx, "batch: member contexts must share device, geometry and search configuration", cudaSuccess);
+        if (!c->frame_ready[pass]) return ctx_fail(ctx, "batch: a member context has no frame uploaded for that pass", cudaSuccess);
+        for (int k = 0; k < i; k++)
+            if (ctxs[k] == c) return ctx_fail(ctx, "batch: a context appears twice", cudaSuccess);
+    }
+    return 0;
+}
+
+static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev)
+{
+    pcamv_ctx *ctx = ctxs[0];
+    const DevFrameCtx &fc = ctx->fc;
+    if (ctx->batch_items_cap < n)
+    {
+        cudaFree(ctx->d_batch); if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
+        ctx->d_batch = nullptr; ctx->h_batch = nullptr; ctx->batch_items_cap = 0;
+        CK(cudaMalloc(&ctx->d_batch, n * sizeof(BatchItem)));
+        CK(cudaMallocHost(&ctx->h_batch, n * sizeof(BatchItem)));
+        ctx->batch_items_cap = n;
+    }
+    if (!ctx->d_batch_claim) CK(cudaMalloc(&ctx->d_batch_claim, sizeof(int)));
+    int cost_table = pass == 1;
+    for (int i = 0; i < n; i++)
+    {
+        pcamv_ctx *c = ctxs[i];
+        c->fp[pass].trace = c->trace_on ? c->d_trace : nullptr;
+        ctx->h_batch[i].fc = c->fc;
+        ctx->h_batch[i].fp = c->fp[pass];
+        cost_table = cost_table && c->frame_cost_table;
+        // everything a member uploaded on its own stream has been synchronised by pcamv_frame_upload
+        CK(cudaMemsetAsync(c->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->d_batch, ctx->h_batch, n * sizeof(BatchItem), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_batch_claim, 0, sizeof(int), ctx->stream));
+    if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
+    launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta, ctx->batch_max_ctas, ctx->stream);
+    ctx->launches += 1;
+    if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
+    if (cost_table)
+    {
+        launch_cost_table_batch(ctx->d_batch, n, fc.mb_w * fc.mb_h, ctx->stream);
+        ctx->launches += 1;
+    }
+    if (ev) CK(cudaEventRecord(ev[2], ctx->stream));
+    CK(cudaGetLastError());
+    for (int i = 0; i < n; i++) ctxs[i]->frame_last = pass;
+    return 0;
+}
+
+extern "C" int pcamv_frame_run_batch(pcamv_ctx *const *ctxs, int n, int pass, int iters, float *ms_per_step, float *ms_kernels)
+{
+    if (batch_check(ctxs, n, pass)) return -1;
+    pcamv_ctx *ctx = ctxs[0];
+    if (iters <= 0) return ctx_fail(ctx, "pcamv_frame_run_batch: iters must be positive", cudaSuccess);
+    while ((int)ctx->ev_pool.size() < 3 * iters)
+    {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->ev_pool.push_back(e);
+    }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i < iters; i++)
+        if (launch_batch(ctxs, n, pass, ctx->ev_pool.data() + 3 * i)) return -1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ms_per_step) *ms_per_step = ms / iters;
+    if (ms_kernels)
+    {
+        double a = 0, b = 0;
+        for (int i = 0; i < iters; i++)
+        {
+            float t0 = 0, t1 = 0;
+            CK(cudaEventElapsedTime(&t0, ctx->ev_pool[3 * i], ctx->ev_pool[3 * i + 1]));
+            CK(cudaEventElapsedTime(&t1, ctx->ev_pool[3 * i + 1], ctx->ev_pool[3 * i + 2]));
+            a += t0; b += t1;
+        }
+        ms_kernels[0] = (float)(a / iters); ms_kernels[1] = (float)(b / iters);
+    }
+    return 0;
+}
+
+extern "C" int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *ins, int n,
+                                     pcamv_mb_out *const *mbs, pcamv_log_entry *const *logs)
+{
+    if (!ctxs || !ins || !mbs || n <= 0 || !ctxs[0]) return -1;
+    pcamv_ctx *ctx = ctxs[0];
+    GUARD();
+    // every member stages and copies on its own stream, all in flight together
+    for (int i = 0; i < n; i++)
+    {
+        if (!ctxs[i] || !ins[i] || !mbs[i]) return ctx_fail(ctx, "pcamv_analyse_p_batch: null member", cudaSuccess);
+        if (ctxs[i]->failed) return ctx_fail(ctx, "pcamv_analyse_p_batch: a member context has failed", cudaSuccess);
+        if (ins[i]->pass != ins[0]->pass) return ctx_fail(ctx, "pcamv_analyse_p_batch: all frames of a launch must be in the same pass", cudaSuccess);
+        if (frame_upload_async(ctxs[i], ins[i]))
+            return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
+    }
+    for (int i = 0; i < n; i++)
+    {
+        CK(cudaStreamSynchronize(ctxs[i]->stream));
+        ctxs[i]->frame_ready[ins[0]->pass] = true;
+    }
+    if (batch_check(ctxs, n, ins[0]->pass)) return -1;
+    if (launch_batch(ctxs, n, ins[0]->pass, nullptr)) return -1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    for (int i = 0; i < n; i++)
+    {
+        if (ctxs[i] != ctx) CK(cudaStreamWaitEvent(ctxs[i]->stream, ctx->ev1, 0));
+        if (frame_download_async(ctxs[i], mbs[i], logs ? logs[i] : nullptr))
+            return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
+    }
+    for (int i = 0; i < n; i++)
+        if (frame_download_finish(ctxs[i], mbs[i], logs ? logs[i] : nullptr))
+            return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
     return 0;
 }

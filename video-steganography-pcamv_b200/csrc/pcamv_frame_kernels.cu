@@ -52,6 +52,39 @@ __device__ __forceinline__ void stage_fenc(const DevFrameCtx &fc, int mb_x, int 
 }
 
 
+// one macroblock row, left to right, behind the row above (the caller has claimed `row` in increasing order)
+__device__ __forceinline__ void analyse_row(const DevFrameCtx &fc, const FrameParams &fp, MbCtx &c, MbWork &work, int row)
+{
+    const int lane = threadIdx.x & 31;
+    const int mb_w = fc.mb_w;
+    for (int x = 0; x < mb_w; x++)
+    {
+        if (row > 0)
+        {
+            const int need = min(x + 2, mb_w);
+            // back off while waiting: with many encoder contexts resident, spinning warps would otherwise take
+            // issue slots from the ones doing the work
+            unsigned ns = 32;
+            while (ld_acquire(fp.row_progress + row - 1) < need)
+            {
+                __nanosleep(ns);
+                if (ns < 512) ns <<= 1;
+            }
+        }
+        c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;
+        if (fp.trace && lane == 0) fp.trace[2 * c.mb_xy] = globaltimer_ns();
+        stage_fenc(fc, x, row, work);
+        analyse_p_mb(c, c.mb_xy ? fp.results[c.mb_xy - 1].mv : fp.stale_mv);
+        __syncwarp();
+        if (lane == 0)
+        {
+            if (fp.trace) fp.trace[2 * c.mb_xy + 1] = globaltimer_ns();
+            __threadfence();
+            st_release(fp.row_progress + row, x + 1);
+        }
+    }
+}
+
 template <int AP_WARPS>
 __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_constant__ DevFrameCtx fc,
                                                             const __grid_constant__ FrameParams fp, int *row_claim)
@@ -60,8 +93,8 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
     __shared__ __align__(16) unsigned char s_ctx[AP_WARPS][sizeof(MbCtx)];
     MbWork &work = s_work[threadIdx.x >> 5];
     MbCtx &c = *new (s_ctx[threadIdx.x >> 5]) MbCtx(fc, fp, work);      // every lane writes the same values
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int mb_w = fc.mb_w, mb_h = fc.mb_h;
+    const int warp = threadIdx.x >> 5;
+    const int mb_h = fc.mb_h;
     __shared__ int s_group;
     for (;;)
     {
@@ -74,33 +107,39 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
         const int row = s_group * AP_WARPS + warp;
         if (s_group * AP_WARPS >= mb_h)
             return;
-        if (row >= mb_h)
-            continue;
-        for (int x = 0; x < mb_w; x++)
+        if (row < mb_h)
+            analyse_row(fc, fp, c, work, row);
+    }
+}
+
+// Several frames (independent encoder contexts: GOP shards / streams of equal geometry) in ONE launch: the claim
+// counter walks (row group, frame) pairs frame-fastest, so all frames advance together and every awaited row has a
+// smaller claim index than the waiting one — the same no-deadlock argument as for a single frame, for any grid size.
+// The grid is sized to what is resident at once; CTAs keep claiming until the work is gone (persistent).
+template <int AP_WARPS>
+__global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p_batch(const BatchItem *__restrict__ items, int n_items, int *row_claim)
+{
+    __shared__ MbWork s_work[AP_WARPS];
+    __shared__ __align__(16) unsigned char s_ctx[AP_WARPS][sizeof(MbCtx)];
+    __shared__ int s_claim;
+    const int warp = threadIdx.x >> 5;
+    MbWork &work = s_work[warp];
+    const int mb_h = items[0].fc.mb_h;
+    for (;;)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_claim = atomicAdd(row_claim, 1);
+        __syncthreads();
+        const int group = s_claim / n_items, frame = s_claim - group * n_items;
+        if (group * AP_WARPS >= mb_h)
+            return;
+        const int row = group * AP_WARPS + warp;
+        if (row < mb_h)
         {
-            if (row > 0)
-            {
-                const int need = min(x + 2, mb_w);
-                // back off while waiting: with many encoder contexts resident, spinning warps would otherwise take
-                // issue slots from the ones doing the work
-                unsigned ns = 32;
-                while (ld_acquire(fp.row_progress + row - 1) < need)
-                {
-                    __nanosleep(ns);
-                    if (ns < 512) ns <<= 1;
-                }
-            }
-            c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;
-            if (fp.trace && lane == 0) fp.trace[2 * c.mb_xy] = globaltimer_ns();
-            stage_fenc(fc, x, row, work);
-            analyse_p_mb(c, c.mb_xy ? fp.results[c.mb_xy - 1].mv : fp.stale_mv);
-            __syncwarp();
-            if (lane == 0)
-            {
-                if (fp.trace) fp.trace[2 * c.mb_xy + 1] = globaltimer_ns();
-                __threadfence();
-                st_release(fp.row_progress + row, x + 1);
-            }
+            const BatchItem &it = items[frame];
+            MbCtx &c = *new (s_ctx[warp]) MbCtx(it.fc, it.fp, work);
+            analyse_row(it.fc, it.fp, c, work, row);
         }
     }
 }
@@ -117,17 +156,25 @@ void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_cla
         k_analyse_p<1><<<n_rows, 32, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
 }
 
+void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, void *stream)
+{
+    const int w = rows_per_cta >= 4 ? 4 : rows_per_cta >= 2 ? 2 : 1;
+    int ctas = n_items * ((n_rows + w - 1) / w);
+    if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+    if (w == 4)      k_analyse_p_batch<4><<<ctas, 128, 0, (cudaStream_t)stream>>>(items, n_items, row_claim);
+    else if (w == 2) k_analyse_p_batch<2><<<ctas, 64, 0, (cudaStream_t)stream>>>(items, n_items, row_claim);
+    else             k_analyse_p_batch<1><<<ctas, 32, 0, (cudaStream_t)stream>>>(items, n_items, row_claim);
+}
+
 // ---- cost table: one lane team per macroblock; macroblocks are independent -------------------------------
 #define CT_WARPS 4
 
-__global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_constant__ DevFrameCtx fc,
-                                                             const __grid_constant__ FrameParams fp, int n_mb)
+__device__ __forceinline__ void cost_table_team(const DevFrameCtx &fc, const FrameParams &fp, int mb, int n_mb)
 {
     __shared__ MbWork s_work[CT_WARPS];
     __shared__ MbResult s_res[CT_WARPS];
     __shared__ __align__(16) unsigned char s_ctx[CT_WARPS][sizeof(MbCtx)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mb = blockIdx.x * CT_WARPS + warp;
     if (mb >= n_mb)
         return;
     MbWork &work = s_work[warp];
@@ -147,9 +194,30 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_const
     cost_table_mb(c, res);
 }
 
+__global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_constant__ DevFrameCtx fc,
+                                                             const __grid_constant__ FrameParams fp, int n_mb)
+{
+    cost_table_team(fc, fp, blockIdx.x * CT_WARPS + (threadIdx.x >> 5), n_mb);
+}
+
+// blockIdx.y = frame of the batch
+__global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table_batch(const BatchItem *__restrict__ items, int n_mb)
+{
+    const BatchItem &it = items[blockIdx.y];
+    cost_table_team(it.fc, it.fp, blockIdx.x * CT_WARPS + (threadIdx.x >> 5), n_mb);
+}
+
 void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream)
 {
     k_cost_table<<<(n_mb + CT_WARPS - 1) / CT_WARPS, CT_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, fp, n_mb);
 }
 
 } // namespace pcamv
+
+namespace pcamv {
+void launch_cost_table_batch(const BatchItem *items, int n_items, int n_mb, void *stream)
+{
+    dim3 grid((n_mb + CT_WARPS - 1) / CT_WARPS, n_items);
+    k_cost_table_batch<<<grid, CT_WARPS * 32, 0, (cudaStream_t)stream>>>(items, n_mb);
+}
+}

@@ -4,6 +4,7 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/pcamv.h"
+#include "pcamv_device.h"
 
 namespace pcamv {
 
@@ -60,11 +61,17 @@ struct FrameParams
     const ForcedMb *forced;  // pass 2 only
     uint32_t stale_mv[16];   // what the MV cache held before MB 0 of this pass (quirk q2)
     FrameArrays cur;
-    LogEntry *log;           // [n_mb][PCAMV_LOG_MAX]
+    LogEntry *log;           // [n_mb][log_stride]
+    int log_stride;          // entries per macroblock (pcamv_log_stride)
     MbResult *results;       // [n_mb]
     int *row_progress;       // [mb_h] wavefront counters
     unsigned long long *trace;   // optional [n_mb][2]: globaltimer ns at the start / end of each macroblock (profiling aid)
 };
 
+struct BatchItem             // one frame of a multi-context launch (pcamv_frame_run_batch): lives in device memory
+{
+    DevFrameCtx fc;
+    FrameParams fp;
+};
 
 } // namespace pcamv

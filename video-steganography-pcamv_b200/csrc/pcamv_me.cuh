@@ -251,9 +251,13 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
 }
 
 // costs[i] = cost of candidate i (i < n <= 4) in EVERY lane
+#if defined(PCAMV_EMU)
+static long g_eval_calls[4][5][7];      // [kind][n][i_pixel]: evaluator calls made, for the candidate-mix statistics of tests/emu
+#endif
 PCAMV_DEV void eval4(const MeBlock &b, int kind, int n, int c0, int c1, int c2, int c3, int costs[4])
 {
 #if defined(PCAMV_EMU)
+    g_eval_calls[kind][n][b.i_pixel]++;
     const int c[4] = { c0, c1, c2, c3 };
     for (int i = 0; i < 4; i++)
         costs[i] = i < n ? cand_cost(b, kind, 1, c[i], c[i], c[i], c[i]) : PCAMV_COST_MAX;

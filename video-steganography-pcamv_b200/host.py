@@ -66,7 +66,8 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_put_fenc", "pcamv_put_ref", "pcamv_put_ref_planes", "pcamv_get_ref_plane", "pcamv_plane_bytes",
            "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
            "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
-           "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace"]
+           "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
+           "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free"]
 
 _lib = None
 
@@ -103,6 +104,13 @@ def load_library(path=None):
     lib.pcamv_frame_run.argtypes = [vp, ip, ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]; lib.pcamv_frame_run.restype = ip
     lib.pcamv_frame_download.argtypes = [vp, vp, vp]; lib.pcamv_frame_download.restype = ip
     lib.pcamv_frame_trace.argtypes = [vp, ip, vp]; lib.pcamv_frame_trace.restype = ip
+    lib.pcamv_log_stride.argtypes = [vp]; lib.pcamv_log_stride.restype = ip
+    lib.pcamv_host_alloc.argtypes = [C.c_size_t]; lib.pcamv_host_alloc.restype = vp
+    lib.pcamv_host_free.argtypes = [vp]; lib.pcamv_host_free.restype = None
+    lib.pcamv_analyse_p_batch.argtypes = [C.POINTER(vp), C.POINTER(C.POINTER(FrameIn)), ip, C.POINTER(vp), C.POINTER(vp)]
+    lib.pcamv_analyse_p_batch.restype = ip
+    lib.pcamv_frame_run_batch.argtypes = [C.POINTER(vp), ip, ip, ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.pcamv_frame_run_batch.restype = ip
     if path == build.LIB:
         _lib = lib
     return lib
@@ -110,6 +118,28 @@ def load_library(path=None):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+_pinned_keep = []
+
+
+def pinned_array(shape, dtype):
+    """numpy array over page-locked memory from pcamv_host_alloc (kept alive for the life of the process)."""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = lib.pcamv_host_alloc(n)
+    if not p:
+        raise PcamvError("pcamv_host_alloc(%d) failed" % n)
+    buf = (C.c_uint8 * n).from_address(p)
+    _pinned_keep.append(buf)
+    return np.frombuffer(buf, dtype=dt).reshape(shape)
+
+
+def pinned_copy(a):
+    out = pinned_array(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 class PcamvContext:
@@ -131,6 +161,7 @@ class PcamvContext:
         if self.lib.pcamv_open(C.byref(self.handle), C.byref(cfg)) != 0:
             raise PcamvError(self.lib.pcamv_last_error(None).decode())
         self.width, self.height = width, height
+        self.log_stride = int(self.lib.pcamv_log_stride(self.handle))
         self._keep = []
 
     def close(self):
@@ -249,12 +280,16 @@ class PcamvContext:
                 fi.stale_mv[i][0], fi.stale_mv[i][1] = int(stale_mv[i][0]), int(stale_mv[i][1])
         return fi, keep
 
-    def analyse_p(self, pass_, ref_slots, ref_pocs, cur_poc, **kw):
-        """pcamv_analyse_p: returns (mb records [n_mb], log [n_mb, LOG_MAX])."""
-        fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
+    def alloc_outputs(self, pinned=False):
+        """(mb records [n_mb], log [n_mb, log_stride]) buffers for analyse_p(out=...)."""
         n_mb = (self.width // 16) * (self.height // 16)
-        mbs = np.zeros(n_mb, dtype=MB_OUT_DTYPE)
-        log = np.zeros((n_mb, LOG_MAX), dtype=LOG_ENTRY_DTYPE)
+        mk = pinned_array if pinned else (lambda s, d: np.zeros(s, dtype=d))
+        return mk((n_mb,), MB_OUT_DTYPE), mk((n_mb, self.log_stride), LOG_ENTRY_DTYPE)
+
+    def analyse_p(self, pass_, ref_slots, ref_pocs, cur_poc, out=None, **kw):
+        """pcamv_analyse_p: returns (mb records [n_mb], log [n_mb, log_stride])."""
+        fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
+        mbs, log = out if out is not None else self.alloc_outputs()
         self._check(self.lib.pcamv_analyse_p(self.handle, C.byref(fi), _ptr(mbs), _ptr(log)))
         return mbs, log
 
@@ -272,7 +307,7 @@ class PcamvContext:
     def frame_download(self, want_log=True):
         n_mb = (self.width // 16) * (self.height // 16)
         mbs = np.zeros(n_mb, dtype=MB_OUT_DTYPE)
-        log = np.zeros((n_mb, LOG_MAX), dtype=LOG_ENTRY_DTYPE) if want_log else None
+        log = np.zeros((n_mb, self.log_stride), dtype=LOG_ENTRY_DTYPE) if want_log else None
         self._check(self.lib.pcamv_frame_download(self.handle, _ptr(mbs), _ptr(log) if want_log else None))
         return mbs, log
 
@@ -290,3 +325,37 @@ class PcamvContext:
 
     def launch_count(self):
         return int(self.lib.pcamv_launch_count(self.handle))
+
+
+# -- multi-context launches (pcamv_analyse_p_batch / pcamv_frame_run_batch) -------------------------------------------
+def analyse_p_batch(ctxs, frame_args, outs=None):
+    """frame_args[i] = (pass_, ref_slots, ref_pocs, cur_poc, kwargs) for ctxs[i]; one wavefront launch for all of them.
+    outs: optional preallocated [(mbs, log), ...] (ctx.alloc_outputs).  Returns [(mbs, log), ...]."""
+    n = len(ctxs)
+    lib = ctxs[0].lib
+    fins, keeps = [], []
+    if outs is None:
+        outs = [c.alloc_outputs() for c in ctxs]
+    for c, (pass_, slots, pocs, cur_poc, kw) in zip(ctxs, frame_args):
+        fi, keep = c._frame_in(pass_, slots, pocs, cur_poc, **kw)
+        fins.append(fi); keeps.append(keep)
+    h = (C.c_void_p * n)(*[c.handle for c in ctxs])
+    pin = (C.POINTER(FrameIn) * n)(*[C.pointer(f) for f in fins])
+    pm = (C.c_void_p * n)(*[o[0].ctypes.data for o in outs])
+    pl = (C.c_void_p * n)(*[o[1].ctypes.data for o in outs])
+    if lib.pcamv_analyse_p_batch(h, pin, n, pm, pl) != 0:
+        raise PcamvError(lib.pcamv_last_error(ctxs[0].handle).decode())
+    return outs
+
+
+def frame_run_batch(ctxs, pass_, iters=1):
+    """Re-launch the staged frames of all contexts in one wavefront (+ cost-table) launch.
+    Returns (ms per launch pair, wavefront ms, cost-table ms)."""
+    n = len(ctxs)
+    lib = ctxs[0].lib
+    h = (C.c_void_p * n)(*[c.handle for c in ctxs])
+    ms = C.c_float()
+    mk = (C.c_float * 2)()
+    if lib.pcamv_frame_run_batch(h, n, pass_, iters, C.byref(ms), mk) != 0:
+        raise PcamvError(lib.pcamv_last_error(ctxs[0].handle).decode())
+    return float(ms.value), float(mk[0]), float(mk[1])

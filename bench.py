@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--streams", type=int, default=16,
+    ap.add_argument("--streams", type=int, default=128,
                     help="independent encoder contexts (GOP shards / streams) analysing concurrently on each GPU")
     ap.add_argument("--launch", choices=["batch", "streams"], default="batch",
                     help="batch: all contexts' frames in ONE wavefront launch (pcamv_analyse_p_batch); streams: one launch per context on its own CUDA stream")

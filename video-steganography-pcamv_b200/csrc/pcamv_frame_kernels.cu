@@ -116,8 +116,11 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
 // counter walks (row group, frame) pairs frame-fastest, so all frames advance together and every awaited row has a
 // smaller claim index than the waiting one — the same no-deadlock argument as for a single frame, for any grid size.
 // The grid is sized to what is resident at once; CTAs keep claiming until the work is gone (persistent).
+#ifndef PCAMV_BATCH_MIN_CTAS
+#define PCAMV_BATCH_MIN_CTAS 6      // CTAs of 4 warps per SM the register budget must allow (resident warps are what hides latency here)
+#endif
 template <int AP_WARPS>
-__global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p_batch(const BatchItem *__restrict__ items, int n_items, int *row_claim)
+__global__ void __launch_bounds__(AP_WARPS * 32, PCAMV_BATCH_MIN_CTAS * 4 / AP_WARPS) k_analyse_p_batch(const BatchItem *__restrict__ items, int n_items, int *row_claim)
 {
     __shared__ MbWork s_work[AP_WARPS];
     __shared__ __align__(16) unsigned char s_ctx[AP_WARPS][sizeof(MbCtx)];

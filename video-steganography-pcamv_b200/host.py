@@ -77,7 +77,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or build.LIB
+    path = path or os.environ.get("PCAMV_LIB") or build.LIB        # PCAMV_LIB: try an experimental build of the library
     if not os.path.exists(path):
         raise PcamvError("libpcamv_cuda.so is not built (%s); run __graft_entry__.build()" % path)
     lib = C.CDLL(path)

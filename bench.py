@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--launch", choices=["batch", "streams"], default="batch",
                     help="batch: all contexts' frames in ONE wavefront launch (pcamv_analyse_p_batch); streams: one launch per context on its own CUDA stream")
     ap.add_argument("--rows-per-cta", type=int, default=4, help="wavefront layout used when --streams > 1 (pcamv_cfg.rows_per_cta)")
+    ap.add_argument("--pass2-elide", action="store_true",
+                    help="pcamv_cfg.pass2_elide: skip the pass-2 searches whose results the reference overwrites (not the default: "
+                         "the headline number executes everything the reference executes)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (profiling runs)")
     args = ap.parse_args()
 
@@ -248,8 +251,13 @@ def main():
     ops_per_frame = 2.0 * work["pix_sad"] + 7.0 * work["pix_satd"]
 
     # ---- parity gate before any number ---------------------------------------------------------------------------
-    ctxs = [frame_parity.open_ctx(pcamv, dump, s, device=local_rank, rows_per_cta=args.rows_per_cta if S > 1 else 1) for _ in range(S)]
-    par = frame_parity.check_dump(pcamv, dump, units=units, ctx=ctxs[0], keep_ctx=True)       # raises on the first mismatch
+    ctxs = [frame_parity.open_ctx(pcamv, dump, s, device=local_rank, rows_per_cta=args.rows_per_cta if S > 1 else 1, pass2_elide=int(args.pass2_elide)) for _ in range(S)]
+    if args.pass2_elide:
+        # the gate compares complete pass-2 logs, so it runs on a context that executes everything
+        gate = frame_parity.open_ctx(pcamv, dump, s, device=local_rank)
+        par = frame_parity.check_dump(pcamv, dump, units=units, ctx=gate)
+    else:
+        par = frame_parity.check_dump(pcamv, dump, units=units, ctx=ctxs[0], keep_ctx=True)       # raises on the first mismatch
 
     x = units[0]["ctx"]
     H, W = s.lines_y, s.width
@@ -362,11 +370,32 @@ def main():
     h2d = 2 * (fy.nbytes + fu.nbytes + fv.nbytes) + 2 * 68 * n_mb + n_mb * pcamv.host.PASS1_MB_DTYPE.itemsize + len(e["filp"])
     d2h = out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes
 
+    # extra, not the headline: the same device-resident step with the dead pass-2 searches elided (what the host encoder runs)
+    elided = None
+    if not args.pass2_elide:
+        for c in ctxs:
+            c.set_pass2_elide(True)
+        dev_run(1)
+        barrier()
+        t0 = time.perf_counter()
+        k2 = np.array(dev_run(3)) / 3
+        torch.cuda.synchronize()
+        el_s = time.perf_counter() - t0
+        barrier()
+        for c in ctxs:
+            c.set_pass2_elide(False)
+        elided = {"ms_per_step": el_s / 3 * 1e3, "steps": 3, "kernel_ms_pass2": float(k2.mean(axis=0)[2]),
+                  "note": "pcamv_cfg.pass2_elide = 1: pass 2 runs only the 16x16 search of macroblocks whose decision is forced from "
+                          "pass 1; the other searches' results are overwritten by the reference (encoder/analyse.c:2868-2991) and the "
+                          "host encoder does not need them.  Candidates are still credited as the reference executes them."}
+
     int_peak = ctxs[0].int_peak_gops()
 
     # ---- aggregate over ranks (max time, summed work) ----------------------------------------------------------------
     from pcamv_b200 import shard
     dev_s_max, e2e_s_max = shard.max_over_ranks([dev_s, e2e_s])
+    if elided is not None:
+        elided["ms_per_step"] = shard.max_over_ranks([elided["ms_per_step"]])[0]
     cand_all = shard.sum_over_ranks([float(cand_per_frame) * S])[0]           # candidates of one step over all ranks and contexts
     # the one exchange step of a sharded run: per-shard statistics to rank 0 (payload bits travel the same way, shard.py)
     shards = shard.gather_gop_results([{"gop": rank * S + i, "n_bits": 0, "payload": b"", "n_mv": int(par["ih"]), "n_flipped": 0,
@@ -399,7 +428,8 @@ def main():
                        "step": "one 1080p P frame through the frame seam in each of %d independent encoder contexts per GPU (GOP shards: own "
                                "CUDA stream, own frame buffers): wavefront analysis pass 1 + candidate-MV cost table + wavefront analysis "
                                "pass 2 (%d searches/refines, %d cost-table entries per frame)" % (S, par["calls"], par["ih"]),
-                       "contexts_per_gpu": S, "launch": ("one wavefront launch for all contexts (pcamv_analyse_p_batch)" if batch else
+                       "contexts_per_gpu": S, "pass2": ("searches whose results the reference overwrites are elided (pcamv_cfg.pass2_elide)"
+                                                        if args.pass2_elide else "everything the reference executes"), "launch": ("one wavefront launch for all contexts (pcamv_analyse_p_batch)" if batch else
                                                            "one launch per context, each on its own CUDA stream"), "shards_gathered": len(shards), "candidates_per_frame": int(cand_per_frame),
                        "l2": "inputs larger than L2: %d contexts x %.1f MB of planes each, no flush" % (S, (alg_bytes) / 1e6),
                        "parity_gate": "passed: %d searches, %d macroblock decisions, %d cost-table entries bit-exact vs reference"
@@ -423,6 +453,10 @@ def main():
         for c in ctxs:
             c.close()
         ctxs = []
+        if elided is not None:
+            elided["value"] = cand_all / (elided["ms_per_step"] * 1e-3) / 1e6
+            elided["unit"] = "Mcandidates/s"
+            line["pass2_elided"] = elided
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(pcamv, clip, workdir)
             line["encoder_e2e"] = encoder_e2e(pcamv, workdir, local_rank)

@@ -45,6 +45,7 @@ typedef struct
     int active;                     /* a P-slice pass with GPU results is being replayed */
     int cur_mb, cur_pos;            /* replay cursor */
     int qp_loaded;
+    int elide, pass;                /* pass-2 elision on; pass of the slice being replayed */
     int fenc_frame;                 /* h->fenc->i_frame currently on the GPU */
     /* reference slots: which frame each GPU slot holds */
     struct { x264_frame_t *fr; int i_frame, i_poc, age; } slot[PCAMV_MAX_REFS + 2];
@@ -113,6 +114,10 @@ void pcamv_hook_open( x264_t *h )
     cfg.analyse_inter = h->param.analyse.inter;
     cfg.chroma_qp_offset = h->param.analyse.i_chroma_qp_offset;
     cfg.rows_per_cta = (s = getenv( "PCAMV_ROWS_PER_CTA" )) ? atoi( s ) : 1;
+    /* pass 2 of a forced macroblock: only the 16x16 search is live in the reference (see include/pcamv.h); PCAMV_PASS2_FULL=1
+     * makes the GPU execute and log the dead searches as well */
+    g.elide = !((s = getenv( "PCAMV_PASS2_FULL" )) && atoi( s ));
+    cfg.pass2_elide = g.elide;
     if( pcamv_open( &g.ctx, &cfg ) )
         die( "pcamv_open" );
     g.n_mb = h->sps->i_mb_width * h->sps->i_mb_height;
@@ -252,6 +257,7 @@ void pcamv_hook_slice_begin( x264_t *h )
     if( pcamv_analyse_p( g.ctx, &in, g.mbs, g.log ) )
         die( "pcamv_analyse_p" );
     g.active = 1;
+    g.pass = pass;
     g.cur_mb = -1; g.cur_pos = 0;
     g.n_passes++;
     g.t_gpu += now_s() - t0;
@@ -275,7 +281,8 @@ void pcamv_hook_analyse_end( x264_t *h )
     {
         /* every GPU entry of this macroblock must have been consumed, and the host must have arrived at the GPU's decision */
         const pcamv_mb_out *r = &g.mbs[g.cur_mb];
-        if( g.cur_pos != r->n_log )
+        const int elided = g.elide && g.pass == 2 && h->info.cache[g.cur_mb].used;
+        if( elided ? g.cur_pos < r->n_log : g.cur_pos != r->n_log )
         {
             fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host made %d search calls, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, r->n_log );
             exit( 4 );
@@ -294,6 +301,12 @@ static const pcamv_log_entry *next_entry( x264_t *h, x264_me_t *m, int kind )
     const pcamv_log_entry *e;
     if( !g.active || g.cur_mb != h->mb.i_mb_xy )
         die_msg( "motion search outside a GPU-analysed P slice (no CPU fallback)" );
+    if( g.cur_pos >= g.mbs[g.cur_mb].n_log && g.elide && g.pass == 2 && h->info.cache[g.cur_mb].used && kind != PCAMV_LOG_IHCOST )
+    {
+        /* a search of pass 2 whose result the reference overwrites at analyse.c:2868-2991: not executed on the GPU */
+        g.cur_pos++;
+        return NULL;
+    }
     if( g.cur_pos >= g.log_stride || g.cur_pos >= g.mbs[g.cur_mb].n_log )
     {
         fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host asks for call %d, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, g.mbs[g.cur_mb].n_log );
@@ -317,6 +330,12 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
     (void)mvc; (void)i_mvc;
     /* the multi-reference half-pel threshold only ever feeds later searches, which are replayed too */
     (void)p_halfpel_thresh;
+    if( !e )
+    {
+        /* dead value: large enough that no partition built from it is ever preferred, small enough that sums do not overflow */
+        m->mv[0] = m->mv[1] = 0; m->cost = 1 << 26; m->cost_mv = 0;
+        return;
+    }
     m->mv[0] = e->mv[0]; m->mv[1] = e->mv[1];
     m->cost = e->cost;
     m->cost_mv = e->cost_mv;
@@ -325,6 +344,8 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
 void x264_me_refine_qpel( x264_t *h, x264_me_t *m )
 {
     const pcamv_log_entry *e = next_entry( h, m, PCAMV_LOG_REFINE );
+    if( !e )
+        return;         /* dead refinement of pass 2: the vector is overwritten by the forcing block */
     m->mv[0] = e->mv[0]; m->mv[1] = e->mv[1];
     m->cost = e->cost;
     m->cost_mv = e->cost_mv;

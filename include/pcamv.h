@@ -65,7 +65,12 @@ typedef struct pcamv_cfg
     int chroma_qp_offset;   /* pps chroma_qp_index_offset */
     int rows_per_cta;       /* wavefront layout: 0/1 = one macroblock row per CTA (lowest latency, a single encoder);
                                2 or 4 = consecutive rows share a CTA (throughput, many concurrent contexts per GPU) */
-    int reserved[7];
+    int pass2_elide;        /* 1: in pass 2, macroblocks whose decision is forced from pass 1 (info.cache[].used) only run the
+                               16x16 search — the one result of that pass the reference still uses (h->mb.mvr candidates of later
+                               macroblocks, early-skip detection); the 8x8 / 16x8 / 8x16 searches and the refinement, whose
+                               results the reference overwrites at encoder/analyse.c:2868-2991, are not executed and do not
+                               appear in the log.  0: pass 2 executes and logs everything the reference executes. */
+    int reserved[6];
 } pcamv_cfg;
 
 /* Per-QP tables.  They are built on the host because the reference builds cost_mv with float
@@ -215,6 +220,9 @@ typedef struct pcamv_frame_in
     int32_t cost_table;                 /* pass 1: also build the candidate-MV cost table (emrate != 0) */
     int16_t stale_mv[16][2];            /* h->mb.cache.mv[0][x264_scan8[i]] as left by the previous slice pass */
 } pcamv_frame_in;
+
+/* Switch pcamv_cfg.pass2_elide of an open context (takes effect with the next launch). */
+int pcamv_set_pass2_elide(pcamv_ctx *ctx, int on);
 
 /* Entries per macroblock in the log arrays of this context: the most its configuration can produce (14 -> 16 for one
  * reference frame), never more than PCAMV_LOG_MAX.  Entry k of macroblock mb is log[mb * pcamv_log_stride(ctx) + k]. */

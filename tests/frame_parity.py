@@ -3,12 +3,12 @@ Shared by tests/test_gpu_frame.py, bench.py's parity gate and __graft_entry__.sm
 import numpy as np
 
 
-def open_ctx(pcamv, dump, s, device=0, rows_per_cta=1):
+def open_ctx(pcamv, dump, s, device=0, rows_per_cta=1, pass2_elide=0):
     c = dump.cfg
     ctx = pcamv.PcamvContext(s.width, s.lines_y, me_method=c["me_method"], me_range=c["me_range"],
                              subpel_refine=c["subme"], chroma_me=c["chroma_me"], max_refs=max(c["refs"], 1),
                              mv_range=c["mv_range"], b_cabac=c["b_cabac"], b_fast_pskip=c["fast_pskip"],
-                             b_dct_decimate=c["dct_decimate"], analyse_inter=c["inter"], device=device, rows_per_cta=rows_per_cta)
+                             b_dct_decimate=c["dct_decimate"], analyse_inter=c["inter"], device=device, rows_per_cta=rows_per_cta, pass2_elide=pass2_elide)
     t = dump.cost_tables[s.qp]
     q = dump.quant_tables()[s.qp]
     ctx.set_qp_tables(s.qp, t["lambda"], t["cost_mv"], t["cost_ref"], lambda2_chroma=q["lambda2_chroma"],

@@ -31,12 +31,12 @@ def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
-def encode_pair(pcamv, name, w, h, frames, config, noise, ref_bin, args, workdir):
+def encode_pair(pcamv, name, w, h, frames, config, noise, ref_bin, args, workdir, extra_env=None):
     clip = refrun.synth_clip(pcamv, w, h, frames, config=config, stream=1, noise16=noise, workdir=workdir)
     ref_out, _ = refrun.run_ref(clip, w, h, args.split(), binary=ref_bin, out=os.path.join(workdir, name + "_ref.264"))
     out = os.path.join(workdir, name + "_gpu.264")
     stats = os.path.join(workdir, name + "_stats.json")
-    env = dict(os.environ, PCAMV_STATS=stats)
+    env = dict(os.environ, PCAMV_STATS=stats, **(extra_env or {}))
     p = subprocess.run([HOST] + args.split() + ["-o", out, clip, "%dx%d" % (w, h)], env=env, capture_output=True, timeout=1800)
     assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")      # (the reference prints GB18030 text)
     return ref_out, out, json.load(open(stats))
@@ -50,6 +50,14 @@ def test_bitstream_identical(pcamv, cuda_lib, case, tmp_path):
     assert os.path.getsize(out) > 1000
     assert md5(out) == md5(ref_out), "bitstream differs from the reference (%d vs %d bytes)" % (os.path.getsize(out), os.path.getsize(ref_out))
     assert stats["gpu_launches"] > 0 and stats["replayed_calls"] > 0
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[2]], ids=[CASES[1][0], CASES[2][0]])
+def test_bitstream_identical_with_full_pass2(pcamv, cuda_lib, case, tmp_path):
+    """Same, with the GPU executing and logging every pass-2 search the reference executes (PCAMV_PASS2_FULL=1) instead of
+    eliding the ones whose results the reference overwrites."""
+    ref_out, out, stats = encode_pair(pcamv, *case, workdir=str(tmp_path), extra_env={"PCAMV_PASS2_FULL": "1"})
+    assert md5(out) == md5(ref_out)
 
 
 def test_payload_identical(pcamv, cuda_lib, tmp_path):

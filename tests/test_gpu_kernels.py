@@ -100,3 +100,38 @@ def test_search_calls_live_reference(pcamv, cuda_lib, args, frames, size, tmp_pa
     dump = pcamv.dumpfmt.Dump(dumpf)
     total, bad = run_calls(pcamv, dump, use_gpu_filter=True)
     assert total > 5000 and bad == 0, (total, bad)
+
+
+@pytest.mark.parametrize("w,h,mode", [(176, 144, "random"), (352, 288, "saturating"), (1280, 720, "random"), (1920, 1088, "edges")])
+def test_put_ref_planes_equal_plain_c_oracle(pcamv, cuda_lib, w, h, mode):
+    """A6/A7 on inputs no reference dump covers (random, saturating 0/255, hard edges): border expansion + the 6-tap
+    half-pel planes built on the GPU equal the plain-C restatement (oracle/leaf_oracle.c, itself pinned against the
+    reference's function tables and planes by tests/test_oracle_leaf.py)."""
+    import ctypes as C
+    from test_oracle_leaf import build_oracle_lib
+    lib = build_oracle_lib()
+    rng = np.random.default_rng(w * 7 + h)
+    if mode == "random":
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    elif mode == "saturating":
+        y = (rng.integers(0, 2, (h, w), dtype=np.uint8) * 255).astype(np.uint8)
+    else:
+        y = np.zeros((h, w), dtype=np.uint8); y[:, ::7] = 255; y[::5, :] = 255; y[h // 2:, w // 2:] = 128
+    u = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+    ctx = pcamv.PcamvContext(w, h)
+    ctx.put_ref(0, 0, y, u, v)
+    S, Sc = ctx.plane_stride(0), ctx.plane_stride(4)
+    bufs = [np.zeros((h + 64, S), dtype=np.uint8) for _ in range(4)]
+    bufs[0][32:32 + h, 32:32 + w] = y
+    ptrs = (C.c_void_p * 4)(*[b.ctypes.data + 32 * S + 32 for b in bufs])
+    lib.pcamv_oracle_frame_planes(ptrs, S, w, h)
+    for k in range(4):
+        got = ctx.get_ref_plane(0, k)
+        assert np.array_equal(got[:, :w + 64], bufs[k][:, :w + 64]), "luma plane %d" % k
+    for k, src in ((4, u), (5, v)):
+        c = np.zeros((h // 2 + 32, Sc), dtype=np.uint8)
+        c[16:16 + h // 2, 16:16 + w // 2] = src
+        lib.pcamv_oracle_chroma_border(C.c_void_p(c.ctypes.data + 16 * Sc + 16), Sc, w // 2, h // 2)
+        assert np.array_equal(ctx.get_ref_plane(0, k)[:, :w // 2 + 32], c[:, :w // 2 + 32]), "chroma plane %d" % k
+    ctx.close()

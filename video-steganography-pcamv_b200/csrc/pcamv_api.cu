@@ -83,7 +83,7 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
     fc.me_method = cfg->me_method; fc.me_range = cfg->me_range; fc.subme = cfg->subpel_refine;
     fc.chroma_me = cfg->chroma_me; fc.mv_range = cfg->mv_range; fc.max_refs = cfg->max_refs;
     fc.b_cabac = cfg->b_cabac; fc.b_fast_pskip = cfg->b_fast_pskip; fc.b_dct_decimate = cfg->b_dct_decimate;
-    fc.analyse_inter = cfg->analyse_inter;
+    fc.analyse_inter = cfg->analyse_inter; fc.pass2_elide = cfg->pass2_elide != 0;
     {
         // most entries one macroblock can log: a 16x16 search per reference (twice in pass 2 when an early skip is
         // overridden), four 8x8, two 16x8 + two 8x16 per candidate reference (<= 2 each), two refinements, two cost-table

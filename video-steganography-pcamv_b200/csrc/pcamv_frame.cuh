@@ -735,6 +735,8 @@ PCAMV_FN void update_cache(MbCtx &c, const MbAnalysis &a, int type, int partitio
 // store the MB's final state to the frame arrays (x264_macroblock_cache_save, inter part) and the result record
 PCAMV_FN void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition, int early_skip)
 {
+    const int no_parts = partition < 0;        // elided pass-2 macroblock: the partition slots were never searched
+    if (no_parts) partition = -partition;
     const int mb_w = c.fc.mb_w, s8 = 2 * mb_w, s4 = 4 * mb_w;
     const int cur8 = 2 * c.mb_y * s8 + 2 * c.mb_x, cur4 = 4 * c.mb_y * s4 + 4 * c.mb_x;
     if (team_lane() == 0)
@@ -753,7 +755,7 @@ PCAMV_FN void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition
 #pragma unroll 1
         for (int i = 0; i < 16; i++) r.mv[i] = c.w.mv[scan8(i)];
         r.n_part = 0;
-        if (type != MB_P_SKIP)
+        if (type != MB_P_SKIP && !no_parts)
         {
             const int np = partition == PART_16x16 ? 1 : partition == PART_8x8 ? 4 : 2;
             r.n_part = (int8_t)np;
@@ -847,6 +849,19 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
             for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = PCAMV_LDV(prev_mv + i);
         }
         finalize_mb(c, a, MB_P_SKIP, PART_16x16, early_skip);
+        return;
+    }
+
+    if (forced && forced->used && fc.pass2_elide)
+    {
+        // pass 2, decision forced from pass 1: nothing the remaining searches produce survives analyse.c:2868-2991
+        type = forced->type; partition = forced->partition;
+#pragma unroll 1
+        for (int i = 0; i < 4; i++)
+            cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
+        finalize_mb(c, a, type, -partition, 0);
         return;
     }
 

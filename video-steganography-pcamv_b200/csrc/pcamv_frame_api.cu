@@ -238,6 +238,13 @@ extern "C" int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_m
     return pcamv_frame_download(ctx, mbs, log);
 }
 
+extern "C" int pcamv_set_pass2_elide(pcamv_ctx *ctx, int on)
+{
+    GUARD();
+    ctx->fc.pass2_elide = on != 0;
+    return 0;
+}
+
 extern "C" int pcamv_log_stride(const pcamv_ctx *ctx) { return ctx ? ctx->log_stride : 0; }
 
 extern "C" int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out)

@@ -24,7 +24,7 @@ class Cfg(C.Structure):
                 ("me_method", C.c_int), ("me_range", C.c_int), ("subpel_refine", C.c_int), ("chroma_me", C.c_int),
                 ("max_refs", C.c_int), ("mv_range", C.c_int), ("b_cabac", C.c_int), ("b_fast_pskip", C.c_int),
                 ("b_dct_decimate", C.c_int), ("analyse_inter", C.c_int), ("chroma_qp_offset", C.c_int),
-                ("rows_per_cta", C.c_int), ("reserved", C.c_int * 7)]
+                ("rows_per_cta", C.c_int), ("pass2_elide", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class QpTables(C.Structure):
@@ -67,7 +67,7 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
            "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
            "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
-           "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free"]
+           "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide"]
 
 _lib = None
 
@@ -105,6 +105,7 @@ def load_library(path=None):
     lib.pcamv_frame_download.argtypes = [vp, vp, vp]; lib.pcamv_frame_download.restype = ip
     lib.pcamv_frame_trace.argtypes = [vp, ip, vp]; lib.pcamv_frame_trace.restype = ip
     lib.pcamv_log_stride.argtypes = [vp]; lib.pcamv_log_stride.restype = ip
+    lib.pcamv_set_pass2_elide.argtypes = [vp, ip]; lib.pcamv_set_pass2_elide.restype = ip
     lib.pcamv_host_alloc.argtypes = [C.c_size_t]; lib.pcamv_host_alloc.restype = vp
     lib.pcamv_host_free.argtypes = [vp]; lib.pcamv_host_free.restype = None
     lib.pcamv_analyse_p_batch.argtypes = [C.POINTER(vp), C.POINTER(C.POINTER(FrameIn)), ip, C.POINTER(vp), C.POINTER(vp)]
@@ -146,7 +147,7 @@ class PcamvContext:
     """One encoder's GPU context (mirrors one x264_t)."""
 
     def __init__(self, width, height, me_method=1, me_range=16, subpel_refine=5, chroma_me=1, max_refs=1,
-                 mv_range=512, b_cabac=1, b_fast_pskip=1, b_dct_decimate=1, analyse_inter=0x113, device=0, rows_per_cta=1):
+                 mv_range=512, b_cabac=1, b_fast_pskip=1, b_dct_decimate=1, analyse_inter=0x113, device=0, rows_per_cta=1, pass2_elide=0):
         self.lib = load_library()
         cfg = Cfg()
         cfg.abi_version = self.lib.pcamv_abi_version()
@@ -156,6 +157,7 @@ class PcamvContext:
         cfg.max_refs, cfg.mv_range, cfg.b_cabac, cfg.b_fast_pskip = max_refs, mv_range, b_cabac, b_fast_pskip
         cfg.b_dct_decimate, cfg.analyse_inter = b_dct_decimate, analyse_inter
         cfg.rows_per_cta = rows_per_cta
+        cfg.pass2_elide = pass2_elide
         self.cfg = cfg
         self.handle = C.c_void_p()
         if self.lib.pcamv_open(C.byref(self.handle), C.byref(cfg)) != 0:
@@ -317,6 +319,9 @@ class PcamvContext:
         out = np.zeros((n_mb, 2), dtype=np.uint64) if fetch else None
         self._check(self.lib.pcamv_frame_trace(self.handle, int(enable), _ptr(out) if fetch else None))
         return out
+
+    def set_pass2_elide(self, on):
+        self._check(self.lib.pcamv_set_pass2_elide(self.handle, int(bool(on))))
 
     def int_peak_gops(self):
         g = C.c_double()

@@ -121,7 +121,7 @@ def cpu_baseline_block(pcamv, clip, workdir):
             "encode_frames_per_sec": CLIP_FRAMES / st["t_total"]}
 
 
-def encoder_e2e(pcamv, workdir, device, frames=8):
+def encoder_e2e(pcamv, workdir, device, frames=24):
     """Whole-encoder leg: the reference's C host with the CUDA shim bound in (host/_build/x264_pcamv) against the
     reference encoder on the same 1080p clip and flags — wall-clock frames/s of encode + embed, bitstreams compared."""
     import hashlib
@@ -419,6 +419,13 @@ def main():
         plane_y = ctxs[0].plane_bytes(0); plane_c = ctxs[0].plane_bytes(4)
         alg_bytes = fy.nbytes + fu.nbytes + fv.nbytes + 4 * plane_y + 2 * plane_c + n_mb * (128 + ctxs[0].log_stride * 16 + 68)
         achieved = S * alg_bytes / (kernels[dom] * 1e-3) / 1e9      # (batch: one launch covers S frames; streams: S overlapping launches)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr["contexts_per_gpu"] == S and batch:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]       # per launch of the dominant kernel, one ncu capture
+        except Exception:
+            pass
         frames_all = world * S * args.steps
         line = {
             "metric": METRIC, "value": value, "unit": "Mcandidates/s", "n_gpus": world, "steps": args.steps,
@@ -441,7 +448,7 @@ def main():
             "gpu_launches": int(n_launch + n_launch_e2e),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": dom,
+                         "traffic": traffic, "kernel": dom, "algorithmic_bytes_per_launch": int(S * alg_bytes),
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "note": "the analysis kernels are integer-issue / dependency-latency bound, not HBM bound (SURVEY.md 8(d)); "
                                  "see int_issue"},

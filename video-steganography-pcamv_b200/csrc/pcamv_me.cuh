@@ -164,7 +164,14 @@ PCAMV_DEV void ld_row16(const uint8_t *p, uint32_t w[4])
 // SAD: a lane owns whole rows (sub, sub + 8) of up to 16 pixels; SATD: a lane owns 4x4 units.
 PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2, int c3)
 {
-    const int grp = team_grp(), sub = team_sub();
+    // a single candidate gets the whole team (32 lanes) instead of one group of 8
+#if defined(PCAMV_EMU)
+    const int wide = 0, lpg = 1, grp = 0, sub = 0;
+#else
+    const int wide = n == 1;
+    const int lpg = wide ? 32 : PCAMV_LPG;
+    const int grp = wide ? 0 : team_grp(), sub = wide ? team_lane() : team_sub();
+#endif
     const int c = grp == 0 ? c0 : grp == 1 ? c1 : grp == 2 ? c2 : c3;
     const int qx = pk_x(c), qy = pk_y(c);
     int acc = 0;
@@ -174,9 +181,9 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
     {
         const int w4 = b.bw >> 2;
 #pragma unroll 1
-        for (int r = 0; r < PCAMV_ROWS && PCAMV_LPG * r < b.bh; r++)
+        for (int r = 0; r < PCAMV_ROWS && lpg * r < b.bh; r++)
         {
-            const int y = sub + PCAMV_LPG * r;
+            const int y = sub + lpg * r;
             const int yy = imin(y, b.bh - 1);
             uint32_t p[4];
             ld_row16(s1 + yy * b.stride, p);
@@ -196,41 +203,39 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
     }
     else
     {
-        const int llx = b.bw == 16 ? 2 : b.bw == 8 ? 1 : 0;         // log2(luma 4x4 units per row)
+        // 4x4 units: nl luma units, then nc units of U, then nc units of V; one Hadamard per unit
+        const int llx = b.bw == 16 ? 2 : b.bw == 8 ? 1 : 0;         // log2(luma units per row)
         const int nl = (b.bh >> 2) << llx;
+        const int lcx = b.bw == 16 ? 1 : 0;                        // log2(chroma units per row)
+        const int nc = kind == COST_SATD_CHROMA ? (b.bh >> 3) << lcx : 0;
+        const int total = nl + 2 * nc;
+        const int dx = qx & 7, dy = qy & 7;
+        const int cA = (8 - dx) * (8 - dy), cB = dx * (8 - dy), cC = (8 - dx) * dy, cD = dx * dy;
 #pragma unroll 1
-        for (int k = 0; k * PCAMV_LPG < nl; k++)
+        for (int k = 0; k * lpg < total; k++)
         {
-            const int u = sub + PCAMV_LPG * k;
-            const int uu = u < nl ? u : 0;
-            const int x = (uu & ((1 << llx) - 1)) << 2, y = (uu >> llx) << 2;
+            const int u = sub + lpg * k;
+            const int uu = u < total ? u : 0;
             uint32_t f[4], a[4];
+            if (uu < nl)
+            {
+                const int x = (uu & ((1 << llx) - 1)) << 2, y = (uu >> llx) << 2;
 #pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                f[r] = ld4a(b.fenc + (y + r) * 16 + x);
-                a[r] = pred4(s1, s2, b.stride, x, y + r);
+                for (int r = 0; r < 4; r++)
+                {
+                    f[r] = ld4a(b.fenc + (y + r) * 16 + x);
+                    a[r] = pred4(s1, s2, b.stride, x, y + r);
+                }
             }
-            const int h = (int)(hadamard_4x4_sum(f, a) >> 1);
-            acc += u < nl ? h : 0;
-        }
-        if (kind == COST_SATD_CHROMA)
-        {
-            const int lcx = b.bw == 16 ? 1 : 0;                        // log2(chroma 4x4 units per row)
-            const int nc = (b.bh >> 3) << lcx;                         // units per chroma plane
-            const int dx = qx & 7, dy = qy & 7;
-            const int cA = (8 - dx) * (8 - dy), cB = dx * (8 - dy), cC = (8 - dx) * dy, cD = dx * dy;
-#pragma unroll 1
-            for (int k = 0; k * PCAMV_LPG < 2 * nc; k++)
+            else
             {
-                const int u = sub + PCAMV_LPG * k;
-                int v = u < 2 * nc ? u : 0;
+                int v = uu - nl;
                 const int pl = v >= nc;
                 v -= pl ? nc : 0;
                 const int x = (v & ((1 << lcx) - 1)) << 2, y = (v >> lcx) << 2;
                 const uint8_t *fe = (pl ? b.fenc_v : b.fenc_u) + y * 8 + x;
                 const uint8_t *s = (pl ? b.ref_v : b.ref_u) + ((qy >> 3) + y) * b.stride_c + (qx >> 3) + x;
-                uint32_t f[4], a[4], t0, t1;
+                uint32_t t0, t1;
                 ld4x2(s, t0, t1);
 #pragma unroll
                 for (int r = 0; r < 4; r++)
@@ -241,12 +246,14 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
                     a[r] = bilin4(t0, t1, u0, u1, cA, cB, cC, cD);
                     t0 = u0; t1 = u1;
                 }
-                const int h = (int)(hadamard_4x4_sum(f, a) >> 1);
-                acc += u < 2 * nc ? h : 0;
             }
+            const int h = (int)(hadamard_4x4_sum(f, a) >> 1);
+            acc += u < total ? h : 0;
         }
     }
-    acc = grp_sum(acc);
+#if !defined(PCAMV_EMU)
+    acc = wide ? team_sum(acc) : grp_sum(acc);
+#endif
     return grp < n ? acc + b.cost_mvx[qx] + b.cost_mvy[qy] : PCAMV_COST_MAX;
 }
 

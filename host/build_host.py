@@ -36,6 +36,103 @@ ANALYSE_EXTRA = ("struct x264_me_t_tag; int pcamv_glue_ih_cost( x264_t *h, x264_
                  "  x264_mb_analyse_load_costs( h, &a ); }\n")
 IH_WRAPPER = ("{ int r = pcamv_glue_ih_cost( h, m, m_x, m_y ); x264_analyse_update_cache( h, analysis ); return r; }\n")
 
+# x264.c: `x264_pcamv --shards N --shard-frames K <x264 arguments>` encodes N IDR-bounded shards of K frames each
+# (frames [g*K, (g+1)*K) = the CLI's own --seek / --frames) on N threads of one process, which share the
+# GPU through an encoder group, and concatenates the shards' NAL streams in order.  Without --shards the CLI is unchanged.
+SHARD_MAIN = r'''
+/* ---- appended by host/build_host.py: GOP-sharded encoding on threads of one process -------------------------------- */
+#include <pthread.h>
+void pcamv_glue_set_shards( int n );
+void pcamv_glue_shard_done( void );
+typedef struct { x264_param_t param; cli_opt_t opt; int ret; char out[1024]; } pcamv_shard_t;
+static void *pcamv_shard_thread( void *p )
+{
+    pcamv_shard_t *s = (pcamv_shard_t *)p;
+    s->ret = Encode( &s->param, &s->opt );
+    pcamv_glue_shard_done();
+    return NULL;
+}
+int main( int argc, char **argv )
+{
+    int n, k, g, i, o_at = -1, ret = 0;
+    pcamv_shard_t *sh;
+    pthread_t *th;
+    FILE *fo;
+    if( argc < 6 || strcmp( argv[1], "--shards" ) || strcmp( argv[3], "--shard-frames" ) )
+        return x264_cli_main( argc, argv );
+    n = atoi( argv[2] ); k = atoi( argv[4] );
+    if( n < 1 || k < 1 ) { fprintf( stderr, "x264 [error]: bad --shards / --shard-frames\n" ); return -1; }
+    for( i = 5; i < argc - 1; i++ )
+        if( !strcmp( argv[i], "-o" ) || !strcmp( argv[i], "--output" ) ) o_at = i + 1;
+    if( o_at < 0 ) { fprintf( stderr, "x264 [error]: --shards needs -o\n" ); return -1; }
+    sh = calloc( n, sizeof(*sh) ); th = calloc( n, sizeof(*th) );
+    for( g = 0; g < n; g++ )
+    {
+        /* the shard's command line: the user's arguments, its own output file, --seek g*K --frames K */
+        char **av = calloc( argc + 8, sizeof(char *) ), seek[32], frames[32];
+        int ac = 0;
+        av[ac++] = argv[0];
+        snprintf( sh[g].out, sizeof(sh[g].out), "%s.%d", argv[o_at], g );
+        snprintf( seek, sizeof(seek), "%d", g * k ); snprintf( frames, sizeof(frames), "%d", k );
+        av[ac++] = "--seek"; av[ac++] = strdup( seek ); av[ac++] = "--frames"; av[ac++] = strdup( frames );
+        for( i = 5; i < argc; i++ ) av[ac++] = i == o_at ? sh[g].out : argv[i];
+        optind = 0;                                   /* getopt state is global: shards are parsed one after the other */
+        x264_param_default( &sh[g].param );
+        if( Parse( ac, av, &sh[g].param, &sh[g].opt ) < 0 ) return -1;
+        sh[g].opt.b_progress = 0;
+    }
+    {
+        /* the reference fills several global tables the first time an encoder opens (x264_rdo_init, x264_init_vlc_tables,
+         * x264_dct_init_weights, the lambda*bits tables): open and close one encoder before any thread runs */
+        x264_param_t warm = sh[0].param;
+        x264_t *hw = x264_encoder_open( &warm );
+        if( !hw ) return -1;
+        x264_encoder_close( hw );
+    }
+    pcamv_glue_set_shards( n );
+    signal( SIGINT, SigIntHandler );
+    for( g = 0; g < n; g++ ) pthread_create( &th[g], NULL, pcamv_shard_thread, &sh[g] );
+    for( g = 0; g < n; g++ ) { pthread_join( th[g], NULL ); ret |= sh[g].ret; }
+    fo = fopen( argv[o_at], "wb" );
+    if( !fo ) return -1;
+    for( g = 0; g < n; g++ )
+    {
+        FILE *fi = fopen( sh[g].out, "rb" );
+        char buf[1 << 16]; size_t r;
+        if( !fi ) { ret = -1; continue; }
+        while( ( r = fread( buf, 1, sizeof(buf), fi ) ) > 0 ) fwrite( buf, 1, r, fo );
+        fclose( fi ); remove( sh[g].out );
+    }
+    fclose( fo );
+    return ret;
+}
+'''
+
+
+def shard_driver(tree):
+    p = os.path.join(tree, "x264.c")
+    t = reftree.read(p)
+    t = reftree.sub_exact(t, r"\nint main\( int argc, char \*\*argv \)\n", "\nint x264_cli_main( int argc, char **argv )\n", 1, "main")
+    # the NAL staging buffer of the CLI is a global: one per encoder thread
+    t = reftree.sub_exact(t, r"\nuint8_t \*mux_buffer = NULL;\nint mux_buffer_size = 0;", "\n__thread uint8_t *mux_buffer = NULL;\n__thread int mux_buffer_size = 0;", 1, "mux_buffer")
+    t += SHARD_MAIN
+    reftree.write(p, t)
+    # payload bits: rand() & 1 (encoder/encoder.c:1838-1840) -> the same seed-1 stream, but per encoder thread
+    p = os.path.join(tree, "encoder/encoder.c")
+    t = reftree.read(p)
+    t = reftree.sub_exact(t, r"h->info\.message\[i\] = rand\(\) & 0x01;", "h->info.message[i] = pcamv_tls_rand() & 0x01;", 1, "rand")
+    t = t.replace("void pcamv_hook_open( x264_t *h );", "int pcamv_tls_rand( void ); void pcamv_hook_open( x264_t *h );", 1)
+    # x264_encoder_close frees the process-wide lambda*bits tables (encoder/encoder.c:2944-2952) although the function-static
+    # pointers in encoder/analyse.c:195 keep referring to them: with more than one encoder per process they must stay
+    t = reftree.sub_exact(t, r"x264_free\(g_x264_cost_mv_fpel\[i\]\[j\]\);", ";", 1, "free fpel tables")
+    t = reftree.sub_exact(t, r"x264_free\(g_cost_mv\[i\]\);", ";", 1, "free cost_mv tables")
+    reftree.write(p, t)
+    # the LCG behind the STC sub-matrices for widths outside the built-in tables (embed.h:134-139) keeps static state
+    p = os.path.join(tree, "embed.h")
+    t = reftree.read(p)
+    t = reftree.sub_exact(t, r"static long myholdrand = 1L;", "static __thread long myholdrand = 1L;", 1, "myholdrand")
+    reftree.write(p, t)
+
 
 def main():
     if not os.path.isdir(reftree.REF):
@@ -49,6 +146,7 @@ def main():
     reftree.copy_tree(tree)
     reftree.widen(tree)
     reftree.hook_call_sites(tree, HOOK_DECL, IH_WRAPPER, analyse_extra=ANALYSE_EXTRA)
+    shard_driver(tree)
     exe = os.path.join(OUT, "x264_pcamv")
     reftree.compile_tree(tree, exe,
                          extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c")],

@@ -24,6 +24,7 @@
 #include "encoder/macroblock.h"
 #include "pcamv.h"
 #include <time.h>
+#include <pthread.h>
 
 void x264_me_search_ref_real( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
 void x264_me_refine_qpel_real( x264_t *h, x264_me_t *m );
@@ -55,7 +56,52 @@ typedef struct
     long n_passes, n_replayed;
 } glue_t;
 
-static glue_t g;
+/* one encoder instance lives on one thread from x264_encoder_open to x264_encoder_close (x264.c Encode), so the glue
+ * state is thread-local: several encoders (GOP shards) run side by side in one process (--shards, see host/build_host.py) */
+static __thread glue_t g;
+
+/* shards of one process share the GPU through an encoder group (include/pcamv.h): one multi-context launch per step */
+static pcamv_group *g_group;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static __thread int g_in_group;
+
+void pcamv_glue_set_shards( int n )
+{
+    if( n > 1 && pcamv_group_create( &g_group, n ) )
+    {
+        fprintf( stderr, "x264 [pcamv]: pcamv_group_create failed\n" );
+        exit( 3 );
+    }
+}
+
+/* called by a shard's thread when its encoder is gone, however it ended */
+void pcamv_glue_shard_done( void )
+{
+    if( g_group && g_in_group )
+    {
+        pcamv_group_leave( g_group );
+        g_in_group = 0;
+    }
+}
+
+/* The payload is rand() & 1 with no srand anywhere (encoder/encoder.c:1838-1840): the seed-1 stream of glibc rand().  A
+ * shard is an independent encoder run, so it needs that stream from its start — per thread, not shared.  random_r with
+ * initstate_r( 1, 128 bytes ) is the generator behind rand() (checked value for value in tests). */
+int pcamv_tls_rand( void )
+{
+    static __thread struct random_data rd;
+    static __thread char st[128];
+    static __thread int init;
+    int32_t r;
+    if( !init )
+    {
+        rd.state = NULL;
+        initstate_r( 1, st, sizeof(st), &rd );
+        init = 1;
+    }
+    random_r( &rd, &r );
+    return r;
+}
 
 static double now_s( void )
 {
@@ -118,8 +164,14 @@ void pcamv_hook_open( x264_t *h )
      * makes the GPU execute and log the dead searches as well */
     g.elide = !((s = getenv( "PCAMV_PASS2_FULL" )) && atoi( s ));
     cfg.pass2_elide = g.elide;
+    pthread_mutex_lock( &g_mu );
     if( pcamv_open( &g.ctx, &cfg ) )
         die( "pcamv_open" );
+    /* the reference builds its lambda*bits tables lazily into function-static storage (analyse.c:193-229): do it here, once,
+     * under the lock, so that concurrent encoders only ever read them */
+    pcamv_glue_load_costs( h, h->param.rc.i_qp_constant );
+    pthread_mutex_unlock( &g_mu );
+    g_in_group = g_group != NULL;
     g.n_mb = h->sps->i_mb_width * h->sps->i_mb_height;
     g.n_slots = cfg.max_refs + 2;
     g.mbs = pcamv_host_alloc( g.n_mb * sizeof(*g.mbs) );      /* page-locked: results arrive without a staging copy */
@@ -145,6 +197,7 @@ void pcamv_hook_close( x264_t *h )
             fclose( f );
         }
     }
+    pcamv_glue_shard_done();
     if( g.ctx ) pcamv_close( g.ctx );
     pcamv_host_free( g.mbs ); pcamv_host_free( g.log ); free( g.pass1 );
     memset( &g, 0, sizeof(g) );
@@ -192,7 +245,9 @@ void pcamv_hook_slice_begin( x264_t *h )
     {
         pcamv_qp_tables t;
         int qpc = h->chroma_qp_table[qp];
+        pthread_mutex_lock( &g_mu );
         pcamv_glue_load_costs( h, qp );       /* the reference builds the table lazily at the first macroblock (analyse.c:198) */
+        pthread_mutex_unlock( &g_mu );
         memset( &t, 0, sizeof(t) );
         t.qp = qp; t.lambda = x264_lambda_tab[qp]; t.lambda2_chroma = x264_lambda2_tab[qpc]; t.chroma_qp = qpc;
         t.cost_mv = g_cost_mv[qp];
@@ -254,7 +309,7 @@ void pcamv_hook_slice_begin( x264_t *h )
         in.stale_mv[i][0] = h->mb.cache.mv[0][x264_scan8[i]][0];
         in.stale_mv[i][1] = h->mb.cache.mv[0][x264_scan8[i]][1];
     }
-    if( pcamv_analyse_p( g.ctx, &in, g.mbs, g.log ) )
+    if( g_group ? pcamv_group_analyse_p( g_group, g.ctx, &in, g.mbs, g.log ) : pcamv_analyse_p( g.ctx, &in, g.mbs, g.log ) )
         die( "pcamv_analyse_p" );
     g.active = 1;
     g.pass = pass;

@@ -253,6 +253,16 @@ int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *i
                           pcamv_mb_out *const *mbs, pcamv_log_entry *const *logs);
 int pcamv_frame_run_batch(pcamv_ctx *const *ctxs, int n, int pass, int iters, float *ms_per_step, float *ms_kernels);
 
+/* Encoder groups: n encoder threads of one process (one per GOP shard / stream, each with its own context) share the
+ * GPU through multi-context launches without knowing about each other.  pcamv_group_analyse_p is pcamv_analyse_p for a
+ * member: it blocks until every live member has submitted its frame, the last arriver launches for all, and each call
+ * returns with its own results.  A member whose encoder has no more frames calls pcamv_group_leave (once). */
+typedef struct pcamv_group pcamv_group;
+int pcamv_group_create(pcamv_group **out, int n_members);
+void pcamv_group_destroy(pcamv_group *g);
+int pcamv_group_analyse_p(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log);
+int pcamv_group_leave(pcamv_group *g);
+
 /* Profiling aid: with enable != 0 the next wavefront launches record the device globaltimer (ns) at the start and end
  * of every macroblock; out (may be NULL) receives the [n_mb][2] records of the last traced launch. */
 int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out);

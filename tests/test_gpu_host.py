@@ -88,3 +88,24 @@ def test_payload_identical(pcamv, cuda_lib, tmp_path):
         assert np.array_equal(msg, e["message"]) and np.array_equal(stego, e["stego"])
         bits += max(an, 0)
     assert bits > 100
+
+
+def test_sharded_encode_equals_per_gop_reference_runs(pcamv, cuda_lib, tmp_path):
+    """GOP sharding: `x264_pcamv --shards N --shard-frames K` runs N encoder instances on threads of one
+    process, sharing the GPU through an encoder group (one multi-context launch per step); its output must be the
+    concatenation of N independent reference runs `--seek g*K --frames K` (the parity definition for sharded mode)."""
+    w, h, n, k = 352, 288, 4, 5
+    args = "--qp 26 --ref 2 --keyint 250 --me hex --subme 5 --emrate 0.2"
+    workdir = str(tmp_path)
+    clip = refrun.synth_clip(pcamv, w, h, n * k, config=1, stream=4, workdir=workdir)
+    want = b""
+    for g in range(n):
+        out, _ = refrun.run_ref(clip, w, h, args.split() + ["--seek", str(g * k), "--frames", str(k)], binary="x264_wide",
+                                out=os.path.join(workdir, "ref_%d.264" % g))
+        want += open(out, "rb").read()
+    out = os.path.join(workdir, "sharded.264")
+    p = subprocess.run([HOST, "--shards", str(n), "--shard-frames", str(k)] + args.split() + ["-o", out, clip, "%dx%d" % (w, h)],
+                       capture_output=True, timeout=1800)
+    assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")
+    got = open(out, "rb").read()
+    assert len(got) == len(want) and got == want

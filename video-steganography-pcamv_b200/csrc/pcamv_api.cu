@@ -22,7 +22,7 @@ int pcamv::ctx_fail(pcamv_ctx *c, const char *what, cudaError_t e)
 }
 static int fail(pcamv_ctx *c, const char *what, cudaError_t e) { return ctx_fail(c, what, e); }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, #call, e_); } while (0)
-#define GUARD() do { if (!ctx) return -1; if (ctx->failed) return -1; } while (0)
+#define GUARD() do { if (!ctx) return -1; if (ctx->failed) return -1; cudaSetDevice(ctx->cfg.device); } while (0)   /* calls may come from any host thread */
 
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -131,6 +131,7 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
 extern "C" void pcamv_close(pcamv_ctx *ctx)
 {
     if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_fenc);
     for (int s = 0; s < PCAMV_SLOTS; s++) { cudaFree(ctx->d_ref[s]); cudaFree(ctx->d_integral[s]); }

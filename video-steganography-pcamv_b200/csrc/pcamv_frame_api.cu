@@ -25,7 +25,7 @@ static_assert(sizeof(pcamv_pass1_mb) == sizeof(Pass1Mb) && offsetof(pcamv_pass1_
 static_assert(sizeof(ForcedOut) == sizeof(ForcedMb), "forced layout");
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(ctx, #call, e_); } while (0)
-#define GUARD() do { if (!ctx) return -1; if (ctx->failed) return -1; } while (0)
+#define GUARD() do { if (!ctx) return -1; if (ctx->failed) return -1; cudaSetDevice(ctx->cfg.device); } while (0)   /* calls may come from any host thread */
 
 static int ensure_frame_buffers(pcamv_ctx *ctx)
 {
@@ -389,5 +389,96 @@ extern "C" int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_i
     for (int i = 0; i < n; i++)
         if (frame_download_finish(ctxs[i], mbs[i], logs ? logs[i] : nullptr))
             return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
+    return 0;
+}
+
+// ---- encoder groups: several encoder threads of one process (GOP shards / streams), one GPU launch per step --------------
+// Every member calls pcamv_group_analyse_p when its encoder reaches a P-slice pass; the call blocks until every live
+// member has submitted, the last arriver analyses all submitted frames with multi-context launches (one per distinct pass),
+// and everybody returns with its own results.  Members that have no more frames call pcamv_group_leave.
+#include <condition_variable>
+#include <mutex>
+
+struct pcamv_group
+{
+    std::mutex mu;
+    std::condition_variable cv;
+    int n_live = 0, n_arrived = 0;
+    unsigned long long generation = 0;
+    std::vector<pcamv_ctx *> ctxs;
+    std::vector<const pcamv_frame_in *> ins;
+    std::vector<pcamv_mb_out *> mbs;
+    std::vector<pcamv_log_entry *> logs;
+    std::vector<int *> rcs;
+    std::string err;
+};
+
+extern "C" int pcamv_group_create(pcamv_group **out, int n_members)
+{
+    if (!out || n_members <= 0) return -1;
+    pcamv_group *g = new pcamv_group();
+    g->n_live = n_members;
+    *out = g;
+    return 0;
+}
+
+extern "C" void pcamv_group_destroy(pcamv_group *g) { delete g; }
+
+// runs with g->mu held by the last arriver
+static void group_launch(pcamv_group *g)
+{
+    const int n = (int)g->ctxs.size();
+    std::vector<char> done(n, 0);
+    for (int i = 0; i < n; i++)
+    {
+        if (done[i]) continue;
+        std::vector<pcamv_ctx *> c; std::vector<const pcamv_frame_in *> in; std::vector<pcamv_mb_out *> mb; std::vector<pcamv_log_entry *> lg;
+        std::vector<int> idx;
+        for (int k = i; k < n; k++)
+            if (!done[k] && g->ins[k]->pass == g->ins[i]->pass)
+            {
+                c.push_back(g->ctxs[k]); in.push_back(g->ins[k]); mb.push_back(g->mbs[k]); lg.push_back(g->logs[k]);
+                idx.push_back(k); done[k] = 1;
+            }
+        const int rc = pcamv_analyse_p_batch(c.data(), in.data(), (int)c.size(), mb.data(), lg.data());
+        if (rc) g->err = pcamv_last_error(c[0]);
+        for (int k : idx) *g->rcs[k] = rc;
+    }
+    g->ctxs.clear(); g->ins.clear(); g->mbs.clear(); g->logs.clear(); g->rcs.clear();
+    g->n_arrived = 0;
+    g->generation++;
+}
+
+extern "C" int pcamv_group_analyse_p(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    if (!g || !ctx || !in || !mbs) return -1;
+    int rc = 0;
+    std::unique_lock<std::mutex> lk(g->mu);
+    g->ctxs.push_back(ctx); g->ins.push_back(in); g->mbs.push_back(mbs); g->logs.push_back(log); g->rcs.push_back(&rc);
+    g->n_arrived++;
+    if (g->n_arrived >= g->n_live)
+    {
+        group_launch(g);
+        g->cv.notify_all();
+    }
+    else
+    {
+        const unsigned long long gen = g->generation;
+        g->cv.wait(lk, [&] { return g->generation != gen; });
+    }
+    return rc;
+}
+
+extern "C" int pcamv_group_leave(pcamv_group *g)
+{
+    if (!g) return -1;
+    std::unique_lock<std::mutex> lk(g->mu);
+    g->n_live--;
+    if (g->n_live > 0 && g->n_arrived >= g->n_live)
+    {
+        // the members still waiting were only waiting for this one
+        group_launch(g);
+        g->cv.notify_all();
+    }
     return 0;
 }

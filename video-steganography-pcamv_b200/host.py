@@ -67,7 +67,8 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
            "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
            "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
-           "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide"]
+           "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide",
+           "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave"]
 
 _lib = None
 
@@ -106,6 +107,10 @@ def load_library(path=None):
     lib.pcamv_frame_trace.argtypes = [vp, ip, vp]; lib.pcamv_frame_trace.restype = ip
     lib.pcamv_log_stride.argtypes = [vp]; lib.pcamv_log_stride.restype = ip
     lib.pcamv_set_pass2_elide.argtypes = [vp, ip]; lib.pcamv_set_pass2_elide.restype = ip
+    lib.pcamv_group_create.argtypes = [C.POINTER(vp), ip]; lib.pcamv_group_create.restype = ip
+    lib.pcamv_group_destroy.argtypes = [vp]; lib.pcamv_group_destroy.restype = None
+    lib.pcamv_group_analyse_p.argtypes = [vp, vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_group_analyse_p.restype = ip
+    lib.pcamv_group_leave.argtypes = [vp]; lib.pcamv_group_leave.restype = ip
     lib.pcamv_host_alloc.argtypes = [C.c_size_t]; lib.pcamv_host_alloc.restype = vp
     lib.pcamv_host_free.argtypes = [vp]; lib.pcamv_host_free.restype = None
     lib.pcamv_analyse_p_batch.argtypes = [C.POINTER(vp), C.POINTER(C.POINTER(FrameIn)), ip, C.POINTER(vp), C.POINTER(vp)]

@@ -44,10 +44,12 @@ SHARD_MAIN = r'''
 #include <pthread.h>
 void pcamv_glue_set_shards( int n );
 void pcamv_glue_shard_done( void );
-typedef struct { x264_param_t param; cli_opt_t opt; int ret; char out[1024]; } pcamv_shard_t;
+void pcamv_glue_set_shard_index( int i );
+typedef struct { x264_param_t param; cli_opt_t opt; int ret, index; char out[1024]; } pcamv_shard_t;
 static void *pcamv_shard_thread( void *p )
 {
     pcamv_shard_t *s = (pcamv_shard_t *)p;
+    pcamv_glue_set_shard_index( s->index );
     s->ret = Encode( &s->param, &s->opt );
     pcamv_glue_shard_done();
     return NULL;
@@ -80,6 +82,7 @@ int main( int argc, char **argv )
         x264_param_default( &sh[g].param );
         if( Parse( ac, av, &sh[g].param, &sh[g].opt ) < 0 ) return -1;
         sh[g].opt.b_progress = 0;
+        sh[g].index = g;
     }
     {
         /* the reference fills several global tables the first time an encoder opens (x264_rdo_init, x264_init_vlc_tables,

@@ -46,13 +46,13 @@ typedef struct
     int active;                     /* a P-slice pass with GPU results is being replayed */
     int cur_mb, cur_pos;            /* replay cursor */
     int qp_loaded;
-    int elide, pass;                /* pass-2 elision on; pass of the slice being replayed */
+    int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
     int fenc_frame;                 /* h->fenc->i_frame currently on the GPU */
     /* reference slots: which frame each GPU slot holds */
     struct { x264_frame_t *fr; int i_frame, i_poc, age; } slot[PCAMV_MAX_REFS + 2];
     int n_slots, tick;
     /* accounting */
-    double t_gpu, t_total0;
+    double t_gpu, t_total0, t_open;
     long n_passes, n_replayed;
 } glue_t;
 
@@ -61,17 +61,37 @@ typedef struct
 static __thread glue_t g;
 
 /* shards of one process share the GPU through an encoder group (include/pcamv.h): one multi-context launch per step */
-static pcamv_group *g_group;
+/* PCAMV_GROUPS=G (default 2) splits the shards into G groups that rendezvous independently (shard i joins group i % G):
+ * while one group's frames are on the GPU the other groups' encoders do their host work, so neither side idles */
+#define PCAMV_MAX_GROUPS 8
+static pcamv_group *g_groups[PCAMV_MAX_GROUPS];
+static int g_n_groups;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static __thread pcamv_group *g_group;       /* this encoder thread's group, NULL outside --shards */
 static __thread int g_in_group;
 
 void pcamv_glue_set_shards( int n )
 {
-    if( n > 1 && pcamv_group_create( &g_group, n ) )
-    {
-        fprintf( stderr, "x264 [pcamv]: pcamv_group_create failed\n" );
-        exit( 3 );
-    }
+    const char *s = getenv( "PCAMV_GROUPS" );
+    int i, ng = s ? atoi( s ) : 2;
+    if( n <= 1 )
+        return;
+    if( ng < 1 ) ng = 1;
+    if( ng > PCAMV_MAX_GROUPS ) ng = PCAMV_MAX_GROUPS;
+    if( ng > n ) ng = n;
+    for( i = 0; i < ng; i++ )
+        if( pcamv_group_create( &g_groups[i], ( n - i + ng - 1 ) / ng ) )     /* members with index = i mod ng */
+        {
+            fprintf( stderr, "x264 [pcamv]: pcamv_group_create failed\n" );
+            exit( 3 );
+        }
+    g_n_groups = ng;
+}
+
+/* called first thing by a shard's thread */
+void pcamv_glue_set_shard_index( int i )
+{
+    g_group = g_n_groups ? g_groups[i % g_n_groups] : NULL;
 }
 
 /* called by a shard's thread when its encoder is gone, however it ended */
@@ -174,13 +194,15 @@ void pcamv_hook_open( x264_t *h )
     g_in_group = g_group != NULL;
     g.n_mb = h->sps->i_mb_width * h->sps->i_mb_height;
     g.n_slots = cfg.max_refs + 2;
-    g.mbs = pcamv_host_alloc( g.n_mb * sizeof(*g.mbs) );      /* page-locked: results arrive without a staging copy */
+    g.pinned = !((s = getenv( "PCAMV_NO_PINNED" )) && atoi( s ));
+    g.mbs = g.pinned ? pcamv_host_alloc( g.n_mb * sizeof(*g.mbs) ) : calloc( g.n_mb, sizeof(*g.mbs) );      /* page-locked: results arrive without a staging copy */
     g.log_stride = pcamv_log_stride( g.ctx );
-    g.log = pcamv_host_alloc( (size_t)g.n_mb * g.log_stride * sizeof(*g.log) );
+    g.log = g.pinned ? pcamv_host_alloc( (size_t)g.n_mb * g.log_stride * sizeof(*g.log) ) : calloc( (size_t)g.n_mb * g.log_stride, sizeof(*g.log) );
     g.pass1 = calloc( g.n_mb, sizeof(*g.pass1) );
     if( !g.mbs || !g.log || !g.pass1 )
         die_msg( "out of memory" );
     g.qp_loaded = -1;
+    g.t_open = now_s() - g.t_total0;
 }
 
 void pcamv_hook_close( x264_t *h )
@@ -192,14 +214,18 @@ void pcamv_hook_close( x264_t *h )
         FILE *f = fopen( s, "w" );
         if( f )
         {
-            fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_total\": %.6f}\n",
-                     g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, now_s() - g.t_total0 );
+            fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_open\": %.6f, \"t_total\": %.6f}\n",
+                     g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, g.t_open, now_s() - g.t_total0 );
             fclose( f );
         }
     }
     pcamv_glue_shard_done();
+    if( getenv( "PCAMV_VERBOSE" ) )
+        fprintf( stderr, "x264 [pcamv]: %ld P passes, open %.3f s, GPU calls %.3f s (waiting for the group included), encoder lifetime %.3f s\n",
+                 g.n_passes, g.t_open, g.t_gpu, now_s() - g.t_total0 );
     if( g.ctx ) pcamv_close( g.ctx );
-    pcamv_host_free( g.mbs ); pcamv_host_free( g.log ); free( g.pass1 );
+    if( g.pinned ) { pcamv_host_free( g.mbs ); pcamv_host_free( g.log ); } else { free( g.mbs ); free( g.log ); }
+    free( g.pass1 );
     memset( &g, 0, sizeof(g) );
 }
 

@@ -24,6 +24,9 @@ CASES = [
     ("cif_noembed", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5"),
     ("qcif_esa", 176, 144, 6, 9, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me esa --merange 16 --subme 5 --emrate 0.2"),
     ("720p_umh5", 1280, 720, 4, 5, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
+    # BASELINE.json config 2 / config 4 geometries (1080p is padded to 1088 lines; 4K = 240 x 135 macroblocks)
+    ("1080p_umh5", 1920, 1080, 3, 2, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
+    ("4k_hex5_ref2", 3840, 2160, 3, 4, 32, "x264_wide", "--qp 28 --ref 2 --keyint 250 --me hex --subme 5 --emrate 0.2"),
 ]
 
 

@@ -255,6 +255,7 @@ def main():
                     help="independent encoder contexts (GOP shards / streams) analysing concurrently on each GPU")
     ap.add_argument("--launch", choices=["batch", "streams"], default="batch",
                     help="batch: all contexts' frames in ONE wavefront launch (pcamv_analyse_p_batch); streams: one launch per context on its own CUDA stream")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="end-to-end arm: independent context sets whose copies and launches overlap")
     ap.add_argument("--rows-per-cta", type=int, default=4, help="wavefront layout used when --streams > 1 (pcamv_cfg.rows_per_cta)")
     ap.add_argument("--pass2-elide", action="store_true",
                     help="pcamv_cfg.pass2_elide: skip the pass-2 searches whose results the reference overwrites (not the default: "
@@ -394,17 +395,37 @@ def main():
             m1, l1 = c.analyse_p(1, refs, pocs, cur_poc, cost_table=True, out=outs1[i], **col)
             m2, l2 = c.analyse_p(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], out=outs2[i], **col)
         return m1, l1, m2, l2
-    def e2e_steps_batch(k):
+    # batch launches: the contexts are split into E2E_LANES independent sets, each driven by its own host thread through
+    # upload -> pcamv_analyse_p_batch(pass 1) -> pcamv_analyse_p_batch(pass 2) -> download, so that one set's PCIe copies
+    # overlap the other sets' kernels
+    lanes = max(1, min(args.e2e_lanes, S))
+    lane_sets = [list(range(i, S, lanes)) for i in range(lanes)]
+
+    def e2e_lane(ids, k):
+        cs = [ctxs[i] for i in ids]
         for _ in range(k):
-            def put(i):
-                ctxs[i].put_fenc(fy, fu, fv)
-                ctxs[i].put_ref(0, r["poc"], ry, ru, rv)
-            run_threads(put)
-            a1 = [(1, refs, pocs, cur_poc, dict(cost_table=True, **col)) for _ in ctxs]
-            o1 = pcamv.host.analyse_p_batch(ctxs, a1, outs=outs1)
+            for c in cs:
+                c.put_fenc(fy, fu, fv)
+                c.put_ref(0, r["poc"], ry, ru, rv)
+            a1 = [(1, refs, pocs, cur_poc, dict(cost_table=True, **col)) for _ in cs]
+            o1 = pcamv.host.analyse_p_batch(cs, a1, outs=[outs1[i] for i in ids])
             a2 = [(2, refs, pocs, cur_poc, dict(pass1=pass1, filp=e["filp"], stale_mv=o[0]["mv"][-1], **col)) for o in o1]
-            o2 = pcamv.host.analyse_p_batch(ctxs, a2, outs=outs2)
-        return [(o1[i][0], o1[i][1], o2[i][0], o2[i][1]) for i in range(S)]
+            o2 = pcamv.host.analyse_p_batch(cs, a2, outs=[outs2[i] for i in ids])
+        return o1, o2
+
+    def e2e_steps_batch(k):
+        res = [None] * lanes
+        def wrap(j):
+            res[j] = e2e_lane(lane_sets[j], k)
+        th = [threading.Thread(target=wrap, args=(j,)) for j in range(lanes)]
+        for x_ in th: x_.start()
+        for x_ in th: x_.join()
+        out = [None] * S
+        for j, ids in enumerate(lane_sets):
+            o1, o2 = res[j]
+            for n_, i in enumerate(ids):
+                out[i] = (o1[n_][0], o1[n_][1], o2[n_][0], o2[n_][1])
+        return out
     e2e_run = e2e_steps_batch if batch else (lambda k: run_threads(lambda i: e2e_steps(i, k)))
     e2e_run(args.warmup)
     barrier()

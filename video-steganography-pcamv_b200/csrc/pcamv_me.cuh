@@ -175,39 +175,50 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
     const int c = grp == 0 ? c0 : grp == 1 ? c1 : grp == 2 ? c2 : c3;
     const int qx = pk_x(c), qy = pk_y(c);
     int acc = 0;
+    // the block descriptor lives in memory the compiler cannot prove unaliased: read each field once
+    const uint8_t *const fenc = b.fenc;
+    const int stride = b.stride, bw = b.bw, bh = b.bh;
     const uint8_t *s1, *s2;
-    qpel_sources(b, qx, qy, s1, s2);
+    {
+        const int fx = qx & 3, fy = qy & 3;
+        const int h0 = (fy == 2 ? ((fx == 0) ? 2 : 3) : ((fx == 0) ? 0 : 1));
+        const int h1 = (fy == 0) ? 0 : ((fx == 2) ? 3 : 2);
+        const int off = (qy >> 2) * stride + (qx >> 2);
+        s1 = b.ref[h0] + off + (fy == 3 ? stride : 0);
+        s2 = (((fy << 2) + fx) & 5) ? b.ref[h1] + off + (fx == 3 ? 1 : 0) : s1;
+    }
     if (kind == COST_SAD_FPEL || kind == COST_SAD)
     {
-        const int w4 = b.bw >> 2;
+        const int w4 = bw >> 2;
 #pragma unroll 1
-        for (int r = 0; r < PCAMV_ROWS && lpg * r < b.bh; r++)
+        for (int r = 0; r < PCAMV_ROWS && lpg * r < bh; r++)
         {
             const int y = sub + lpg * r;
-            const int yy = imin(y, b.bh - 1);
+            const int yy = imin(y, bh - 1);
             uint32_t p[4];
-            ld_row16(s1 + yy * b.stride, p);
+            ld_row16(s1 + yy * stride, p);
             if (kind == COST_SAD)
             {
                 uint32_t q[4];
-                ld_row16(s2 + yy * b.stride, q);
+                ld_row16(s2 + yy * stride, q);
 #pragma unroll
                 for (int j = 0; j < 4; j++) p[j] = avg4(p[j], q[j]);
             }
             int s = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                s += j < w4 ? sad4(ld4a(b.fenc + yy * 16 + 4 * j), p[j]) : 0;
-            acc += y < b.bh ? s : 0;
+                s += j < w4 ? sad4(ld4a(fenc + yy * 16 + 4 * j), p[j]) : 0;
+            acc += y < bh ? s : 0;
         }
     }
     else
     {
         // 4x4 units: nl luma units, then nc units of U, then nc units of V; one Hadamard per unit
-        const int llx = b.bw == 16 ? 2 : b.bw == 8 ? 1 : 0;         // log2(luma units per row)
-        const int nl = (b.bh >> 2) << llx;
-        const int lcx = b.bw == 16 ? 1 : 0;                        // log2(chroma units per row)
-        const int nc = kind == COST_SATD_CHROMA ? (b.bh >> 3) << lcx : 0;
+        const int llx = bw == 16 ? 2 : bw == 8 ? 1 : 0;         // log2(luma units per row)
+        const int nl = (bh >> 2) << llx;
+        const int lcx = bw == 16 ? 1 : 0;                        // log2(chroma units per row)
+        const int nc = kind == COST_SATD_CHROMA ? (bh >> 3) << lcx : 0;
+        const int stride_c = b.stride_c;
         const int total = nl + 2 * nc;
         const int dx = qx & 7, dy = qy & 7;
         const int cA = (8 - dx) * (8 - dy), cB = dx * (8 - dy), cC = (8 - dx) * dy, cD = dx * dy;
@@ -223,8 +234,8 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
 #pragma unroll
                 for (int r = 0; r < 4; r++)
                 {
-                    f[r] = ld4a(b.fenc + (y + r) * 16 + x);
-                    a[r] = pred4(s1, s2, b.stride, x, y + r);
+                    f[r] = ld4a(fenc + (y + r) * 16 + x);
+                    a[r] = pred4(s1, s2, stride, x, y + r);
                 }
             }
             else
@@ -234,14 +245,14 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
                 v -= pl ? nc : 0;
                 const int x = (v & ((1 << lcx) - 1)) << 2, y = (v >> lcx) << 2;
                 const uint8_t *fe = (pl ? b.fenc_v : b.fenc_u) + y * 8 + x;
-                const uint8_t *s = (pl ? b.ref_v : b.ref_u) + ((qy >> 3) + y) * b.stride_c + (qx >> 3) + x;
+                const uint8_t *s = (pl ? b.ref_v : b.ref_u) + ((qy >> 3) + y) * stride_c + (qx >> 3) + x;
                 uint32_t t0, t1;
                 ld4x2(s, t0, t1);
 #pragma unroll
                 for (int r = 0; r < 4; r++)
                 {
                     uint32_t u0, u1;
-                    ld4x2(s + (r + 1) * b.stride_c, u0, u1);
+                    ld4x2(s + (r + 1) * stride_c, u0, u1);
                     f[r] = ld4a(fe + r * 8);
                     a[r] = bilin4(t0, t1, u0, u1, cA, cB, cC, cD);
                     t0 = u0; t1 = u1;
@@ -252,7 +263,13 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
         }
     }
 #if !defined(PCAMV_EMU)
-    acc = wide ? team_sum(acc) : grp_sum(acc);
+    {
+        // group totals, then (always, branch-free) the team total for the single-candidate layout
+        acc = grp_sum(acc);
+        int all = acc + __shfl_xor_sync(0xffffffffu, acc, 8);
+        all += __shfl_xor_sync(0xffffffffu, all, 16);
+        acc = wide ? all : acc;
+    }
 #endif
     return grp < n ? acc + b.cost_mvx[qx] + b.cost_mvy[qy] : PCAMV_COST_MAX;
 }

@@ -338,30 +338,75 @@ PCAMV_DEV bool fpel_in_range(const MeEnv &e, int mx, int my)
     return mx >= e.mv_min_fpel[0] && mx <= e.mv_max_fpel[0] && my >= e.mv_min_fpel[1] && my <= e.mv_max_fpel[1];
 }
 
+// ---- one candidate per LANE --------------------------------------------------------------------------
+// Candidate sets that do not depend on intermediate results (the rings of the UMH hexagon grid, the rows of the exhaustive
+// search) are costed 32 at a time: every lane computes the whole SAD of its own full-pel position, so there is no
+// cross-lane reduction per candidate, and the 32 results are folded in evaluation order (first minimum wins, strict <
+// against the running best — the same outcome as the reference's sequential COST_MV loop).
+#if defined(PCAMV_EMU)
+  #define PCAMV_WIDE 1
+#else
+  #define PCAMV_WIDE 32
+#endif
+
+// SAD + MV cost of the block at full-pel (mx, my), computed by the calling lane alone
+PCAMV_FN int lane_sad(const MeBlock &b, int mx, int my)
+{
+    const uint8_t *const fenc = b.fenc;
+    const int stride = b.stride, bh = b.bh, w4 = b.bw >> 2;
+    const uint8_t *s = b.ref[0] + my * stride + mx;
+    int acc = 0;
+#pragma unroll 1
+    for (int y = 0; y < bh; y++)
+    {
+        uint32_t p[4];
+        ld_row16(s + y * stride, p);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            acc += j < w4 ? sad4(ld4a(fenc + y * 16 + 4 * j), p[j]) : 0;
+    }
+    return acc + b.cost_mvx[mx << 2] + b.cost_mvy[my << 2];
+}
+
+// fold the lanes' (cost, mv) of candidates k0 + lane (cost = COST_MAX for lanes without a candidate) into the best
+PCAMV_FN best_t fold_wide(best_t best, int cost, int mv)
+{
+#if !defined(PCAMV_EMU)
+    // first minimum in lane order: minimise (cost, lane)
+    unsigned long long key = ((unsigned long long)(uint32_t)cost << 32) | (uint32_t)team_lane();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
+        key = o < key ? o : key;
+    }
+    cost = (int)(key >> 32);
+    mv = __shfl_sync(0xffffffffu, mv, (int)(key & 31));
+#endif
+    return cost < best_cost(best) ? best_make(cost, mv) : best;
+}
+
 // symmetric cross around (ox,oy)  (reference encoder/me.c:131-155)
 PCAMV_FN best_t search_cross(const MeEnv &e, const MeBlock &b, best_t best, int ox, int oy, int start, int x_max, int y_max)
 {
-    int i = start;
-    if (x_max <= imin(e.mv_max_fpel[0] - ox, ox - e.mv_min_fpel[0]))
+    // evaluation order of the reference: (+i,0) (-i,0) for i = start, start+2, .. < x_max, then (0,+i) (0,-i) for i < y_max;
+    // a point outside the MV range is skipped (the reference's unchecked 4-at-a-time loops only run when none can be).
+    // The centre is fixed, so the points are independent: one per lane.
+    const int nx = x_max > start ? 2 * ((x_max - start + 1) >> 1) : 0;
+    const int ny = y_max > start ? 2 * ((y_max - start + 1) >> 1) : 0;
 #pragma unroll 1
-        for (; i < x_max - 2; i += 4)
-            best = try4(b, best, 4, ox, oy, PCAMV_OFF4(i, -i, i + 2, -i - 2), 0);
-#pragma unroll 1
-    for (; i < x_max; i += 2)
+    for (int k0 = 0; k0 < nx + ny; k0 += PCAMV_WIDE)
     {
-        if (ox + i <= e.mv_max_fpel[0]) best = try1(b, best, ox + i, oy);
-        if (ox - i >= e.mv_min_fpel[0]) best = try1(b, best, ox - i, oy);
-    }
-    i = start;
-    if (y_max <= imin(e.mv_max_fpel[1] - oy, oy - e.mv_min_fpel[1]))
-#pragma unroll 1
-        for (; i < y_max - 2; i += 4)
-            best = try4(b, best, 4, ox, oy, 0, PCAMV_OFF4(i, -i, i + 2, -i - 2));
-#pragma unroll 1
-    for (; i < y_max; i += 2)
-    {
-        if (oy + i <= e.mv_max_fpel[1]) best = try1(b, best, ox, oy + i);
-        if (oy - i >= e.mv_min_fpel[1]) best = try1(b, best, ox, oy - i);
+        const int k = k0 + team_lane();
+        const int vert = k >= nx;
+        const int kk = vert ? k - nx : k;
+        const int i = start + 2 * (kk >> 1);
+        const int d = (kk & 1) ? -i : i;
+        const int mx = vert ? ox : ox + d, my = vert ? oy + d : oy;
+        const bool valid = k < nx + ny && (vert ? (my <= e.mv_max_fpel[1] && my >= e.mv_min_fpel[1])
+                                                : (mx <= e.mv_max_fpel[0] && mx >= e.mv_min_fpel[0]));
+        const int cost = valid ? lane_sad(b, mx, my) : PCAMV_COST_MAX;
+        best = fold_wide(best, cost, pk(mx, my));
     }
     return best;
 }
@@ -504,37 +549,28 @@ PCAMV_FN best_t search_umh(const MeEnv &e, const MeBlock &b, best_t best, int pm
     best = search_cross(e, b, best, ox, oy, cross_start, me_range, me_range / 2);
     best = try4(b, best, 4, ox, oy, PCAMV_OFF4(-2, -2, 2, 2), PCAMV_OFF4(-2, 2, -2, 2));
 
-    // 16-point hexagon grid, radius 4*i; rows of the table = four consecutive points
+    // 16-point hexagon grid, radius 4*i for i = 1 .. me_range/4 (at least one ring): point k = 16*(i-1) + j, one per lane
     ox = pk_x(best_mv(best)); oy = pk_y(best_mv(best));
-    int i = 1;
-    do
     {
-        const bool near_edge = 4 * i > imin(imin(e.mv_max_fpel[0] - ox, ox - e.mv_min_fpel[0]),
-                                            imin(e.mv_max_fpel[1] - oy, oy - e.mv_min_fpel[1]));
+        const int rings = imax(me_range / 4, 1);
+        const int n_pts = 16 * rings;
 #pragma unroll 1
-        for (int j = 0; j < 4; j++)
+        for (int k0 = 0; k0 < n_pts; k0 += PCAMV_WIDE)
         {
-            // { -4,-4,-4,-4 | -4,4,4,4 | 4,4,2,0 | -2,-2,0,2 } and { 2,1,0,-1 | -2,-2,-1,0 | 1,2,3,4 | 3,-3,-4,-3 }
-            const uint32_t gx = j == 0 ? PCAMV_OFF4(-4, -4, -4, -4) : j == 1 ? PCAMV_OFF4(-4, 4, 4, 4)
-                              : j == 2 ? PCAMV_OFF4(4, 4, 2, 0) : PCAMV_OFF4(-2, -2, 0, 2);
-            const uint32_t gy = j == 0 ? PCAMV_OFF4(2, 1, 0, -1) : j == 1 ? PCAMV_OFF4(-2, -2, -1, 0)
-                              : j == 2 ? PCAMV_OFF4(1, 2, 3, 4) : PCAMV_OFF4(3, -3, -4, -3);
-            const uint32_t dxs = PCAMV_OFF4(off_at(gx, 0) * i, off_at(gx, 1) * i, off_at(gx, 2) * i, off_at(gx, 3) * i);
-            const uint32_t dys = PCAMV_OFF4(off_at(gy, 0) * i, off_at(gy, 1) * i, off_at(gy, 2) * i, off_at(gy, 3) * i);
-            if (!near_edge)
-                best = try4(b, best, 4, ox, oy, dxs, dys);
-            else
-            {
-#pragma unroll 1
-                for (int k = 0; k < 4; k++)
-                {
-                    const int mx = ox + off_at(dxs, k), my = oy + off_at(dys, k);
-                    if (fpel_in_range(e, mx, my))
-                        best = try1(b, best, mx, my);
-                }
-            }
+            const int k = k0 + team_lane();
+            const int i = (k >> 4) + 1, j = k & 15;
+            // { -4,-4,-4,-4,-4, 4,4,4,4,4, 2,0,-2,-2,0,2 } and { 2,1,0,-1,-2, -2,-1,0,1,2, 3,4,3,-3,-4,-3 } as signed nibbles
+            const int gx = (int)(((long long)(0x20EE0244444CCCCCull << (60 - 4 * j))) >> 60);
+            const int gy = (int)(((long long)(0xDCD343210FEEF012ull << (60 - 4 * j))) >> 60);
+            const int mx = ox + gx * i, my = oy + gy * i;
+            // the reference tests every point against the MV range only when the ring can leave it (me.c:453-470)
+            const bool near_edge = 4 * i > imin(imin(e.mv_max_fpel[0] - ox, ox - e.mv_min_fpel[0]),
+                                                imin(e.mv_max_fpel[1] - oy, oy - e.mv_min_fpel[1]));
+            const bool valid = k < n_pts && (!near_edge || fpel_in_range(e, mx, my));
+            const int cost = valid ? lane_sad(b, mx, my) : PCAMV_COST_MAX;
+            best = fold_wide(best, cost, pk(mx, my));
         }
-    } while (++i <= me_range / 4);
+    }
     if (pk_y(best_mv(best)) <= e.mv_max_fpel[1])
     {
         *run_hex = 1; *hex_range = me_range;
@@ -660,8 +696,13 @@ PCAMV_FN best_t search_esa(const MeEnv &e, const MeBlock &b, best_t best)
     const int width = (max_x - min_x + 3) & ~3;
 #pragma unroll 1
     for (int my = min_y; my <= max_y; my++)
-        for (int x = 0; x < width; x += 4)
-            best = try4(b, best, 4, min_x + x, my, PCAMV_OFF4(0, 1, 2, 3), 0);
+#pragma unroll 1
+        for (int x0 = 0; x0 < width; x0 += PCAMV_WIDE)
+        {
+            const int x = x0 + team_lane();
+            const int cost = x < width ? lane_sad(b, min_x + x, my) : PCAMV_COST_MAX;
+            best = fold_wide(best, cost, pk(min_x + x, my));
+        }
     return best;
 }
 

@@ -356,7 +356,8 @@ PCAMV_FN int lane_sad(const MeBlock &b, int mx, int my)
     const int stride = b.stride, bh = b.bh, w4 = b.bw >> 2;
     const uint8_t *s = b.ref[0] + my * stride + mx;
     int acc = 0;
-#pragma unroll 1
+    // four rows in flight: a lone warp has nothing else to hide the load latency with
+#pragma unroll 4
     for (int y = 0; y < bh; y++)
     {
         uint32_t p[4];

@@ -38,7 +38,7 @@ struct pcamv_ctx
     pcamv::MbResult *d_mb_results = nullptr;   // [n_mb]
     pcamv::BatchItem *d_batch = nullptr, *h_batch = nullptr; int batch_items_cap = 0;   // leader of a multi-context launch
     int *d_batch_claim = nullptr;
-    int batch_max_ctas = 0;                    // 0 = one CTA per row group of every frame
+    int batch_max_ctas = 0, batch_claim_cap = 0;   // persistent grid size of multi-context launches (0 = not yet computed)
     unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
     bool trace_on = false;
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter

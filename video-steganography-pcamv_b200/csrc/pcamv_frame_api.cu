@@ -294,7 +294,20 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
         CK(cudaMallocHost(&ctx->h_batch, n * sizeof(BatchItem)));
         ctx->batch_items_cap = n;
     }
-    if (!ctx->d_batch_claim) CK(cudaMalloc(&ctx->d_batch_claim, sizeof(int)));
+    if (ctx->batch_claim_cap < n)
+    {
+        cudaFree(ctx->d_batch_claim); ctx->d_batch_claim = nullptr;
+        CK(cudaMalloc(&ctx->d_batch_claim, n * sizeof(int)));
+        ctx->batch_claim_cap = n;
+    }
+    if (!ctx->batch_max_ctas)
+    {
+        // persistent grid: what can be resident at once (the kernel's launch bounds ask for 24 warps per SM)
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, ctx->cfg.device));
+        const int w = ctx->cfg.rows_per_cta >= 4 ? 4 : ctx->cfg.rows_per_cta >= 2 ? 2 : 1;
+        ctx->batch_max_ctas = prop.multiProcessorCount * (24 / w);
+    }
     int cost_table = pass == 1;
     for (int i = 0; i < n; i++)
     {
@@ -307,7 +320,7 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
         CK(cudaMemsetAsync(c->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
     }
     CK(cudaMemcpyAsync(ctx->d_batch, ctx->h_batch, n * sizeof(BatchItem), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_batch_claim, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_batch_claim, 0, n * sizeof(int), ctx->stream));
     if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
     launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta, ctx->batch_max_ctas, ctx->stream);
     ctx->launches += 1;

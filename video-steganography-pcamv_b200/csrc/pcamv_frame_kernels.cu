@@ -114,35 +114,68 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
     }
 }
 
-// Several frames (independent encoder contexts: GOP shards / streams of equal geometry) in ONE launch: the claim
-// counter walks (row group, frame) pairs frame-fastest, so all frames advance together and every awaited row has a
-// smaller claim index than the waiting one — the same no-deadlock argument as for a single frame, for any grid size.
-// The grid is sized to what is resident at once; CTAs keep claiming until the work is gone (persistent).
+// Several frames (independent encoder contexts: GOP shards / streams of equal geometry) in ONE launch.  Work unit = a
+// group of AP_WARPS consecutive rows of one frame.  A persistent CTA looking for work scans the frames (each thread
+// looks at one, starting from a CTA-specific offset) for one whose NEXT group is ready — it is the first group, or the
+// last row of the previous group is already a few macroblocks in — and claims it with a compare-and-swap on that
+// frame's counter.  So a claimed group starts working at once instead of spinning through the wavefront's ramp (with
+// a static assignment about half of the resident warps were waiting at any time), the resident warps are spread
+// over as many frames as it takes to keep them busy, and every awaited row belongs to a group that was claimed before
+// the waiter's — the no-deadlock argument of the single-frame kernel, for any grid size.
 #ifndef PCAMV_BATCH_MIN_CTAS
 #define PCAMV_BATCH_MIN_CTAS 6      // CTAs of 4 warps per SM the register budget must allow (resident warps are what hides latency here)
 #endif
+#define PCAMV_GROUP_READY 4      // macroblocks the previous group's last row must have finished before the next group is handed out
 template <int AP_WARPS>
-__global__ void __launch_bounds__(AP_WARPS * 32, PCAMV_BATCH_MIN_CTAS * 4 / AP_WARPS) k_analyse_p_batch(const BatchItem *__restrict__ items, int n_items, int *row_claim)
+__global__ void __launch_bounds__(AP_WARPS * 32, PCAMV_BATCH_MIN_CTAS * 4 / AP_WARPS) k_analyse_p_batch(const BatchItem *__restrict__ items, int n_items, int *next_group)
 {
     __shared__ MbWork s_work[AP_WARPS];
     __shared__ __align__(16) unsigned char s_ctx[AP_WARPS][sizeof(MbCtx)];
-    __shared__ int s_claim;
+    __shared__ int s_pick, s_left, s_frame, s_grp;
     const int warp = threadIdx.x >> 5;
     MbWork &work = s_work[warp];
     const int mb_h = items[0].fc.mb_h;
+    const int n_groups = (mb_h + AP_WARPS - 1) / AP_WARPS;
+    unsigned rot = blockIdx.x * 37u;
     for (;;)
     {
         __syncthreads();
-        if (threadIdx.x == 0)
-            s_claim = atomicAdd(row_claim, 1);
+        if (threadIdx.x == 0) { s_pick = 0x7fffffff; s_left = 0; s_frame = -1; }
         __syncthreads();
-        const int group = s_claim / n_items, frame = s_claim - group * n_items;
-        if (group * AP_WARPS >= mb_h)
-            return;
-        const int row = group * AP_WARPS + warp;
+        // every thread inspects frames rot + t, rot + t + blockDim, ...: lowest ready candidate wins
+        int mine = 0x7fffffff, left = 0;
+        for (int t = threadIdx.x; t < n_items; t += blockDim.x)
+        {
+            const int f = (int)((rot + (unsigned)t) % (unsigned)n_items);
+            const int g = ld_acquire(next_group + f);
+            if (g >= n_groups) continue;
+            left = 1;
+            if (mine == 0x7fffffff &&
+                (g == 0 || ld_acquire(items[f].fp.row_progress + g * AP_WARPS - 1) >= min(PCAMV_GROUP_READY, items[f].fc.mb_w)))
+                mine = t;
+        }
+        if (left) s_left = 1;                       // (benign race: everybody writes 1)
+        if (mine != 0x7fffffff) atomicMin(&s_pick, mine);
+        __syncthreads();
+        if (!s_left)
+            return;                                 // every group of every frame has been handed out
+        if (threadIdx.x == 0 && s_pick != 0x7fffffff)
+        {
+            const int f = (int)((rot + (unsigned)s_pick) % (unsigned)n_items);
+            const int g = ld_acquire(next_group + f);
+            if (g < n_groups && atomicCAS(next_group + f, g, g + 1) == g) { s_frame = f; s_grp = g; }
+        }
+        __syncthreads();
+        rot += 1u;
+        if (s_frame < 0)
+        {
+            if (s_pick == 0x7fffffff) __nanosleep(2000);      // nothing ready anywhere: the running groups will get there
+            continue;
+        }
+        const int row = s_grp * AP_WARPS + warp;
         if (row < mb_h)
         {
-            const BatchItem &it = items[frame];
+            const BatchItem &it = items[s_frame];
             MbCtx &c = *new (s_ctx[warp]) MbCtx(it.fc, it.fp, work);
             analyse_row(it.fc, it.fp, c, work, row);
         }
@@ -161,6 +194,7 @@ void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_cla
         k_analyse_p<1><<<n_rows, 32, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
 }
 
+// next_group: n_items counters, zeroed by the caller
 void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, void *stream)
 {
     const int w = rows_per_cta >= 4 ? 4 : rows_per_cta >= 2 ? 2 : 1;

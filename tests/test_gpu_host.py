@@ -24,6 +24,15 @@ CASES = [
     ("cif_noembed", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5"),
     ("qcif_esa", 176, 144, 6, 9, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me esa --merange 16 --subme 5 --emrate 0.2"),
     ("720p_umh5", 1280, 720, 4, 5, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
+    # option coverage (the reference Makefile's OPT0..OPT7 flag sets, Makefile:108-115, restricted to the supported path)
+    ("cif_nocabac", 352, 288, 8, 1, 16, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --no-cabac --emrate 0.2"),
+    ("cif_nofastpskip_ref4", 352, 288, 9, 1, 8, "x264_wide", "--qp 28 --ref 4 --keyint 250 --me umh --subme 4 --no-fast-pskip --emrate 0.2"),
+    ("cif_subme1_dia", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me dia --subme 1 --emrate 0.2"),
+    ("cif_subme3_merange8", 352, 288, 8, 1, 32, "x264_wide", "--qp 22 --ref 2 --keyint 250 --me hex --merange 8 --subme 3 --emrate 0.5"),
+    ("cif_fixed_bits", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --emrate 40"),
+    ("cif_p16x16_only", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --partitions none --emrate 0.2"),
+    ("odd_size_umh", 360, 270, 6, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
+    ("cif_nodecimate_qp36", 352, 288, 8, 1, 8, "x264_wide", "--qp 36 --ref 1 --keyint 250 --me hex --subme 5 --no-dct-decimate --emrate 0.2"),
     # BASELINE.json config 2 / config 4 geometries (1080p is padded to 1088 lines; 4K = 240 x 135 macroblocks)
     ("1080p_umh5", 1920, 1080, 3, 2, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
     ("4k_hex5_ref2", 3840, 2160, 3, 4, 32, "x264_wide", "--qp 28 --ref 2 --keyint 250 --me hex --subme 5 --emrate 0.2"),

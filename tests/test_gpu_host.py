@@ -121,3 +121,21 @@ def test_sharded_encode_equals_per_gop_reference_runs(pcamv, cuda_lib, tmp_path)
     assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")
     got = open(out, "rb").read()
     assert len(got) == len(want) and got == want
+
+
+def test_static_clip_no_carriers(pcamv, cuda_lib, tmp_path):
+    """Edge case: identical frames -> (almost) every macroblock is P_SKIP, frames carry few or no motion vectors, and the
+    embed stage runs through its degenerate paths (an = 0, embed.h:347; stc_embed's return value is ignored,
+    encoder/encoder.c:1843).  The GPU-backed encoder must still be byte-identical."""
+    w, h, n = 352, 288, 6
+    args = "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --emrate 0.2"
+    workdir = str(tmp_path)
+    one = refrun.synth_clip(pcamv, w, h, 1, config=1, stream=7, workdir=workdir)
+    clip = os.path.join(workdir, "static.yuv")
+    with open(clip, "wb") as f:
+        f.write(open(one, "rb").read() * n)
+    ref_out, _ = refrun.run_ref(clip, w, h, args.split(), binary="x264_wide", out=os.path.join(workdir, "ref.264"))
+    out = os.path.join(workdir, "gpu.264")
+    p = subprocess.run([HOST] + args.split() + ["-o", out, clip, "%dx%d" % (w, h)], capture_output=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")
+    assert md5(out) == md5(ref_out)

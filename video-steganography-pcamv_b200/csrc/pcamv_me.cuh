@@ -633,28 +633,20 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
     {
         const int odir = bdir;
         const int omx = bmx, omy = bmy;
-        // direction d (0 up, 1 down, 2 left, 3 right) is skipped when it would step straight back (d^1 == odir),
-        // except in the final refine
-        int c[4], dirs[4], n = 0;
+        // direction d (0 up, 1 down, 2 left, 3 right) is skipped when it would step straight back (d^1 == odir), except in
+        // the final refine.  All four are costed (four lane groups are there anyway); the skipped one is ignored in the fold,
+        // which is what not evaluating it amounts to.
+        eval4(b, mbcmp, 4, pk(omx, omy - 1), pk(omx, omy + 1), pk(omx - 1, omy), pk(omx + 1, omy), costs);
 #pragma unroll
         for (int d = 0; d < 4; d++)
         {
-            const int ddx = d == 2 ? -1 : d == 3 ? 1 : 0, ddy = d == 0 ? -1 : d == 1 ? 1 : 0;
             const bool take = b_refine_qpel || (d ^ 1) != odir;
-            // compact the taken directions to the front without local-memory indexing
-            if (take)
+            if (take && costs[d] < bcost)
             {
-                const int v = pk(omx + ddx, omy + ddy);
-                if (n == 0) { c[0] = v; dirs[0] = d; } else if (n == 1) { c[1] = v; dirs[1] = d; }
-                else if (n == 2) { c[2] = v; dirs[2] = d; } else { c[3] = v; dirs[3] = d; }
-                n++;
+                bcost = costs[d]; bdir = d;
+                bmx = omx + (d == 2 ? -1 : d == 3 ? 1 : 0); bmy = omy + (d == 0 ? -1 : d == 1 ? 1 : 0);
             }
         }
-        if (n < 4) { c[3] = c[0]; dirs[3] = dirs[0]; }
-        eval4(b, mbcmp, n, c[0], c[1], c[2], c[3], costs);
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (k < n && costs[k] < bcost) { bcost = costs[k]; bmx = pk_x(c[k]); bmy = pk_y(c[k]); bdir = dirs[k]; }
         if (bmx == omx && bmy == omy)
             break;
     }

@@ -176,9 +176,12 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
     const int qx = pk_x(c), qy = pk_y(c);
     int acc = 0;
     // the block descriptor lives in memory the compiler cannot prove unaliased: read each field once
-    const uint8_t *const fenc = b.fenc;
+    const smem_ptr fenc = to_smem(b.fenc);
     const int stride = b.stride, bw = b.bw, bh = b.bh;
     const uint8_t *s1, *s2;
+    if (kind == COST_SAD_FPEL)
+        s1 = s2 = b.ref[0] + (qy >> 2) * stride + (qx >> 2);          // integer position: the plane itself
+    else
     {
         const int fx = qx & 3, fy = qy & 3;
         const int h0 = (fy == 2 ? ((fx == 0) ? 2 : 3) : ((fx == 0) ? 0 : 1));
@@ -207,7 +210,7 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
             int s = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                s += j < w4 ? sad4(ld4a(fenc + yy * 16 + 4 * j), p[j]) : 0;
+                s += j < w4 ? sad4(ld4s(fenc + yy * 16 + 4 * j), p[j]) : 0;
             acc += y < bh ? s : 0;
         }
     }
@@ -234,7 +237,7 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
 #pragma unroll
                 for (int r = 0; r < 4; r++)
                 {
-                    f[r] = ld4a(fenc + (y + r) * 16 + x);
+                    f[r] = ld4s(fenc + (y + r) * 16 + x);
                     a[r] = pred4(s1, s2, stride, x, y + r);
                 }
             }
@@ -244,7 +247,7 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
                 const int pl = v >= nc;
                 v -= pl ? nc : 0;
                 const int x = (v & ((1 << lcx) - 1)) << 2, y = (v >> lcx) << 2;
-                const uint8_t *fe = (pl ? b.fenc_v : b.fenc_u) + y * 8 + x;
+                const smem_ptr fe = to_smem(pl ? b.fenc_v : b.fenc_u) + y * 8 + x;
                 const uint8_t *s = (pl ? b.ref_v : b.ref_u) + ((qy >> 3) + y) * stride_c + (qx >> 3) + x;
                 uint32_t t0, t1;
                 ld4x2(s, t0, t1);
@@ -253,7 +256,7 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
                 {
                     uint32_t u0, u1;
                     ld4x2(s + (r + 1) * stride_c, u0, u1);
-                    f[r] = ld4a(fe + r * 8);
+                    f[r] = ld4s(fe + r * 8);
                     a[r] = bilin4(t0, t1, u0, u1, cA, cB, cC, cD);
                     t0 = u0; t1 = u1;
                 }
@@ -353,7 +356,7 @@ PCAMV_DEV bool fpel_in_range(const MeEnv &e, int mx, int my)
 // SAD + MV cost of the block at full-pel (mx, my), computed by the calling lane alone
 PCAMV_FN int lane_sad(const MeBlock &b, int mx, int my)
 {
-    const uint8_t *const fenc = b.fenc;
+    const smem_ptr fenc = to_smem(b.fenc);
     const int stride = b.stride, bh = b.bh, w4 = b.bw >> 2;
     const uint8_t *s = b.ref[0] + my * stride + mx;
     int acc = 0;
@@ -365,7 +368,7 @@ PCAMV_FN int lane_sad(const MeBlock &b, int mx, int my)
         ld_row16(s + y * stride, p);
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            acc += j < w4 ? sad4(ld4a(fenc + y * 16 + 4 * j), p[j]) : 0;
+            acc += j < w4 ? sad4(ld4s(fenc + y * 16 + 4 * j), p[j]) : 0;
     }
     return acc + b.cost_mvx[mx << 2] + b.cost_mvy[my << 2];
 }

@@ -115,6 +115,23 @@ PCAMV_DEV uint32_t ld4a(const uint8_t *p)
     return *(const uint32_t *)p;
 #endif
 }
+// The block being matched (source pixels, or the reconstruction in the cost table) always sits in shared memory on the
+// GPU.  Inside the out-of-line evaluators — where that memory is read-only — it is addressed as such: LDS needs no memory
+// descriptor, while every generic / global load in an out-of-line function costs two extra R2UR instructions.
+#if defined(PCAMV_EMU)
+typedef const uint8_t *smem_ptr;
+PCAMV_DEV smem_ptr to_smem(const uint8_t *p) { return p; }
+PCAMV_DEV uint32_t ld4s(smem_ptr p) { uint32_t v; memcpy(&v, p, 4); return v; }
+#else
+typedef unsigned smem_ptr;
+PCAMV_DEV smem_ptr to_smem(const uint8_t *p) { return (unsigned)__cvta_generic_to_shared(p); }
+PCAMV_DEV uint32_t ld4s(smem_ptr p)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p));
+    return v;
+}
+#endif
 // per-byte (a+b+1)>>1 : the quarter-pel average of pixel_avg (reference common/mc.c:34-50)
 PCAMV_DEV uint32_t avg4(uint32_t a, uint32_t b)
 {

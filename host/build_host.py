@@ -46,6 +46,38 @@ void pcamv_glue_set_shards( int n );
 void pcamv_glue_shard_done( void );
 void pcamv_glue_set_shard_index( int i );
 typedef struct { x264_param_t param; cli_opt_t opt; int ret, index; char out[1024]; } pcamv_shard_t;
+/* `x264_pcamv --extract STEGO -o MESSAGE`: STEGO holds, per embedded frame in coding order, int32 frame, length, an and the
+ * `length` stego LSBs (what the encoder writes with PCAMV_STEGO=<file>; a decoder-side MV parser would deliver the same
+ * vector); MESSAGE receives int32 frame, an and the `an` recovered payload bits.  Frames that carried nothing (an <= 0) are
+ * passed through with an = 0. */
+int pcamv_stc_extract( const uint8_t *stego, int n, uint8_t *message, int an, int matrixheight );
+static int pcamv_extract_main( int argc, char **argv )
+{
+    const char *in = argv[2], *out = NULL;
+    FILE *fi, *fo;
+    int32_t hd[3];
+    int i, frames = 0, bits = 0;
+    for( i = 3; i < argc - 1; i++ )
+        if( !strcmp( argv[i], "-o" ) || !strcmp( argv[i], "--output" ) ) out = argv[i + 1];
+    if( !out ) { fprintf( stderr, "x264 [error]: --extract needs -o\n" ); return -1; }
+    fi = fopen( in, "rb" ); fo = fopen( out, "wb" );
+    if( !fi || !fo ) { fprintf( stderr, "x264 [error]: cannot open %s / %s\n", in, out ); return -1; }
+    while( fread( hd, 4, 3, fi ) == 3 )
+    {
+        const int length = hd[1], an = hd[2] > 0 ? hd[2] : 0;
+        uint8_t *stego = malloc( length > 0 ? length : 1 ), *msg = malloc( an + 1 );
+        int32_t oh[2] = { hd[0], an };
+        if( length < 0 || (int)fread( stego, 1, length, fi ) != length ) { fprintf( stderr, "x264 [error]: truncated stego file\n" ); return -1; }
+        if( an > 0 && pcamv_stc_extract( stego, length, msg, an, 10 ) < 0 ) { fprintf( stderr, "x264 [error]: frame %d: cannot extract %d bits from %d\n", hd[0], an, length ); return -1; }
+        fwrite( oh, 4, 2, fo );
+        fwrite( msg, 1, an, fo );
+        free( stego ); free( msg );
+        frames++; bits += an;
+    }
+    fclose( fi ); fclose( fo );
+    fprintf( stderr, "x264 [info]: extracted %d payload bits from %d frames\n", bits, frames );
+    return 0;
+}
 static void *pcamv_shard_thread( void *p )
 {
     pcamv_shard_t *s = (pcamv_shard_t *)p;
@@ -60,6 +92,8 @@ int main( int argc, char **argv )
     pcamv_shard_t *sh;
     pthread_t *th;
     FILE *fo;
+    if( argc >= 3 && !strcmp( argv[1], "--extract" ) )
+        return pcamv_extract_main( argc, argv );
     if( argc < 6 || strcmp( argv[1], "--shards" ) || strcmp( argv[3], "--shard-frames" ) )
         return x264_cli_main( argc, argv );
     n = atoi( argv[2] ); k = atoi( argv[4] );
@@ -129,6 +163,8 @@ def shard_driver(tree):
     # pointers in encoder/analyse.c:195 keep referring to them: with more than one encoder per process they must stay
     t = reftree.sub_exact(t, r"x264_free\(g_x264_cost_mv_fpel\[i\]\[j\]\);", ";", 1, "free fpel tables")
     t = reftree.sub_exact(t, r"x264_free\(g_cost_mv\[i\]\);", ";", 1, "free cost_mv tables")
+    # the extractor the reference lacks (host/pcamv_stc_extract.c) joins the translation unit that owns getMatrix (embed.h)
+    t += "\n" + open(os.path.join(HERE, "pcamv_stc_extract.c")).read()
     reftree.write(p, t)
     # the LCG behind the STC sub-matrices for widths outside the built-in tables (embed.h:134-139) keeps static state
     p = os.path.join(tree, "embed.h")

@@ -161,8 +161,6 @@ void pcamv_hook_open( x264_t *h )
         die_msg( "sub-8x8 partitions (--partitions p4x4) are not supported" );
     if( h->param.analyse.b_mixed_references )
         die_msg( "--mixed-refs is not supported" );
-    if( h->param.analyse.i_me_method > X264_ME_ESA )
-        die_msg( "--me tesa is not supported" );
     memset( &cfg, 0, sizeof(cfg) );
     cfg.abi_version = PCAMV_ABI_VERSION;
     cfg.device = (s = getenv( "PCAMV_DEVICE" )) ? atoi( s ) : 0;
@@ -454,6 +452,19 @@ void pcamv_hook_embed( x264_t *h, int an )
             int32_t hd[3] = { h->i_frame, h->info.length, an };
             fwrite( hd, 4, 3, f );
             if( an > 0 ) fwrite( h->info.message, 1, an, f );
+            fwrite( h->info.stego, 1, h->info.length, f );
+            fclose( f );
+        }
+    }
+    /* PCAMV_STEGO=<file>: the extractor's input (x264_pcamv --extract) — frame, length, an and the stego LSBs only */
+    s = getenv( "PCAMV_STEGO" );
+    if( s && *s )
+    {
+        FILE *f = fopen( s, "ab" );
+        if( f )
+        {
+            int32_t hd[3] = { h->i_frame, h->info.length, an };
+            fwrite( hd, 4, 3, f );
             fwrite( h->info.stego, 1, h->info.length, f );
             fclose( f );
         }

@@ -50,6 +50,10 @@ int main(int argc, char **argv)
     std::vector<ForcedOut> forced(n_mb);
     std::map<int, std::vector<uint32_t>> last_mv_pass1;      // frame -> final cache MVs of the last MB of pass 1
     MbWork work;
+    // checker-side integral planes (8x8 box sums of the padded integer plane, what k_box_sum8 builds on the GPU) and the
+    // --me tesa candidate list of the single emulated team
+    std::vector<std::vector<uint16_t>> integral(PCAMV_MAX_REFS);
+    std::vector<unsigned long long> mvsads((size_t)(2 * fc.me_range + 4) * (2 * fc.me_range + 1));
 
     long n_call = 0, bad_call = 0, n_mbs = 0, bad_mb = 0, n_ih = 0, bad_ih = 0, n_passes = 0;
     int frames_done = 0;
@@ -74,6 +78,23 @@ int main(int argc, char **argv)
             DevRef &r = fc.ref[i];
             for (int k = 0; k < 4; k++) r.y[k] = (uint8_t *)sp.refs[i].y[k];
             r.u = (uint8_t *)sp.refs[i].u; r.v = (uint8_t *)sp.refs[i].v; r.valid = 1;
+            r.integral = nullptr;
+            if (fc.me_method >= ME_ESA)
+            {
+                const int st = fc.stride_y, rows = sp.hd.lines_y + 64;
+                const uint8_t *base = sp.refs[i].y[0] - (size_t)st * 32 - 32;
+                std::vector<uint16_t> &sum = integral[i];
+                sum.assign((size_t)st * rows, 0);
+                for (int y = 0; y + 8 <= rows; y++)
+                    for (int x = 0; x + 8 <= st; x++)
+                    {
+                        int a = 0;
+                        for (int yy = 0; yy < 8; yy++)
+                            for (int xx = 0; xx < 8; xx++) a += base[(size_t)(y + yy) * st + x + xx];
+                        sum[(size_t)y * st + x] = (uint16_t)a;
+                    }
+                r.integral = sum.data() + (size_t)st * 32 + 32;
+            }
         }
         fp.col_n_ref = hx[18];
         for (int i = 0; i < 16; i++) fp.col_inv_ref_poc[i] = hx[19 + i];
@@ -81,6 +102,7 @@ int main(int argc, char **argv)
         fp.col_mv4 = (const uint32_t *)(sx.data + sizeof(hx) + 4 * n_mb);
         fp.cur.type = type.data(); fp.cur.ref8 = ref8.data(); fp.cur.mv4 = mv4.data(); fp.cur.mvr = mvr.data();
         fp.log = log.data(); fp.log_stride = PCAMV_LOG_MAX; fp.results = results.data();
+        fp.mvsads = fc.me_method == ME_TESA ? mvsads.data() : nullptr; fp.mvsads_cap = 0;       // one team: every row shares the list
 
         // reference records of this frame/pass
         std::vector<std::vector<CallRec>> calls(n_mb);
@@ -135,7 +157,7 @@ int main(int argc, char **argv)
                 memcpy(work.fenc_u + 8 * y, fc.fenc_u + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
                 memcpy(work.fenc_v + 8 * y, fc.fenc_v + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
             }
-            analyse_p_mb(c, mb ? results[mb - 1].mv : fp.stale_mv);
+            analyse_p_mb<1>(c, mb ? results[mb - 1].mv : fp.stale_mv);
             MbResult &res = results[mb];
             // (1) call log
             const std::vector<CallRec> &rc = calls[mb];

@@ -64,7 +64,7 @@ int main(int argc, char **argv)
             int mvc[10][2];
             for (int i = 0; i < c.i_mvc && i < 10; i++) { mvc[i][0] = c.mvc[i][0]; mvc[i][1] = c.mvc[i][1]; }
             m.mv[0] = m.mv[1] = 0; m.cost = 0; m.cost_mv = 0;
-            me_search_ref(env, b, mvc, c.i_mvc, c.has_thresh ? &thresh : nullptr, m);
+            me_search_ref<1>(env, b, mvc, c.i_mvc, c.has_thresh ? &thresh : nullptr, m);
         }
         else
         {

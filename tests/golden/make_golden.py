@@ -23,6 +23,7 @@ CASES = {
     "qcif_hex5": (176, 144, 4, 32, "1:4", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --emrate 0.2"),
     "qcif_umh5_ref2": (176, 144, 4, 16, "2:4", "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.2"),
     "qcif_esa5": (176, 144, 3, 32, "1:2", "--qp 26 --ref 1 --keyint 250 --me esa --merange 16 --subme 5 --emrate 0.2"),
+    "qcif_tesa5": (176, 144, 3, 32, "1:2", "--qp 26 --ref 1 --keyint 250 --me tesa --merange 16 --subme 5 --emrate 0.2"),
     "qcif_dia2_lownoise": (176, 144, 4, 4, "1:4", "--qp 30 --ref 1 --keyint 250 --me dia --subme 2 --emrate 0.2"),
 }
 
@@ -30,7 +31,10 @@ CASES = {
 def main():
     pcamv = pcamv_loader.load()
     work = tempfile.mkdtemp(prefix="pcamv_mkgold_")
+    only = sys.argv[1:]
     for name, (w, h, n, noise, rng, args) in CASES.items():
+        if only and name not in only:
+            continue
         clip = refrun.synth_clip(pcamv, w, h, n, config=9, stream=len(name), noise16=noise, workdir=work)
         dump = os.path.join(work, name + ".bin")
         refrun.run_ref(clip, w, h, args.split(), dump=dump, frames=rng, count=True)

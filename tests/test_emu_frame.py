@@ -24,7 +24,7 @@ def run_checker(checker, dump):
     return {k: int(v) for k, v in out.items()}
 
 
-@pytest.mark.parametrize("name", ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"])
+@pytest.mark.parametrize("name", ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_tesa5", "qcif_dia2_lownoise"])
 def test_golden_frames(checker, name, tmp_path):
     n = run_checker(checker, refrun.golden_dump_path(name, str(tmp_path)))
     assert n["passes"] >= 2 and n["calls"] > 1000 and n["ih"] > 100
@@ -36,6 +36,8 @@ LIVE = [
     ("--me hex --subme 4 --ref 2 --no-fast-pskip", "2:4", 32),
     ("--me dia --subme 2 --ref 1 --qp 32", "1:4", 4),          # low noise: P_SKIP-heavy, exercises the pass-2 quirks
     ("--me hex --subme 5 --ref 1 --no-cabac", "1:3", 16),
+    ("--me esa --merange 16 --subme 5 --ref 2", "1:3", 32),            # successive elimination on the integral plane
+    ("--me tesa --merange 24 --subme 3 --ref 2", "1:3", 32),           # SATD as fpelcmp, ADS/SAD thresholds, list pruning
 ]
 
 

@@ -14,7 +14,7 @@ import refrun
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"]
+GOLDEN = ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_tesa5", "qcif_dia2_lownoise"]
 
 
 from frame_parity import check_dump
@@ -32,6 +32,8 @@ def test_frame_analysis_matches_reference(pcamv, cuda_lib, name, tmp_path):
     ("--me hex --subme 5 --ref 1", "1:4", (352, 288)),
     ("--me umh --subme 5 --ref 3", "3:5", (352, 288)),
     ("--me umh --subme 5 --ref 1", "1:2", (1280, 720)),
+    ("--me esa --merange 32 --subme 5 --ref 4", "3:4", (352, 288)),      # BASELINE config 3's search at CIF
+    ("--me tesa --merange 24 --subme 4 --ref 2", "2:3", (352, 288)),
 ])
 def test_frame_analysis_live_reference(pcamv, cuda_lib, args, frames, size, tmp_path):
     w, h = size

@@ -81,6 +81,8 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
     fc.stride_y = align_up(cfg->width + 2 * PCAMV_PADH, 16);
     fc.stride_c = align_up(fc.stride_y / 2, 16);
     fc.me_method = cfg->me_method; fc.me_range = cfg->me_range; fc.subme = cfg->subpel_refine;
+    if (fc.me_method == PCAMV_ME_TESA && fc.subme <= 1)
+        fc.me_method = PCAMV_ME_ESA;          // as the reference does (encoder/encoder.c:490-492)
     fc.chroma_me = cfg->chroma_me; fc.mv_range = cfg->mv_range; fc.max_refs = cfg->max_refs;
     fc.b_cabac = cfg->b_cabac; fc.b_fast_pskip = cfg->b_fast_pskip; fc.b_dct_decimate = cfg->b_dct_decimate;
     fc.analyse_inter = cfg->analyse_inter; fc.pass2_elide = cfg->pass2_elide != 0;
@@ -119,6 +121,12 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
         r.u = ctx->d_ref[s] + 4 * ctx->luma_bytes + (size_t)fc.stride_c * (PCAMV_PADV / 2) + PCAMV_PADH / 2;
         r.v = r.u + ctx->chroma_bytes;
         r.integral = nullptr; r.poc = -1; r.valid = 0;
+        if (fc.me_method >= PCAMV_ME_ESA)
+        {
+            OCK(cudaMalloc(&ctx->d_integral[s], ctx->luma_bytes * sizeof(uint16_t)));
+            OCK(cudaMemsetAsync(ctx->d_integral[s], 0, ctx->luma_bytes * sizeof(uint16_t), ctx->stream));
+            r.integral = ctx->d_integral[s] + (size_t)fc.stride_y * PCAMV_PADV + PCAMV_PADH;
+        }
     }
     OCK(cudaMalloc(&ctx->d_cost_mv, 32769 * sizeof(int16_t)));
     OCK(cudaMalloc(&ctx->d_tables, 4096));
@@ -139,7 +147,7 @@ extern "C" void pcamv_close(pcamv_ctx *ctx)
     cudaFree(ctx->d_calls); cudaFree(ctx->d_results);
     cudaFree(ctx->fa.type); cudaFree(ctx->fa.ref8); cudaFree(ctx->fa.mv4); cudaFree(ctx->fa.mvr);
     cudaFree(ctx->d_col_ref8); cudaFree(ctx->d_col_mv4); cudaFree(ctx->d_forced); cudaFree(ctx->d_log);
-    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim);
+    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_mvsads); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim);
     if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
     if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
     if (ctx->h_calls) cudaFreeHost(ctx->h_calls);
@@ -203,6 +211,12 @@ static int filter_slot(pcamv_ctx *ctx, int slot)
     launch_expand_border(r.y[0], nullptr, nullptr, 1, fc.stride_y, 0, W, 0, H, -PCAMV_PADH, W + PCAMV_PADH, -PCAMV_PADV, H + PCAMV_PADV, ctx->stream);
     launch_expand_border(r.u, r.v, nullptr, 2, fc.stride_c, 0, W / 2, 0, H / 2, -PCAMV_PADH / 2, W / 2 + PCAMV_PADH / 2,
                          -PCAMV_PADV / 2, H / 2 + PCAMV_PADV / 2, ctx->stream);
+    if (r.integral)
+    {
+        launch_box_sum8(r.y[0] - (size_t)fc.stride_y * PCAMV_PADV - PCAMV_PADH, r.integral - (size_t)fc.stride_y * PCAMV_PADV - PCAMV_PADH,
+                        fc.stride_y, H + 2 * PCAMV_PADV, ctx->stream);
+        ctx->launches += 1;
+    }
     launch_hpel_filter(r.y[0], r.y[1], r.y[2], r.y[3], fc.stride_y, W, H, ctx->stream);
     launch_expand_border(r.y[1], r.y[2], r.y[3], 3, fc.stride_y, -4, W + 4, -8, H + 8, -PCAMV_PADH, W + PCAMV_PADH,
                          -PCAMV_PADV, H + PCAMV_PADV, ctx->stream);
@@ -240,6 +254,12 @@ extern "C" int pcamv_put_ref_planes(pcamv_ctx *ctx, int slot, int poc, const uin
         CK(cudaMemcpyAsync(base + k * ctx->luma_bytes, luma_padded[k], ctx->luma_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(base + 4 * ctx->luma_bytes, u_padded, ctx->chroma_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(base + 4 * ctx->luma_bytes + ctx->chroma_bytes, v_padded, ctx->chroma_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (r.integral)
+    {
+        launch_box_sum8(base, ctx->d_integral[slot], ctx->fc.stride_y, ctx->fc.height + 2 * PCAMV_PADV, ctx->stream);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     r.poc = poc; r.valid = 1;
     return 0;
@@ -287,6 +307,8 @@ static int ensure_batch(pcamv_ctx *ctx, int n)
 static int check_calls(pcamv_ctx *ctx, const pcamv_me_call *calls, int n)
 {
     if (!ctx->fc.tab.cost_mv) return fail(ctx, "search: pcamv_set_qp_tables has not been called", cudaSuccess);
+    if (ctx->fc.me_method == PCAMV_ME_TESA)
+        return fail(ctx, "search: --me tesa is served by the frame seam only (pcamv_analyse_p)", cudaSuccess);
     for (int i = 0; i < n; i++)
     {
         const pcamv_me_call &c = calls[i];

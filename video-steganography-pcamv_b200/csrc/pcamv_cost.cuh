@@ -197,6 +197,7 @@ PCAMV_FN void cost_table_mb(MbCtx &c, MbResult &res)
     c.env.me_method = c.fc.me_method; c.env.me_range = c.fc.me_range; c.env.subme = c.fc.subme;
     c.env.chroma_me = c.fc.chroma_me && c.fc.subme >= 5;
     c.env.mbcmp_satd = c.fc.subme > 1;
+    c.env.mvsads = nullptr;
     for (int k = 0; k < res.n_part; k++)
     {
         int m_x, m_y;

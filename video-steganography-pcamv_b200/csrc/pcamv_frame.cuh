@@ -582,9 +582,10 @@ PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, i
     for (int k = 0; k < 4; k++) b.ref[k] = rf.y[k] + off;
     const ptrdiff_t offc = (ptrdiff_t)(8 * c.mb_y + (yoff >> 1)) * b.stride_c + 8 * c.mb_x + (xoff >> 1);
     b.ref_u = rf.u + offc; b.ref_v = rf.v + offc;
-    b.integral = nullptr;
+    b.integral = rf.integral ? rf.integral + off : nullptr;
 }
 
+template <int XS>
 PCAMV_FN void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
 {
     MeBlock &b = c.w.blk;
@@ -592,7 +593,7 @@ PCAMV_FN void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2],
     s.mvp[0] = mv_x(mvp); s.mvp[1] = mv_y(mvp);
     block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
     s.r.mv[0] = s.r.mv[1] = 0; s.r.cost = 0; s.r.cost_mv = 0;
-    me_search_ref(c.env, b, mvc, i_mvc, thresh, s.r);
+    me_search_ref<XS>(c.env, b, mvc, i_mvc, thresh, s.r);
     log_push(c, LOG_SEARCH, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
 }
 
@@ -611,6 +612,7 @@ PCAMV_DEV int ref_cost(const MbCtx &c, int i_ref)
 }
 
 // 16x16 search over all references; returns 1 when the early P_SKIP termination fired
+template <int XS>
 PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_pskip)
 {
     const int lambda = c.fc.tab.lambda;
@@ -628,7 +630,7 @@ PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_p
         int (*mvc)[2] = c.w.mvc;
         const uint32_t mvp = predict_mv_16x16(c, i_ref);
         const int i_mvc = predict_mv_ref16x16(c, i_ref, mvc);
-        run_search(c, m, mvp, mvc, i_mvc, p_thresh);
+        run_search<XS>(c, m, mvp, mvc, i_mvc, p_thresh);
         if (allow_skip && i_ref == 0 && b_try_pskip && m.r.cost - m.r.cost_mv < 300 * lambda &&
             iabs(m.r.mv[0] - c.pskip_mv[0]) + iabs(m.r.mv[1] - c.pskip_mv[1]) <= 1 && probe_pskip(c))
             return 1;
@@ -644,6 +646,7 @@ PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_p
     return 0;
 }
 
+template <int XS>
 PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
 {
     const int i_ref = a.me16x16.i_ref;
@@ -658,7 +661,7 @@ PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
         MeSlot &m = a.me8x8[i];
         const int x8 = i & 1, y8 = i >> 1;
         m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_8x8; m.xoff = 8 * x8; m.yoff = 8 * y8;
-        run_search(c, m, predict_mv(c, 4 * i, 2), mvc, i_mvc, nullptr);
+        run_search<XS>(c, m, predict_mv(c, 4 * i, 2), mvc, i_mvc, nullptr);
         cache_fill_rect(c, 2 * x8, 2 * y8, 2, 2, 0, pack_mv(m.r.mv[0], m.r.mv[1]), 0, 1);
         mvc[i_mvc][0] = m.r.mv[0]; mvc[i_mvc][1] = m.r.mv[1];
         i_mvc++;
@@ -671,6 +674,7 @@ PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
 }
 
 // 16x8 (dir = 0) or 8x16 (dir = 1)
+template <int XS>
 PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
 {
     c.partition = dir ? PART_8x16 : PART_16x8;
@@ -698,7 +702,7 @@ PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
             mvc[2][0] = a.mvc[i_ref][k2][0]; mvc[2][1] = a.mvc[i_ref][k2][1];
             if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, i_ref, 0, 1, 0);
             else     cache_fill_rect(c, 0, 2 * i, 4, 2, i_ref, 0, 1, 0);
-            run_search(c, m, dir ? predict_mv(c, 4 * i, 2) : predict_mv(c, 8 * i, 4), mvc, 3, nullptr);
+            run_search<XS>(c, m, dir ? predict_mv(c, 4 * i, 2) : predict_mv(c, 8 * i, 4), mvc, 3, nullptr);
             m.r.cost += m.i_ref_cost;
             if (m.r.cost < best.r.cost)
                 best = m;
@@ -798,6 +802,7 @@ PCAMV_DEV void wait_prev_raster(const MbCtx &c)
 
 // One macroblock of a P slice.  `prev_mv` = the 16 cache MVs left behind by the previous MB in raster order
 // (needed only for the pass-2 "forced skip without cache update" quirk, analyse.c:2668-2676).
+template <int XS>
 PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
 {
     const DevFrameCtx &fc = c.fc;
@@ -812,6 +817,7 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     c.env.me_method = fc.me_method; c.env.me_range = fc.me_range; c.env.subme = fc.subme;
     c.env.chroma_me = fc.chroma_me && fc.subme >= 5;
     c.env.mbcmp_satd = fc.subme > 1;
+    c.env.mvsads = c.fp.mvsads ? c.fp.mvsads + (size_t)c.mb_y * c.fp.mvsads_cap : nullptr;
 
     int b_try_pskip = 0, b_skip = 0;
     if (fc.b_fast_pskip)
@@ -829,7 +835,7 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
         finalize_mb(c, a, MB_P_SKIP, PART_16x16, 1);
         return;
     }
-    early_skip = analyse_p16x16(c, a, 1, b_try_pskip);
+    early_skip = analyse_p16x16<XS>(c, a, 1, b_try_pskip);
     if (early_skip)
     {
         type = MB_P_SKIP;
@@ -838,7 +844,7 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     if (forced)
     {
         if (forced->type != MB_P_SKIP && type == MB_P_SKIP)
-            analyse_p16x16(c, a, 0, b_try_pskip);       // the reference re-runs the 16x16 search without the skip exit
+            analyse_p16x16<XS>(c, a, 0, b_try_pskip);       // the reference re-runs the 16x16 search without the skip exit
         type = forced->type;
     }
     if (type == MB_P_SKIP)
@@ -871,7 +877,7 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     const int flags = fc.analyse_inter;
     const int psub16 = (flags & 0x10) != 0;
     if (psub16)
-        analyse_p8x8(c, a);
+        analyse_p8x8<XS>(c, a);
     int i_cost = a.me16x16.r.cost;
     // (with X264_ANALYSE_PSUB8x8 the reference would go on to P_8x8 / sub-partitions here; pcamv_open rejects that flag)
     if (psub16)
@@ -879,9 +885,9 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
         const int thresh16x8 = a.me8x8[1].r.cost_mv + a.me8x8[2].r.cost_mv;
         if (a.cost8x8 < a.me16x16.r.cost + thresh16x8)
         {
-            analyse_p16x8_8x16(c, a, 0);
+            analyse_p16x8_8x16<XS>(c, a, 0);
             if (a.cost16x8 < i_cost) { i_cost = a.cost16x8; partition = PART_16x8; }
-            analyse_p16x8_8x16(c, a, 1);
+            analyse_p16x8_8x16<XS>(c, a, 1);
             if (a.cost8x16 < i_cost) { i_cost = a.cost8x16; partition = PART_8x16; }
         }
     }

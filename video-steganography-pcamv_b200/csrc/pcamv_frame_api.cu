@@ -13,7 +13,7 @@ using namespace pcamv;
 namespace pcamv {
 void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_rows, int rows_per_cta, void *stream);
 void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream);
-void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, void *stream);
+void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, int exhaustive, void *stream);
 void launch_cost_table_batch(const BatchItem *items, int n_items, int n_mb, void *stream);
 }
 
@@ -42,6 +42,12 @@ static int ensure_frame_buffers(pcamv_ctx *ctx)
     CK(cudaMalloc(&ctx->d_mb_results, n_mb * sizeof(MbResult)));
     CK(cudaMalloc(&ctx->d_progress, (fc.mb_h + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->d_trace, 2 * n_mb * sizeof(unsigned long long)));
+    if (fc.me_method == PCAMV_ME_TESA)
+    {
+        // every position of the widest window can end up in a team's list (reference: h->scratch_buffer)
+        ctx->mvsads_cap = (2 * fc.me_range + 4) * (2 * fc.me_range + 1);
+        CK(cudaMalloc(&ctx->d_mvsads, (size_t)fc.mb_h * ctx->mvsads_cap * sizeof(unsigned long long)));
+    }
     CK(cudaMemsetAsync(ctx->fa.type, 0, n_mb, ctx->stream));
     CK(cudaMemsetAsync(ctx->fa.ref8, 0, 4 * n_mb, ctx->stream));
     CK(cudaMemsetAsync(ctx->fa.mv4, 0, 16 * n_mb * sizeof(uint32_t), ctx->stream));
@@ -67,8 +73,8 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
         return ctx_fail(ctx, "pcamv_frame_upload: frame analysis supports subpel_refine 1..5 (RD mode decision is raster-serial)", cudaSuccess);
     if (fc.analyse_inter & 0x20)
         return ctx_fail(ctx, "pcamv_frame_upload: sub-8x8 partitions (X264_ANALYSE_PSUB8x8) are not supported", cudaSuccess);
-    if (fc.me_method < PCAMV_ME_DIA || fc.me_method > PCAMV_ME_ESA)
-        return ctx_fail(ctx, "pcamv_frame_upload: me_method must be dia/hex/umh/esa", cudaSuccess);
+    if (fc.me_method < PCAMV_ME_DIA || fc.me_method > PCAMV_ME_TESA)
+        return ctx_fail(ctx, "pcamv_frame_upload: me_method must be dia/hex/umh/esa/tesa", cudaSuccess);
     if (in->pass < 0 || in->pass > 2 || in->n_ref < 1 || in->n_ref > ctx->cfg.max_refs)
         return ctx_fail(ctx, "pcamv_frame_upload: bad pass / n_ref", cudaSuccess);
     for (int i = 0; i < in->n_ref; i++)
@@ -119,6 +125,7 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
     for (int i = 0; i < 16; i++)
         fp.stale_mv[i] = ((uint32_t)(uint16_t)in->stale_mv[i][0]) | ((uint32_t)(uint16_t)in->stale_mv[i][1] << 16);
     fp.cur = ctx->fa;
+    fp.mvsads = ctx->d_mvsads; fp.mvsads_cap = ctx->mvsads_cap;
     fp.log = ctx->d_log; fp.log_stride = ctx->log_stride; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
     if (in->pass == 1) ctx->frame_cost_table = in->cost_table != 0;
     ctx->frame_last = in->pass;
@@ -322,7 +329,7 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
     CK(cudaMemcpyAsync(ctx->d_batch, ctx->h_batch, n * sizeof(BatchItem), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_batch_claim, 0, n * sizeof(int), ctx->stream));
     if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
-    launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta, ctx->batch_max_ctas, ctx->stream);
+    launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta, ctx->batch_max_ctas, fc.me_method >= PCAMV_ME_ESA, ctx->stream);
     ctx->launches += 1;
     if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
     if (cost_table)

@@ -53,6 +53,7 @@ __device__ __forceinline__ void stage_fenc(const DevFrameCtx &fc, int mb_x, int 
 
 
 // one macroblock row, left to right, behind the row above (the caller has claimed `row` in increasing order)
+template <int XS>
 __device__ __forceinline__ void analyse_row(const DevFrameCtx &fc, const FrameParams &fp, MbCtx &c, MbWork &work, int row)
 {
     const int lane = threadIdx.x & 31;
@@ -76,7 +77,7 @@ __device__ __forceinline__ void analyse_row(const DevFrameCtx &fc, const FramePa
         c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;
         if (fp.trace && lane == 0) fp.trace[2 * c.mb_xy] = globaltimer_ns();
         stage_fenc(fc, x, row, work);
-        analyse_p_mb(c, c.mb_xy ? fp.results[c.mb_xy - 1].mv : fp.stale_mv);
+        analyse_p_mb<XS>(c, c.mb_xy ? fp.results[c.mb_xy - 1].mv : fp.stale_mv);
         __syncwarp();
         if (lane == 0)
         {
@@ -87,7 +88,7 @@ __device__ __forceinline__ void analyse_row(const DevFrameCtx &fc, const FramePa
     }
 }
 
-template <int AP_WARPS>
+template <int AP_WARPS, int XS>
 __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_constant__ DevFrameCtx fc,
                                                             const __grid_constant__ FrameParams fp, int *row_claim)
 {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
         if (s_group * AP_WARPS >= mb_h)
             return;
         if (row < mb_h)
-            analyse_row(fc, fp, c, work, row);
+            analyse_row<XS>(fc, fp, c, work, row);
     }
 }
 
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(AP_WARPS * 32) k_analyse_p(const __grid_consta
 #define PCAMV_BATCH_MIN_CTAS 6      // CTAs of 4 warps per SM the register budget must allow (resident warps are what hides latency here)
 #endif
 #define PCAMV_GROUP_READY 4      // macroblocks the previous group's last row must have finished before the next group is handed out
-template <int AP_WARPS>
+template <int AP_WARPS, int XS>
 __global__ void __launch_bounds__(AP_WARPS * 32, PCAMV_BATCH_MIN_CTAS * 4 / AP_WARPS) k_analyse_p_batch(const BatchItem *__restrict__ items, int n_items, int *next_group)
 {
     __shared__ MbWork s_work[AP_WARPS];
@@ -177,32 +178,57 @@ __global__ void __launch_bounds__(AP_WARPS * 32, PCAMV_BATCH_MIN_CTAS * 4 / AP_W
         {
             const BatchItem &it = items[s_frame];
             MbCtx &c = *new (s_ctx[warp]) MbCtx(it.fc, it.fp, work);
-            analyse_row(it.fc, it.fp, c, work, row);
+            analyse_row<XS>(it.fc, it.fp, c, work, row);
         }
     }
 }
 
 // rows_per_cta: 1 = every row on its own SM (lowest latency for a single encoder), 4 = four consecutive rows share a
 // CTA and its L1 (higher throughput when many encoder contexts run concurrently)
+// XS = 1 instantiations carry the exhaustive searches (--me esa / tesa), XS = 0 the pattern searches only
 void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_rows, int rows_per_cta, void *stream)
 {
+    const cudaStream_t st = (cudaStream_t)stream;
+    const bool xs = fc.me_method >= ME_ESA;
     if (rows_per_cta >= 4)
-        k_analyse_p<4><<<(n_rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
+    {
+        if (xs) k_analyse_p<4, 1><<<(n_rows + 3) / 4, 128, 0, st>>>(fc, fp, row_claim);
+        else    k_analyse_p<4, 0><<<(n_rows + 3) / 4, 128, 0, st>>>(fc, fp, row_claim);
+    }
     else if (rows_per_cta >= 2)
-        k_analyse_p<2><<<(n_rows + 1) / 2, 64, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
+    {
+        if (xs) k_analyse_p<2, 1><<<(n_rows + 1) / 2, 64, 0, st>>>(fc, fp, row_claim);
+        else    k_analyse_p<2, 0><<<(n_rows + 1) / 2, 64, 0, st>>>(fc, fp, row_claim);
+    }
     else
-        k_analyse_p<1><<<n_rows, 32, 0, (cudaStream_t)stream>>>(fc, fp, row_claim);
+    {
+        if (xs) k_analyse_p<1, 1><<<n_rows, 32, 0, st>>>(fc, fp, row_claim);
+        else    k_analyse_p<1, 0><<<n_rows, 32, 0, st>>>(fc, fp, row_claim);
+    }
 }
 
-// next_group: n_items counters, zeroed by the caller
-void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, void *stream)
+// next_group: n_items counters, zeroed by the caller; all items share one search method (checked by the caller)
+void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, int exhaustive, void *stream)
 {
+    const cudaStream_t st = (cudaStream_t)stream;
     const int w = rows_per_cta >= 4 ? 4 : rows_per_cta >= 2 ? 2 : 1;
     int ctas = n_items * ((n_rows + w - 1) / w);
     if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
-    if (w == 4)      k_analyse_p_batch<4><<<ctas, 128, 0, (cudaStream_t)stream>>>(items, n_items, row_claim);
-    else if (w == 2) k_analyse_p_batch<2><<<ctas, 64, 0, (cudaStream_t)stream>>>(items, n_items, row_claim);
-    else             k_analyse_p_batch<1><<<ctas, 32, 0, (cudaStream_t)stream>>>(items, n_items, row_claim);
+    if (w == 4)
+    {
+        if (exhaustive) k_analyse_p_batch<4, 1><<<ctas, 128, 0, st>>>(items, n_items, row_claim);
+        else            k_analyse_p_batch<4, 0><<<ctas, 128, 0, st>>>(items, n_items, row_claim);
+    }
+    else if (w == 2)
+    {
+        if (exhaustive) k_analyse_p_batch<2, 1><<<ctas, 64, 0, st>>>(items, n_items, row_claim);
+        else            k_analyse_p_batch<2, 0><<<ctas, 64, 0, st>>>(items, n_items, row_claim);
+    }
+    else
+    {
+        if (exhaustive) k_analyse_p_batch<1, 1><<<ctas, 32, 0, st>>>(items, n_items, row_claim);
+        else            k_analyse_p_batch<1, 0><<<ctas, 32, 0, st>>>(items, n_items, row_claim);
+    }
 }
 
 // ---- cost table: one lane team per macroblock; macroblocks are independent -------------------------------

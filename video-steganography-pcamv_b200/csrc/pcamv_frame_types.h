@@ -65,6 +65,8 @@ struct FrameParams
     int log_stride;          // entries per macroblock (pcamv_log_stride)
     MbResult *results;       // [n_mb]
     int *row_progress;       // [mb_h] wavefront counters
+    unsigned long long *mvsads;  // --me tesa: [mb_h][mvsads_cap] candidate lists, one per macroblock row (= per lane team), else null
+    int mvsads_cap;
     unsigned long long *trace;   // optional [n_mb][2]: globaltimer ns at the start / end of each macroblock (profiling aid)
 };
 

@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_search_batch(const __grid_con
     env.cost_mv_fpel[0] = env.cost_mv_fpel[1] = env.cost_mv_fpel[2] = env.cost_mv_fpel[3] = nullptr;
     env.me_method = fc.me_method; env.me_range = fc.me_range; env.subme = fc.subme; env.chroma_me = fc.chroma_me && fc.subme >= 5;
     env.mbcmp_satd = fc.subme > 1;
+    env.mvsads = nullptr;
 #pragma unroll
     for (int k = 0; k < 2; k++)
     {
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_search_batch(const __grid_con
         const int nm = min(c.i_mvc, PCAMV_MAX_MVC);
         for (int i = 0; i < nm; i++) { mvc[i][0] = c.mvc[i][0]; mvc[i][1] = c.mvc[i][1]; }
         m.mv[0] = m.mv[1] = 0; m.cost = 0; m.cost_mv = 0;
-        me_search_ref(env, b, mvc, nm, c.has_thresh ? &thresh : nullptr, m);
+        me_search_ref<1>(env, b, mvc, nm, c.has_thresh ? &thresh : nullptr, m);
     }
     else
     {
@@ -283,6 +284,57 @@ void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int 
 {
     if (n <= 0) return;
     k_search_batch<<<(n + SB_WARPS - 1) / SB_WARPS, SB_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, calls, n, results);
+}
+
+// =====================================================================================================
+// Integral plane for the exhaustive searches (reference common/mc.c:311-345 integral_init8h / integral_init8v as
+// x264_frame_filter strings them together, mc.c:477-511): out[y][x] = sum of the 8x8 pixels of the PADDED integer luma
+// plane whose top-left corner is (x, y), as uint16 (<= 64 * 255, so the reference's modular running sums give exactly
+// this).  Positions whose box leaves the padded plane are never read by a search (MV limits keep a 16x16 block + the
+// 3-column overshoot inside the 32-pixel border) and are written as 0.  Horizontal 8-sums of a tile go through
+// shared memory, then 8 of them are added vertically: 1 byte read + 2 bytes written per pixel, HBM-bound.
+// =====================================================================================================
+#define BS_TW 64
+#define BS_TH 32
+__global__ void __launch_bounds__(256) k_box_sum8(const uint8_t *__restrict__ src, uint16_t *__restrict__ dst, int stride, int rows)
+{
+    __shared__ uint16_t hs[BS_TH + 7][BS_TW];
+    const int x0 = blockIdx.x * BS_TW, y0 = blockIdx.y * BS_TH;
+    for (int i = threadIdx.x; i < (BS_TH + 7) * BS_TW; i += 256)
+    {
+        const int r = i / BS_TW, c = i - r * BS_TW;
+        const int y = y0 + r, x = x0 + c;
+        int s = 0;
+        if (y < rows && x + 8 <= stride)
+        {
+            const uint8_t *p = src + (size_t)y * stride + x;
+#pragma unroll
+            for (int k = 0; k < 8; k++) s += p[k];
+        }
+        hs[r][c] = (uint16_t)s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BS_TH * BS_TW; i += 256)
+    {
+        const int r = i / BS_TW, c = i - r * BS_TW;
+        const int y = y0 + r, x = x0 + c;
+        if (y < rows && x < stride)
+        {
+            int s = 0;
+            if (y + 8 <= rows && x + 8 <= stride)
+            {
+#pragma unroll
+                for (int k = 0; k < 8; k++) s += hs[r + k][c];
+            }
+            dst[(size_t)y * stride + x] = (uint16_t)s;
+        }
+    }
+}
+
+void launch_box_sum8(const uint8_t *src_padded, uint16_t *dst_padded, int stride, int rows, void *stream)
+{
+    dim3 grid((stride + BS_TW - 1) / BS_TW, (rows + BS_TH - 1) / BS_TH);
+    k_box_sum8<<<grid, 256, 0, (cudaStream_t)stream>>>(src_padded, dst_padded, stride, rows);
 }
 
 // =====================================================================================================

@@ -30,6 +30,7 @@ struct MeEnv
     int mbcmp_satd;                  // mbcmp is SATD when subme > 1, else SAD (reference encoder/encoder.c:615-625)
     int mv_min_fpel[2], mv_max_fpel[2];   // per-MB limits (reference encoder/analyse.c:279-318)
     int mv_min_spel[2], mv_max_spel[2];
+    unsigned long long *mvsads;      // --me tesa: candidate list of the team ((2*range+4) * (2*range+1) entries), else null
 };
 
 // One block to be searched: fenc pixels, the 4 luma planes + 2 chroma planes of ONE reference,
@@ -46,6 +47,7 @@ struct MeBlock
     int i_pixel, bw, bh;
     int mvp[2];
     const int16_t *cost_mvx, *cost_mvy;   // cost_mv - mvp[0], cost_mv - mvp[1]
+    int k_fpel, k_qsad;       // what fpelcmp is at integer / quarter-pel positions: SAD, or SATD with --me tesa (encoder/encoder.c:621-624)
 };
 
 // search state / result (the in/out part of the reference's x264_me_t, encoder/me.h:30-51)
@@ -61,6 +63,9 @@ PCAMV_DEV void block_set_mvp(MeBlock &b, const MeEnv &env, int mvpx, int mvpy)
     b.mvp[0] = mvpx; b.mvp[1] = mvpy;
     b.cost_mvx = env.cost_mv - mvpx;
     b.cost_mvy = env.cost_mv - mvpy;
+    const int tesa = env.me_method == 4 && env.mbcmp_satd;
+    b.k_fpel = tesa ? 1 : 3;        // COST_SATD : COST_SAD_FPEL
+    b.k_qsad = tesa ? 1 : 0;        // COST_SATD : COST_SAD
 }
 
 // ---- quarter-pel reference addressing (reference common/mc.c:192-243) ---------------------------
@@ -268,7 +273,8 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
 #if !defined(PCAMV_EMU)
     {
         // group totals, then (always, branch-free) the team total for the single-candidate layout
-        // (three shuffles beat one REDUX here: a lone warp waits out the reduction's latency, measured 7 % per pass)
+        // (three shuffles beat one REDUX here: a lone warp waits out the reduction's latency, measured 7 % per pass;
+        // summing the four group totals from eval4's broadcasts instead of the two extra shuffles: measured no faster)
         acc = grp_sum(acc);
         int all = acc + __shfl_xor_sync(0xffffffffu, acc, 8);
         all += __shfl_xor_sync(0xffffffffu, all, 16);
@@ -324,7 +330,7 @@ PCAMV_FN best_t try4(const MeBlock &b, best_t best, int n, int ox, int oy, uint3
 #pragma unroll
     for (int i = 0; i < 4; i++)
         mv[i] = pk(ox + off_at(dxs, i), oy + off_at(dys, i));
-    eval4(b, COST_SAD_FPEL, n, pk(pk_x(mv[0]) << 2, pk_y(mv[0]) << 2), pk(pk_x(mv[1]) << 2, pk_y(mv[1]) << 2),
+    eval4(b, b.k_fpel, n, pk(pk_x(mv[0]) << 2, pk_y(mv[0]) << 2), pk(pk_x(mv[1]) << 2, pk_y(mv[1]) << 2),
           pk(pk_x(mv[2]) << 2, pk_y(mv[2]) << 2), pk(pk_x(mv[3]) << 2, pk_y(mv[3]) << 2), costs);
     int bcost = best_cost(best), bmv = best_mv(best);
 #pragma unroll
@@ -593,7 +599,7 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
         const int my = clip3(b.mvp[1], env.mv_min_spel[1], env.mv_max_spel[1]);
         if ((mx - bmx) | (my - bmy))
         {
-            const int s = eval1(b, COST_SAD, pk(mx, my));
+            const int s = eval1(b, b.k_qsad, pk(mx, my));
             if (s < bcost) { bcost = s; bmx = mx; bmy = my; }
         }
     }
@@ -602,7 +608,7 @@ PCAMV_FN void refine_subpel(const MeEnv &env, const MeBlock &b, MeResult &m, int
     for (int i = hpel_iters; i > 0; i--)
     {
         const int omx = bmx, omy = bmy;
-        eval4(b, COST_SAD, 4, pk(omx, omy - 2), pk(omx, omy + 2), pk(omx - 2, omy), pk(omx + 2, omy), costs);
+        eval4(b, b.k_qsad, 4, pk(omx, omy - 2), pk(omx, omy + 2), pk(omx - 2, omy), pk(omx + 2, omy), costs);
         // the vertical pair only ever moves bmy (reference COPY2_IF_LT on bmy alone)
         if (costs[0] < bcost) { bcost = costs[0]; bmy = omy - 2; }
         if (costs[1] < bcost) { bcost = costs[1]; bmy = omy + 2; }
@@ -674,11 +680,59 @@ PCAMV_DEV void subpel_iters(int subme, int out[4])
     out[0] = t & 15; out[1] = (t >> 4) & 15; out[2] = (t >> 8) & 15; out[3] = (t >> 12) & 15;
 }
 
-// Exhaustive search (reference encoder/me.c:483-634, --me esa).  The reference prunes with the
-// successive-elimination lower bound (ads) and skips rows whose y-cost alone is not below the best;
-// both are pure accelerations of a raster scan (y outer, x inner) with strict-< updates, which is
-// what is restated here.  The scanned width is rounded to a multiple of 4 exactly as the reference
-// rounds it (me.c:491), so up to 3 columns right of max_x are visited and the last one may be cut.
+// Exhaustive search (reference encoder/me.c:483-634, --me esa / tesa): a raster scan (y outer, x inner, strict <) of the
+// window around the best predictor; the scanned width is rounded to a multiple of 4 exactly as the reference rounds it
+// (me.c:491), so up to 3 columns right of max_x are visited and the last one may be cut.
+// Successive elimination (common/pixel.c:515-559): sum |DC(fenc sub-block) - DC(reference sub-block)| + cost_mvx is a lower
+// bound of SAD + cost_mvx; the 8x8 box sums of the reference come from the integral plane k_box_sum8 builds
+// (common/mc.c:311-345,477-511).  One candidate column per lane.
+
+// DCs of the (up to four) 8x8 quadrants of the block: enc_dc of me.c:515-523
+PCAMV_FN void block_dcs(const MeBlock &b, int dc[4])
+{
+    const smem_ptr fenc = to_smem(b.fenc);
+    const int bw = b.bw, bh = b.bh;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++)
+    {
+        const int qx = q & 1, qy = q >> 1;
+        int part = 0;
+        if (8 * qx < bw && 8 * qy < bh)
+        {
+#if defined(PCAMV_EMU)
+            for (int it = 0; it < 16; it++)
+                part += sad4(ld4s(fenc + (8 * qy + (it >> 1)) * 16 + 8 * qx + 4 * (it & 1)), 0u);
+#else
+            const int it = team_lane();
+            part = it < 16 ? sad4(ld4s(fenc + (8 * qy + (it >> 1)) * 16 + 8 * qx + 4 * (it & 1)), 0u) : 0;
+            part = team_sum(part);
+#endif
+        }
+        dc[q] = part;
+    }
+}
+
+PCAMV_DEV int ld_u16(const uint16_t *p)
+{
+#if defined(PCAMV_EMU)
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
+
+// x264_pixel_ads4 / ads2 / ads1 at full-pel (mx, my)
+PCAMV_DEV int ads_at(const MeBlock &b, const int dc[4], int mx, int my)
+{
+    const int stride = b.stride;
+    const uint16_t *s = b.integral + my * stride + mx;
+    int a = iabs(dc[0] - ld_u16(s));
+    if (b.bw == 16) a += iabs(dc[1] - ld_u16(s + 8));
+    if (b.bh == 16) a += iabs(dc[2] - ld_u16(s + 8 * stride));
+    if (b.bw == 16 && b.bh == 16) a += iabs(dc[3] - ld_u16(s + 8 * stride + 8));
+    return a + b.cost_mvx[mx << 2];
+}
+
 PCAMV_FN best_t search_esa(const MeEnv &e, const MeBlock &b, best_t best)
 {
     const int range = e.me_range;
@@ -686,18 +740,186 @@ PCAMV_FN best_t search_esa(const MeEnv &e, const MeBlock &b, best_t best)
     const int min_x = imax(bmx - range, e.mv_min_fpel[0]), min_y = imax(bmy - range, e.mv_min_fpel[1]);
     const int max_x = imin(bmx + range, e.mv_max_fpel[0]), max_y = imin(bmy + range, e.mv_max_fpel[1]);
     const int width = (max_x - min_x + 3) & ~3;
+    if (!b.integral || b.bw < 8 || b.bh < 8)
+    {
+        // without 8x8 box sums that bound this block (sub-8x8 blocks of the stateless search seam): every position gets its SAD
+#pragma unroll 1
+        for (int my = min_y; my <= max_y; my++)
+#pragma unroll 1
+            for (int x0 = 0; x0 < width; x0 += PCAMV_WIDE)
+            {
+                const int x = x0 + team_lane();
+                const int cost = x < width ? lane_sad(b, min_x + x, my) : PCAMV_COST_MAX;
+                best = fold_wide(best, cost, pk(min_x + x, my));
+            }
+        return best;
+    }
+    // A position whose lower bound is not below the running best cannot win under strict <: skipping it (and whole
+    // rows whose y cost alone reaches the best, me.c:617-619) leaves the first minimum of the raster scan unchanged.
+    int dc[4];
+    block_dcs(b, dc);
 #pragma unroll 1
     for (int my = min_y; my <= max_y; my++)
+    {
+        const int ycost = b.cost_mvy[my << 2];
+        if (best_cost(best) <= ycost)
+            continue;
 #pragma unroll 1
         for (int x0 = 0; x0 < width; x0 += PCAMV_WIDE)
         {
             const int x = x0 + team_lane();
-            const int cost = x < width ? lane_sad(b, min_x + x, my) : PCAMV_COST_MAX;
-            best = fold_wide(best, cost, pk(min_x + x, my));
+            const bool pass = x < width && ads_at(b, dc, min_x + x, my) < best_cost(best) - ycost;
+            unsigned m = team_ballot(pass);
+            if (!m)
+                continue;
+            if (popc32(m) > 8)
+            {
+                const int cost = pass ? lane_sad(b, min_x + x, my) : PCAMV_COST_MAX;
+                best = fold_wide(best, cost, pk(min_x + x, my));
+                continue;
+            }
+            // few survivors: the whole team costs them four at a time, in x order
+#pragma unroll 1
+            while (m)
+            {
+                int l[4], n = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    l[k] = 0;
+                    if (m) { l[k] = ctz32(m); m &= m - 1; n++; }
+                }
+                best = try4(b, best, n, min_x + x0, my, PCAMV_OFF4(l[0], l[1], l[2], l[3]), 0);
+            }
         }
+    }
     return best;
 }
 
+// --me tesa (me.c:524-613): ADS threshold, then SAD threshold, keep the best few SADs, then SATD on those.
+// Unlike ESA the prefilters decide the outcome here, so thresholds, list order and the partial selection sort are the
+// reference's own; only the evaluation is spread over the lanes (the running SAD threshold a sequential scan would hold
+// before each candidate is the prefix minimum over the lower lanes).
+PCAMV_DEV unsigned long long mvsad_make(int sad, int mx, int my)
+{
+    return ((unsigned long long)(uint32_t)sad << 32) | ((uint32_t)(mx & 0xffff) << 16) | (uint32_t)(my & 0xffff);
+}
+PCAMV_DEV int mvsad_sad(unsigned long long v) { return (int)(v >> 32); }
+PCAMV_DEV int mvsad_mv(unsigned long long v) { return pk((int)(int16_t)(v >> 16), (int)(int16_t)v); }
+
+PCAMV_FN best_t search_tesa(const MeEnv &e, const MeBlock &b, best_t best)
+{
+    const int range = e.me_range;
+    const int bmx = pk_x(best_mv(best)), bmy = pk_y(best_mv(best));
+    const int min_x = imax(bmx - range, e.mv_min_fpel[0]), min_y = imax(bmy - range, e.mv_min_fpel[1]);
+    const int max_x = imin(bmx + range, e.mv_max_fpel[0]), max_y = imin(bmy + range, e.mv_max_fpel[1]);
+    const int width = (max_x - min_x + 3) & ~3;
+    const int sad_thresh = range <= 16 ? 10 : range <= 24 ? 11 : 12;
+    unsigned long long *mvsads = e.mvsads;
+    int dc[4];
+    block_dcs(b, dc);
+    int n = 0;
+    int bsad = eval1(b, COST_SAD_FPEL, pk(bmx << 2, bmy << 2));      // plain SAD + BITS_MVD(bmx, bmy)
+#pragma unroll 1
+    for (int my = min_y; my <= max_y; my++)
+    {
+        const int ycost = b.cost_mvy[my << 2];
+        if (bsad <= ycost)
+            continue;
+        bsad -= ycost;
+        const int thresh = bsad * 17 / 16;          // fixed for the row, as in the reference's one ads call per row
+#pragma unroll 1
+        for (int x0 = 0; x0 < width; x0 += PCAMV_WIDE)
+        {
+            const int x = x0 + team_lane();
+            const bool pass = x < width && ads_at(b, dc, min_x + x, my) < thresh;
+            if (!team_ballot(pass))
+                continue;
+            // Reference quirk, reproduced: the SAD stage looks the x cost up with the column index RELATIVE to min_x
+            // (cost_fpel_mvx[xs[i]], me.c:549,565) where the ads call was handed cost_fpel_mvx + min_x, so the MV cost in
+            // these SADs is that of column x, not of min_x + x.
+            const int sad = pass ? lane_sad(b, min_x + x, my) - ycost - b.cost_mvx[(min_x + x) << 2] + b.cost_mvx[x << 2] : 0x7fffffff;
+            const int run = imin(bsad, team_prefix_min_excl(sad));
+            const bool take = pass && sad < ((run * sad_thresh) >> 3);
+            const unsigned tm = team_ballot(take);
+            if (take)
+                mvsads[n + popc_below(tm)] = mvsad_make(sad + ycost, min_x + x, my);
+            n += popc32(tm);
+            bsad = imin(bsad, team_min(sad));
+        }
+        bsad += ycost;
+    }
+    team_sync();
+    const int limit = range / 2;
+    if (n > limit * 2)
+    {
+        // halve the range if the domain is too large: keep, in order, the entries within the relaxed threshold
+        const int cut = (bsad * (sad_thresh + 8)) >> 4;
+        int w = 0;
+#pragma unroll 1
+        for (int j0 = 0; j0 < n; j0 += PCAMV_WIDE)
+        {
+            const int j = j0 + team_lane();
+            const unsigned long long v = j < n ? mvsads[j] : 0ull;
+            const bool keep = j < n && mvsad_sad(v) <= cut;
+            const unsigned km = team_ballot(keep);
+            team_sync();                        // the chunk is in registers before any of it is overwritten
+            if (keep)
+                mvsads[w + popc_below(km)] = v;
+            w += popc32(km);
+            team_sync();
+        }
+        n = w;
+    }
+    if (n > limit)
+    {
+        // partial selection sort of the first `limit` entries: first minimum, swapped into place
+#pragma unroll 1
+        for (int i = 0; i < limit; i++)
+        {
+            int bs = 0x7fffffff, bj = 0x7fffffff;
+#pragma unroll 1
+            for (int j = i + team_lane(); j < n; j += PCAMV_WIDE)
+            {
+                const int sj = mvsad_sad(mvsads[j]);
+                if (sj < bs) { bs = sj; bj = j; }
+            }
+            const int mn = team_min(bs);
+            bj = team_min(bs == mn ? bj : 0x7fffffff);
+            if (bj > i && team_lane() == 0)
+            {
+                const unsigned long long t = mvsads[i];
+                mvsads[i] = mvsads[bj];
+                mvsads[bj] = t;
+            }
+            team_sync();
+        }
+        n = limit;
+    }
+    // fpelcmp (SATD here) of the survivors, in list order
+#pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += 4)
+    {
+        const int nn = imin(4, n - i0);
+        int mv[4], costs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            mv[k] = mvsad_mv(mvsads[i0 + (k < nn ? k : 0)]);
+        eval4(b, b.k_fpel, nn, pk(pk_x(mv[0]) << 2, pk_y(mv[0]) << 2), pk(pk_x(mv[1]) << 2, pk_y(mv[1]) << 2),
+              pk(pk_x(mv[2]) << 2, pk_y(mv[2]) << 2), pk(pk_x(mv[3]) << 2, pk_y(mv[3]) << 2), costs);
+        int bcost = best_cost(best), bmv = best_mv(best);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < nn && costs[k] < bcost) { bcost = costs[k]; bmv = mv[k]; }
+        best = best_make(bcost, bmv);
+    }
+    return best;
+}
+
+// XS: the exhaustive searches (--me esa / tesa) are compiled in.  The kernels of the pattern searches are instantiated
+// without them: merely having that code in the call graph cost the UMH workload 7 % (register allocation and code layout
+// of the whole per-macroblock call tree; measured on B200).
+template <int XS>
 PCAMV_FN void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)[2], int i_mvc,
                              int *p_halfpel_thresh, MeResult &m)
 {
@@ -736,7 +958,7 @@ PCAMV_FN void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)
             if (n == 4 || (i == i_mvc && n > 0))
             {
                 int costs[4];
-                eval4(b, COST_SAD, n, c[0], c[1], c[2], c[3], costs);
+                eval4(b, b.k_qsad, n, c[0], c[1], c[2], c[3], costs);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if (k < n && costs[k] < bpred_cost) { bpred_cost = costs[k]; bpred_mv = c[k]; }
@@ -770,7 +992,8 @@ PCAMV_FN void me_search_ref(const MeEnv &env, const MeBlock &b, const int (*mvc)
     int run_hex = env.me_method == ME_HEX, hex_range = env.me_range;
     if (env.me_method == ME_DIA) best = search_dia(env, b, best, env.me_range);
     else if (env.me_method == ME_UMH) best = search_umh(env, b, best, pmx, pmy, mvc, i_mvc, &run_hex, &hex_range);
-    else if (env.me_method != ME_HEX) best = search_esa(env, b, best);
+    else if (XS && env.me_method == ME_TESA && env.mbcmp_satd) best = search_tesa(env, b, best);
+    else if (XS && env.me_method != ME_HEX) best = search_esa(env, b, best);
     if (run_hex)
         best = search_hex(env, b, best, hex_range);
 

@@ -86,6 +86,64 @@ PCAMV_DEV int lane_bcast(int v, int lane)
     return __shfl_sync(0xffffffffu, v, lane);
 #endif
 }
+// smallest value over the team, in every lane
+PCAMV_DEV int team_min(int v)
+{
+#if !defined(PCAMV_EMU)
+    v = __reduce_min_sync(0xffffffffu, v);
+#endif
+    return v;
+}
+// min over the LOWER lanes of the team (INT_MAX in lane 0): the running minimum a sequential scan would hold
+PCAMV_DEV int team_prefix_min_excl(int v)
+{
+#if defined(PCAMV_EMU)
+    (void)v; return 0x7fffffff;
+#else
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v = o < v ? o : v;
+    }
+    const int up = __shfl_up_sync(0xffffffffu, v, 1);
+    return lane ? up : 0x7fffffff;
+#endif
+}
+// bit l = predicate of lane l
+PCAMV_DEV unsigned team_ballot(bool p)
+{
+#if defined(PCAMV_EMU)
+    return p ? 1u : 0u;
+#else
+    return __ballot_sync(0xffffffffu, p);
+#endif
+}
+PCAMV_DEV int popc_below(unsigned mask)       // set bits of `mask` in lanes below the caller
+{
+#if defined(PCAMV_EMU)
+    (void)mask; return 0;
+#else
+    return __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
+#endif
+}
+PCAMV_DEV int ctz32(unsigned mask)            // index of the lowest set bit (mask != 0)
+{
+#if defined(PCAMV_EMU)
+    return __builtin_ctz(mask);
+#else
+    return __ffs((int)mask) - 1;
+#endif
+}
+PCAMV_DEV int popc32(unsigned mask)
+{
+#if defined(PCAMV_EMU)
+    return __builtin_popcount(mask);
+#else
+    return __popc(mask);
+#endif
+}
 PCAMV_DEV void team_sync()
 {
 #if !defined(PCAMV_EMU)

@@ -69,6 +69,7 @@ static int g_n_groups;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static __thread pcamv_group *g_group;       /* this encoder thread's group, NULL outside --shards */
 static __thread int g_in_group;
+static __thread int g_shard = -1;           /* this encoder thread's shard index, -1 outside --shards */
 
 void pcamv_glue_set_shards( int n )
 {
@@ -92,6 +93,16 @@ void pcamv_glue_set_shards( int n )
 void pcamv_glue_set_shard_index( int i )
 {
     g_group = g_n_groups ? g_groups[i % g_n_groups] : NULL;
+    g_shard = i;
+}
+
+/* side files (PCAMV_PAYLOAD, PCAMV_STEGO): one per shard ("<name>.<shard>") when several encoders share the process */
+static FILE *open_side_file( const char *name )
+{
+    char path[1200];
+    if( g_shard >= 0 ) snprintf( path, sizeof(path), "%s.%d", name, g_shard );
+    else snprintf( path, sizeof(path), "%s", name );
+    return fopen( path, "ab" );
 }
 
 /* called by a shard's thread when its encoder is gone, however it ended */
@@ -446,7 +457,7 @@ void pcamv_hook_embed( x264_t *h, int an )
     const char *s = getenv( "PCAMV_PAYLOAD" );
     if( s && *s )
     {
-        FILE *f = fopen( s, "ab" );
+        FILE *f = open_side_file( s );
         if( f )
         {
             int32_t hd[3] = { h->i_frame, h->info.length, an };
@@ -460,7 +471,7 @@ void pcamv_hook_embed( x264_t *h, int an )
     s = getenv( "PCAMV_STEGO" );
     if( s && *s )
     {
-        FILE *f = fopen( s, "ab" );
+        FILE *f = open_side_file( s );
         if( f )
         {
             int32_t hd[3] = { h->i_frame, h->info.length, an };

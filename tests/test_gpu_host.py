@@ -141,3 +141,42 @@ def test_static_clip_no_carriers(pcamv, cuda_lib, tmp_path):
     p = subprocess.run([HOST] + args.split() + ["-o", out, clip, "%dx%d" % (w, h)], capture_output=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")
     assert md5(out) == md5(ref_out)
+
+
+def test_multi_stream_embed_extract_round_trip(pcamv, cuda_lib, tmp_path):
+    """BASELINE config 5 in small: a batch of independent streams (different content, concatenated in one clip and encoded as
+    shards of one process sharing the GPU) — every stream's bitstream equals the reference encoder's run on that stream,
+    and the payload extracted from the stego vectors our encoder wrote (x264_pcamv --extract, host/pcamv_stc_extract.c)
+    equals, bit for bit, the message the REFERENCE embedded in that stream."""
+    import numpy as np
+    import test_extract
+    w, h, n, k = 640, 368, 8, 4
+    args = "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"
+    workdir = str(tmp_path)
+    clip = os.path.join(workdir, "streams.yuv")
+    with open(clip, "wb") as f:
+        for g in range(n):          # stream g: its own seed
+            f.write(open(refrun.synth_clip(pcamv, w, h, k, config=5, stream=10 + g, workdir=workdir), "rb").read())
+    want, ref_msgs = b"", []
+    for g in range(n):
+        dump = os.path.join(workdir, "d%d.bin" % g)
+        out, _ = refrun.run_ref(clip, w, h, args.split() + ["--seek", str(g * k), "--frames", str(k)], dump=dump, planes=False,
+                                calls=False, out=os.path.join(workdir, "ref_%d.264" % g))
+        want += open(out, "rb").read()
+        ref_msgs.append(pcamv.dumpfmt.Dump(dump).embeds())
+    out, stego = os.path.join(workdir, "batch.264"), os.path.join(workdir, "stego")
+    p = subprocess.run([HOST, "--shards", str(n), "--shard-frames", str(k)] + args.split() + ["-o", out, clip, "%dx%d" % (w, h)],
+                       env=dict(os.environ, PCAMV_STEGO=stego), capture_output=True, timeout=1800)
+    assert p.returncode == 0, p.stderr[-2000:].decode("latin-1")
+    assert open(out, "rb").read() == want, "batch of streams differs from the per-stream reference runs"
+    bits = 0
+    for g in range(n):
+        msg = os.path.join(workdir, "msg_%d.bin" % g)
+        q = subprocess.run([HOST, "--extract", "%s.%d" % (stego, g), "-o", msg], capture_output=True, timeout=600)
+        assert q.returncode == 0, q.stderr[-2000:].decode("latin-1")
+        got = test_extract.read_messages(msg)
+        assert len(got) == len(ref_msgs[g]) == k - 1
+        for (frame, an, m), e in zip(got, ref_msgs[g]):
+            assert an == e["an"] and np.array_equal(m, e["message"][:an]), "stream %d frame %d: extracted payload differs" % (g, frame)
+            bits += an
+    assert bits > 1000

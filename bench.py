@@ -134,7 +134,10 @@ def _run_encoder(binary, args, out, clip, env=None):
     return time.perf_counter() - t0, _x264_fps(p.stderr), p
 
 
-def encoder_e2e(pcamv, workdir, device, frames=24):
+ESA_ARGS = "--qp 26 --ref 4 --keyint 250 --me esa --merange 32 --subme 5 --emrate 0.2"       # BASELINE.json config 3
+
+
+def encoder_e2e(pcamv, workdir, device, frames=24, ref_args=REF_ARGS, config=2, tag="e2e"):
     """Whole-encoder leg: the reference's C host with the CUDA shim bound in (host/_build/x264_pcamv) against the
     reference encoder on the same 1080p clip and flags — frames/s of encode + embed, bitstreams compared."""
     import hashlib
@@ -143,16 +146,16 @@ def encoder_e2e(pcamv, workdir, device, frames=24):
     ref = os.path.join(ROOT, "oracle", "_ref", "x264_wide")
     if not os.path.exists(host):
         return {"unavailable": "host/_build/x264_pcamv is not built"}
-    clip = refrun.synth_clip(pcamv, WIDTH, HEIGHT, frames, config=2, stream=0, workdir=workdir)
-    ref_out, out = os.path.join(workdir, "e2e_ref.264"), os.path.join(workdir, "e2e_gpu.264")
-    t_ref, fps_ref, _ = _run_encoder(ref, REF_ARGS.split(), ref_out, clip)
-    stats = os.path.join(workdir, "e2e_stats.json")
-    t_gpu, fps_gpu, p = _run_encoder(host, REF_ARGS.split(), out, clip, env=dict(os.environ, PCAMV_STATS=stats, PCAMV_DEVICE=str(device)))
+    clip = refrun.synth_clip(pcamv, WIDTH, HEIGHT, frames, config=config, stream=0, workdir=workdir)
+    ref_out, out = os.path.join(workdir, tag + "_ref.264"), os.path.join(workdir, tag + "_gpu.264")
+    t_ref, fps_ref, _ = _run_encoder(ref, ref_args.split(), ref_out, clip)
+    stats = os.path.join(workdir, tag + "_stats.json")
+    t_gpu, fps_gpu, p = _run_encoder(host, ref_args.split(), out, clip, env=dict(os.environ, PCAMV_STATS=stats, PCAMV_DEVICE=str(device)))
     if p.returncode != 0:
         return {"unavailable": "x264_pcamv failed: " + p.stderr[-300:].decode("latin-1")}
     st = json.load(open(stats))
     same = hashlib.md5(open(out, "rb").read()).hexdigest() == hashlib.md5(open(ref_out, "rb").read()).hexdigest()
-    return {"frames": frames, "bitstream_identical": same,
+    return {"frames": frames, "args": ref_args, "bitstream_identical": same,
             "reference_fps": fps_ref[0] if fps_ref else None, "ours_fps": fps_gpu[0] if fps_gpu else None,
             "reference_fps_wall": frames / t_ref, "ours_fps_wall": frames / t_gpu,
             "ours_seconds_in_gpu_calls": st["t_gpu_calls"], "ours_seconds_open": st.get("t_open"), "ours_seconds_total": st["t_total"],
@@ -539,6 +542,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline_block(pcamv, clip, workdir)
             line["encoder_e2e"] = encoder_e2e(pcamv, workdir, local_rank)
             line["encoder_e2e_sharded"] = encoder_e2e_sharded(pcamv, workdir, local_rank)
+            # BASELINE.json config 3 (exhaustive search, merange 32, 4 references): one stream, whole encoder
+            line["encoder_e2e_esa"] = encoder_e2e(pcamv, workdir, local_rank, frames=6, ref_args=ESA_ARGS, config=3, tag="esa")
         print(json.dumps(line))
     for c in ctxs:
         c.close()

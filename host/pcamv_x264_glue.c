@@ -168,8 +168,6 @@ void pcamv_hook_open( x264_t *h )
         die_msg( "B frames are not supported" );
     if( h->param.analyse.i_subpel_refine > 5 )
         die_msg( "--subme 6 and above (RD mode decision on live CABAC state) is raster-serial; use --subme 1..5" );
-    if( h->param.analyse.inter & X264_ANALYSE_PSUB8x8 )
-        die_msg( "sub-8x8 partitions (--partitions p4x4) are not supported" );
     if( h->param.analyse.b_mixed_references )
         die_msg( "--mixed-refs is not supported" );
     memset( &cfg, 0, sizeof(cfg) );
@@ -192,6 +190,10 @@ void pcamv_hook_open( x264_t *h )
     /* pass 2 of a forced macroblock: only the 16x16 search is live in the reference (see include/pcamv.h); PCAMV_PASS2_FULL=1
      * makes the GPU execute and log the dead searches as well */
     g.elide = !((s = getenv( "PCAMV_PASS2_FULL" )) && atoi( s ));
+    /* with sub-8x8 partitions a forced P_8x8 macroblock keeps the h->mb.i_partition its own pass-2 analysis decided
+     * (analyse.c:2872-2890), and the MVD prediction of the bitstream writer reads it: those searches are not dead */
+    if( h->param.analyse.inter & X264_ANALYSE_PSUB8x8 )
+        g.elide = 0;
     cfg.pass2_elide = g.elide;
     pthread_mutex_lock( &g_mu );
     if( pcamv_open( &g.ctx, &cfg ) )
@@ -331,8 +333,14 @@ void pcamv_hook_slice_begin( x264_t *h )
             memcpy( p->ref, h->info.cache[i].ref, 16 );
             memcpy( p->mv, h->info.cache[i].mv, 64 );
             memcpy( p->mv_stego, h->info.cache[i].mv_stego, 64 );
-            if( p->used )
-                n += p->type == P_8x8 ? 4 : p->partition == D_16x16 ? 1 : 2;
+            if( p->used && p->type == P_8x8 )
+            {
+                int k;      /* carriers of a split 8x8 block: 4x4 -> 4, 8x4 / 4x8 -> 2, 8x8 -> 1 (encoder/encoder.c:1571-1620) */
+                for( k = 0; k < 4; k++ )
+                    n += p->sub[k] == D_L0_4x4 ? 4 : p->sub[k] == D_L0_8x8 ? 1 : 2;
+            }
+            else if( p->used )
+                n += p->partition == D_16x16 ? 1 : 2;
         }
         in.pass1 = g.pass1;
         in.filp = h->info.filp;

@@ -164,7 +164,7 @@ int pcamv_me_batch_run(pcamv_ctx *ctx, int iters, float *ms_per_launch);
 int pcamv_me_batch_download(pcamv_ctx *ctx, pcamv_me_result *results, int n);
 
 /* ---- frame seam: the P-slice body of x264_macroblock_analyse ------------------------------------------------ */
-#define PCAMV_LOG_MAX 48
+#define PCAMV_LOG_MAX 112
 
 /* One entry of a macroblock's result log.  The analysis of a macroblock calls x264_me_search_ref,
  * x264_me_refine_qpel and (pass 1) x264_ih_get_mv_cost in a data-dependent order (encoder/analyse.c:2646-2810,

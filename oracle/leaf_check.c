@@ -11,6 +11,10 @@ int pcamv_oracle_satd(const uint8_t *a, int sa, const uint8_t *b, int sb, int w,
 void pcamv_oracle_mc_luma(uint8_t *dst, int dst_stride, uint8_t *const src[4], int stride, int mvx, int mvy, int w, int h);
 void pcamv_oracle_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, int stride, int mvx, int mvy, int w, int h);
 
+void pcamv_oracle_integral8(const uint8_t *plane, uint16_t *sum8, int stride, int rows);
+int pcamv_oracle_ads(const int enc_dc[4], const uint16_t *sums, int delta, const uint16_t *cost_mvx, int16_t *mvs, int width,
+                     int thresh, int n_dc);
+
 static uint64_t rng = 0x5043414D56ULL;
 static uint32_t rnd(void) { rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27; return (uint32_t)((rng * 2685821657736338717ULL) >> 32); }
 
@@ -52,6 +56,43 @@ int main(void)
             mc.mc_chroma(d1, 32, src[0], S, mvx, mvy, pw[i_pix] / 2, ph[i_pix] / 2);
             pcamv_oracle_mc_chroma(d2, 32, src[0], S, mvx, mvy, pw[i_pix] / 2, ph[i_pix] / 2);
             checks++; bad += memcmp(d1, d2, sizeof(d1)) != 0;
+        }
+    }
+    /* integral plane (mc.c:311-345 driven as in x264_frame_filter, mc.c:489-509) and the ads prefilters (pixel.c:515-559) */
+    {
+        enum { IS = 96, IR = 72 };
+        static uint8_t pl[IS * IR + 64];
+        static uint16_t s_ref[IS * (IR + 1) + 64], s_or[IS * (IR + 1) + 64], cost[IS];
+        int y, x;
+        for (it = 0; it < 40; it++)
+        {
+            for (i = 0; i < IS * IR; i++) pl[i] = it % 3 == 2 ? 255 : (uint8_t)rnd();
+            memset(s_ref, 0, sizeof(s_ref)); memset(s_or, 0, sizeof(s_or));
+            for (y = 0; y < IR - 1; y++)
+            {
+                mc.integral_init8h(s_ref + (y + 1) * IS, pl + y * IS, IS);
+                if (y >= 7) mc.integral_init8v(s_ref + (y + 1) * IS - 8 * IS, IS);
+            }
+            pcamv_oracle_integral8(pl, s_or, IS, IR);
+            for (y = 0; y <= IR - 9; y++)
+                for (x = 0; x < IS - 8; x++)
+                {
+                    int box = 0, yy, xx;
+                    for (yy = 0; yy < 8; yy++) for (xx = 0; xx < 8; xx++) box += pl[(y + yy) * IS + x + xx];
+                    checks++; bad += s_ref[y * IS + x] != s_or[y * IS + x] || s_or[y * IS + x] != box;
+                }
+            for (k = 0; k < 30; k++)
+            {
+                int dc[4], n1, n2, th = (int)(rnd() % 6000), w = 4 * (1 + (int)(rnd() % 8));
+                int16_t m1[64], m2[64];
+                const int which = k % 3, pix = which == 0 ? PIXEL_16x16 : which == 1 ? PIXEL_16x8 : PIXEL_8x8;
+                const int delta = which == 0 ? 8 * IS : 8;
+                for (i = 0; i < 4; i++) dc[i] = (int)(rnd() % 16321);
+                for (i = 0; i < IS; i++) cost[i] = (uint16_t)(rnd() % 200);
+                n1 = pixf.ads[pix](dc, s_or + 10 * IS + 5, delta, cost, m1, w, th);
+                n2 = pcamv_oracle_ads(dc, s_or + 10 * IS + 5, delta, cost, m2, w, th, which == 0 ? 4 : which == 1 ? 2 : 1);
+                checks++; bad += n1 != n2 || memcmp(m1, m2, n1 * sizeof(int16_t)) != 0;
+            }
         }
     }
     printf("checks=%ld mismatches=%ld\n", checks, bad);

@@ -135,3 +135,48 @@ void pcamv_oracle_mc_chroma(uint8_t *dst, int dst_stride, const uint8_t *src, in
             dst[y * dst_stride + x] = (uint8_t)((cA * s[y * stride + x] + cB * s[y * stride + x + 1] +
                                                  cC * s[(y + 1) * stride + x] + cD * s[(y + 1) * stride + x + 1] + 32) >> 6);
 }
+
+/* common/mc.c:311-345 integral_init8h / integral_init8v as x264_frame_filter runs them (mc.c:477-511): a running
+ * column-prefix of horizontal 8-pixel sums in uint16 (wrapping), turned into 8x8 box sums eight rows behind.
+ * plane / sum8: top-left of the PADDED buffers (stride x rows).  On return sum8[y * stride + x] holds the sum of the
+ * 8x8 pixels whose top-left corner is (x, y) for x < stride - 8, y <= rows - 9; the eight rows below keep running
+ * prefixes, as in the reference's buffer. */
+void pcamv_oracle_integral8(const uint8_t *plane, uint16_t *sum8, int stride, int rows)
+{
+    int x, y;
+    memset(sum8, 0, (size_t)stride * sizeof(uint16_t));            /* the zero row above the first prefix row */
+    for (y = 0; y < rows - 1; y++)
+    {
+        const uint8_t *pix = plane + (size_t)y * stride;
+        uint16_t *sum = sum8 + (size_t)(y + 1) * stride;
+        int v = pix[0] + pix[1] + pix[2] + pix[3] + pix[4] + pix[5] + pix[6] + pix[7];
+        for (x = 0; x < stride - 8; x++)
+        {
+            sum[x] = (uint16_t)(v + sum[x - stride]);
+            v += pix[x + 8] - pix[x];
+        }
+        if (y >= 7)
+        {
+            uint16_t *s = sum8 + (size_t)(y - 7) * stride;         /* integral_init8v on the row 8 above the newest prefix */
+            for (x = 0; x < stride - 8; x++)
+                s[x] = (uint16_t)(s[x + 8 * stride] - s[x]);
+        }
+    }
+}
+
+/* common/pixel.c:515-559 x264_pixel_ads4 / ads2 / ads1 (n_dc = 4 / 2 / 1): candidates whose DC lower bound + MV cost stays
+ * below thresh, in increasing x */
+int pcamv_oracle_ads(const int enc_dc[4], const uint16_t *sums, int delta, const uint16_t *cost_mvx, int16_t *mvs, int width,
+                     int thresh, int n_dc)
+{
+    int nmv = 0, i;
+    for (i = 0; i < width; i++, sums++)
+    {
+        int ads = abs(enc_dc[0] - sums[0]) + cost_mvx[i];
+        if (n_dc == 2) ads += abs(enc_dc[1] - sums[delta]);
+        if (n_dc == 4) ads += abs(enc_dc[1] - sums[8]) + abs(enc_dc[2] - sums[delta]) + abs(enc_dc[3] - sums[delta + 8]);
+        if (ads < thresh)
+            mvs[nmv++] = (int16_t)i;
+    }
+    return nmv;
+}

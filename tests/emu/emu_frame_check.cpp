@@ -43,11 +43,11 @@ int main(int argc, char **argv)
     fc.tab.quant4_mf[0] = (const uint16_t *)qp_; fc.tab.quant4_bias[0] = (const uint16_t *)(qp_ + 32);
     fc.tab.quant4_mf[1] = (const uint16_t *)(qp_ + 64); fc.tab.quant4_bias[1] = (const uint16_t *)(qp_ + 96);
     fc.tab.dequant4_mf[0] = (const int32_t *)(qp_ + 128); fc.tab.dequant4_mf[1] = (const int32_t *)(qp_ + 128 + 384);
-    if (fc.analyse_inter & 0x20) { printf("skipped: sub-8x8 partitions are outside the supported frame analysis\n"); return 0; }
 
     std::vector<int8_t> type(n_mb), ref8(4 * n_mb); std::vector<uint32_t> mv4(16 * n_mb), mvr((size_t)PCAMV_MAX_REFS * n_mb);
     std::vector<LogEntry> log((size_t)n_mb * PCAMV_LOG_MAX); std::vector<MbResult> results(n_mb);
     std::vector<ForcedOut> forced(n_mb);
+    std::vector<PartInfo> subparts((size_t)16 * n_mb);
     std::map<int, std::vector<uint32_t>> last_mv_pass1;      // frame -> final cache MVs of the last MB of pass 1
     MbWork work;
     // checker-side integral planes (8x8 box sums of the padded integer plane, what k_box_sum8 builds on the GPU) and the
@@ -102,6 +102,7 @@ int main(int argc, char **argv)
         fp.col_mv4 = (const uint32_t *)(sx.data + sizeof(hx) + 4 * n_mb);
         fp.cur.type = type.data(); fp.cur.ref8 = ref8.data(); fp.cur.mv4 = mv4.data(); fp.cur.mvr = mvr.data();
         fp.log = log.data(); fp.log_stride = PCAMV_LOG_MAX; fp.results = results.data();
+        fp.subparts = (fc.analyse_inter & 0x20) ? subparts.data() : nullptr;
         fp.mvsads = fc.me_method == ME_TESA ? mvsads.data() : nullptr; fp.mvsads_cap = 0;       // one team: every row shares the list
 
         // reference records of this frame/pass
@@ -157,7 +158,7 @@ int main(int argc, char **argv)
                 memcpy(work.fenc_u + 8 * y, fc.fenc_u + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
                 memcpy(work.fenc_v + 8 * y, fc.fenc_v + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
             }
-            analyse_p_mb<1>(c, mb ? results[mb - 1].mv : fp.stale_mv);
+            analyse_p_mb<3>(c, mb ? results[mb - 1].mv : fp.stale_mv);
             MbResult &res = results[mb];
             // (1) call log
             const std::vector<CallRec> &rc = calls[mb];
@@ -226,8 +227,15 @@ int main(int argc, char **argv)
                 const LogEntry *le = &log[(size_t)mb * PCAMV_LOG_MAX + n0];
                 for (int k = 0; k < res.n_part; k++)
                 {
-                    const int slot = res.partition == PART_16x16 ? 0 : res.partition == PART_16x8 ? 8 * k : res.partition == PART_8x16 ? 4 * k : 4 * k;
-                    const int want_x = mbs[mb].mv_stego[slot][0] - res.part[k].mv[0], want_y = mbs[mb].mv_stego[slot][1] - res.part[k].mv[1];
+                    const PartInfo &pk = (res.type == MB_P_8x8 && fp.subparts) ? fp.subparts[(size_t)16 * mb + k] : res.part[k];
+                    int slot = res.partition == PART_16x16 ? 0 : res.partition == PART_16x8 ? 8 * k : res.partition == PART_8x16 ? 4 * k : 4 * k;
+                    if (res.type == MB_P_8x8)
+                    {
+                        // info.cache slot of a (sub-)block of P_8x8 (analyse.c:3559-3601): 4 * i8 + { 8x8: 0, 8x4: 2j, 4x8: j, 4x4: j }
+                        const int i8 = (pk.xoff >> 3) + 2 * (pk.yoff >> 3), sx = (pk.xoff & 7) >> 2, sy = (pk.yoff & 7) >> 2;
+                        slot = 4 * i8 + (pk.i_pixel == PIX_8x8 ? 0 : pk.i_pixel == PIX_8x4 ? 2 * sy : pk.i_pixel == PIX_4x8 ? sx : sx + 2 * sy);
+                    }
+                    const int want_x = mbs[mb].mv_stego[slot][0] - pk.mv[0], want_y = mbs[mb].mv_stego[slot][1] - pk.mv[1];
                     n_ih++;
                     if (le[k].mv[0] != want_x || le[k].mv[1] != want_y || le[k].cost != mbs[mb].cost[slot])
                     {

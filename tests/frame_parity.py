@@ -82,10 +82,20 @@ def check_dump(pcamv, dump, units=None, ctx=None, keep_ctx=False):
             last_mv[s.frame] = mbs["mv"][n_mb - 1]
             for mb in np.nonzero(mbs["type"] != 6)[0]:
                 r = mbs[mb]
-                for k in range(r["n_part"]):
-                    sl = {16: 0, 14: 8 * k, 15: 4 * k}.get(int(r["partition"]), 4 * k)
+                if int(r["type"]) == 5:
+                    # P_8x8: info.cache slots of the (sub-)blocks in the reference's order (encoder/analyse.c:3546-3606), from the
+                    # reference's own sub-partition types; a block's original vector is the final cache MV of its first 4x4
+                    slots = []
+                    for i8, kind in enumerate(e["mbs"][mb]["sub"]):
+                        slots += [4 * i8 + d for d in {3: [0], 1: [0, 2], 2: [0, 1], 0: [0, 1, 2, 3]}[int(kind)]]
+                    assert int(r["n_part"]) == len(slots), "frame %d MB %d: %d MV-carrying blocks, reference has %d" % (s.frame, mb, r["n_part"], len(slots))
+                    origs = [r["mv"][sl] for sl in slots]
+                else:
+                    slots = [{16: 0, 14: 8 * k, 15: 4 * k}[int(r["partition"])] for k in range(r["n_part"])]
+                    origs = [r["part"][k]["mv"] for k in range(r["n_part"])]
+                for k, (sl, orig) in enumerate(zip(slots, origs)):
                     le = log[mb, counts[mb] + k]
-                    want = e["mbs"][mb]["mv_stego"][sl] - r["part"][k]["mv"]
+                    want = e["mbs"][mb]["mv_stego"][sl] - orig
                     assert le["kind"] == 2 and (le["mv"] == want).all() and le["cost"] == e["mbs"][mb]["inter_stego_cost"][sl], \
                         "frame %d MB %d part %d: cost table differs: got d%s cost %d, reference d%s cost %d" % (
                             s.frame, mb, k, le["mv"], le["cost"], want, e["mbs"][mb]["inter_stego_cost"][sl])

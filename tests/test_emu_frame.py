@@ -37,7 +37,10 @@ LIVE = [
     ("--me dia --subme 2 --ref 1 --qp 32", "1:4", 4),          # low noise: P_SKIP-heavy, exercises the pass-2 quirks
     ("--me hex --subme 5 --ref 1 --no-cabac", "1:3", 16),
     ("--me esa --merange 16 --subme 5 --ref 2", "1:3", 32),            # successive elimination on the integral plane
-    ("--me tesa --merange 24 --subme 3 --ref 2", "1:3", 32),           # SATD as fpelcmp, ADS/SAD thresholds, list pruning
+    ("--me tesa --merange 24 --subme 3 --ref 2", "1:3", 32),
+    ("--me hex --subme 5 --ref 1 --partitions p8x8,p4x4", "1:3", 32),   # sub-8x8 partitions: P_8x8 with 4x4 / 8x4 / 4x8 splits
+    ("--me umh --subme 5 --ref 2 --partitions all", "2:4", 24),
+    ("--me dia --subme 1 --ref 1 --partitions all --qp 30", "1:3", 24),           # SATD as fpelcmp, ADS/SAD thresholds, list pruning
 ]
 
 

@@ -34,6 +34,8 @@ def test_frame_analysis_matches_reference(pcamv, cuda_lib, name, tmp_path):
     ("--me umh --subme 5 --ref 1", "1:2", (1280, 720)),
     ("--me esa --merange 32 --subme 5 --ref 4", "3:4", (352, 288)),      # BASELINE config 3's search at CIF
     ("--me tesa --merange 24 --subme 4 --ref 2", "2:3", (352, 288)),
+    ("--me hex --subme 5 --ref 1 --partitions p8x8,p4x4", "1:3", (352, 288)),      # sub-8x8 partitions
+    ("--me umh --subme 5 --ref 2 --partitions all", "2:4", (352, 288)),
 ])
 def test_frame_analysis_live_reference(pcamv, cuda_lib, args, frames, size, tmp_path):
     w, h = size
@@ -45,7 +47,7 @@ def test_frame_analysis_live_reference(pcamv, cuda_lib, args, frames, size, tmp_
 
 
 def test_frame_seam_rejects_unsupported(pcamv, cuda_lib):
-    """subme >= 6 (RD) and sub-8x8 partitions are refused loudly, never silently approximated."""
+    """subme >= 6 (RD mode decision) is refused loudly, never silently approximated."""
     ctx = pcamv.PcamvContext(176, 144, subpel_refine=7)
     cm = np.zeros(32769, dtype=np.int16)
     z16 = np.zeros(16, dtype=np.uint16); z96 = np.zeros(96, dtype=np.int32)

@@ -25,6 +25,8 @@ CASES = [
     ("qcif_esa", 176, 144, 6, 9, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me esa --merange 16 --subme 5 --emrate 0.2"),
     ("qcif_tesa", 176, 144, 6, 9, 32, "x264_wide", "--qp 26 --ref 2 --keyint 250 --me tesa --merange 16 --subme 5 --emrate 0.2"),
     ("cif_esa32_ref4", 352, 288, 6, 1, 32, "x264_wide", "--qp 26 --ref 4 --keyint 250 --me esa --merange 32 --subme 5 --emrate 0.2"),
+    ("cif_p4x4_hex5", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --partitions p8x8,p4x4 --emrate 0.2"),
+    ("cif_p4x4_umh_ref3", 352, 288, 8, 1, 24, "x264_wide", "--qp 24 --ref 3 --keyint 250 --me umh --subme 4 --partitions all --emrate 0.3"),
     ("720p_umh5", 1280, 720, 4, 5, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
     # option coverage (the reference Makefile's OPT0..OPT7 flag sets, Makefile:108-115, restricted to the supported path)
     ("cif_nocabac", 352, 288, 8, 1, 16, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --no-cabac --emrate 0.2"),

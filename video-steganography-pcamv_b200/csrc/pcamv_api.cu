@@ -85,13 +85,17 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
         fc.me_method = PCAMV_ME_ESA;          // as the reference does (encoder/encoder.c:490-492)
     fc.chroma_me = cfg->chroma_me; fc.mv_range = cfg->mv_range; fc.max_refs = cfg->max_refs;
     fc.b_cabac = cfg->b_cabac; fc.b_fast_pskip = cfg->b_fast_pskip; fc.b_dct_decimate = cfg->b_dct_decimate;
-    fc.analyse_inter = cfg->analyse_inter; fc.pass2_elide = cfg->pass2_elide != 0;
+    fc.analyse_inter = cfg->analyse_inter;
+    // (not with sub-8x8 partitions: a forced P_8x8 keeps the partition its own pass-2 analysis decided, which the host reads)
+    fc.pass2_elide = cfg->pass2_elide != 0 && !(cfg->analyse_inter & 0x20);
     {
         // most entries one macroblock can log: a 16x16 search per reference (twice in pass 2 when an early skip is
         // overridden), four 8x8, two 16x8 + two 8x16 per candidate reference (<= 2 each), two refinements, two cost-table
         // entries; rounded up to a multiple of 4 and capped by the ABI constant
         const int r = cfg->max_refs, r2 = r < 2 ? r : 2;
         int n = 2 * r + 4 + 4 * r2 + 2 + 2;
+        if (cfg->analyse_inter & 0x20)
+            n += 32 + 14 + 14;      // X264_ANALYSE_PSUB8x8: 8 sub-block searches per 8x8 block, up to 16 refinements and 16 cost-table entries
         n = (n + 3) & ~3;
         ctx->log_stride = n < PCAMV_LOG_MAX ? n : PCAMV_LOG_MAX;
     }
@@ -147,7 +151,7 @@ extern "C" void pcamv_close(pcamv_ctx *ctx)
     cudaFree(ctx->d_calls); cudaFree(ctx->d_results);
     cudaFree(ctx->fa.type); cudaFree(ctx->fa.ref8); cudaFree(ctx->fa.mv4); cudaFree(ctx->fa.mvr);
     cudaFree(ctx->d_col_ref8); cudaFree(ctx->d_col_mv4); cudaFree(ctx->d_forced); cudaFree(ctx->d_log);
-    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_mvsads); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim);
+    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_mvsads); cudaFree(ctx->d_subparts); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim);
     if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
     if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
     if (ctx->h_calls) cudaFreeHost(ctx->h_calls);

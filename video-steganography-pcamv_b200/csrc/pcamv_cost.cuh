@@ -12,13 +12,19 @@ namespace pcamv {
 
 // x264_macroblock_encode for an inter MB whose partition k_over uses MV (omx, omy) instead of its own.
 // Leaves the reconstruction in c.w.pred_y / pred_u / pred_v.
+// partition k of the macroblock's final mode: the record holds up to four, P_8x8 macroblocks keep theirs in the side array
+PCAMV_DEV const PartInfo &mb_part(const MbCtx &c, const MbResult &res, int k)
+{
+    return (res.type == MB_P_8x8 && c.fp.subparts) ? c.fp.subparts[(size_t)16 * c.mb_xy + k] : res.part[k];
+}
+
 PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx, int omy)
 {
     const DevTables &t = c.fc.tab;
     const int b_decimate = c.fc.b_dct_decimate;
     for (int p = 0; p < res.n_part; p++)
     {
-        const PartInfo &pi = res.part[p];
+        const PartInfo &pi = mb_part(c, res, p);
         const int mx = clip3(p == k_over ? omx : pi.mv[0], c.mv_min[0], c.mv_max[0]);
         const int my = clip3(p == k_over ? omy : pi.mv[1], c.mv_min[1], c.mv_max[1]);
         mc_rect(c, c.fp.ref_slot[pi.ref], pi.xoff, pi.yoff, pix_w(pi.i_pixel), pix_h(pi.i_pixel), mx, my);
@@ -124,7 +130,7 @@ PCAMV_DEV int cand_dy(int ii) { return (int)(((long long)(0xFEEF1221010Full << (
 // x264_ih_get_mv_cost for partition k of macroblock `res`; returns cost_opt, writes the chosen delta
 PCAMV_FN int ih_get_mv_cost(MbCtx &c, const MbResult &res, int k, int &m_x, int &m_y)
 {
-    const PartInfo &pi = res.part[k];
+    const PartInfo &pi = mb_part(c, res, k);
     const int bmx = pi.mv[0], bmy = pi.mv[1];
     MeBlock &b = c.w.blk;
     setup_block(c, b, pi.ref, pi.i_pixel, pi.xoff, pi.yoff);
@@ -202,7 +208,7 @@ PCAMV_FN void cost_table_mb(MbCtx &c, MbResult &res)
     {
         int m_x, m_y;
         const int cost_opt = ih_get_mv_cost(c, res, k, m_x, m_y);
-        log_push(c, LOG_IHCOST, res.part[k].i_pixel, res.part[k].ref, m_x, m_y, cost_opt, 0);
+        log_push(c, LOG_IHCOST, mb_part(c, res, k).i_pixel, mb_part(c, res, k).ref, m_x, m_y, cost_opt, 0);
     }
     if (team_lane() == 0)
         c.fp.results[c.mb_xy].n_log = c.n_log;

@@ -36,6 +36,7 @@ struct pcamv_ctx
     pcamv::LogEntry *d_log = nullptr;          // [n_mb][log_stride]
     int log_stride = PCAMV_LOG_MAX;            // entries per macroblock: what the configured search can produce at most
     pcamv::MbResult *d_mb_results = nullptr;   // [n_mb]
+    pcamv::PartInfo *d_subparts = nullptr;     // [n_mb][16], only with sub-8x8 partitions enabled
     pcamv::BatchItem *d_batch = nullptr, *h_batch = nullptr; int batch_items_cap = 0;   // leader of a multi-context launch
     int *d_batch_claim = nullptr;
     int batch_max_ctas = 0, batch_claim_cap = 0;   // persistent grid size of multi-context launches (0 = not yet computed)

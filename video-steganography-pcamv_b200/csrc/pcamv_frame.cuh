@@ -37,6 +37,7 @@ struct MbAnalysis
     MeSlot me16x16, me8x8[4], me16x8[2], me8x16[2];
     int mvc[PCAMV_MAX_REFS][5][2];        // [ref][0] = 16x16 result, [ref][1..4] = 8x8 results
     int cost8x8, cost16x8, cost8x16;
+    int8_t sub[4];                        // h->mb.i_sub_partition
 };
 
 // team-shared scratch of one macroblock
@@ -54,6 +55,19 @@ struct alignas(16) MbWork
     int mvc[PCAMV_MAX_MVC][2];
     int halfpel_thresh;
 };
+
+// Search results of the sub-8x8 partitions (reference x264_mb_analysis_t.l0.me4x4 / me8x4 / me4x8, encoder/analyse.c:66-75),
+// 8 per 8x8 block: [0..3] 4x4, [4..5] 8x4, [6..7] 4x8.  They live in MbWork::coef (512 of its 768 bytes): the coefficient
+// scratch is only in use inside the P_SKIP probe and the cost-table kernel, never while partitions are being searched.
+struct SubSlot { int16_t mv[2]; int16_t mvp[2]; int32_t cost, cost_mv; };
+enum { SUB_4x4 = 0, SUB_8x4 = 1, SUB_4x8 = 2, SUB_8x8 = 3 };       // D_L0_4x4 .. D_L0_8x8 (common/macroblock.h:115-118)
+PCAMV_DEV SubSlot *sub_slots(MbWork &w, int i8) { return (SubSlot *)&w.coef[0][0] + 8 * i8; }
+PCAMV_DEV int sub_first(int kind) { return kind == SUB_4x4 ? 0 : kind == SUB_8x4 ? 4 : 6; }
+PCAMV_DEV int sub_count(int kind) { return kind == SUB_4x4 ? 4 : kind == SUB_8x8 ? 1 : 2; }
+PCAMV_DEV int sub_pixel(int kind) { return kind == SUB_4x4 ? PIX_4x4 : kind == SUB_8x4 ? PIX_8x4 : kind == SUB_4x8 ? PIX_4x8 : PIX_8x8; }
+// offset of sub-block j of an 8x8 block split as `kind`, in pixels
+PCAMV_DEV int sub_xoff(int kind, int j) { return kind == SUB_4x4 ? 4 * (j & 1) : kind == SUB_4x8 ? 4 * j : 0; }
+PCAMV_DEV int sub_yoff(int kind, int j) { return kind == SUB_4x4 ? 4 * (j >> 1) : kind == SUB_8x4 ? 4 * j : 0; }
 
 // Loads of per-frame motion state written by OTHER macroblocks of the running wavefront (possibly on another SM):
 // they bypass the non-coherent L1 (ld.global.cg).  Ordering against the writer is the row-progress flag
@@ -429,6 +443,20 @@ PCAMV_FN void mc_rect(MbCtx &c, int ref_slot, int x0, int y0, int wd, int ht, in
     }
     const int cw4 = wd >> 3, chh = ht >> 1;      // chroma words per row / rows
     const ptrdiff_t offc = (ptrdiff_t)(8 * c.mb_y + (y0 >> 1)) * b.stride_c + 8 * c.mb_x + (x0 >> 1);
+    if (cw4 == 0)
+    {
+        // 4 luma pixels wide: two chroma pixels per row
+        PCAMV_FOR_ITEMS(it, 2 * chh)
+        {
+            const int pl = it / chh, y = it - pl * chh;
+            const uint8_t *src = (pl ? rf.v : rf.u) + offc;
+            uint8_t *dst = (pl ? c.w.pred_v : c.w.pred_u) + ((y0 >> 1) + y) * 8 + (x0 >> 1);
+            const uint32_t v = chroma4(src, b.stride_c, qmx, qmy, 0, y);
+            dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8);
+        }
+        team_sync();
+        return;
+    }
     PCAMV_FOR_ITEMS(it, 2 * cw4 * chh)
     {
         const int pl = it / (cw4 * chh), r = it - pl * cw4 * chh;
@@ -671,6 +699,7 @@ PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
     a.cost8x8 = a.me8x8[0].r.cost + a.me8x8[1].r.cost + a.me8x8[2].r.cost + a.me8x8[3].r.cost;
     if (c.fc.b_cabac)
         a.cost8x8 -= rc;
+    a.sub[0] = a.sub[1] = a.sub[2] = a.sub[3] = SUB_8x8;
 }
 
 // 16x8 (dir = 0) or 8x16 (dir = 1)
@@ -715,7 +744,125 @@ PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
     if (dir) a.cost8x16 = total; else a.cost16x8 = total;
 }
 
+// ---- sub-8x8 partitions of one 8x8 block (reference encoder/analyse.c:1569-1693) --------------------------------
+// chroma part of a sub-partition cost (x264_mb_analyse_inter_p4x4_chroma, analyse.c:1535-1567): the 4x4 chroma block of
+// each plane is predicted piecewise with the sub-blocks' own vectors (one pixel per lane) and compared with mbcmp 4x4
+template <int XS>
+PCAMV_FN int sub_chroma_cost(MbCtx &c, MbAnalysis &a, int i8, int kind)
+{
+    const DevRef &rf = c.fc.ref[c.fp.ref_slot[a.me8x8[i8].i_ref]];
+    const SubSlot *ss = sub_slots(c.w, i8) + sub_first(kind);
+    const int stride_c = c.fc.stride_c;
+    const int cx0 = 4 * (i8 & 1), cy0 = 4 * (i8 >> 1);
+    const ptrdiff_t offc = (ptrdiff_t)(8 * c.mb_y + cy0) * stride_c + 8 * c.mb_x + cx0;
+    team_sync();
+    PCAMV_FOR_ITEMS(it, 32)
+    {
+        const int pl = it >> 4, px_ = it & 3, py_ = (it >> 2) & 3;
+        const int j = kind == SUB_4x4 ? (px_ >> 1) + 2 * (py_ >> 1) : kind == SUB_8x4 ? py_ >> 1 : px_ >> 1;
+        const int mvx = ss[j].mv[0], mvy = ss[j].mv[1];
+        const int dx = mvx & 7, dy = mvy & 7;
+        const uint8_t *s = (pl ? rf.v : rf.u) + offc + (py_ + (mvy >> 3)) * stride_c + px_ + (mvx >> 3);
+        const int v = ((8 - dx) * (8 - dy) * s[0] + dx * (8 - dy) * s[1] + (8 - dx) * dy * s[stride_c] + dx * dy * s[stride_c + 1] + 32) >> 6;
+        (pl ? c.w.pred_v : c.w.pred_u)[(cy0 + py_) * 8 + cx0 + px_] = (uint8_t)v;
+    }
+    team_sync();
+    int cost = 0;
+    PCAMV_FOR_ITEMS(pl, 2)
+    {
+        const uint8_t *fe = (pl ? c.w.fenc_v : c.w.fenc_u) + cy0 * 8 + cx0, *pr = (pl ? c.w.pred_v : c.w.pred_u) + cy0 * 8 + cx0;
+        uint32_t f[4], p4[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) { f[r] = ld4a(fe + 8 * r); p4[r] = ld4a(pr + 8 * r); }
+        if (c.env.mbcmp_satd)
+            cost += (int)(hadamard_4x4_sum(f, p4) >> 1);
+        else
+            cost += sad4(f[0], p4[0]) + sad4(f[1], p4[1]) + sad4(f[2], p4[2]) + sad4(f[3], p4[3]);
+    }
+    return team_sum(cost);
+}
+
+// searches of 8x8 block i8 split as `kind` (p4x4 / p8x4 / p4x8); returns the cost of that split
+template <int XS>
+PCAMV_FN int analyse_sub8x8(MbCtx &c, MbAnalysis &a, int i8, int kind)
+{
+    const int i_ref = a.me8x8[i8].i_ref;
+    const int n = sub_count(kind);
+    SubSlot *ss = sub_slots(c.w, i8) + sub_first(kind);
+    c.partition = PART_8x8;
+    int total = 0;
+#pragma unroll 1
+    for (int j = 0; j < n; j++)
+    {
+        // idx of the sub-block's first 4x4 in block_idx order: 4x4 -> j, 8x4 -> 2j, 4x8 -> j
+        const int idx = 4 * i8 + (kind == SUB_8x4 ? 2 * j : j);
+        const int x4 = (idx & 1) | ((idx >> 1) & 2), y4 = ((idx >> 1) & 1) | ((idx >> 2) & 2);
+        MeSlot &m = c.w.slot;
+        m.i_ref = i_ref; m.i_ref_cost = 0; m.i_pixel = sub_pixel(kind); m.xoff = 4 * x4; m.yoff = 4 * y4;
+        int (*mvc)[2] = c.w.mvc;
+        if (kind == SUB_4x4) { mvc[0][0] = a.me8x8[i8].r.mv[0]; mvc[0][1] = a.me8x8[i8].r.mv[1]; }
+        else { const SubSlot &f = sub_slots(c.w, i8)[0]; mvc[0][0] = f.mv[0]; mvc[0][1] = f.mv[1]; }
+        const uint32_t mvp = predict_mv(c, idx, kind == SUB_8x4 ? 2 : 1);
+        run_search<XS>(c, m, mvp, mvc, j == 0, nullptr);
+        ss[j].mv[0] = (int16_t)m.r.mv[0]; ss[j].mv[1] = (int16_t)m.r.mv[1];
+        ss[j].mvp[0] = (int16_t)m.mvp[0]; ss[j].mvp[1] = (int16_t)m.mvp[1];
+        ss[j].cost = m.r.cost; ss[j].cost_mv = m.r.cost_mv;
+        cache_fill_rect(c, x4, y4, kind == SUB_4x8 || kind == SUB_4x4 ? 1 : 2, kind == SUB_8x4 || kind == SUB_4x4 ? 1 : 2, 0,
+                        pack_mv(m.r.mv[0], m.r.mv[1]), 0, 1);
+        total += m.r.cost;
+    }
+    // i_sub_mb_p_cost_table = { 5, 3, 3, 1 } for 4x4, 8x4, 4x8, 8x8 (analyse.c:179-181)
+    total += ref_cost(c, i_ref) + c.fc.tab.lambda * (kind == SUB_4x4 ? 5 : 3);
+    if (c.env.chroma_me)
+        total += sub_chroma_cost<XS>(c, a, i8, kind);
+    return total;
+}
+
+// x264_mb_cache_mv_p8x8 (analyse.c:1821-1849): the chosen split's vectors of 8x8 block i8 into the MV cache
+PCAMV_FN void cache_mv_p8x8(MbCtx &c, const MbAnalysis &a, int i8)
+{
+    const int x = 2 * (i8 & 1), y = 2 * (i8 >> 1), kind = a.sub[i8];
+    if (kind == SUB_8x8)
+    {
+        cache_fill_rect(c, x, y, 2, 2, 0, pack_mv(a.me8x8[i8].r.mv[0], a.me8x8[i8].r.mv[1]), 0, 1);
+        return;
+    }
+    const SubSlot *ss = sub_slots(c.w, i8) + sub_first(kind);
+#pragma unroll 1
+    for (int j = 0; j < sub_count(kind); j++)
+        cache_fill_rect(c, x + (sub_xoff(kind, j) >> 2), y + (sub_yoff(kind, j) >> 2), kind == SUB_8x4 ? 2 : 1, kind == SUB_4x8 ? 2 : 1, 0,
+                        pack_mv(ss[j].mv[0], ss[j].mv[1]), 0, 1);
+}
+
+// x264_me_refine_qpel on the sub-blocks of a split 8x8 block; returns the summed cost
+PCAMV_FN int refine_sub8x8(MbCtx &c, MbAnalysis &a, int i8)
+{
+    const int kind = a.sub[i8];
+    if (kind == SUB_8x8)
+    {
+        run_refine(c, a.me8x8[i8]);
+        return a.me8x8[i8].r.cost;
+    }
+    SubSlot *ss = sub_slots(c.w, i8) + sub_first(kind);
+    int total = 0;
+#pragma unroll 1
+    for (int j = 0; j < sub_count(kind); j++)
+    {
+        MeSlot &m = c.w.slot;
+        m.i_ref = a.me8x8[i8].i_ref; m.i_ref_cost = 0; m.i_pixel = sub_pixel(kind);
+        m.xoff = 8 * (i8 & 1) + sub_xoff(kind, j); m.yoff = 8 * (i8 >> 1) + sub_yoff(kind, j);
+        m.mvp[0] = ss[j].mvp[0]; m.mvp[1] = ss[j].mvp[1];
+        m.r.mv[0] = ss[j].mv[0]; m.r.mv[1] = ss[j].mv[1]; m.r.cost = ss[j].cost; m.r.cost_mv = ss[j].cost_mv;
+        run_refine(c, m);
+        ss[j].mv[0] = (int16_t)m.r.mv[0]; ss[j].mv[1] = (int16_t)m.r.mv[1]; ss[j].cost = m.r.cost; ss[j].cost_mv = m.r.cost_mv;
+        total += m.r.cost;
+    }
+    return total;
+}
+
 // write the decided mode into the neighbour cache (x264_analyse_update_cache, P part)
+// SUB8: the sub-8x8 partition code is compiled in (X264_ANALYSE_PSUB8x8); kernels for the default partition set leave it out
+template <int SUB8>
 PCAMV_FN void update_cache(MbCtx &c, const MbAnalysis &a, int type, int partition)
 {
     if (type == MB_P_SKIP)
@@ -736,10 +883,19 @@ PCAMV_FN void update_cache(MbCtx &c, const MbAnalysis &a, int type, int partitio
     else
 #pragma unroll 1
         for (int i = 0; i < 4; i++)
-            cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, a.me8x8[i].i_ref, pack_mv(a.me8x8[i].r.mv[0], a.me8x8[i].r.mv[1]), 1, 1);
+        {
+            if (SUB8)
+            {
+                cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, a.me8x8[i].i_ref, 0, 1, 0);
+                cache_mv_p8x8(c, a, i);
+            }
+            else
+                cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, a.me8x8[i].i_ref, pack_mv(a.me8x8[i].r.mv[0], a.me8x8[i].r.mv[1]), 1, 1);
+        }
 }
 
 // store the MB's final state to the frame arrays (x264_macroblock_cache_save, inter part) and the result record
+template <int SUB8>
 PCAMV_FN void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition, int early_skip)
 {
     const int no_parts = partition < 0;        // elided pass-2 macroblock: the partition slots were never searched
@@ -762,20 +918,53 @@ PCAMV_FN void finalize_mb(MbCtx &c, const MbAnalysis &a, int type, int partition
 #pragma unroll 1
         for (int i = 0; i < 16; i++) r.mv[i] = c.w.mv[scan8(i)];
         r.n_part = 0;
-        if (type != MB_P_SKIP && !no_parts)
+        if (type != MB_P_SKIP && !no_parts && partition != PART_8x8)
         {
-            const int np = partition == PART_16x16 ? 1 : partition == PART_8x8 ? 4 : 2;
+            const int np = partition == PART_16x16 ? 1 : 2;
             r.n_part = (int8_t)np;
 #pragma unroll 1
             for (int i = 0; i < np; i++)
             {
-                const MeSlot &m = partition == PART_16x16 ? a.me16x16 : partition == PART_16x8 ? a.me16x8[i]
-                                : partition == PART_8x16 ? a.me8x16[i] : a.me8x8[i];
+                const MeSlot &m = partition == PART_16x16 ? a.me16x16 : partition == PART_16x8 ? a.me16x8[i] : a.me8x16[i];
                 r.part[i].mv[0] = (int16_t)m.r.mv[0]; r.part[i].mv[1] = (int16_t)m.r.mv[1];
                 r.part[i].mvp[0] = (int16_t)m.mvp[0]; r.part[i].mvp[1] = (int16_t)m.mvp[1];
                 r.part[i].ref = (int8_t)m.i_ref; r.part[i].i_pixel = (int8_t)m.i_pixel;
                 r.part[i].xoff = (int8_t)m.xoff; r.part[i].yoff = (int8_t)m.yoff;
             }
+        }
+        else if (SUB8 && type != MB_P_SKIP && !no_parts)
+        {
+            // P_8x8: up to 16 MV-carrying blocks, in the order the reference costs them (analyse.c:3546-3606); they go to the
+            // side array (the first four are mirrored into the record)
+            int np = 0;
+            PartInfo *sp = c.fp.subparts ? c.fp.subparts + (size_t)16 * c.mb_xy : nullptr;
+#pragma unroll 1
+            for (int i = 0; i < 4; i++)
+            {
+                const int kind = a.sub[i];
+                const SubSlot *ss = sub_slots(c.w, i) + sub_first(kind);
+#pragma unroll 1
+                for (int j = 0; j < sub_count(kind); j++)
+                {
+                    PartInfo pi;
+                    if (kind == SUB_8x8)
+                    {
+                        const MeSlot &m = a.me8x8[i];
+                        pi.mv[0] = (int16_t)m.r.mv[0]; pi.mv[1] = (int16_t)m.r.mv[1];
+                        pi.mvp[0] = (int16_t)m.mvp[0]; pi.mvp[1] = (int16_t)m.mvp[1];
+                    }
+                    else
+                    {
+                        pi.mv[0] = ss[j].mv[0]; pi.mv[1] = ss[j].mv[1]; pi.mvp[0] = ss[j].mvp[0]; pi.mvp[1] = ss[j].mvp[1];
+                    }
+                    pi.ref = (int8_t)a.me8x8[i].i_ref; pi.i_pixel = (int8_t)sub_pixel(kind);
+                    pi.xoff = (int8_t)(8 * (i & 1) + sub_xoff(kind, j)); pi.yoff = (int8_t)(8 * (i >> 1) + sub_yoff(kind, j));
+                    if (np < 4) r.part[np] = pi;
+                    if (sp) sp[np] = pi;
+                    np++;
+                }
+            }
+            r.n_part = (int8_t)np;
         }
         r.n_log = c.n_log;
         r.pskip_mv[0] = (int16_t)c.pskip_mv[0]; r.pskip_mv[1] = (int16_t)c.pskip_mv[1];
@@ -802,9 +991,11 @@ PCAMV_DEV void wait_prev_raster(const MbCtx &c)
 
 // One macroblock of a P slice.  `prev_mv` = the 16 cache MVs left behind by the previous MB in raster order
 // (needed only for the pass-2 "forced skip without cache update" quirk, analyse.c:2668-2676).
-template <int XS>
+// F: feature mask of the instantiation — bit 0 = exhaustive searches (--me esa / tesa), bit 1 = sub-8x8 partitions
+template <int F>
 PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
 {
+    constexpr int XS = F & 1, SUB8 = (F >> 1) & 1;
     const DevFrameCtx &fc = c.fc;
     MbAnalysis &a = c.w.an;
     c.n_log = 0;
@@ -831,15 +1022,15 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     if (b_skip)
     {
         // (subme < 3 only) the reference takes this MB as P_SKIP before any search; pass 2 cannot override it
-        update_cache(c, a, MB_P_SKIP, PART_16x16);
-        finalize_mb(c, a, MB_P_SKIP, PART_16x16, 1);
+        update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
+        finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, 1);
         return;
     }
     early_skip = analyse_p16x16<XS>(c, a, 1, b_try_pskip);
     if (early_skip)
     {
         type = MB_P_SKIP;
-        update_cache(c, a, MB_P_SKIP, PART_16x16);
+        update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
     }
     if (forced)
     {
@@ -857,20 +1048,21 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
 #pragma unroll 1
             for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = PCAMV_LDV(prev_mv + i);
         }
-        finalize_mb(c, a, MB_P_SKIP, PART_16x16, early_skip);
+        finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, early_skip);
         return;
     }
 
     if (forced && forced->used && fc.pass2_elide)
     {
         // pass 2, decision forced from pass 1: nothing the remaining searches produce survives analyse.c:2868-2991
-        type = forced->type; partition = forced->partition;
+        // (info.cache[].i_partition is only written for P_L0, analyse.c:3612: a forced P_8x8 is 8x8 by construction)
+        type = forced->type; partition = forced->type == MB_P_8x8 ? PART_8x8 : forced->partition;
 #pragma unroll 1
         for (int i = 0; i < 4; i++)
             cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
 #pragma unroll 1
         for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
-        finalize_mb(c, a, type, -partition, 0);
+        finalize_mb<SUB8>(c, a, type, -partition, 0);
         return;
     }
 
@@ -879,27 +1071,54 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     if (psub16)
         analyse_p8x8<XS>(c, a);
     int i_cost = a.me16x16.r.cost;
-    // (with X264_ANALYSE_PSUB8x8 the reference would go on to P_8x8 / sub-partitions here; pcamv_open rejects that flag)
+    if (SUB8 && psub16 && (flags & 0x20) && a.cost8x8 < a.me16x16.r.cost)
+    {
+        // X264_ANALYSE_PSUB8x8: P_8x8 becomes the incumbent and every 8x8 block may split further (analyse.c:2697-2731)
+        type = MB_P_8x8; partition = PART_8x8;
+        i_cost = a.cost8x8;
+#pragma unroll 1
+        for (int i = 0; i < 4; i++)
+        {
+            const int c4x4 = analyse_sub8x8<XS>(c, a, i, SUB_4x4);
+            if (c4x4 < a.me8x8[i].r.cost)
+            {
+                int best8 = c4x4;
+                a.sub[i] = SUB_4x4;
+                const int c8x4 = analyse_sub8x8<XS>(c, a, i, SUB_8x4);
+                if (c8x4 < best8) { best8 = c8x4; a.sub[i] = SUB_8x4; }
+                const int c4x8 = analyse_sub8x8<XS>(c, a, i, SUB_4x8);
+                if (c4x8 < best8) { best8 = c4x8; a.sub[i] = SUB_4x8; }
+                i_cost += best8 - a.me8x8[i].r.cost;
+            }
+            cache_mv_p8x8(c, a, i);
+        }
+        a.cost8x8 = i_cost;
+    }
     if (psub16)
     {
         const int thresh16x8 = a.me8x8[1].r.cost_mv + a.me8x8[2].r.cost_mv;
         if (a.cost8x8 < a.me16x16.r.cost + thresh16x8)
         {
             analyse_p16x8_8x16<XS>(c, a, 0);
-            if (a.cost16x8 < i_cost) { i_cost = a.cost16x8; partition = PART_16x8; }
+            if (a.cost16x8 < i_cost) { i_cost = a.cost16x8; type = MB_P_L0; partition = PART_16x8; }
             analyse_p16x8_8x16<XS>(c, a, 1);
-            if (a.cost8x16 < i_cost) { i_cost = a.cost8x16; partition = PART_8x16; }
+            if (a.cost8x16 < i_cost) { i_cost = a.cost8x16; type = MB_P_L0; partition = PART_8x16; }
         }
     }
     c.partition = partition;
     if (partition == PART_16x16) run_refine(c, a.me16x16);
     else if (partition == PART_16x8) { run_refine(c, a.me16x8[0]); run_refine(c, a.me16x8[1]); }
-    else { run_refine(c, a.me8x16[0]); run_refine(c, a.me8x16[1]); }
+    else if (partition == PART_8x16) { run_refine(c, a.me8x16[0]); run_refine(c, a.me8x16[1]); }
+    else if (SUB8)
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) refine_sub8x8(c, a, i);
 
     if (forced && forced->used)
     {
-        // pass 2: type / partition / refs / MVs come from pass 1 with the embedding flips applied
-        type = forced->type; partition = forced->partition;
+        // pass 2: type / partition / refs / MVs come from pass 1 with the embedding flips applied; for P_8x8 the reference
+        // forces the sub-partition types and leaves h->mb.i_partition as this pass decided it (analyse.c:2872-2890)
+        type = forced->type;
+        if (type != MB_P_8x8) partition = forced->partition;
 #pragma unroll 1
         for (int i = 0; i < 4; i++)
             cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
@@ -908,8 +1127,8 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
         // the analysis slots keep the searched values; neighbours only ever see the cache
     }
     else
-        update_cache(c, a, type, partition);
-    finalize_mb(c, a, type, partition, 0);
+        update_cache<SUB8>(c, a, type, partition);
+    finalize_mb<SUB8>(c, a, type, partition, 0);
 }
 
 } // namespace pcamv

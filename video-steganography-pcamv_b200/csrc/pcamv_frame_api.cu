@@ -13,7 +13,7 @@ using namespace pcamv;
 namespace pcamv {
 void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_rows, int rows_per_cta, void *stream);
 void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream);
-void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, int exhaustive, void *stream);
+void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, const DevFrameCtx &fc, void *stream);
 void launch_cost_table_batch(const BatchItem *items, int n_items, int n_mb, void *stream);
 }
 
@@ -42,6 +42,11 @@ static int ensure_frame_buffers(pcamv_ctx *ctx)
     CK(cudaMalloc(&ctx->d_mb_results, n_mb * sizeof(MbResult)));
     CK(cudaMalloc(&ctx->d_progress, (fc.mb_h + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->d_trace, 2 * n_mb * sizeof(unsigned long long)));
+    if (fc.analyse_inter & 0x20)
+    {
+        CK(cudaMalloc(&ctx->d_subparts, 16 * n_mb * sizeof(PartInfo)));
+        CK(cudaMemsetAsync(ctx->d_subparts, 0, 16 * n_mb * sizeof(PartInfo), ctx->stream));
+    }
     if (fc.me_method == PCAMV_ME_TESA)
     {
         // every position of the widest window can end up in a team's list (reference: h->scratch_buffer)
@@ -71,8 +76,6 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
     if (!fc.tab.cost_mv || !fc.tab.quant4_mf[0]) return ctx_fail(ctx, "pcamv_frame_upload: pcamv_set_qp_tables has not been called", cudaSuccess);
     if (fc.subme < 1 || fc.subme > 5)
         return ctx_fail(ctx, "pcamv_frame_upload: frame analysis supports subpel_refine 1..5 (RD mode decision is raster-serial)", cudaSuccess);
-    if (fc.analyse_inter & 0x20)
-        return ctx_fail(ctx, "pcamv_frame_upload: sub-8x8 partitions (X264_ANALYSE_PSUB8x8) are not supported", cudaSuccess);
     if (fc.me_method < PCAMV_ME_DIA || fc.me_method > PCAMV_ME_TESA)
         return ctx_fail(ctx, "pcamv_frame_upload: me_method must be dia/hex/umh/esa/tesa", cudaSuccess);
     if (in->pass < 0 || in->pass > 2 || in->n_ref < 1 || in->n_ref > ctx->cfg.max_refs)
@@ -126,6 +129,7 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
         fp.stale_mv[i] = ((uint32_t)(uint16_t)in->stale_mv[i][0]) | ((uint32_t)(uint16_t)in->stale_mv[i][1] << 16);
     fp.cur = ctx->fa;
     fp.mvsads = ctx->d_mvsads; fp.mvsads_cap = ctx->mvsads_cap;
+    fp.subparts = ctx->d_subparts;
     fp.log = ctx->d_log; fp.log_stride = ctx->log_stride; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
     if (in->pass == 1) ctx->frame_cost_table = in->cost_table != 0;
     ctx->frame_last = in->pass;
@@ -248,7 +252,7 @@ extern "C" int pcamv_analyse_p(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_m
 extern "C" int pcamv_set_pass2_elide(pcamv_ctx *ctx, int on)
 {
     GUARD();
-    ctx->fc.pass2_elide = on != 0;
+    ctx->fc.pass2_elide = on != 0 && !(ctx->fc.analyse_inter & 0x20);
     return 0;
 }
 
@@ -280,7 +284,7 @@ static int batch_check(pcamv_ctx *const *ctxs, int n, int pass)
         pcamv_ctx *c = ctxs[i];
         if (!c || c->failed) return ctx_fail(ctx, "batch: a member context is null or failed", cudaSuccess);
         if (c->cfg.device != ctx->cfg.device || c->fc.mb_w != ctx->fc.mb_w || c->fc.mb_h != ctx->fc.mb_h ||
-            c->fc.me_method != ctx->fc.me_method || c->fc.subme != ctx->fc.subme)
+            c->fc.me_method != ctx->fc.me_method || c->fc.subme != ctx->fc.subme || c->fc.analyse_inter != ctx->fc.analyse_inter)
             return ctx_fail(ctx, "batch: member contexts must share device, geometry and search configuration", cudaSuccess);
         if (!c->frame_ready[pass]) return ctx_fail(ctx, "batch: a member context has no frame uploaded for that pass", cudaSuccess);
         for (int k = 0; k < i; k++)
@@ -329,7 +333,7 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
     CK(cudaMemcpyAsync(ctx->d_batch, ctx->h_batch, n * sizeof(BatchItem), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_batch_claim, 0, n * sizeof(int), ctx->stream));
     if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
-    launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta, ctx->batch_max_ctas, fc.me_method >= PCAMV_ME_ESA, ctx->stream);
+    launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta, ctx->batch_max_ctas, fc, ctx->stream);
     ctx->launches += 1;
     if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
     if (cost_table)

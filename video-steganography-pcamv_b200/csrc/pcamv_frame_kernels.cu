@@ -185,50 +185,31 @@ __global__ void __launch_bounds__(AP_WARPS * 32, PCAMV_BATCH_MIN_CTAS * 4 / AP_W
 
 // rows_per_cta: 1 = every row on its own SM (lowest latency for a single encoder), 4 = four consecutive rows share a
 // CTA and its L1 (higher throughput when many encoder contexts run concurrently)
-// XS = 1 instantiations carry the exhaustive searches (--me esa / tesa), XS = 0 the pattern searches only
+// feature mask of the instantiation: bit 0 = exhaustive searches (--me esa / tesa), bit 1 = sub-8x8 partitions; the default
+// configuration runs the leanest kernel (code that is merely present in the call graph costs registers and layout)
+#define PCAMV_DISPATCH_F(f, CALL) do { switch (f) { case 0: { constexpr int F_ = 0; CALL; } break; case 1: { constexpr int F_ = 1; CALL; } break; \
+                                                     case 2: { constexpr int F_ = 2; CALL; } break; default: { constexpr int F_ = 3; CALL; } break; } } while (0)
+static int feature_mask(const DevFrameCtx &fc) { return (fc.me_method >= ME_ESA ? 1 : 0) | ((fc.analyse_inter & 0x20) ? 2 : 0); }
 void launch_analyse_p(const DevFrameCtx &fc, const FrameParams &fp, int *row_claim, int n_rows, int rows_per_cta, void *stream)
 {
     const cudaStream_t st = (cudaStream_t)stream;
-    const bool xs = fc.me_method >= ME_ESA;
-    if (rows_per_cta >= 4)
-    {
-        if (xs) k_analyse_p<4, 1><<<(n_rows + 3) / 4, 128, 0, st>>>(fc, fp, row_claim);
-        else    k_analyse_p<4, 0><<<(n_rows + 3) / 4, 128, 0, st>>>(fc, fp, row_claim);
-    }
-    else if (rows_per_cta >= 2)
-    {
-        if (xs) k_analyse_p<2, 1><<<(n_rows + 1) / 2, 64, 0, st>>>(fc, fp, row_claim);
-        else    k_analyse_p<2, 0><<<(n_rows + 1) / 2, 64, 0, st>>>(fc, fp, row_claim);
-    }
-    else
-    {
-        if (xs) k_analyse_p<1, 1><<<n_rows, 32, 0, st>>>(fc, fp, row_claim);
-        else    k_analyse_p<1, 0><<<n_rows, 32, 0, st>>>(fc, fp, row_claim);
-    }
+    const int f = feature_mask(fc);
+    if (rows_per_cta >= 4)      PCAMV_DISPATCH_F(f, (k_analyse_p<4, F_><<<(n_rows + 3) / 4, 128, 0, st>>>(fc, fp, row_claim)));
+    else if (rows_per_cta >= 2) PCAMV_DISPATCH_F(f, (k_analyse_p<2, F_><<<(n_rows + 1) / 2, 64, 0, st>>>(fc, fp, row_claim)));
+    else                        PCAMV_DISPATCH_F(f, (k_analyse_p<1, F_><<<n_rows, 32, 0, st>>>(fc, fp, row_claim)));
 }
 
-// next_group: n_items counters, zeroed by the caller; all items share one search method (checked by the caller)
-void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, int exhaustive, void *stream)
+// next_group: n_items counters, zeroed by the caller; all items share one configuration (checked by the caller)
+void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim, int n_rows, int rows_per_cta, int max_ctas, const DevFrameCtx &fc, void *stream)
 {
     const cudaStream_t st = (cudaStream_t)stream;
+    const int f = feature_mask(fc);
     const int w = rows_per_cta >= 4 ? 4 : rows_per_cta >= 2 ? 2 : 1;
     int ctas = n_items * ((n_rows + w - 1) / w);
     if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
-    if (w == 4)
-    {
-        if (exhaustive) k_analyse_p_batch<4, 1><<<ctas, 128, 0, st>>>(items, n_items, row_claim);
-        else            k_analyse_p_batch<4, 0><<<ctas, 128, 0, st>>>(items, n_items, row_claim);
-    }
-    else if (w == 2)
-    {
-        if (exhaustive) k_analyse_p_batch<2, 1><<<ctas, 64, 0, st>>>(items, n_items, row_claim);
-        else            k_analyse_p_batch<2, 0><<<ctas, 64, 0, st>>>(items, n_items, row_claim);
-    }
-    else
-    {
-        if (exhaustive) k_analyse_p_batch<1, 1><<<ctas, 32, 0, st>>>(items, n_items, row_claim);
-        else            k_analyse_p_batch<1, 0><<<ctas, 32, 0, st>>>(items, n_items, row_claim);
-    }
+    if (w == 4)      PCAMV_DISPATCH_F(f, (k_analyse_p_batch<4, F_><<<ctas, 128, 0, st>>>(items, n_items, row_claim)));
+    else if (w == 2) PCAMV_DISPATCH_F(f, (k_analyse_p_batch<2, F_><<<ctas, 64, 0, st>>>(items, n_items, row_claim)));
+    else             PCAMV_DISPATCH_F(f, (k_analyse_p_batch<1, F_><<<ctas, 32, 0, st>>>(items, n_items, row_claim)));
 }
 
 // ---- cost table: one lane team per macroblock; macroblocks are independent -------------------------------

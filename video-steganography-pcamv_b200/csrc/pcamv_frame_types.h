@@ -64,6 +64,8 @@ struct FrameParams
     LogEntry *log;           // [n_mb][log_stride]
     int log_stride;          // entries per macroblock (pcamv_log_stride)
     MbResult *results;       // [n_mb]
+    PartInfo *subparts;      // [n_mb][16], P_8x8 macroblocks only (X264_ANALYSE_PSUB8x8), else null: the up to 16 MV-carrying
+                             // blocks of the final mode in the reference's cost-table order (device-internal, not in the ABI)
     int *row_progress;       // [mb_h] wavefront counters
     unsigned long long *mvsads;  // --me tesa: [mb_h][mvsads_cap] candidate lists, one per macroblock row (= per lane team), else null
     int mvsads_cap;

@@ -73,13 +73,41 @@ static inline int build_forced(int n_mb, const Pass1Mb *in, const int8_t *filp, 
                 }
             }
         }
-        else if (p.type == 5)                    // P_8x8 with unsplit 8x8 blocks: slots 4*i (analyse.c:2944-2955, 3017-3023)
+        else if (p.type == 5)                    // P_8x8: per 8x8 block by its split (analyse.c:2944-2978, 3005-3052)
         {
             for (int i8 = 0; i8 < 4; i8++)
             {
-                const int16_t *mv = filp[n++] == 1 ? p.mv_stego[4 * i8] : p.mv[4 * i8];
                 o.ref[i8] = p.ref[4 * i8];
-                for (int i = 0; i < 4; i++) o.mv[4 * i8 + i] = glue_pack(mv);
+                const int kind = p.sub[i8];      // D_L0_4x4 = 0, D_L0_8x4 = 1, D_L0_4x8 = 2, D_L0_8x8 = 3
+                if (kind == 3)
+                {
+                    const int16_t *mv = filp[n++] == 1 ? p.mv_stego[4 * i8] : p.mv[4 * i8];
+                    for (int i = 0; i < 4; i++) o.mv[4 * i8 + i] = glue_pack(mv);
+                }
+                else if (kind == 2)              // 4x8: slots 4i, 4i+1 = left / right column
+                {
+                    for (int j = 0; j < 2; j++)
+                    {
+                        const int16_t *mv = filp[n++] == 1 ? p.mv_stego[4 * i8 + j] : p.mv[4 * i8 + j];
+                        o.mv[4 * i8 + j] = o.mv[4 * i8 + j + 2] = glue_pack(mv);
+                    }
+                }
+                else if (kind == 1)              // 8x4: slots 4i, 4i+2 = top / bottom row
+                {
+                    for (int j = 0; j < 2; j++)
+                    {
+                        const int16_t *mv = filp[n++] == 1 ? p.mv_stego[4 * i8 + 2 * j] : p.mv[4 * i8 + 2 * j];
+                        o.mv[4 * i8 + 2 * j] = o.mv[4 * i8 + 2 * j + 1] = glue_pack(mv);
+                    }
+                }
+                else                             // 4x4: slots 4i .. 4i+3
+                {
+                    for (int j = 0; j < 4; j++)
+                    {
+                        const int16_t *mv = filp[n++] == 1 ? p.mv_stego[4 * i8 + j] : p.mv[4 * i8 + j];
+                        o.mv[4 * i8 + j] = glue_pack(mv);
+                    }
+                }
             }
         }
     }

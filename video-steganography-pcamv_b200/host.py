@@ -43,7 +43,7 @@ ME_CALL_DTYPE = np.dtype([
     ("cost_in", "<i4"), ("cost_mv_in", "<i4")], align=True)
 ME_RESULT_DTYPE = np.dtype([("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4"), ("thresh_out", "<i4")], align=True)
 
-LOG_MAX = 48
+LOG_MAX = 112
 LOG_ENTRY_DTYPE = np.dtype([("kind", "i1"), ("i_pixel", "i1"), ("i_ref", "i1"), ("pad", "i1"), ("mv", "<i2", 2),
                             ("cost", "<i4"), ("cost_mv", "<i4")], align=True)
 MB_OUT_DTYPE = np.dtype([("type", "i1"), ("partition", "i1"), ("n_part", "i1"), ("early_skip", "i1"), ("ref", "i1", 4),

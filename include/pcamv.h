@@ -145,7 +145,8 @@ int pcamv_put_ref(pcamv_ctx *ctx, int slot, int poc, const uint8_t *y, const uin
 int pcamv_put_ref_planes(pcamv_ctx *ctx, int slot, int poc, const uint8_t *const luma_padded[4],
                          const uint8_t *u_padded, const uint8_t *v_padded);
 /* Copy one device plane of a slot back (padded buffer, same layout as above).  plane: 0..3 luma
- * (integer, H, V, HV), 4 = U, 5 = V.  dst must hold pcamv_plane_bytes(). */
+ * (integer, H, V, HV), 4 = U, 5 = V, 6 = the integral plane (--me esa / tesa contexts only: uint16 8x8 box sums, same
+ * geometry as a luma plane, reference common/mc.c:311-345).  dst must hold pcamv_plane_bytes(). */
 int pcamv_get_ref_plane(pcamv_ctx *ctx, int slot, int plane, uint8_t *dst);
 size_t pcamv_plane_bytes(const pcamv_ctx *ctx, int plane);
 int pcamv_plane_stride(const pcamv_ctx *ctx, int plane);

@@ -135,3 +135,27 @@ def test_put_ref_planes_equal_plain_c_oracle(pcamv, cuda_lib, w, h, mode):
         lib.pcamv_oracle_chroma_border(C.c_void_p(c.ctypes.data + 16 * Sc + 16), Sc, w // 2, h // 2)
         assert np.array_equal(ctx.get_ref_plane(0, k)[:, :w // 2 + 32], c[:, :w // 2 + 32]), "chroma plane %d" % k
     ctx.close()
+
+
+def test_integral_plane_matches_oracle(pcamv, cuda_lib, tmp_path):
+    """A11: the integral plane k_box_sum8 builds for the exhaustive searches equals the restatement of the reference's
+    integral_init8h / 8v chain (oracle/leaf_oracle.c, pinned against the reference's own functions in test_oracle_leaf.py)
+    wherever the reference defines it: every 8x8 box inside the padded plane."""
+    import ctypes as C
+    import test_oracle_leaf
+    lib = test_oracle_leaf.build_oracle_lib()
+    dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path("qcif_esa5", str(tmp_path)))
+    s = next(x for x in dump.slices() if x.with_planes)
+    ctx = open_ctx(pcamv, dump, s)
+    r = s.refs[0]
+    H, W = s.lines_y, s.width
+    ctx.put_ref(0, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2], r["v"][16:16 + H // 2, 16:16 + W // 2])
+    got = ctx.get_integral(0)
+    plane = np.ascontiguousarray(r["luma"][0])
+    rows, stride = plane.shape
+    assert got.shape == (rows, stride)
+    want = np.zeros((rows + 1, stride), dtype=np.uint16)
+    lib.pcamv_oracle_integral8(C.c_void_p(plane.ctypes.data), C.c_void_p(want.ctypes.data), stride, rows)
+    assert np.array_equal(got[:rows - 8, :stride - 8], want[:rows - 8, :stride - 8])
+    assert got[:rows - 8, :stride - 8].max() > 1000
+    ctx.close()

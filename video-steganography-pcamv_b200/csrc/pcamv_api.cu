@@ -271,22 +271,24 @@ extern "C" int pcamv_put_ref_planes(pcamv_ctx *ctx, int slot, int poc, const uin
 
 extern "C" size_t pcamv_plane_bytes(const pcamv_ctx *ctx, int plane)
 {
-    if (!ctx || plane < 0 || plane > 5) return 0;
+    if (!ctx || plane < 0 || plane > 6) return 0;
+    if (plane == 6) return ctx->fc.me_method >= PCAMV_ME_ESA ? ctx->luma_bytes * sizeof(uint16_t) : 0;
     return plane < 4 ? ctx->luma_bytes : ctx->chroma_bytes;
 }
 
 extern "C" int pcamv_plane_stride(const pcamv_ctx *ctx, int plane)
 {
-    if (!ctx || plane < 0 || plane > 5) return 0;
+    if (!ctx || plane < 0 || plane > 6) return 0;
+    if (plane == 6) return ctx->fc.stride_y * (int)sizeof(uint16_t);
     return plane < 4 ? ctx->fc.stride_y : ctx->fc.stride_c;
 }
 
 extern "C" int pcamv_get_ref_plane(pcamv_ctx *ctx, int slot, int plane, uint8_t *dst)
 {
     GUARD();
-    if (slot < 0 || slot >= ctx->cfg.max_refs + 2 || plane < 0 || plane > 5 || !dst)
+    if (slot < 0 || slot >= ctx->cfg.max_refs + 2 || plane < 0 || plane > 6 || !dst || (plane == 6 && !ctx->d_integral[slot]))
         return fail(ctx, "pcamv_get_ref_plane: bad argument", cudaSuccess);
-    const uint8_t *src = ctx->d_ref[slot] + (plane < 4 ? plane * ctx->luma_bytes : 4 * ctx->luma_bytes + (plane - 4) * ctx->chroma_bytes);
+    const uint8_t *src = plane == 6 ? (const uint8_t *)ctx->d_integral[slot] : ctx->d_ref[slot] + (plane < 4 ? plane * ctx->luma_bytes : 4 * ctx->luma_bytes + (plane - 4) * ctx->chroma_bytes);
     CK(cudaMemcpyAsync(dst, src, pcamv_plane_bytes(ctx, plane), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -238,6 +238,12 @@ class PcamvContext:
         self._check(self.lib.pcamv_get_ref_plane(self.handle, slot, plane, _ptr(out)))
         return out.reshape(-1, self.plane_stride(plane))
 
+    def get_integral(self, slot):
+        """The integral plane of a slot (--me esa / tesa contexts): uint16 [rows, stride_y]."""
+        out = np.empty(self.plane_bytes(6), dtype=np.uint8)
+        self._check(self.lib.pcamv_get_ref_plane(self.handle, slot, 6, _ptr(out)))
+        return out.view(np.uint16).reshape(-1, self.plane_stride(0))
+
     # -- search seam ------------------------------------------------------------------------------
     def me_search_batch(self, calls):
         calls = np.ascontiguousarray(calls, dtype=ME_CALL_DTYPE)

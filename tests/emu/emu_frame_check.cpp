@@ -52,7 +52,7 @@ int main(int argc, char **argv)
     MbWork work;
     // checker-side integral planes (8x8 box sums of the padded integer plane, what k_box_sum8 builds on the GPU) and the
     // --me tesa candidate list of the single emulated team
-    std::vector<std::vector<uint16_t>> integral(PCAMV_MAX_REFS);
+    std::vector<std::vector<uint16_t>> integral(PCAMV_MAX_REFS), integral4(PCAMV_MAX_REFS);
     std::vector<unsigned long long> mvsads((size_t)(2 * fc.me_range + 4) * (2 * fc.me_range + 1));
 
     long n_call = 0, bad_call = 0, n_mbs = 0, bad_mb = 0, n_ih = 0, bad_ih = 0, n_passes = 0;
@@ -78,7 +78,23 @@ int main(int argc, char **argv)
             DevRef &r = fc.ref[i];
             for (int k = 0; k < 4; k++) r.y[k] = (uint8_t *)sp.refs[i].y[k];
             r.u = (uint8_t *)sp.refs[i].u; r.v = (uint8_t *)sp.refs[i].v; r.valid = 1;
-            r.integral = nullptr;
+            r.integral = nullptr; r.integral4 = nullptr;
+            if (fc.me_method >= ME_ESA && (fc.analyse_inter & 0x20))
+            {
+                const int st = fc.stride_y, rows = sp.hd.lines_y + 64;
+                const uint8_t *base = sp.refs[i].y[0] - (size_t)st * 32 - 32;
+                std::vector<uint16_t> &sum = integral4[i];
+                sum.assign((size_t)st * rows, 0);
+                for (int y = 0; y + 4 <= rows; y++)
+                    for (int x = 0; x + 4 <= st; x++)
+                    {
+                        int a = 0;
+                        for (int yy = 0; yy < 4; yy++)
+                            for (int xx = 0; xx < 4; xx++) a += base[(size_t)(y + yy) * st + x + xx];
+                        sum[(size_t)y * st + x] = (uint16_t)a;
+                    }
+                r.integral4 = sum.data() + (size_t)st * 32 + 32;
+            }
             if (fc.me_method >= ME_ESA)
             {
                 const int st = fc.stride_y, rows = sp.hd.lines_y + 64;

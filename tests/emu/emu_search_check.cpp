@@ -5,6 +5,8 @@
 #define PCAMV_EMU 1
 #include "../../video-steganography-pcamv_b200/csrc/pcamv_me.cuh"
 #include "dump_reader.h"
+#include <map>
+#include <vector>
 
 using namespace pcamv;
 
@@ -56,6 +58,37 @@ int main(int argc, char **argv)
         for (int k = 0; k < 4; k++) b.ref[k] = rf.y[k] + off;
         const size_t offc = (size_t)(8 * c.mb_y + (c.yoff >> 1)) * b.stride_c + 8 * c.mb_x + (c.xoff >> 1);
         b.ref_u = rf.u + offc; b.ref_v = rf.v + offc;
+        if (c.me_method >= ME_ESA)
+        {
+            // checker-side integral planes of this reference (8x8 and 4x4 box sums of the padded plane), built on first use
+            static std::map<const uint8_t *, std::pair<std::vector<uint16_t>, std::vector<uint16_t>>> sums;
+            auto it = sums.find(rf.y[0]);
+            if (it == sums.end())
+            {
+                const int st = b.stride, rows = sp.hd.lines_y + 64;
+                const uint8_t *base = rf.y[0] - (size_t)st * 32 - 32;
+                auto &pr = sums[rf.y[0]];
+                for (int n = 8; n >= 4; n -= 4)
+                {
+                    std::vector<uint16_t> &sum = n == 8 ? pr.first : pr.second;
+                    sum.assign((size_t)st * rows, 0);
+                    for (int y = 0; y + n <= rows; y++)
+                        for (int x = 0; x + n <= st; x++)
+                        {
+                            int a = 0;
+                            for (int yy = 0; yy < n; yy++)
+                                for (int xx = 0; xx < n; xx++) a += base[(size_t)(y + yy) * st + x + xx];
+                            sum[(size_t)y * st + x] = (uint16_t)a;
+                        }
+                }
+                it = sums.find(rf.y[0]);
+            }
+            b.integral = it->second.first.data() + (size_t)b.stride * 32 + 32 + off;
+            b.integral4 = it->second.second.data() + (size_t)b.stride * 32 + 32 + off;
+            static std::vector<unsigned long long> mvsads;
+            mvsads.resize((size_t)(2 * c.me_range + 4) * (2 * c.me_range + 1));
+            env.mvsads = mvsads.data();
+        }
         block_set_mvp(b, env, c.mvp[0], c.mvp[1]);
 
         MeResult m; int thresh = c.thresh_in;

@@ -24,7 +24,7 @@ def run_checker(checker, dump):
     return calls
 
 
-@pytest.mark.parametrize("name", ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"])
+@pytest.mark.parametrize("name", ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_tesa5", "qcif_dia2_lownoise"])
 def test_golden_calls(checker, name, tmp_path):
     assert run_checker(checker, refrun.golden_dump_path(name, str(tmp_path))) > 1000
 
@@ -36,6 +36,7 @@ LIVE = [
     ("--me dia --subme 1 --ref 1", "1:3"),
     ("--me hex --subme 3 --ref 2 --partitions all --mixed-refs", "2:4"),
     ("--me esa --merange 24 --subme 4 --ref 1", "1:2"),
+    ("--me tesa --merange 16 --subme 5 --ref 1 --partitions all", "1:2"),      # ADS on the 8x8 and the 4x4 integral planes
 ]
 
 

@@ -36,6 +36,7 @@ def test_frame_analysis_matches_reference(pcamv, cuda_lib, name, tmp_path):
     ("--me tesa --merange 24 --subme 4 --ref 2", "2:3", (352, 288)),
     ("--me hex --subme 5 --ref 1 --partitions p8x8,p4x4", "1:3", (352, 288)),      # sub-8x8 partitions
     ("--me umh --subme 5 --ref 2 --partitions all", "2:4", (352, 288)),
+    ("--me tesa --merange 16 --subme 5 --ref 1 --partitions p8x8,p4x4", "1:2", (352, 288)),      # 4x4 integral plane
 ])
 def test_frame_analysis_live_reference(pcamv, cuda_lib, args, frames, size, tmp_path):
     w, h = size

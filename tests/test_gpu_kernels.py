@@ -8,7 +8,7 @@ import refrun
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"]
+GOLDEN = ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_tesa5", "qcif_dia2_lownoise"]
 
 
 def open_ctx(pcamv, dump, slice_):
@@ -91,6 +91,8 @@ def test_search_calls_match_reference(pcamv, cuda_lib, name, tmp_path):
     ("--me umh --subme 5 --ref 1", "1:3", (352, 288)),
     ("--me hex --subme 5 --ref 3 --partitions all --mixed-refs", "3:5", (352, 288)),
     ("--me umh --subme 5 --ref 1", "1:2", (1280, 720)),
+    ("--me tesa --merange 16 --subme 5 --ref 1 --partitions all", "1:2", (352, 288)),     # tesa through the search seam, both integral planes
+    ("--me esa --merange 24 --subme 4 --ref 2 --partitions all", "2:3", (352, 288)),
 ])
 def test_search_calls_live_reference(pcamv, cuda_lib, args, frames, size, tmp_path):
     w, h = size

@@ -124,12 +124,18 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
             r.y[k] = ctx->d_ref[s] + k * ctx->luma_bytes + (size_t)fc.stride_y * PCAMV_PADV + PCAMV_PADH;
         r.u = ctx->d_ref[s] + 4 * ctx->luma_bytes + (size_t)fc.stride_c * (PCAMV_PADV / 2) + PCAMV_PADH / 2;
         r.v = r.u + ctx->chroma_bytes;
-        r.integral = nullptr; r.poc = -1; r.valid = 0;
+        r.integral = nullptr; r.integral4 = nullptr; r.poc = -1; r.valid = 0;
         if (fc.me_method >= PCAMV_ME_ESA)
         {
             OCK(cudaMalloc(&ctx->d_integral[s], ctx->luma_bytes * sizeof(uint16_t)));
             OCK(cudaMemsetAsync(ctx->d_integral[s], 0, ctx->luma_bytes * sizeof(uint16_t), ctx->stream));
             r.integral = ctx->d_integral[s] + (size_t)fc.stride_y * PCAMV_PADV + PCAMV_PADH;
+            if (fc.analyse_inter & 0x20)
+            {
+                OCK(cudaMalloc(&ctx->d_integral4[s], ctx->luma_bytes * sizeof(uint16_t)));
+                OCK(cudaMemsetAsync(ctx->d_integral4[s], 0, ctx->luma_bytes * sizeof(uint16_t), ctx->stream));
+                r.integral4 = ctx->d_integral4[s] + (size_t)fc.stride_y * PCAMV_PADV + PCAMV_PADH;
+            }
         }
     }
     OCK(cudaMalloc(&ctx->d_cost_mv, 32769 * sizeof(int16_t)));
@@ -146,12 +152,12 @@ extern "C" void pcamv_close(pcamv_ctx *ctx)
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_fenc);
-    for (int s = 0; s < PCAMV_SLOTS; s++) { cudaFree(ctx->d_ref[s]); cudaFree(ctx->d_integral[s]); }
+    for (int s = 0; s < PCAMV_SLOTS; s++) { cudaFree(ctx->d_ref[s]); cudaFree(ctx->d_integral[s]); cudaFree(ctx->d_integral4[s]); }
     cudaFree(ctx->d_cost_mv); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_calls); cudaFree(ctx->d_results);
     cudaFree(ctx->fa.type); cudaFree(ctx->fa.ref8); cudaFree(ctx->fa.mv4); cudaFree(ctx->fa.mvr);
     cudaFree(ctx->d_col_ref8); cudaFree(ctx->d_col_mv4); cudaFree(ctx->d_forced); cudaFree(ctx->d_log);
-    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_mvsads); cudaFree(ctx->d_subparts); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim);
+    cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_mvsads); cudaFree(ctx->d_seam_mvsads); cudaFree(ctx->d_subparts); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim);
     if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
     if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
     if (ctx->h_calls) cudaFreeHost(ctx->h_calls);
@@ -217,9 +223,14 @@ static int filter_slot(pcamv_ctx *ctx, int slot)
                          -PCAMV_PADV / 2, H / 2 + PCAMV_PADV / 2, ctx->stream);
     if (r.integral)
     {
-        launch_box_sum8(r.y[0] - (size_t)fc.stride_y * PCAMV_PADV - PCAMV_PADH, r.integral - (size_t)fc.stride_y * PCAMV_PADV - PCAMV_PADH,
-                        fc.stride_y, H + 2 * PCAMV_PADV, ctx->stream);
+        const size_t pad = (size_t)fc.stride_y * PCAMV_PADV + PCAMV_PADH;
+        launch_box_sum(r.y[0] - pad, r.integral - pad, fc.stride_y, H + 2 * PCAMV_PADV, 8, ctx->stream);
         ctx->launches += 1;
+        if (r.integral4)
+        {
+            launch_box_sum(r.y[0] - pad, r.integral4 - pad, fc.stride_y, H + 2 * PCAMV_PADV, 4, ctx->stream);
+            ctx->launches += 1;
+        }
     }
     launch_hpel_filter(r.y[0], r.y[1], r.y[2], r.y[3], fc.stride_y, W, H, ctx->stream);
     launch_expand_border(r.y[1], r.y[2], r.y[3], 3, fc.stride_y, -4, W + 4, -8, H + 8, -PCAMV_PADH, W + PCAMV_PADH,
@@ -260,8 +271,13 @@ extern "C" int pcamv_put_ref_planes(pcamv_ctx *ctx, int slot, int poc, const uin
     CK(cudaMemcpyAsync(base + 4 * ctx->luma_bytes + ctx->chroma_bytes, v_padded, ctx->chroma_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (r.integral)
     {
-        launch_box_sum8(base, ctx->d_integral[slot], ctx->fc.stride_y, ctx->fc.height + 2 * PCAMV_PADV, ctx->stream);
+        launch_box_sum(base, ctx->d_integral[slot], ctx->fc.stride_y, ctx->fc.height + 2 * PCAMV_PADV, 8, ctx->stream);
         ctx->launches += 1;
+        if (r.integral4)
+        {
+            launch_box_sum(base, ctx->d_integral4[slot], ctx->fc.stride_y, ctx->fc.height + 2 * PCAMV_PADV, 4, ctx->stream);
+            ctx->launches += 1;
+        }
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -310,11 +326,22 @@ static int ensure_batch(pcamv_ctx *ctx, int n)
     return 0;
 }
 
+// --me tesa through the stateless seam: calls are launched PCAMV_SEAM_CHUNK at a time, each with its own candidate list
+#define PCAMV_SEAM_CHUNK 2048
+static int seam_cap(const pcamv_ctx *ctx) { return (2 * ctx->fc.me_range + 4) * (2 * ctx->fc.me_range + 1); }
+static void run_search_batch(pcamv_ctx *ctx, int n)
+{
+    launch_search_batch(ctx->fc, ctx->d_calls, n, ctx->d_results, ctx->d_seam_mvsads, seam_cap(ctx), PCAMV_SEAM_CHUNK, ctx->stream);
+}
+
 static int check_calls(pcamv_ctx *ctx, const pcamv_me_call *calls, int n)
 {
     if (!ctx->fc.tab.cost_mv) return fail(ctx, "search: pcamv_set_qp_tables has not been called", cudaSuccess);
-    if (ctx->fc.me_method == PCAMV_ME_TESA)
-        return fail(ctx, "search: --me tesa is served by the frame seam only (pcamv_analyse_p)", cudaSuccess);
+    if (ctx->fc.me_method == PCAMV_ME_TESA && !ctx->d_seam_mvsads)
+    {
+        cudaError_t e = cudaMalloc(&ctx->d_seam_mvsads, (size_t)PCAMV_SEAM_CHUNK * seam_cap(ctx) * sizeof(unsigned long long));
+        if (e != cudaSuccess) return fail(ctx, "search: cudaMalloc of the --me tesa candidate lists", e);
+    }
     for (int i = 0; i < n; i++)
     {
         const pcamv_me_call &c = calls[i];
@@ -347,7 +374,7 @@ extern "C" int pcamv_me_batch_run(pcamv_ctx *ctx, int iters, float *ms_per_launc
     if (iters <= 0 || ctx->batch_n <= 0) return fail(ctx, "pcamv_me_batch_run: nothing to run", cudaSuccess);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int i = 0; i < iters; i++)
-        launch_search_batch(ctx->fc, ctx->d_calls, ctx->batch_n, ctx->d_results, ctx->stream);
+        run_search_batch(ctx, ctx->batch_n);
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaGetLastError());
     CK(cudaEventSynchronize(ctx->ev1));
@@ -374,7 +401,7 @@ extern "C" int pcamv_me_search_batch(pcamv_ctx *ctx, const pcamv_me_call *calls,
     if (n < 0 || (n && (!calls || !results))) return fail(ctx, "pcamv_me_search_batch: bad argument", cudaSuccess);
     if (n == 0) return 0;
     if (pcamv_me_batch_upload(ctx, calls, n)) return -1;
-    launch_search_batch(ctx->fc, ctx->d_calls, n, ctx->d_results, ctx->stream);
+    run_search_batch(ctx, n);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return pcamv_me_batch_download(ctx, results, n);

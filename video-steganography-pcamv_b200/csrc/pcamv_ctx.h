@@ -20,7 +20,7 @@ struct pcamv_ctx
     // HBM
     uint8_t *d_fenc = nullptr;                 // Y | U | V, strides = stride_y / stride_c
     uint8_t *d_ref[PCAMV_SLOTS] = {};          // per slot: 4 luma planes | U | V (+slack)
-    uint16_t *d_integral[PCAMV_SLOTS] = {};
+    uint16_t *d_integral[PCAMV_SLOTS] = {}, *d_integral4[PCAMV_SLOTS] = {};
     size_t luma_bytes = 0, chroma_bytes = 0, ref_bytes = 0;
     int16_t *d_cost_mv = nullptr;              // 32769
     uint8_t *d_tables = nullptr;               // cost_ref | quant mf/bias | dequant
@@ -41,6 +41,7 @@ struct pcamv_ctx
     int *d_batch_claim = nullptr;
     int batch_max_ctas = 0, batch_claim_cap = 0;   // persistent grid size of multi-context launches (0 = not yet computed)
     unsigned long long *d_mvsads = nullptr; int mvsads_cap = 0;    // --me tesa: per-row candidate lists
+    unsigned long long *d_seam_mvsads = nullptr;                   // --me tesa, stateless search seam: PCAMV_SEAM_CHUNK lists
     unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
     bool trace_on = false;
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter

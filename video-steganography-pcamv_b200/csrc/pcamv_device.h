@@ -17,7 +17,8 @@ struct DevRef
 {
     uint8_t *y[4];
     uint8_t *u, *v;
-    uint16_t *integral;     // --me esa / tesa only, else null: 8x8 box sums (k_box_sum8), same geometry as y[0], at pixel (0,0)
+    uint16_t *integral;     // --me esa / tesa only, else null: 8x8 box sums (k_box_sum), same geometry as y[0], at pixel (0,0)
+    uint16_t *integral4;    // 4x4 box sums, only when sub-8x8 partitions are searched exhaustively
     int poc;
     int valid;
 };
@@ -50,8 +51,9 @@ void launch_expand_border(uint8_t *p0, uint8_t *p1, uint8_t *p2, int nplanes, in
                           int pad_x0, int pad_x1, int pad_y0, int pad_y1, void *stream);
 void launch_hpel_filter(const uint8_t *src, uint8_t *dsth, uint8_t *dstv, uint8_t *dstc,
                         int stride, int width, int height, void *stream);
-void launch_box_sum8(const uint8_t *src_padded, uint16_t *dst_padded, int stride, int rows, void *stream);
-void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int n, pcamv_me_result *results, void *stream);
+void launch_box_sum(const uint8_t *src_padded, uint16_t *dst_padded, int stride, int rows, int box, void *stream);
+void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int n, pcamv_me_result *results,
+                         unsigned long long *mvsads, int mvsads_cap, int chunk, void *stream);
 
 void launch_int_peak(uint32_t *out, int blocks, int iters, void *stream);
 

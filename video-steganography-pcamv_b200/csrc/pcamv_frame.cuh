@@ -611,6 +611,7 @@ PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, i
     const ptrdiff_t offc = (ptrdiff_t)(8 * c.mb_y + (yoff >> 1)) * b.stride_c + 8 * c.mb_x + (xoff >> 1);
     b.ref_u = rf.u + offc; b.ref_v = rf.v + offc;
     b.integral = rf.integral ? rf.integral + off : nullptr;
+    b.integral4 = rf.integral4 ? rf.integral4 + off : nullptr;
 }
 
 template <int XS>

@@ -225,11 +225,14 @@ __device__ __forceinline__ void make_block(const DevFrameCtx &fc, MeBlock &b, in
     const ptrdiff_t offc = (ptrdiff_t)(8 * mb_y + (yoff >> 1)) * fc.stride_c + 8 * mb_x + (xoff >> 1);
     b.ref_u = rf.u + offc; b.ref_v = rf.v + offc;
     b.integral = rf.integral ? rf.integral + off : nullptr;
+    b.integral4 = rf.integral4 ? rf.integral4 + off : nullptr;
 }
 
+// mvsads: --me tesa candidate lists, one of mvsads_cap entries per call of this launch (null otherwise)
 __global__ void __launch_bounds__(SB_WARPS * 32) k_search_batch(const __grid_constant__ DevFrameCtx fc,
                                                                const pcamv_me_call *__restrict__ calls, int n,
-                                                               pcamv_me_result *__restrict__ results)
+                                                               pcamv_me_result *__restrict__ results,
+                                                               unsigned long long *mvsads, int mvsads_cap)
 {
     __shared__ __align__(16) uint8_t s_fenc[SB_WARPS][384];
     const int warp = threadIdx.x >> 5;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_search_batch(const __grid_con
     env.cost_mv_fpel[0] = env.cost_mv_fpel[1] = env.cost_mv_fpel[2] = env.cost_mv_fpel[3] = nullptr;
     env.me_method = fc.me_method; env.me_range = fc.me_range; env.subme = fc.subme; env.chroma_me = fc.chroma_me && fc.subme >= 5;
     env.mbcmp_satd = fc.subme > 1;
-    env.mvsads = nullptr;
+    env.mvsads = mvsads ? mvsads + (size_t)idx * mvsads_cap : nullptr;
 #pragma unroll
     for (int k = 0; k < 2; k++)
     {
@@ -280,10 +283,17 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_search_batch(const __grid_con
     }
 }
 
-void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int n, pcamv_me_result *results, void *stream)
+// with --me tesa the calls go out in chunks of `chunk` (what the scratch holds lists for), else in one launch
+void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int n, pcamv_me_result *results,
+                         unsigned long long *mvsads, int mvsads_cap, int chunk, void *stream)
 {
     if (n <= 0) return;
-    k_search_batch<<<(n + SB_WARPS - 1) / SB_WARPS, SB_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, calls, n, results);
+    if (!mvsads) chunk = n;
+    for (int at = 0; at < n; at += chunk)
+    {
+        const int m = n - at < chunk ? n - at : chunk;
+        k_search_batch<<<(m + SB_WARPS - 1) / SB_WARPS, SB_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, calls + at, m, results + at, mvsads, mvsads_cap);
+    }
 }
 
 // =====================================================================================================
@@ -294,22 +304,24 @@ void launch_search_batch(const DevFrameCtx &fc, const pcamv_me_call *calls, int 
 // 3-column overshoot inside the 32-pixel border) and are written as 0.  Horizontal 8-sums of a tile go through
 // shared memory, then 8 of them are added vertically: 1 byte read + 2 bytes written per pixel, HBM-bound.
 // =====================================================================================================
+// N = 8, and N = 4 when sub-8x8 partitions are searched exhaustively (the reference's second integral plane, mc.c:322-337).
 #define BS_TW 64
 #define BS_TH 32
-__global__ void __launch_bounds__(256) k_box_sum8(const uint8_t *__restrict__ src, uint16_t *__restrict__ dst, int stride, int rows)
+template <int N>
+__global__ void __launch_bounds__(256) k_box_sum(const uint8_t *__restrict__ src, uint16_t *__restrict__ dst, int stride, int rows)
 {
-    __shared__ uint16_t hs[BS_TH + 7][BS_TW];
+    __shared__ uint16_t hs[BS_TH + N - 1][BS_TW];
     const int x0 = blockIdx.x * BS_TW, y0 = blockIdx.y * BS_TH;
-    for (int i = threadIdx.x; i < (BS_TH + 7) * BS_TW; i += 256)
+    for (int i = threadIdx.x; i < (BS_TH + N - 1) * BS_TW; i += 256)
     {
         const int r = i / BS_TW, c = i - r * BS_TW;
         const int y = y0 + r, x = x0 + c;
         int s = 0;
-        if (y < rows && x + 8 <= stride)
+        if (y < rows && x + N <= stride)
         {
             const uint8_t *p = src + (size_t)y * stride + x;
 #pragma unroll
-            for (int k = 0; k < 8; k++) s += p[k];
+            for (int k = 0; k < N; k++) s += p[k];
         }
         hs[r][c] = (uint16_t)s;
     }
@@ -321,20 +333,21 @@ __global__ void __launch_bounds__(256) k_box_sum8(const uint8_t *__restrict__ sr
         if (y < rows && x < stride)
         {
             int s = 0;
-            if (y + 8 <= rows && x + 8 <= stride)
+            if (y + N <= rows && x + N <= stride)
             {
 #pragma unroll
-                for (int k = 0; k < 8; k++) s += hs[r + k][c];
+                for (int k = 0; k < N; k++) s += hs[r + k][c];
             }
             dst[(size_t)y * stride + x] = (uint16_t)s;
         }
     }
 }
 
-void launch_box_sum8(const uint8_t *src_padded, uint16_t *dst_padded, int stride, int rows, void *stream)
+void launch_box_sum(const uint8_t *src_padded, uint16_t *dst_padded, int stride, int rows, int box, void *stream)
 {
     dim3 grid((stride + BS_TW - 1) / BS_TW, (rows + BS_TH - 1) / BS_TH);
-    k_box_sum8<<<grid, 256, 0, (cudaStream_t)stream>>>(src_padded, dst_padded, stride, rows);
+    if (box == 4) k_box_sum<4><<<grid, 256, 0, (cudaStream_t)stream>>>(src_padded, dst_padded, stride, rows);
+    else          k_box_sum<8><<<grid, 256, 0, (cudaStream_t)stream>>>(src_padded, dst_padded, stride, rows);
 }
 
 // =====================================================================================================

@@ -42,7 +42,7 @@ struct MeBlock
     const uint8_t *fenc_v;
     const uint8_t *ref[4];    // integer, H, V, HV planes at the block origin
     const uint8_t *ref_u, *ref_v;
-    const uint16_t *integral; // ESA only
+    const uint16_t *integral, *integral4; // exhaustive searches only: 8x8 / 4x4 box sums of the reference at the block origin
     int stride, stride_c;
     int i_pixel, bw, bh;
     int mvp[2];
@@ -687,24 +687,27 @@ PCAMV_DEV void subpel_iters(int subme, int out[4])
 // bound of SAD + cost_mvx; the 8x8 box sums of the reference come from the integral plane k_box_sum8 builds
 // (common/mc.c:311-345,477-511).  One candidate column per lane.
 
-// DCs of the (up to four) 8x8 quadrants of the block: enc_dc of me.c:515-523
+// DCs of the (up to four) u x u quadrants of the block, u = 8 (blocks of 8x8 and up) or 4 (sub-8x8 blocks): enc_dc of
+// me.c:507-523
+PCAMV_DEV int block_unit(const MeBlock &b) { return (b.bw < 8 || b.bh < 8) ? 4 : 8; }
 PCAMV_FN void block_dcs(const MeBlock &b, int dc[4])
 {
     const smem_ptr fenc = to_smem(b.fenc);
-    const int bw = b.bw, bh = b.bh;
+    const int bw = b.bw, bh = b.bh, u = block_unit(b);
+    const int words = u * u / 4, wpr = u / 4;         // 4-pixel words per quadrant / per quadrant row
 #pragma unroll 1
     for (int q = 0; q < 4; q++)
     {
         const int qx = q & 1, qy = q >> 1;
         int part = 0;
-        if (8 * qx < bw && 8 * qy < bh)
+        if (u * qx < bw && u * qy < bh)
         {
 #if defined(PCAMV_EMU)
-            for (int it = 0; it < 16; it++)
-                part += sad4(ld4s(fenc + (8 * qy + (it >> 1)) * 16 + 8 * qx + 4 * (it & 1)), 0u);
+            for (int it = 0; it < words; it++)
+                part += sad4(ld4s(fenc + (u * qy + it / wpr) * 16 + u * qx + 4 * (it % wpr)), 0u);
 #else
             const int it = team_lane();
-            part = it < 16 ? sad4(ld4s(fenc + (8 * qy + (it >> 1)) * 16 + 8 * qx + 4 * (it & 1)), 0u) : 0;
+            part = it < words ? sad4(ld4s(fenc + (u * qy + it / wpr) * 16 + u * qx + 4 * (it % wpr)), 0u) : 0;
             part = team_sum(part);
 #endif
         }
@@ -724,14 +727,16 @@ PCAMV_DEV int ld_u16(const uint16_t *p)
 // x264_pixel_ads4 / ads2 / ads1 at full-pel (mx, my)
 PCAMV_DEV int ads_at(const MeBlock &b, const int dc[4], int mx, int my)
 {
-    const int stride = b.stride;
-    const uint16_t *s = b.integral + my * stride + mx;
+    const int stride = b.stride, u = block_unit(b);
+    const uint16_t *s = (u == 4 ? b.integral4 : b.integral) + my * stride + mx;
+    const bool two_x = b.bw == 2 * u, two_y = b.bh == 2 * u;
     int a = iabs(dc[0] - ld_u16(s));
-    if (b.bw == 16) a += iabs(dc[1] - ld_u16(s + 8));
-    if (b.bh == 16) a += iabs(dc[2] - ld_u16(s + 8 * stride));
-    if (b.bw == 16 && b.bh == 16) a += iabs(dc[3] - ld_u16(s + 8 * stride + 8));
+    if (two_x) a += iabs(dc[1] - ld_u16(s + u));
+    if (two_y) a += iabs(dc[2] - ld_u16(s + u * stride));
+    if (two_x && two_y) a += iabs(dc[3] - ld_u16(s + u * stride + u));
     return a + b.cost_mvx[mx << 2];
 }
+PCAMV_DEV bool have_box_sums(const MeBlock &b) { return block_unit(b) == 4 ? b.integral4 != nullptr : b.integral != nullptr; }
 
 PCAMV_FN best_t search_esa(const MeEnv &e, const MeBlock &b, best_t best)
 {
@@ -740,9 +745,9 @@ PCAMV_FN best_t search_esa(const MeEnv &e, const MeBlock &b, best_t best)
     const int min_x = imax(bmx - range, e.mv_min_fpel[0]), min_y = imax(bmy - range, e.mv_min_fpel[1]);
     const int max_x = imin(bmx + range, e.mv_max_fpel[0]), max_y = imin(bmy + range, e.mv_max_fpel[1]);
     const int width = (max_x - min_x + 3) & ~3;
-    if (!b.integral || b.bw < 8 || b.bh < 8)
+    if (!have_box_sums(b))
     {
-        // without 8x8 box sums that bound this block (sub-8x8 blocks of the stateless search seam): every position gets its SAD
+        // without box sums that bound this block (contexts opened without the matching integral plane): every position gets its SAD
 #pragma unroll 1
         for (int my = min_y; my <= max_y; my++)
 #pragma unroll 1

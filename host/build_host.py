@@ -51,6 +51,7 @@ typedef struct { x264_param_t param; cli_opt_t opt; int ret, index; char out[102
  * vector); MESSAGE receives int32 frame, an and the `an` recovered payload bits.  Frames that carried nothing (an <= 0) are
  * passed through with an = 0. */
 int pcamv_stc_extract( const uint8_t *stego, int n, uint8_t *message, int an, int matrixheight );
+int pcamv_stc_columns( int width, int height, uint32_t *out );
 static int pcamv_extract_main( int argc, char **argv )
 {
     const char *in = argv[2], *out = NULL;
@@ -94,6 +95,13 @@ int main( int argc, char **argv )
     FILE *fo;
     if( argc >= 3 && !strcmp( argv[1], "--extract" ) )
         return pcamv_extract_main( argc, argv );
+    if( argc == 4 && !strcmp( argv[1], "--stc-columns" ) )
+    {
+        uint32_t cols[64]; int w = atoi( argv[2] ), hh = atoi( argv[3] ), i;
+        if( w < 1 || w > 64 || pcamv_stc_columns( w, hh, cols ) ) return -1;
+        for( i = 0; i < w; i++ ) printf( "%u\n", cols[i] );
+        return 0;
+    }
     if( argc < 6 || strcmp( argv[1], "--shards" ) || strcmp( argv[3], "--shard-frames" ) )
         return x264_cli_main( argc, argv );
     n = atoi( argv[2] ); k = atoi( argv[4] );
@@ -163,6 +171,12 @@ def shard_driver(tree):
     # pointers in encoder/analyse.c:195 keep referring to them: with more than one encoder per process they must stay
     t = reftree.sub_exact(t, r"x264_free\(g_x264_cost_mv_fpel\[i\]\[j\]\);", ";", 1, "free fpel tables")
     t = reftree.sub_exact(t, r"x264_free\(g_cost_mv\[i\]\);", ";", 1, "free cost_mv tables")
+    # the embedder's trellis runs on the GPU: the one stc_embed call of the embed stage (encoder/encoder.c:1843) goes to the
+    # wrapper in host/pcamv_stc_extract.c (PCAMV_HOST_STC=1 at build time keeps the reference's CPU routine, for A/B timing)
+    if not os.environ.get("PCAMV_HOST_STC"):
+        t = reftree.sub_exact(t, r"\n(\s*)stc_embed\(h->info\.cover, h->info\.length, h->info\.message, an, h->info\.rho_final, h->info\.stego, 10\);",
+                              r"\n\1pcamv_glue_stc_embed( h, an );", 1, "stc_embed call")
+        t = t.replace("void pcamv_hook_open( x264_t *h );", "void pcamv_glue_stc_embed( x264_t *h, int an ); void pcamv_hook_open( x264_t *h );", 1)
     # the extractor the reference lacks (host/pcamv_stc_extract.c) joins the translation unit that owns getMatrix (embed.h)
     t += "\n" + open(os.path.join(HERE, "pcamv_stc_extract.c")).read()
     reftree.write(p, t)

@@ -48,3 +48,45 @@ int pcamv_stc_extract( const uint8_t *stego, int n, uint8_t *message, int an, in
     free( columns[1] );
     return index;           /* cover elements consumed (= n when the schedule covers the vector exactly) */
 }
+
+/* `x264_pcamv --stc-columns W H`: the sub-matrix getMatrix( W, H ) hands out (tests fetch the embedder's matrices this way) */
+int pcamv_stc_columns( int width, int height, uint32_t *out )
+{
+    uint32_t *c = getMatrix( width, height );
+    if( !c ) return -1;
+    memcpy( out, c, width * sizeof(uint32_t) );
+    free( c );
+    return 0;
+}
+
+/* The embed stage's stc_embed call (encoder/encoder.c:1843) on the GPU: same argument checks, same order of getMatrix
+ * draws (shorter, then longer), same effect on h->info.stego - including none at all when the message does not fit. */
+#include "pcamv.h"
+pcamv_ctx *pcamv_glue_ctx( void );
+void pcamv_glue_stc_embed( x264_t *h, int an )
+{
+    const int n = h->info.length;
+    uint32_t *cols[2];
+    double invalpha;
+    int shorter, longer, rc;
+    if( an < 1 || n < an )
+    {
+        if( an >= 1 ) fprintf( stderr, "The message cannot be longer than the cover object.\n" );
+        return;                     /* stc_embed gives up before touching stego (embed.h:349-356; an == 0: no matrix can be drawn) */
+    }
+    invalpha = (double)n / an;
+    shorter = (int)floor( invalpha );
+    longer = (int)ceil( invalpha );
+    if( !( cols[0] = getMatrix( shorter, 10 ) ) ) return;
+    if( !( cols[1] = getMatrix( longer, 10 ) ) ) { free( cols[0] ); return; }
+    rc = pcamv_stc_embed( pcamv_glue_ctx(), h->info.cover, n, h->info.message, an, h->info.rho_final, h->info.stego, 10,
+                          cols[0], shorter, cols[1], longer );
+    free( cols[0] ); free( cols[1] );
+    if( rc < 0 )
+    {
+        fprintf( stderr, "x264 [pcamv]: pcamv_stc_embed: %s\n", pcamv_last_error( pcamv_glue_ctx() ) );
+        exit( 3 );                  /* no CPU fallback */
+    }
+    if( rc == 1 )
+        fprintf( stderr, "The syndrome is not in the range of the syndrome matrix.\n" );
+}

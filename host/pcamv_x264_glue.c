@@ -89,6 +89,9 @@ void pcamv_glue_set_shards( int n )
     g_n_groups = ng;
 }
 
+/* this encoder thread's context (the embed-stage hook in the encoder.c translation unit needs it) */
+pcamv_ctx *pcamv_glue_ctx( void ) { return g.ctx; }
+
 /* called first thing by a shard's thread */
 void pcamv_glue_set_shard_index( int i )
 {

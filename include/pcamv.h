@@ -272,6 +272,17 @@ int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out);
  * VABSDIFF4 / IADD3 / LOP3 mix the SAD and SATD loops consist of.  Roofline denominator for the search kernels. */
 int pcamv_int_peak(pcamv_ctx *ctx, double *gops);
 
+/* ---- embed stage: the syndrome-trellis code of the embedder (reference embed.h:309-548 stc_embed) -----
+ * Replaces the call at encoder/encoder.c:1843: Viterbi over 2^matrixheight states on the GPU (forward pass: one CTA, one
+ * thread per state; backward trace: one warp).  cover / message / stego are one byte per bit, rho the float embedding
+ * costs, all of the host's own buffers; cols_short / cols_long are the two sub-matrices the host drew with the reference's
+ * getMatrix( floor(n/an) ), getMatrix( ceil(n/an) ) (embed.h:276-306; drawing them is stateful beyond width 20, so it
+ * stays with the caller).  Returns 0 = stego written (bit-identical to stc_embed's), 1 = the message is not embeddable in
+ * this cover (stc_embed returns 0 and leaves stego untouched; so does this), -1 = error. */
+int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, const uint8_t *message, int an, const float *rho,
+                    uint8_t *stego, int matrixheight, const uint32_t *cols_short, int w_short,
+                    const uint32_t *cols_long, int w_long);
+
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 long long pcamv_launch_count(const pcamv_ctx *ctx);
 

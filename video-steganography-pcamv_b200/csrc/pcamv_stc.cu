@@ -1,0 +1,185 @@
+// pcamv_stc.cu — the embedder's syndrome-trellis code on the GPU.
+//
+// Behavioural contract (bit-exact): reference embed.h:309-548 (stc_embed): Viterbi over 2^h states (h = 10 in the encoder,
+// encoder/encoder.c:1843), one trellis column per cover element, the state shifted right by one message bit at the end of
+// every block of the banded parity-check matrix; float path metrics, `<=` tie-breaks, a bit-packed survivor path, then the
+// backward trace that emits the stego bits.  Only float additions and comparisons occur, each computed exactly as the
+// scalar code computes it (no contraction possible: there is no multiply), so the metrics are IEEE-identical.
+//
+//   forward   one CTA of 2^h threads per vector: thread s owns state s.  Per cover element:
+//               stay  = price[s]       + (cover ? rho : 0)      (stego bit 0, state unchanged)
+//               other = price[s ^ col] + (cover ? 0 : rho)      (stego bit 1)
+//               price'[s] = other <= stay ? other : stay;  path bit = other <= stay
+//             which is the reference's pairwise update (embed.h:439-468) written per state: the pair (m, m ^ col) sets the
+//             survivor bit of either member exactly when the transition from the other member is not worse.
+//             Path bits leave as one 32-bit ballot per warp: 2^h / 8 bytes per cover element, coalesced.
+//   backward  one warp: the 128-byte path line of element idx is known before the state is, so lines are fetched eight
+//             elements ahead and the state-dependent word is picked with a shuffle.
+// The sub-matrix columns come from the caller (the host encoder draws them with the reference's getMatrix, embed.h:276-306);
+// the block schedule (embed.h:376-392) is rebuilt here in the same double arithmetic.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "pcamv_ctx.h"
+
+namespace pcamv {
+
+struct StcElem { uint32_t col; uint8_t last, msg, pad[2]; };     // per cover element: masked column, end-of-block flag, block's message bit
+
+template <int H>
+__global__ void __launch_bounds__(1 << H) k_stc_forward(const uint8_t *__restrict__ cover, const float *__restrict__ rho,
+                                                        const StcElem *__restrict__ elem, int n, uint32_t *__restrict__ path,
+                                                        float *__restrict__ total_price)
+{
+    constexpr int S = 1 << H;
+    __shared__ float pr[2][S];
+    const int s = threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    pr[0][s] = s == 0 ? 0.0f : inf;
+    __syncthreads();
+    int cur = 0;
+    for (int idx = 0; idx < n; idx++)
+    {
+        const StcElem e = elem[idx];
+        const float p = rho[idx];
+        const bool one = cover[idx] != 0;
+        const float stay = __fadd_rn(pr[cur][s], one ? p : 0.0f);
+        const float other = __fadd_rn(pr[cur][s ^ (int)e.col], one ? 0.0f : p);
+        const bool take = other <= stay;
+        const unsigned bits = __ballot_sync(0xffffffffu, take);
+        if ((s & 31) == 0)
+            path[(size_t)idx * (S / 32) + (s >> 5)] = bits;
+        pr[cur ^ 1][s] = take ? other : stay;
+        __syncthreads();
+        cur ^= 1;
+        if (e.last)
+        {
+            // end of a block: the next message bit selects the states that survive, the state register shifts right
+            pr[cur ^ 1][s] = s < S / 2 ? pr[cur][2 * s + e.msg] : inf;
+            __syncthreads();
+            cur ^= 1;
+        }
+    }
+    if (s == 0)
+        *total_price = pr[cur][0];
+}
+
+// one warp; stego[idx] = survivor bit of the running state, which then moves along the column when the bit is set
+template <int H>
+__global__ void __launch_bounds__(32) k_stc_backward(const StcElem *__restrict__ elem, int n, const uint32_t *__restrict__ path,
+                                                     uint8_t *__restrict__ stego)
+{
+    constexpr int W = (1 << H) / 32;              // path words per element (<= 32)
+    const int lane = threadIdx.x;
+    uint32_t state = 0;
+    for (int top = n - 1; top >= 0; top -= 8)
+    {
+        uint32_t line[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            line[k] = (top - k >= 0 && lane < W) ? path[(size_t)(top - k) * W + lane] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const int idx = top - k;
+            if (idx < 0) break;
+            const StcElem e = elem[idx];
+            if (e.last)
+                state = (state << 1) | e.msg;             // entering the block from behind: its message bit comes back in
+            const uint32_t word = __shfl_sync(0xffffffffu, line[k], (int)(state >> 5));
+            const uint32_t bit = (word >> (state & 31)) & 1u;
+            if (lane == 0) stego[idx] = (uint8_t)bit;
+            if (bit) state ^= e.col;
+        }
+    }
+}
+
+} // namespace pcamv
+
+using namespace pcamv;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(ctx, #call, e_); } while (0)
+
+// returns 0 = embedded, 1 = the syndrome is not in the range of the matrix (the reference's stc_embed returns 0 and leaves
+// stego untouched), -1 = error (pcamv_last_error)
+extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, const uint8_t *message, int an, const float *rho,
+                               uint8_t *stego, int matrixheight, const uint32_t *cols_short, int w_short,
+                               const uint32_t *cols_long, int w_long)
+{
+    if (!ctx || ctx->failed) return -1;
+    cudaSetDevice(ctx->cfg.device);
+    if (!cover || !message || !rho || !stego || !cols_short || !cols_long || n <= 0 || an <= 0 || an > n)
+        return ctx_fail(ctx, "pcamv_stc_embed: bad argument", cudaSuccess);
+    if (matrixheight < 7 || matrixheight > 10)
+        return ctx_fail(ctx, "pcamv_stc_embed: matrix height must be 7..10 (the encoder uses 10)", cudaSuccess);
+    // block schedule (embed.h:376-392) and per-element columns with the shrinking mask of the last h blocks (embed.h:482-483)
+    const double invalpha = (double)n / an;
+    const int shorter = (int)floor(invalpha), longer = (int)ceil(invalpha);
+    if (shorter != w_short || longer != w_long)
+        return ctx_fail(ctx, "pcamv_stc_embed: sub-matrix widths must be floor / ceil of n / an", cudaSuccess);
+    std::vector<StcElem> el((size_t)n);
+    uint32_t colmask = (1u << matrixheight) - 1;
+    int worm = 0, index = 0;
+    double total = 0;
+    for (int b = 0; b < an; b++)
+    {
+        const bool wide = worm + longer <= (b + 1) * invalpha + 0.5;
+        const int width = wide ? longer : shorter;
+        const uint32_t *cols = wide ? cols_long : cols_short;
+        worm += width;
+        if (index + width > n)
+            return ctx_fail(ctx, "pcamv_stc_embed: block schedule overruns the cover", cudaSuccess);
+        for (int k = 0; k < width; k++, index++)
+        {
+            el[index].col = cols[k] & colmask;
+            el[index].last = k == width - 1;
+            el[index].msg = message[b] ? 1 : 0;
+            el[index].pad[0] = el[index].pad[1] = 0;
+            total += rho[index];
+        }
+        if (an - b <= matrixheight)
+            colmask >>= 1;
+    }
+    const int used = index;           // the schedule's total width; elements past it (if any) are never touched, as in the reference
+    const size_t words = (size_t)used * ((1u << matrixheight) / 32);
+    uint8_t *d_cover = nullptr, *d_stego = nullptr; float *d_rho = nullptr, *d_total = nullptr; StcElem *d_el = nullptr; uint32_t *d_path = nullptr;
+    auto release = [&]() { cudaFree(d_cover); cudaFree(d_stego); cudaFree(d_rho); cudaFree(d_total); cudaFree(d_el); cudaFree(d_path); };
+#define SK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return ctx_fail(ctx, #call, e_); } } while (0)
+    SK(cudaMalloc(&d_cover, used)); SK(cudaMalloc(&d_stego, used)); SK(cudaMalloc(&d_rho, used * sizeof(float)));
+    SK(cudaMalloc(&d_total, sizeof(float))); SK(cudaMalloc(&d_el, used * sizeof(StcElem))); SK(cudaMalloc(&d_path, words * sizeof(uint32_t)));
+    SK(cudaMemcpyAsync(d_cover, cover, used, cudaMemcpyHostToDevice, ctx->stream));
+    SK(cudaMemcpyAsync(d_rho, rho, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SK(cudaMemcpyAsync(d_el, el.data(), used * sizeof(StcElem), cudaMemcpyHostToDevice, ctx->stream));
+    switch (matrixheight)
+    {
+    case 7:  k_stc_forward<7><<<1, 128, 0, ctx->stream>>>(d_cover, d_rho, d_el, used, d_path, d_total); break;
+    case 8:  k_stc_forward<8><<<1, 256, 0, ctx->stream>>>(d_cover, d_rho, d_el, used, d_path, d_total); break;
+    case 9:  k_stc_forward<9><<<1, 512, 0, ctx->stream>>>(d_cover, d_rho, d_el, used, d_path, d_total); break;
+    default: k_stc_forward<10><<<1, 1024, 0, ctx->stream>>>(d_cover, d_rho, d_el, used, d_path, d_total); break;
+    }
+    float total_price = 0;
+    SK(cudaMemcpyAsync(&total_price, d_total, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 1;
+    if ((double)total_price >= total)
+    {
+        release();
+        return 1;               // "The syndrome is not in the range of the syndrome matrix." (embed.h:503-512)
+    }
+    switch (matrixheight)
+    {
+    case 7:  k_stc_backward<7><<<1, 32, 0, ctx->stream>>>(d_el, used, d_path, d_stego); break;
+    case 8:  k_stc_backward<8><<<1, 32, 0, ctx->stream>>>(d_el, used, d_path, d_stego); break;
+    case 9:  k_stc_backward<9><<<1, 32, 0, ctx->stream>>>(d_el, used, d_path, d_stego); break;
+    default: k_stc_backward<10><<<1, 32, 0, ctx->stream>>>(d_el, used, d_path, d_stego); break;
+    }
+    SK(cudaMemcpyAsync(stego, d_stego, used, cudaMemcpyDeviceToHost, ctx->stream));
+    SK(cudaStreamSynchronize(ctx->stream));
+    SK(cudaGetLastError());
+    ctx->launches += 1;
+    release();
+#undef SK
+    return 0;
+}

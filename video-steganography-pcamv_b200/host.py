@@ -68,7 +68,7 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
            "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
            "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide",
-           "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave"]
+           "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave", "pcamv_stc_embed"]
 
 _lib = None
 
@@ -111,6 +111,7 @@ def load_library(path=None):
     lib.pcamv_group_destroy.argtypes = [vp]; lib.pcamv_group_destroy.restype = None
     lib.pcamv_group_analyse_p.argtypes = [vp, vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_group_analyse_p.restype = ip
     lib.pcamv_group_leave.argtypes = [vp]; lib.pcamv_group_leave.restype = ip
+    lib.pcamv_stc_embed.argtypes = [vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp, ip]; lib.pcamv_stc_embed.restype = ip
     lib.pcamv_host_alloc.argtypes = [C.c_size_t]; lib.pcamv_host_alloc.restype = vp
     lib.pcamv_host_free.argtypes = [vp]; lib.pcamv_host_free.restype = None
     lib.pcamv_analyse_p_batch.argtypes = [C.POINTER(vp), C.POINTER(C.POINTER(FrameIn)), ip, C.POINTER(vp), C.POINTER(vp)]
@@ -237,6 +238,18 @@ class PcamvContext:
         out = np.empty(self.plane_bytes(plane), dtype=np.uint8)
         self._check(self.lib.pcamv_get_ref_plane(self.handle, slot, plane, _ptr(out)))
         return out.reshape(-1, self.plane_stride(plane))
+
+    def stc_embed(self, cover, message, rho, cols_short, cols_long, height=10):
+        """pcamv_stc_embed: returns the stego bit vector, or None when the message is not embeddable in this cover."""
+        cover = np.ascontiguousarray(cover, dtype=np.uint8); message = np.ascontiguousarray(message, dtype=np.uint8)
+        rho = np.ascontiguousarray(rho, dtype=np.float32)
+        cs = np.ascontiguousarray(cols_short, dtype=np.uint32); cl = np.ascontiguousarray(cols_long, dtype=np.uint32)
+        stego = np.zeros(len(cover), dtype=np.uint8)
+        rc = self.lib.pcamv_stc_embed(self.handle, _ptr(cover), len(cover), _ptr(message), len(message), _ptr(rho), _ptr(stego),
+                                      height, _ptr(cs), len(cs), _ptr(cl), len(cl))
+        if rc < 0:
+            self._check(rc)
+        return stego if rc == 0 else None
 
     def get_integral(self, slot):
         """The integral plane of a slot (--me esa / tesa contexts): uint16 [rows, stride_y]."""

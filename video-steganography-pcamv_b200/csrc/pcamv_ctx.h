@@ -42,6 +42,7 @@ struct pcamv_ctx
     int batch_max_ctas = 0, batch_claim_cap = 0;   // persistent grid size of multi-context launches (0 = not yet computed)
     unsigned long long *d_mvsads = nullptr; int mvsads_cap = 0;    // --me tesa: per-row candidate lists
     unsigned long long *d_seam_mvsads = nullptr;                   // --me tesa, stateless search seam: PCAMV_SEAM_CHUNK lists
+    uint8_t *d_stc = nullptr; size_t stc_bytes = 0;               // embed stage (pcamv_stc_embed): cover | stego | rho | elems | path | total
     unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
     bool trace_on = false;
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter

@@ -144,11 +144,21 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
     }
     const int used = index;           // the schedule's total width; elements past it (if any) are never touched, as in the reference
     const size_t words = (size_t)used * ((1u << matrixheight) / 32);
-    uint8_t *d_cover = nullptr, *d_stego = nullptr; float *d_rho = nullptr, *d_total = nullptr; StcElem *d_el = nullptr; uint32_t *d_path = nullptr;
-    auto release = [&]() { cudaFree(d_cover); cudaFree(d_stego); cudaFree(d_rho); cudaFree(d_total); cudaFree(d_el); cudaFree(d_path); };
+    // one device block per context, grown on demand: path | elems | rho | total | cover | stego (16-byte aligned parts)
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_path = 0, o_el = up(words * sizeof(uint32_t)), o_rho = o_el + up(used * sizeof(StcElem)),
+                 o_total = o_rho + up(used * sizeof(float)), o_cover = o_total + 256, o_stego = o_cover + up(used), need = o_stego + up(used);
+    if (ctx->stc_bytes < need)
+    {
+        cudaFree(ctx->d_stc); ctx->d_stc = nullptr; ctx->stc_bytes = 0;
+        CK(cudaMalloc(&ctx->d_stc, need + need / 4));
+        ctx->stc_bytes = need + need / 4;
+    }
+    uint32_t *d_path = (uint32_t *)(ctx->d_stc + o_path); StcElem *d_el = (StcElem *)(ctx->d_stc + o_el);
+    float *d_rho = (float *)(ctx->d_stc + o_rho), *d_total = (float *)(ctx->d_stc + o_total);
+    uint8_t *d_cover = ctx->d_stc + o_cover, *d_stego = ctx->d_stc + o_stego;
+    auto release = []() {};
 #define SK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return ctx_fail(ctx, #call, e_); } } while (0)
-    SK(cudaMalloc(&d_cover, used)); SK(cudaMalloc(&d_stego, used)); SK(cudaMalloc(&d_rho, used * sizeof(float)));
-    SK(cudaMalloc(&d_total, sizeof(float))); SK(cudaMalloc(&d_el, used * sizeof(StcElem))); SK(cudaMalloc(&d_path, words * sizeof(uint32_t)));
     SK(cudaMemcpyAsync(d_cover, cover, used, cudaMemcpyHostToDevice, ctx->stream));
     SK(cudaMemcpyAsync(d_rho, rho, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     SK(cudaMemcpyAsync(d_el, el.data(), used * sizeof(StcElem), cudaMemcpyHostToDevice, ctx->stream));

@@ -25,7 +25,9 @@ elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True)
 syms = []
 for l in elf.splitlines():
     m = re.match(r"\s+0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+\S+\s+(\S+)", l)
-    if m and kern in m.group(3):
+    # symbols of device functions are "$<kernel>$<function>"; an exact kernel mangled name can be given as 4th argument so
+    # that other template instantiations of the same kernel are not mixed in
+    if m and (sys.argv[4] in m.group(3) if len(sys.argv) > 4 else kern in m.group(3)):
         short = re.sub(r"_INTERNAL_[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]+", "", m.group(3).split("$")[-1])
         syms.append((int(m.group(1), 16), int(m.group(2), 16), short[:40]))
 syms.sort()

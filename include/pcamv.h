@@ -64,7 +64,9 @@ typedef struct pcamv_cfg
     int analyse_inter;      /* param.analyse.inter flag word (X264_ANALYSE_PSUB16x16 = 0x10, PSUB8x8 = 0x20) */
     int chroma_qp_offset;   /* pps chroma_qp_index_offset */
     int rows_per_cta;       /* wavefront layout: 0/1 = one macroblock row per CTA (lowest latency, a single encoder);
-                               2 or 4 = consecutive rows share a CTA (throughput, many concurrent contexts per GPU) */
+                               2 or 4 = consecutive rows share a CTA (throughput, many concurrent contexts per GPU);
+                               -1 = row pool for multi-context launches: rows are resumable tasks claimed by any team whose
+                               next macroblock is ready, so no team sleeps on a dependency (single launches: as 1) */
     int pass2_elide;        /* 1: in pass 2, macroblocks whose decision is forced from pass 1 (info.cache[].used) only run the
                                16x16 search — the one result of that pass the reference still uses (h->mb.mvr candidates of later
                                macroblocks, early-skip detection); the 8x8 / 16x8 / 8x16 searches and the refinement, whose

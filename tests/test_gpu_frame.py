@@ -60,9 +60,11 @@ def test_frame_seam_rejects_unsupported(pcamv, cuda_lib):
     ctx.close()
 
 
-def test_batch_launch_equals_single(pcamv, cuda_lib, tmp_path):
+@pytest.mark.parametrize("rows_per_cta", [4, 2, -1], ids=["row-groups-4", "row-groups-2", "row-pool"])
+def test_batch_launch_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
     """pcamv_analyse_p_batch: several encoder contexts (different frames) analysed by ONE wavefront launch give exactly
-    the records and logs each context gets on its own."""
+    the records and logs each context gets on its own — for the row-group kernels and for the row pool (rows as resumable
+    tasks claimed by whichever team finds them ready)."""
     import frame_parity
     dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path("qcif_hex5", str(tmp_path)))
     units = [u for u in dump.slice_units() if u["slice"].with_planes and u["slice"].pass_ == 1][:3]
@@ -71,7 +73,7 @@ def test_batch_launch_equals_single(pcamv, cuda_lib, tmp_path):
     for rpc, u in zip((1, 1, 1), units):
         s, x = u["slice"], u["ctx"]
         H, W = s.lines_y, s.width
-        c = frame_parity.open_ctx(pcamv, dump, s, rows_per_cta=4)
+        c = frame_parity.open_ctx(pcamv, dump, s, rows_per_cta=rows_per_cta)
         c.put_fenc(s.fenc[0][:, :W], s.fenc[1][:, :W // 2], s.fenc[2][:, :W // 2])
         for slot, r in enumerate(s.refs):
             c.put_ref(slot, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2],
@@ -90,5 +92,44 @@ def test_batch_launch_equals_single(pcamv, cuda_lib, tmp_path):
     assert not (single[0][0]["mv"] == single[1][0]["mv"]).all()       # the frames really differ
     ms, w, ct = pcamv.host.frame_run_batch(ctxs, 1, iters=2)
     assert ms > 0 and w > 0 and ct > 0
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.parametrize("rows_per_cta", [4, -1], ids=["row-groups-4", "row-pool"])
+def test_batch_pass2_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
+    """Pass 2 through a multi-context launch on the P_SKIP-heavy clip, where the 'forced skip keeps the previous macroblock's
+    MV cache' quirk (analyse.c:2668-2676) makes row starts depend on the whole previous row: the row-group kernels wait for
+    it inside the macroblock, the row pool folds it into the readiness test.  Every context must reproduce the single-launch
+    pass-2 records (which test_frame_analysis_matches_reference pins against the reference)."""
+    import frame_parity
+    dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path("qcif_dia2_lownoise", str(tmp_path)))
+    units = [u for u in dump.slice_units() if u["slice"].with_planes]
+    frames = sorted({u["slice"].frame for u in units})[:3]
+    ctxs, args2, single = [], [], []
+    for fr in frames:
+        u1 = next(u for u in units if u["slice"].frame == fr and u["slice"].pass_ == 1)
+        u2 = next(u for u in units if u["slice"].frame == fr and u["slice"].pass_ == 2)
+        s, x, e = u1["slice"], u1["ctx"], u1["embd"]
+        H, W = s.lines_y, s.width
+        c = frame_parity.open_ctx(pcamv, dump, s, rows_per_cta=rows_per_cta)
+        c.put_fenc(s.fenc[0][:, :W], s.fenc[1][:, :W // 2], s.fenc[2][:, :W // 2])
+        for slot, r in enumerate(s.refs):
+            c.put_ref(slot, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2],
+                      r["v"][16:16 + H // 2, 16:16 + W // 2])
+        kw = dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"])
+        refs, pocs = list(range(x["n_ref"])), x["ref_poc"][:x["n_ref"]]
+        m1, _ = c.analyse_p(1, refs, pocs, x["cur_poc"], cost_table=True, **kw)
+        kw2 = dict(pass1=frame_parity.pass1_records(pcamv, e), filp=e["filp"], stale_mv=m1["mv"][-1].copy(), **kw)
+        m2, l2 = c.analyse_p(2, refs, pocs, x["cur_poc"], **kw2)
+        single.append((m2.copy(), l2.copy()))
+        ctxs.append(c); args2.append((2, refs, pocs, x["cur_poc"], kw2))
+    assert any((m["type"] == 6).mean() > 0.3 for m, _ in single)         # really skip-heavy
+    outs = pcamv.host.analyse_p_batch(ctxs, args2)
+    for (m0, l0), (m1, l1) in zip(single, outs):
+        assert m0.tobytes() == m1.tobytes()
+        for mb in range(len(m0)):
+            n = int(m0["n_log"][mb])
+            assert l0[mb, :n].tobytes() == l1[mb, :n].tobytes()
     for c in ctxs:
         c.close()

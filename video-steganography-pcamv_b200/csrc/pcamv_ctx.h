@@ -45,7 +45,7 @@ struct pcamv_ctx
     uint8_t *d_stc = nullptr; size_t stc_bytes = 0;               // embed stage (pcamv_stc_embed): cover | stego | rho | elems | path | total
     unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
     bool trace_on = false;
-    int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter
+    int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter + [mb_h] row owners (row pool)
     uint8_t *h_frame = nullptr; size_t h_frame_bytes = 0, h_frame_in_bytes = 0;
     bool dl_mbs_direct = false, dl_log_direct = false;             // pinned staging for frame inputs / outputs
     pcamv::FrameParams fp[3] = {};             // parameters of the last uploaded frame, per pass (0 / 1 / 2)

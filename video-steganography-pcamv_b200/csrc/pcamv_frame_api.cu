@@ -40,7 +40,7 @@ static int ensure_frame_buffers(pcamv_ctx *ctx)
     CK(cudaMalloc(&ctx->d_col_mv4, 16 * n_mb * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->d_forced, n_mb * sizeof(ForcedMb)));
     CK(cudaMalloc(&ctx->d_mb_results, n_mb * sizeof(MbResult)));
-    CK(cudaMalloc(&ctx->d_progress, (fc.mb_h + 1) * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_progress, (2 * fc.mb_h + 2) * sizeof(int)));      // row progress | row-claim counter | row owners (row pool)
     CK(cudaMalloc(&ctx->d_trace, 2 * n_mb * sizeof(unsigned long long)));
     if (fc.analyse_inter & 0x20)
     {
@@ -149,7 +149,7 @@ static int launch_frame(pcamv_ctx *ctx, int pass, cudaEvent_t *ev = nullptr)
 {
     const DevFrameCtx &fc = ctx->fc;
     ctx->fp[pass].trace = ctx->trace_on ? ctx->d_trace : nullptr;
-    CK(cudaMemsetAsync(ctx->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_progress, 0, (2 * fc.mb_h + 2) * sizeof(int), ctx->stream));
     if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
     launch_analyse_p(fc, ctx->fp[pass], ctx->d_progress + fc.mb_h, fc.mb_h, ctx->cfg.rows_per_cta, ctx->stream);
     ctx->launches += 1;
@@ -316,7 +316,7 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
         // persistent grid: what can be resident at once (the kernel's launch bounds ask for 24 warps per SM)
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, ctx->cfg.device));
-        const int w = ctx->cfg.rows_per_cta >= 4 ? 4 : ctx->cfg.rows_per_cta >= 2 ? 2 : 1;
+        const int w = ctx->cfg.rows_per_cta >= 4 || ctx->cfg.rows_per_cta < 0 ? 4 : ctx->cfg.rows_per_cta >= 2 ? 2 : 1;
         ctx->batch_max_ctas = prop.multiProcessorCount * (24 / w);
     }
     int cost_table = pass == 1;
@@ -328,7 +328,7 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
         ctx->h_batch[i].fp = c->fp[pass];
         cost_table = cost_table && c->frame_cost_table;
         // everything a member uploaded on its own stream has been synchronised by pcamv_frame_upload
-        CK(cudaMemsetAsync(c->d_progress, 0, (fc.mb_h + 1) * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(c->d_progress, 0, (2 * fc.mb_h + 2) * sizeof(int), ctx->stream));
     }
     CK(cudaMemcpyAsync(ctx->d_batch, ctx->h_batch, n * sizeof(BatchItem), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_batch_claim, 0, n * sizeof(int), ctx->stream));

@@ -183,6 +183,113 @@ __global__ void __launch_bounds__(AP_WARPS * 32, PCAMV_BATCH_MIN_CTAS * 4 / AP_W
     }
 }
 
+// ---- row pool: the multi-context wavefront without standing waits ---------------------------------------------------
+// In the row-group kernel above a team that reaches a macroblock whose top-right neighbour is not finished sleeps until it
+// is; with minimal lag between consecutive rows that is the common case, and the profile of the 128-context launch shows
+// ~45 % of the resident warp time asleep or polling.  Here a ROW is a resumable task, not a team's property: a team
+// claims any row whose next macroblock is ready (compare-and-swap on the row's owner word), analyses macroblocks while
+// they stay ready, then publishes the row's progress, releases it and looks for the next one — a blocked row waits in
+// memory, not in a warp.  Nothing the analysis of a macroblock needs lives in the team between macroblocks (MbCtx / MbWork
+// are rebuilt from the frame's records), so any team can resume any row.  Progress: the topmost unfinished row of a frame
+// never waits on anything, so some row is always claimable until all are done — for any grid size.
+// The pass-2 "forced skip" quirk (q2, analyse.c:2668-2676: the stale MV cache of the previous macroblock in raster
+// order) makes macroblock 0 of a row depend on the whole previous row; the readiness test asks for that whenever the
+// pass-1 record says P_SKIP, so wait_prev_raster() finds its condition already true and never spins here.
+__device__ __forceinline__ bool row_ready(const DevFrameCtx &fc, const FrameParams &fp, int row, int x)
+{
+    if (row == 0)
+        return true;
+    int need = min(x + 2, fc.mb_w);
+    if (x == 0 && fp.pass == 2 && fp.forced[row * fc.mb_w].type == MB_P_SKIP)
+        need = fc.mb_w;
+    return ld_acquire(fp.row_progress + row - 1) >= need;
+}
+
+template <int F>
+__global__ void __launch_bounds__(128, PCAMV_BATCH_MIN_CTAS) k_analyse_p_pool(const BatchItem *__restrict__ items, int n_items, int *rows_done)
+{
+    __shared__ MbWork s_work[4];
+    __shared__ __align__(16) unsigned char s_ctx[4][sizeof(MbCtx)];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    MbWork &work = s_work[warp];
+    const int mb_h = items[0].fc.mb_h, mb_w = items[0].fc.mb_w;
+    const int total = n_items * mb_h;
+    // teams start their searches spread over the frames; a team stays near the row it last ran (its reference window is warm)
+    unsigned pos = (unsigned)(((unsigned long long)(blockIdx.x * 4 + warp) * (unsigned)total) / (gridDim.x * 4u));
+    unsigned backoff = 256;
+    for (;;)
+    {
+        if (ld_acquire(rows_done) >= total)
+            return;
+        // one sweep over the rows, 32 per step, from `pos`: first claimable row wins
+        int got = -1;
+        for (int step = 0; step * 32 < total && got < 0; step++)
+        {
+            const int g = (int)((pos + (unsigned)(step * 32 + lane)) % (unsigned)total);
+            const int f = g / mb_h, r = g - f * mb_h;
+            const FrameParams &fp = items[f].fp;
+            const int *owner = fp.row_progress + mb_h + 1;
+            bool ok = false;
+            if (step * 32 + lane < total)
+            {
+                const int x = ld_acquire(fp.row_progress + r);
+                ok = x < mb_w && ld_acquire(owner + r) == 0 && row_ready(items[f].fc, fp, r, x);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            while (m && got < 0)
+            {
+                const int l = __ffs((int)m) - 1;
+                m &= m - 1;
+                int won = 0;
+                if (lane == l)
+                    won = atomicCAS((int *)owner + r, 0, 1) == 0;
+                won = __shfl_sync(0xffffffffu, won, l);
+                if (won)
+                    got = __shfl_sync(0xffffffffu, g, l);
+            }
+        }
+        if (got < 0)
+        {
+            __nanosleep(backoff);
+            if (backoff < 8192) backoff <<= 1;
+            continue;
+        }
+        backoff = 256;
+        __threadfence();                                    // the previous owner's writes (this row's left neighbours) are visible
+        const int f = got / mb_h, row = got - f * mb_h;
+        const BatchItem &it = items[f];
+        int *owner = it.fp.row_progress + mb_h + 1;
+        MbCtx &c = *new (s_ctx[warp]) MbCtx(it.fc, it.fp, work);
+        int x = ld_acquire(it.fp.row_progress + row);       // (may have moved between the look and the claim)
+        bool finished = false;
+        while (x < mb_w && row_ready(it.fc, it.fp, row, x))
+        {
+            c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;
+            if (it.fp.trace && lane == 0) it.fp.trace[2 * c.mb_xy] = globaltimer_ns();
+            stage_fenc(it.fc, x, row, work);
+            analyse_p_mb<F>(c, c.mb_xy ? it.fp.results[c.mb_xy - 1].mv : it.fp.stale_mv);
+            __syncwarp();
+            if (lane == 0)
+            {
+                if (it.fp.trace) it.fp.trace[2 * c.mb_xy + 1] = globaltimer_ns();
+                __threadfence();
+                st_release(it.fp.row_progress + row, x + 1);
+            }
+            x++;
+            finished = x == mb_w;
+        }
+        if (lane == 0)
+        {
+            __threadfence();
+            st_release(owner + row, 0);
+            if (finished)
+                atomicAdd(rows_done, 1);
+        }
+        __syncwarp();
+        pos = (unsigned)got + 1u;                           // the row below is the likeliest to have become ready
+    }
+}
+
 // rows_per_cta: 1 = every row on its own SM (lowest latency for a single encoder), 4 = four consecutive rows share a
 // CTA and its L1 (higher throughput when many encoder contexts run concurrently)
 // feature mask of the instantiation: bit 0 = exhaustive searches (--me esa / tesa), bit 1 = sub-8x8 partitions; the default
@@ -204,6 +311,14 @@ void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim,
 {
     const cudaStream_t st = (cudaStream_t)stream;
     const int f = feature_mask(fc);
+    if (rows_per_cta < 0)
+    {
+        // row pool (rows_per_cta = -1): persistent grid of 4-team CTAs, row_claim[0] counts finished rows
+        int ctas = max_ctas > 0 ? max_ctas : (n_items * n_rows + 3) / 4;
+        if (ctas > (n_items * n_rows + 3) / 4) ctas = (n_items * n_rows + 3) / 4;
+        PCAMV_DISPATCH_F(f, (k_analyse_p_pool<F_><<<ctas, 128, 0, st>>>(items, n_items, row_claim)));
+        return;
+    }
     const int w = rows_per_cta >= 4 ? 4 : rows_per_cta >= 2 ? 2 : 1;
     int ctas = n_items * ((n_rows + w - 1) / w);
     if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;

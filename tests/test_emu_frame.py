@@ -34,7 +34,8 @@ LIVE = [
     ("--me hex --subme 5 --ref 1", "1:4", 32),
     ("--me umh --subme 5 --ref 3", "3:5", 32),
     ("--me hex --subme 4 --ref 2 --no-fast-pskip", "2:4", 32),
-    ("--me dia --subme 2 --ref 1 --qp 32", "1:4", 4),          # low noise: P_SKIP-heavy, exercises the pass-2 quirks
+    ("--me dia --subme 2 --ref 1 --qp 32", "1:4", 4),          # subme < 3: skips only through the neighbour-gated probe
+    ("--me dia --subme 4 --ref 2 --qp 34", "1:4", 2),          # low noise: a quarter to a third P_SKIP, exercises the pass-2 quirks
     ("--me hex --subme 5 --ref 1 --no-cabac", "1:3", 16),
     ("--me esa --merange 16 --subme 5 --ref 2", "1:3", 32),            # successive elimination on the integral plane
     ("--me tesa --merange 24 --subme 3 --ref 2", "1:3", 32),

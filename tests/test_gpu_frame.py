@@ -96,6 +96,7 @@ def test_batch_launch_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
         c.close()
 
 
+@pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/x264_dump not built")
 @pytest.mark.parametrize("rows_per_cta", [4, -1], ids=["row-groups-4", "row-pool"])
 def test_batch_pass2_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
     """Pass 2 through a multi-context launch on the P_SKIP-heavy clip, where the 'forced skip keeps the previous macroblock's
@@ -103,7 +104,10 @@ def test_batch_pass2_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
     it inside the macroblock, the row pool folds it into the readiness test.  Every context must reproduce the single-launch
     pass-2 records (which test_frame_analysis_matches_reference pins against the reference)."""
     import frame_parity
-    dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path("qcif_dia2_lownoise", str(tmp_path)))
+    clip = refrun.synth_clip(pcamv, 352, 288, 5, config=1, stream=5, noise16=0, workdir=str(tmp_path))
+    dumpf = str(tmp_path / "d.bin")
+    refrun.run_ref(clip, 352, 288, "--qp 36 --keyint 250 --emrate 0.2 --me hex --subme 3 --ref 1".split(), dump=dumpf, frames="1:4")
+    dump = pcamv.dumpfmt.Dump(dumpf)
     units = [u for u in dump.slice_units() if u["slice"].with_planes]
     frames = sorted({u["slice"].frame for u in units})[:3]
     ctxs, args2, single = [], [], []
@@ -124,7 +128,7 @@ def test_batch_pass2_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
         m2, l2 = c.analyse_p(2, refs, pocs, x["cur_poc"], **kw2)
         single.append((m2.copy(), l2.copy()))
         ctxs.append(c); args2.append((2, refs, pocs, x["cur_poc"], kw2))
-    assert any((m["type"] == 6).mean() > 0.3 for m, _ in single)         # really skip-heavy
+    assert all((m["type"] == 6).mean() > 0.2 for m, _ in single)         # really skip-heavy
     outs = pcamv.host.analyse_p_batch(ctxs, args2)
     for (m0, l0), (m1, l1) in zip(single, outs):
         assert m0.tobytes() == m1.tobytes()

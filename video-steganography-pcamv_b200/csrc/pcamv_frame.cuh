@@ -1129,7 +1129,9 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     }
     else
         update_cache<SUB8>(c, a, type, partition);
-    finalize_mb<SUB8>(c, a, type, partition, 0);
+    // a forced decision names partitions this pass may never have searched: its record carries no partition slots
+    // (pass 2 has no cost table; the slots would be whatever the team's scratch held)
+    finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, 0);
 }
 
 } // namespace pcamv

@@ -1,6 +1,7 @@
 // pcamv_frame_api.cu — C-ABI of the frame seam (include/pcamv.h: pcamv_analyse_p and its three stages).
 // Host-side only: argument checks, the pass-2 glue (pcamv_glue.h), staging, launches.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stddef.h>
 #include <stdio.h>
 #include <string.h>
@@ -317,7 +318,10 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, ctx->cfg.device));
         const int w = ctx->cfg.rows_per_cta >= 4 || ctx->cfg.rows_per_cta < 0 ? 4 : ctx->cfg.rows_per_cta >= 2 ? 2 : 1;
-        ctx->batch_max_ctas = prop.multiProcessorCount * (24 / w);
+        int warps_per_sm = 24;
+        if (const char *e = getenv("PCAMV_BATCH_WARPS_PER_SM"))        // experiments with other register budgets (PCAMV_BATCH_MIN_CTAS at build time)
+            if (atoi(e) >= 4) warps_per_sm = atoi(e);
+        ctx->batch_max_ctas = prop.multiProcessorCount * (warps_per_sm / w);
     }
     int cost_table = pass == 1;
     for (int i = 0; i < n; i++)

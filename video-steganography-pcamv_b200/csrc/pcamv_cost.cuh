@@ -33,7 +33,7 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
     int *sc = c.w.scratch;
     int16_t *dcs = (int16_t *)(c.w.scratch + 24);           // 8 x int16
     PCAMV_FOR_ITEMS(it, 24)
-        sc[it] = quant_block(c, it, dcs);
+        sc[it] = quant_block<0>(c, it, dcs);
     team_sync();
 
     // ---- decisions (uniform) -------------------------------------------------------------------------------

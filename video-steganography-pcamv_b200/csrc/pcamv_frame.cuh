@@ -286,17 +286,21 @@ PCAMV_FN void init_limits(MbCtx &c)
 
 // ---- 4x4 transform / quantisation (one 4x4 block per lane) -----------------------------------------
 // d[] = fenc - pred residual in raster order (d[4*y+x]); out = coefficients in the reference's dct[i][j] layout
+// ROLL = 1 keeps the 4- and 16-element loops of the transform / quantiser rolled (arrays in local memory): the wavefront
+// kernel only needs them for the P_SKIP probe of some macroblocks, and there a small body beats a fast one — the launch
+// is bound by the footprint of its code (DESIGN.md "What limits it").  The cost-table kernel uses the unrolled forms.
+template <int ROLL>
 PCAMV_DEV void dct4x4(const int d[16], int out[16])
 {
     int tmp[16];
-#pragma unroll
+#pragma unroll (ROLL ? 1 : 4)
     for (int i = 0; i < 4; i++)
     {
         const int s03 = d[4 * i] + d[4 * i + 3], s12 = d[4 * i + 1] + d[4 * i + 2];
         const int d03 = d[4 * i] - d[4 * i + 3], d12 = d[4 * i + 1] - d[4 * i + 2];
         tmp[0 * 4 + i] = s03 + s12; tmp[1 * 4 + i] = 2 * d03 + d12; tmp[2 * 4 + i] = s03 - s12; tmp[3 * 4 + i] = d03 - 2 * d12;
     }
-#pragma unroll
+#pragma unroll (ROLL ? 1 : 4)
     for (int i = 0; i < 4; i++)
     {
         const int s03 = tmp[4 * i] + tmp[4 * i + 3], s12 = tmp[4 * i + 1] + tmp[4 * i + 2];
@@ -306,10 +310,11 @@ PCAMV_DEV void dct4x4(const int d[16], int out[16])
     }
 }
 // in-place quantisation with dead-zone bias; returns nonzero flag
+template <int ROLL>
 PCAMV_DEV int quant4x4(int coef[16], const uint16_t *mf, const uint16_t *bias)
 {
     int nz = 0;
-#pragma unroll
+#pragma unroll (ROLL ? 1 : 16)
     for (int i = 0; i < 16; i++)
     {
         const int v = coef[i];
@@ -342,19 +347,20 @@ PCAMV_DEV int decimate_score(const int16_t *coef, int first)
     }
     return score;
 }
+template <int ROLL>
 PCAMV_DEV void dequant4x4(int coef[16], const int32_t *dequant_mf, int qp)
 {
     const int32_t *dm = dequant_mf + (qp % 6) * 16;
     const int qbits = qp / 6 - 4;
     if (qbits >= 0)
     {
-#pragma unroll
+#pragma unroll (ROLL ? 1 : 16)
         for (int i = 0; i < 16; i++) coef[i] = (int16_t)((coef[i] * dm[i]) << qbits);
     }
     else
     {
         const int f = 1 << (-qbits - 1);
-#pragma unroll
+#pragma unroll (ROLL ? 1 : 16)
         for (int i = 0; i < 16; i++) coef[i] = (int16_t)((coef[i] * dm[i] + f) >> (-qbits));
     }
 }
@@ -473,6 +479,7 @@ PCAMV_FN void mc_rect(MbCtx &c, int ref_slot, int x0, int y0, int wd, int ht, in
 // the DC term is set aside (raw, in dcs[]) and zeroed; quantise; decimate score; dequantise.  The coefficients end up
 // in w.coef[it] (dequantised when non-zero).  Returns score | nz << 8.
 // (reference encoder/macroblock.c:605-755 luma, :277-372 chroma, :809-895 probe; common/dct.c:122-162; quant.c:33-75,203-252)
+template <int ROLL>
 PCAMV_FN int quant_block(MbCtx &c, int it, int16_t *dcs)
 {
     const DevTables &t = c.fc.tab;
@@ -489,22 +496,22 @@ PCAMV_FN int quant_block(MbCtx &c, int it, int16_t *dcs)
         const uint8_t *fe = pl ? c.w.fenc_v : c.w.fenc_u, *pr = pl ? c.w.pred_v : c.w.pred_u;
         load_residual(fe + 32 * (blk >> 1) + 4 * (blk & 1), 8, pr + 32 * (blk >> 1) + 4 * (blk & 1), 8, d);
     }
-    dct4x4(d, co);
+    dct4x4<ROLL>(d, co);
     if (ch)
     {
         dcs[it - 16] = (int16_t)co[0];
         co[0] = 0;
     }
-    const int nz = quant4x4(co, t.quant4_mf[ch], t.quant4_bias[ch]);
+    const int nz = quant4x4<ROLL>(co, t.quant4_mf[ch], t.quant4_bias[ch]);
     int16_t *out = c.w.coef[it];
     int score = 0;
     if (nz)
     {
-#pragma unroll
+#pragma unroll (ROLL ? 1 : 16)
         for (int i = 0; i < 16; i++) out[i] = (int16_t)co[i];
         score = decimate_score(out, ch);
-        dequant4x4(co, t.dequant4_mf[ch], ch ? t.chroma_qp : t.qp);
-#pragma unroll
+        dequant4x4<ROLL>(co, t.dequant4_mf[ch], ch ? t.chroma_qp : t.qp);
+#pragma unroll (ROLL ? 1 : 16)
         for (int i = 0; i < 16; i++) out[i] = (int16_t)co[i];
     }
     return score | (nz << 8);
@@ -555,7 +562,7 @@ PCAMV_FN int probe_pskip(MbCtx &c)
     int score = 0;
     PCAMV_FOR_ITEMS(blk, 16)
     {
-        const int v = quant_block(c, blk, dcs);
+        const int v = quant_block<1>(c, blk, dcs);
         if (v >> 8) score += v & 0xff;
     }
     score = team_sum(score);
@@ -577,7 +584,7 @@ PCAMV_FN int probe_pskip(MbCtx &c)
         int sc = 0;
         PCAMV_FOR_ITEMS(blk, 4)
         {
-            const int v = quant_block(c, 16 + 4 * pl + blk, dcs);
+            const int v = quant_block<1>(c, 16 + 4 * pl + blk, dcs);
             if (v >> 8) sc += v & 0xff;
         }
         team_sync();

@@ -362,7 +362,12 @@ __global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_const
 }
 
 // blockIdx.y = frame of the batch
-__global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table_batch(const BatchItem *__restrict__ items, int n_mb)
+// independent macroblocks, nothing to wait for: more resident teams hide more latency (6 CTAs per SM = 80 registers per
+// thread: 60 ms per 128 frames against 66 ms at the unconstrained 96 registers; 8 CTAs = 64 registers: 59 ms)
+#ifndef PCAMV_CT_MIN_CTAS
+#define PCAMV_CT_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(CT_WARPS * 32, PCAMV_CT_MIN_CTAS) k_cost_table_batch(const BatchItem *__restrict__ items, int n_mb)
 {
     const BatchItem &it = items[blockIdx.y];
     cost_table_team(it.fc, it.fp, blockIdx.x * CT_WARPS + (threadIdx.x >> 5), n_mb);

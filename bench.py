@@ -212,6 +212,7 @@ def run_reference_arm(args, pcamv, rank, world):
     from concurrent.futures import ThreadPoolExecutor
     cores = max(1, min(os.cpu_count() or 1, 64))
     workdir = tempfile.mkdtemp(prefix="pcamv_bench_ref_")
+    pcamv.build.build_synth()            # once, before the worker threads need it
     dirs = []
     for i in range(cores):
         d = os.path.join(workdir, "s%d" % i)

@@ -2,6 +2,7 @@
 import os
 import subprocess
 import sys
+import threading
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
@@ -38,21 +39,31 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
-def build_tool(name, src, extra=()):
-    """gcc/g++ helper for the small host tools (synth generator, emulation checkers)."""
+_tool_lock = threading.Lock()
+
+
+def build_tool(name, src, extra=(), deps=None):
+    """gcc/g++ helper for the small host tools (synth generator, emulation checkers).  `deps`: the files the tool is built
+    from besides `src` (default: everything under csrc/, which the emulation checkers include).  Safe to call from several
+    threads: one build at a time, and the binary is replaced atomically (a running copy is never written to)."""
     out_dir = os.path.join(ROOT, "build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, name)
-    if _newer(out, [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]):
-        return out
-    cc = "g++" if src.endswith(".cpp") else "gcc"
-    std = ["-std=c++17"] if cc == "g++" else []
-    subprocess.check_call([cc, "-O2", "-w"] + std + ["-o", out, src] + list(extra))
+    if deps is None:
+        deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    with _tool_lock:
+        if _newer(out, [src] + list(deps)):
+            return out
+        cc = "g++" if src.endswith(".cpp") else "gcc"
+        std = ["-std=c++17"] if cc == "g++" else []
+        tmp = "%s.tmp.%d" % (out, os.getpid())
+        subprocess.check_call([cc, "-O2", "-w"] + std + ["-o", tmp, src] + list(extra))
+        os.replace(tmp, out)
     return out
 
 
 def build_synth():
-    return build_tool("pcamv_synth", os.path.join(ROOT, "synth", "pcamv_synth.c"))
+    return build_tool("pcamv_synth", os.path.join(ROOT, "synth", "pcamv_synth.c"), deps=[])
 
 
 if __name__ == "__main__":

@@ -542,7 +542,7 @@ def main():
             elided["value"] = cand_all / (elided["ms_per_step"] * 1e-3) / 1e6
             elided["unit"] = "Mcandidates/s"
             line["pass2_elided"] = elided
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # (CPU and whole-encoder legs: rank 0 at N = 1 only)
             line["cpu_baseline"] = cpu_baseline_block(pcamv, clip, workdir)
             line["encoder_e2e"] = encoder_e2e(pcamv, workdir, local_rank)
             line["encoder_e2e_sharded"] = encoder_e2e_sharded(pcamv, workdir, local_rank)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PCAMV_ABI_VERSION 4
+#define PCAMV_ABI_VERSION 5
 #define PCAMV_MAX_REFS 16
 #define PCAMV_MAX_MVC 10
 

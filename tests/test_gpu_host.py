@@ -27,6 +27,11 @@ CASES = [
     ("cif_esa32_ref4", 352, 288, 6, 1, 32, "x264_wide", "--qp 26 --ref 4 --keyint 250 --me esa --merange 32 --subme 5 --emrate 0.2"),
     ("cif_p4x4_hex5", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --partitions p8x8,p4x4 --emrate 0.2"),
     ("cif_p4x4_umh_ref3", 352, 288, 8, 1, 24, "x264_wide", "--qp 24 --ref 3 --keyint 250 --me umh --subme 4 --partitions all --emrate 0.3"),
+    # tiny frames: one macroblock, one macroblock row / column, and a 3x2 frame whose messages are shorter than the STC matrix height
+    ("tiny_16x16", 16, 16, 5, 1, 32, "x264_wide", "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3"),
+    ("tiny_1024x16", 1024, 16, 4, 1, 32, "x264_wide", "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3"),
+    ("tiny_16x512", 16, 512, 4, 1, 32, "x264_wide", "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3"),
+    ("tiny_48x32", 48, 32, 6, 1, 32, "x264_wide", "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3"),
     ("720p_umh5", 1280, 720, 4, 5, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"),
     # option coverage (the reference Makefile's OPT0..OPT7 flag sets, Makefile:108-115, restricted to the supported path)
     ("cif_nocabac", 352, 288, 8, 1, 16, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --no-cabac --emrate 0.2"),
@@ -63,7 +68,7 @@ def test_bitstream_identical(pcamv, cuda_lib, case, tmp_path):
     if not os.path.exists(HOST):
         pytest.fail("host/_build/x264_pcamv is not built (host/build_host.py)")
     ref_out, out, stats = encode_pair(pcamv, *case, workdir=str(tmp_path))
-    assert os.path.getsize(out) > 1000
+    assert os.path.getsize(out) > (1000 if case[1] * case[2] > 20000 else 100)
     assert md5(out) == md5(ref_out), "bitstream differs from the reference (%d vs %d bytes)" % (os.path.getsize(out), os.path.getsize(ref_out))
     assert stats["gpu_launches"] > 0 and stats["replayed_calls"] > 0
 

@@ -55,17 +55,20 @@ def test_stc_embed_matches_reference_golden(pcamv, cuda_lib, name, tmp_path):
 
 
 @pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/x264_dump not built")
-@pytest.mark.parametrize("size,emrate,extra", [((352, 288), "0.2", ""), ((352, 288), "0.1", "--partitions all"), ((1280, 720), "0.3", ""),
+@pytest.mark.parametrize("size,emrate,extra", [((48, 32), "0.3", "--ref 2"),        # messages shorter than the matrix height: the reference's
+                                               ((64, 48), "0.5", ""),               # forward and backward column masks differ (embed.h:415,519-524)
+                                               ((352, 288), "0.2", ""), ((352, 288), "0.1", "--partitions all"), ((1280, 720), "0.3", ""),
                                                ((1920, 1080), "0.2", "")])
 def test_stc_embed_matches_reference_live(pcamv, cuda_lib, size, emrate, extra, tmp_path):
     w, h = size
     frames = 6 if w < 1000 else 3
+    tiny = w < 100
     clip = refrun.synth_clip(pcamv, w, h, frames, config=2, stream=3, workdir=str(tmp_path))
     dump = str(tmp_path / "d.bin")
     refrun.run_ref(clip, w, h, ("--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --emrate %s %s" % (emrate, extra)).split(), dump=dump,
                    planes=False, calls=False)
     n_ok, bits = check_embeds(pcamv, pcamv.dumpfmt.Dump(dump).embeds())
-    assert n_ok == frames - 1 and bits > 100
+    assert n_ok == frames - 1 and bits > (5 if tiny else 100)
 
 
 def test_stc_embed_unembeddable_and_bad_arguments(pcamv, cuda_lib):

@@ -26,7 +26,11 @@
 
 namespace pcamv {
 
-struct StcElem { uint32_t col; uint8_t last, msg, pad[2]; };     // per cover element: masked column, end-of-block flag, block's message bit
+// per cover element: the column as the forward pass masks it, as the backward trace masks it, end-of-block flag, the block's
+// message bit.  The two masks agree whenever the message has at least `matrixheight` bits; for shorter messages the
+// reference's forward pass starts from the full mask and only then shrinks it (embed.h:415,482-483) while its backward
+// trace grows the mask from zero (embed.h:519-524), and both are reproduced as they are.
+struct StcElem { uint32_t col, colb; uint8_t last, msg, pad[2]; };
 
 template <int H>
 __global__ void __launch_bounds__(1 << H) k_stc_forward(const uint8_t *__restrict__ cover, const float *__restrict__ rho,
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(32) k_stc_backward(const StcElem *__restrict__
             const uint32_t word = __shfl_sync(0xffffffffu, line[k], (int)(state >> 5));
             const uint32_t bit = (word >> (state & 31)) & 1u;
             if (lane == 0) stego[idx] = (uint8_t)bit;
-            if (bit) state ^= e.col;
+            if (bit) state ^= e.colb;
         }
     }
 }
@@ -131,9 +135,12 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
         worm += width;
         if (index + width > n)
             return ctx_fail(ctx, "pcamv_stc_embed: block schedule overruns the cover", cudaSuccess);
+        const int left = an - b;                              // blocks from here to the end
+        const uint32_t backmask = left <= matrixheight ? (1u << left) - 1u : (1u << matrixheight) - 1u;
         for (int k = 0; k < width; k++, index++)
         {
             el[index].col = cols[k] & colmask;
+            el[index].colb = cols[k] & backmask;
             el[index].last = k == width - 1;
             el[index].msg = message[b] ? 1 : 0;
             el[index].pad[0] = el[index].pad[1] = 0;

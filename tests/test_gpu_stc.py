@@ -40,7 +40,12 @@ def check_embeds(pcamv, embeds):
         if not (2 <= shorter and longer <= 20):
             continue
         stego = ctx.stc_embed(e["cover"], e["message"][:an], e["rho"], columns(shorter), columns(longer))
-        assert stego is not None, "frame %d: GPU trellis reports the message as not embeddable" % e["frame"]
+        if stego is None:
+            # "not in the range of the syndrome matrix": the reference's stc_embed then returns 0 and leaves the zeroed stego
+            # buffer alone (encoder/encoder.c:1826,1843) — happens for messages shorter than the matrix height
+            assert not e["stego"].any(), "frame %d: GPU trellis reports the message as not embeddable, the reference embedded it" % e["frame"]
+            n_ok += 1
+            continue
         assert np.array_equal(stego, e["stego"]), "frame %d: stego vector differs from the reference's (%d of %d bits)" % (
             e["frame"], int((stego != e["stego"]).sum()), n)
         n_ok += 1; bits += an

@@ -27,6 +27,9 @@ CASES = [
     ("cif_esa32_ref4", 352, 288, 6, 1, 32, "x264_wide", "--qp 26 --ref 4 --keyint 250 --me esa --merange 32 --subme 5 --emrate 0.2"),
     ("cif_p4x4_hex5", 352, 288, 8, 1, 32, "x264_wide", "--qp 26 --ref 1 --keyint 250 --me hex --subme 5 --partitions p8x8,p4x4 --emrate 0.2"),
     ("cif_p4x4_umh_ref3", 352, 288, 8, 1, 24, "x264_wide", "--qp 24 --ref 3 --keyint 250 --me umh --subme 4 --partitions all --emrate 0.3"),
+    # skip-heavy (38 % P_SKIP): pass-2 probes succeed on macroblocks pass 1 coded, the host keeps b_skip_mc set (quirk q1) and the
+    # residual is taken against what its intra analysis left in fdec — those macroblocks are exempt from pass-2 elision
+    ("cif_qp48_skips", 352, 288, 6, 1, 24, "x264_wide", "--qp 48 --ref 2 --keyint 250 --me umh --subme 4 --emrate 0.2"),
     # tiny frames: one macroblock, one macroblock row / column, and a 3x2 frame whose messages are shorter than the STC matrix height
     ("tiny_16x16", 16, 16, 5, 1, 32, "x264_wide", "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3"),
     ("tiny_1024x16", 1024, 16, 4, 1, 32, "x264_wide", "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3"),

@@ -7,11 +7,13 @@ import numpy as np
 import pcamv_loader, refrun, frame_parity, test_gpu_stc
 pcamv = pcamv_loader.load()
 w, h = int(sys.argv[1]), int(sys.argv[2])
+ARGS = sys.argv[3] if len(sys.argv) > 3 else "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3"
+SYNTH = sys.argv[4].split() if len(sys.argv) > 4 else ["6", "1", "0", "32"]
 wd = tempfile.mkdtemp()
 clip = os.path.join(wd, "e.yuv")
-subprocess.check_call([os.path.join(ROOT, "build", "pcamv_synth"), str(w), str(h), "6", "1", "0", clip, "32"])
+subprocess.check_call([os.path.join(ROOT, "build", "pcamv_synth"), str(w), str(h), SYNTH[0], SYNTH[1], SYNTH[2], clip, SYNTH[3]])
 dumpf = os.path.join(wd, "d.bin")
-refrun.run_ref(clip, w, h, "--qp 26 --ref 2 --keyint 250 --me umh --subme 5 --emrate 0.3".split(), dump=dumpf)
+refrun.run_ref(clip, w, h, ARGS.split(), dump=dumpf)
 dump = pcamv.dumpfmt.Dump(dumpf)
 for s in dump.slices():
     if not s.with_planes: continue

@@ -1060,7 +1060,11 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
         return;
     }
 
-    if (forced && forced->used && fc.pass2_elide)
+    // Elision has one exception.  When this pass's probe found the macroblock skippable but pass 1 did not (the re-run above),
+    // the host keeps b_skip_mc set (quirk q1, analyse.c:2663-2668 / encoder/macroblock.c:611-612): x264_macroblock_encode then
+    // takes the residual against whatever the analysis left in fdec, and that is the host's INTRA analysis, whose early-outs
+    // compare against the inter cost of the "dead" searches and refinement.  Such macroblocks get the full analysis.
+    if (forced && forced->used && fc.pass2_elide && !early_skip)
     {
         // pass 2, decision forced from pass 1: nothing the remaining searches produce survives analyse.c:2868-2991
         // (info.cache[].i_partition is only written for P_L0, analyse.c:3612: a forced P_8x8 is 8x8 by construction)

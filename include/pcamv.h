@@ -71,7 +71,11 @@ typedef struct pcamv_cfg
                                16x16 search — the one result of that pass the reference still uses (h->mb.mvr candidates of later
                                macroblocks, early-skip detection); the 8x8 / 16x8 / 8x16 searches and the refinement, whose
                                results the reference overwrites at encoder/analyse.c:2868-2991, are not executed and do not
-                               appear in the log.  0: pass 2 executes and logs everything the reference executes. */
+                               appear in the log.  Exempt (full analysis, complete log): macroblocks whose pass-2 probe
+                               finds them skippable although pass 1 coded them — the host keeps b_skip_mc set there and
+                               its residual depends on the intra analysis, which prunes against those "dead" costs.
+                               Ignored with sub-8x8 partitions (a forced P_8x8 keeps the partition pass 2 decided).
+                               0: pass 2 executes and logs everything the reference executes. */
     int reserved[6];
 } pcamv_cfg;
 

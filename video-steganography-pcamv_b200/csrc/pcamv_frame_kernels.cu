@@ -67,11 +67,15 @@ __device__ __forceinline__ void analyse_row(const DevFrameCtx &fc, const FramePa
             // issue slots from the ones doing the work
             // (a macroblock takes ~150 us, so polling every few microseconds costs no latency worth the name, while
             // tight polling by the waiting half of the resident warps was measured at two thirds of all issued instructions)
-            unsigned ns = 64;
+#ifndef PCAMV_POLL_NS_MIN
+#define PCAMV_POLL_NS_MIN 64
+#define PCAMV_POLL_NS_MAX 4096
+#endif
+            unsigned ns = PCAMV_POLL_NS_MIN;
             while (ld_acquire(fp.row_progress + row - 1) < need)
             {
                 __nanosleep(ns);
-                if (ns < 4096) ns <<= 1;
+                if (ns < PCAMV_POLL_NS_MAX) ns <<= 1;
             }
         }
         c.mb_x = x; c.mb_y = row; c.mb_xy = row * mb_w + x;

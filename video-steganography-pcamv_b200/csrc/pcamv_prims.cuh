@@ -223,6 +223,8 @@ PCAMV_DEV uint32_t abs2(uint32_t a)
     return (a + s) ^ s;
 }
 
+PCAMV_DEV int imax_abs(int a, int b) { a = a < 0 ? -a : a; b = b < 0 ? -b : b; return a > b ? a : b; }
+
 #define PCAMV_HADAMARD4(d0, d1, d2, d3, s0, s1, s2, s3) \
     { uint32_t t0 = (s0) + (s1), t1 = (s0) - (s1), t2 = (s2) + (s3), t3 = (s2) - (s3); \
       d0 = t0 + t2; d2 = t0 - t2; d1 = t1 + t3; d3 = t1 - t3; }
@@ -255,31 +257,36 @@ PCAMV_DEV uint32_t hadamard_8x4_sum(const uint32_t f[4], const uint32_t g[4], co
 }
 
 // Sum of |4x4 Hadamard coefficients| of one 4x4 block, NOT yet halved (common/pixel.c:187-207).
+// Two differences per word throughout: the even and the odd bytes of a row are split with one mask each, so one
+// subtraction yields (d0, d2) and one (d1, d3) in the x + (y << 16) representation the reference's own packing uses;
+// sums and differences of such words are the packed sums and differences as long as every half stays within 16 bits
+// (|coefficient| <= 16 * 255).  The first horizontal butterfly and the whole vertical transform run on packed words; the
+// last horizontal butterfly is never formed: |a + b| + |a - b| = 2 * max(|a|, |b|).
+PCAMV_DEV int pk_lo(uint32_t p) { return (int)(int16_t)(p & 0xffffu); }
+PCAMV_DEV int pk_hi(uint32_t p) { return ((int)p - pk_lo(p)) >> 16; }
 PCAMV_DEV uint32_t hadamard_4x4_sum(const uint32_t f[4], const uint32_t a[4])
 {
-    uint32_t tmp[4][2];
+    const uint32_t m = 0x00ff00ffu;
+    uint32_t x[4], y[4];
 #pragma unroll
     for (int r = 0; r < 4; r++)
     {
-        uint32_t a0 = (uint32_t)(px(f[r], 0) - px(a[r], 0));
-        uint32_t a1 = (uint32_t)(px(f[r], 1) - px(a[r], 1));
-        uint32_t b0 = (a0 + a1) + ((a0 - a1) << 16);
-        uint32_t a2 = (uint32_t)(px(f[r], 2) - px(a[r], 2));
-        uint32_t a3 = (uint32_t)(px(f[r], 3) - px(a[r], 3));
-        uint32_t b1 = (a2 + a3) + ((a2 - a3) << 16);
-        tmp[r][0] = b0 + b1;
-        tmp[r][1] = b0 - b1;
+        const uint32_t de = (f[r] & m) - (a[r] & m);                   // (d0, d2)
+        const uint32_t dq = ((f[r] >> 8) & m) - ((a[r] >> 8) & m);     // (d1, d3)
+        x[r] = de + dq;                                               // (d0 + d1, d2 + d3)
+        y[r] = de - dq;                                               // (d0 - d1, d2 - d3)
     }
-    uint32_t sum = 0;
+    uint32_t xv[4], yv[4];
+    PCAMV_HADAMARD4(xv[0], xv[1], xv[2], xv[3], x[0], x[1], x[2], x[3]);
+    PCAMV_HADAMARD4(yv[0], yv[1], yv[2], yv[3], y[0], y[1], y[2], y[3]);
+    int sum = 0;
 #pragma unroll
-    for (int c = 0; c < 2; c++)
+    for (int k = 0; k < 4; k++)
     {
-        uint32_t a0, a1, a2, a3;
-        PCAMV_HADAMARD4(a0, a1, a2, a3, tmp[0][c], tmp[1][c], tmp[2][c], tmp[3][c]);
-        a0 = abs2(a0) + abs2(a1) + abs2(a2) + abs2(a3);
-        sum += (a0 & 0xffffu) + (a0 >> 16);
+        sum += imax_abs(pk_lo(xv[k]), pk_hi(xv[k]));
+        sum += imax_abs(pk_lo(yv[k]), pk_hi(yv[k]));
     }
-    return sum;
+    return (uint32_t)(2 * sum);
 }
 
 PCAMV_DEV int clip3(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }

@@ -44,8 +44,8 @@ SHARD_MAIN = r'''
 #include <pthread.h>
 void pcamv_glue_set_shards( int n );
 void pcamv_glue_shard_done( void );
-void pcamv_glue_set_shard_index( int i );
-typedef struct { x264_param_t param; cli_opt_t opt; int ret, index; char out[1024]; } pcamv_shard_t;
+void pcamv_glue_set_shard_index( int i, int gop );
+typedef struct { x264_param_t param; cli_opt_t opt; int ret, index, gop; char out[1024]; } pcamv_shard_t;
 /* `x264_pcamv --extract STEGO -o MESSAGE`: STEGO holds, per embedded frame in coding order, int32 frame, length, an and the
  * `length` stego LSBs (what the encoder writes with PCAMV_STEGO=<file>; a decoder-side MV parser would deliver the same
  * vector); MESSAGE receives int32 frame, an and the `an` recovered payload bits.  Frames that carried nothing (an <= 0) are
@@ -82,14 +82,14 @@ static int pcamv_extract_main( int argc, char **argv )
 static void *pcamv_shard_thread( void *p )
 {
     pcamv_shard_t *s = (pcamv_shard_t *)p;
-    pcamv_glue_set_shard_index( s->index );
+    pcamv_glue_set_shard_index( s->index, s->gop );
     s->ret = Encode( &s->param, &s->opt );
     pcamv_glue_shard_done();
     return NULL;
 }
 int main( int argc, char **argv )
 {
-    int n, k, g, i, o_at = -1, ret = 0;
+    int n, k, g, i, o_at = -1, ret = 0, first = 0, step = 1, keep = 0, a0 = 5;
     pcamv_shard_t *sh;
     pthread_t *th;
     FILE *fo;
@@ -106,25 +106,38 @@ int main( int argc, char **argv )
         return x264_cli_main( argc, argv );
     n = atoi( argv[2] ); k = atoi( argv[4] );
     if( n < 1 || k < 1 ) { fprintf( stderr, "x264 [error]: bad --shards / --shard-frames\n" ); return -1; }
-    for( i = 5; i < argc - 1; i++ )
+    /* optional, right after --shard-frames K: --shard-first F --shard-step S (shard i encodes GOP F + i*S: the share of one
+     * rank when the GOPs of a job are dealt round-robin to several processes / GPUs), --shard-keep (leave the per-GOP
+     * streams "<out>.<gop>" in place for the launcher to concatenate) */
+    while( a0 < argc - 1 )
+    {
+        if( !strcmp( argv[a0], "--shard-first" ) ) { first = atoi( argv[a0 + 1] ); a0 += 2; }
+        else if( !strcmp( argv[a0], "--shard-step" ) ) { step = atoi( argv[a0 + 1] ); a0 += 2; }
+        else if( !strcmp( argv[a0], "--shard-keep" ) ) { keep = 1; a0 += 1; }
+        else break;
+    }
+    if( first < 0 || step < 1 ) { fprintf( stderr, "x264 [error]: bad --shard-first / --shard-step\n" ); return -1; }
+    for( i = a0; i < argc - 1; i++ )
         if( !strcmp( argv[i], "-o" ) || !strcmp( argv[i], "--output" ) ) o_at = i + 1;
     if( o_at < 0 ) { fprintf( stderr, "x264 [error]: --shards needs -o\n" ); return -1; }
     sh = calloc( n, sizeof(*sh) ); th = calloc( n, sizeof(*th) );
     for( g = 0; g < n; g++ )
     {
-        /* the shard's command line: the user's arguments, its own output file, --seek g*K --frames K */
+        /* the shard's command line: the user's arguments, its own output file, --seek gop*K --frames K */
         char **av = calloc( argc + 8, sizeof(char *) ), seek[32], frames[32];
         int ac = 0;
+        const int gop = first + g * step;
         av[ac++] = argv[0];
-        snprintf( sh[g].out, sizeof(sh[g].out), "%s.%d", argv[o_at], g );
-        snprintf( seek, sizeof(seek), "%d", g * k ); snprintf( frames, sizeof(frames), "%d", k );
+        snprintf( sh[g].out, sizeof(sh[g].out), "%s.%d", argv[o_at], gop );
+        snprintf( seek, sizeof(seek), "%d", gop * k ); snprintf( frames, sizeof(frames), "%d", k );
         av[ac++] = "--seek"; av[ac++] = strdup( seek ); av[ac++] = "--frames"; av[ac++] = strdup( frames );
-        for( i = 5; i < argc; i++ ) av[ac++] = i == o_at ? sh[g].out : argv[i];
+        for( i = a0; i < argc; i++ ) av[ac++] = i == o_at ? sh[g].out : argv[i];
         optind = 0;                                   /* getopt state is global: shards are parsed one after the other */
         x264_param_default( &sh[g].param );
         if( Parse( ac, av, &sh[g].param, &sh[g].opt ) < 0 ) return -1;
         sh[g].opt.b_progress = 0;
         sh[g].index = g;
+        sh[g].gop = gop;
     }
     {
         /* the reference fills several global tables the first time an encoder opens (x264_rdo_init, x264_init_vlc_tables,
@@ -146,7 +159,7 @@ int main( int argc, char **argv )
         char buf[1 << 16]; size_t r;
         if( !fi ) { ret = -1; continue; }
         while( ( r = fread( buf, 1, sizeof(buf), fi ) ) > 0 ) fwrite( buf, 1, r, fo );
-        fclose( fi ); remove( sh[g].out );
+        fclose( fi ); if( !keep ) remove( sh[g].out );
     }
     fclose( fo );
     return ret;
@@ -198,7 +211,7 @@ def main():
     tree = os.path.join(OUT, "tree")
     reftree.copy_tree(tree)
     reftree.widen(tree)
-    reftree.hook_call_sites(tree, HOOK_DECL, IH_WRAPPER, analyse_extra=ANALYSE_EXTRA)
+    reftree.hook_call_sites(tree, HOOK_DECL, IH_WRAPPER, analyse_extra=ANALYSE_EXTRA, drop_real=True)
     shard_driver(tree)
     exe = os.path.join(OUT, "x264_pcamv")
     reftree.compile_tree(tree, exe,

@@ -25,9 +25,8 @@
 #include "pcamv.h"
 #include <time.h>
 #include <pthread.h>
+#include <unistd.h>
 
-void x264_me_search_ref_real( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
-void x264_me_refine_qpel_real( x264_t *h, x264_me_t *m );
 void pcamv_glue_load_costs( x264_t *h, int qp );      /* added to encoder/analyse.c by host/build_host.py */
 
 extern int16_t *g_cost_mv[52];            /* reference encoder/analyse.c:189 (malloc base, centre at +2*4*2048) */
@@ -92,11 +91,14 @@ void pcamv_glue_set_shards( int n )
 /* this encoder thread's context (the embed-stage hook in the encoder.c translation unit needs it) */
 pcamv_ctx *pcamv_glue_ctx( void ) { return g.ctx; }
 
-/* called first thing by a shard's thread */
-void pcamv_glue_set_shard_index( int i )
+/* called first thing by a shard's thread: i = its index in this process (decides the group), gop = the GOP it encodes
+ * (names its side files).  Group membership starts HERE, not at x264_encoder_open: a shard whose Encode() fails before it
+ * ever opens an encoder must still leave its group, or its siblings would wait for it forever. */
+void pcamv_glue_set_shard_index( int i, int gop )
 {
     g_group = g_n_groups ? g_groups[i % g_n_groups] : NULL;
-    g_shard = i;
+    g_in_group = g_group != NULL;
+    g_shard = gop;
 }
 
 /* side files (PCAMV_PAYLOAD, PCAMV_STEGO): one per shard ("<name>.<shard>") when several encoders share the process */
@@ -143,15 +145,19 @@ static double now_s( void )
     return ts.tv_sec + 1e-9*ts.tv_nsec;
 }
 
+/* fatal errors end the process at once (_exit): with several encoder threads in one process, exit() would run the
+ * teardown of the CUDA runtime while sibling shards sit inside CUDA calls or wait on their group, which can hang */
 static void die( const char *what )
 {
     fprintf( stderr, "x264 [pcamv]: %s: %s\n", what, g.ctx ? pcamv_last_error( g.ctx ) : pcamv_last_error( NULL ) );
-    exit( 3 );
+    fflush( stderr );
+    _exit( 3 );
 }
 static void die_msg( const char *msg )
 {
     fprintf( stderr, "x264 [pcamv]: %s\n", msg );
-    exit( 3 );
+    fflush( stderr );
+    _exit( 3 );
 }
 
 /* ---- open / close ---------------------------------------------------------------------------- */
@@ -205,7 +211,6 @@ void pcamv_hook_open( x264_t *h )
      * under the lock, so that concurrent encoders only ever read them */
     pcamv_glue_load_costs( h, h->param.rc.i_qp_constant );
     pthread_mutex_unlock( &g_mu );
-    g_in_group = g_group != NULL;
     g.n_mb = h->sps->i_mb_width * h->sps->i_mb_height;
     g.n_slots = cfg.max_refs + 2;
     g.pinned = !((s = getenv( "PCAMV_NO_PINNED" )) && atoi( s ));
@@ -386,13 +391,13 @@ void pcamv_hook_analyse_end( x264_t *h )
         if( elided ? g.cur_pos < r->n_log : g.cur_pos != r->n_log )
         {
             fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host made %d search calls, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, r->n_log );
-            exit( 4 );
+            fflush( stderr ); _exit( 4 );
         }
         if( h->mb.i_type != r->type || ( r->type != P_SKIP && h->mb.i_partition != r->partition ) )
         {
             fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host decided type %d partition %d, GPU %d / %d\n",
                      h->i_frame, g.cur_mb, h->mb.i_type, h->mb.i_partition, r->type, r->partition );
-            exit( 4 );
+            fflush( stderr ); _exit( 4 );
         }
     }
 }
@@ -411,14 +416,14 @@ static const pcamv_log_entry *next_entry( x264_t *h, x264_me_t *m, int kind )
     if( g.cur_pos >= g.log_stride || g.cur_pos >= g.mbs[g.cur_mb].n_log )
     {
         fprintf( stderr, "x264 [pcamv]: frame %d mb %d: host asks for call %d, GPU logged %d\n", h->i_frame, g.cur_mb, g.cur_pos, g.mbs[g.cur_mb].n_log );
-        exit( 4 );
+        fflush( stderr ); _exit( 4 );
     }
     e = &g.log[(size_t)g.cur_mb * g.log_stride + g.cur_pos];
     if( e->kind != kind || e->i_pixel != m->i_pixel )
     {
         fprintf( stderr, "x264 [pcamv]: frame %d mb %d call %d: host wants kind %d pixel %d, GPU logged kind %d pixel %d\n",
                  h->i_frame, g.cur_mb, g.cur_pos, kind, m->i_pixel, e->kind, e->i_pixel );
-        exit( 4 );
+        fflush( stderr ); _exit( 4 );
     }
     g.cur_pos++;
     g.n_replayed++;

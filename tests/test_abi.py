@@ -55,3 +55,22 @@ def test_open_rejects_bad_arguments(pcamv, cuda_lib):
     cfg.abi_version = cuda_lib.pcamv_abi_version()
     cfg.width, cfg.height, cfg.max_refs = 100, 100, 1       # not multiples of 16
     assert cuda_lib.pcamv_open(ctypes.byref(h), ctypes.byref(cfg)) == -1
+
+
+def test_host_encoder_carries_no_cpu_search():
+    """No CPU fallback, provable with nm: the GPU host links the reference's C encoder WITHOUT the reference's own motion
+    search (x264_me_search_ref / refine_subpel / x264_me_refine_qpel bodies, x264_ih_get_mv_cost) — the only
+    x264_me_search_ref in the binary is the replay stub of host/pcamv_x264_glue.c, which pops GPU results."""
+    import subprocess
+    exe = os.path.join(ROOT, "host", "_build", "x264_pcamv")
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("host/_build/x264_pcamv is not built")
+    syms = subprocess.run(["nm", exe], capture_output=True, text=True, check=True).stdout
+    names = [l.split()[-1] for l in syms.splitlines() if l.strip()]
+    for bad in ("x264_me_search_ref_real", "x264_me_refine_qpel_real", "x264_ih_get_mv_cost_real", "refine_subpel"):
+        assert bad not in names, "%s is linked into the GPU host" % bad
+    assert "x264_me_search_ref" in names and "pcamv_hook_slice_begin" in names
+    # and it is bound to the CUDA library, not to a CPU copy of it
+    dyn = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True, check=True).stdout
+    assert "pcamv_analyse_p" in dyn and "pcamv_open" in dyn

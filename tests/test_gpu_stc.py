@@ -84,4 +84,8 @@ def test_stc_embed_unembeddable_and_bad_arguments(pcamv, cuda_lib):
     assert ctx.stc_embed(cover, msg, rho, c5, c5) is None
     with pytest.raises(pcamv.PcamvError, match="widths"):
         pcamv.PcamvContext(176, 144).stc_embed(cover, msg, np.ones(50, np.float32), columns(4), c5)
+    # an even column would make the per-state survivor rule differ from the reference's pairwise update once masked to zero
+    even = np.array(c5, dtype=np.uint32).copy(); even[2] &= ~np.uint32(1)
+    with pytest.raises(pcamv.PcamvError, match="odd"):
+        pcamv.PcamvContext(176, 144).stc_embed(cover, msg, np.ones(50, np.float32), even, c5)
     ctx.close()

@@ -103,10 +103,13 @@ def compile_tree(tree, exe, extra_sources=(), extra_cflags=(), extra_ldflags=(),
     return exe
 
 
-def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra=""):
+def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra="", drop_real=False):
     """The anchored edits both instrumented builds share: calls to pcamv_hook_* at the frame-level points, the search
     entry points renamed *_real (the hook file defines the originals' names), and a wrapper in front of
-    x264_ih_get_mv_cost.  (file:line of the reference in oracle/ref_hooks.c / host/pcamv_x264_glue.c.)"""
+    x264_ih_get_mv_cost.  (file:line of the reference in oracle/ref_hooks.c / host/pcamv_x264_glue.c.)
+    drop_real: the GPU host never calls the reference's own searches, so there the renamed originals become unused statics
+    and the compiler drops them (and refine_subpel with them) — `nm x264_pcamv` then shows no CPU search code at all; the
+    instrumented oracle keeps them (its hooks time and count the real functions)."""
     p = os.path.join(tree, "encoder/encoder.c")
     t = read(p)
     t = sub_exact(t, r'(#include "common/common.h"\n)', r"\1" + hook_decl.replace("\\", "\\\\"), 1, "encoder.c include")
@@ -128,8 +131,9 @@ def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra=""):
 
     p = os.path.join(tree, "encoder/me.c")
     t = read(p)
-    t = sub_exact(t, r"\nvoid x264_me_search_ref\(", "\nvoid x264_me_search_ref_real(", 1, "me_search_ref def")
-    t = sub_exact(t, r"\nvoid x264_me_refine_qpel\(", "\nvoid x264_me_refine_qpel_real(", 1, "me_refine_qpel def")
+    lead = "\nstatic __attribute__((unused)) void " if drop_real else "\nvoid "
+    t = sub_exact(t, r"\nvoid x264_me_search_ref\(", lead + "x264_me_search_ref_real(", 1, "me_search_ref def")
+    t = sub_exact(t, r"\nvoid x264_me_refine_qpel\(", lead + "x264_me_refine_qpel_real(", 1, "me_refine_qpel def")
     write(p, t)
 
     p = os.path.join(tree, "encoder/analyse.c")
@@ -138,7 +142,7 @@ def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra=""):
     t = sub_exact(t, r"(#define MV_SATD_FDEC_IH\(mx, my\)\\\n\{\\\n)", r"\1\tpcamv_hook_ih_satd( m->i_pixel, h->mb.b_chroma_me && m->i_pixel <= PIXEL_8x8 );\\\n", 1, "MV_SATD_FDEC_IH")
     # x264_ih_get_mv_cost (encoder/analyse.c:2391): rename the definition and put a wrapper of the same name in front of
     # x264_macroblock_analyse (its only caller, encoder/analyse.c:3557-3673)
-    t = sub_exact(t, r"\nstatic inline int x264_ih_get_mv_cost\(", "\nstatic inline int x264_ih_get_mv_cost_real(", 1, "ih_get_mv_cost def")
+    t = sub_exact(t, r"\nstatic inline int x264_ih_get_mv_cost\(", "\nstatic inline __attribute__((unused)) int x264_ih_get_mv_cost_real(", 1, "ih_get_mv_cost def")
     wrapper = ("static int x264_ih_get_mv_cost( x264_t *h, x264_mb_analysis_t *analysis, x264_me_t *m, int16_t *m_x, int16_t *m_y,\n"
                "    int8_t d_mv[][2], int8_t d_mv_1_neighborhood[][2], int mb_xy )\n" + ih_wrapper_body)
     idx = t.index("\nvoid x264_macroblock_analyse( x264_t *h )\n")

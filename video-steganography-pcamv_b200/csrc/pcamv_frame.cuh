@@ -113,14 +113,21 @@ struct MbCtx
 
 PCAMV_FN void log_push(MbCtx &c, int kind, int i_pixel, int i_ref, int mvx, int mvy, int cost, int cost_mv)
 {
-    if (c.n_log < c.fp.log_stride && team_lane() == 0)
+    // the counter lives in the team-shared context: every lane reads it before lane 0 alone advances it
+    const int n = c.n_log;
+    team_sync();
+    if (team_lane() == 0)
     {
-        LogEntry e;
-        e.kind = (int8_t)kind; e.i_pixel = (int8_t)i_pixel; e.i_ref = (int8_t)i_ref; e.pad = 0;
-        e.mv[0] = (int16_t)mvx; e.mv[1] = (int16_t)mvy; e.cost = cost; e.cost_mv = cost_mv;
-        c.fp.log[(size_t)c.mb_xy * c.fp.log_stride + c.n_log] = e;
+        if (n < c.fp.log_stride)
+        {
+            LogEntry e;
+            e.kind = (int8_t)kind; e.i_pixel = (int8_t)i_pixel; e.i_ref = (int8_t)i_ref; e.pad = 0;
+            e.mv[0] = (int16_t)mvx; e.mv[1] = (int16_t)mvy; e.cost = cost; e.cost_mv = cost_mv;
+            c.fp.log[(size_t)c.mb_xy * c.fp.log_stride + n] = e;
+        }
+        c.n_log = n + 1;
     }
-    c.n_log++;
+    team_sync();
 }
 
 // ---- neighbour cache -------------------------------------------------------------------------------
@@ -990,7 +997,14 @@ PCAMV_DEV void wait_prev_raster(const MbCtx &c)
     {
         const int *flag = c.fp.row_progress + c.mb_y - 1;
         int v;
-        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); } while (v < c.fc.mb_w);
+        unsigned ns = 64;
+        for (;;)
+        {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v >= c.fc.mb_w) break;
+            __nanosleep(ns);                       // back off: the row above still has macroblocks to go
+            if (ns < 4096) ns <<= 1;
+        }
     }
 #else
     (void)c;

@@ -118,6 +118,14 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
         return ctx_fail(ctx, "pcamv_stc_embed: bad argument", cudaSuccess);
     if (matrixheight < 7 || matrixheight > 10)
         return ctx_fail(ctx, "pcamv_stc_embed: matrix height must be 7..10 (the encoder uses 10)", cudaSuccess);
+    // The per-state survivor rule of k_stc_forward equals the reference's pairwise update (embed.h:439-468) only for columns
+    // whose masked value is non-zero; the mask never drops bit 0, so an odd column is always safe.  Every column getMatrix
+    // can produce is odd (embed.h:276-306: the tabulated ones, and the generated ones have bit 0 forced), so an even one is a
+    // caller error, not a case to emulate.
+    for (int k = 0; k < w_short; k++)
+        if (!(cols_short[k] & 1u)) return ctx_fail(ctx, "pcamv_stc_embed: sub-matrix columns must be odd (bit 0 set)", cudaSuccess);
+    for (int k = 0; k < w_long; k++)
+        if (!(cols_long[k] & 1u)) return ctx_fail(ctx, "pcamv_stc_embed: sub-matrix columns must be odd (bit 0 set)", cudaSuccess);
     // block schedule (embed.h:376-392) and per-element columns with the shrinking mask of the last h blocks (embed.h:482-483)
     const double invalpha = (double)n / an;
     const int shorter = (int)floor(invalpha), longer = (int)ceil(invalpha);
@@ -164,8 +172,7 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
     uint32_t *d_path = (uint32_t *)(ctx->d_stc + o_path); StcElem *d_el = (StcElem *)(ctx->d_stc + o_el);
     float *d_rho = (float *)(ctx->d_stc + o_rho), *d_total = (float *)(ctx->d_stc + o_total);
     uint8_t *d_cover = ctx->d_stc + o_cover, *d_stego = ctx->d_stc + o_stego;
-    auto release = []() {};
-#define SK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return ctx_fail(ctx, #call, e_); } } while (0)
+#define SK(call) CK(call)
     SK(cudaMemcpyAsync(d_cover, cover, used, cudaMemcpyHostToDevice, ctx->stream));
     SK(cudaMemcpyAsync(d_rho, rho, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     SK(cudaMemcpyAsync(d_el, el.data(), used * sizeof(StcElem), cudaMemcpyHostToDevice, ctx->stream));
@@ -181,10 +188,7 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
     SK(cudaStreamSynchronize(ctx->stream));
     ctx->launches += 1;
     if ((double)total_price >= total)
-    {
-        release();
         return 1;               // "The syndrome is not in the range of the syndrome matrix." (embed.h:503-512)
-    }
     switch (matrixheight)
     {
     case 7:  k_stc_backward<7><<<1, 32, 0, ctx->stream>>>(d_el, used, d_path, d_stego); break;
@@ -196,7 +200,6 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
     SK(cudaStreamSynchronize(ctx->stream));
     SK(cudaGetLastError());
     ctx->launches += 1;
-    release();
 #undef SK
     return 0;
 }

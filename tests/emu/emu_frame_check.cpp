@@ -55,6 +55,9 @@ int main(int argc, char **argv)
     std::vector<std::vector<uint16_t>> integral(PCAMV_MAX_REFS), integral4(PCAMV_MAX_REFS);
     std::vector<unsigned long long> mvsads((size_t)(2 * fc.me_range + 4) * (2 * fc.me_range + 1));
 
+    // PCAMV_EMU_ASYNC=1: run the resumable (split wavefront) form of the analysis; not for configurations with sub-8x8 partitions
+    const bool async_mode = getenv("PCAMV_EMU_ASYNC") && atoi(getenv("PCAMV_EMU_ASYNC")) && !(fc.analyse_inter & 0x20);
+    long n_yield = 0;
     long n_call = 0, bad_call = 0, n_mbs = 0, bad_mb = 0, n_ih = 0, bad_ih = 0, n_passes = 0;
     int frames_done = 0;
     for (size_t ri = 0; ri < d.recs.size(); ri++)
@@ -174,7 +177,48 @@ int main(int argc, char **argv)
                 memcpy(work.fenc_u + 8 * y, fc.fenc_u + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
                 memcpy(work.fenc_v + 8 * y, fc.fenc_v + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
             }
-            analyse_p_mb<3>(c, mb ? results[mb - 1].mv : fp.stale_mv);
+            if (!async_mode)
+                analyse_p_mb<3>(c, mb ? results[mb - 1].mv : fp.stale_mv);
+            else
+            {
+                // the split wavefront's protocol on one lane: every search leaves as a request; the macroblock's persistent
+                // bytes (everything before MbWork::fenc_y, and the scalars of MbCtx) are parked, the rest of both structures is
+                // trashed, a "search team" serves the request from a scratch MbWork of its own, and the analysis is resumed
+                static MbWork park, team;
+                static unsigned char park_ctx[sizeof(MbCtx)];
+                work.pt.stage = 0;
+                int guard = 0;
+                while (analyse_p_mb<1, 1>(c, mb ? results[mb - 1].mv : fp.stale_mv) == PT_YIELD)
+                {
+                    n_yield++;
+                    if (++guard > 200) { fprintf(stderr, "mb %d never finishes\n", mb); return 1; }
+                    const size_t keep = offsetof(MbWork, fenc_y), ctx0 = offsetof(MbCtx, mb_x);
+                    memcpy(&park, &work, keep);
+                    memcpy(park_ctx, (unsigned char *)&c + ctx0, sizeof(MbCtx) - ctx0);
+                    const SearchReq rq = work.rq;
+                    memset(&work, 0xA5, sizeof(work));
+                    memset((unsigned char *)&c + ctx0, 0x5A, sizeof(MbCtx) - ctx0);
+                    memset(&team, 0x3C, sizeof(team));
+                    for (int y = 0; y < 16; y++) memcpy(team.fenc_y + 16 * y, fc.fenc_y + (size_t)(16 * rq.mb_y + y) * fc.stride_y + 16 * rq.mb_x, 16);
+                    for (int y = 0; y < 8; y++)
+                    {
+                        memcpy(team.fenc_u + 8 * y, fc.fenc_u + (size_t)(8 * rq.mb_y + y) * fc.stride_c + 8 * rq.mb_x, 8);
+                        memcpy(team.fenc_v + 8 * y, fc.fenc_v + (size_t)(8 * rq.mb_y + y) * fc.stride_c + 8 * rq.mb_x, 8);
+                    }
+                    SearchRes rs;
+                    serve_request<1>(fc, fp, team, rq, rs);
+                    memcpy(&work, &park, keep);
+                    memcpy((unsigned char *)&c + ctx0, park_ctx, sizeof(MbCtx) - ctx0);
+                    work.rs = rs;
+                    // the control side restages the source pixels when it resumes (the P_SKIP probe reads them)
+                    for (int y = 0; y < 16; y++) memcpy(work.fenc_y + 16 * y, fc.fenc_y + (size_t)(16 * c.mb_y + y) * fc.stride_y + 16 * c.mb_x, 16);
+                    for (int y = 0; y < 8; y++)
+                    {
+                        memcpy(work.fenc_u + 8 * y, fc.fenc_u + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
+                        memcpy(work.fenc_v + 8 * y, fc.fenc_v + (size_t)(8 * c.mb_y + y) * fc.stride_c + 8 * c.mb_x, 8);
+                    }
+                }
+            }
             MbResult &res = results[mb];
             // (1) call log
             const std::vector<CallRec> &rc = calls[mb];
@@ -268,6 +312,7 @@ int main(int argc, char **argv)
         n_passes++;
         if (fp.pass != 1) frames_done++;
     }
+    if (async_mode) fprintf(stderr, "async: %ld searches handed out\n", n_yield);
     printf("passes=%ld calls=%ld bad_mb_logs=%ld mbs=%ld bad_decisions=%ld ih=%ld bad_ih=%ld\n", n_passes, n_call, bad_call, n_mbs, bad_mb, n_ih, bad_ih);
     return (bad_call || bad_mb || bad_ih || !n_passes) ? 1 : 0;
 }

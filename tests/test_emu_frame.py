@@ -16,8 +16,11 @@ def checker(pcamv):
     return pcamv.build.build_tool("emu_frame_check", os.path.join(ROOT, "tests", "emu", "emu_frame_check.cpp"))
 
 
-def run_checker(checker, dump):
-    p = subprocess.run([checker, dump], capture_output=True, text=True)
+def run_checker(checker, dump, async_mode=False):
+    env = dict(os.environ, PCAMV_EMU_ASYNC="1") if async_mode else None
+    p = subprocess.run([checker, dump], capture_output=True, text=True, env=env)
+    if async_mode:
+        assert "searches handed out" in p.stderr and int(p.stderr.split("async:")[1].split()[0]) > 1000, p.stderr
     assert p.returncode == 0, p.stdout + p.stderr
     out = dict(kv.split("=") for kv in p.stdout.split())
     assert out["bad_mb_logs"] == "0" and out["bad_decisions"] == "0" and out["bad_ih"] == "0", p.stdout
@@ -28,6 +31,15 @@ def run_checker(checker, dump):
 def test_golden_frames(checker, name, tmp_path):
     n = run_checker(checker, refrun.golden_dump_path(name, str(tmp_path)))
     assert n["passes"] >= 2 and n["calls"] > 1000 and n["ih"] > 100
+
+
+@pytest.mark.parametrize("name", ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"])
+def test_golden_frames_resumable_analysis(checker, name, tmp_path):
+    """The split wavefront's form of the analysis: every search leaves the macroblock as a request, the macroblock's
+    persistent bytes are parked and everything else is overwritten, a separate team serves the request, the analysis
+    resumes — and the records still equal the reference's."""
+    n = run_checker(checker, refrun.golden_dump_path(name, str(tmp_path)), async_mode=True)
+    assert n["passes"] >= 2 and n["calls"] > 1000
 
 
 LIVE = [
@@ -53,3 +65,5 @@ def test_live_reference_frames(pcamv, checker, args, frames, noise, tmp_path):
     refrun.run_ref(clip, 352, 288, ("--qp 26 --keyint 250 --emrate 0.2 " + args).split(), dump=dump, frames=frames)
     n = run_checker(checker, dump)
     assert n["passes"] >= 2 and n["calls"] > 5000
+    if "--partitions" not in args or "p4x4" not in args and "all" not in args:
+        run_checker(checker, dump, async_mode=True)

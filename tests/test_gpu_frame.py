@@ -60,11 +60,12 @@ def test_frame_seam_rejects_unsupported(pcamv, cuda_lib):
     ctx.close()
 
 
-@pytest.mark.parametrize("rows_per_cta", [4, 2, -1], ids=["row-groups-4", "row-groups-2", "row-pool"])
+@pytest.mark.parametrize("rows_per_cta", [4, 2, -1, -2], ids=["row-groups-4", "row-groups-2", "row-pool", "split"])
 def test_batch_launch_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
     """pcamv_analyse_p_batch: several encoder contexts (different frames) analysed by ONE wavefront launch give exactly
-    the records and logs each context gets on its own — for the row-group kernels and for the row pool (rows as resumable
-    tasks claimed by whichever team finds them ready)."""
+    the records and logs each context gets on its own — for the row-group kernels, for the row pool (rows as resumable
+    tasks claimed by whichever team finds them ready) and for the split wavefront (searches served by search SMs, the
+    per-macroblock control code resumed on control SMs, pcamv_split.cu)."""
     import frame_parity
     dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path("qcif_hex5", str(tmp_path)))
     units = [u for u in dump.slice_units() if u["slice"].with_planes and u["slice"].pass_ == 1][:3]
@@ -97,7 +98,7 @@ def test_batch_launch_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
 
 
 @pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/x264_dump not built")
-@pytest.mark.parametrize("rows_per_cta", [4, -1], ids=["row-groups-4", "row-pool"])
+@pytest.mark.parametrize("rows_per_cta", [4, -1, -2], ids=["row-groups-4", "row-pool", "split"])
 def test_batch_pass2_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
     """Pass 2 through a multi-context launch on the P_SKIP-heavy clip, where the 'forced skip keeps the previous macroblock's
     MV cache' quirk (analyse.c:2668-2676) makes row starts depend on the whole previous row: the row-group kernels wait for

@@ -39,6 +39,7 @@ struct pcamv_ctx
     pcamv::PartInfo *d_subparts = nullptr;     // [n_mb][16], only with sub-8x8 partitions enabled
     pcamv::BatchItem *d_batch = nullptr, *h_batch = nullptr; int batch_items_cap = 0;   // leader of a multi-context launch
     int *d_batch_claim = nullptr;
+    unsigned char *d_split = nullptr; size_t split_bytes = 0; int split_warps = 0;     // split wavefront (rows_per_cta = -2): rings, requests, parked rows
     int batch_max_ctas = 0, batch_claim_cap = 0;   // persistent grid size of multi-context launches (0 = not yet computed)
     unsigned long long *d_mvsads = nullptr; int mvsads_cap = 0;    // --me tesa: per-row candidate lists
     unsigned long long *d_seam_mvsads = nullptr;                   // --me tesa, stateless search seam: PCAMV_SEAM_CHUNK lists

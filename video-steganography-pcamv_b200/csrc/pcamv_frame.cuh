@@ -40,20 +40,59 @@ struct MbAnalysis
     int8_t sub[4];                        // h->mb.i_sub_partition
 };
 
-// team-shared scratch of one macroblock
+// One search handed to a search team by the split wavefront (pcamv_split.cu): everything x264_me_search_ref /
+// x264_me_refine_qpel read for one call (the fields of the reference's x264_me_t that are inputs, encoder/me.h:30-51)
+struct SearchReq
+{
+    int32_t item;                // frame of the launch
+    int16_t mb_x, mb_y;
+    int8_t kind;                 // LOG_SEARCH / LOG_REFINE
+    int8_t i_ref, i_pixel, i_mvc;
+    int8_t xoff, yoff, has_thresh, pad;
+    uint32_t mvp;                // packed x | y << 16
+    int32_t thresh;              // *p_halfpel_thresh on entry
+    uint32_t mv;                 // refine: the slot's vector, cost, cost_mv and reference cost on entry
+    int32_t cost, cost_mv, i_ref_cost;
+    int16_t lim[8];              // mv_min_fpel[2], mv_max_fpel[2], mv_min_spel[2], mv_max_spel[2]
+    uint32_t mvc[PCAMV_MAX_MVC];
+    int32_t pad2;                // split wavefront: sequence number of the row slot's request
+};
+static_assert(sizeof(SearchReq) <= 128 && sizeof(SearchReq) % 4 == 0, "a request is copied as up to 32 words");
+struct alignas(16) SearchRes { uint32_t mv; int32_t cost, cost_mv, thresh; };
+static_assert(sizeof(SearchRes) == 16, "a result is one 16-byte store");
+
+// Where the analysis of a macroblock stands when it hands a search to somebody else and is resumed with the result (split
+// wavefront).  The synchronous kernels run the same code and never leave it in the middle.
+enum { PT_DONE = 0, PT_YIELD = 1 };
+struct PtState
+{
+    int8_t stage;                // analyse_p_mb: 0 = not started
+    int8_t in16, in8, in168;     // inside analyse_p16x16 / analyse_p8x8 / analyse_p16x8_8x16
+    int8_t wait;                 // a search has been issued and its result not yet taken
+    int8_t i_ref, i, j;          // loop positions of the function in progress
+    int8_t type, partition, early_skip, b_try_pskip;
+    int32_t i_cost, total;
+};
+
+// team-shared state of one macroblock.  Everything up to `fenc_y` is what has to survive while a search is out (the split
+// wavefront parks exactly those bytes); the rest is scratch that is rebuilt or dead at those points.
 struct alignas(16) MbWork
 {
     int8_t ref[48];          // scan8-indexed neighbour cache, list 0
     uint32_t mv[48];
-    uint8_t fenc_y[256], fenc_u[64], fenc_v[64];
+    MbAnalysis an;           // search results of the partitions tried so far
+    MeSlot slot;             // the search in flight
+    int mvc[PCAMV_MAX_MVC][2];
+    int halfpel_thresh;
+    PtState pt;
+    SearchReq rq;            // the search handed out
+    SearchRes rs;            // ... and its result
+    alignas(16) uint8_t fenc_y[256];
+    uint8_t fenc_u[64], fenc_v[64];
     uint8_t pred_y[256], pred_u[64], pred_v[64];     // MC / reconstruction staging
     int32_t scratch[32];
     int16_t coef[24][16];    // per 4x4 block (16 luma in block_idx order, 4 U, 4 V): quantised / dequantised coefficients
-    MbAnalysis an;           // search results of the partitions tried so far
-    MeSlot slot;             // the search in flight
-    MeBlock blk;             // its block descriptor
-    int mvc[PCAMV_MAX_MVC][2];
-    int halfpel_thresh;
+    MeBlock blk;             // block descriptor of the search in flight (synchronous kernels)
 };
 
 // Search results of the sub-8x8 partitions (reference x264_mb_analysis_t.l0.me4x4 / me8x4 / me4x8, encoder/analyse.c:66-75),
@@ -628,25 +667,143 @@ PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, i
     b.integral4 = rf.integral4 ? rf.integral4 + off : nullptr;
 }
 
-template <int XS>
-PCAMV_FN void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
+// A search is issued in two halves.  AS = 0 (synchronous kernels, emulation): run_search_begin does the whole search and
+// returns 0.  AS = 1 (split wavefront): it only writes the request into w.rq and returns 1 — the caller records where it
+// stands and unwinds with PT_YIELD; when the result is back in w.rs the same code runs again, skips to that point and
+// takes it with run_search_end.
+template <int XS, int AS>
+PCAMV_FN int run_search_begin(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
 {
-    MeBlock &b = c.w.blk;
-    setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
     s.mvp[0] = mv_x(mvp); s.mvp[1] = mv_y(mvp);
-    block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
     s.r.mv[0] = s.r.mv[1] = 0; s.r.cost = 0; s.r.cost_mv = 0;
-    me_search_ref<XS>(c.env, b, mvc, i_mvc, thresh, s.r);
+    if (!AS)
+    {
+        MeBlock &b = c.w.blk;
+        setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
+        block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
+        me_search_ref<XS>(c.env, b, mvc, i_mvc, thresh, s.r);
+        log_push(c, LOG_SEARCH, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
+        return 0;
+    }
+    team_sync();
+    if (team_lane() == 0)
+    {
+        SearchReq &q = c.w.rq;
+        q.mb_x = (int16_t)c.mb_x; q.mb_y = (int16_t)c.mb_y;
+        q.kind = LOG_SEARCH; q.i_ref = (int8_t)s.i_ref; q.i_pixel = (int8_t)s.i_pixel; q.i_mvc = (int8_t)i_mvc;
+        q.xoff = (int8_t)s.xoff; q.yoff = (int8_t)s.yoff; q.has_thresh = thresh != nullptr; q.pad = 0;
+        q.mvp = mvp; q.thresh = thresh ? *thresh : 0;
+        q.mv = 0; q.cost = 0; q.cost_mv = 0; q.i_ref_cost = s.i_ref_cost;
+        for (int k = 0; k < 2; k++)
+        {
+            q.lim[k] = (int16_t)c.env.mv_min_fpel[k]; q.lim[2 + k] = (int16_t)c.env.mv_max_fpel[k];
+            q.lim[4 + k] = (int16_t)c.env.mv_min_spel[k]; q.lim[6 + k] = (int16_t)c.env.mv_max_spel[k];
+        }
+        for (int k = 0; k < i_mvc; k++) q.mvc[k] = pack_mv(mvc[k][0], mvc[k][1]);
+    }
+    team_sync();
+    return 1;
+}
+template <int AS>
+PCAMV_FN void run_search_end(MbCtx &c, MeSlot &s, int *thresh)
+{
+    if (!AS)
+        return;
+    const SearchRes r = c.w.rs;
+    team_sync();
+    s.r.mv[0] = mv_x(r.mv); s.r.mv[1] = mv_y(r.mv); s.r.cost = r.cost; s.r.cost_mv = r.cost_mv;
+    if (thresh) *thresh = r.thresh;
+    team_sync();
     log_push(c, LOG_SEARCH, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
 }
-
-PCAMV_FN void run_refine(MbCtx &c, MeSlot &s)
+// synchronous form (sub-8x8 partitions: those configurations never run split)
+template <int XS>
+PCAMV_DEV void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
 {
-    MeBlock &b = c.w.blk;
-    setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
-    block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
-    me_refine_qpel(c.env, b, s.r, s.i_ref_cost);
+    run_search_begin<XS, 0>(c, s, mvp, mvc, i_mvc, thresh);
+}
+
+template <int AS>
+PCAMV_FN int run_refine_begin(MbCtx &c, MeSlot &s)
+{
+    if (!AS)
+    {
+        MeBlock &b = c.w.blk;
+        setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
+        block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
+        me_refine_qpel(c.env, b, s.r, s.i_ref_cost);
+        log_push(c, LOG_REFINE, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
+        return 0;
+    }
+    team_sync();
+    if (team_lane() == 0)
+    {
+        SearchReq &q = c.w.rq;
+        q.mb_x = (int16_t)c.mb_x; q.mb_y = (int16_t)c.mb_y;
+        q.kind = LOG_REFINE; q.i_ref = (int8_t)s.i_ref; q.i_pixel = (int8_t)s.i_pixel; q.i_mvc = 0;
+        q.xoff = (int8_t)s.xoff; q.yoff = (int8_t)s.yoff; q.has_thresh = 0; q.pad = 0;
+        q.mvp = pack_mv(s.mvp[0], s.mvp[1]); q.thresh = 0;
+        q.mv = pack_mv(s.r.mv[0], s.r.mv[1]); q.cost = s.r.cost; q.cost_mv = s.r.cost_mv; q.i_ref_cost = s.i_ref_cost;
+        for (int k = 0; k < 2; k++)
+        {
+            q.lim[k] = (int16_t)c.env.mv_min_fpel[k]; q.lim[2 + k] = (int16_t)c.env.mv_max_fpel[k];
+            q.lim[4 + k] = (int16_t)c.env.mv_min_spel[k]; q.lim[6 + k] = (int16_t)c.env.mv_max_spel[k];
+        }
+    }
+    team_sync();
+    return 1;
+}
+template <int AS>
+PCAMV_FN void run_refine_end(MbCtx &c, MeSlot &s)
+{
+    if (!AS)
+        return;
+    const SearchRes r = c.w.rs;
+    team_sync();
+    s.r.mv[0] = mv_x(r.mv); s.r.mv[1] = mv_y(r.mv); s.r.cost = r.cost; s.r.cost_mv = r.cost_mv;
+    team_sync();
     log_push(c, LOG_REFINE, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
+}
+PCAMV_DEV void run_refine(MbCtx &c, MeSlot &s) { run_refine_begin<0>(c, s); }
+
+// What a search team does with a request (split wavefront; the emulation checker serves its own requests with it): the block
+// descriptor and search limits are rebuilt from the request, then the same me_search_ref / me_refine_qpel run.
+// `w` only lends its source-pixel staging (fenc_*, already holding the macroblock) and block descriptor.
+template <int XS>
+PCAMV_FN void serve_request(const DevFrameCtx &fc, const FrameParams &fp, MbWork &w, const SearchReq &q, SearchRes &out)
+{
+    MbCtx c(fc, fp, w);
+    c.mb_x = q.mb_x; c.mb_y = q.mb_y; c.mb_xy = q.mb_y * fc.mb_w + q.mb_x;
+    MeEnv &env = c.env;
+    env.cost_mv = fc.tab.cost_mv;
+    env.cost_mv_fpel[0] = env.cost_mv_fpel[1] = env.cost_mv_fpel[2] = env.cost_mv_fpel[3] = nullptr;
+    env.me_method = fc.me_method; env.me_range = fc.me_range; env.subme = fc.subme;
+    env.chroma_me = fc.chroma_me && fc.subme >= 5;
+    env.mbcmp_satd = fc.subme > 1;
+    env.mvsads = fp.mvsads ? fp.mvsads + (size_t)q.mb_y * fp.mvsads_cap : nullptr;
+    for (int k = 0; k < 2; k++)
+    {
+        env.mv_min_fpel[k] = q.lim[k]; env.mv_max_fpel[k] = q.lim[2 + k];
+        env.mv_min_spel[k] = q.lim[4 + k]; env.mv_max_spel[k] = q.lim[6 + k];
+    }
+    MeBlock &b = w.blk;
+    setup_block(c, b, q.i_ref, q.i_pixel, q.xoff, q.yoff);
+    block_set_mvp(b, env, mv_x(q.mvp), mv_y(q.mvp));
+    MeResult m;
+    int thresh = q.thresh;
+    if (q.kind == LOG_SEARCH)
+    {
+        int mvc[PCAMV_MAX_MVC][2];
+        for (int k = 0; k < q.i_mvc; k++) { mvc[k][0] = mv_x(q.mvc[k]); mvc[k][1] = mv_y(q.mvc[k]); }
+        m.mv[0] = m.mv[1] = 0; m.cost = 0; m.cost_mv = 0;
+        me_search_ref<XS>(env, b, mvc, q.i_mvc, q.has_thresh ? &thresh : nullptr, m);
+    }
+    else
+    {
+        m.mv[0] = mv_x(q.mv); m.mv[1] = mv_y(q.mv); m.cost = q.cost; m.cost_mv = q.cost_mv;
+        me_refine_qpel(env, b, m, q.i_ref_cost);
+    }
+    out.mv = pack_mv(m.mv[0], m.mv[1]); out.cost = m.cost; out.cost_mv = m.cost_mv; out.thresh = thresh;
 }
 
 PCAMV_DEV int ref_cost(const MbCtx &c, int i_ref)
@@ -654,29 +811,43 @@ PCAMV_DEV int ref_cost(const MbCtx &c, int i_ref)
     return c.fc.tab.cost_ref[clip3(c.fp.n_ref - 1, 0, 2) * 33 + i_ref];
 }
 
-// 16x16 search over all references; returns 1 when the early P_SKIP termination fired
-template <int XS>
+// 16x16 search over all references; returns 1 when the early P_SKIP termination fired, 2 when a search is out (AS)
+template <int XS, int AS>
 PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_pskip)
 {
     const int lambda = c.fc.tab.lambda;
+    PtState &pt = c.w.pt;
     int &halfpel_thresh = c.w.halfpel_thresh;
-    halfpel_thresh = 0x7fffffff;
     int *p_thresh = c.fp.n_ref > 1 ? &halfpel_thresh : nullptr;
-    a.me16x16.r.cost = 0x7fffffff;
-#pragma unroll 1
-    for (int i_ref = 0; i_ref < c.fp.n_ref; i_ref++)
+    if (!pt.in16)
     {
+        halfpel_thresh = 0x7fffffff;
+        a.me16x16.r.cost = 0x7fffffff;
+        pt.in16 = 1; pt.i_ref = 0; pt.wait = 0;
+    }
+#pragma unroll 1
+    for (; pt.i_ref < c.fp.n_ref; pt.i_ref++)
+    {
+        const int i_ref = pt.i_ref;
         MeSlot &m = c.w.slot;
         const int rc = ref_cost(c, i_ref);
-        halfpel_thresh -= rc;
-        m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_16x16; m.xoff = 0; m.yoff = 0;
-        int (*mvc)[2] = c.w.mvc;
-        const uint32_t mvp = predict_mv_16x16(c, i_ref);
-        const int i_mvc = predict_mv_ref16x16(c, i_ref, mvc);
-        run_search<XS>(c, m, mvp, mvc, i_mvc, p_thresh);
+        if (!pt.wait)
+        {
+            halfpel_thresh -= rc;
+            m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_16x16; m.xoff = 0; m.yoff = 0;
+            int (*mvc)[2] = c.w.mvc;
+            const uint32_t mvp = predict_mv_16x16(c, i_ref);
+            const int i_mvc = predict_mv_ref16x16(c, i_ref, mvc);
+            if (run_search_begin<XS, AS>(c, m, mvp, mvc, i_mvc, p_thresh)) { pt.wait = 1; return 2; }
+        }
+        pt.wait = 0;
+        run_search_end<AS>(c, m, p_thresh);
         if (allow_skip && i_ref == 0 && b_try_pskip && m.r.cost - m.r.cost_mv < 300 * lambda &&
             iabs(m.r.mv[0] - c.pskip_mv[0]) + iabs(m.r.mv[1] - c.pskip_mv[1]) <= 1 && probe_pskip(c))
+        {
+            pt.in16 = 0;
             return 1;
+        }
         m.r.cost += rc;
         halfpel_thresh += rc;
         if (m.r.cost < a.me16x16.r.cost)
@@ -685,78 +856,109 @@ PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_p
         if (team_lane() == 0)
             c.fp.cur.mvr[(size_t)i_ref * c.fc.mb_w * c.fc.mb_h + c.mb_xy] = pack_mv(m.r.mv[0], m.r.mv[1]);
     }
+    pt.in16 = 0;
     cache_fill_rect(c, 0, 0, 4, 4, a.me16x16.i_ref, 0, 1, 0);
     return 0;
 }
 
-template <int XS>
-PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
+template <int XS, int AS>
+PCAMV_FN int analyse_p8x8(MbCtx &c, MbAnalysis &a)
 {
+    PtState &pt = c.w.pt;
     const int i_ref = a.me16x16.i_ref;
     const int rc = (c.fc.b_cabac || i_ref) ? ref_cost(c, i_ref) : 0;
     int (*mvc)[2] = a.mvc[i_ref];
-    c.partition = PART_8x8;
-    int i_mvc = 1;
-    mvc[0][0] = a.me16x16.r.mv[0]; mvc[0][1] = a.me16x16.r.mv[1];
-#pragma unroll 1
-    for (int i = 0; i < 4; i++)
+    if (!pt.in8)
     {
+        c.partition = PART_8x8;
+        mvc[0][0] = a.me16x16.r.mv[0]; mvc[0][1] = a.me16x16.r.mv[1];
+        pt.in8 = 1; pt.i = 0; pt.wait = 0;
+    }
+#pragma unroll 1
+    for (; pt.i < 4; pt.i++)
+    {
+        const int i = pt.i;
         MeSlot &m = a.me8x8[i];
         const int x8 = i & 1, y8 = i >> 1;
-        m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_8x8; m.xoff = 8 * x8; m.yoff = 8 * y8;
-        run_search<XS>(c, m, predict_mv(c, 4 * i, 2), mvc, i_mvc, nullptr);
+        if (!pt.wait)
+        {
+            m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_8x8; m.xoff = 8 * x8; m.yoff = 8 * y8;
+            if (run_search_begin<XS, AS>(c, m, predict_mv(c, 4 * i, 2), mvc, i + 1, nullptr)) { pt.wait = 1; return PT_YIELD; }
+        }
+        pt.wait = 0;
+        run_search_end<AS>(c, m, nullptr);
         cache_fill_rect(c, 2 * x8, 2 * y8, 2, 2, 0, pack_mv(m.r.mv[0], m.r.mv[1]), 0, 1);
-        mvc[i_mvc][0] = m.r.mv[0]; mvc[i_mvc][1] = m.r.mv[1];
-        i_mvc++;
+        mvc[i + 1][0] = m.r.mv[0]; mvc[i + 1][1] = m.r.mv[1];
         m.r.cost += rc;
         m.r.cost += c.fc.tab.lambda * 1;          // sub-partition type cost of an unsplit 8x8
     }
+    pt.in8 = 0;
     a.cost8x8 = a.me8x8[0].r.cost + a.me8x8[1].r.cost + a.me8x8[2].r.cost + a.me8x8[3].r.cost;
     if (c.fc.b_cabac)
         a.cost8x8 -= rc;
     a.sub[0] = a.sub[1] = a.sub[2] = a.sub[3] = SUB_8x8;
+    return PT_DONE;
 }
 
 // 16x8 (dir = 0) or 8x16 (dir = 1)
-template <int XS>
-PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
+template <int XS, int AS>
+PCAMV_FN int analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
 {
-    c.partition = dir ? PART_8x16 : PART_16x8;
-    int total = 0;
-#pragma unroll 1
-    for (int i = 0; i < 2; i++)
+    PtState &pt = c.w.pt;
+    if (!pt.in168)
     {
+        c.partition = dir ? PART_8x16 : PART_16x8;
+        pt.total = 0;
+        pt.in168 = 1; pt.i = 0; pt.j = 0; pt.wait = 0;
+    }
+#pragma unroll 1
+    for (; pt.i < 2; pt.i++)
+    {
+        const int i = pt.i;
         MeSlot &best = dir ? a.me8x16[i] : a.me16x8[i];
         const int r0 = dir ? a.me8x8[i].i_ref : a.me8x8[2 * i].i_ref;
         const int r1 = dir ? a.me8x8[i + 2].i_ref : a.me8x8[2 * i + 1].i_ref;
         const int nrefs = r0 == r1 ? 1 : 2;
-        best.r.cost = 0x7fffffff;
+        if (pt.j == 0 && !pt.wait)
+            best.r.cost = 0x7fffffff;
 #pragma unroll 1
-        for (int j = 0; j < nrefs; j++)
+        for (; pt.j < nrefs; pt.j++)
         {
-            const int i_ref = j ? r1 : r0;
+            const int i_ref = pt.j ? r1 : r0;
             MeSlot &m = c.w.slot;
-            m.i_ref = i_ref; m.i_ref_cost = ref_cost(c, i_ref);
-            m.i_pixel = dir ? PIX_8x16 : PIX_16x8;
-            m.xoff = dir ? 8 * i : 0; m.yoff = dir ? 0 : 8 * i;
-            int (*mvc)[2] = c.w.mvc;
-            const int k1 = dir ? i + 1 : 2 * i + 1, k2 = dir ? i + 3 : 2 * i + 2;
-            mvc[0][0] = a.mvc[i_ref][0][0]; mvc[0][1] = a.mvc[i_ref][0][1];
-            mvc[1][0] = a.mvc[i_ref][k1][0]; mvc[1][1] = a.mvc[i_ref][k1][1];
-            mvc[2][0] = a.mvc[i_ref][k2][0]; mvc[2][1] = a.mvc[i_ref][k2][1];
-            if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, i_ref, 0, 1, 0);
-            else     cache_fill_rect(c, 0, 2 * i, 4, 2, i_ref, 0, 1, 0);
-            run_search<XS>(c, m, dir ? predict_mv(c, 4 * i, 2) : predict_mv(c, 8 * i, 4), mvc, 3, nullptr);
+            if (!pt.wait)
+            {
+                m.i_ref = i_ref; m.i_ref_cost = ref_cost(c, i_ref);
+                m.i_pixel = dir ? PIX_8x16 : PIX_16x8;
+                m.xoff = dir ? 8 * i : 0; m.yoff = dir ? 0 : 8 * i;
+                int (*mvc)[2] = c.w.mvc;
+                const int k1 = dir ? i + 1 : 2 * i + 1, k2 = dir ? i + 3 : 2 * i + 2;
+                mvc[0][0] = a.mvc[i_ref][0][0]; mvc[0][1] = a.mvc[i_ref][0][1];
+                mvc[1][0] = a.mvc[i_ref][k1][0]; mvc[1][1] = a.mvc[i_ref][k1][1];
+                mvc[2][0] = a.mvc[i_ref][k2][0]; mvc[2][1] = a.mvc[i_ref][k2][1];
+                if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, i_ref, 0, 1, 0);
+                else     cache_fill_rect(c, 0, 2 * i, 4, 2, i_ref, 0, 1, 0);
+                if (run_search_begin<XS, AS>(c, m, dir ? predict_mv(c, 4 * i, 2) : predict_mv(c, 8 * i, 4), mvc, 3, nullptr))
+                {
+                    pt.wait = 1;
+                    return PT_YIELD;
+                }
+            }
+            pt.wait = 0;
+            run_search_end<AS>(c, m, nullptr);
             m.r.cost += m.i_ref_cost;
             if (m.r.cost < best.r.cost)
                 best = m;
         }
+        pt.j = 0;
         const uint32_t mv = pack_mv(best.r.mv[0], best.r.mv[1]);
         if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, best.i_ref, mv, 1, 1);
         else     cache_fill_rect(c, 0, 2 * i, 4, 2, best.i_ref, mv, 1, 1);
-        total += best.r.cost;
+        pt.total += best.r.cost;
     }
-    if (dir) a.cost8x16 = total; else a.cost16x8 = total;
+    pt.in168 = 0;
+    if (dir) a.cost8x16 = pt.total; else a.cost16x8 = pt.total;
+    return PT_DONE;
 }
 
 // ---- sub-8x8 partitions of one 8x8 block (reference encoder/analyse.c:1569-1693) --------------------------------
@@ -1013,132 +1215,188 @@ PCAMV_DEV void wait_prev_raster(const MbCtx &c)
 
 // One macroblock of a P slice.  `prev_mv` = the 16 cache MVs left behind by the previous MB in raster order
 // (needed only for the pass-2 "forced skip without cache update" quirk, analyse.c:2668-2676).
-// F: feature mask of the instantiation — bit 0 = exhaustive searches (--me esa / tesa), bit 1 = sub-8x8 partitions
-template <int F>
-PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
+// F: feature mask of the instantiation — bit 0 = exhaustive searches (--me esa / tesa), bit 1 = sub-8x8 partitions.
+// AS = 1 (split wavefront): every search is handed out — the function returns PT_YIELD with the request in w.rq and is
+// called again, with w.pt and everything before MbWork::fenc_y as it left them and the result in w.rs, until it returns
+// PT_DONE.  The caller zeroes w.pt.stage before the first call of a macroblock.  AS = 0 never yields.
+template <int F, int AS>
+PCAMV_FN int analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
 {
     constexpr int XS = F & 1, SUB8 = (F >> 1) & 1;
+    static_assert(!(AS && SUB8), "the sub-8x8 partition searches are synchronous");
     const DevFrameCtx &fc = c.fc;
     MbAnalysis &a = c.w.an;
-    c.n_log = 0;
-    c.partition = PART_16x16;
-    cache_load(c);
-    const uint32_t ps = predict_mv_pskip(c);
-    c.pskip_mv[0] = mv_x(ps); c.pskip_mv[1] = mv_y(ps);
-    init_limits(c);
-    c.env.cost_mv = fc.tab.cost_mv;
-    c.env.me_method = fc.me_method; c.env.me_range = fc.me_range; c.env.subme = fc.subme;
-    c.env.chroma_me = fc.chroma_me && fc.subme >= 5;
-    c.env.mbcmp_satd = fc.subme > 1;
-    c.env.mvsads = c.fp.mvsads ? c.fp.mvsads + (size_t)c.mb_y * c.fp.mvsads_cap : nullptr;
-
-    int b_try_pskip = 0, b_skip = 0;
-    if (fc.b_fast_pskip)
-    {
-        if (fc.subme >= 3) b_try_pskip = 1;
-        else if (c.type_left == MB_P_SKIP || c.type_top == MB_P_SKIP || c.type_topleft == MB_P_SKIP || c.type_topright == MB_P_SKIP)
-            b_skip = probe_pskip(c);
-    }
+    PtState &pt = c.w.pt;
     const ForcedMb *forced = c.fp.pass == 2 ? &c.fp.forced[c.mb_xy] : nullptr;
-    int type = MB_P_L0, partition = PART_16x16, early_skip = 0;
-    if (b_skip)
+    if (pt.stage == 0)
     {
-        // (subme < 3 only) the reference takes this MB as P_SKIP before any search; pass 2 cannot override it
-        update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
-        finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, 1);
-        return;
-    }
-    early_skip = analyse_p16x16<XS>(c, a, 1, b_try_pskip);
-    if (early_skip)
-    {
-        type = MB_P_SKIP;
-        update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
-    }
-    if (forced)
-    {
-        if (forced->type != MB_P_SKIP && type == MB_P_SKIP)
-            analyse_p16x16<XS>(c, a, 0, b_try_pskip);       // the reference re-runs the 16x16 search without the skip exit
-        type = forced->type;
-    }
-    if (type == MB_P_SKIP)
-    {
-        if (!early_skip)
-        {
-            // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
-            // and the refs are what the 16x16 search left (its best reference)
-            wait_prev_raster(c);
-#pragma unroll 1
-            for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = PCAMV_LDV(prev_mv + i);
-        }
-        finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, early_skip);
-        return;
-    }
+        c.n_log = 0;
+        c.partition = PART_16x16;
+        cache_load(c);
+        const uint32_t ps = predict_mv_pskip(c);
+        c.pskip_mv[0] = mv_x(ps); c.pskip_mv[1] = mv_y(ps);
+        init_limits(c);
+        c.env.cost_mv = fc.tab.cost_mv;
+        c.env.me_method = fc.me_method; c.env.me_range = fc.me_range; c.env.subme = fc.subme;
+        c.env.chroma_me = fc.chroma_me && fc.subme >= 5;
+        c.env.mbcmp_satd = fc.subme > 1;
+        c.env.mvsads = c.fp.mvsads ? c.fp.mvsads + (size_t)c.mb_y * c.fp.mvsads_cap : nullptr;
 
-    // Elision has one exception.  When this pass's probe found the macroblock skippable but pass 1 did not (the re-run above),
-    // the host keeps b_skip_mc set (quirk q1, analyse.c:2663-2668 / encoder/macroblock.c:611-612): x264_macroblock_encode then
-    // takes the residual against whatever the analysis left in fdec, and that is the host's INTRA analysis, whose early-outs
-    // compare against the inter cost of the "dead" searches and refinement.  Such macroblocks get the full analysis.
-    if (forced && forced->used && fc.pass2_elide && !early_skip)
+        int b_try_pskip = 0, b_skip = 0;
+        if (fc.b_fast_pskip)
+        {
+            if (fc.subme >= 3) b_try_pskip = 1;
+            else if (c.type_left == MB_P_SKIP || c.type_top == MB_P_SKIP || c.type_topleft == MB_P_SKIP || c.type_topright == MB_P_SKIP)
+                b_skip = probe_pskip(c);
+        }
+        pt.b_try_pskip = (int8_t)b_try_pskip; pt.type = MB_P_L0; pt.partition = PART_16x16; pt.early_skip = 0;
+        pt.in16 = pt.in8 = pt.in168 = pt.wait = 0;
+        if (b_skip)
+        {
+            // (subme < 3 only) the reference takes this MB as P_SKIP before any search; pass 2 cannot override it
+            update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
+            finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, 1);
+            return PT_DONE;
+        }
+        pt.stage = 1;
+    }
+    if (pt.stage == 1)
     {
-        // pass 2, decision forced from pass 1: nothing the remaining searches produce survives analyse.c:2868-2991
-        // (info.cache[].i_partition is only written for P_L0, analyse.c:3612: a forced P_8x8 is 8x8 by construction)
-        type = forced->type; partition = forced->type == MB_P_8x8 ? PART_8x8 : forced->partition;
+        const int r = analyse_p16x16<XS, AS>(c, a, 1, pt.b_try_pskip);
+        if (r == 2) return PT_YIELD;
+        pt.early_skip = (int8_t)r;
+        if (r)
+        {
+            pt.type = MB_P_SKIP;
+            update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
+        }
+        // the reference re-runs the 16x16 search without the skip exit when pass 1 coded a macroblock this pass would skip
+        pt.stage = (forced && forced->type != MB_P_SKIP && pt.type == MB_P_SKIP) ? 2 : 3;
+    }
+    if (pt.stage == 2)
+    {
+        if (analyse_p16x16<XS, AS>(c, a, 0, pt.b_try_pskip) == 2) return PT_YIELD;
+        pt.stage = 3;
+    }
+    if (pt.stage == 3)
+    {
+        const int early_skip = pt.early_skip;
+        if (forced)
+            pt.type = forced->type;
+        if (pt.type == MB_P_SKIP)
+        {
+            if (!early_skip)
+            {
+                // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
+                // and the refs are what the 16x16 search left (its best reference)
+                wait_prev_raster(c);
 #pragma unroll 1
-        for (int i = 0; i < 4; i++)
-            cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
+                for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = PCAMV_LDV(prev_mv + i);
+            }
+            finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, early_skip);
+            return PT_DONE;
+        }
+
+        // Elision has one exception.  When this pass's probe found the macroblock skippable but pass 1 did not (the re-run above),
+        // the host keeps b_skip_mc set (quirk q1, analyse.c:2663-2668 / encoder/macroblock.c:611-612): x264_macroblock_encode then
+        // takes the residual against whatever the analysis left in fdec, and that is the host's INTRA analysis, whose early-outs
+        // compare against the inter cost of the "dead" searches and refinement.  Such macroblocks get the full analysis.
+        if (forced && forced->used && fc.pass2_elide && !early_skip)
+        {
+            // pass 2, decision forced from pass 1: nothing the remaining searches produce survives analyse.c:2868-2991
+            // (info.cache[].i_partition is only written for P_L0, analyse.c:3612: a forced P_8x8 is 8x8 by construction)
+            const int type = forced->type, partition = forced->type == MB_P_8x8 ? PART_8x8 : forced->partition;
 #pragma unroll 1
-        for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
-        finalize_mb<SUB8>(c, a, type, -partition, 0);
-        return;
+            for (int i = 0; i < 4; i++)
+                cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
+#pragma unroll 1
+            for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
+            finalize_mb<SUB8>(c, a, type, -partition, 0);
+            return PT_DONE;
+        }
+        pt.type = MB_P_L0; pt.partition = PART_16x16;
+        pt.stage = 4;
     }
 
     const int flags = fc.analyse_inter;
     const int psub16 = (flags & 0x10) != 0;
-    if (psub16)
-        analyse_p8x8<XS>(c, a);
-    int i_cost = a.me16x16.r.cost;
-    if (SUB8 && psub16 && (flags & 0x20) && a.cost8x8 < a.me16x16.r.cost)
+    if (pt.stage == 4)
     {
-        // X264_ANALYSE_PSUB8x8: P_8x8 becomes the incumbent and every 8x8 block may split further (analyse.c:2697-2731)
-        type = MB_P_8x8; partition = PART_8x8;
-        i_cost = a.cost8x8;
-#pragma unroll 1
-        for (int i = 0; i < 4; i++)
+        if (psub16 && analyse_p8x8<XS, AS>(c, a) == PT_YIELD)
+            return PT_YIELD;
+        pt.i_cost = a.me16x16.r.cost;
+        if (SUB8 && psub16 && (flags & 0x20) && a.cost8x8 < a.me16x16.r.cost)
         {
-            const int c4x4 = analyse_sub8x8<XS>(c, a, i, SUB_4x4);
-            if (c4x4 < a.me8x8[i].r.cost)
+            // X264_ANALYSE_PSUB8x8: P_8x8 becomes the incumbent and every 8x8 block may split further (analyse.c:2697-2731)
+            pt.type = MB_P_8x8; pt.partition = PART_8x8;
+            int i_cost = a.cost8x8;
+#pragma unroll 1
+            for (int i = 0; i < 4; i++)
             {
-                int best8 = c4x4;
-                a.sub[i] = SUB_4x4;
-                const int c8x4 = analyse_sub8x8<XS>(c, a, i, SUB_8x4);
-                if (c8x4 < best8) { best8 = c8x4; a.sub[i] = SUB_8x4; }
-                const int c4x8 = analyse_sub8x8<XS>(c, a, i, SUB_4x8);
-                if (c4x8 < best8) { best8 = c4x8; a.sub[i] = SUB_4x8; }
-                i_cost += best8 - a.me8x8[i].r.cost;
+                const int c4x4 = analyse_sub8x8<XS>(c, a, i, SUB_4x4);
+                if (c4x4 < a.me8x8[i].r.cost)
+                {
+                    int best8 = c4x4;
+                    a.sub[i] = SUB_4x4;
+                    const int c8x4 = analyse_sub8x8<XS>(c, a, i, SUB_8x4);
+                    if (c8x4 < best8) { best8 = c8x4; a.sub[i] = SUB_8x4; }
+                    const int c4x8 = analyse_sub8x8<XS>(c, a, i, SUB_4x8);
+                    if (c4x8 < best8) { best8 = c4x8; a.sub[i] = SUB_4x8; }
+                    i_cost += best8 - a.me8x8[i].r.cost;
+                }
+                cache_mv_p8x8(c, a, i);
             }
-            cache_mv_p8x8(c, a, i);
+            a.cost8x8 = i_cost;
+            pt.i_cost = i_cost;
         }
-        a.cost8x8 = i_cost;
-    }
-    if (psub16)
-    {
-        const int thresh16x8 = a.me8x8[1].r.cost_mv + a.me8x8[2].r.cost_mv;
-        if (a.cost8x8 < a.me16x16.r.cost + thresh16x8)
+        pt.stage = 7;
+        if (psub16)
         {
-            analyse_p16x8_8x16<XS>(c, a, 0);
-            if (a.cost16x8 < i_cost) { i_cost = a.cost16x8; type = MB_P_L0; partition = PART_16x8; }
-            analyse_p16x8_8x16<XS>(c, a, 1);
-            if (a.cost8x16 < i_cost) { i_cost = a.cost8x16; type = MB_P_L0; partition = PART_8x16; }
+            const int thresh16x8 = a.me8x8[1].r.cost_mv + a.me8x8[2].r.cost_mv;
+            if (a.cost8x8 < a.me16x16.r.cost + thresh16x8)
+                pt.stage = 5;
         }
     }
-    c.partition = partition;
-    if (partition == PART_16x16) run_refine(c, a.me16x16);
-    else if (partition == PART_16x8) { run_refine(c, a.me16x8[0]); run_refine(c, a.me16x8[1]); }
-    else if (partition == PART_8x16) { run_refine(c, a.me8x16[0]); run_refine(c, a.me8x16[1]); }
-    else if (SUB8)
+    if (pt.stage == 5)
+    {
+        if (analyse_p16x8_8x16<XS, AS>(c, a, 0) == PT_YIELD) return PT_YIELD;
+        if (a.cost16x8 < pt.i_cost) { pt.i_cost = a.cost16x8; pt.type = MB_P_L0; pt.partition = PART_16x8; }
+        pt.stage = 6;
+    }
+    if (pt.stage == 6)
+    {
+        if (analyse_p16x8_8x16<XS, AS>(c, a, 1) == PT_YIELD) return PT_YIELD;
+        if (a.cost8x16 < pt.i_cost) { pt.i_cost = a.cost8x16; pt.type = MB_P_L0; pt.partition = PART_8x16; }
+        pt.stage = 7;
+    }
+    if (pt.stage == 7)
+    {
+        c.partition = pt.partition;
+        pt.i = 0; pt.wait = 0;
+        pt.stage = 8;
+    }
+    if (pt.stage == 8)
+    {
+        // quarter-pel refinement of the winner's partitions
+        if (pt.partition != PART_8x8)
+        {
+            const int np = pt.partition == PART_16x16 ? 1 : 2;
 #pragma unroll 1
-        for (int i = 0; i < 4; i++) refine_sub8x8(c, a, i);
+            for (; pt.i < np; pt.i++)
+            {
+                MeSlot &m = pt.partition == PART_16x16 ? a.me16x16 : pt.partition == PART_16x8 ? a.me16x8[pt.i] : a.me8x16[pt.i];
+                if (!pt.wait && run_refine_begin<AS>(c, m)) { pt.wait = 1; return PT_YIELD; }
+                pt.wait = 0;
+                run_refine_end<AS>(c, m);
+            }
+        }
+        else if (SUB8)
+#pragma unroll 1
+            for (int i = 0; i < 4; i++) refine_sub8x8(c, a, i);
+        pt.stage = 9;
+    }
 
+    int type = pt.type, partition = pt.partition;
     if (forced && forced->used)
     {
         // pass 2: type / partition / refs / MVs come from pass 1 with the embedding flips applied; for P_8x8 the reference
@@ -1157,6 +1415,14 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     // a forced decision names partitions this pass may never have searched: its record carries no partition slots
     // (pass 2 has no cost table; the slots would be whatever the team's scratch held)
     finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, 0);
+    return PT_DONE;
+}
+// synchronous form: the whole macroblock in one call
+template <int F>
+PCAMV_DEV void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
+{
+    c.w.pt.stage = 0;
+    analyse_p_mb<F, 0>(c, prev_mv);
 }
 
 } // namespace pcamv

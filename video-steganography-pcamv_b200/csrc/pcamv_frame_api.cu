@@ -8,6 +8,7 @@
 #include <vector>
 #include "pcamv_ctx.h"
 #include "pcamv_glue.h"
+#include "pcamv_split.h"
 
 using namespace pcamv;
 
@@ -336,8 +337,40 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
     }
     CK(cudaMemcpyAsync(ctx->d_batch, ctx->h_batch, n * sizeof(BatchItem), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_batch_claim, 0, n * sizeof(int), ctx->stream));
+    // split wavefront (rows_per_cta = -2): searches and per-macroblock control code on different SMs (pcamv_split.cu); the
+    // sub-8x8 partition searches are synchronous, those configurations keep the row groups
+    const bool split = ctx->cfg.rows_per_cta == -2 && !(fc.analyse_inter & 0x20);
+    SplitBufs sb = {};
+    int split_ctrl = 0, split_rows = 0, n_sms = 0;
+    if (split)
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, ctx->cfg.device));
+        n_sms = prop.multiProcessorCount;
+        const int total_warps = ctx->batch_max_ctas * 4;
+        if (ctx->split_warps < total_warps)
+        {
+            cudaFree(ctx->d_split); ctx->d_split = nullptr; ctx->split_warps = 0;
+            ctx->split_bytes = split_bytes(total_warps, nullptr);
+            CK(cudaMalloc(&ctx->d_split, ctx->split_bytes));
+            ctx->split_warps = total_warps;
+        }
+        size_t zero = 0;
+        sb = split_carve(ctx->d_split, ctx->split_warps, &zero);
+        CK(cudaMemsetAsync(ctx->d_split, 0, zero, ctx->stream));
+        split_ctrl = n_sms * 2 / 9;                         // control SMs (PCAMV_SPLIT_CTRL_SMS), row slots per control team (PCAMV_SPLIT_ROWS)
+        split_rows = 6;
+        if (const char *e = getenv("PCAMV_SPLIT_CTRL_SMS")) if (atoi(e) > 0) split_ctrl = atoi(e);
+        if (const char *e = getenv("PCAMV_SPLIT_ROWS")) if (atoi(e) > 0) split_rows = atoi(e);
+        if (split_ctrl >= n_sms) split_ctrl = n_sms - 1;
+        if (split_rows > SPLIT_MAX_ROWS) split_rows = SPLIT_MAX_ROWS;
+    }
     if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
-    launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta, ctx->batch_max_ctas, fc, ctx->stream);
+    if (split)
+        launch_analyse_p_split(ctx->d_batch, n, ctx->d_batch_claim, sb, ctx->batch_max_ctas, split_ctrl, n_sms, split_rows,
+                               fc.me_method >= PCAMV_ME_ESA ? 1 : 0, ctx->stream);
+    else
+        launch_analyse_p_batch(ctx->d_batch, n, ctx->d_batch_claim, fc.mb_h, ctx->cfg.rows_per_cta == -2 ? 4 : ctx->cfg.rows_per_cta, ctx->batch_max_ctas, fc, ctx->stream);
     ctx->launches += 1;
     if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
     if (cost_table)
@@ -348,6 +381,16 @@ static int launch_batch(pcamv_ctx *const *ctxs, int n, int pass, cudaEvent_t *ev
     if (ev) CK(cudaEventRecord(ev[2], ctx->stream));
     CK(cudaGetLastError());
     for (int i = 0; i < n; i++) ctxs[i]->frame_last = pass;
+    return 0;
+}
+
+// after a split-wavefront launch has been synchronised: did its watchdog fire?
+static int split_check(pcamv_ctx *ctx)
+{
+    if (ctx->cfg.rows_per_cta != -2 || !ctx->d_split) return 0;
+    int flag = 0;
+    CK(cudaMemcpy(&flag, ctx->d_split + SPH_ABORT * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return ctx_fail(ctx, "split wavefront: a team waited 20 s for work that never came (watchdog); the launch was abandoned", cudaSuccess);
     return 0;
 }
 
@@ -367,6 +410,7 @@ extern "C" int pcamv_frame_run_batch(pcamv_ctx *const *ctxs, int n, int pass, in
         if (launch_batch(ctxs, n, pass, ctx->ev_pool.data() + 3 * i)) return -1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
+    if (split_check(ctx)) return -1;
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (ms_per_step) *ms_per_step = ms / iters;
@@ -417,7 +461,7 @@ extern "C" int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_i
     for (int i = 0; i < n; i++)
         if (frame_download_finish(ctxs[i], mbs[i], logs ? logs[i] : nullptr))
             return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
-    return 0;
+    return split_check(ctx);
 }
 
 // ---- encoder groups: several encoder threads of one process (GOP shards / streams), one GPU launch per step --------------

@@ -39,10 +39,17 @@ static int g_pslice;
 static uint64_t g_cnt_sad, g_cnt_satd, g_cnt_ih_luma, g_cnt_ih_chroma;
 static uint64_t g_cnt_search, g_cnt_refine, g_cnt_mb_p, g_cnt_pframes, g_cnt_ads;
 static uint64_t g_pix_sad, g_pix_satd;  /* pixel-normalised (w*h) */
+/* further work of the P-slice analysis, pixel-normalised, for the integer-op roofline (SURVEY.md 8(d) weights): quarter-pel
+ * averaging in get_ref / mc_luma (2 ops/pixel), chroma bilinear MC (8 ops/pixel), DCT + quant + dequant + IDCT of the
+ * macroblock reconstructions and P_SKIP probes (14 ops/pixel).  Counted only inside x264_macroblock_analyse of P slices. */
+static uint64_t g_pix_avg, g_pix_chroma_mc, g_pix_dct;
+static uint64_t g_ih_pix_avg, g_ih_pix_chroma_mc, g_ih_pix_dct, g_ih_pix_satd;     /* the share of x264_ih_get_mv_cost (the cost-table kernel) */
+static int g_in_analyse_p, g_in_ih;
 static double g_t_analyse_p, g_t_me, g_t_ih, g_t_total0;
 static uint64_t g_cnt_ih_calls;
 static struct timespec g_ts_an, g_ts_me, g_ts_ih;
 static uint64_t g_slice_c0[9];      /* counters at the start of the current slice pass */
+static uint64_t g_slice_x0[7];      /* ... and of pix_avg, pix_chroma_mc, pix_dct, and the cost table's share of avg / chroma / dct / satd */
 static double g_slice_t0[3];
 
 static double now_s( void )
@@ -86,9 +93,33 @@ WRAP7(WRAPX4, sad_x4, sad)
 WRAP7(WRAPX3, satd_x3, satd)
 WRAP7(WRAPX4, satd_x4, satd)
 
+static x264_mc_functions_t g_orig_mc;
+static x264_dct_function_t g_orig_dct;
+static void w_mc_luma( uint8_t *dst, int i_dst, uint8_t **src, int i_src, int mvx, int mvy, int w, int hh )
+{
+    if( g_in_analyse_p && ( ((mvy&3)<<2) + (mvx&3) ) & 5 ) { g_pix_avg += w*hh; if( g_in_ih ) g_ih_pix_avg += w*hh; }      /* the positions mc.c:206,232 average */
+    g_orig_mc.mc_luma( dst, i_dst, src, i_src, mvx, mvy, w, hh );
+}
+static uint8_t *w_get_ref( uint8_t *dst, int *i_dst, uint8_t **src, int i_src, int mvx, int mvy, int w, int hh )
+{
+    if( g_in_analyse_p && ( ((mvy&3)<<2) + (mvx&3) ) & 5 ) { g_pix_avg += w*hh; if( g_in_ih ) g_ih_pix_avg += w*hh; }
+    return g_orig_mc.get_ref( dst, i_dst, src, i_src, mvx, mvy, w, hh );
+}
+static void w_mc_chroma( uint8_t *dst, int i_dst, uint8_t *src, int i_src, int mvx, int mvy, int w, int hh )
+{
+    if( g_in_analyse_p ) { g_pix_chroma_mc += w*hh; if( g_in_ih ) g_ih_pix_chroma_mc += w*hh; }
+    g_orig_mc.mc_chroma( dst, i_dst, src, i_src, mvx, mvy, w, hh );
+}
+static void w_sub16x16_dct( int16_t dct[16][4][4], uint8_t *a, uint8_t *b ) { if( g_in_analyse_p ) { g_pix_dct += 256; if( g_in_ih ) g_ih_pix_dct += 256; } g_orig_dct.sub16x16_dct( dct, a, b ); }
+static void w_sub8x8_dct( int16_t dct[4][4][4], uint8_t *a, uint8_t *b ) { if( g_in_analyse_p ) { g_pix_dct += 64; if( g_in_ih ) g_ih_pix_dct += 64; } g_orig_dct.sub8x8_dct( dct, a, b ); }
+/* (sub4x4_dct is left alone: on this path only the host-side intra 4x4 analysis calls it) */
+
 static void install_count_wrappers( x264_t *h )
 {
     int i;
+    g_orig_mc = h->mc; g_orig_dct = h->dctf;
+    h->mc.mc_luma = w_mc_luma; h->mc.get_ref = w_get_ref; h->mc.mc_chroma = w_mc_chroma;
+    h->dctf.sub16x16_dct = w_sub16x16_dct; h->dctf.sub8x8_dct = w_sub8x8_dct;
     x264_pixel_cmp_t wsad[7]  = { w_sad_0, w_sad_1, w_sad_2, w_sad_3, w_sad_4, w_sad_5, w_sad_6 };
     x264_pixel_cmp_t wsatd[7] = { w_satd_0, w_satd_1, w_satd_2, w_satd_3, w_satd_4, w_satd_5, w_satd_6 };
     x264_pixel_cmp_x3_t wsad3[7]  = { w_sad_x3_0, w_sad_x3_1, w_sad_x3_2, w_sad_x3_3, w_sad_x3_4, w_sad_x3_5, w_sad_x3_6 };
@@ -157,13 +188,14 @@ void pcamv_hook_close( x264_t *h )
         if( f )
         {
             fprintf( f, "{\"sad\": %llu, \"satd\": %llu, \"ih_luma\": %llu, \"ih_chroma\": %llu, "
-                        "\"pix_sad\": %llu, \"pix_satd\": %llu, "
+                        "\"pix_sad\": %llu, \"pix_satd\": %llu, \"pix_avg\": %llu, \"pix_chroma_mc\": %llu, \"pix_dct\": %llu, "
                         "\"searches\": %llu, \"refines\": %llu, \"p_mb_passes\": %llu, \"p_frames\": %llu, "
                         "\"ih_calls\": %llu, \"t_ih\": %.6f, "
                         "\"t_analyse_p\": %.6f, \"t_me\": %.6f, \"t_total\": %.6f}\n",
                      (unsigned long long)g_cnt_sad, (unsigned long long)g_cnt_satd,
                      (unsigned long long)g_cnt_ih_luma, (unsigned long long)g_cnt_ih_chroma,
                      (unsigned long long)g_pix_sad, (unsigned long long)g_pix_satd,
+                     (unsigned long long)g_pix_avg, (unsigned long long)g_pix_chroma_mc, (unsigned long long)g_pix_dct,
                      (unsigned long long)g_cnt_search, (unsigned long long)g_cnt_refine,
                      (unsigned long long)g_cnt_mb_p, (unsigned long long)g_cnt_pframes,
                      (unsigned long long)g_cnt_ih_calls, g_t_ih,
@@ -192,6 +224,8 @@ void pcamv_hook_slice_begin( x264_t *h )
         double t[3] = { g_t_me, g_t_ih, g_t_analyse_p };
         memcpy( g_slice_c0, c, sizeof(c) );
         memcpy( g_slice_t0, t, sizeof(t) );
+        g_slice_x0[0] = g_pix_avg; g_slice_x0[1] = g_pix_chroma_mc; g_slice_x0[2] = g_pix_dct;
+        g_slice_x0[3] = g_ih_pix_avg; g_slice_x0[4] = g_ih_pix_chroma_mc; g_slice_x0[5] = g_ih_pix_dct; g_slice_x0[6] = g_ih_pix_satd;
     }
     if( !dump_on( h ) )
         return;
@@ -301,6 +335,14 @@ void pcamv_hook_slice_end( x264_t *h )
         rec_begin( "CNT0", sizeof(c) + sizeof(t) );
         fwrite( c, 1, sizeof(c), g_dump );
         fwrite( t, 1, sizeof(t), g_dump );
+        {
+            /* 'CNT1': pixels of this slice pass that went through quarter-pel averaging, chroma MC, DCT/quant/IDCT (uint64 each), then
+             * the share of x264_ih_get_mv_cost in those three and in pix_satd */
+            uint64_t x[7] = { g_pix_avg - g_slice_x0[0], g_pix_chroma_mc - g_slice_x0[1], g_pix_dct - g_slice_x0[2],
+                              g_ih_pix_avg - g_slice_x0[3], g_ih_pix_chroma_mc - g_slice_x0[4], g_ih_pix_dct - g_slice_x0[5], g_ih_pix_satd - g_slice_x0[6] };
+            rec_begin( "CNT1", sizeof(x) );
+            fwrite( x, 1, sizeof(x), g_dump );
+        }
     }
     {
         /* 'SLCE': int32 frame, pass, n_mb; then int8 type[n_mb]; int8 ref[4*n_mb] in b8 raster;
@@ -320,11 +362,15 @@ void pcamv_hook_slice_end( x264_t *h )
 void pcamv_hook_analyse_begin( x264_t *h )
 {
     if( h->sh.i_type == SLICE_TYPE_P )
+    {
         clock_gettime( CLOCK_MONOTONIC, &g_ts_an );
+        g_in_analyse_p = 1;
+    }
 }
 
 void pcamv_hook_analyse_end( x264_t *h )
 {
+    g_in_analyse_p = 0;
     if( h->sh.i_type == SLICE_TYPE_P )
     {
         struct timespec t; clock_gettime( CLOCK_MONOTONIC, &t );
@@ -497,10 +543,11 @@ void x264_me_refine_qpel( x264_t *h, x264_me_t *m )
     }
 }
 
-void pcamv_hook_ih_begin( void ) { clock_gettime( CLOCK_MONOTONIC, &g_ts_ih ); g_cnt_ih_calls++; }
+void pcamv_hook_ih_begin( void ) { clock_gettime( CLOCK_MONOTONIC, &g_ts_ih ); g_cnt_ih_calls++; g_in_ih = 1; }
 void pcamv_hook_ih_end( void )
 {
-    struct timespec t; clock_gettime( CLOCK_MONOTONIC, &t );
+    struct timespec t;
+    g_in_ih = 0; clock_gettime( CLOCK_MONOTONIC, &t );
     g_t_ih += (t.tv_sec - g_ts_ih.tv_sec) + 1e-9*(t.tv_nsec - g_ts_ih.tv_nsec);
 }
 
@@ -509,9 +556,11 @@ void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me )
 {
     g_cnt_ih_luma++;
     g_pix_satd += g_pw[i_pixel]*g_ph[i_pixel];
+    g_ih_pix_satd += g_pw[i_pixel]*g_ph[i_pixel];
     if( b_chroma_me )
     {
         g_cnt_ih_chroma += 2;
         g_pix_satd += g_pw[i_pixel]*g_ph[i_pixel]/2;
+        g_ih_pix_satd += g_pw[i_pixel]*g_ph[i_pixel]/2;
     }
 }

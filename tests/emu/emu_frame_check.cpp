@@ -188,7 +188,7 @@ int main(int argc, char **argv)
                 static unsigned char park_ctx[sizeof(MbCtx)];
                 work.pt.stage = 0;
                 int guard = 0;
-                while (analyse_p_mb<1, 1>(c, mb ? results[mb - 1].mv : fp.stale_mv) == PT_YIELD)
+                while (analyse_p_mb_rs<1, 1>(c, mb ? results[mb - 1].mv : fp.stale_mv) == PT_YIELD)
                 {
                     n_yield++;
                     if (++guard > 200) { fprintf(stderr, "mb %d never finishes\n", mb); return 1; }

@@ -26,8 +26,10 @@ def _worker(rank, world, port, q):
     for g in mine:
         rnd = random.Random(1000 + g)
         n = 50 + 7 * g
+        import hashlib
         local.append({"gop": g, "n_bits": n, "payload": bytes(rnd.getrandbits(1) for _ in range(n)), "n_mv": 5 * n,
-                      "n_flipped": n // 3, "bytes": 1000 + g})
+                      "n_flipped": n // 3, "bytes": 1000 + g, "md5": hashlib.md5(b"gop%d" % g).hexdigest(),
+                      "payload_md5": hashlib.md5(b"pay%d" % g).hexdigest()})
     res = shard.gather_gop_results(local)
     t = shard.max_over_ranks([0.5 + rank, 2.0 - rank])
     s = shard.sum_over_ranks([float(len(mine))])
@@ -55,6 +57,9 @@ def test_gop_sharding_two_ranks():
         rnd = random.Random(1000 + r["gop"])
         assert r["payload"] == bytes(rnd.getrandbits(1) for _ in range(r["n_bits"]))     # payload arrives intact, in GOP order
         assert r["n_mv"] == 5 * r["n_bits"] and r["bytes"] == 1000 + r["gop"]
+        import hashlib
+        assert r["md5"] == hashlib.md5(b"gop%d" % r["gop"]).hexdigest()      # 128-bit digests survive the int64 transport
+        assert r["payload_md5"] == hashlib.md5(b"pay%d" % r["gop"]).hexdigest()
     assert t0 == [1.5, 2.0] and got[1][1] == [1.5, 2.0]          # max over ranks
     assert s0 == [8.0]
 

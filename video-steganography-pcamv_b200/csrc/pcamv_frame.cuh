@@ -667,6 +667,28 @@ PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, i
     b.integral4 = rf.integral4 ? rf.integral4 + off : nullptr;
 }
 
+template <int XS>
+PCAMV_FN void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
+{
+    MeBlock &b = c.w.blk;
+    setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
+    s.mvp[0] = mv_x(mvp); s.mvp[1] = mv_y(mvp);
+    block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
+    s.r.mv[0] = s.r.mv[1] = 0; s.r.cost = 0; s.r.cost_mv = 0;
+    me_search_ref<XS>(c.env, b, mvc, i_mvc, thresh, s.r);
+    log_push(c, LOG_SEARCH, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
+}
+
+PCAMV_FN void run_refine(MbCtx &c, MeSlot &s)
+{
+    MeBlock &b = c.w.blk;
+    setup_block(c, b, s.i_ref, s.i_pixel, s.xoff, s.yoff);
+    block_set_mvp(b, c.env, s.mvp[0], s.mvp[1]);
+    me_refine_qpel(c.env, b, s.r, s.i_ref_cost);
+    log_push(c, LOG_REFINE, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
+}
+
+// ---- resumable form (split wavefront, pcamv_split.cu) -------------------------------------------------------------
 // A search is issued in two halves.  AS = 0 (synchronous kernels, emulation): run_search_begin does the whole search and
 // returns 0.  AS = 1 (split wavefront): it only writes the request into w.rq and returns 1 — the caller records where it
 // stands and unwinds with PT_YIELD; when the result is back in w.rs the same code runs again, skips to that point and
@@ -705,7 +727,7 @@ PCAMV_FN int run_search_begin(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc
     return 1;
 }
 template <int AS>
-PCAMV_FN void run_search_end(MbCtx &c, MeSlot &s, int *thresh)
+PCAMV_DEV void run_search_end(MbCtx &c, MeSlot &s, int *thresh)
 {
     if (!AS)
         return;
@@ -716,13 +738,6 @@ PCAMV_FN void run_search_end(MbCtx &c, MeSlot &s, int *thresh)
     team_sync();
     log_push(c, LOG_SEARCH, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
 }
-// synchronous form (sub-8x8 partitions: those configurations never run split)
-template <int XS>
-PCAMV_DEV void run_search(MbCtx &c, MeSlot &s, uint32_t mvp, const int (*mvc)[2], int i_mvc, int *thresh)
-{
-    run_search_begin<XS, 0>(c, s, mvp, mvc, i_mvc, thresh);
-}
-
 template <int AS>
 PCAMV_FN int run_refine_begin(MbCtx &c, MeSlot &s)
 {
@@ -754,7 +769,7 @@ PCAMV_FN int run_refine_begin(MbCtx &c, MeSlot &s)
     return 1;
 }
 template <int AS>
-PCAMV_FN void run_refine_end(MbCtx &c, MeSlot &s)
+PCAMV_DEV void run_refine_end(MbCtx &c, MeSlot &s)
 {
     if (!AS)
         return;
@@ -764,7 +779,6 @@ PCAMV_FN void run_refine_end(MbCtx &c, MeSlot &s)
     team_sync();
     log_push(c, LOG_REFINE, s.i_pixel, s.i_ref, s.r.mv[0], s.r.mv[1], s.r.cost, s.r.cost_mv);
 }
-PCAMV_DEV void run_refine(MbCtx &c, MeSlot &s) { run_refine_begin<0>(c, s); }
 
 // What a search team does with a request (split wavefront; the emulation checker serves its own requests with it): the block
 // descriptor and search limits are rebuilt from the request, then the same me_search_ref / me_refine_qpel run.
@@ -811,9 +825,115 @@ PCAMV_DEV int ref_cost(const MbCtx &c, int i_ref)
     return c.fc.tab.cost_ref[clip3(c.fp.n_ref - 1, 0, 2) * 33 + i_ref];
 }
 
+// 16x16 search over all references; returns 1 when the early P_SKIP termination fired
+template <int XS>
+PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_pskip)
+{
+    const int lambda = c.fc.tab.lambda;
+    int &halfpel_thresh = c.w.halfpel_thresh;
+    halfpel_thresh = 0x7fffffff;
+    int *p_thresh = c.fp.n_ref > 1 ? &halfpel_thresh : nullptr;
+    a.me16x16.r.cost = 0x7fffffff;
+#pragma unroll 1
+    for (int i_ref = 0; i_ref < c.fp.n_ref; i_ref++)
+    {
+        MeSlot &m = c.w.slot;
+        const int rc = ref_cost(c, i_ref);
+        halfpel_thresh -= rc;
+        m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_16x16; m.xoff = 0; m.yoff = 0;
+        int (*mvc)[2] = c.w.mvc;
+        const uint32_t mvp = predict_mv_16x16(c, i_ref);
+        const int i_mvc = predict_mv_ref16x16(c, i_ref, mvc);
+        run_search<XS>(c, m, mvp, mvc, i_mvc, p_thresh);
+        if (allow_skip && i_ref == 0 && b_try_pskip && m.r.cost - m.r.cost_mv < 300 * lambda &&
+            iabs(m.r.mv[0] - c.pskip_mv[0]) + iabs(m.r.mv[1] - c.pskip_mv[1]) <= 1 && probe_pskip(c))
+            return 1;
+        m.r.cost += rc;
+        halfpel_thresh += rc;
+        if (m.r.cost < a.me16x16.r.cost)
+            a.me16x16 = m;
+        a.mvc[i_ref][0][0] = m.r.mv[0]; a.mvc[i_ref][0][1] = m.r.mv[1];
+        if (team_lane() == 0)
+            c.fp.cur.mvr[(size_t)i_ref * c.fc.mb_w * c.fc.mb_h + c.mb_xy] = pack_mv(m.r.mv[0], m.r.mv[1]);
+    }
+    cache_fill_rect(c, 0, 0, 4, 4, a.me16x16.i_ref, 0, 1, 0);
+    return 0;
+}
+
+template <int XS>
+PCAMV_FN void analyse_p8x8(MbCtx &c, MbAnalysis &a)
+{
+    const int i_ref = a.me16x16.i_ref;
+    const int rc = (c.fc.b_cabac || i_ref) ? ref_cost(c, i_ref) : 0;
+    int (*mvc)[2] = a.mvc[i_ref];
+    c.partition = PART_8x8;
+    int i_mvc = 1;
+    mvc[0][0] = a.me16x16.r.mv[0]; mvc[0][1] = a.me16x16.r.mv[1];
+#pragma unroll 1
+    for (int i = 0; i < 4; i++)
+    {
+        MeSlot &m = a.me8x8[i];
+        const int x8 = i & 1, y8 = i >> 1;
+        m.i_ref = i_ref; m.i_ref_cost = rc; m.i_pixel = PIX_8x8; m.xoff = 8 * x8; m.yoff = 8 * y8;
+        run_search<XS>(c, m, predict_mv(c, 4 * i, 2), mvc, i_mvc, nullptr);
+        cache_fill_rect(c, 2 * x8, 2 * y8, 2, 2, 0, pack_mv(m.r.mv[0], m.r.mv[1]), 0, 1);
+        mvc[i_mvc][0] = m.r.mv[0]; mvc[i_mvc][1] = m.r.mv[1];
+        i_mvc++;
+        m.r.cost += rc;
+        m.r.cost += c.fc.tab.lambda * 1;          // sub-partition type cost of an unsplit 8x8
+    }
+    a.cost8x8 = a.me8x8[0].r.cost + a.me8x8[1].r.cost + a.me8x8[2].r.cost + a.me8x8[3].r.cost;
+    if (c.fc.b_cabac)
+        a.cost8x8 -= rc;
+    a.sub[0] = a.sub[1] = a.sub[2] = a.sub[3] = SUB_8x8;
+}
+
+// 16x8 (dir = 0) or 8x16 (dir = 1)
+template <int XS>
+PCAMV_FN void analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
+{
+    c.partition = dir ? PART_8x16 : PART_16x8;
+    int total = 0;
+#pragma unroll 1
+    for (int i = 0; i < 2; i++)
+    {
+        MeSlot &best = dir ? a.me8x16[i] : a.me16x8[i];
+        const int r0 = dir ? a.me8x8[i].i_ref : a.me8x8[2 * i].i_ref;
+        const int r1 = dir ? a.me8x8[i + 2].i_ref : a.me8x8[2 * i + 1].i_ref;
+        const int nrefs = r0 == r1 ? 1 : 2;
+        best.r.cost = 0x7fffffff;
+#pragma unroll 1
+        for (int j = 0; j < nrefs; j++)
+        {
+            const int i_ref = j ? r1 : r0;
+            MeSlot &m = c.w.slot;
+            m.i_ref = i_ref; m.i_ref_cost = ref_cost(c, i_ref);
+            m.i_pixel = dir ? PIX_8x16 : PIX_16x8;
+            m.xoff = dir ? 8 * i : 0; m.yoff = dir ? 0 : 8 * i;
+            int (*mvc)[2] = c.w.mvc;
+            const int k1 = dir ? i + 1 : 2 * i + 1, k2 = dir ? i + 3 : 2 * i + 2;
+            mvc[0][0] = a.mvc[i_ref][0][0]; mvc[0][1] = a.mvc[i_ref][0][1];
+            mvc[1][0] = a.mvc[i_ref][k1][0]; mvc[1][1] = a.mvc[i_ref][k1][1];
+            mvc[2][0] = a.mvc[i_ref][k2][0]; mvc[2][1] = a.mvc[i_ref][k2][1];
+            if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, i_ref, 0, 1, 0);
+            else     cache_fill_rect(c, 0, 2 * i, 4, 2, i_ref, 0, 1, 0);
+            run_search<XS>(c, m, dir ? predict_mv(c, 4 * i, 2) : predict_mv(c, 8 * i, 4), mvc, 3, nullptr);
+            m.r.cost += m.i_ref_cost;
+            if (m.r.cost < best.r.cost)
+                best = m;
+        }
+        const uint32_t mv = pack_mv(best.r.mv[0], best.r.mv[1]);
+        if (dir) cache_fill_rect(c, 2 * i, 0, 2, 4, best.i_ref, mv, 1, 1);
+        else     cache_fill_rect(c, 0, 2 * i, 4, 2, best.i_ref, mv, 1, 1);
+        total += best.r.cost;
+    }
+    if (dir) a.cost8x16 = total; else a.cost16x8 = total;
+}
+
+// resumable forms of the three drivers above: same logic, loop positions and the search in flight kept in w.pt
 // 16x16 search over all references; returns 1 when the early P_SKIP termination fired, 2 when a search is out (AS)
 template <int XS, int AS>
-PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_pskip)
+PCAMV_FN int analyse_p16x16_rs(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_pskip)
 {
     const int lambda = c.fc.tab.lambda;
     PtState &pt = c.w.pt;
@@ -862,7 +982,7 @@ PCAMV_FN int analyse_p16x16(MbCtx &c, MbAnalysis &a, int allow_skip, int b_try_p
 }
 
 template <int XS, int AS>
-PCAMV_FN int analyse_p8x8(MbCtx &c, MbAnalysis &a)
+PCAMV_FN int analyse_p8x8_rs(MbCtx &c, MbAnalysis &a)
 {
     PtState &pt = c.w.pt;
     const int i_ref = a.me16x16.i_ref;
@@ -902,7 +1022,7 @@ PCAMV_FN int analyse_p8x8(MbCtx &c, MbAnalysis &a)
 
 // 16x8 (dir = 0) or 8x16 (dir = 1)
 template <int XS, int AS>
-PCAMV_FN int analyse_p16x8_8x16(MbCtx &c, MbAnalysis &a, int dir)
+PCAMV_FN int analyse_p16x8_8x16_rs(MbCtx &c, MbAnalysis &a, int dir)
 {
     PtState &pt = c.w.pt;
     if (!pt.in168)
@@ -1215,12 +1335,158 @@ PCAMV_DEV void wait_prev_raster(const MbCtx &c)
 
 // One macroblock of a P slice.  `prev_mv` = the 16 cache MVs left behind by the previous MB in raster order
 // (needed only for the pass-2 "forced skip without cache update" quirk, analyse.c:2668-2676).
-// F: feature mask of the instantiation — bit 0 = exhaustive searches (--me esa / tesa), bit 1 = sub-8x8 partitions.
+// F: feature mask of the instantiation — bit 0 = exhaustive searches (--me esa / tesa), bit 1 = sub-8x8 partitions
+template <int F>
+PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
+{
+    constexpr int XS = F & 1, SUB8 = (F >> 1) & 1;
+    const DevFrameCtx &fc = c.fc;
+    MbAnalysis &a = c.w.an;
+    c.n_log = 0;
+    c.partition = PART_16x16;
+    cache_load(c);
+    const uint32_t ps = predict_mv_pskip(c);
+    c.pskip_mv[0] = mv_x(ps); c.pskip_mv[1] = mv_y(ps);
+    init_limits(c);
+    c.env.cost_mv = fc.tab.cost_mv;
+    c.env.me_method = fc.me_method; c.env.me_range = fc.me_range; c.env.subme = fc.subme;
+    c.env.chroma_me = fc.chroma_me && fc.subme >= 5;
+    c.env.mbcmp_satd = fc.subme > 1;
+    c.env.mvsads = c.fp.mvsads ? c.fp.mvsads + (size_t)c.mb_y * c.fp.mvsads_cap : nullptr;
+
+    int b_try_pskip = 0, b_skip = 0;
+    if (fc.b_fast_pskip)
+    {
+        if (fc.subme >= 3) b_try_pskip = 1;
+        else if (c.type_left == MB_P_SKIP || c.type_top == MB_P_SKIP || c.type_topleft == MB_P_SKIP || c.type_topright == MB_P_SKIP)
+            b_skip = probe_pskip(c);
+    }
+    const ForcedMb *forced = c.fp.pass == 2 ? &c.fp.forced[c.mb_xy] : nullptr;
+    int type = MB_P_L0, partition = PART_16x16, early_skip = 0;
+    if (b_skip)
+    {
+        // (subme < 3 only) the reference takes this MB as P_SKIP before any search; pass 2 cannot override it
+        update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
+        finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, 1);
+        return;
+    }
+    early_skip = analyse_p16x16<XS>(c, a, 1, b_try_pskip);
+    if (early_skip)
+    {
+        type = MB_P_SKIP;
+        update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
+    }
+    if (forced)
+    {
+        if (forced->type != MB_P_SKIP && type == MB_P_SKIP)
+            analyse_p16x16<XS>(c, a, 0, b_try_pskip);       // the reference re-runs the 16x16 search without the skip exit
+        type = forced->type;
+    }
+    if (type == MB_P_SKIP)
+    {
+        if (!early_skip)
+        {
+            // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
+            // and the refs are what the 16x16 search left (its best reference)
+            wait_prev_raster(c);
+#pragma unroll 1
+            for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = PCAMV_LDV(prev_mv + i);
+        }
+        finalize_mb<SUB8>(c, a, MB_P_SKIP, PART_16x16, early_skip);
+        return;
+    }
+
+    // Elision has one exception.  When this pass's probe found the macroblock skippable but pass 1 did not (the re-run above),
+    // the host keeps b_skip_mc set (quirk q1, analyse.c:2663-2668 / encoder/macroblock.c:611-612): x264_macroblock_encode then
+    // takes the residual against whatever the analysis left in fdec, and that is the host's INTRA analysis, whose early-outs
+    // compare against the inter cost of the "dead" searches and refinement.  Such macroblocks get the full analysis.
+    if (forced && forced->used && fc.pass2_elide && !early_skip)
+    {
+        // pass 2, decision forced from pass 1: nothing the remaining searches produce survives analyse.c:2868-2991
+        // (info.cache[].i_partition is only written for P_L0, analyse.c:3612: a forced P_8x8 is 8x8 by construction)
+        type = forced->type; partition = forced->type == MB_P_8x8 ? PART_8x8 : forced->partition;
+#pragma unroll 1
+        for (int i = 0; i < 4; i++)
+            cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
+        finalize_mb<SUB8>(c, a, type, -partition, 0);
+        return;
+    }
+
+    const int flags = fc.analyse_inter;
+    const int psub16 = (flags & 0x10) != 0;
+    if (psub16)
+        analyse_p8x8<XS>(c, a);
+    int i_cost = a.me16x16.r.cost;
+    if (SUB8 && psub16 && (flags & 0x20) && a.cost8x8 < a.me16x16.r.cost)
+    {
+        // X264_ANALYSE_PSUB8x8: P_8x8 becomes the incumbent and every 8x8 block may split further (analyse.c:2697-2731)
+        type = MB_P_8x8; partition = PART_8x8;
+        i_cost = a.cost8x8;
+#pragma unroll 1
+        for (int i = 0; i < 4; i++)
+        {
+            const int c4x4 = analyse_sub8x8<XS>(c, a, i, SUB_4x4);
+            if (c4x4 < a.me8x8[i].r.cost)
+            {
+                int best8 = c4x4;
+                a.sub[i] = SUB_4x4;
+                const int c8x4 = analyse_sub8x8<XS>(c, a, i, SUB_8x4);
+                if (c8x4 < best8) { best8 = c8x4; a.sub[i] = SUB_8x4; }
+                const int c4x8 = analyse_sub8x8<XS>(c, a, i, SUB_4x8);
+                if (c4x8 < best8) { best8 = c4x8; a.sub[i] = SUB_4x8; }
+                i_cost += best8 - a.me8x8[i].r.cost;
+            }
+            cache_mv_p8x8(c, a, i);
+        }
+        a.cost8x8 = i_cost;
+    }
+    if (psub16)
+    {
+        const int thresh16x8 = a.me8x8[1].r.cost_mv + a.me8x8[2].r.cost_mv;
+        if (a.cost8x8 < a.me16x16.r.cost + thresh16x8)
+        {
+            analyse_p16x8_8x16<XS>(c, a, 0);
+            if (a.cost16x8 < i_cost) { i_cost = a.cost16x8; type = MB_P_L0; partition = PART_16x8; }
+            analyse_p16x8_8x16<XS>(c, a, 1);
+            if (a.cost8x16 < i_cost) { i_cost = a.cost8x16; type = MB_P_L0; partition = PART_8x16; }
+        }
+    }
+    c.partition = partition;
+    if (partition == PART_16x16) run_refine(c, a.me16x16);
+    else if (partition == PART_16x8) { run_refine(c, a.me16x8[0]); run_refine(c, a.me16x8[1]); }
+    else if (partition == PART_8x16) { run_refine(c, a.me8x16[0]); run_refine(c, a.me8x16[1]); }
+    else if (SUB8)
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) refine_sub8x8(c, a, i);
+
+    if (forced && forced->used)
+    {
+        // pass 2: type / partition / refs / MVs come from pass 1 with the embedding flips applied; for P_8x8 the reference
+        // forces the sub-partition types and leaves h->mb.i_partition as this pass decided it (analyse.c:2872-2890)
+        type = forced->type;
+        if (type != MB_P_8x8) partition = forced->partition;
+#pragma unroll 1
+        for (int i = 0; i < 4; i++)
+            cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) c.w.mv[scan8(i)] = forced->mv[i];
+        // the analysis slots keep the searched values; neighbours only ever see the cache
+    }
+    else
+        update_cache<SUB8>(c, a, type, partition);
+    // a forced decision names partitions this pass may never have searched: its record carries no partition slots
+    // (pass 2 has no cost table; the slots would be whatever the team's scratch held)
+    finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, 0);
+}
+
+// Resumable form of analyse_p_mb (same decisions, written as stages that can be left and re-entered).
 // AS = 1 (split wavefront): every search is handed out — the function returns PT_YIELD with the request in w.rq and is
 // called again, with w.pt and everything before MbWork::fenc_y as it left them and the result in w.rs, until it returns
 // PT_DONE.  The caller zeroes w.pt.stage before the first call of a macroblock.  AS = 0 never yields.
 template <int F, int AS>
-PCAMV_FN int analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
+PCAMV_FN int analyse_p_mb_rs(MbCtx &c, const uint32_t *prev_mv)
 {
     constexpr int XS = F & 1, SUB8 = (F >> 1) & 1;
     static_assert(!(AS && SUB8), "the sub-8x8 partition searches are synchronous");
@@ -1262,7 +1528,7 @@ PCAMV_FN int analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     }
     if (pt.stage == 1)
     {
-        const int r = analyse_p16x16<XS, AS>(c, a, 1, pt.b_try_pskip);
+        const int r = analyse_p16x16_rs<XS, AS>(c, a, 1, pt.b_try_pskip);
         if (r == 2) return PT_YIELD;
         pt.early_skip = (int8_t)r;
         if (r)
@@ -1275,7 +1541,7 @@ PCAMV_FN int analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     }
     if (pt.stage == 2)
     {
-        if (analyse_p16x16<XS, AS>(c, a, 0, pt.b_try_pskip) == 2) return PT_YIELD;
+        if (analyse_p16x16_rs<XS, AS>(c, a, 0, pt.b_try_pskip) == 2) return PT_YIELD;
         pt.stage = 3;
     }
     if (pt.stage == 3)
@@ -1322,7 +1588,7 @@ PCAMV_FN int analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     const int psub16 = (flags & 0x10) != 0;
     if (pt.stage == 4)
     {
-        if (psub16 && analyse_p8x8<XS, AS>(c, a) == PT_YIELD)
+        if (psub16 && analyse_p8x8_rs<XS, AS>(c, a) == PT_YIELD)
             return PT_YIELD;
         pt.i_cost = a.me16x16.r.cost;
         if (SUB8 && psub16 && (flags & 0x20) && a.cost8x8 < a.me16x16.r.cost)
@@ -1359,13 +1625,13 @@ PCAMV_FN int analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     }
     if (pt.stage == 5)
     {
-        if (analyse_p16x8_8x16<XS, AS>(c, a, 0) == PT_YIELD) return PT_YIELD;
+        if (analyse_p16x8_8x16_rs<XS, AS>(c, a, 0) == PT_YIELD) return PT_YIELD;
         if (a.cost16x8 < pt.i_cost) { pt.i_cost = a.cost16x8; pt.type = MB_P_L0; pt.partition = PART_16x8; }
         pt.stage = 6;
     }
     if (pt.stage == 6)
     {
-        if (analyse_p16x8_8x16<XS, AS>(c, a, 1) == PT_YIELD) return PT_YIELD;
+        if (analyse_p16x8_8x16_rs<XS, AS>(c, a, 1) == PT_YIELD) return PT_YIELD;
         if (a.cost8x16 < pt.i_cost) { pt.i_cost = a.cost8x16; pt.type = MB_P_L0; pt.partition = PART_8x16; }
         pt.stage = 7;
     }
@@ -1417,12 +1683,4 @@ PCAMV_FN int analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, 0);
     return PT_DONE;
 }
-// synchronous form: the whole macroblock in one call
-template <int F>
-PCAMV_DEV void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
-{
-    c.w.pt.stage = 0;
-    analyse_p_mb<F, 0>(c, prev_mv);
-}
-
 } // namespace pcamv

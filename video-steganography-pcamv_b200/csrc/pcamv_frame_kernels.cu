@@ -14,6 +14,7 @@
 // st.release.gpu after the macroblock's state is in HBM and consumed with ld.acquire.gpu.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <new>
 #include "pcamv_device.h"
 #include "pcamv_cost.cuh"

@@ -111,6 +111,9 @@ __device__ __forceinline__ void search_team(const BatchItem *__restrict__ items,
     const unsigned long long t_start = sp_globaltimer();
     unsigned long long *ring = sb.ring + (size_t)q * SPLIT_RING_CAP;
     unsigned long long *head = sb.heads + (size_t)q * 16;          // one 128-byte line per counter
+    unsigned long long *stats = (unsigned long long *)(sb.hdr + SPH_STATS);
+    unsigned long long s_wait = 0, s_serve = 0, s_n = 0, tm = t_start;
+#define SP_WORKER_EXIT() do { if (lane == 0) { atomicAdd(stats + 0, s_wait); atomicAdd(stats + 1, s_serve); atomicAdd(stats + 2, s_n); atomicAdd(stats + 3, 1ull); } } while (0)
     for (;;)
     {
         unsigned long long t = 0;
@@ -125,7 +128,11 @@ __device__ __forceinline__ void search_team(const BatchItem *__restrict__ items,
             if ((v >> 32) == t + 1)
                 break;
             if (sp_ld_acquire(sb.hdr + SPH_DONE))
+            {
+                s_wait += sp_globaltimer() - tm;
+                SP_WORKER_EXIT();
                 return;                                            // every row of every frame is finished: no request will come
+            }
             __nanosleep(ns);
             if (ns < 1024) ns <<= 1;
             else if (sp_globaltimer() - t_start > SPLIT_WATCHDOG_NS)
@@ -134,6 +141,7 @@ __device__ __forceinline__ void search_team(const BatchItem *__restrict__ items,
                 return;
             }
         }
+        { const unsigned long long now = sp_globaltimer(); s_wait += now - tm; tm = now; }
         const unsigned gslot = (unsigned)v;
         // the request: 32 words, one per lane
         {
@@ -155,6 +163,7 @@ __device__ __forceinline__ void search_team(const BatchItem *__restrict__ items,
             __threadfence();
             sp_st_release(sb.ready + gslot, seq);
         }
+        { const unsigned long long now = sp_globaltimer(); s_serve += now - tm; tm = now; s_n++; }
     }
 }
 
@@ -218,6 +227,11 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
     int claim_holdoff = 0;
     unsigned backoff = 64;
     const unsigned long long t_start = sp_globaltimer();
+    unsigned long long *stats = (unsigned long long *)(sb.hdr + SPH_STATS);
+    unsigned long long s_idle = 0, s_claim = 0, s_in = 0, s_run = 0, s_out = 0, s_steps = 0, tm = t_start;
+#define SP_TICK(acc) do { const unsigned long long now_ = sp_globaltimer(); acc += now_ - tm; tm = now_; } while (0)
+#define SP_CTRL_EXIT() do { if (lane == 0) { atomicAdd(stats + 4, s_idle); atomicAdd(stats + 5, s_claim); atomicAdd(stats + 6, s_in); atomicAdd(stats + 7, s_run); \
+        atomicAdd(stats + 8, s_out); atomicAdd(stats + 9, s_steps); atomicAdd(stats + 10, 1ull); atomicAdd(stats + 11, sp_globaltimer() - t_start); } } while (0)
     for (;;)
     {
         // ---- fill a free slot with a fresh row --------------------------------------------------------------------------
@@ -242,6 +256,7 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
         }
         else if (claim_holdoff)
             claim_holdoff--;
+        SP_TICK(s_claim);
 
         // ---- which rows can take a step? ---------------------------------------------------------------------------------
         bool ok = false;
@@ -258,8 +273,12 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
         {
             const unsigned busy_m = __ballot_sync(0xffffffffu, lane < rows_per_team && tt.state[lane] != SLOT_FREE);
             if (!busy_m && exhausted)
+            {
+                SP_CTRL_EXIT();
                 return;
+            }
             __nanosleep(backoff);
+            SP_TICK(s_idle);
             if (backoff < 2048) backoff <<= 1;
             else if (sp_ld_acquire(sb.hdr + SPH_ABORT) || sp_globaltimer() - t_start > SPLIT_WATCHDOG_NS)
             {
@@ -300,8 +319,11 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
         __syncwarp();
         if (it.fp.trace && lane == 0 && !resume) it.fp.trace[2 * c.mb_xy] = sp_globaltimer();
         sp_stage_fenc(it.fc, x, row, work);
-        const int r = analyse_p_mb<F, 1>(c, c.mb_xy ? it.fp.results[c.mb_xy - 1].mv : it.fp.stale_mv);
+        SP_TICK(s_in);
+        const int r = analyse_p_mb_rs<F, 1>(c, c.mb_xy ? it.fp.results[c.mb_xy - 1].mv : it.fp.stale_mv);
         __syncwarp();
+        SP_TICK(s_run);
+        s_steps++;
         if (r == PT_YIELD)
         {
             const int seq = tt.seq[k] + 1;
@@ -347,6 +369,7 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
             }
         }
         __syncwarp();
+        SP_TICK(s_out);
     }
 }
 

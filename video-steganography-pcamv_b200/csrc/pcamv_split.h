@@ -14,7 +14,9 @@ namespace pcamv {
 #define PCAMV_SPLIT_MIN_CTAS 6        // CTAs of 4 teams per SM the register budget must allow
 #endif
 // header words
-enum { SPH_ROWS_DONE = 0, SPH_DONE = 1, SPH_WORKERS = 2, SPH_SMS = 3, SPH_ABORT = 4, SPH_SM_ROLE = 32 };
+enum { SPH_ROWS_DONE = 0, SPH_DONE = 1, SPH_WORKERS = 2, SPH_SMS = 3, SPH_ABORT = 4, SPH_STATS = 8 /* 12 x u64 */, SPH_SM_ROLE = 32 };
+// SPH_STATS (ns summed over teams, globaltimer): search teams 0 waiting for a request, 1 serving, 2 requests served, 3 teams;
+// control teams 4 idle (nothing runnable), 5 claiming rows, 6 restore + stage, 7 analysis, 8 park + publish, 9 steps, 10 teams, 11 lifetime
 #define SPLIT_WATCHDOG_NS 20000000000ull    // a team that has waited this long for anything gives up and stops the launch (reported by the host)
 #define SPLIT_HDR_INTS (SPH_SM_ROLE + SPLIT_MAX_SMS)
 

@@ -169,8 +169,17 @@ class Dump:
             c = np.frombuffer(self.raw, dtype="<u8", count=9, offset=off)
             t = np.frombuffer(self.raw, dtype="<f8", count=3, offset=off + 72)
             d = {k: int(v) for k, v in zip(names, c)}
-            d.update(t_me=float(t[0]), t_ih=float(t[1]), t_analyse_p=float(t[2]))
+            d.update(t_me=float(t[0]), t_ih=float(t[1]), t_analyse_p=float(t[2]), pix_avg=0, pix_chroma_mc=0, pix_dct=0, ih_pix_avg=0, ih_pix_chroma_mc=0, ih_pix_dct=0, ih_pix_satd=0)
             out.append(d)
+        # 'CNT1' (newer dumps) follows its 'CNT0': pixels through quarter-pel averaging, chroma MC, DCT/quant/IDCT
+        k = 0
+        for tag, off, size in self.records:
+            if tag == "CNT0":
+                k += 1
+            elif tag == "CNT1" and k:
+                x = np.frombuffer(self.raw, dtype="<u8", count=7, offset=off)
+                out[k - 1].update(pix_avg=int(x[0]), pix_chroma_mc=int(x[1]), pix_dct=int(x[2]), ih_pix_avg=int(x[3]),
+                                  ih_pix_chroma_mc=int(x[4]), ih_pix_dct=int(x[5]), ih_pix_satd=int(x[6]))
         return out
 
     def quant_tables(self):

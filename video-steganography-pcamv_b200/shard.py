@@ -20,8 +20,19 @@ def assign_gops(n_gops, world):
     return [list(range(r, n_gops, world)) for r in range(world)]
 
 
+def _md5_to_ints(hexdigest):
+    v = int(hexdigest or "0", 16)
+    hi, lo = v >> 64, v & ((1 << 64) - 1)
+    return [hi - (1 << 64) if hi >= (1 << 63) else hi, lo - (1 << 64) if lo >= (1 << 63) else lo]
+
+
+def _ints_to_md5(hi, lo):
+    return "%032x" % (((hi & ((1 << 64) - 1)) << 64) | (lo & ((1 << 64) - 1)))
+
+
 def gather_gop_results(local, group=None):
-    """local: list of dicts {gop, n_bits, payload (bytes of 0/1), n_mv, n_flipped, bytes} of this rank's GOPs.
+    """local: list of dicts {gop, n_bits, payload (bytes of 0/1), n_mv, n_flipped, bytes[, md5, payload_md5]} of this rank's
+    GOPs (md5 = digest of the GOP's NAL stream, payload_md5 = digest of its message + stego bits; hex strings).
     Returns on rank 0 the records of all ranks sorted by GOP index (None elsewhere)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return sorted(local, key=lambda r: r["gop"])
@@ -29,14 +40,15 @@ def gather_gop_results(local, group=None):
     rank = dist.get_rank(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     # fixed-size header per GOP + one flat payload tensor: two collectives, no pickling on the data path
-    hdr = torch.tensor([[r["gop"], r["n_bits"], r["n_mv"], r["n_flipped"], r["bytes"]] for r in local] or [[-1, 0, 0, 0, 0]],
+    hdr = torch.tensor([[r["gop"], r["n_bits"], r["n_mv"], r["n_flipped"], r["bytes"]] + _md5_to_ints(r.get("md5")) +
+                        _md5_to_ints(r.get("payload_md5")) for r in local] or [[-1, 0, 0, 0, 0, 0, 0, 0, 0]],
                        dtype=torch.int64, device=dev)
     pay = torch.tensor(list(b"".join(bytes(r["payload"]) for r in local)) or [0], dtype=torch.uint8, device=dev)
     sizes = torch.tensor([hdr.shape[0], pay.numel()], dtype=torch.int64, device=dev)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes, group=group)
     max_h = int(max(s[0] for s in all_sizes)); max_p = int(max(s[1] for s in all_sizes))
-    hdr_pad = torch.full((max_h, 5), -1, dtype=torch.int64, device=dev); hdr_pad[:hdr.shape[0]] = hdr
+    hdr_pad = torch.full((max_h, 9), -1, dtype=torch.int64, device=dev); hdr_pad[:hdr.shape[0]] = hdr
     pay_pad = torch.zeros(max_p, dtype=torch.uint8, device=dev); pay_pad[:pay.numel()] = pay
     hdrs = [torch.zeros_like(hdr_pad) for _ in range(world)]
     pays = [torch.zeros_like(pay_pad) for _ in range(world)]
@@ -52,6 +64,7 @@ def gather_gop_results(local, group=None):
             if row[0] < 0:
                 continue
             out.append({"gop": row[0], "n_bits": row[1], "n_mv": row[2], "n_flipped": row[3], "bytes": row[4],
+                        "md5": _ints_to_md5(row[5], row[6]), "payload_md5": _ints_to_md5(row[7], row[8]),
                         "payload": raw[pos:pos + row[1]], "rank": r})
             pos += row[1]
     return sorted(out, key=lambda r: r["gop"])

@@ -42,17 +42,20 @@ WIDTH, HEIGHT = 1920, 1080
 REF_ARGS = "--qp 26 --ref 1 --keyint 250 --me umh --subme 5 --emrate 0.2"
 WORKLOAD = ("1080p synthetic YUV420 (synth/pcamv_synth.c config 2), --me umh --subme 5 --ref 1 --qp 26 --emrate 0.2; "
             "subme 5 instead of 7: RD mode decision is raster-serial on CABAC state (DESIGN.md)")
-CLIP_FRAMES = 3            # I P P
-BATCH_FRAME = 2            # the second P frame: spatial + temporal MV candidates are both live
+DISTINCT = 8               # distinct P frames the contexts of a GPU analyse (context i gets frame BATCH_FRAME + i % DISTINCT of its clip)
+CLIP_FRAMES = 3            # I P P: the clip of the CPU legs (reference arm, cpu_baseline)
+BATCH_FRAME = 2            # first analysed frame: spatial + temporal MV candidates are both live from here on
 METRIC = "me_mcandidates_per_sec"
+ENCODER_JOB = "config4-small"      # the whole-encoder job every default run encodes across its ranks (encjob.JOBS)
 
 
-def prepare_inputs(pcamv, rank, workdir):
-    """Synthetic clip + instrumented reference run for BATCH_FRAME: planes, expected records, candidate counters."""
+def prepare_inputs(pcamv, rank, workdir, n_frames=1):
+    """Synthetic clip + instrumented reference run for frames BATCH_FRAME .. BATCH_FRAME + n_frames - 1: planes, expected
+    records, work counters."""
     import refrun
-    clip = refrun.synth_clip(pcamv, WIDTH, HEIGHT, CLIP_FRAMES, config=2, stream=rank, workdir=workdir)
+    clip = refrun.synth_clip(pcamv, WIDTH, HEIGHT, BATCH_FRAME + n_frames, config=2, stream=rank, workdir=workdir)
     dump = os.path.join(workdir, "dump.bin")
-    refrun.run_ref(clip, WIDTH, HEIGHT, REF_ARGS.split(), dump=dump, frames="%d:%d" % (BATCH_FRAME, BATCH_FRAME + 1), count=True)
+    refrun.run_ref(clip, WIDTH, HEIGHT, REF_ARGS.split(), dump=dump, frames="%d:%d" % (BATCH_FRAME, BATCH_FRAME + n_frames), count=True)
     return clip, dump
 
 
@@ -246,6 +249,16 @@ def run_reference_arm(args, pcamv, rank, world):
             "analysed_p_frames_per_sec": p_frames / t,
             "encode_frames_per_sec": cores * CLIP_FRAMES / float(np.mean(totals)),
             "e2e": {"value": v, "unit": "Mcandidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.encoder_job != "none":
+        # the same whole-encoder job the GPU arm shards over its ranks, here as one reference encoder process per shard on
+        # the host cores; the outputs' digests stay cached on this box as the parity oracle of the GPU arm
+        from pcamv_b200 import encjob
+        encjob.make_clip(pcamv, args.encoder_job)
+        ref = encjob.reference_side(pcamv, args.encoder_job)
+        job = encjob.JOBS[args.encoder_job]
+        line["encoder_job"] = {"job": args.encoder_job, "what": job["what"], "args": " ".join(encjob.job_args(job)), "frames": ref["frames"],
+                               "shards": job["shards"], "encode_embed_fps": ref["fps"], "seconds": ref["seconds"], "cores": ref["cores"],
+                               "note": "oracle/_ref/x264_wide (the reference's C sources, no asm), one single-threaded process per shard"}
     print(json.dumps(line))
 
 
@@ -265,6 +278,10 @@ def main():
                     help="pcamv_cfg.pass2_elide: skip the pass-2 searches whose results the reference overwrites (not the default: "
                          "the headline number executes everything the reference executes)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (profiling runs)")
+    ap.add_argument("--distinct-frames", type=int, default=DISTINCT, help="distinct P frames of the clip spread over the contexts of a GPU")
+    ap.add_argument("--encoder-job", default=ENCODER_JOB,
+                    help="whole-encoder job sharded over the ranks (encjob.JOBS: config2 / config4 / config4-k30 / config5 at BASELINE's sizes, "
+                         "*-small bounded versions), or 'none'")
     args = ap.parse_args()
 
     # one hardware work queue per context stream (the default of 8 would serialise contexts 9..S behind the first 8)
@@ -293,45 +310,62 @@ def main():
 
     import frame_parity
     S = max(1, args.streams)
+    D = max(1, min(args.distinct_frames, S))
     workdir = tempfile.mkdtemp(prefix="pcamv_bench_%d_" % rank)
-    clip, dumpf = prepare_inputs(pcamv, rank, workdir)
+    clip, dumpf = prepare_inputs(pcamv, rank, workdir, n_frames=D)
     dump = pcamv.dumpfmt.Dump(dumpf)
-    units = [u for u in dump.slice_units() if u["slice"].frame == BATCH_FRAME and u["slice"].with_planes]
-    assert [u["slice"].pass_ for u in units] == [1, 2], "dump does not hold both passes of frame %d" % BATCH_FRAME
-    s = units[0]["slice"]
+    all_units = [u for u in dump.slice_units() if u["slice"].with_planes]
+    frames = sorted({u["slice"].frame for u in all_units})
+    assert frames == list(range(BATCH_FRAME, BATCH_FRAME + D)), "dump holds frames %s" % frames
+    by_frame = []
+    for fr in frames:
+        us = [u for u in all_units if u["slice"].frame == fr]
+        assert [u["slice"].pass_ for u in us] == [1, 2], "dump does not hold both passes of frame %d" % fr
+        by_frame.append(us)
+    s = by_frame[0][0]["slice"]
 
-    # reference-counted work of this frame: the per-pass counters of the two dumped passes
+    # reference-counted work per distinct frame: the per-pass counters of its two dumped passes (file order = frame order)
     cnt = dump.counters()
-    assert len(cnt) == 2, "expected the counters of two passes, got %d" % len(cnt)
-    work = {k: cnt[0][k] + cnt[1][k] for k in ("sad", "satd", "ih_luma", "ih_chroma", "pix_sad", "pix_satd")}
-    cand_per_frame = candidates_of(work)
-    # integer-op count per frame, reference-counted: SAD 2 ops/pixel, SATD 7 ops/pixel
-    ops_per_frame = 2.0 * work["pix_sad"] + 7.0 * work["pix_satd"]
+    assert len(cnt) == 2 * D, "expected the counters of %d passes, got %d" % (2 * D, len(cnt))
+    W_SAD, W_SATD, W_AVG, W_CHROMA, W_DCT = 2.0, 7.0, 2.0, 8.0, 14.0       # integer ops per pixel, SURVEY.md 8(d)
+    def ops_of(c, part):
+        """reference-counted integer ops of one pass: part = 'search' (wavefront kernel) or 'table' (cost-table kernel)"""
+        if part == "table":
+            return W_SATD * c["ih_pix_satd"] + W_AVG * c["ih_pix_avg"] + W_CHROMA * c["ih_pix_chroma_mc"] + W_DCT * c["ih_pix_dct"]
+        return (W_SAD * c["pix_sad"] + W_SATD * (c["pix_satd"] - c["ih_pix_satd"]) + W_AVG * (c["pix_avg"] - c["ih_pix_avg"]) +
+                W_CHROMA * (c["pix_chroma_mc"] - c["ih_pix_chroma_mc"]) + W_DCT * (c["pix_dct"] - c["ih_pix_dct"]))
+    cand_frame = [candidates_of({k: cnt[2 * d][k] + cnt[2 * d + 1][k] for k in ("sad", "satd", "ih_luma", "ih_chroma")}) for d in range(D)]
+    ops_frame = [{"pass1": ops_of(cnt[2 * d], "search"), "table": ops_of(cnt[2 * d], "table"), "pass2": ops_of(cnt[2 * d + 1], "search")}
+                 for d in range(D)]
+    frame_of = [i % D for i in range(S)]                        # context i analyses distinct frame i % D
+    cand_step = float(sum(cand_frame[d] for d in frame_of))      # candidates of one step of this rank
+    ops_step = {k: float(sum(ops_frame[d][k] for d in frame_of)) for k in ("pass1", "table", "pass2")}
 
-    # ---- parity gate before any number ---------------------------------------------------------------------------
+    # ---- parity gate before any number: every distinct frame, both passes, bit for bit against the reference's records ----
     ctxs = [frame_parity.open_ctx(pcamv, dump, s, device=local_rank, rows_per_cta=args.rows_per_cta if S > 1 else 1, pass2_elide=int(args.pass2_elide)) for _ in range(S)]
-    if args.pass2_elide:
-        # the gate compares complete pass-2 logs, so it runs on a context that executes everything
-        gate = frame_parity.open_ctx(pcamv, dump, s, device=local_rank)
-        par = frame_parity.check_dump(pcamv, dump, units=units, ctx=gate)
-    else:
-        par = frame_parity.check_dump(pcamv, dump, units=units, ctx=ctxs[0], keep_ctx=True)       # raises on the first mismatch
+    gate = frame_parity.open_ctx(pcamv, dump, s, device=local_rank)           # (executes everything, whatever --pass2-elide says)
+    par = {"calls": 0, "mbs": 0, "ih": 0}
+    for us in by_frame:
+        p_ = frame_parity.check_dump(pcamv, dump, units=us, ctx=gate, keep_ctx=True)       # raises on the first mismatch
+        for k in par:
+            par[k] += p_[k]
+    gate.close()
 
-    x = units[0]["ctx"]
     H, W = s.lines_y, s.width
-    fy, fu, fv = (np.ascontiguousarray(s.fenc[0][:, :W]), np.ascontiguousarray(s.fenc[1][:, :W // 2]),
-                  np.ascontiguousarray(s.fenc[2][:, :W // 2]))
-    r = s.refs[0]
-    ry = np.ascontiguousarray(r["luma"][0][32:32 + H, 32:32 + W])
-    ru = np.ascontiguousarray(r["u"][16:16 + H // 2, 16:16 + W // 2])
-    rv = np.ascontiguousarray(r["v"][16:16 + H // 2, 16:16 + W // 2])
-    # the end-to-end arm copies from / to page-locked host memory (pcamv_host_alloc), as an encoder host would hold its frames
-    fy, fu, fv, ry, ru, rv = [pcamv.host.pinned_copy(a) for a in (fy, fu, fv, ry, ru, rv)]
-    col = dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"])
-    e = units[0]["embd"]
-    pass1 = frame_parity.pass1_records(pcamv, e)
-    refs, pocs, cur_poc = list(range(x["n_ref"])), x["ref_poc"][:x["n_ref"]], x["cur_poc"]
     n_mb = (W // 16) * (H // 16)
+    inputs = []
+    for us in by_frame:
+        s1, x, e = us[0]["slice"], us[0]["ctx"], us[0]["embd"]
+        r = s1.refs[0]
+        planes = [np.ascontiguousarray(s1.fenc[0][:, :W]), np.ascontiguousarray(s1.fenc[1][:, :W // 2]), np.ascontiguousarray(s1.fenc[2][:, :W // 2]),
+                  np.ascontiguousarray(r["luma"][0][32:32 + H, 32:32 + W]), np.ascontiguousarray(r["u"][16:16 + H // 2, 16:16 + W // 2]),
+                  np.ascontiguousarray(r["v"][16:16 + H // 2, 16:16 + W // 2])]
+        # the end-to-end arm copies from / to page-locked host memory (pcamv_host_alloc), as an encoder host would hold its frames
+        planes = [pcamv.host.pinned_copy(a) for a in planes]
+        inputs.append(dict(fenc=planes[:3], ref=planes[3:], poc=r["poc"],
+                           col=dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"]),
+                           pass1=frame_parity.pass1_records(pcamv, e), filp=e["filp"], refs=list(range(x["n_ref"])),
+                           pocs=x["ref_poc"][:x["n_ref"]], cur_poc=x["cur_poc"]))
 
     def barrier():
         if world > 1:
@@ -344,21 +378,22 @@ def main():
         def wrap(i):
             out[i] = fn(i)
         th = [threading.Thread(target=wrap, args=(i,)) for i in range(S)]
-        for t in th: t.start()
-        for t in th: t.join()
+        for t_ in th: t_.start()
+        for t_ in th: t_.join()
         return out
 
-    # ---- device-resident arm: every context holds its own copy of the frame inputs in HBM ---------------------------
+    # ---- device-resident arm: every context holds its own frame inputs in HBM ----------------------------------------------
     def stage(i):
-        c = ctxs[i]
-        c.put_fenc(fy, fu, fv)
-        c.put_ref(0, r["poc"], ry, ru, rv)
-        c.frame_upload(1, refs, pocs, cur_poc, cost_table=True, **col)
-        m1, _ = c.analyse_p(1, refs, pocs, cur_poc, cost_table=True, **col)
-        c.frame_upload(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], **col)
+        c, q = ctxs[i], inputs[frame_of[i]]
+        c.put_fenc(*q["fenc"])
+        c.put_ref(0, q["poc"], *q["ref"])
+        c.frame_upload(1, q["refs"], q["pocs"], q["cur_poc"], cost_table=True, **q["col"])
+        m1, _ = c.analyse_p(1, q["refs"], q["pocs"], q["cur_poc"], cost_table=True, **q["col"])
+        c.frame_upload(2, q["refs"], q["pocs"], q["cur_poc"], pass1=q["pass1"], filp=q["filp"], stale_mv=m1["mv"][-1], **q["col"])
         return m1
     staged = run_threads(stage)
-    assert all((m["mv"] == staged[0]["mv"]).all() for m in staged)
+    assert all((staged[i]["mv"] == staged[frame_of[i]]["mv"]).all() for i in range(S))        # same frame, same result
+    assert D == 1 or not (staged[0]["mv"] == staged[1]["mv"]).all()                            # the frames really differ
 
     def dev_steps(i, k):
         c = ctxs[i]
@@ -390,17 +425,17 @@ def main():
     k_ms = np.array(k_ms) / args.steps            # mean kernel durations (per context while all S run concurrently, or of the batch launch)
     n_launch = sum(c.launch_count() for c in ctxs) - launches0
 
-    # ---- end-to-end arm: host buffers in, host records out, S encoder threads ------------------------------------------
+    # ---- end-to-end arm: host buffers in, host records out ---------------------------------------------------------------------
     outs1 = [c.alloc_outputs(pinned=True) for c in ctxs]
     outs2 = [c.alloc_outputs(pinned=True) for c in ctxs]
 
     def e2e_steps(i, k):
-        c = ctxs[i]
+        c, q = ctxs[i], inputs[frame_of[i]]
         for _ in range(k):
-            c.put_fenc(fy, fu, fv)
-            c.put_ref(0, r["poc"], ry, ru, rv)
-            m1, l1 = c.analyse_p(1, refs, pocs, cur_poc, cost_table=True, out=outs1[i], **col)
-            m2, l2 = c.analyse_p(2, refs, pocs, cur_poc, pass1=pass1, filp=e["filp"], stale_mv=m1["mv"][-1], out=outs2[i], **col)
+            c.put_fenc(*q["fenc"])
+            c.put_ref(0, q["poc"], *q["ref"])
+            m1, l1 = c.analyse_p(1, q["refs"], q["pocs"], q["cur_poc"], cost_table=True, out=outs1[i], **q["col"])
+            m2, l2 = c.analyse_p(2, q["refs"], q["pocs"], q["cur_poc"], pass1=q["pass1"], filp=q["filp"], stale_mv=m1["mv"][-1], out=outs2[i], **q["col"])
         return m1, l1, m2, l2
     # batch launches: the contexts are split into E2E_LANES independent sets, each driven by its own host thread through
     # upload -> pcamv_analyse_p_batch(pass 1) -> pcamv_analyse_p_batch(pass 2) -> download, so that one set's PCIe copies
@@ -410,13 +445,14 @@ def main():
 
     def e2e_lane(ids, k):
         cs = [ctxs[i] for i in ids]
+        qs = [inputs[frame_of[i]] for i in ids]
         for _ in range(k):
-            for c in cs:
-                c.put_fenc(fy, fu, fv)
-                c.put_ref(0, r["poc"], ry, ru, rv)
-            a1 = [(1, refs, pocs, cur_poc, dict(cost_table=True, **col)) for _ in cs]
+            for c, q in zip(cs, qs):
+                c.put_fenc(*q["fenc"])
+                c.put_ref(0, q["poc"], *q["ref"])
+            a1 = [(1, q["refs"], q["pocs"], q["cur_poc"], dict(cost_table=True, **q["col"])) for q in qs]
             o1 = pcamv.host.analyse_p_batch(cs, a1, outs=[outs1[i] for i in ids])
-            a2 = [(2, refs, pocs, cur_poc, dict(pass1=pass1, filp=e["filp"], stale_mv=o[0]["mv"][-1], **col)) for o in o1]
+            a2 = [(2, q["refs"], q["pocs"], q["cur_poc"], dict(pass1=q["pass1"], filp=q["filp"], stale_mv=o[0]["mv"][-1], **q["col"])) for q, o in zip(qs, o1)]
             o2 = pcamv.host.analyse_p_batch(cs, a2, outs=[outs2[i] for i in ids])
         return o1, o2
 
@@ -443,10 +479,11 @@ def main():
     barrier()
     clocks = sampler.result()
     n_launch_e2e = sum(c.launch_count() for c in ctxs) - launches0 - n_launch
-    out = outs[0]
-    assert all((o[2]["mv"] == out[2]["mv"]).all() and (o[2]["type"] == out[2]["type"]).all() for o in outs)
-    h2d = 2 * (fy.nbytes + fu.nbytes + fv.nbytes) + 2 * 68 * n_mb + n_mb * pcamv.host.PASS1_MB_DTYPE.itemsize + len(e["filp"])
-    d2h = out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes
+    assert all((outs[i][2]["mv"] == outs[frame_of[i]][2]["mv"]).all() and (outs[i][2]["type"] == outs[frame_of[i]][2]["type"]).all() for i in range(S))
+    q0 = inputs[0]
+    h2d = 2 * sum(a.nbytes for a in q0["fenc"]) + sum(a.nbytes for a in q0["ref"]) - sum(a.nbytes for a in q0["fenc"]) + 2 * 68 * n_mb + \
+        n_mb * pcamv.host.PASS1_MB_DTYPE.itemsize + len(q0["filp"])
+    d2h = sum(o.nbytes for o in outs[0])
 
     # extra, not the headline: the same device-resident step with the dead pass-2 searches elided (what the host encoder runs)
     elided = None
@@ -468,16 +505,23 @@ def main():
                           "host encoder does not need them.  Candidates are still credited as the reference executes them."}
 
     int_peak = ctxs[0].int_peak_gops()
+    plane_y = ctxs[0].plane_bytes(0); plane_c = ctxs[0].plane_bytes(4)
+    log_stride = ctxs[0].log_stride
+    for c in ctxs:
+        c.close()
+    ctxs = []
+
+    # ---- whole-encoder job, sharded over the ranks: encode + embed, NCCL gather of payload / statistics inside the clock -------
+    job = None
+    if args.encoder_job != "none":
+        job = encoder_job_leg(pcamv, args.encoder_job, rank, world, local_rank, barrier)
 
     # ---- aggregate over ranks (max time, summed work) ----------------------------------------------------------------
     from pcamv_b200 import shard
     dev_s_max, e2e_s_max = shard.max_over_ranks([dev_s, e2e_s])
     if elided is not None:
         elided["ms_per_step"] = shard.max_over_ranks([elided["ms_per_step"]])[0]
-    cand_all = shard.sum_over_ranks([float(cand_per_frame) * S])[0]           # candidates of one step over all ranks and contexts
-    # the one exchange step of a sharded run: per-shard statistics to rank 0 (payload bits travel the same way, shard.py)
-    shards = shard.gather_gop_results([{"gop": rank * S + i, "n_bits": 0, "payload": b"", "n_mv": int(par["ih"]), "n_flipped": 0,
-                                        "bytes": 0} for i in range(S)])
+    cand_all = shard.sum_over_ranks([cand_step])[0]           # candidates of one step over all ranks and contexts
 
     if rank == 0:
         value = cand_all * args.steps / dev_s_max / 1e6
@@ -490,69 +534,125 @@ def main():
         hbm_peak = peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6650.0))
         ms_w1, ms_ct, ms_w2 = [float(v) for v in k_ms.mean(axis=0)]
         kernels = {"k_analyse_p(pass1)": ms_w1, "k_cost_table": ms_ct, "k_analyse_p(pass2)": ms_w2}
+        kops = {"k_analyse_p(pass1)": ops_step["pass1"], "k_cost_table": ops_step["table"], "k_analyse_p(pass2)": ops_step["pass2"]}
         dom = max(kernels, key=kernels.get)
         # algorithmic HBM bytes of one launch of either kernel: fenc once, 4 luma + 2 chroma reference planes once,
-        # per-MB records in/out (DESIGN.md "HBM traffic"); S launches of the dominant kernel overlap, so the achieved
-        # figure is S launches' bytes over the mean launch duration
-        plane_y = ctxs[0].plane_bytes(0); plane_c = ctxs[0].plane_bytes(4)
-        alg_bytes = fy.nbytes + fu.nbytes + fv.nbytes + 4 * plane_y + 2 * plane_c + n_mb * (128 + ctxs[0].log_stride * 16 + 68)
-        achieved = S * alg_bytes / (kernels[dom] * 1e-3) / 1e9      # (batch: one launch covers S frames; streams: S overlapping launches)
-        traffic = None
+        # per-MB records in/out (DESIGN.md "Data layout"); a batch launch covers S frames
+        alg_bytes = sum(a.nbytes for a in q0["fenc"]) + 4 * plane_y + 2 * plane_c + n_mb * (128 + log_stride * 16 + 68)
+        traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if tr["contexts_per_gpu"] == S and batch:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]       # per launch of the dominant kernel, one ncu capture
+                traffic_src = tr.get("source")
         except Exception:
             pass
+        # Integer-issue roofline (this path is integer-ALU / issue bound, not HBM bound).  Numerator: the
+        # REFERENCE's work for the frames of one launch in 8(d)'s per-pixel weights (SAD 2, SATD 7, quarter-pel average 2,
+        # chroma bilinear 8, DCT+quant+dequant+IDCT 14), counted by the instrumented reference (oracle/ref_hooks.c CNT0 / CNT1).
+        # Denominator: 32-bit lane-instructions per second of the VABSDIFF4 / IADD3 / LOP3 mix measured on this GPU
+        # (pcamv_int_peak).  A packed VABSDIFF4-accumulate retires 8 numerator ops per lane-instruction, so 100 % is not the
+        # ceiling of a perfectly packed SAD loop; the figure is comparable between kernels and rounds, which is its use.
+        def roof(name):
+            ach = kops[name] / (kernels[name] * 1e-3) / 1e9
+            return {"kernel": name, "bound": "int_issue", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak,
+                    "ms_per_launch": kernels[name], "ops_per_launch": kops[name],
+                    "hbm_algorithmic_gbs": S * alg_bytes / (kernels[name] * 1e-3) / 1e9}
+        per_kernel = [roof(k) for k in kernels]
+        dom_roof = dict(roof(dom))
+        dom_roof.update({"traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(S * alg_bytes),
+                         "hbm_peak_gbs": hbm_peak, "hbm_frac": S * alg_bytes / (kernels[dom] * 1e-3) / 1e9 / hbm_peak,
+                         "peak_source": "pcamv_int_peak microbenchmark on this GPU (lane-instructions/s); HBM peak from " +
+                                        ("MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"),
+                         "ops": "reference-counted per launch: 2/px SAD, 7/px SATD, 2/px qpel average, 8/px chroma MC, 14/px DCT+quant+IDCT",
+                         "note": "integer-issue bound (SURVEY.md 8(d)); HBM traffic is a fraction of a percent of peak by design"})
         frames_all = world * S * args.steps
+        ops_all = sum(ops_step.values())
         line = {
             "metric": METRIC, "value": value, "unit": "Mcandidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "step": "one 1080p P frame through the frame seam in each of %d independent encoder contexts per GPU (GOP shards: own "
-                               "CUDA stream, own frame buffers): wavefront analysis pass 1 + candidate-MV cost table + wavefront analysis "
-                               "pass 2 (%d searches/refines, %d cost-table entries per frame)" % (S, par["calls"], par["ih"]),
-                       "contexts_per_gpu": S, "pass2": ("searches whose results the reference overwrites are elided (pcamv_cfg.pass2_elide)"
-                                                        if args.pass2_elide else "everything the reference executes"), "launch": ("one wavefront launch for all contexts (pcamv_analyse_p_batch)" if batch else
-                                                           "one launch per context, each on its own CUDA stream"), "shards_gathered": len(shards), "candidates_per_frame": int(cand_per_frame),
+                               "frame buffers; %d distinct frames of the clip, context i holds frame %d + i %% %d): wavefront analysis pass 1 + "
+                               "candidate-MV cost table + wavefront analysis pass 2" % (S, D, BATCH_FRAME, D),
+                       "contexts_per_gpu": S, "distinct_frames": D,
+                       "pass2": ("searches whose results the reference overwrites are elided (pcamv_cfg.pass2_elide)"
+                                 if args.pass2_elide else "everything the reference executes"),
+                       "launch": ("one wavefront launch for all contexts (pcamv_analyse_p_batch)" if batch else
+                                  "one launch per context, each on its own CUDA stream"),
+                       "candidates_per_step_per_gpu": int(cand_step),
                        "l2": "inputs larger than L2: %d contexts x %.1f MB of planes each, no flush" % (S, (alg_bytes) / 1e6),
-                       "parity_gate": "passed: %d searches, %d macroblock decisions, %d cost-table entries bit-exact vs reference"
-                                      % (par["calls"], par["mbs"], par["ih"])},
+                       "parity_gate": "passed: %d searches, %d macroblock decisions, %d cost-table entries of %d distinct frames bit-exact vs reference"
+                                      % (par["calls"], par["mbs"], par["ih"], D)},
             "analysed_p_frames_per_sec": frames_all / dev_s_max,
             "kernel_ms": kernels,
             "e2e": {"value": e2e_v, "unit": "Mcandidates/s", "h2d_bytes_per_step": int(h2d) * S, "d2h_bytes_per_step": int(d2h) * S,
-                    "ms_per_step": e2e_s_max / args.steps * 1e3, "analysed_p_frames_per_sec": frames_all / e2e_s_max},
+                    "ms_per_step": e2e_s_max / args.steps * 1e3, "analysed_p_frames_per_sec": frames_all / e2e_s_max,
+                    "note": "includes pcamv_put_ref (H2D + GPU border expansion + half-pel filter), which the reference arm's clock "
+                            "(x264_macroblock_analyse of the P slices) does not contain"},
             "gpu_launches": int(n_launch + n_launch_e2e),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "kernel": dom, "algorithmic_bytes_per_launch": int(S * alg_bytes),
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                         "note": "the analysis kernels are integer-issue / dependency-latency bound, not HBM bound (SURVEY.md 8(d)); "
-                                 "see int_issue"},
-            "int_issue": {"achieved_gops": ops_per_frame * frames_all / dev_s_max / 1e9 / world, "peak_gops": int_peak,
-                          "frac": ops_per_frame * frames_all / dev_s_max / 1e9 / world / int_peak,
-                          "ops": "reference-counted per GPU: 2/pixel SAD, 7/pixel SATD",
-                          "peak_source": "pcamv_int_peak microbenchmark on this box"},
+            "roofline": dom_roof,
+            "roofline_per_kernel": per_kernel,
+            "int_issue": {"achieved_gops": ops_all * args.steps / dev_s_max / 1e9, "peak_gops": int_peak,
+                          "frac": ops_all * args.steps / dev_s_max / 1e9 / int_peak, "ops": "whole step (three kernels), per GPU, weights as in roofline"},
         }
-        for c in ctxs:
-            c.close()
-        ctxs = []
         if elided is not None:
             elided["value"] = cand_all / (elided["ms_per_step"] * 1e-3) / 1e6
             elided["unit"] = "Mcandidates/s"
             line["pass2_elided"] = elided
-        if not args.no_cpu_baseline and world == 1:          # (CPU and whole-encoder legs: rank 0 at N = 1 only)
-            line["cpu_baseline"] = cpu_baseline_block(pcamv, clip, workdir)
+        if job is not None:
+            line["encoder_job"] = job
+        if not args.no_cpu_baseline and world == 1:          # (CPU and single-stream legs: rank 0 at N = 1 only)
+            cclip = __import__("refrun").synth_clip(pcamv, WIDTH, HEIGHT, CLIP_FRAMES, config=2, stream=0, workdir=workdir)
+            line["cpu_baseline"] = cpu_baseline_block(pcamv, cclip, workdir)
             line["encoder_e2e"] = encoder_e2e(pcamv, workdir, local_rank)
-            line["encoder_e2e_sharded"] = encoder_e2e_sharded(pcamv, workdir, local_rank)
             # BASELINE.json config 3 (exhaustive search, merange 32, 4 references): one stream, whole encoder
             line["encoder_e2e_esa"] = encoder_e2e(pcamv, workdir, local_rank, frames=6, ref_args=ESA_ARGS, config=3, tag="esa")
         print(json.dumps(line))
-    for c in ctxs:
-        c.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def encoder_job_leg(pcamv, name, rank, world, local_rank, barrier):
+    """BASELINE configs 2 / 4 / 5 through the whole encoder, sharded over the ranks (encjob.py).  Timed region: every rank's
+    x264_pcamv process over its shards + the NCCL gather of per-shard payload bits, statistics and digests; max over ranks."""
+    import torch
+    from pcamv_b200 import encjob, shard
+    job = encjob.JOBS[name]
+    ref = None
+    if rank == 0:
+        encjob.make_clip(pcamv, name)
+        ref = encjob.reference_side(pcamv, name)         # cached per box (the reference arm of bench.py fills the same cache)
+    barrier()
+    t0 = time.perf_counter()
+    secs, recs, _ = encjob.run_rank(name, rank, world, local_rank)
+    t_enc = time.perf_counter() - t0
+    gathered = shard.gather_gop_results(recs)
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    barrier()
+    t_max, t_enc_max = shard.max_over_ranks([t_all, t_enc])
+    if rank != 0:
+        return None
+    n = job["shards"]
+    ok_bits = len(gathered) == n and all(g["md5"] == ref["md5"][g["gop"]] for g in gathered)
+    ok_pay = None
+    if ref.get("payload_md5"):
+        ok_pay = len(gathered) == n and all(g["payload_md5"] == ref["payload_md5"][g["gop"]] and g["n_bits"] == ref["payload_bits"][g["gop"]] for g in gathered)
+    frames = n * job["shard_frames"]
+    return {"job": name, "what": job["what"], "args": " ".join(encjob.job_args(job)), "frames": frames, "shards": n, "ranks": world,
+            "encode_embed_fps": frames / t_max, "seconds": t_max, "seconds_encode_only": t_enc_max, "seconds_gather": t_max - t_enc_max,
+            "bitstream_identical": bool(ok_bits), "payload_identical": ok_pay,
+            "payload_bits": int(sum(g["n_bits"] for g in gathered)), "bytes": int(sum(g["bytes"] for g in gathered)),
+            "reference_fps": ref["fps"], "reference_cores": ref["cores"], "reference_seconds": ref["seconds"],
+            "scaling": "strong (the job is fixed, shards are dealt round-robin to the ranks)",
+            "gather": "shard.gather_gop_results (NCCL all_gather x3) of payload bits + statistics + digests, inside the timed region" if world > 1
+                      else "single rank: no collective",
+            "note": "wall clock of the slowest rank's x264_pcamv process (process start, CUDA context creation and encoder open included) plus the "
+                    "gather; reference = oracle/_ref/x264_wide (the reference's C sources, no asm), one single-threaded process per shard on the host cores"}
 
 
 if __name__ == "__main__":

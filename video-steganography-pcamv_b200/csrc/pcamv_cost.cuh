@@ -127,11 +127,31 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
 PCAMV_DEV int cand_dx(int ii) { return (int)(((long long)(0xEF1221FEF010ull << (60 - 4 * ii))) >> 60); }
 PCAMV_DEV int cand_dy(int ii) { return (int)(((long long)(0xFEEF1221010Full << (60 - 4 * ii))) >> 60); }
 
-// x264_ih_get_mv_cost for partition k of macroblock `res`; returns cost_opt, writes the chosen delta
-PCAMV_FN int ih_get_mv_cost(MbCtx &c, const MbResult &res, int k, int &m_x, int &m_y)
+// ---- x264_ih_get_mv_cost (analyse.c:2391-2550), in two parts so that the candidates can be costed by different teams ----
+// (1) one vector: reconstruct the macroblock with it, cost its 9-point ring against the reconstruction
+struct IhCand { int centre, min9, r[4]; };        // r[] = the four distance-1 ring costs (used for the original vector only)
+
+// ii = -1: the original vector of partition k; ii = 0..11: replacement candidate ii.  c.w.blk must describe partition k with
+// its source-pixel pointers aimed at c.w.pred_* (ih_setup_block).
+PCAMV_FN void ih_eval(MbCtx &c, const MbResult &res, int k, int ii, int kind, int bmx, int bmy, IhCand &o)
+{
+    MeBlock &b = c.w.blk;
+    const int cx = bmx + (ii < 0 ? 0 : cand_dx(ii)), cy = bmy + (ii < 0 ? 0 : cand_dy(ii));
+    encode_mb_inter(c, res, ii < 0 ? -1 : k, cx, cy);
+    // 9-point ring around (cx, cy) against the reconstruction: up, right, down, left, then the diagonals, then the centre
+    int r[4];
+    eval4(b, kind, 4, pk(cx, cy - 1), pk(cx + 1, cy), pk(cx, cy + 1), pk(cx - 1, cy), r);
+    int min9 = imin(imin(r[0], r[1]), imin(r[2], r[3]));
+    o.r[0] = r[0]; o.r[1] = r[1]; o.r[2] = r[2]; o.r[3] = r[3];
+    eval4(b, kind, 4, pk(cx - 1, cy - 1), pk(cx - 1, cy + 1), pk(cx + 1, cy - 1), pk(cx + 1, cy + 1), r);
+    min9 = imin(min9, imin(imin(r[0], r[1]), imin(r[2], r[3])));
+    o.centre = eval1(b, kind, pk(cx, cy));
+    o.min9 = imin(min9, o.centre);
+}
+
+PCAMV_DEV int ih_setup_block(MbCtx &c, const MbResult &res, int k)
 {
     const PartInfo &pi = mb_part(c, res, k);
-    const int bmx = pi.mv[0], bmy = pi.mv[1];
     MeBlock &b = c.w.blk;
     setup_block(c, b, pi.ref, pi.i_pixel, pi.xoff, pi.yoff);
     block_set_mvp(b, c.env, pi.mvp[0], pi.mvp[1]);
@@ -139,56 +159,64 @@ PCAMV_FN int ih_get_mv_cost(MbCtx &c, const MbResult &res, int k, int &m_x, int 
     b.fenc = c.w.pred_y + pi.yoff * 16 + pi.xoff;
     b.fenc_u = c.w.pred_u + (pi.yoff >> 1) * 8 + (pi.xoff >> 1);
     b.fenc_v = c.w.pred_v + (pi.yoff >> 1) * 8 + (pi.xoff >> 1);
-    const int kind = !c.env.mbcmp_satd ? COST_SAD : (c.env.chroma_me && pi.i_pixel <= PIX_8x8) ? COST_SATD_CHROMA : COST_SATD;
+    return !c.env.mbcmp_satd ? COST_SAD : (c.env.chroma_me && pi.i_pixel <= PIX_8x8) ? COST_SATD_CHROMA : COST_SATD;
+}
 
-    int orig = 0, non_opt = 0, fb_cost = PCAMV_COST_MAX, fb_idx = -1;
-    int best = PCAMV_COST_MAX, ii_best = -1;
-    m_x = 0; m_y = 0;
-    // ii = -1: the original vector; ii = 0..11: the replacement candidates (the first four decide whether the rest run)
-#pragma unroll 1
-    for (int ii = -1; ii < 12; ii++)
-    {
-        const int cx = bmx + (ii < 0 ? 0 : cand_dx(ii)), cy = bmy + (ii < 0 ? 0 : cand_dy(ii));
-        encode_mb_inter(c, res, ii < 0 ? -1 : k, cx, cy);
-        // 9-point ring around (cx, cy) against the reconstruction: up, right, down, left, then the diagonals, then the centre
-        int r[4];
-        eval4(b, kind, 4, pk(cx, cy - 1), pk(cx + 1, cy), pk(cx, cy + 1), pk(cx - 1, cy), r);
-        int min9 = imin(imin(r[0], r[1]), imin(r[2], r[3]));
-        if (ii < 0)
-        {
+// (2) the selection, folded over the candidates in the reference's order
+struct IhFold { int orig, non_opt, fb_cost, fb_idx, best, ii_best, m_x, m_y; };
+PCAMV_DEV void ih_fold_orig(IhFold &f, const IhCand &o)
+{
+    f.fb_cost = PCAMV_COST_MAX; f.fb_idx = -1; f.best = PCAMV_COST_MAX; f.ii_best = -1; f.m_x = 0; f.m_y = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (r[i] < fb_cost) { fb_cost = r[i]; fb_idx = i; }
-        }
-        eval4(b, kind, 4, pk(cx - 1, cy - 1), pk(cx - 1, cy + 1), pk(cx + 1, cy - 1), pk(cx + 1, cy + 1), r);
-        min9 = imin(min9, imin(imin(r[0], r[1]), imin(r[2], r[3])));
-        const int centre = eval1(b, kind, pk(cx, cy));
-        min9 = imin(min9, centre);
-        if (ii < 0)
-        {
-            orig = centre;
-            non_opt = min9 < orig;          // the original vector is not a local optimum of its ring
-            continue;
-        }
-        const int qualifies = non_opt ? (min9 != centre) : (min9 == centre);
-        if (qualifies && centre < best) { best = centre; m_x = cand_dx(ii); m_y = cand_dy(ii); ii_best = ii; }
-        if (ii == 3 && best != PCAMV_COST_MAX)
-            break;
-    }
+    for (int i = 0; i < 4; i++)
+        if (o.r[i] < f.fb_cost) { f.fb_cost = o.r[i]; f.fb_idx = i; }
+    f.orig = o.centre;
+    f.non_opt = o.min9 < f.orig;          // the original vector is not a local optimum of its ring
+}
+// returns 1 when the reference stops looking at further candidates (after the first four, if one of them qualified)
+PCAMV_DEV int ih_fold_cand(IhFold &f, int ii, const IhCand &o)
+{
+    const int qualifies = f.non_opt ? (o.min9 != o.centre) : (o.min9 == o.centre);
+    if (qualifies && o.centre < f.best) { f.best = o.centre; f.m_x = cand_dx(ii); f.m_y = cand_dy(ii); f.ii_best = ii; }
+    return ii == 3 && f.best != PCAMV_COST_MAX;
+}
+PCAMV_DEV int ih_fold_finish(IhFold &f)
+{
     int b_1_neighbor, b_error_pos = 0;
-    if (best == PCAMV_COST_MAX)
+    if (f.best == PCAMV_COST_MAX)
     {
         b_error_pos = 1; b_1_neighbor = 1;
-        m_x = 0; m_y = 0;
-        if (fb_idx >= 0) { best = fb_cost; m_x = cand_dx(fb_idx); m_y = cand_dy(fb_idx); }
+        f.m_x = 0; f.m_y = 0;
+        if (f.fb_idx >= 0) { f.best = f.fb_cost; f.m_x = cand_dx(f.fb_idx); f.m_y = cand_dy(f.fb_idx); }
     }
     else
-        b_1_neighbor = ii_best <= 3;
-    int cost_opt = best > orig ? best - orig : 1;
+        b_1_neighbor = f.ii_best <= 3;
+    int cost_opt = f.best > f.orig ? f.best - f.orig : 1;
     if (!b_1_neighbor)
         cost_opt = (int)(1.4f * (float)cost_opt);
     else if (b_error_pos)
         cost_opt = (int)(4.0f * (float)cost_opt);
+    return cost_opt;
+}
+
+// x264_ih_get_mv_cost for partition k of macroblock `res` by ONE team; returns cost_opt, writes the chosen delta
+PCAMV_FN int ih_get_mv_cost(MbCtx &c, const MbResult &res, int k, int &m_x, int &m_y)
+{
+    const PartInfo &pi = mb_part(c, res, k);
+    const int bmx = pi.mv[0], bmy = pi.mv[1];
+    const int kind = ih_setup_block(c, res, k);
+    IhFold f;
+    IhCand o;
+    // ii = -1: the original vector; ii = 0..11: the replacement candidates (the first four decide whether the rest run)
+#pragma unroll 1
+    for (int ii = -1; ii < 12; ii++)
+    {
+        ih_eval(c, res, k, ii, kind, bmx, bmy, o);
+        if (ii < 0) ih_fold_orig(f, o);
+        else if (ih_fold_cand(f, ii, o)) break;
+    }
+    const int cost_opt = ih_fold_finish(f);
+    m_x = f.m_x; m_y = f.m_y;
     return cost_opt;
 }
 

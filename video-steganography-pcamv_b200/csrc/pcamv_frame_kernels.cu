@@ -332,55 +332,100 @@ void launch_analyse_p_batch(const BatchItem *items, int n_items, int *row_claim,
     else             PCAMV_DISPATCH_F(f, (k_analyse_p_batch<1, F_><<<ctas, 32, 0, st>>>(items, n_items, row_claim)));
 }
 
-// ---- cost table: one lane team per macroblock; macroblocks are independent -------------------------------
-#define CT_WARPS 4
-
-__device__ __forceinline__ void cost_table_team(const DevFrameCtx &fc, const FrameParams &fp, int mb, int n_mb)
+// ---- cost table: macroblocks are independent; one CTA of CTP_TEAMS teams per macroblock, one candidate vector per team ----
+// x264_ih_get_mv_cost always costs the original vector and the first four replacement candidates, and the other eight only
+// when none of those four qualified (analyse.c:2443-2449); each needs its own whole-macroblock reconstruction and 9-point
+// ring, independent of the others — the "stop after four" rule is a selection made afterwards.  So team w of the CTA takes
+// vector w - 1 of the round (the original, then candidates 0..3; second and third round: candidates 4..7 and 8..11 on teams
+// 0..3) and the fold runs over the teams' results in the reference's order.  Besides cutting the latency of a vector five
+// ways, the teams of a CTA walk the same code at the same time, which is what the instruction caches reward: the
+// one-team-per-macroblock kernel of round 1 kept ~60 KB of code hot under 24 unrelated teams per SM and stalled on instruction
+// fetch (profiles/r02_cost_table_base_ncu_summary.txt: no_instruction 4.6 warp-cycles per issue, the largest stall).  Measured
+// gain of this layout at 128 frames: 57.9 -> 56.1 ms (profiles/r02_cost_table_ab.txt) — the fetch stalls are per team, not
+// per distinct code stream, so most of the win is the latency of one vector.
+#define CTP_TEAMS 5
+#ifndef PCAMV_CTP_MIN_CTAS
+#define PCAMV_CTP_MIN_CTAS 6
+#endif
+__device__ __forceinline__ void cost_table_cta(const DevFrameCtx &fc, const FrameParams &fp, int mb)
 {
-    __shared__ MbWork s_work[CT_WARPS];
-    __shared__ MbResult s_res[CT_WARPS];
-    __shared__ __align__(16) unsigned char s_ctx[CT_WARPS][sizeof(MbCtx)];
+    __shared__ MbWork s_work[CTP_TEAMS];
+    __shared__ MbResult s_res;
+    __shared__ IhCand s_cand[CTP_TEAMS];
+    __shared__ __align__(16) unsigned char s_ctx[CTP_TEAMS][sizeof(MbCtx)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (mb >= n_mb)
-        return;
-    MbWork &work = s_work[warp];
-    MbResult &res = s_res[warp];
     {
         const uint32_t *src = (const uint32_t *)(fp.results + mb);
-        uint32_t *dst = (uint32_t *)&res;
-        for (int i = lane; i < (int)(sizeof(MbResult) / 4); i += 32) dst[i] = src[i];
-        __syncwarp();
+        uint32_t *dst = (uint32_t *)&s_res;
+        for (int i = threadIdx.x; i < (int)(sizeof(MbResult) / 4); i += blockDim.x) dst[i] = src[i];
     }
+    __syncthreads();
+    const MbResult &res = s_res;
     if (res.type == MB_P_SKIP)
         return;
+    MbWork &work = s_work[warp];
     MbCtx &c = *new (s_ctx[warp]) MbCtx(fc, fp, work);
     c.mb_x = mb % fc.mb_w; c.mb_y = mb / fc.mb_w; c.mb_xy = mb;
     c.partition = res.partition;
     stage_fenc(fc, c.mb_x, c.mb_y, work);
-    cost_table_mb(c, res);
+    c.n_log = res.n_log;
+    init_limits(c);
+    c.env.cost_mv = fc.tab.cost_mv;
+    c.env.me_method = fc.me_method; c.env.me_range = fc.me_range; c.env.subme = fc.subme;
+    c.env.chroma_me = fc.chroma_me && fc.subme >= 5;
+    c.env.mbcmp_satd = fc.subme > 1;
+    c.env.mvsads = nullptr;
+    const int n_part = res.n_part;
+    for (int k = 0; k < n_part; k++)
+    {
+        const PartInfo &pi = mb_part(c, res, k);
+        const int bmx = pi.mv[0], bmy = pi.mv[1];
+        const int kind = ih_setup_block(c, res, k);
+        IhFold f;
+        int stop = 0;
+        // round 0: original + candidates 0..3; rounds 1, 2: candidates 4..7, 8..11 (team 4 has nothing to do there)
+        for (int round = 0; round < 3 && !stop; round++)
+        {
+            const int ii = round == 0 ? warp - 1 : 4 * round + warp;
+            if (round == 0 || warp < 4)
+            {
+                IhCand o;
+                ih_eval(c, res, k, ii, kind, bmx, bmy, o);
+                if (lane == 0) s_cand[warp] = o;
+            }
+            __syncthreads();
+            if (round == 0)
+            {
+                ih_fold_orig(f, s_cand[0]);
+                for (int j = 0; j < 4 && !stop; j++) stop = ih_fold_cand(f, j, s_cand[1 + j]);
+            }
+            else
+                for (int j = 0; j < 4 && !stop; j++) stop = ih_fold_cand(f, 4 * round + j, s_cand[j]);
+            __syncthreads();                       // everybody has read the results before the next round overwrites them
+        }
+        const int cost_opt = ih_fold_finish(f);
+        if (warp == 0)
+            log_push(c, LOG_IHCOST, pi.i_pixel, pi.ref, f.m_x, f.m_y, cost_opt, 0);
+    }
+    if (threadIdx.x == 0)
+        fp.results[mb].n_log = res.n_log + n_part;
 }
 
-__global__ void __launch_bounds__(CT_WARPS * 32) k_cost_table(const __grid_constant__ DevFrameCtx fc,
-                                                             const __grid_constant__ FrameParams fp, int n_mb)
+__global__ void __launch_bounds__(CTP_TEAMS * 32, PCAMV_CTP_MIN_CTAS) k_cost_table_cta(const __grid_constant__ DevFrameCtx fc,
+                                                                                    const __grid_constant__ FrameParams fp)
 {
-    cost_table_team(fc, fp, blockIdx.x * CT_WARPS + (threadIdx.x >> 5), n_mb);
+    cost_table_cta(fc, fp, blockIdx.x);
 }
-
 // blockIdx.y = frame of the batch
-// independent macroblocks, nothing to wait for: more resident teams hide more latency (6 CTAs per SM = 80 registers per
-// thread: 60 ms per 128 frames against 66 ms at the unconstrained 96 registers; 8 CTAs = 64 registers: 59 ms)
-#ifndef PCAMV_CT_MIN_CTAS
-#define PCAMV_CT_MIN_CTAS 6
-#endif
-__global__ void __launch_bounds__(CT_WARPS * 32, PCAMV_CT_MIN_CTAS) k_cost_table_batch(const BatchItem *__restrict__ items, int n_mb)
+__global__ void __launch_bounds__(CTP_TEAMS * 32, PCAMV_CTP_MIN_CTAS) k_cost_table_cta_batch(const BatchItem *__restrict__ items)
 {
     const BatchItem &it = items[blockIdx.y];
-    cost_table_team(it.fc, it.fp, blockIdx.x * CT_WARPS + (threadIdx.x >> 5), n_mb);
+    cost_table_cta(it.fc, it.fp, blockIdx.x);
 }
 
 void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, void *stream)
 {
-    k_cost_table<<<(n_mb + CT_WARPS - 1) / CT_WARPS, CT_WARPS * 32, 0, (cudaStream_t)stream>>>(fc, fp, n_mb);
+    k_cost_table_cta<<<n_mb, CTP_TEAMS * 32, 0, (cudaStream_t)stream>>>(fc, fp);
 }
 
 } // namespace pcamv
@@ -388,7 +433,6 @@ void launch_cost_table(const DevFrameCtx &fc, const FrameParams &fp, int n_mb, v
 namespace pcamv {
 void launch_cost_table_batch(const BatchItem *items, int n_items, int n_mb, void *stream)
 {
-    dim3 grid((n_mb + CT_WARPS - 1) / CT_WARPS, n_items);
-    k_cost_table_batch<<<grid, CT_WARPS * 32, 0, (cudaStream_t)stream>>>(items, n_mb);
+    k_cost_table_cta_batch<<<dim3(n_mb, n_items), CTP_TEAMS * 32, 0, (cudaStream_t)stream>>>(items);
 }
 }

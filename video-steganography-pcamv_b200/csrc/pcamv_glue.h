@@ -28,24 +28,29 @@ struct ForcedOut             // == ForcedMb of pcamv_frame.cuh
     uint32_t mv[16];
 };
 
-static inline uint32_t glue_pack(const int16_t v[2]) { return ((uint32_t)(uint16_t)v[0]) | ((uint32_t)(uint16_t)v[1] << 16); }
+#if defined(__CUDACC__)
+  #define PCAMV_HD __host__ __device__
+#else
+  #define PCAMV_HD
+#endif
 
-// Fills out[0..n_mb) and returns the number of filp[] entries consumed (== number of carrier MVs).
-static inline int build_forced(int n_mb, const Pass1Mb *in, const int8_t *filp, ForcedOut *out)
+PCAMV_HD static inline uint32_t glue_pack(const int16_t v[2]) { return ((uint32_t)(uint16_t)v[0]) | ((uint32_t)(uint16_t)v[1] << 16); }
+// block_idx -> (x,y) of the 4x4 block
+PCAMV_HD static inline int glue_bx(int idx) { return (idx & 1) | ((idx >> 1) & 2); }
+PCAMV_HD static inline int glue_by(int idx) { return ((idx >> 1) & 1) | ((idx >> 2) & 2); }
+
+// One macroblock: fills `o` from the pass-1 record and the flips of ITS carriers (filp = first of them, in cover order);
+// returns how many it consumed.  Runs on the host (build_forced) and on the device (k_embed_forced, pcamv_embed.cu).
+PCAMV_HD static inline int build_forced_mb(const Pass1Mb &p, const int8_t *filp, ForcedOut &o)
 {
     int n = 0;
-    for (int mb = 0; mb < n_mb; mb++)
     {
-        const Pass1Mb &p = in[mb];
-        ForcedOut &o = out[mb];
+        {
         o.type = (int8_t)p.type; o.used = (int8_t)p.used; o.partition = (int8_t)p.partition; o.pad = 0;
         for (int i = 0; i < 4; i++) o.ref[i] = 0;
         for (int i = 0; i < 16; i++) o.mv[i] = 0;
         if (!p.used)
-            continue;
-        // block_idx -> (x,y) of the 4x4 block
-        auto bx = [](int idx) { return (idx & 1) | ((idx >> 1) & 2); };
-        auto by = [](int idx) { return ((idx >> 1) & 1) | ((idx >> 2) & 2); };
+            return 0;
         if (p.type == 4)
         {
             if (p.partition == 16)
@@ -60,7 +65,7 @@ static inline int build_forced(int n_mb, const Pass1Mb *in, const int8_t *filp, 
                 {
                     const int16_t *mv = filp[n++] == 1 ? p.mv_stego[8 * j] : p.mv[8 * j];
                     o.ref[2 * j] = o.ref[2 * j + 1] = p.ref[8 * j];
-                    for (int i = 0; i < 16; i++) if ((by(i) >> 1) == j) o.mv[i] = glue_pack(mv);
+                    for (int i = 0; i < 16; i++) if ((glue_by(i) >> 1) == j) o.mv[i] = glue_pack(mv);
                 }
             }
             else                                 // 8x16: slots 0 and 4 (analyse.c:2923-2928, 3069-3077)
@@ -69,7 +74,7 @@ static inline int build_forced(int n_mb, const Pass1Mb *in, const int8_t *filp, 
                 {
                     const int16_t *mv = filp[n++] == 1 ? p.mv_stego[4 * j] : p.mv[4 * j];
                     o.ref[j] = o.ref[j + 2] = p.ref[4 * j];
-                    for (int i = 0; i < 16; i++) if ((bx(i) >> 1) == j) o.mv[i] = glue_pack(mv);
+                    for (int i = 0; i < 16; i++) if ((glue_bx(i) >> 1) == j) o.mv[i] = glue_pack(mv);
                 }
             }
         }
@@ -110,7 +115,17 @@ static inline int build_forced(int n_mb, const Pass1Mb *in, const int8_t *filp, 
                 }
             }
         }
+        }
     }
+    return n;
+}
+
+// Fills out[0..n_mb) and returns the number of filp[] entries consumed (== number of carrier MVs).
+static inline int build_forced(int n_mb, const Pass1Mb *in, const int8_t *filp, ForcedOut *out)
+{
+    int n = 0;
+    for (int mb = 0; mb < n_mb; mb++)
+        n += build_forced_mb(in[mb], filp + n, out[mb]);
     return n;
 }
 

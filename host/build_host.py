@@ -57,7 +57,7 @@ static int pcamv_extract_main( int argc, char **argv )
     const char *in = argv[2], *out = NULL;
     FILE *fi, *fo;
     int32_t hd[3];
-    int i, frames = 0, bits = 0;
+    int i, frames = 0, bits = 0, skipped = 0;
     for( i = 3; i < argc - 1; i++ )
         if( !strcmp( argv[i], "-o" ) || !strcmp( argv[i], "--output" ) ) out = argv[i + 1];
     if( !out ) { fprintf( stderr, "x264 [error]: --extract needs -o\n" ); return -1; }
@@ -69,14 +69,19 @@ static int pcamv_extract_main( int argc, char **argv )
         uint8_t *stego = malloc( length > 0 ? length : 1 ), *msg = malloc( an + 1 );
         int32_t oh[2] = { hd[0], an };
         if( length < 0 || (int)fread( stego, 1, length, fi ) != length ) { fprintf( stderr, "x264 [error]: truncated stego file\n" ); return -1; }
-        if( an > 0 && pcamv_stc_extract( stego, length, msg, an, 10 ) < 0 ) { fprintf( stderr, "x264 [error]: frame %d: cannot extract %d bits from %d\n", hd[0], an, length ); return -1; }
+        if( an > 0 && pcamv_stc_extract( stego, length, msg, an, 10 ) < 0 )
+        {
+            /* a frame that cannot carry what its header claims: pass it by (an = 0) instead of giving up on the whole stream */
+            fprintf( stderr, "x264 [warning]: frame %d: cannot extract %d bits from %d carriers, skipped\n", hd[0], an, length );
+            oh[1] = 0; skipped++;
+        }
         fwrite( oh, 4, 2, fo );
-        fwrite( msg, 1, an, fo );
+        fwrite( msg, 1, oh[1], fo );
         free( stego ); free( msg );
-        frames++; bits += an;
+        frames++; bits += oh[1];
     }
     fclose( fi ); fclose( fo );
-    fprintf( stderr, "x264 [info]: extracted %d payload bits from %d frames\n", bits, frames );
+    fprintf( stderr, "x264 [info]: extracted %d payload bits from %d frames (%d skipped)\n", bits, frames, skipped );
     return 0;
 }
 static void *pcamv_shard_thread( void *p )

@@ -46,6 +46,7 @@ typedef struct
     int cur_mb, cur_pos;            /* replay cursor */
     int qp_loaded;
     int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
+    int device_forced;              /* the embed stage of this frame ran on the device: pass 2 takes its forced decisions from HBM */
     int fenc_frame;                 /* h->fenc->i_frame currently on the GPU */
     /* reference slots: which frame each GPU slot holds */
     struct { x264_frame_t *fr; int i_frame, i_poc, age; } slot[PCAMV_MAX_REFS + 2];
@@ -90,6 +91,12 @@ void pcamv_glue_set_shards( int n )
 
 /* this encoder thread's context (the embed-stage hook in the encoder.c translation unit needs it) */
 pcamv_ctx *pcamv_glue_ctx( void ) { return g.ctx; }
+void pcamv_glue_set_device_forced( int on ) { g.device_forced = on; }
+/* did the trellis of the frame being encoded actually embed its message?  (no: fewer carriers than the message needs, or
+ * "not in the range of the syndrome matrix" - the reference carries on with stego = 0 and flips every carrier whose cover
+ * bit is 1, encoder/encoder.c:1826,1843-1855; nothing can be extracted from such a frame) */
+static __thread int g_embedded;
+void pcamv_glue_set_embed_status( int embedded ) { g_embedded = embedded; }
 
 /* called first thing by a shard's thread: i = its index in this process (decides the group), gop = the GOP it encodes
  * (names its side files).  Group membership starts HERE, not at x264_encoder_open: a shard whose Encode() fails before it
@@ -328,7 +335,11 @@ void pcamv_hook_slice_begin( x264_t *h )
         in.col_mv4 = (const int16_t *)l0->mv[0];
     }
     in.cost_table = pass == 1;
-    if( pass == 2 )
+    if( pass == 1 )
+        g.device_forced = 0;
+    if( pass == 2 && g.device_forced )
+        in.device_forced = 1;       /* cover, flips and forced decisions of this frame are already in HBM (pcamv_glue_stc_embed) */
+    else if( pass == 2 )
     {
         n = 0;
         for( i = 0; i < g.n_mb; i++ )
@@ -483,14 +494,15 @@ void pcamv_hook_embed( x264_t *h, int an )
             fclose( f );
         }
     }
-    /* PCAMV_STEGO=<file>: the extractor's input (x264_pcamv --extract) — frame, length, an and the stego LSBs only */
+    /* PCAMV_STEGO=<file>: the extractor's input (x264_pcamv --extract) — frame, length, an and the stego LSBs only; a frame whose
+     * embedding failed is recorded with an = 0 ("carries nothing"), so that the extractor passes it by */
     s = getenv( "PCAMV_STEGO" );
     if( s && *s )
     {
         FILE *f = open_side_file( s );
         if( f )
         {
-            int32_t hd[3] = { h->i_frame, h->info.length, an };
+            int32_t hd[3] = { h->i_frame, h->info.length, g_embedded ? an : 0 };
             fwrite( hd, 4, 3, f );
             fwrite( h->info.stego, 1, h->info.length, f );
             fclose( f );

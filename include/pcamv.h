@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PCAMV_ABI_VERSION 5
+#define PCAMV_ABI_VERSION 6
 #define PCAMV_MAX_REFS 16
 #define PCAMV_MAX_MVC 10
 
@@ -226,6 +226,8 @@ typedef struct pcamv_frame_in
     int32_t n_filp;
     int32_t cost_table;                 /* pass 1: also build the candidate-MV cost table (emrate != 0) */
     int16_t stale_mv[16][2];            /* h->mb.cache.mv[0][x264_scan8[i]] as left by the previous slice pass */
+    int32_t device_forced;              /* pass 2: the forced decisions are already in HBM (pcamv_embed_stc built them from this
+                                         * context's pass 1): pass1 / filp / n_filp are ignored */
 } pcamv_frame_in;
 
 /* Switch pcamv_cfg.pass2_elide of an open context (takes effect with the next launch). */
@@ -288,6 +290,23 @@ int pcamv_int_peak(pcamv_ctx *ctx, double *gops);
 int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, const uint8_t *message, int an, const float *rho,
                     uint8_t *stego, int matrixheight, const uint32_t *cols_short, int w_short,
                     const uint32_t *cols_long, int w_long);
+
+/* ---- the embed stage between the two passes, device-resident (reference encoder/encoder.c:1561-1855) ----------------------
+ * After pcamv_analyse_p( pass 1, cost_table = 1 ) the frame's records and cost table are in HBM.  pcamv_embed_prepare builds
+ * from them, on the device, what the reference's embed stage builds on the host: the h->info.cache[] entry of every macroblock
+ * (encoder/analyse.c:3526-3689, including the motion vectors as the unsequenced copy loops leave them), the cover bits
+ * LSB(mvx + mvy) and the float costs rho_final with the MVC penalties (x 2, x (0.7 n + 1)), in the reference's carrier order;
+ * *length = h->info.length.  The host then draws its message (an = (int)(rate * length) bits of rand() & 1,
+ * encoder/encoder.c:1828-1840) and calls pcamv_embed_stc: the syndrome-trellis code runs on the device-resident cover / rho
+ * (same contract and return value as pcamv_stc_embed; total = the reference's sum of rho_final in double, or < 0 to have it
+ * summed on the device), then filp = cover ^ stego and the decisions pass 2 forces (encoder/analyse.c:2870-3107) are built in
+ * HBM; an <= 0 or message == NULL embeds nothing (stego stays zero, as when the reference's stc_embed gives up).  stego (may be
+ * NULL) receives the length stego bits.  pcamv_analyse_p( pass 2 ) with in->device_forced = 1 then needs neither the pass-1
+ * records nor filp from the host.  pcamv_embed_download copies out whatever the host wants to see (any pointer may be NULL). */
+int pcamv_embed_prepare(pcamv_ctx *ctx, int *length);
+int pcamv_embed_stc(pcamv_ctx *ctx, const uint8_t *message, int an, int matrixheight, const uint32_t *cols_short, int w_short,
+                    const uint32_t *cols_long, int w_long, double total, uint8_t *stego);
+int pcamv_embed_download(pcamv_ctx *ctx, uint8_t *cover, float *rho, uint8_t *stego, int8_t *filp, pcamv_pass1_mb *pass1);
 
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 long long pcamv_launch_count(const pcamv_ctx *ctx);

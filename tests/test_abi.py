@@ -27,7 +27,7 @@ def test_host_mirror_lists_every_export(pcamv):
 
 
 def test_abi_version_and_record_layout(pcamv, cuda_lib):
-    assert cuda_lib.pcamv_abi_version() == 5
+    assert cuda_lib.pcamv_abi_version() == 6
     # sizes of the POD records as laid out by the C compiler (see include/pcamv.h)
     assert pcamv.host.ME_CALL_DTYPE.itemsize == 132
     assert pcamv.host.ME_RESULT_DTYPE.itemsize == 16

@@ -84,3 +84,13 @@ def test_extract_rejects_truncated_input(tmp_path):
         f.write(bytes(10))
     p = subprocess.run([HOST, "--extract", src, "-o", str(tmp_path / "o.bin")], capture_output=True)
     assert p.returncode != 0 and b"truncated" in p.stderr
+
+
+def test_extract_passes_unextractable_frames_by(tmp_path):
+    """A frame whose header claims more message bits than it has carriers (an embedding the encoder could not have made)
+    does not take the rest of the stream with it: it comes out with an = 0 and the following frames are extracted."""
+    good = (2, 40, 8, np.tile(np.array([1, 0, 0, 1, 0], dtype=np.uint8), 8))
+    got = extract([(1, 5, 9, np.ones(5, dtype=np.uint8)), good], str(tmp_path))
+    assert [(f, an) for f, an, _ in got] == [(1, 0), (2, 8)]
+    alone = extract([good], str(tmp_path))
+    assert np.array_equal(got[1][2], alone[0][2])

@@ -43,7 +43,12 @@ struct pcamv_ctx
     int batch_max_ctas = 0, batch_claim_cap = 0;   // persistent grid size of multi-context launches (0 = not yet computed)
     unsigned long long *d_mvsads = nullptr; int mvsads_cap = 0;    // --me tesa: per-row candidate lists
     unsigned long long *d_seam_mvsads = nullptr;                   // --me tesa, stateless search seam: PCAMV_SEAM_CHUNK lists
+    uint8_t *d_stc_io = nullptr; size_t stc_io_bytes = 0;        // pcamv_stc_embed's staging of host cover / rho / stego
     uint8_t *d_stc = nullptr; size_t stc_bytes = 0;               // embed stage (pcamv_stc_embed): cover | stego | rho | elems | path | total
+    // embed stage on the device (pcamv_embed.cu): one allocation carved into offsets | info.cache records | cover | stego | filp | rho | total
+    uint8_t *d_emb = nullptr; int *emb_offsets = nullptr; void *emb_pass1 = nullptr; uint8_t *emb_cover = nullptr, *emb_stego = nullptr;
+    int8_t *emb_filp = nullptr; float *emb_rho = nullptr; double *emb_total = nullptr;
+    int emb_length = 0, emb_state = 0;         // 0 = nothing, 1 = cover / rho built for the frame in HBM, 2 = flips + forced decisions built
     unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
     bool trace_on = false;
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter + [mb_h] row owners (row pool)

@@ -87,8 +87,10 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
             return ctx_fail(ctx, "pcamv_frame_upload: reference slot was never uploaded", cudaSuccess);
     if (in->col_n_ref > 0 && (!in->col_ref8 || !in->col_mv4))
         return ctx_fail(ctx, "pcamv_frame_upload: co-located ref/mv arrays missing", cudaSuccess);
-    if (in->pass == 2 && (!in->pass1 || (in->n_filp > 0 && !in->filp)))
+    if (in->pass == 2 && !in->device_forced && (!in->pass1 || (in->n_filp > 0 && !in->filp)))
         return ctx_fail(ctx, "pcamv_frame_upload: pass 2 needs the pass-1 records and filp[]", cudaSuccess);
+    if (in->pass == 2 && in->device_forced && ctx->emb_state < 2)
+        return ctx_fail(ctx, "pcamv_frame_upload: device_forced set, but pcamv_embed_stc has not built the forced decisions of this frame", cudaSuccess);
     if (ensure_frame_buffers(ctx)) return -1;
 
     const size_t n_mb = (size_t)fc.mb_w * fc.mb_h;
@@ -111,7 +113,9 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
         CK(cudaMemcpyAsync(ctx->d_col_mv4, h + 4 * n_mb, 64 * n_mb, cudaMemcpyHostToDevice, ctx->stream));
     }
     fp.col_ref8 = ctx->d_col_ref8; fp.col_mv4 = ctx->d_col_mv4;
-    if (in->pass == 2)
+    if (in->pass == 2 && in->device_forced)
+        fp.forced = ctx->d_forced;                   // built in HBM by pcamv_embed_stc
+    else if (in->pass == 2)
     {
         ForcedOut *fo = (ForcedOut *)(h + 68 * n_mb);
         // filp[] is consumed in cover order; build_forced walks the macroblocks in the same order
@@ -133,7 +137,7 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
     fp.mvsads = ctx->d_mvsads; fp.mvsads_cap = ctx->mvsads_cap;
     fp.subparts = ctx->d_subparts;
     fp.log = ctx->d_log; fp.log_stride = ctx->log_stride; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
-    if (in->pass == 1) ctx->frame_cost_table = in->cost_table != 0;
+    if (in->pass == 1) { ctx->frame_cost_table = in->cost_table != 0; ctx->emb_state = 0; }
     ctx->frame_last = in->pass;
     return 0;
 }

@@ -106,15 +106,15 @@ using namespace pcamv;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(ctx, #call, e_); } while (0)
 
-// returns 0 = embedded, 1 = the syndrome is not in the range of the matrix (the reference's stc_embed returns 0 and leaves
-// stego untouched), -1 = error (pcamv_last_error)
-extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, const uint8_t *message, int an, const float *rho,
-                               uint8_t *stego, int matrixheight, const uint32_t *cols_short, int w_short,
-                               const uint32_t *cols_long, int w_long)
+// The trellis on device-resident cover / rho (n elements); `message` (an bits) and the sub-matrix columns are host arrays;
+// `total` = sum of rho over the elements (what the reference compares the trellis result with, embed.h:496-505).
+// Writes the stego bits to d_stego (device, n bytes; elements the block schedule does not reach stay untouched).
+// Returns 0 = embedded, 1 = not embeddable (d_stego untouched), -1 = error.
+namespace pcamv {
+int stc_run_device(pcamv_ctx *ctx, const uint8_t *d_cover, const float *d_rho, int n, const uint8_t *message, int an, int matrixheight,
+                   const uint32_t *cols_short, int w_short, const uint32_t *cols_long, int w_long, double total, uint8_t *d_stego)
 {
-    if (!ctx || ctx->failed) return -1;
-    cudaSetDevice(ctx->cfg.device);
-    if (!cover || !message || !rho || !stego || !cols_short || !cols_long || n <= 0 || an <= 0 || an > n)
+    if (!message || !cols_short || !cols_long || n <= 0 || an <= 0 || an > n)
         return ctx_fail(ctx, "pcamv_stc_embed: bad argument", cudaSuccess);
     if (matrixheight < 7 || matrixheight > 10)
         return ctx_fail(ctx, "pcamv_stc_embed: matrix height must be 7..10 (the encoder uses 10)", cudaSuccess);
@@ -134,7 +134,6 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
     std::vector<StcElem> el((size_t)n);
     uint32_t colmask = (1u << matrixheight) - 1;
     int worm = 0, index = 0;
-    double total = 0;
     for (int b = 0; b < an; b++)
     {
         const bool wide = worm + longer <= (b + 1) * invalpha + 0.5;
@@ -152,17 +151,15 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
             el[index].last = k == width - 1;
             el[index].msg = message[b] ? 1 : 0;
             el[index].pad[0] = el[index].pad[1] = 0;
-            total += rho[index];
         }
         if (an - b <= matrixheight)
             colmask >>= 1;
     }
     const int used = index;           // the schedule's total width; elements past it (if any) are never touched, as in the reference
     const size_t words = (size_t)used * ((1u << matrixheight) / 32);
-    // one device block per context, grown on demand: path | elems | rho | total | cover | stego (16-byte aligned parts)
+    // one device block per context, grown on demand: path | elems | total
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t o_path = 0, o_el = up(words * sizeof(uint32_t)), o_rho = o_el + up(used * sizeof(StcElem)),
-                 o_total = o_rho + up(used * sizeof(float)), o_cover = o_total + 256, o_stego = o_cover + up(used), need = o_stego + up(used);
+    const size_t o_path = 0, o_el = up(words * sizeof(uint32_t)), o_total = o_el + up(used * sizeof(StcElem)), need = o_total + 256;
     if (ctx->stc_bytes < need)
     {
         cudaFree(ctx->d_stc); ctx->d_stc = nullptr; ctx->stc_bytes = 0;
@@ -170,12 +167,8 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
         ctx->stc_bytes = need + need / 4;
     }
     uint32_t *d_path = (uint32_t *)(ctx->d_stc + o_path); StcElem *d_el = (StcElem *)(ctx->d_stc + o_el);
-    float *d_rho = (float *)(ctx->d_stc + o_rho), *d_total = (float *)(ctx->d_stc + o_total);
-    uint8_t *d_cover = ctx->d_stc + o_cover, *d_stego = ctx->d_stc + o_stego;
-#define SK(call) CK(call)
-    SK(cudaMemcpyAsync(d_cover, cover, used, cudaMemcpyHostToDevice, ctx->stream));
-    SK(cudaMemcpyAsync(d_rho, rho, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    SK(cudaMemcpyAsync(d_el, el.data(), used * sizeof(StcElem), cudaMemcpyHostToDevice, ctx->stream));
+    float *d_total = (float *)(ctx->d_stc + o_total);
+    CK(cudaMemcpyAsync(d_el, el.data(), used * sizeof(StcElem), cudaMemcpyHostToDevice, ctx->stream));
     switch (matrixheight)
     {
     case 7:  k_stc_forward<7><<<1, 128, 0, ctx->stream>>>(d_cover, d_rho, d_el, used, d_path, d_total); break;
@@ -184,8 +177,8 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
     default: k_stc_forward<10><<<1, 1024, 0, ctx->stream>>>(d_cover, d_rho, d_el, used, d_path, d_total); break;
     }
     float total_price = 0;
-    SK(cudaMemcpyAsync(&total_price, d_total, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    SK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(&total_price, d_total, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));          // (also: `el` may go out of scope)
     ctx->launches += 1;
     if ((double)total_price >= total)
         return 1;               // "The syndrome is not in the range of the syndrome matrix." (embed.h:503-512)
@@ -196,10 +189,51 @@ extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, cons
     case 9:  k_stc_backward<9><<<1, 32, 0, ctx->stream>>>(d_el, used, d_path, d_stego); break;
     default: k_stc_backward<10><<<1, 32, 0, ctx->stream>>>(d_el, used, d_path, d_stego); break;
     }
-    SK(cudaMemcpyAsync(stego, d_stego, used, cudaMemcpyDeviceToHost, ctx->stream));
-    SK(cudaStreamSynchronize(ctx->stream));
-    SK(cudaGetLastError());
     ctx->launches += 1;
-#undef SK
+    CK(cudaGetLastError());
+    return 0;
+}
+} // namespace pcamv
+
+// returns 0 = embedded, 1 = the syndrome is not in the range of the matrix (the reference's stc_embed returns 0 and leaves
+// stego untouched), -1 = error (pcamv_last_error)
+extern "C" int pcamv_stc_embed(pcamv_ctx *ctx, const uint8_t *cover, int n, const uint8_t *message, int an, const float *rho,
+                               uint8_t *stego, int matrixheight, const uint32_t *cols_short, int w_short,
+                               const uint32_t *cols_long, int w_long)
+{
+    if (!ctx || ctx->failed) return -1;
+    cudaSetDevice(ctx->cfg.device);
+    if (!cover || !message || !rho || !stego || !cols_short || !cols_long || n <= 0 || an <= 0 || an > n)
+        return ctx_fail(ctx, "pcamv_stc_embed: bad argument", cudaSuccess);
+    // host-pointer entry: stage cover / rho in a block of their own, run, fetch the stego bits
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t need = 2 * up(n) + up((size_t)n * sizeof(float));
+    if (ctx->stc_io_bytes < need)
+    {
+        cudaFree(ctx->d_stc_io); ctx->d_stc_io = nullptr; ctx->stc_io_bytes = 0;
+        CK(cudaMalloc(&ctx->d_stc_io, need + need / 4));
+        ctx->stc_io_bytes = need + need / 4;
+    }
+    uint8_t *d_cover = ctx->d_stc_io, *d_stego = ctx->d_stc_io + up(n);
+    float *d_rho = (float *)(ctx->d_stc_io + 2 * up(n));
+    CK(cudaMemcpyAsync(d_cover, cover, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_rho, rho, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // the reference's total: rho of the elements the block schedule covers, summed in order in double (embed.h:405-470)
+    const double invalpha = (double)n / an;
+    const int shorter = (int)floor(invalpha), longer = (int)ceil(invalpha);
+    int worm = 0, used = 0;
+    for (int b = 0; b < an; b++)
+    {
+        const bool wide = worm + longer <= (b + 1) * invalpha + 0.5;
+        worm += wide ? longer : shorter;
+        used += wide ? longer : shorter;
+    }
+    if (used > n) used = n;
+    double total = 0;
+    for (int i = 0; i < used; i++) total += rho[i];
+    const int rc = stc_run_device(ctx, d_cover, d_rho, n, message, an, matrixheight, cols_short, w_short, cols_long, w_long, total, d_stego);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(stego, d_stego, used, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

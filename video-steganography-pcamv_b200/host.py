@@ -59,7 +59,7 @@ class FrameIn(C.Structure):
     _fields_ = [("pass_", C.c_int32), ("n_ref", C.c_int32), ("ref_slot", C.c_int32 * 16), ("ref_poc", C.c_int32 * 16),
                 ("cur_poc", C.c_int32), ("col_n_ref", C.c_int32), ("col_inv_ref_poc", C.c_int32 * 16),
                 ("col_ref8", C.c_void_p), ("col_mv4", C.c_void_p), ("pass1", C.c_void_p), ("filp", C.c_void_p),
-                ("n_filp", C.c_int32), ("cost_table", C.c_int32), ("stale_mv", (C.c_int16 * 2) * 16)]
+                ("n_filp", C.c_int32), ("cost_table", C.c_int32), ("stale_mv", (C.c_int16 * 2) * 16), ("device_forced", C.c_int32)]
 
 
 EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version", "pcamv_set_qp_tables",
@@ -68,7 +68,8 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
            "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
            "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide",
-           "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave", "pcamv_stc_embed"]
+           "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave", "pcamv_stc_embed",
+           "pcamv_embed_prepare", "pcamv_embed_stc", "pcamv_embed_download"]
 
 _lib = None
 
@@ -112,6 +113,9 @@ def load_library(path=None):
     lib.pcamv_group_analyse_p.argtypes = [vp, vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_group_analyse_p.restype = ip
     lib.pcamv_group_leave.argtypes = [vp]; lib.pcamv_group_leave.restype = ip
     lib.pcamv_stc_embed.argtypes = [vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp, ip]; lib.pcamv_stc_embed.restype = ip
+    lib.pcamv_embed_prepare.argtypes = [vp, C.POINTER(C.c_int)]; lib.pcamv_embed_prepare.restype = ip
+    lib.pcamv_embed_stc.argtypes = [vp, vp, ip, ip, vp, ip, vp, ip, C.c_double, vp]; lib.pcamv_embed_stc.restype = ip
+    lib.pcamv_embed_download.argtypes = [vp, vp, vp, vp, vp, vp]; lib.pcamv_embed_download.restype = ip
     lib.pcamv_host_alloc.argtypes = [C.c_size_t]; lib.pcamv_host_alloc.restype = vp
     lib.pcamv_host_free.argtypes = [vp]; lib.pcamv_host_free.restype = None
     lib.pcamv_analyse_p_batch.argtypes = [C.POINTER(vp), C.POINTER(C.POINTER(FrameIn)), ip, C.POINTER(vp), C.POINTER(vp)]
@@ -251,6 +255,39 @@ class PcamvContext:
             self._check(rc)
         return stego if rc == 0 else None
 
+    # -- embed stage on the device -----------------------------------------------------------------
+    def embed_prepare(self):
+        """pcamv_embed_prepare: cover / rho assembly from the pass-1 results in HBM; returns the cover length."""
+        n = C.c_int()
+        self._check(self.lib.pcamv_embed_prepare(self.handle, C.byref(n)))
+        self._emb_len = int(n.value)
+        return self._emb_len
+
+    def embed_stc(self, message, cols_short, cols_long, height=10, total=-1.0):
+        """pcamv_embed_stc on the device-resident cover / rho; returns (rc, stego) with rc 0 = embedded, 1 = not embeddable."""
+        stego = np.zeros(max(self._emb_len, 1), dtype=np.uint8)
+        if message is None or len(message) == 0:
+            rc = self.lib.pcamv_embed_stc(self.handle, None, 0, height, None, 0, None, 0, C.c_double(total), _ptr(stego))
+        else:
+            message = np.ascontiguousarray(message, dtype=np.uint8)
+            cs = np.ascontiguousarray(cols_short, dtype=np.uint32); cl = np.ascontiguousarray(cols_long, dtype=np.uint32)
+            rc = self.lib.pcamv_embed_stc(self.handle, _ptr(message), len(message), height, _ptr(cs), len(cs), _ptr(cl), len(cl),
+                                          C.c_double(total), _ptr(stego))
+        if rc < 0:
+            self._check(rc)
+        return rc, stego[:self._emb_len]
+
+    def embed_download(self, want_stego=True):
+        """cover, rho, stego, filp (length entries each) and the per-macroblock info.cache[] records."""
+        n = max(self._emb_len, 1)
+        n_mb = (self.width // 16) * (self.height // 16)
+        cover = np.zeros(n, np.uint8); rho = np.zeros(n, np.float32); stego = np.zeros(n, np.uint8); filp = np.zeros(n, np.int8)
+        p1 = np.zeros(n_mb, dtype=PASS1_MB_DTYPE)
+        self._check(self.lib.pcamv_embed_download(self.handle, _ptr(cover), _ptr(rho), _ptr(stego) if want_stego else None,
+                                                  _ptr(filp) if want_stego else None, _ptr(p1)))
+        k = self._emb_len
+        return cover[:k], rho[:k], stego[:k], filp[:k], p1
+
     def get_integral(self, slot):
         """The integral plane of a slot (--me esa / tesa contexts): uint16 [rows, stride_y]."""
         out = np.empty(self.plane_bytes(6), dtype=np.uint8)
@@ -281,7 +318,7 @@ class PcamvContext:
 
     # -- frame seam --------------------------------------------------------------------------------
     def _frame_in(self, pass_, ref_slots, ref_pocs, cur_poc, col_n_ref=0, col_inv_ref_poc=None, col_ref8=None,
-                  col_mv4=None, pass1=None, filp=None, cost_table=True, stale_mv=None):
+                  col_mv4=None, pass1=None, filp=None, cost_table=True, stale_mv=None, device_forced=False):
         fi = FrameIn()
         keep = []
         fi.pass_, fi.n_ref, fi.cur_poc, fi.col_n_ref = pass_, len(ref_slots), cur_poc, col_n_ref
@@ -301,6 +338,7 @@ class PcamvContext:
             keep += [a, f]
             fi.pass1, fi.filp, fi.n_filp = a.ctypes.data, f.ctypes.data, len(f)
         fi.cost_table = int(bool(cost_table))
+        fi.device_forced = int(bool(device_forced))
         if stale_mv is not None:
             for i in range(16):
                 fi.stale_mv[i][0], fi.stale_mv[i][1] = int(stale_mv[i][0]), int(stale_mv[i][1])

@@ -42,7 +42,7 @@ JOBS = {
     # BASELINE config 5: 64 independent 720p streams, embed + extract round trip
     "config5": dict(width=1280, height=720, shards=64, shard_frames=30, synth=5, args=ENC, streams=True, what="64 streams of 1280x720 x 30 frames"),
     # bounded jobs for the default bench run (same shapes, fewer frames)
-    "config4-small": dict(width=3840, height=2160, shards=8, shard_frames=6, synth=4, args=ENC, what="3840x2160 x 48 frames, 8 GOPs of 6"),
+    "config4-small": dict(width=3840, height=2160, shards=8, shard_frames=12, synth=4, args=ENC, what="3840x2160 x 96 frames, 8 GOPs of 12"),
     "config2-small": dict(width=1920, height=1080, shards=16, shard_frames=8, synth=2, args=ENC, what="1080p x 128 frames, 16 GOPs of 8"),
     "config5-small": dict(width=1280, height=720, shards=16, shard_frames=5, synth=5, args=ENC, streams=True, what="16 streams of 1280x720 x 5 frames"),
     # CPU-sized job for the tests

@@ -125,6 +125,7 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
         r.u = ctx->d_ref[s] + 4 * ctx->luma_bytes + (size_t)fc.stride_c * (PCAMV_PADV / 2) + PCAMV_PADH / 2;
         r.v = r.u + ctx->chroma_bytes;
         r.integral = nullptr; r.integral4 = nullptr; r.poc = -1; r.valid = 0;
+        r.base = ctx->d_ref[s]; r.bytes = ctx->ref_bytes + 4096;
         if (fc.me_method >= PCAMV_ME_ESA)
         {
             OCK(cudaMalloc(&ctx->d_integral[s], ctx->luma_bytes * sizeof(uint16_t)));

@@ -21,6 +21,8 @@ struct DevRef
     uint16_t *integral4;    // 4x4 box sums, only when sub-8x8 partitions are searched exhaustively
     int poc;
     int valid;
+    const uint8_t *base;    // the slot's allocation (4 luma planes | U | V | slack) and its size: what the PCAMV_CHECKED build checks loads against
+    size_t bytes;
 };
 
 struct DevTables

@@ -487,6 +487,16 @@ PCAMV_FN void mc_rect(MbCtx &c, int ref_slot, int x0, int y0, int wd, int ht, in
     for (int k = 0; k < 4; k++) b.ref[k] = rf.y[k] + off;
     const uint8_t *s1, *s2;
     qpel_sources(b, qmx, qmy, s1, s2);
+#if defined(PCAMV_CHECKED)
+    b.chk_lo = rf.base; b.chk_hi = rf.base + rf.bytes;
+    PCAMV_CHK_RANGE(b, (s1 < s2 ? s1 : s2) - 3, (s1 > s2 ? s1 : s2) + (ht - 1) * b.stride + wd + 7, "mc_rect (luma)");
+    {
+        const uint8_t *cu = rf.u + (ptrdiff_t)(8 * c.mb_y + (y0 >> 1) + (qmy >> 3)) * b.stride_c + 8 * c.mb_x + (x0 >> 1) + (qmx >> 3);
+        const uint8_t *cv = rf.v + (ptrdiff_t)(8 * c.mb_y + (y0 >> 1) + (qmy >> 3)) * b.stride_c + 8 * c.mb_x + (x0 >> 1) + (qmx >> 3);
+        PCAMV_CHK_RANGE(b, cu - 3, cu + (ht >> 1) * b.stride_c + (wd >> 1) + 1 + 7, "mc_rect (U)");
+        PCAMV_CHK_RANGE(b, cv - 3, cv + (ht >> 1) * b.stride_c + (wd >> 1) + 1 + 7, "mc_rect (V)");
+    }
+#endif
     const int w4 = wd >> 2;
     PCAMV_FOR_ITEMS(it, w4 * ht)
     {
@@ -665,6 +675,9 @@ PCAMV_DEV void setup_block(const MbCtx &c, MeBlock &b, int i_ref, int i_pixel, i
     b.ref_u = rf.u + offc; b.ref_v = rf.v + offc;
     b.integral = rf.integral ? rf.integral + off : nullptr;
     b.integral4 = rf.integral4 ? rf.integral4 + off : nullptr;
+#if defined(PCAMV_CHECKED)
+    b.chk_lo = rf.base; b.chk_hi = rf.base + rf.bytes;
+#endif
 }
 
 template <int XS>

@@ -226,6 +226,9 @@ __device__ __forceinline__ void make_block(const DevFrameCtx &fc, MeBlock &b, in
     b.ref_u = rf.u + offc; b.ref_v = rf.v + offc;
     b.integral = rf.integral ? rf.integral + off : nullptr;
     b.integral4 = rf.integral4 ? rf.integral4 + off : nullptr;
+#if defined(PCAMV_CHECKED)
+    b.chk_lo = rf.base; b.chk_hi = rf.base + rf.bytes;
+#endif
 }
 
 // mvsads: --me tesa candidate lists, one of mvsads_cap entries per call of this launch (null otherwise)

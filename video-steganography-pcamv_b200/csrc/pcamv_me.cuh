@@ -8,6 +8,9 @@
 // with its strict-< rule, so the first minimum wins exactly as in the scalar code.
 #pragma once
 #include "pcamv_prims.cuh"
+#if defined(PCAMV_CHECKED) && !defined(PCAMV_EMU)
+#include <stdio.h>
+#endif
 
 namespace pcamv {
 
@@ -48,7 +51,23 @@ struct MeBlock
     int mvp[2];
     const int16_t *cost_mvx, *cost_mvy;   // cost_mv - mvp[0], cost_mv - mvp[1]
     int k_fpel, k_qsad;       // what fpelcmp is at integer / quarter-pel positions: SAD, or SATD with --me tesa (encoder/encoder.c:621-624)
+#if defined(PCAMV_CHECKED)
+    const uint8_t *chk_lo, *chk_hi;    // the reference slot's allocation: every pixel load of the evaluators must stay inside
+#endif
 };
+
+// PCAMV_CHECKED build (tools/checked_build.sh): the address range a call is about to read from the reference planes is checked
+// against the slot's allocation, and the kernel traps on a violation — the pool this project is measured on refuses
+// compute-sanitizer (profiles/r02_sanitizer_attempt.txt), so the out-of-bounds class that matters here (a motion vector, a
+// border or a stride computed wrongly sends the evaluator outside the padded planes) is checked by the code itself.
+#if defined(PCAMV_CHECKED) && !defined(PCAMV_EMU)
+  #define PCAMV_CHK_RANGE(b, first, last, what) do { \
+      if ((const uint8_t *)(first) < (b).chk_lo || (const uint8_t *)(last) > (b).chk_hi) { \
+          if ((threadIdx.x & 31) == 0) printf("PCAMV_CHECKED: %s reads [%p, %p) outside the reference slot [%p, %p)\n", what, (const void *)(first), (const void *)(last), (const void *)(b).chk_lo, (const void *)(b).chk_hi); \
+          __trap(); } } while (0)
+#else
+  #define PCAMV_CHK_RANGE(b, first, last, what) do { } while (0)
+#endif
 
 // search state / result (the in/out part of the reference's x264_me_t, encoder/me.h:30-51)
 struct MeResult
@@ -194,6 +213,14 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
         const int off = (qy >> 2) * stride + (qx >> 2);
         s1 = b.ref[h0] + off + (fy == 3 ? stride : 0);
         s2 = (((fy << 2) + fx) & 5) ? b.ref[h1] + off + (fx == 3 ? 1 : 0) : s1;
+    }
+    // (ld_row16 / ld4 read whole aligned words: up to 3 bytes before and 7 after the pixels they deliver)
+    PCAMV_CHK_RANGE(b, (s1 < s2 ? s1 : s2) - 3, (s1 > s2 ? s1 : s2) + (bh - 1) * stride + 16 + 7, "cand_cost (luma)");
+    if (kind == COST_SATD_CHROMA)
+    {
+        const uint8_t *cu = b.ref_u + (qy >> 3) * b.stride_c + (qx >> 3), *cv = b.ref_v + (qy >> 3) * b.stride_c + (qx >> 3);
+        PCAMV_CHK_RANGE(b, cu - 3, cu + (bh >> 1) * b.stride_c + (bw >> 1) + 1 + 7, "cand_cost (U)");
+        PCAMV_CHK_RANGE(b, cv - 3, cv + (bh >> 1) * b.stride_c + (bw >> 1) + 1 + 7, "cand_cost (V)");
     }
     if (kind == COST_SAD_FPEL || kind == COST_SAD)
     {
@@ -365,6 +392,7 @@ PCAMV_FN int lane_sad(const MeBlock &b, int mx, int my)
     const smem_ptr fenc = to_smem(b.fenc);
     const int stride = b.stride, bh = b.bh, w4 = b.bw >> 2;
     const uint8_t *s = b.ref[0] + my * stride + mx;
+    PCAMV_CHK_RANGE(b, s - 3, s + (bh - 1) * stride + 16 + 7, "lane_sad");
     int acc = 0;
     // (not unrolled: measured no faster with four rows in flight, and the instruction cache is the scarcer resource)
 #pragma unroll 1

@@ -54,7 +54,10 @@ def main():
     sweep = [tuple(x.split(":")) for x in os.environ.get("PCAMV_QT_SWEEP", "").split(",") if x] or [None]
     for setting in sweep:
         if setting:
-            os.environ["PCAMV_SPLIT_CTRL_SMS"], os.environ["PCAMV_SPLIT_ROWS"] = setting
+            os.environ["PCAMV_SPLIT_CTRL_SMS"], os.environ["PCAMV_SPLIT_ROWS"] = setting[:2]
+            if len(setting) > 2:        # ctrl_sms:rows:phase_ns[:patience_ns]
+                os.environ["PCAMV_SPLIT_PHASE_NS"] = setting[2]
+                os.environ["PCAMV_SPLIT_PATIENCE_NS"] = setting[3] if len(setting) > 3 else "2000"
         time_one(pcamv, ctxs, S, rpc, reps, m_ref, l1_ref, par, setting)
 
 

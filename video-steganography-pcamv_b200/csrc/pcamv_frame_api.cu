@@ -396,13 +396,13 @@ static int split_check(pcamv_ctx *ctx)
     CK(cudaMemcpy(&flag, ctx->d_split + SPH_ABORT * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost));
     if (getenv("PCAMV_SPLIT_STATS"))
     {
-        unsigned long long s[12];
+        unsigned long long s[13];
         CK(cudaMemcpy(s, ctx->d_split + SPH_STATS * sizeof(int), sizeof(s), cudaMemcpyDeviceToHost));
         fprintf(stderr, "split stats: search teams %llu: wait %.1f ms serve %.1f ms each, %llu requests (%.1f us per request) | control teams %llu: "
-                        "idle %.1f claim %.1f restore %.1f analyse %.1f park %.1f ms each of %.1f, %llu steps (%.2f us analysis per step)\n",
+                        "idle %.1f claim %.1f restore %.1f analyse %.1f park %.1f ms each of %.1f, %llu steps (%.2f us analysis per step), %llu in phase\n",
                 s[3], s[3] ? s[0] / 1e6 / s[3] : 0.0, s[3] ? s[1] / 1e6 / s[3] : 0.0, s[2], s[2] ? s[1] / 1e3 / s[2] : 0.0,
                 s[10], s[10] ? s[4] / 1e6 / s[10] : 0.0, s[10] ? s[5] / 1e6 / s[10] : 0.0, s[10] ? s[6] / 1e6 / s[10] : 0.0, s[10] ? s[7] / 1e6 / s[10] : 0.0,
-                s[10] ? s[8] / 1e6 / s[10] : 0.0, s[10] ? s[11] / 1e6 / s[10] : 0.0, s[9], s[9] ? s[7] / 1e3 / s[9] : 0.0);
+                s[10] ? s[8] / 1e6 / s[10] : 0.0, s[10] ? s[11] / 1e6 / s[10] : 0.0, s[9], s[9] ? s[7] / 1e3 / s[9] : 0.0, s[12]);
     }
     if (flag) return ctx_fail(ctx, "split wavefront: a team waited 20 s for work that never came (watchdog); the launch was abandoned", cudaSuccess);
     return 0;

@@ -24,6 +24,7 @@
 // wait on control teams except for work: no deadlock for any grid that has at least one SM in each role.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <new>
 #include "pcamv_device.h"
 #include "pcamv_cost.cuh"
@@ -85,7 +86,24 @@ enum { SLOT_FREE = 0, SLOT_WAIT_DEP = 1, SLOT_WAIT_SEARCH = 2 };
 struct TeamTable            // per control team, in shared memory
 {
     int state[SPLIT_MAX_ROWS], item[SPLIT_MAX_ROWS], row[SPLIT_MAX_ROWS], x[SPLIT_MAX_ROWS], seq[SPLIT_MAX_ROWS];
+    int kind[SPLIT_MAX_ROWS];        // which piece of the analysis the row's next step runs (step_kind)
 };
+
+// The next step of a parked macroblock, by the code it will run: 0 = start of a macroblock (neighbour cache, predictors, first
+// 16x16 search out), 1 = a 16x16 result (P_SKIP probe, on to the 8x8 searches), 2 = an 8x8 result, 3 = a 16x8 / 8x16 result,
+// 4 = a refinement result (decision, records).  Kind-affine scheduling (PCAMV_SPLIT_PHASE_NS > 0): all control teams of the
+// GPU prefer, at any time, the steps of ONE kind — the kind is a function of %globaltimer, so nobody has to agree on it — and a
+// control SM's instruction caches see one ~10 KB piece of code for a while instead of all 60 KB at once.
+__device__ __forceinline__ int step_kind(const PtState &pt)
+{
+    return pt.in16 ? 1 : pt.in8 ? 2 : pt.in168 ? 3 : 4;
+}
+// phase schedule: the kinds in the order and proportion a macroblock needs them (1 start, 1 x 16x16, 4 x 8x8, 3 x 16x8 / 8x16, 1 refine)
+__device__ __forceinline__ int phase_kind(unsigned long long now, unsigned phase_ns)
+{
+    const unsigned slot = (unsigned)((now / phase_ns) % 10ull);
+    return slot == 0 ? 0 : slot == 1 ? 1 : slot <= 5 ? 2 : slot <= 8 ? 3 : 4;
+}
 
 __device__ __forceinline__ bool sp_dep_ready(const DevFrameCtx &fc, const FrameParams &fp, int row, int x)
 {
@@ -212,7 +230,8 @@ __device__ __forceinline__ int claim_row(const BatchItem *__restrict__ items, in
 
 template <int F>
 __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items, int n_items, int *next_row, const SplitBufs sb,
-                                             MbWork &work, unsigned char *ctx_mem, TeamTable &tt, int rows_per_team)
+                                             MbWork &work, unsigned char *ctx_mem, TeamTable &tt, int rows_per_team, unsigned phase_ns,
+                                             unsigned phase_patience_ns)
 {
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -228,10 +247,11 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
     unsigned backoff = 64;
     const unsigned long long t_start = sp_globaltimer();
     unsigned long long *stats = (unsigned long long *)(sb.hdr + SPH_STATS);
-    unsigned long long s_idle = 0, s_claim = 0, s_in = 0, s_run = 0, s_out = 0, s_steps = 0, tm = t_start;
+    unsigned long long s_idle = 0, s_claim = 0, s_in = 0, s_run = 0, s_out = 0, s_steps = 0, tm = t_start, wait0 = 0, s_match = 0;
 #define SP_TICK(acc) do { const unsigned long long now_ = sp_globaltimer(); acc += now_ - tm; tm = now_; } while (0)
 #define SP_CTRL_EXIT() do { if (lane == 0) { atomicAdd(stats + 4, s_idle); atomicAdd(stats + 5, s_claim); atomicAdd(stats + 6, s_in); atomicAdd(stats + 7, s_run); \
-        atomicAdd(stats + 8, s_out); atomicAdd(stats + 9, s_steps); atomicAdd(stats + 10, 1ull); atomicAdd(stats + 11, sp_globaltimer() - t_start); } } while (0)
+        atomicAdd(stats + 8, s_out); atomicAdd(stats + 9, s_steps); atomicAdd(stats + 10, 1ull); atomicAdd(stats + 11, sp_globaltimer() - t_start); \
+        atomicAdd(stats + 12, s_match); } } while (0)
     for (;;)
     {
         // ---- fill a free slot with a fresh row --------------------------------------------------------------------------
@@ -245,7 +265,7 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
             if (f >= 0)
             {
                 const int k = __ffs((int)free_m) - 1;
-                if (lane == 0) { tt.state[k] = SLOT_WAIT_DEP; tt.item[k] = f; tt.row[k] = row; tt.x[k] = 0; }
+                if (lane == 0) { tt.state[k] = SLOT_WAIT_DEP; tt.item[k] = f; tt.row[k] = row; tt.x[k] = 0; tt.kind[k] = 0; }
                 __syncwarp();
             }
             else
@@ -288,8 +308,24 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
             continue;
         }
         backoff = 64;
-        // first ready slot at or after rr
-        const unsigned rotm = (ready_m >> rr) | (rr ? ready_m << (32 - rr) : 0u);
+        // kind-affine pick: a ready step of the current phase's kind if there is one; otherwise wait a little for one to turn up
+        // (other teams of this SM are running that kind right now), then take whatever is ready
+        unsigned pick_m = ready_m;
+        if (phase_ns)
+        {
+            const unsigned long long now = sp_globaltimer();
+            const int want = phase_kind(now, phase_ns);
+            const unsigned match_m = __ballot_sync(0xffffffffu, ok && tt.kind[lane] == want);
+            if (match_m) { pick_m = match_m; wait0 = 0; s_match++; }
+            else
+            {
+                if (!wait0) wait0 = now;
+                if (now - wait0 < phase_patience_ns) { __nanosleep(200); SP_TICK(s_idle); continue; }
+                wait0 = 0;
+            }
+        }
+        // first picked slot at or after rr
+        const unsigned rotm = (pick_m >> rr) | (rr ? pick_m << (32 - rr) : 0u);
         const int k = (int)((rr + (unsigned)(__ffs((int)rotm) - 1)) & 31u);
         rr = (unsigned)(k + 1) % (unsigned)rows_per_team;
 
@@ -327,7 +363,7 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
         if (r == PT_YIELD)
         {
             const int seq = tt.seq[k] + 1;
-            if (lane == 0) { work.rq.item = item; work.rq.pad2 = seq; tt.seq[k] = seq; tt.state[k] = SLOT_WAIT_SEARCH; }
+            if (lane == 0) { work.rq.item = item; work.rq.pad2 = seq; tt.seq[k] = seq; tt.state[k] = SLOT_WAIT_SEARCH; tt.kind[k] = step_kind(work.pt); }
             __syncwarp();
             {
                 uint4 *dst = (uint4 *)park;
@@ -365,6 +401,7 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
                 {
                     tt.x[k] = x + 1;
                     tt.state[k] = SLOT_WAIT_DEP;
+                    tt.kind[k] = 0;
                 }
             }
         }
@@ -375,7 +412,8 @@ __device__ __forceinline__ void control_team(const BatchItem *__restrict__ items
 
 template <int F>
 __global__ void __launch_bounds__(128, PCAMV_SPLIT_MIN_CTAS) k_analyse_p_split(const BatchItem *__restrict__ items, int n_items, int *next_row,
-                                                                              const SplitBufs sb, int n_ctrl_sms, int n_sms, int rows_per_team)
+                                                                              const SplitBufs sb, int n_ctrl_sms, int n_sms, int rows_per_team,
+                                                                              unsigned phase_ns, unsigned phase_patience_ns)
 {
     __shared__ MbWork s_work[4];
     __shared__ __align__(16) unsigned char s_ctx[4][sizeof(MbCtx)];
@@ -401,7 +439,7 @@ __global__ void __launch_bounds__(128, PCAMV_SPLIT_MIN_CTAS) k_analyse_p_split(c
     }
     __syncthreads();
     if (s_role == 2)
-        control_team<F>(items, n_items, next_row, sb, s_work[warp], s_ctx[warp], s_tt[warp], rows_per_team);
+        control_team<F>(items, n_items, next_row, sb, s_work[warp], s_ctx[warp], s_tt[warp], rows_per_team, phase_ns, phase_patience_ns);
     else
         search_team<(F & 1)>(items, sb, s_work[warp]);
 }
@@ -446,8 +484,13 @@ void launch_analyse_p_split(const BatchItem *items, int n_items, int *next_row, 
                             int rows_per_team, int feature, void *stream)
 {
     const cudaStream_t st = (cudaStream_t)stream;
-    if (feature & 1) k_analyse_p_split<1><<<ctas, 128, 0, st>>>(items, n_items, next_row, sb, n_ctrl_sms, n_sms, rows_per_team);
-    else             k_analyse_p_split<0><<<ctas, 128, 0, st>>>(items, n_items, next_row, sb, n_ctrl_sms, n_sms, rows_per_team);
+    // kind-affine control scheduling: PCAMV_SPLIT_PHASE_NS = length of a phase (0 / unset = off), PCAMV_SPLIT_PATIENCE_NS = how long a
+    // team with only other kinds ready waits for one of the phase's kind before it takes what it has
+    unsigned phase_ns = 0, patience_ns = 2000;
+    if (const char *e = getenv("PCAMV_SPLIT_PHASE_NS")) phase_ns = (unsigned)atoi(e);
+    if (const char *e = getenv("PCAMV_SPLIT_PATIENCE_NS")) patience_ns = (unsigned)atoi(e);
+    if (feature & 1) k_analyse_p_split<1><<<ctas, 128, 0, st>>>(items, n_items, next_row, sb, n_ctrl_sms, n_sms, rows_per_team, phase_ns, patience_ns);
+    else             k_analyse_p_split<0><<<ctas, 128, 0, st>>>(items, n_items, next_row, sb, n_ctrl_sms, n_sms, rows_per_team, phase_ns, patience_ns);
 }
 
 } // namespace pcamv

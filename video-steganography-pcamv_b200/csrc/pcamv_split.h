@@ -7,16 +7,16 @@ namespace pcamv {
 
 #define SPLIT_NQ 8                    // request rings (a search team serves one; spreads the ticket atomics over 8 lines)
 #define SPLIT_RING_CAP 65536          // entries per ring, >= row slots of the largest grid: a ring can never wrap onto a pending entry
-#define SPLIT_MAX_ROWS 8              // row slots per control team
+#define SPLIT_MAX_ROWS 16             // row slots per control team
 #define SPLIT_REQ_STRIDE 128          // bytes per request record
 #define SPLIT_MAX_SMS 512
 #ifndef PCAMV_SPLIT_MIN_CTAS
 #define PCAMV_SPLIT_MIN_CTAS 6        // CTAs of 4 teams per SM the register budget must allow
 #endif
 // header words
-enum { SPH_ROWS_DONE = 0, SPH_DONE = 1, SPH_WORKERS = 2, SPH_SMS = 3, SPH_ABORT = 4, SPH_STATS = 8 /* 12 x u64 */, SPH_SM_ROLE = 32 };
+enum { SPH_ROWS_DONE = 0, SPH_DONE = 1, SPH_WORKERS = 2, SPH_SMS = 3, SPH_ABORT = 4, SPH_STATS = 8 /* 13 x u64: ints 8 .. 33 */, SPH_SM_ROLE = 40 };
 // SPH_STATS (ns summed over teams, globaltimer): search teams 0 waiting for a request, 1 serving, 2 requests served, 3 teams;
-// control teams 4 idle (nothing runnable), 5 claiming rows, 6 restore + stage, 7 analysis, 8 park + publish, 9 steps, 10 teams, 11 lifetime
+// control teams 4 idle (nothing runnable), 5 claiming rows, 6 restore + stage, 7 analysis, 8 park + publish, 9 steps, 10 teams, 11 lifetime, 12 steps that matched the phase's kind
 #define SPLIT_WATCHDOG_NS 20000000000ull    // a team that has waited this long for anything gives up and stops the launch (reported by the host)
 #define SPLIT_HDR_INTS (SPH_SM_ROLE + SPLIT_MAX_SMS)
 

@@ -47,9 +47,14 @@ typedef struct
     int qp_loaded;
     int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
     int device_forced;              /* the embed stage of this frame ran on the device: pass 2 takes its forced decisions from HBM */
+    /* reference frames built on the device (PCAMV_DEVICE_RECON=1): after the final pass of a P frame the GPU reconstructs and
+     * deblocks the frame into a free slot, and the next frame finds it resident instead of uploading it */
+    int recon_on, recon_check, cur_ref_slots[PCAMV_MAX_REFS], cur_n_ref;
+    pcamv_recon_patch *patches; int n_patches, cap_patches;
+    long recon_frames, recon_mismatch, recon_patched_mbs;
     int fenc_frame;                 /* h->fenc->i_frame currently on the GPU */
     /* reference slots: which frame each GPU slot holds */
-    struct { x264_frame_t *fr; int i_frame, i_poc, age; } slot[PCAMV_MAX_REFS + 2];
+    struct { x264_frame_t *fr; int i_frame, i_poc, age, device_built; } slot[PCAMV_MAX_REFS + 2];
     int n_slots, tick;
     /* accounting */
     double t_gpu, t_total0, t_open;
@@ -202,6 +207,9 @@ void pcamv_hook_open( x264_t *h )
     cfg.b_dct_decimate = h->param.analyse.b_dct_decimate;
     cfg.analyse_inter = h->param.analyse.inter;
     cfg.chroma_qp_offset = h->param.analyse.i_chroma_qp_offset;
+    cfg.no_deblock = !h->param.b_deblocking_filter;
+    cfg.deblock_alpha_c0_offset = h->param.i_deblocking_filter_alphac0 << 1;    /* sh.i_alpha_c0_offset, encoder/encoder.c:170-171 */
+    cfg.deblock_beta_offset = h->param.i_deblocking_filter_beta << 1;
     cfg.rows_per_cta = (s = getenv( "PCAMV_ROWS_PER_CTA" )) ? atoi( s ) : 1;
     /* pass 2 of a forced macroblock: only the 16x16 search is live in the reference (see include/pcamv.h); PCAMV_PASS2_FULL=1
      * makes the GPU execute and log the dead searches as well */
@@ -228,6 +236,8 @@ void pcamv_hook_open( x264_t *h )
     if( !g.mbs || !g.log || !g.pass1 )
         die_msg( "out of memory" );
     g.qp_loaded = -1;
+    g.recon_on = (s = getenv( "PCAMV_DEVICE_RECON" )) && atoi( s );
+    g.recon_check = (s = getenv( "PCAMV_CHECK_RECON" )) && atoi( s );
     g.t_open = now_s() - g.t_total0;
 }
 
@@ -240,8 +250,10 @@ void pcamv_hook_close( x264_t *h )
         FILE *f = fopen( s, "w" );
         if( f )
         {
-            fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_open\": %.6f, \"t_total\": %.6f}\n",
-                     g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, g.t_open, now_s() - g.t_total0 );
+            fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_open\": %.6f, \"t_total\": %.6f, "
+                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld}\n",
+                     g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, g.t_open, now_s() - g.t_total0,
+                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs );
             fclose( f );
         }
     }
@@ -251,11 +263,30 @@ void pcamv_hook_close( x264_t *h )
                  g.n_passes, g.t_open, g.t_gpu, now_s() - g.t_total0 );
     if( g.ctx ) pcamv_close( g.ctx );
     if( g.pinned ) { pcamv_host_free( g.mbs ); pcamv_host_free( g.log ); } else { free( g.mbs ); free( g.log ); }
-    free( g.pass1 );
+    free( g.pass1 ); free( g.patches );
     memset( &g, 0, sizeof(g) );
 }
 
 /* ---- slice begin: upload what is new, analyse the whole P slice on the GPU ---------------------- */
+/* returns 0 when the GPU's planes of slot `s` equal the host's planes of `fr`, else 1 + the first differing plane */
+static int check_device_ref( int s, x264_frame_t *fr )
+{
+    int k, bad = 0;
+    for( k = 0; k < 6 && !bad; k++ )
+    {
+        const size_t n = pcamv_plane_bytes( g.ctx, k );
+        const int stride = pcamv_plane_stride( g.ctx, k ), padv = k < 4 ? 32 : 16, padh = k < 4 ? 32 : 16;
+        uint8_t *dev = malloc( n );
+        const uint8_t *host = ( k < 4 ? fr->filtered[k] : fr->plane[k - 3] ) - (size_t)padv * stride - padh;
+        if( !dev || pcamv_get_ref_plane( g.ctx, s, k, dev ) )
+            die( "pcamv_get_ref_plane" );
+        if( stride != fr->i_stride[k < 4 ? 0 : 1] || memcmp( dev, host, n ) )
+            bad = k + 1;
+        free( dev );
+    }
+    return bad;
+}
+
 static int slot_of( x264_frame_t *fr, const int *in_use, int n_in_use )
 {
     int i, k, best = -1;
@@ -263,6 +294,20 @@ static int slot_of( x264_frame_t *fr, const int *in_use, int n_in_use )
         if( g.slot[i].fr == fr && g.slot[i].i_frame == fr->i_frame && g.slot[i].i_poc == fr->i_poc )
         {
             g.slot[i].age = ++g.tick;
+            if( g.slot[i].device_built == 1 && g.recon_check )
+            {
+                /* check mode: the planes the GPU built for this picture against the host's own (integer + the three half-pel
+                 * planes + chroma, whole padded buffers: same layout on both sides); on a mismatch the host's are uploaded */
+                int bad = check_device_ref( i, fr );
+                g.slot[i].device_built = 2;
+                if( bad )
+                {
+                    g.recon_mismatch++;
+                    fprintf( stderr, "x264 [pcamv]: frame %d: reference planes built on the GPU differ from the host's (plane %d)\n", fr->i_frame, bad - 1 );
+                    if( pcamv_put_ref( g.ctx, i, fr->i_poc, fr->plane[0], fr->plane[1], fr->plane[2], fr->i_stride[0], fr->i_stride[1] ) )
+                        die( "pcamv_put_ref" );
+                }
+            }
             return i;
         }
     /* not resident: take the least recently used slot that no reference of this slice occupies */
@@ -280,6 +325,7 @@ static int slot_of( x264_frame_t *fr, const int *in_use, int n_in_use )
     if( pcamv_put_ref( g.ctx, best, fr->i_poc, fr->plane[0], fr->plane[1], fr->plane[2], fr->i_stride[0], fr->i_stride[1] ) )
         die( "pcamv_put_ref" );
     g.slot[best].fr = fr; g.slot[best].i_frame = fr->i_frame; g.slot[best].i_poc = fr->i_poc; g.slot[best].age = ++g.tick;
+    g.slot[best].device_built = 0;
     return best;
 }
 
@@ -327,6 +373,9 @@ void pcamv_hook_slice_begin( x264_t *h )
         in.ref_poc[i] = h->fref0[i]->i_poc;
     }
     in.cur_poc = h->fdec->i_poc;
+    g.cur_n_ref = h->i_ref0;
+    for( i = 0; i < h->i_ref0; i++ ) g.cur_ref_slots[i] = in.ref_slot[i];
+    g.n_patches = 0;
     {
         x264_frame_t *l0 = h->fref0[0];
         in.col_n_ref = l0->i_ref[0];
@@ -380,7 +429,61 @@ void pcamv_hook_slice_begin( x264_t *h )
     g.t_gpu += now_s() - t0;
 }
 
-void pcamv_hook_slice_end( x264_t *h ) { (void)h; g.active = 0; }
+/* after x264_macroblock_encode: the macroblocks the device cannot reconstruct on its own (records with early_skip == 2: the host
+ * kept b_skip_mc set and coded the residual against what its intra analysis left in fdec, quirk q1) are handed over as they are */
+void pcamv_hook_encoded( x264_t *h )
+{
+    if( g.active && g.recon_on && g.pass != 1 && g.mbs[h->mb.i_mb_xy].early_skip == 2 )
+    {
+        pcamv_recon_patch *p;
+        int i, y;
+        if( g.n_patches == g.cap_patches )
+        {
+            g.cap_patches = g.cap_patches ? 2 * g.cap_patches : 64;
+            g.patches = realloc( g.patches, g.cap_patches * sizeof(*g.patches) );
+            if( !g.patches ) die_msg( "out of memory" );
+        }
+        p = &g.patches[g.n_patches++];
+        p->mb_xy = h->mb.i_mb_xy; p->nnz = 0; p->pad = 0;
+        for( y = 0; y < 16; y++ ) memcpy( p->y + 16 * y, h->mb.pic.p_fdec[0] + y * FDEC_STRIDE, 16 );
+        for( y = 0; y < 8; y++ )
+        {
+            memcpy( p->u + 8 * y, h->mb.pic.p_fdec[1] + y * FDEC_STRIDE, 8 );
+            memcpy( p->v + 8 * y, h->mb.pic.p_fdec[2] + y * FDEC_STRIDE, 8 );
+        }
+        for( i = 0; i < 16; i++ )
+            if( h->mb.cache.non_zero_count[x264_scan8[i]] )
+                p->nnz |= 1 << ( block_idx_x[i] + 4 * block_idx_y[i] );
+        g.recon_patched_mbs++;
+    }
+}
+
+void pcamv_hook_slice_end( x264_t *h )
+{
+    if( g.active && g.recon_on && g.pass != 1 && h->sh.i_type == SLICE_TYPE_P && h->fdec->b_kept_as_ref )
+    {
+        /* the frame just analysed in its final pass becomes a reference: build it on the GPU, in the least recently used slot
+         * that none of its own references occupies */
+        int i, k, best = -1;
+        double t0 = now_s();
+        for( i = 0; i < g.n_slots; i++ )
+        {
+            int busy = 0;
+            for( k = 0; k < g.cur_n_ref; k++ ) busy |= g.cur_ref_slots[k] == i;
+            if( !busy && ( best < 0 || g.slot[i].age < g.slot[best].age ) )
+                best = i;
+        }
+        if( best < 0 )
+            die_msg( "no free reference slot" );
+        if( pcamv_reconstruct_ref( g.ctx, best, h->fdec->i_poc, g.pass, g.patches, g.n_patches ) )
+            die( "pcamv_reconstruct_ref" );
+        g.slot[best].fr = h->fdec; g.slot[best].i_frame = h->fdec->i_frame; g.slot[best].i_poc = h->fdec->i_poc;
+        g.slot[best].age = ++g.tick; g.slot[best].device_built = 1;
+        g.recon_frames++;
+        g.t_gpu += now_s() - t0;
+    }
+    g.active = 0;
+}
 
 /* ---- per-macroblock replay --------------------------------------------------------------------- */
 void pcamv_hook_analyse_begin( x264_t *h )

@@ -76,7 +76,9 @@ typedef struct pcamv_cfg
                                its residual depends on the intra analysis, which prunes against those "dead" costs.
                                Ignored with sub-8x8 partitions (a forced P_8x8 keeps the partition pass 2 decided).
                                0: pass 2 executes and logs everything the reference executes. */
-    int reserved[6];
+    int no_deblock;         /* sh.i_disable_deblocking_filter_idc == 1 (--nf); the three deblocking fields matter to pcamv_reconstruct_ref only */
+    int deblock_alpha_c0_offset, deblock_beta_offset;   /* sh.i_alpha_c0_offset, sh.i_beta_offset (the --deblock values, doubled) */
+    int reserved[3];
 } pcamv_cfg;
 
 /* Per-QP tables.  They are built on the host because the reference builds cost_mv with float
@@ -189,7 +191,8 @@ typedef struct pcamv_log_entry
 /* Per-macroblock outcome of the analysis (what x264_macroblock_analyse leaves in h->mb for a P macroblock). */
 typedef struct pcamv_mb_out
 {
-    int8_t type, partition, n_part, early_skip;   /* PCAMV_P_*, PCAMV_D_*, MV-carrying partitions, early P_SKIP exit */
+    int8_t type, partition, n_part, early_skip;   /* PCAMV_P_*, PCAMV_D_*, MV-carrying partitions; early_skip: 1 = early P_SKIP exit,
+                                                   * 2 = this pass's probe said skippable but the forced decision codes it (the host keeps b_skip_mc: quirk q1) */
     int8_t ref[4];                                /* reference index per 8x8 block */
     int16_t mv[16][2];                            /* h->mb.cache.mv[0][x264_scan8[i]], block_idx order */
     struct { int16_t mv[2]; int16_t mvp[2]; int8_t ref, i_pixel, xoff, yoff; } part[4];
@@ -307,6 +310,24 @@ int pcamv_embed_prepare(pcamv_ctx *ctx, int *length);
 int pcamv_embed_stc(pcamv_ctx *ctx, const uint8_t *message, int an, int matrixheight, const uint32_t *cols_short, int w_short,
                     const uint32_t *cols_long, int w_long, double total, uint8_t *stego);
 int pcamv_embed_download(pcamv_ctx *ctx, uint8_t *cover, float *rho, uint8_t *stego, int8_t *filp, pcamv_pass1_mb *pass1);
+
+/* ---- the reference frame built on the device (reference encoder/macroblock.c:605-755, common/frame.c:594-800,
+ * encoder/encoder.c:1004-1052) ------------------------------------------------------------------------------------------------
+ * After the FINAL pass of a P frame (pass 2, or pass 0 when nothing is embedded) pcamv_reconstruct_ref rebuilds the frame in
+ * reference slot `slot` from the decisions that pass left in HBM: motion compensation + residual coding of every macroblock,
+ * the in-loop deblocking filter, then borders, half-pel planes and integral planes as pcamv_put_ref builds them — byte for
+ * byte the planes the host's x264_fdec_filter_row produces, so the next frame needs no pcamv_put_ref for this picture.
+ * One class of macroblocks the device cannot reconstruct on its own: records with early_skip == 2 (the host keeps b_skip_mc
+ * set and codes the residual against what its intra analysis left in fdec).  For those the caller passes the
+ * host's own reconstruction BEFORE deblocking (h->mb.pic.p_fdec right after x264_macroblock_encode) and the surviving-coefficient
+ * flags of the 16 luma blocks (bit x + 4 y = non_zero_count of raster block (x, y) != 0) as patches. */
+typedef struct pcamv_recon_patch
+{
+    int32_t mb_xy;
+    uint16_t nnz, pad;
+    uint8_t y[256], u[64], v[64];       /* rows of 16 / 8 / 8 pixels */
+} pcamv_recon_patch;
+int pcamv_reconstruct_ref(pcamv_ctx *ctx, int slot, int poc, int pass, const pcamv_recon_patch *patches, int n_patches);
 
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 long long pcamv_launch_count(const pcamv_ctx *ctx);

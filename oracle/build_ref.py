@@ -33,6 +33,7 @@ HOOK_DECL = ("void pcamv_hook_open( x264_t *h ); void pcamv_hook_close( x264_t *
              "void pcamv_hook_slice_begin( x264_t *h ); void pcamv_hook_slice_end( x264_t *h );\n"
              "void pcamv_hook_analyse_begin( x264_t *h ); void pcamv_hook_analyse_end( x264_t *h );\n"
              "void pcamv_hook_embed( x264_t *h, int an ); void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me );\n"
+             "void pcamv_hook_encoded( x264_t *h );\n"
              "void pcamv_hook_ih_begin( void ); void pcamv_hook_ih_end( void );\n")
 # timing wrapper around the cost-table routine
 IH_WRAPPER = ("{ int r; pcamv_hook_ih_begin(); r = x264_ih_get_mv_cost_real( h, analysis, m, m_x, m_y, d_mv, d_mv_1_neighborhood, mb_xy );\n"

@@ -552,6 +552,9 @@ void pcamv_hook_ih_end( void )
 }
 
 /* one MV_SATD_FDEC_IH evaluation (encoder/analyse.c:2364-2385): +1 luma SATD, +2 chroma when chroma ME */
+/* right after x264_macroblock_encode (encoder/encoder.c:1881): nothing to record here */
+void pcamv_hook_encoded( x264_t *h ) { (void)h; }
+
 void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me )
 {
     g_cnt_ih_luma++;

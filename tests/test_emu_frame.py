@@ -24,6 +24,8 @@ def run_checker(checker, dump, async_mode=False):
     assert p.returncode == 0, p.stdout + p.stderr
     out = dict(kv.split("=") for kv in p.stdout.split())
     assert out["bad_mb_logs"] == "0" and out["bad_decisions"] == "0" and out["bad_ih"] == "0", p.stdout
+    # reconstruction + deblocking of every frame whose successor was dumped too == the reference's own reference plane
+    assert out["bad_recon"] == "0", p.stdout + p.stderr[-1500:]
     return {k: int(v) for k, v in out.items()}
 
 
@@ -31,6 +33,7 @@ def run_checker(checker, dump, async_mode=False):
 def test_golden_frames(checker, name, tmp_path):
     n = run_checker(checker, refrun.golden_dump_path(name, str(tmp_path)))
     assert n["passes"] >= 2 and n["calls"] > 1000 and n["ih"] > 100
+    assert n["recon"] >= 1 or name in ("qcif_esa5", "qcif_tesa5")          # (those two fixtures hold a single frame)
 
 
 @pytest.mark.parametrize("name", ["qcif_hex5", "qcif_umh5_ref2", "qcif_esa5", "qcif_dia2_lownoise"])

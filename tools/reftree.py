@@ -120,6 +120,8 @@ def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra="", drop_rea
                   r"\1 pcamv_hook_slice_begin( h );", 1, "slice begin")
     t = sub_exact(t, r"\n(\t\tx264_macroblock_analyse\( h \);)",
                   r"\n\t\tpcamv_hook_analyse_begin( h ); x264_macroblock_analyse( h ); pcamv_hook_analyse_end( h );", 1, "analyse call")
+    # right after the macroblock has been reconstructed in h->mb.pic.p_fdec (encoder/encoder.c:1881), before anything filters it
+    t = sub_exact(t, r"\n(\t\tx264_macroblock_encode\( h \);)", r"\n\1 pcamv_hook_encoded( h );", 1, "macroblock_encode call")
     # after the filp loop of the embed stage (encoder/encoder.c:1848-1855): hook before the DEGUG print
     t = sub_exact(t, r"(\t\t\t\t// [^\n]*\n\t\t\t\tif \(DEGUG_LIJUN\)\n\t\t\t\t\{\n\t\t\t\t\tprintf\(\"1)",
                   r"\t\t\t\tpcamv_hook_embed( h, an );\n\1", 1, "embed end")

@@ -18,17 +18,14 @@ PCAMV_DEV const PartInfo &mb_part(const MbCtx &c, const MbResult &res, int k)
     return (res.type == MB_P_8x8 && c.fp.subparts) ? c.fp.subparts[(size_t)16 * c.mb_xy + k] : res.part[k];
 }
 
-PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx, int omy)
+// Transform / quantisation / decimation / reconstruction of the macroblock whose prediction is staged in c.w.pred_* (the part of
+// x264_macroblock_encode behind the motion compensation, encoder/macroblock.c:690-755 luma, :277-372 chroma).  Leaves the
+// reconstruction in c.w.pred_*.  Returns the luma 4x4 blocks (bit = block_idx) that keep coefficients after decimation: the
+// non_zero_count the reference stores for them is non-zero (what the deblocking filter's bS = 2 test reads).
+PCAMV_FN int encode_mb_residual(MbCtx &c)
 {
     const DevTables &t = c.fc.tab;
     const int b_decimate = c.fc.b_dct_decimate;
-    for (int p = 0; p < res.n_part; p++)
-    {
-        const PartInfo &pi = mb_part(c, res, p);
-        const int mx = clip3(p == k_over ? omx : pi.mv[0], c.mv_min[0], c.mv_max[0]);
-        const int my = clip3(p == k_over ? omy : pi.mv[1], c.mv_min[1], c.mv_max[1]);
-        mc_rect(c, c.fp.ref_slot[pi.ref], pi.xoff, pi.yoff, pix_w(pi.i_pixel), pix_h(pi.i_pixel), mx, my);
-    }
     // scratch layout: [0..23] decimate score | nz << 8 per block; raw chroma DC terms behind them
     int *sc = c.w.scratch;
     int16_t *dcs = (int16_t *)(c.w.scratch + 24);           // 8 x int16
@@ -120,6 +117,26 @@ PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx
         }
     }
     team_sync();
+    int luma_mask = 0;
+#pragma unroll 1
+    for (int it = 0; it < 16; it++)
+        if (((add_luma8 >> (it >> 2)) & 1) && (sc[it] >> 8)) luma_mask |= 1 << it;
+    return luma_mask;
+}
+
+
+// x264_macroblock_encode for an inter MB whose partition k_over uses MV (omx, omy) instead of its own.
+// Leaves the reconstruction in c.w.pred_y / pred_u / pred_v.
+PCAMV_FN void encode_mb_inter(MbCtx &c, const MbResult &res, int k_over, int omx, int omy)
+{
+    for (int p = 0; p < res.n_part; p++)
+    {
+        const PartInfo &pi = mb_part(c, res, p);
+        const int mx = clip3(p == k_over ? omx : pi.mv[0], c.mv_min[0], c.mv_max[0]);
+        const int my = clip3(p == k_over ? omy : pi.mv[1], c.mv_min[1], c.mv_max[1]);
+        mc_rect(c, c.fp.ref_slot[pi.ref], pi.xoff, pi.yoff, pix_w(pi.i_pixel), pix_h(pi.i_pixel), mx, my);
+    }
+    encode_mb_residual(c);
 }
 
 // dx / dy of replacement candidate ii = 0..11 (four at distance 1, eight knight moves), one signed nibble each:

@@ -49,6 +49,7 @@ struct pcamv_ctx
     uint8_t *d_emb = nullptr; int *emb_offsets = nullptr; void *emb_pass1 = nullptr; uint8_t *emb_cover = nullptr, *emb_stego = nullptr;
     int8_t *emb_filp = nullptr; float *emb_rho = nullptr; double *emb_total = nullptr;
     int emb_length = 0, emb_state = 0;         // 0 = nothing, 1 = cover / rho built for the frame in HBM, 2 = flips + forced decisions built
+    uint16_t *d_recon_nnz = nullptr; uint8_t *d_recon_patches = nullptr; int recon_patch_cap = 0;   // device-side reconstruction (pcamv_recon.cu)
     unsigned long long *d_trace = nullptr;     // [n_mb][2] per-MB start/end timestamps (pcamv_frame_trace)
     bool trace_on = false;
     int *d_progress = nullptr;                 // [mb_h] row progress + [1] row claim counter + [mb_h] row owners (row pool)
@@ -61,4 +62,5 @@ struct pcamv_ctx
 
 namespace pcamv {
 int ctx_fail(pcamv_ctx *c, const char *what, cudaError_t e);
+int filter_slot(pcamv_ctx *ctx, int slot);     // borders + half-pel planes (+ integral planes) of a slot whose integer interiors are in HBM
 }

@@ -1491,7 +1491,9 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
         update_cache<SUB8>(c, a, type, partition);
     // a forced decision names partitions this pass may never have searched: its record carries no partition slots
     // (pass 2 has no cost table; the slots would be whatever the team's scratch held)
-    finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, 0);
+    // early_skip = 2: this pass's probe found the macroblock skippable, the decision forced from pass 1 codes it anyway (quirk q1:
+    // the host keeps b_skip_mc set and reconstructs it from what its intra analysis left in fdec — pcamv_recon.cuh needs to know)
+    finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, early_skip ? 2 : 0);
 }
 
 // Resumable form of analyse_p_mb (same decisions, written as stages that can be left and re-entered).
@@ -1693,7 +1695,7 @@ PCAMV_FN int analyse_p_mb_rs(MbCtx &c, const uint32_t *prev_mv)
         update_cache<SUB8>(c, a, type, partition);
     // a forced decision names partitions this pass may never have searched: its record carries no partition slots
     // (pass 2 has no cost table; the slots would be whatever the team's scratch held)
-    finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, 0);
+    finalize_mb<SUB8>(c, a, type, (forced && forced->used) ? -partition : partition, pt.early_skip ? 2 : 0);
     return PT_DONE;
 }
 } // namespace pcamv

@@ -24,7 +24,8 @@ class Cfg(C.Structure):
                 ("me_method", C.c_int), ("me_range", C.c_int), ("subpel_refine", C.c_int), ("chroma_me", C.c_int),
                 ("max_refs", C.c_int), ("mv_range", C.c_int), ("b_cabac", C.c_int), ("b_fast_pskip", C.c_int),
                 ("b_dct_decimate", C.c_int), ("analyse_inter", C.c_int), ("chroma_qp_offset", C.c_int),
-                ("rows_per_cta", C.c_int), ("pass2_elide", C.c_int), ("reserved", C.c_int * 6)]
+                ("rows_per_cta", C.c_int), ("pass2_elide", C.c_int), ("no_deblock", C.c_int), ("deblock_alpha_c0_offset", C.c_int),
+                ("deblock_beta_offset", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class QpTables(C.Structure):
@@ -46,6 +47,7 @@ ME_RESULT_DTYPE = np.dtype([("mv", "<i2", 2), ("cost", "<i4"), ("cost_mv", "<i4"
 LOG_MAX = 112
 LOG_ENTRY_DTYPE = np.dtype([("kind", "i1"), ("i_pixel", "i1"), ("i_ref", "i1"), ("pad", "i1"), ("mv", "<i2", 2),
                             ("cost", "<i4"), ("cost_mv", "<i4")], align=True)
+RECON_PATCH_DTYPE = np.dtype([("mb_xy", "<i4"), ("nnz", "<u2"), ("pad", "<u2"), ("y", "u1", 256), ("u", "u1", 64), ("v", "u1", 64)])
 MB_OUT_DTYPE = np.dtype([("type", "i1"), ("partition", "i1"), ("n_part", "i1"), ("early_skip", "i1"), ("ref", "i1", 4),
                          ("mv", "<i2", (16, 2)),
                          ("part", [("mv", "<i2", 2), ("mvp", "<i2", 2), ("ref", "i1"), ("i_pixel", "i1"), ("xoff", "i1"),
@@ -69,7 +71,7 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
            "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide",
            "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave", "pcamv_stc_embed",
-           "pcamv_embed_prepare", "pcamv_embed_stc", "pcamv_embed_download"]
+           "pcamv_embed_prepare", "pcamv_embed_stc", "pcamv_embed_download", "pcamv_reconstruct_ref"]
 
 _lib = None
 
@@ -116,6 +118,7 @@ def load_library(path=None):
     lib.pcamv_embed_prepare.argtypes = [vp, C.POINTER(C.c_int)]; lib.pcamv_embed_prepare.restype = ip
     lib.pcamv_embed_stc.argtypes = [vp, vp, ip, ip, vp, ip, vp, ip, C.c_double, vp]; lib.pcamv_embed_stc.restype = ip
     lib.pcamv_embed_download.argtypes = [vp, vp, vp, vp, vp, vp]; lib.pcamv_embed_download.restype = ip
+    lib.pcamv_reconstruct_ref.argtypes = [vp, ip, ip, ip, vp, ip]; lib.pcamv_reconstruct_ref.restype = ip
     lib.pcamv_host_alloc.argtypes = [C.c_size_t]; lib.pcamv_host_alloc.restype = vp
     lib.pcamv_host_free.argtypes = [vp]; lib.pcamv_host_free.restype = None
     lib.pcamv_analyse_p_batch.argtypes = [C.POINTER(vp), C.POINTER(C.POINTER(FrameIn)), ip, C.POINTER(vp), C.POINTER(vp)]
@@ -254,6 +257,15 @@ class PcamvContext:
         if rc < 0:
             self._check(rc)
         return stego if rc == 0 else None
+
+    # -- reference frame built on the device ---------------------------------------------------------
+    def reconstruct_ref(self, slot, poc, pass_, patches=None):
+        """pcamv_reconstruct_ref: the frame of the last analysed (final) pass into reference slot `slot`."""
+        if patches is not None and len(patches):
+            patches = np.ascontiguousarray(patches, dtype=RECON_PATCH_DTYPE)
+            self._check(self.lib.pcamv_reconstruct_ref(self.handle, slot, poc, pass_, _ptr(patches), len(patches)))
+        else:
+            self._check(self.lib.pcamv_reconstruct_ref(self.handle, slot, poc, pass_, None, 0))
 
     # -- embed stage on the device -----------------------------------------------------------------
     def embed_prepare(self):

@@ -89,7 +89,7 @@ static int glue_stc_block_total( const float *rho, int n, int an, double *total 
     for( i = 0; i < used; i++ ) *total += rho[i];
     return used;
 }
-void pcamv_glue_stc_embed( x264_t *h, int an )
+static void glue_stc_embed( x264_t *h, int an, int prepared )
 {
     const int n = h->info.length;
     pcamv_ctx *ctx = pcamv_glue_ctx();
@@ -98,7 +98,7 @@ void pcamv_glue_stc_embed( x264_t *h, int an )
     uint32_t *cols[2] = { NULL, NULL };
     double invalpha, total = 0;
     int shorter = 0, longer = 0, rc, embed = 1;
-    if( on_device )
+    if( on_device && !prepared )
     {
         int dev_n = -1;
         if( pcamv_embed_prepare( ctx, &dev_n ) )
@@ -158,3 +158,6 @@ void pcamv_glue_stc_embed( x264_t *h, int an )
     if( rc == 1 )
         fprintf( stderr, "The syndrome is not in the range of the syndrome matrix.\n" );
 }
+void pcamv_glue_stc_embed( x264_t *h, int an ) { glue_stc_embed( h, an, 0 ); }
+/* pass 1 without the host (pcamv_hook_pass1_on_device): cover and rho_final in h->info are the device's own, already assembled */
+void pcamv_glue_stc_embed_prepared( x264_t *h, int an ) { glue_stc_embed( h, an, 1 ); }

@@ -46,6 +46,8 @@ typedef struct
     int cur_mb, cur_pos;            /* replay cursor */
     int qp_loaded;
     int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
+    int direct;                     /* pass 1 of an embedding frame never reaches the host's macroblock loop (pcamv_hook_pass1_on_device) */
+    int16_t last_mv[16][2]; int have_last_mv; long stale_mismatch;
     int device_forced;              /* the embed stage of this frame ran on the device: pass 2 takes its forced decisions from HBM */
     /* reference frames built on the device (PCAMV_DEVICE_RECON=1): after the final pass of a P frame the GPU reconstructs and
      * deblocks the frame into a free slot, and the next frame finds it resident instead of uploading it */
@@ -57,8 +59,8 @@ typedef struct
     struct { x264_frame_t *fr; int i_frame, i_poc, age, device_built; } slot[PCAMV_MAX_REFS + 2];
     int n_slots, tick;
     /* accounting */
-    double t_gpu, t_total0, t_open;
-    long n_passes, n_replayed;
+    double t_gpu, t_total0, t_open, t_ref_upload, t_recon;
+    long n_passes, n_replayed, n_direct;
 } glue_t;
 
 /* one encoder instance lives on one thread from x264_encoder_open to x264_encoder_close (x264.c Encode), so the glue
@@ -236,6 +238,9 @@ void pcamv_hook_open( x264_t *h )
     if( !g.mbs || !g.log || !g.pass1 )
         die_msg( "out of memory" );
     g.qp_loaded = -1;
+    /* pass 1 on the device alone unless the host's own pass 1 is asked for — or needed, because something is to be checked against it */
+    g.direct = !( ( (s = getenv( "PCAMV_HOST_PASS1" )) && atoi( s ) ) || ( (s = getenv( "PCAMV_HOST_EMBED" )) && atoi( s ) ) ||
+                  ( (s = getenv( "PCAMV_CHECK_EMBED" )) && atoi( s ) ) );
     g.recon_on = (s = getenv( "PCAMV_DEVICE_RECON" )) && atoi( s );
     g.recon_check = (s = getenv( "PCAMV_CHECK_RECON" )) && atoi( s );
     g.t_open = now_s() - g.t_total0;
@@ -251,9 +256,9 @@ void pcamv_hook_close( x264_t *h )
         if( f )
         {
             fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_open\": %.6f, \"t_total\": %.6f, "
-                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld}\n",
+                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld, \"t_ref_upload\": %.6f, \"t_recon\": %.6f, \"direct_pass1\": %ld, \"stale_mismatch\": %ld}\n",
                      g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, g.t_open, now_s() - g.t_total0,
-                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs );
+                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs, g.t_ref_upload, g.t_recon, g.n_direct, g.stale_mismatch );
             fclose( f );
         }
     }
@@ -322,8 +327,12 @@ static int slot_of( x264_frame_t *fr, const int *in_use, int n_in_use )
         die_msg( "no free reference slot" );
     /* the integer plane as the host holds it after deblocking (filtered[0] == plane[0]); the GPU rebuilds borders,
      * half-pel planes and integral image itself and must arrive at the host's own planes bit for bit */
-    if( pcamv_put_ref( g.ctx, best, fr->i_poc, fr->plane[0], fr->plane[1], fr->plane[2], fr->i_stride[0], fr->i_stride[1] ) )
-        die( "pcamv_put_ref" );
+    {
+        double t0 = now_s();
+        if( pcamv_put_ref( g.ctx, best, fr->i_poc, fr->plane[0], fr->plane[1], fr->plane[2], fr->i_stride[0], fr->i_stride[1] ) )
+            die( "pcamv_put_ref" );
+        g.t_ref_upload += now_s() - t0;
+    }
     g.slot[best].fr = fr; g.slot[best].i_frame = fr->i_frame; g.slot[best].i_poc = fr->i_poc; g.slot[best].age = ++g.tick;
     g.slot[best].device_built = 0;
     return best;
@@ -414,6 +423,23 @@ void pcamv_hook_slice_begin( x264_t *h )
         in.filp = h->info.filp;
         in.n_filp = n;
     }
+    if( pass == 2 && g.have_last_mv )
+    {
+        /* the MV cache between the passes is what pass 1 left for its last macroblock: with pass 1 on the device it is put
+         * there from the GPU's record, with the host's own pass 1 the two are compared (stale_mismatch in PCAMV_STATS) */
+        for( i = 0; i < 16; i++ )
+            if( g.direct )
+            {
+                h->mb.cache.mv[0][x264_scan8[i]][0] = g.last_mv[i][0];
+                h->mb.cache.mv[0][x264_scan8[i]][1] = g.last_mv[i][1];
+            }
+            else if( h->mb.cache.mv[0][x264_scan8[i]][0] != g.last_mv[i][0] || h->mb.cache.mv[0][x264_scan8[i]][1] != g.last_mv[i][1] )
+            {
+                g.stale_mismatch++;
+                break;
+            }
+    }
+    g.have_last_mv = 0;
     for( i = 0; i < 16; i++ )
     {
         /* what the MV cache holds before macroblock 0 (the pass-2 "forced skip without cache update" quirk reads it) */
@@ -426,7 +452,68 @@ void pcamv_hook_slice_begin( x264_t *h )
     g.pass = pass;
     g.cur_mb = -1; g.cur_pos = 0;
     g.n_passes++;
+    if( pass == 1 )
+    {
+        memcpy( g.last_mv, g.mbs[g.n_mb - 1].mv, sizeof(g.last_mv) );
+        g.have_last_mv = 1;
+    }
     g.t_gpu += now_s() - t0;
+}
+
+/* Pass 1 of an embedding P frame without the host.  Everything the reference's first slice pass produces for the second one
+ * comes out of the GPU: the decisions and the candidate table (pcamv_analyse_p above), cover / rho_final (pcamv_embed_prepare),
+ * the stego vector and the flips (pcamv_embed_stc).  What is left for the host is what encoder/encoder.c:1826-1855 does around
+ * the trellis — message length, the message bits from rand(), filp[] / num_filp — and h->info.cache[] as analyse.c:3518-3680
+ * would have left it, which the host's pass-2 analysis reads (analyse.c:2658-3105).  Returns 1: x264_slice_write returns
+ * without entering its macroblock loop (no entropy coding, reconstruction or filtering of a pass whose bits are thrown away,
+ * encoder/encoder.c:2380-2390). */
+void pcamv_glue_stc_embed_prepared( x264_t *h, int an );
+int pcamv_hook_pass1_on_device( x264_t *h )
+{
+    int i, n = -1, an;
+    float rate = h->param.eparam.iEmRate;
+    double t0;
+    if( !g.active || g.pass != 1 || !g.direct )
+        return 0;
+    t0 = now_s();
+    if( pcamv_embed_prepare( g.ctx, &n ) )
+        die( "pcamv_embed_prepare" );
+    h->info.length = n;
+    if( n > 0 && pcamv_embed_download( g.ctx, h->info.cover, h->info.rho_final, NULL, NULL, NULL ) )
+        die( "pcamv_embed_download" );
+    memset( h->info.filp, 0, sizeof(h->info.filp) );
+    memset( h->info.stego, 0, sizeof(h->info.stego) );
+    if( rate > 1 ) an = rate;                       /* bits per frame */
+    else an = (int)( rate * h->info.length );       /* bits per motion vector */
+    for( i = 0; i < an; i++ )
+        h->info.message[i] = pcamv_tls_rand() & 0x01;
+    pcamv_glue_stc_embed_prepared( h, an );
+    h->info.num_filp = 0;
+    for( i = 0; i < h->info.length; i++ )
+        if( h->info.cover[i] ^ h->info.stego[i] )
+        {
+            h->info.num_filp++;
+            h->info.filp[i] = 1;
+        }
+    pcamv_hook_embed( h, an );
+    if( pcamv_embed_download( g.ctx, NULL, NULL, NULL, NULL, g.pass1 ) )
+        die( "pcamv_embed_download" );
+    for( i = 0; i < g.n_mb; i++ )
+    {
+        const pcamv_pass1_mb *p = &g.pass1[i];
+        h->info.cache[i].i_type = p->type;
+        h->info.cache[i].i_partition = p->partition;
+        h->info.cache[i].used = p->used;
+        h->info.cache[i].i_qp = h->sh.i_qp;
+        memcpy( h->info.cache[i].i_sub_partition, p->sub, 4 );
+        memcpy( h->info.cache[i].ref, p->ref, 16 );
+        memcpy( h->info.cache[i].mv, p->mv, 64 );
+        memcpy( h->info.cache[i].mv_stego, p->mv_stego, 64 );
+    }
+    g.active = 0;
+    g.n_direct++;
+    g.t_gpu += now_s() - t0;
+    return 1;
 }
 
 /* after x264_macroblock_encode: the macroblocks the device cannot reconstruct on its own (records with early_skip == 2: the host
@@ -481,6 +568,7 @@ void pcamv_hook_slice_end( x264_t *h )
         g.slot[best].age = ++g.tick; g.slot[best].device_built = 1;
         g.recon_frames++;
         g.t_gpu += now_s() - t0;
+        g.t_recon += now_s() - t0;
     }
     g.active = 0;
 }

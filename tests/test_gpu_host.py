@@ -74,6 +74,24 @@ def test_bitstream_identical(pcamv, cuda_lib, case, tmp_path):
     assert os.path.getsize(out) > (1000 if case[1] * case[2] > 20000 else 100)
     assert md5(out) == md5(ref_out), "bitstream differs from the reference (%d vs %d bytes)" % (os.path.getsize(out), os.path.getsize(ref_out))
     assert stats["gpu_launches"] > 0 and stats["replayed_calls"] > 0
+    if "--emrate" in case[7]:
+        # pass 1 of every embedding P frame stayed on the device: the host replayed one pass per frame, not two
+        assert stats["direct_pass1"] > 0 and stats["p_passes"] == 2 * stats["direct_pass1"], stats
+
+
+HOST_PASS1 = [c for c in CASES if c[0] in ("cif_hex5", "cif_umh5_ref3", "cif_dia2_lownoise", "cif_p4x4_umh_ref3", "cif_qp48_skips", "cif_nocabac",
+                                           "tiny_48x32", "cif_fixed_bits", "720p_umh5")]
+
+
+@pytest.mark.parametrize("case", HOST_PASS1, ids=[c[0] for c in HOST_PASS1])
+def test_bitstream_identical_with_host_pass1(pcamv, cuda_lib, case, tmp_path):
+    """PCAMV_HOST_PASS1=1: the host walks the macroblocks of pass 1 as the reference does (replaying the GPU's results), and the
+    embed stage built on the device is checked against the host's own cover / rho_final (PCAMV_CHECK_EMBED=1).  Also checks the one
+    piece of host state that pass 1 hands to pass 2 outside h->info — the MV cache of its last macroblock (quirk q2) — against
+    what the device-only pass 1 would have put there."""
+    ref_out, out, stats = encode_pair(pcamv, *case, workdir=str(tmp_path), extra_env={"PCAMV_HOST_PASS1": "1", "PCAMV_CHECK_EMBED": "1"})
+    assert md5(out) == md5(ref_out)
+    assert stats["direct_pass1"] == 0 and stats["stale_mismatch"] == 0, stats
 
 
 @pytest.mark.parametrize("case", [CASES[1], CASES[2]], ids=[CASES[1][0], CASES[2][0]])

@@ -43,8 +43,8 @@ def check_dump(pcamv, dump):
                                  stale_mv=m1["mv"][-1].copy(), **kw)
             final = 2
         else:
-            m, _ = ctx.analyse_p(0, refs, pocs, x["cur_poc"], **kw)
-            final = 0
+            final = s.pass_
+            m, _ = ctx.analyse_p(final, refs, pocs, x["cur_poc"], **kw)
         if (m["early_skip"] == 2).any():
             n["q1_frames"] += 1          # needs the host's patches: covered through the bound host below
             continue

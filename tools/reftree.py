@@ -103,13 +103,16 @@ def compile_tree(tree, exe, extra_sources=(), extra_cflags=(), extra_ldflags=(),
     return exe
 
 
-def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra="", drop_real=False):
+def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra="", drop_real=False, pass1_on_device=False):
     """The anchored edits both instrumented builds share: calls to pcamv_hook_* at the frame-level points, the search
     entry points renamed *_real (the hook file defines the originals' names), and a wrapper in front of
     x264_ih_get_mv_cost.  (file:line of the reference in oracle/ref_hooks.c / host/pcamv_x264_glue.c.)
     drop_real: the GPU host never calls the reference's own searches, so there the renamed originals become unused statics
     and the compiler drops them (and refine_subpel with them) — `nm x264_pcamv` then shows no CPU search code at all; the
-    instrumented oracle keeps them (its hooks time and count the real functions)."""
+    instrumented oracle keeps them (its hooks time and count the real functions).
+    pass1_on_device: x264_slice_write returns right after the slice-begin hook when the hook says the first pass of an embedding
+    frame is complete without the host (int pcamv_hook_pass1_on_device( x264_t * )); x264_slices_write then finds no NAL unit of
+    that pass and must not index nal[-1] (encoder/encoder.c:2091)."""
     p = os.path.join(tree, "encoder/encoder.c")
     t = read(p)
     t = sub_exact(t, r'(#include "common/common.h"\n)', r"\1" + hook_decl.replace("\\", "\\\\"), 1, "encoder.c include")
@@ -117,7 +120,10 @@ def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra="", drop_rea
     idx = t.index("    mbcmp_init( h );")
     t = t[:idx] + "    mbcmp_init( h ); pcamv_hook_open( h );" + t[idx + len("    mbcmp_init( h );"):]
     t = sub_exact(t, r"(    /\* init stats \*/\n    memset\( &h->stat\.frame, 0, sizeof\(h->stat\.frame\) \);)",
-                  r"\1 pcamv_hook_slice_begin( h );", 1, "slice begin")
+                  r"\1 pcamv_hook_slice_begin( h );" + (" if( pcamv_hook_pass1_on_device( h ) ) return;" if pass1_on_device else ""), 1, "slice begin")
+    if pass1_on_device:
+        t = sub_exact(t, r"i_frame_size = h->out\.nal\[h->out\.i_nal-1\]\.i_payload;",
+                      "i_frame_size = h->out.i_nal ? h->out.nal[h->out.i_nal-1].i_payload : 0;", 1, "frame size of an empty pass")
     t = sub_exact(t, r"\n(\t\tx264_macroblock_analyse\( h \);)",
                   r"\n\t\tpcamv_hook_analyse_begin( h ); x264_macroblock_analyse( h ); pcamv_hook_analyse_end( h );", 1, "analyse call")
     # right after the macroblock has been reconstructed in h->mb.pic.p_fdec (encoder/encoder.c:1881), before anything filters it

@@ -224,8 +224,16 @@ def main():
                          extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c")],
                          extra_cflags=["-I" + os.path.join(ROOT, "include")],
                          extra_ldflags=["-L" + PKG, "-lpcamv_cuda", "-Wl,-rpath,$ORIGIN/../../video-steganography-pcamv_b200"])
-    shutil.rmtree(tree)
     print("build_host: built", exe)
+    if "--profile" in sys.argv[1:]:
+        # gprof twin (same flags + -pg): where a single-stream encode spends its HOST time; writes gmon.out into the cwd
+        exe_pg = os.path.join(OUT, "x264_pcamv_pg")
+        reftree.compile_tree(tree, exe_pg,
+                             extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c")],
+                             extra_cflags=["-I" + os.path.join(ROOT, "include"), "-pg", "-fno-omit-frame-pointer"],
+                             extra_ldflags=["-pg", "-L" + PKG, "-lpcamv_cuda", "-Wl,-rpath,$ORIGIN/../../video-steganography-pcamv_b200"])
+        print("build_host: built", exe_pg)
+    shutil.rmtree(tree)
     return 0
 
 

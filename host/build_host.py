@@ -206,6 +206,20 @@ def shard_driver(tree):
     reftree.write(p, t)
 
 
+def stats_only_intra(tree):
+    """Intra macroblocks are disabled in P slices (the COPY2_IF_LT that would pick them is commented out, encoder/analyse.c:2863;
+    SURVEY fact 10): the intra analysis of a P macroblock (analyse.c:2812-2825) only feeds frame statistics — except that its
+    predictions stay in the fdec scratch block, which the macroblocks of quirk q1 are coded against.  The host runs it for those
+    (the GPU's records name them: early_skip == 2) and skips it for the others; PCAMV_HOST_INTRA=1 runs it everywhere."""
+    p = os.path.join(tree, "encoder/analyse.c")
+    t = reftree.read(p)
+    t = reftree.sub_exact(t, r"\n            if\( h->mb\.b_chroma_me \)\n            \{\n([^\n]*\n)                x264_mb_analyse_intra_chroma\( h, &analysis \);",
+                          r"\n            if( !pcamv_hook_want_intra( h ) ) analysis.i_satd_i16x16 = i_cost;\n            else if( h->mb.b_chroma_me )\n            {\n\1                x264_mb_analyse_intra_chroma( h, &analysis );",
+                          1, "P-slice intra analysis")
+    t = t.replace("void pcamv_hook_open( x264_t *h );", "int pcamv_hook_want_intra( x264_t *h ); void pcamv_hook_open( x264_t *h );", 1)
+    reftree.write(p, t)
+
+
 def main():
     if not os.path.isdir(reftree.REF):
         print("build_host: %s not present; keeping prebuilt host/_build/ as is" % reftree.REF)
@@ -219,6 +233,7 @@ def main():
     reftree.widen(tree)
     reftree.hook_call_sites(tree, HOOK_DECL, IH_WRAPPER, analyse_extra=ANALYSE_EXTRA, drop_real=True, pass1_on_device=True)
     shard_driver(tree)
+    stats_only_intra(tree)
     exe = os.path.join(OUT, "x264_pcamv")
     reftree.compile_tree(tree, exe,
                          extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c")],

@@ -46,6 +46,7 @@ typedef struct
     int cur_mb, cur_pos;            /* replay cursor */
     int qp_loaded;
     int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
+    int host_intra;                 /* PCAMV_HOST_INTRA=1: intra analysis of every P macroblock, as the reference does for its statistics */
     int direct;                     /* pass 1 of an embedding frame never reaches the host's macroblock loop (pcamv_hook_pass1_on_device) */
     int16_t last_mv[16][2]; int have_last_mv; long stale_mismatch;
     int device_forced;              /* the embed stage of this frame ran on the device: pass 2 takes its forced decisions from HBM */
@@ -241,6 +242,7 @@ void pcamv_hook_open( x264_t *h )
     /* pass 1 on the device alone unless the host's own pass 1 is asked for — or needed, because something is to be checked against it */
     g.direct = !( ( (s = getenv( "PCAMV_HOST_PASS1" )) && atoi( s ) ) || ( (s = getenv( "PCAMV_HOST_EMBED" )) && atoi( s ) ) ||
                   ( (s = getenv( "PCAMV_CHECK_EMBED" )) && atoi( s ) ) );
+    g.host_intra = (s = getenv( "PCAMV_HOST_INTRA" )) && atoi( s );
     g.recon_on = (s = getenv( "PCAMV_DEVICE_RECON" )) && atoi( s );
     g.recon_check = (s = getenv( "PCAMV_CHECK_RECON" )) && atoi( s );
     g.t_open = now_s() - g.t_total0;
@@ -458,6 +460,12 @@ void pcamv_hook_slice_begin( x264_t *h )
         g.have_last_mv = 1;
     }
     g.t_gpu += now_s() - t0;
+}
+
+/* P slices: is the intra analysis of this macroblock more than a statistic?  (host/build_host.py stats_only_intra) */
+int pcamv_hook_want_intra( x264_t *h )
+{
+    return !g.active || g.host_intra || g.mbs[h->mb.i_mb_xy].early_skip == 2;
 }
 
 /* Pass 1 of an embedding P frame without the host.  Everything the reference's first slice pass produces for the second one

@@ -634,7 +634,12 @@ def encoder_job_leg(pcamv, name, rank, world, local_rank, barrier):
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
     barrier()
-    t_max, t_enc_max = shard.max_over_ranks([t_all, t_enc])
+    # inside the encoder processes (PCAMV_STATS of every shard): the slowest shard's lifetime without / with CUDA start-up
+    st = [r["stats"] for r in recs if r.get("stats")]
+    loop = max([s_["t_total"] - s_["t_open"] for s_ in st] or [0.0])
+    t_open = max([s_["t_open"] for s_ in st] or [0.0])
+    gpu_share = max([s_["t_gpu_calls"] / max(s_["t_total"] - s_["t_open"], 1e-9) for s_ in st] or [0.0])
+    t_max, t_enc_max, loop_max, open_max, gpu_share_max = shard.max_over_ranks([t_all, t_enc, loop, t_open, gpu_share])
     if rank != 0:
         return None
     n = job["shards"]
@@ -645,14 +650,17 @@ def encoder_job_leg(pcamv, name, rank, world, local_rank, barrier):
     frames = n * job["shard_frames"]
     return {"job": name, "what": job["what"], "args": " ".join(encjob.job_args(job)), "frames": frames, "shards": n, "ranks": world,
             "encode_embed_fps": frames / t_max, "seconds": t_max, "seconds_encode_only": t_enc_max, "seconds_gather": t_max - t_enc_max,
+            "encode_loop_fps": frames / loop_max if loop_max > 0 else None, "seconds_encode_loop": loop_max, "seconds_cuda_startup": open_max,
+            "gpu_call_share_of_encoder_thread": gpu_share_max,
             "bitstream_identical": bool(ok_bits), "payload_identical": ok_pay,
             "payload_bits": int(sum(g["n_bits"] for g in gathered)), "bytes": int(sum(g["bytes"] for g in gathered)),
             "reference_fps": ref["fps"], "reference_cores": ref["cores"], "reference_seconds": ref["seconds"],
+            "reference_source": ref.get("source", "per-shard runs of oracle/_ref/x264_wide on this box's host cores"),
             "scaling": "strong (the job is fixed, shards are dealt round-robin to the ranks)",
             "gather": "shard.gather_gop_results (NCCL all_gather x3) of payload bits + statistics + digests, inside the timed region" if world > 1
                       else "single rank: no collective",
             "note": "wall clock of the slowest rank's x264_pcamv process (process start, CUDA context creation and encoder open included) plus the "
-                    "gather; reference = oracle/_ref/x264_wide (the reference's C sources, no asm), one single-threaded process per shard on the host cores"}
+                    "gather; encode_loop_fps = the same job without the slowest shard's pcamv_open (CUDA initialisation, 0.8 - 2.8 s on these boxes); reference = oracle/_ref/x264_wide (the reference's C sources, no asm), one single-threaded process per shard on the host cores"}
 
 
 if __name__ == "__main__":

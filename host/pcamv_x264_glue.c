@@ -47,6 +47,8 @@ typedef struct
     int qp_loaded;
     int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
     int host_intra;                 /* PCAMV_HOST_INTRA=1: intra analysis of every P macroblock, as the reference does for its statistics */
+    int stream_rows, rows_ready, mb_h;      /* the replayed pass is consumed row by row while the kernel runs (PCAMV_NO_ROW_STREAM=1: wait for its end) */
+    double t_row_wait;
     int direct;                     /* pass 1 of an embedding frame never reaches the host's macroblock loop (pcamv_hook_pass1_on_device) */
     int16_t last_mv[16][2]; int have_last_mv; long stale_mismatch;
     int device_forced;              /* the embed stage of this frame ran on the device: pass 2 takes its forced decisions from HBM */
@@ -243,6 +245,8 @@ void pcamv_hook_open( x264_t *h )
     g.direct = !( ( (s = getenv( "PCAMV_HOST_PASS1" )) && atoi( s ) ) || ( (s = getenv( "PCAMV_HOST_EMBED" )) && atoi( s ) ) ||
                   ( (s = getenv( "PCAMV_CHECK_EMBED" )) && atoi( s ) ) );
     g.host_intra = (s = getenv( "PCAMV_HOST_INTRA" )) && atoi( s );
+    g.mb_h = h->sps->i_mb_height;
+    g.stream_rows = g.pinned && !( (s = getenv( "PCAMV_NO_ROW_STREAM" )) && atoi( s ) );
     g.recon_on = (s = getenv( "PCAMV_DEVICE_RECON" )) && atoi( s );
     g.recon_check = (s = getenv( "PCAMV_CHECK_RECON" )) && atoi( s );
     g.t_open = now_s() - g.t_total0;
@@ -254,13 +258,17 @@ void pcamv_hook_close( x264_t *h )
     (void)h;
     if( s && *s )
     {
-        FILE *f = fopen( s, "w" );
+        char path[1200];
+        FILE *f;
+        if( g_shard >= 0 ) snprintf( path, sizeof(path), "%s.%d", s, g_shard );     /* one file per shard, like the side files */
+        else snprintf( path, sizeof(path), "%s", s );
+        f = fopen( path, "w" );
         if( f )
         {
             fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_open\": %.6f, \"t_total\": %.6f, "
-                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld, \"t_ref_upload\": %.6f, \"t_recon\": %.6f, \"direct_pass1\": %ld, \"stale_mismatch\": %ld}\n",
+                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld, \"t_ref_upload\": %.6f, \"t_recon\": %.6f, \"direct_pass1\": %ld, \"stale_mismatch\": %ld, \"t_row_wait\": %.6f}\n",
                      g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, g.t_open, now_s() - g.t_total0,
-                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs, g.t_ref_upload, g.t_recon, g.n_direct, g.stale_mismatch );
+                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs, g.t_ref_upload, g.t_recon, g.n_direct, g.stale_mismatch, g.t_row_wait );
             fclose( f );
         }
     }
@@ -448,7 +456,16 @@ void pcamv_hook_slice_begin( x264_t *h )
         in.stale_mv[i][0] = h->mb.cache.mv[0][x264_scan8[i]][0];
         in.stale_mv[i][1] = h->mb.cache.mv[0][x264_scan8[i]][1];
     }
-    if( g_group ? pcamv_group_analyse_p( g_group, g.ctx, &in, g.mbs, g.log ) : pcamv_analyse_p( g.ctx, &in, g.mbs, g.log ) )
+    /* the pass the host replays (0 or 2): return as soon as the launch is in flight and follow the wavefront row by row
+     * (pcamv_hook_analyse_begin); pass 1 is consumed whole, by the embed stage */
+    g.rows_ready = g.mb_h;
+    if( g.stream_rows && pass != 1 )
+    {
+        if( g_group ? pcamv_group_analyse_p_begin( g_group, g.ctx, &in, g.mbs, g.log ) : pcamv_analyse_p_begin( g.ctx, &in, g.mbs, g.log ) )
+            die( "pcamv_analyse_p_begin" );
+        g.rows_ready = 0;
+    }
+    else if( g_group ? pcamv_group_analyse_p( g_group, g.ctx, &in, g.mbs, g.log ) : pcamv_analyse_p( g.ctx, &in, g.mbs, g.log ) )
         die( "pcamv_analyse_p" );
     g.active = 1;
     g.pass = pass;
@@ -555,6 +572,8 @@ void pcamv_hook_encoded( x264_t *h )
 
 void pcamv_hook_slice_end( x264_t *h )
 {
+    if( g.active && g.rows_ready < g.mb_h && pcamv_analyse_p_rows( g.ctx, g.mb_h - 1, &g.rows_ready ) )     /* (every row is collected before the context's next call) */
+        die( "pcamv_analyse_p_rows" );
     if( g.active && g.recon_on && g.pass != 1 && h->sh.i_type == SLICE_TYPE_P && h->fdec->b_kept_as_ref )
     {
         /* the frame just analysed in its final pass becomes a reference: build it on the GPU, in the least recently used slot
@@ -588,6 +607,15 @@ void pcamv_hook_analyse_begin( x264_t *h )
     {
         g.cur_mb = h->mb.i_mb_xy;
         g.cur_pos = 0;
+        if( h->mb.i_mb_y >= g.rows_ready )
+        {
+            /* the wavefront has not been seen to finish this row yet: wait for it (rows arrive in order, behind the kernel) */
+            double t0 = now_s();
+            if( pcamv_analyse_p_rows( g.ctx, h->mb.i_mb_y, &g.rows_ready ) )
+                die( "pcamv_analyse_p_rows" );
+            g.t_gpu += now_s() - t0;
+            g.t_row_wait += now_s() - t0;
+        }
     }
 }
 

@@ -275,6 +275,21 @@ void pcamv_group_destroy(pcamv_group *g);
 int pcamv_group_analyse_p(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log);
 int pcamv_group_leave(pcamv_group *g);
 
+/* Results while the wavefront is still running.  The host that replays a P slice (host/pcamv_x264_glue.c) walks the macroblocks
+ * in raster order, as x264_slice_write does (encoder/encoder.c:1240-2010), and needs row r only when it gets there; the
+ * wavefront finishes row r after (mb_w + 2 r) of its (mb_w + 2 mb_h) steps.  pcamv_analyse_p_begin / _batch_begin /
+ * pcamv_group_analyse_p_begin are pcamv_analyse_p / _batch / pcamv_group_analyse_p without the wait for the end of the kernel
+ * and without the download: they return once the launch is in flight.  pcamv_analyse_p_rows( ctx, row, &n ) then blocks until
+ * the records and log entries of rows 0..row are in the buffers given to _begin (n = rows complete so far, >= row + 1) — a
+ * second stream follows the kernel's row counters and copies finished rows out behind it.  mbs / log must be page-locked
+ * (pcamv_host_alloc) and stay untouched by the caller until their rows are reported.  Every row must be collected (row =
+ * mb_h - 1 at the latest) before the context's next call; meant for the pass whose results the host replays (0 or 2). */
+int pcamv_analyse_p_begin(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log);
+int pcamv_analyse_p_batch_begin(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *ins, int n,
+                                pcamv_mb_out *const *mbs, pcamv_log_entry *const *logs);
+int pcamv_group_analyse_p_begin(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log);
+int pcamv_analyse_p_rows(pcamv_ctx *ctx, int row, int *rows_ready);
+
 /* Profiling aid: with enable != 0 the next wavefront launches record the device globaltimer (ns) at the start and end
  * of every macroblock; out (may be NULL) receives the [n_mb][2] records of the last traced launch. */
 int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out);

@@ -97,6 +97,64 @@ def test_batch_launch_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):
         c.close()
 
 
+@pytest.mark.parametrize("rows_per_cta", [1, 4, -1], ids=["rows-1", "row-groups-4", "row-pool"])
+def test_rows_behind_the_wavefront_equal_the_download(pcamv, cuda_lib, rows_per_cta, tmp_path):
+    """pcamv_analyse_p_begin / _batch_begin + pcamv_analyse_p_rows: the records and log entries copied out row by row while
+    the kernel is still running are the ones the blocking call downloads at its end — one context, and three contexts
+    (different frames) in one launch.  Repeated, so that a poll of the row counters that saw the previous launch's final values
+    would show as rows reported early with stale contents."""
+    import frame_parity
+    dump = pcamv.dumpfmt.Dump(refrun.golden_dump_path("qcif_hex5", str(tmp_path)))
+    units = [u for u in dump.slice_units() if u["slice"].with_planes and u["slice"].pass_ == 1][:3]
+    ctxs, args, single, outs = [], [], [], []
+    for u in units:
+        s, x = u["slice"], u["ctx"]
+        H, W = s.lines_y, s.width
+        c = frame_parity.open_ctx(pcamv, dump, s, rows_per_cta=rows_per_cta)
+        c.put_fenc(s.fenc[0][:, :W], s.fenc[1][:, :W // 2], s.fenc[2][:, :W // 2])
+        for slot, r in enumerate(s.refs):
+            c.put_ref(slot, r["poc"], r["luma"][0][32:32 + H, 32:32 + W], r["u"][16:16 + H // 2, 16:16 + W // 2],
+                      r["v"][16:16 + H // 2, 16:16 + W // 2])
+        kw = dict(col_n_ref=x["col_n_ref"], col_inv_ref_poc=x["col_inv_ref_poc"], col_ref8=x["col_ref8"], col_mv4=x["col_mv4"])
+        a = (0, list(range(x["n_ref"])), x["ref_poc"][:x["n_ref"]], x["cur_poc"], kw)          # pass 0: the single pass of a frame without embedding
+        m, l = c.analyse_p(a[0], a[1], a[2], a[3], **kw)
+        single.append((m.copy(), l.copy()))
+        ctxs.append(c); args.append(a); outs.append(c.alloc_outputs(pinned=True))
+    mb_h = units[0]["slice"].lines_y // 16
+    mb_w = units[0]["slice"].width // 16
+
+    def same(got, want, rows):
+        m0, l0 = want
+        m1, l1 = got
+        n_mb = rows * mb_w
+        assert m0[:n_mb].tobytes() == m1[:n_mb].tobytes()
+        for mb in range(n_mb):
+            n = int(m0["n_log"][mb])
+            assert l0[mb, :n].tobytes() == l1[mb, :n].tobytes()
+    for rep in range(3):
+        # one context: ask for every row in turn; whatever is reported complete must already be final
+        c, a, o = ctxs[rep % 3], args[rep % 3], outs[rep % 3]
+        o[0][:] = 0; o[1][:] = 0
+        c.analyse_p_begin(a[0], a[1], a[2], a[3], o, **a[4])
+        for r in range(mb_h):
+            n = c.analyse_p_rows(r)
+            assert r + 1 <= n <= mb_h
+            same(o, single[rep % 3], n)
+        # three contexts, one launch
+        for o in outs:
+            o[0][:] = 0; o[1][:] = 0
+        pcamv.host.analyse_p_batch_begin(ctxs, args, outs)
+        for r in (0, mb_h // 2, mb_h - 1):
+            for c, o, w in zip(ctxs, outs, single):
+                n = c.analyse_p_rows(r)
+                assert n >= r + 1
+                same(o, w, n)
+    with pytest.raises(pcamv.host.PcamvError):
+        ctxs[0].frame_upload(a[0], a[1], a[2], a[3], **a[4]); ctxs[0].analyse_p_rows(0)       # nothing in flight
+    for c in ctxs:
+        c.close()
+
+
 @pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/x264_dump not built")
 @pytest.mark.parametrize("rows_per_cta", [4, -1, -2], ids=["row-groups-4", "row-pool", "split"])
 def test_batch_pass2_equals_single(pcamv, cuda_lib, rows_per_cta, tmp_path):

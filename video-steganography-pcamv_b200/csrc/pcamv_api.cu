@@ -159,6 +159,8 @@ extern "C" void pcamv_close(pcamv_ctx *ctx)
     cudaFree(ctx->fa.type); cudaFree(ctx->fa.ref8); cudaFree(ctx->fa.mv4); cudaFree(ctx->fa.mvr);
     cudaFree(ctx->d_col_ref8); cudaFree(ctx->d_col_mv4); cudaFree(ctx->d_forced); cudaFree(ctx->d_log);
     cudaFree(ctx->d_mb_results); cudaFree(ctx->d_progress); cudaFree(ctx->d_trace); cudaFree(ctx->d_mvsads); cudaFree(ctx->d_seam_mvsads); cudaFree(ctx->d_stc); cudaFree(ctx->d_subparts); cudaFree(ctx->d_batch); cudaFree(ctx->d_batch_claim); cudaFree(ctx->d_split); cudaFree(ctx->d_emb); cudaFree(ctx->d_stc_io); cudaFree(ctx->d_recon_nnz); cudaFree(ctx->d_recon_patches);
+    if (ctx->h_progress) cudaFreeHost(ctx->h_progress);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
     if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
     if (ctx->h_calls) cudaFreeHost(ctx->h_calls);

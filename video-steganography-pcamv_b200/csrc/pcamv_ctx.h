@@ -58,6 +58,12 @@ struct pcamv_ctx
     pcamv::FrameParams fp[3] = {};             // parameters of the last uploaded frame, per pass (0 / 1 / 2)
     bool frame_ready[3] = { false, false, false }, frame_cost_table = false;
     int frame_last = -1;
+    // results while the wavefront is still running (pcamv_analyse_p_begin / pcamv_analyse_p_rows): a second stream polls the
+    // row counters and copies finished macroblock rows out behind the kernel
+    cudaStream_t side = nullptr; int *h_progress = nullptr;
+    cudaStream_t sr_kstream = nullptr;         // the stream the kernel was launched on (the leader's, for a multi-context launch)
+    pcamv_mb_out *sr_mbs = nullptr; pcamv_log_entry *sr_log = nullptr;
+    int sr_rows = 0; bool sr_active = false;   // rows already in the caller's buffers; an analysis is being streamed
 };
 
 namespace pcamv {

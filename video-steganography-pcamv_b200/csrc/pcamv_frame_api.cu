@@ -5,6 +5,7 @@
 #include <stddef.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 #include <vector>
 #include "pcamv_ctx.h"
 #include "pcamv_glue.h"
@@ -137,6 +138,10 @@ static int frame_upload_async(pcamv_ctx *ctx, const pcamv_frame_in *in)
     fp.mvsads = ctx->d_mvsads; fp.mvsads_cap = ctx->mvsads_cap;
     fp.subparts = ctx->d_subparts;
     fp.log = ctx->d_log; fp.log_stride = ctx->log_stride; fp.results = ctx->d_mb_results; fp.row_progress = ctx->d_progress;
+    // the row counters are cleared here already (the launch clears them again): whoever polls them between upload and launch
+    // (pcamv_analyse_p_rows) must never see the previous pass's final values
+    ctx->sr_active = false; ctx->sr_rows = 0;
+    CK(cudaMemsetAsync(ctx->d_progress, 0, (2 * fc.mb_h + 2) * sizeof(int), ctx->stream));
     if (in->pass == 1) { ctx->frame_cost_table = in->cost_table != 0; ctx->emb_state = 0; }
     ctx->frame_last = in->pass;
     return 0;
@@ -443,16 +448,15 @@ extern "C" int pcamv_frame_run_batch(pcamv_ctx *const *ctxs, int n, int pass, in
     return 0;
 }
 
-extern "C" int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *ins, int n,
-                                     pcamv_mb_out *const *mbs, pcamv_log_entry *const *logs)
+// upload + launch of a multi-context pass; on return the kernel is in flight on ctxs[0]'s stream and every member's own stream
+// waits for it
+static int batch_begin(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *ins, int n)
 {
-    if (!ctxs || !ins || !mbs || n <= 0 || !ctxs[0]) return -1;
     pcamv_ctx *ctx = ctxs[0];
-    GUARD();
     // every member stages and copies on its own stream, all in flight together
     for (int i = 0; i < n; i++)
     {
-        if (!ctxs[i] || !ins[i] || !mbs[i]) return ctx_fail(ctx, "pcamv_analyse_p_batch: null member", cudaSuccess);
+        if (!ctxs[i] || !ins[i]) return ctx_fail(ctx, "pcamv_analyse_p_batch: null member", cudaSuccess);
         if (ctxs[i]->failed) return ctx_fail(ctx, "pcamv_analyse_p_batch: a member context has failed", cudaSuccess);
         if (ins[i]->pass != ins[0]->pass) return ctx_fail(ctx, "pcamv_analyse_p_batch: all frames of a launch must be in the same pass", cudaSuccess);
         if (frame_upload_async(ctxs[i], ins[i]))
@@ -467,15 +471,110 @@ extern "C" int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_i
     if (launch_batch(ctxs, n, ins[0]->pass, nullptr)) return -1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     for (int i = 0; i < n; i++)
-    {
         if (ctxs[i] != ctx) CK(cudaStreamWaitEvent(ctxs[i]->stream, ctx->ev1, 0));
+    return 0;
+}
+
+extern "C" int pcamv_analyse_p_batch(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *ins, int n,
+                                     pcamv_mb_out *const *mbs, pcamv_log_entry *const *logs)
+{
+    if (!ctxs || !ins || !mbs || n <= 0 || !ctxs[0]) return -1;
+    pcamv_ctx *ctx = ctxs[0];
+    GUARD();
+    for (int i = 0; i < n; i++)
+        if (!mbs[i]) return ctx_fail(ctx, "pcamv_analyse_p_batch: null member", cudaSuccess);
+    if (batch_begin(ctxs, ins, n)) return -1;
+    for (int i = 0; i < n; i++)
         if (frame_download_async(ctxs[i], mbs[i], logs ? logs[i] : nullptr))
             return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
-    }
     for (int i = 0; i < n; i++)
         if (frame_download_finish(ctxs[i], mbs[i], logs ? logs[i] : nullptr))
             return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
     return split_check(ctx);
+}
+
+// ---- results while the wavefront is still running --------------------------------------------------------------------------
+// The host that replays a P slice walks its macroblocks in raster order and needs row r only when it gets there, while the
+// wavefront finishes row r at (mb_w + 2 r) / (mb_w + 2 mb_h) of its run: pcamv_analyse_p_begin returns once the kernel is in
+// flight, pcamv_analyse_p_rows( row ) blocks until rows 0..row are in the caller's (page-locked) buffers.  A second stream reads
+// the row counters the kernel publishes (release at GPU scope after a row's records are written, pcamv_frame_kernels.cu) and
+// copies finished rows out behind it; records and log of a finished row are never written again.
+static int stream_arm(pcamv_ctx *ctx, cudaStream_t kstream, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    if (!mbs || !is_pinned(mbs) || (log && !is_pinned(log)))
+        return ctx_fail(ctx, "pcamv_analyse_p_begin: the result buffers must be page-locked (pcamv_host_alloc)", cudaSuccess);
+    if (!ctx->side)
+    {
+        CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+        CK(cudaMallocHost(&ctx->h_progress, ctx->fc.mb_h * sizeof(int)));
+    }
+    ctx->sr_kstream = kstream; ctx->sr_mbs = mbs; ctx->sr_log = log; ctx->sr_rows = 0; ctx->sr_active = true;
+    return 0;
+}
+
+extern "C" int pcamv_analyse_p_begin(pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    GUARD();
+    if (!in || !mbs) return ctx_fail(ctx, "pcamv_analyse_p_begin: null argument", cudaSuccess);
+    if (pcamv_frame_upload(ctx, in)) return -1;
+    if (launch_frame(ctx, in->pass)) return -1;
+    return stream_arm(ctx, ctx->stream, mbs, log);
+}
+
+extern "C" int pcamv_analyse_p_batch_begin(pcamv_ctx *const *ctxs, const pcamv_frame_in *const *ins, int n,
+                                           pcamv_mb_out *const *mbs, pcamv_log_entry *const *logs)
+{
+    if (!ctxs || !ins || !mbs || n <= 0 || !ctxs[0]) return -1;
+    pcamv_ctx *ctx = ctxs[0];
+    GUARD();
+    if (batch_begin(ctxs, ins, n)) return -1;
+    for (int i = 0; i < n; i++)
+        if (stream_arm(ctxs[i], ctx->stream, mbs[i], logs ? logs[i] : nullptr))
+            return ctxs[i] == ctx ? -1 : ctx_fail(ctx, pcamv_last_error(ctxs[i]), cudaSuccess);
+    return 0;
+}
+
+extern "C" int pcamv_analyse_p_rows(pcamv_ctx *ctx, int row, int *rows_ready)
+{
+    GUARD();
+    const int mb_w = ctx->fc.mb_w, mb_h = ctx->fc.mb_h;
+    if (!ctx->sr_active && ctx->sr_rows < mb_h)
+        return ctx_fail(ctx, "pcamv_analyse_p_rows: no analysis started with pcamv_analyse_p_begin is in flight", cudaSuccess);
+    if (row >= mb_h) row = mb_h - 1;
+    while (ctx->sr_rows <= row)
+    {
+        // the kernel's state BEFORE the look at the counters: once it has ended they are final
+        const cudaError_t q = cudaStreamQuery(ctx->sr_kstream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return ctx_fail(ctx, "pcamv_analyse_p_rows: the wavefront launch failed", q);
+        CK(cudaMemcpyAsync(ctx->h_progress, ctx->d_progress, mb_h * sizeof(int), cudaMemcpyDeviceToHost, ctx->side));
+        CK(cudaStreamSynchronize(ctx->side));
+        int r = ctx->sr_rows;
+        while (r < mb_h && ctx->h_progress[r] >= mb_w) r++;
+        if (r > ctx->sr_rows)
+        {
+            const size_t first = (size_t)ctx->sr_rows * mb_w, cnt = (size_t)(r - ctx->sr_rows) * mb_w;
+            CK(cudaMemcpyAsync(ctx->sr_mbs + first, ctx->d_mb_results + first, cnt * sizeof(MbResult), cudaMemcpyDeviceToHost, ctx->side));
+            if (ctx->sr_log)
+                CK(cudaMemcpyAsync(ctx->sr_log + first * ctx->log_stride, ctx->d_log + first * ctx->log_stride,
+                                   cnt * ctx->log_stride * sizeof(LogEntry), cudaMemcpyDeviceToHost, ctx->side));
+            CK(cudaStreamSynchronize(ctx->side));
+            ctx->sr_rows = r;
+        }
+        else if (q == cudaSuccess)
+            return ctx_fail(ctx, "pcamv_analyse_p_rows: the wavefront kernel ended without finishing the frame", cudaSuccess);
+        else
+        {
+            struct timespec ts = { 0, 20000 };       // the next row is ~0.3 ms away: do not burn the core the other encoder threads need
+            nanosleep(&ts, nullptr);
+        }
+    }
+    if (ctx->sr_rows >= mb_h && ctx->sr_active)
+    {
+        ctx->sr_active = false;
+        if (split_check(ctx)) return -1;
+    }
+    if (rows_ready) *rows_ready = ctx->sr_rows;
+    return 0;
 }
 
 // ---- encoder groups: several encoder threads of one process (GOP shards / streams), one GPU launch per step --------------
@@ -496,6 +595,7 @@ struct pcamv_group
     std::vector<pcamv_mb_out *> mbs;
     std::vector<pcamv_log_entry *> logs;
     std::vector<int *> rcs;
+    std::vector<int> begin_only;       // member asked for pcamv_group_analyse_p_begin: launch, arm the row streaming, no download
     std::string err;
 };
 
@@ -521,26 +621,28 @@ static void group_launch(pcamv_group *g)
         std::vector<pcamv_ctx *> c; std::vector<const pcamv_frame_in *> in; std::vector<pcamv_mb_out *> mb; std::vector<pcamv_log_entry *> lg;
         std::vector<int> idx;
         for (int k = i; k < n; k++)
-            if (!done[k] && g->ins[k]->pass == g->ins[i]->pass)
+            if (!done[k] && g->ins[k]->pass == g->ins[i]->pass && g->begin_only[k] == g->begin_only[i])
             {
                 c.push_back(g->ctxs[k]); in.push_back(g->ins[k]); mb.push_back(g->mbs[k]); lg.push_back(g->logs[k]);
                 idx.push_back(k); done[k] = 1;
             }
-        const int rc = pcamv_analyse_p_batch(c.data(), in.data(), (int)c.size(), mb.data(), lg.data());
+        const int rc = g->begin_only[i] ? pcamv_analyse_p_batch_begin(c.data(), in.data(), (int)c.size(), mb.data(), lg.data())
+                                        : pcamv_analyse_p_batch(c.data(), in.data(), (int)c.size(), mb.data(), lg.data());
         if (rc) g->err = pcamv_last_error(c[0]);
         for (int k : idx) *g->rcs[k] = rc;
     }
-    g->ctxs.clear(); g->ins.clear(); g->mbs.clear(); g->logs.clear(); g->rcs.clear();
+    g->ctxs.clear(); g->ins.clear(); g->mbs.clear(); g->logs.clear(); g->rcs.clear(); g->begin_only.clear();
     g->n_arrived = 0;
     g->generation++;
 }
 
-extern "C" int pcamv_group_analyse_p(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log)
+static int group_submit(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log, int begin_only)
 {
     if (!g || !ctx || !in || !mbs) return -1;
     int rc = 0;
     std::unique_lock<std::mutex> lk(g->mu);
     g->ctxs.push_back(ctx); g->ins.push_back(in); g->mbs.push_back(mbs); g->logs.push_back(log); g->rcs.push_back(&rc);
+    g->begin_only.push_back(begin_only);
     g->n_arrived++;
     if (g->n_arrived >= g->n_live)
     {
@@ -553,6 +655,17 @@ extern "C" int pcamv_group_analyse_p(pcamv_group *g, pcamv_ctx *ctx, const pcamv
         g->cv.wait(lk, [&] { return g->generation != gen; });
     }
     return rc;
+}
+
+extern "C" int pcamv_group_analyse_p(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    return group_submit(g, ctx, in, mbs, log, 0);
+}
+
+// same rendezvous; returns when the group's launch is in flight, results arrive through pcamv_analyse_p_rows( ctx, ... )
+extern "C" int pcamv_group_analyse_p_begin(pcamv_group *g, pcamv_ctx *ctx, const pcamv_frame_in *in, pcamv_mb_out *mbs, pcamv_log_entry *log)
+{
+    return group_submit(g, ctx, in, mbs, log, 1);
 }
 
 extern "C" int pcamv_group_leave(pcamv_group *g)

@@ -114,6 +114,15 @@ def reference_side(pcamv, name, cores=None, want_payload=True):
     cache = os.path.join(d, "reference.json")
     if os.path.exists(cache):
         return json.load(open(cache))
+    # PCAMV_JOB_DIGESTS=<dir>: committed per-shard digests of the reference's output (tools/reference_digests.py; the clips are
+    # seeded and the reference is deterministic) instead of running it on this box; its fps then is the fps of the machine named
+    # in "made_on", and the result says so
+    shipped = os.environ.get("PCAMV_JOB_DIGESTS")
+    if shipped and os.path.exists(os.path.join(shipped, name + ".json")):
+        res = json.load(open(os.path.join(shipped, name + ".json")))
+        res["source"] = "committed digests (%s), reference not run on this box" % res.get("made_on", "?")
+        make_clip(pcamv, name)
+        return res
     clip = make_clip(pcamv, name)
     w, h, k, n = job["width"], job["height"], job["shard_frames"], job["shards"]
     cores = cores or max(1, min(os.cpu_count() or 1, 64))
@@ -180,8 +189,9 @@ def run_rank(name, rank, world, device, groups=4, extract=False, tag="gpu"):
         for f in ("%s.%d" % (out, g), "%s.%d" % (pay, g)):
             if os.path.exists(f):
                 os.remove(f)
+    st = os.path.join(d, "%s_stats_r%d" % (tag, rank))
     env = dict(os.environ, PCAMV_DEVICE=str(device), PCAMV_ROWS_PER_CTA="4", PCAMV_GROUPS=str(max(1, min(groups, len(mine)))),
-               PCAMV_PAYLOAD=pay)
+               PCAMV_PAYLOAD=pay, PCAMV_STATS=st)
     env.pop("CUDA_DEVICE_MAX_CONNECTIONS", None)
     cmd = [HOST, "--shards", str(len(mine)), "--shard-frames", str(k), "--shard-first", str(rank), "--shard-step", str(world), "--shard-keep"] + \
         job_args(job) + ["-o", out, clip, "%dx%d" % (w, h)]
@@ -200,6 +210,10 @@ def run_rank(name, rank, world, device, groups=4, extract=False, tag="gpu"):
             m.update(msg.tobytes()); m.update(stego.tobytes())
             bits += max(an, 0); n_mv += length
             payload.append(msg)
-        recs.append({"gop": g, "n_bits": bits, "payload": np.concatenate(payload).tobytes() if payload else b"", "n_mv": n_mv,
+        try:
+            stats = json.load(open("%s.%d" % (st, g)))
+        except Exception:
+            stats = {}
+        recs.append({"stats": stats, "gop": g, "n_bits": bits, "payload": np.concatenate(payload).tobytes() if payload else b"", "n_mv": n_mv,
                      "n_flipped": 0, "bytes": os.path.getsize(f), "md5": _md5(f), "payload_md5": m.hexdigest(), "file": f})
     return secs, recs, p.stderr.decode("latin-1")

@@ -71,7 +71,8 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
            "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide",
            "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave", "pcamv_stc_embed",
-           "pcamv_embed_prepare", "pcamv_embed_stc", "pcamv_embed_download", "pcamv_reconstruct_ref"]
+           "pcamv_embed_prepare", "pcamv_embed_stc", "pcamv_embed_download", "pcamv_reconstruct_ref",
+           "pcamv_analyse_p_begin", "pcamv_analyse_p_batch_begin", "pcamv_group_analyse_p_begin", "pcamv_analyse_p_rows"]
 
 _lib = None
 
@@ -105,6 +106,11 @@ def load_library(path=None):
     lib.pcamv_int_peak.argtypes = [vp, C.POINTER(C.c_double)]; lib.pcamv_int_peak.restype = ip
     lib.pcamv_analyse_p.argtypes = [vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_analyse_p.restype = ip
     lib.pcamv_frame_upload.argtypes = [vp, C.POINTER(FrameIn)]; lib.pcamv_frame_upload.restype = ip
+    lib.pcamv_analyse_p_begin.argtypes = [vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_analyse_p_begin.restype = ip
+    lib.pcamv_analyse_p_batch_begin.argtypes = [C.POINTER(vp), C.POINTER(C.POINTER(FrameIn)), ip, C.POINTER(vp), C.POINTER(vp)]
+    lib.pcamv_analyse_p_batch_begin.restype = ip
+    lib.pcamv_group_analyse_p_begin.argtypes = [vp, vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_group_analyse_p_begin.restype = ip
+    lib.pcamv_analyse_p_rows.argtypes = [vp, ip, C.POINTER(ip)]; lib.pcamv_analyse_p_rows.restype = ip
     lib.pcamv_frame_run.argtypes = [vp, ip, ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]; lib.pcamv_frame_run.restype = ip
     lib.pcamv_frame_download.argtypes = [vp, vp, vp]; lib.pcamv_frame_download.restype = ip
     lib.pcamv_frame_trace.argtypes = [vp, ip, vp]; lib.pcamv_frame_trace.restype = ip
@@ -369,6 +375,19 @@ class PcamvContext:
         self._check(self.lib.pcamv_analyse_p(self.handle, C.byref(fi), _ptr(mbs), _ptr(log)))
         return mbs, log
 
+    def analyse_p_begin(self, pass_, ref_slots, ref_pocs, cur_poc, out, **kw):
+        """pcamv_analyse_p_begin: the launch is in flight on return; `out` = page-locked (mbs, log) from alloc_outputs(pinned=True),
+        filled row by row by analyse_p_rows."""
+        fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
+        self._check(self.lib.pcamv_analyse_p_begin(self.handle, C.byref(fi), _ptr(out[0]), _ptr(out[1])))
+
+    def analyse_p_rows(self, row):
+        """pcamv_analyse_p_rows: blocks until macroblock rows 0..row are in the buffers given to analyse_p_begin; returns the
+        number of complete rows."""
+        n = C.c_int()
+        self._check(self.lib.pcamv_analyse_p_rows(self.handle, int(row), C.byref(n)))
+        return int(n.value)
+
     def frame_upload(self, pass_, ref_slots, ref_pocs, cur_poc, **kw):
         fi, keep = self._frame_in(pass_, ref_slots, ref_pocs, cur_poc, **kw)
         self._check(self.lib.pcamv_frame_upload(self.handle, C.byref(fi)))
@@ -425,6 +444,23 @@ def analyse_p_batch(ctxs, frame_args, outs=None):
     if lib.pcamv_analyse_p_batch(h, pin, n, pm, pl) != 0:
         raise PcamvError(lib.pcamv_last_error(ctxs[0].handle).decode())
     return outs
+
+
+def analyse_p_batch_begin(ctxs, frame_args, outs):
+    """pcamv_analyse_p_batch_begin: as analyse_p_batch, but returns with the launch in flight; outs = page-locked buffers of every
+    context, collected with ctx.analyse_p_rows()."""
+    n = len(ctxs)
+    lib = ctxs[0].lib
+    fins, keeps = [], []
+    for c, (pass_, slots, pocs, cur_poc, kw) in zip(ctxs, frame_args):
+        fi, keep = c._frame_in(pass_, slots, pocs, cur_poc, **kw)
+        fins.append(fi); keeps.append(keep)
+    h = (C.c_void_p * n)(*[c.handle for c in ctxs])
+    pin = (C.POINTER(FrameIn) * n)(*[C.pointer(f) for f in fins])
+    pm = (C.c_void_p * n)(*[o[0].ctypes.data for o in outs])
+    pl = (C.c_void_p * n)(*[o[1].ctypes.data for o in outs])
+    if lib.pcamv_analyse_p_batch_begin(h, pin, n, pm, pl) != 0:
+        raise PcamvError(lib.pcamv_last_error(ctxs[0].handle).decode())
 
 
 def frame_run_batch(ctxs, pass_, iters=1):

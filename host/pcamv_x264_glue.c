@@ -48,7 +48,7 @@ typedef struct
     int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
     int host_intra;                 /* PCAMV_HOST_INTRA=1: intra analysis of every P macroblock, as the reference does for its statistics */
     int stream_rows, rows_ready, mb_h;      /* the replayed pass is consumed row by row while the kernel runs (PCAMV_NO_ROW_STREAM=1: wait for its end) */
-    double t_row_wait;
+    double t_row_wait, t_pass1, t_embed;
     int direct;                     /* pass 1 of an embedding frame never reaches the host's macroblock loop (pcamv_hook_pass1_on_device) */
     int16_t last_mv[16][2]; int have_last_mv; long stale_mismatch;
     int device_forced;              /* the embed stage of this frame ran on the device: pass 2 takes its forced decisions from HBM */
@@ -73,7 +73,7 @@ static __thread glue_t g;
 /* shards of one process share the GPU through an encoder group (include/pcamv.h): one multi-context launch per step */
 /* PCAMV_GROUPS=G (default 2) splits the shards into G groups that rendezvous independently (shard i joins group i % G):
  * while one group's frames are on the GPU the other groups' encoders do their host work, so neither side idles */
-#define PCAMV_MAX_GROUPS 8
+#define PCAMV_MAX_GROUPS 64
 static pcamv_group *g_groups[PCAMV_MAX_GROUPS];
 static int g_n_groups;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -266,9 +266,9 @@ void pcamv_hook_close( x264_t *h )
         if( f )
         {
             fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_open\": %.6f, \"t_total\": %.6f, "
-                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld, \"t_ref_upload\": %.6f, \"t_recon\": %.6f, \"direct_pass1\": %ld, \"stale_mismatch\": %ld, \"t_row_wait\": %.6f}\n",
+                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld, \"t_ref_upload\": %.6f, \"t_recon\": %.6f, \"direct_pass1\": %ld, \"stale_mismatch\": %ld, \"t_row_wait\": %.6f, \"t_pass1\": %.6f, \"t_embed\": %.6f}\n",
                      g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, g.t_open, now_s() - g.t_total0,
-                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs, g.t_ref_upload, g.t_recon, g.n_direct, g.stale_mismatch, g.t_row_wait );
+                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs, g.t_ref_upload, g.t_recon, g.n_direct, g.stale_mismatch, g.t_row_wait, g.t_pass1, g.t_embed );
             fclose( f );
         }
     }
@@ -475,6 +475,7 @@ void pcamv_hook_slice_begin( x264_t *h )
     {
         memcpy( g.last_mv, g.mbs[g.n_mb - 1].mv, sizeof(g.last_mv) );
         g.have_last_mv = 1;
+        g.t_pass1 += now_s() - t0;
     }
     g.t_gpu += now_s() - t0;
 }
@@ -538,6 +539,7 @@ int pcamv_hook_pass1_on_device( x264_t *h )
     g.active = 0;
     g.n_direct++;
     g.t_gpu += now_s() - t0;
+    g.t_embed += now_s() - t0;
     return 1;
 }
 

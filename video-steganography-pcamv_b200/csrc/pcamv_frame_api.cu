@@ -541,6 +541,7 @@ extern "C" int pcamv_analyse_p_rows(pcamv_ctx *ctx, int row, int *rows_ready)
     if (!ctx->sr_active && ctx->sr_rows < mb_h)
         return ctx_fail(ctx, "pcamv_analyse_p_rows: no analysis started with pcamv_analyse_p_begin is in flight", cudaSuccess);
     if (row >= mb_h) row = mb_h - 1;
+    long idle_ns = 20000;
     while (ctx->sr_rows <= row)
     {
         // the kernel's state BEFORE the look at the counters: once it has ended they are final
@@ -564,9 +565,14 @@ extern "C" int pcamv_analyse_p_rows(pcamv_ctx *ctx, int row, int *rows_ready)
             return ctx_fail(ctx, "pcamv_analyse_p_rows: the wavefront kernel ended without finishing the frame", cudaSuccess);
         else
         {
-            struct timespec ts = { 0, 20000 };       // the next row is ~0.3 ms away: do not burn the core the other encoder threads need
+            // the next row is 0.3 - 1 ms away: back off (20 us .. 320 us) instead of burning the core — and the driver's lock —
+            // that the other encoder threads of the process need
+            struct timespec ts = { 0, idle_ns };
             nanosleep(&ts, nullptr);
+            if (idle_ns < 320000) idle_ns *= 2;
+            continue;
         }
+        idle_ns = 20000;
     }
     if (ctx->sr_rows >= mb_h && ctx->sr_active)
     {

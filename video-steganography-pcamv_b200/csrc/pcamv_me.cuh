@@ -216,12 +216,14 @@ PCAMV_FN int cand_cost(const MeBlock &b, int kind, int n, int c0, int c1, int c2
     }
     // (ld_row16 / ld4 read whole aligned words: up to 3 bytes before and 7 after the pixels they deliver)
     PCAMV_CHK_RANGE(b, (s1 < s2 ? s1 : s2) - 3, (s1 > s2 ? s1 : s2) + (bh - 1) * stride + 16 + 7, "cand_cost (luma)");
+#ifdef PCAMV_CHECKED
     if (kind == COST_SATD_CHROMA)
     {
         const uint8_t *cu = b.ref_u + (qy >> 3) * b.stride_c + (qx >> 3), *cv = b.ref_v + (qy >> 3) * b.stride_c + (qx >> 3);
         PCAMV_CHK_RANGE(b, cu - 3, cu + (bh >> 1) * b.stride_c + (bw >> 1) + 1 + 7, "cand_cost (U)");
         PCAMV_CHK_RANGE(b, cv - 3, cv + (bh >> 1) * b.stride_c + (bw >> 1) + 1 + 7, "cand_cost (V)");
     }
+#endif
     if (kind == COST_SAD_FPEL || kind == COST_SAD)
     {
         const int w4 = bw >> 2;

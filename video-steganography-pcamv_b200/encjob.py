@@ -190,7 +190,8 @@ def run_rank(name, rank, world, device, groups=4, extract=False, tag="gpu"):
             if os.path.exists(f):
                 os.remove(f)
     st = os.path.join(d, "%s_stats_r%d" % (tag, rank))
-    env = dict(os.environ, PCAMV_DEVICE=str(device), PCAMV_ROWS_PER_CTA="4", PCAMV_GROUPS=str(max(1, min(groups, len(mine)))),
+    groups = int(os.environ.get("PCAMV_JOB_GROUPS", groups))           # (tuning: rendezvous groups and wavefront layout of the job's encoders)
+    env = dict(os.environ, PCAMV_DEVICE=str(device), PCAMV_ROWS_PER_CTA=os.environ.get("PCAMV_JOB_RPC", "4"), PCAMV_GROUPS=str(max(1, min(groups, len(mine)))),
                PCAMV_PAYLOAD=pay, PCAMV_STATS=st)
     env.pop("CUDA_DEVICE_MAX_CONNECTIONS", None)
     cmd = [HOST, "--shards", str(len(mine)), "--shard-frames", str(k), "--shard-first", str(rank), "--shard-step", str(world), "--shard-keep"] + \

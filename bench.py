@@ -640,6 +640,15 @@ def encoder_job_leg(pcamv, name, rank, world, local_rank, barrier):
     t_open = max([s_["t_open"] for s_ in st] or [0.0])
     gpu_share = max([s_["t_gpu_calls"] / max(s_["t_total"] - s_["t_open"], 1e-9) for s_ in st] or [0.0])
     t_max, t_enc_max, loop_max, open_max, gpu_share_max = shard.max_over_ranks([t_all, t_enc, loop, t_open, gpu_share])
+    # where an encoder thread of this rank spends its time, mean over its shards, per P frame (ms): pass 1 on the GPU incl. the
+    # wait for the group, the embed stage, waiting for rows of the replayed pass, everything else (the host's own work)
+    per_frame = None
+    if st:
+        nf = max(sum(s_.get("direct_pass1", 0) for s_ in st), 1)
+        tot = sum(s_["t_total"] - s_["t_open"] for s_ in st)
+        p1, em, rw, gp = (sum(s_.get(k, 0.0) for s_ in st) for k in ("t_pass1", "t_embed", "t_row_wait", "t_gpu_calls"))
+        per_frame = {"pass1_ms": 1e3 * p1 / nf, "embed_ms": 1e3 * em / nf, "row_wait_ms": 1e3 * rw / nf,
+                     "other_gpu_calls_ms": 1e3 * (gp - p1 - em - rw) / nf, "host_ms": 1e3 * (tot - gp) / nf, "frames": nf}
     if rank != 0:
         return None
     n = job["shards"]
@@ -651,7 +660,7 @@ def encoder_job_leg(pcamv, name, rank, world, local_rank, barrier):
     return {"job": name, "what": job["what"], "args": " ".join(encjob.job_args(job)), "frames": frames, "shards": n, "ranks": world,
             "encode_embed_fps": frames / t_max, "seconds": t_max, "seconds_encode_only": t_enc_max, "seconds_gather": t_max - t_enc_max,
             "encode_loop_fps": frames / loop_max if loop_max > 0 else None, "seconds_encode_loop": loop_max, "seconds_cuda_startup": open_max,
-            "gpu_call_share_of_encoder_thread": gpu_share_max,
+            "gpu_call_share_of_encoder_thread": gpu_share_max, "encoder_thread_ms_per_p_frame_rank0": per_frame,
             "bitstream_identical": bool(ok_bits), "payload_identical": ok_pay,
             "payload_bits": int(sum(g["n_bits"] for g in gathered)), "bytes": int(sum(g["bytes"] for g in gathered)),
             "reference_fps": ref["fps"], "reference_cores": ref["cores"], "reference_seconds": ref["seconds"],

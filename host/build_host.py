@@ -43,6 +43,7 @@ IH_WRAPPER = ("{ int r = pcamv_glue_ih_cost( h, m, m_x, m_y ); x264_analyse_upda
 SHARD_MAIN = r'''
 /* ---- appended by host/build_host.py: GOP-sharded encoding on threads of one process -------------------------------- */
 #include <pthread.h>
+#include <unistd.h>
 void pcamv_glue_set_shards( int n );
 void pcamv_glue_shard_done( void );
 void pcamv_glue_set_shard_index( int i, int gop );

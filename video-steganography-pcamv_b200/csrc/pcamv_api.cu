@@ -69,6 +69,19 @@ extern "C" int pcamv_open(pcamv_ctx **out, const pcamv_cfg *cfg)
     if (e != cudaSuccess || ndev <= 0)
         return fail(nullptr, "pcamv_open: no CUDA device (this library has no CPU fallback)", e == cudaSuccess ? cudaErrorNoDevice : e);
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "pcamv_open: bad device ordinal", cudaSuccess);
+    // PCAMV_BLOCKING_SYNC=1: host threads waiting for the GPU sleep instead of spinning — for processes with more encoder threads
+    // than cores to spare (the bound host sets it for --shards jobs that oversubscribe the machine).  It is a property of the
+    // device's primary context and must be chosen before that exists: first pcamv_open of the process only.
+    {
+        static bool chosen = false;
+        if (!chosen)
+        {
+            chosen = true;
+            const char *bs = getenv("PCAMV_BLOCKING_SYNC");
+            if (bs && atoi(bs) && cudaInitDevice(cfg->device, cudaDeviceScheduleBlockingSync, cudaInitDeviceFlagsAreValid) != cudaSuccess)
+                cudaGetLastError();             // (context already there with other flags: carry on with those)
+        }
+    }
     e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) return fail(nullptr, "cudaSetDevice", e);
 

@@ -259,10 +259,31 @@ def run_reference_arm(args, pcamv, rank, world):
         line["encoder_job"] = {"job": args.encoder_job, "what": job["what"], "args": " ".join(encjob.job_args(job)), "frames": ref["frames"],
                                "shards": job["shards"], "encode_embed_fps": ref["fps"], "seconds": ref["seconds"], "cores": ref["cores"],
                                "note": "oracle/_ref/x264_wide (the reference's C sources, no asm), one single-threaded process per shard"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the result.  Everything else that writes to file descriptor 1 — NCCL's version banner
+    (NCCL_DEBUG from the environment or from /etc/nccl.conf), child processes, libraries — is sent to stderr: fd 1 is
+    duplicated for the result line and then pointed at fd 2."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -610,7 +631,7 @@ def main():
             line["encoder_e2e"] = encoder_e2e(pcamv, workdir, local_rank)
             # BASELINE.json config 3 (exhaustive search, merange 32, 4 references): one stream, whole encoder
             line["encoder_e2e_esa"] = encoder_e2e(pcamv, workdir, local_rank, frames=6, ref_args=ESA_ARGS, config=3, tag="esa")
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

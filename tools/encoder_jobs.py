@@ -17,6 +17,7 @@ def main():
     import torch
     import torch.distributed as dist
     import bench
+    bench.claim_stdout()
     import pcamv_loader
     pcamv = pcamv_loader.load()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -31,7 +32,7 @@ def main():
     for name in sys.argv[1:]:
         res = bench.encoder_job_leg(pcamv, name, rank, world, local_rank, barrier)
         if rank == 0:
-            print(json.dumps(res), flush=True)
+            bench.emit(res)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

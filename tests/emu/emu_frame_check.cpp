@@ -343,8 +343,9 @@ int main(int argc, char **argv)
             DbFrame df; df.type = type.data(); df.ref8 = ref8.data(); df.mv4 = mv4.data(); df.nnz = rec_nnz.data(); df.mb_w = mb_w;
             DeblockParams dp; memset(&dp, 0, sizeof(dp));
             dp.qp = fc.tab.qp; dp.qp_chroma = fc.tab.chroma_qp; dp.no_sub8x8_all = !(fc.analyse_inter & 0x20);
+            alignas(16) uint8_t db_stage[(DB_STAGE_BYTES + 15) & ~15];
             for (int mb = 0; mb < n_mb; mb++)
-                deblock_mb(df, rp, dp, mb % mb_w, mb / mb_w);
+                deblock_mb(df, rp, dp, mb % mb_w, mb / mb_w, db_stage);
             rec_frame = sp.hd.frame; rec_q1 = 0;
             for (int mb = 0; mb < n_mb; mb++) rec_q1 += results[mb].early_skip == 2;
             for (int mb = 0; mb < n_mb; mb++) { rec_type[mb] = results[mb].type; rec_mv0[mb] = results[mb].mv[0]; memcpy(&rec_ref[4 * mb], results[mb].ref, 4); }

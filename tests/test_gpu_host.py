@@ -102,6 +102,21 @@ def test_bitstream_identical_with_full_pass2(pcamv, cuda_lib, case, tmp_path):
     assert md5(out) == md5(ref_out)
 
 
+@pytest.mark.parametrize("env", [{"PCAMV_NO_ROW_STREAM": "1"}, {"PCAMV_HOST_INTRA": "1"}, {"PCAMV_NO_PINNED": "1"},
+                                 {"PCAMV_ROWS_PER_CTA": "4"}, {"PCAMV_BLOCKING_SYNC": "1"}],
+                         ids=["no-row-stream", "host-intra", "no-pinned", "row-groups-4", "blocking-sync"])
+@pytest.mark.parametrize("case", [CASES[1], CASES[10]], ids=[CASES[1][0], CASES[10][0]])
+def test_bitstream_identical_with_host_switches(pcamv, cuda_lib, case, env, tmp_path):
+    """The switches of the bound host that change HOW it gets its results, never WHAT they are: waiting for the end of the replayed
+    pass instead of following the wavefront row by row, intra analysis of every P macroblock instead of the q1 ones only, pageable
+    result buffers (which also disables the row streaming), the throughput layout of the wavefront, sleeping instead of spinning
+    waits — on a 3-reference umh clip and on the skip-heavy clip that exercises quirks q1 / q2."""
+    ref_out, out, stats = encode_pair(pcamv, *case, workdir=str(tmp_path), extra_env=env)
+    assert md5(out) == md5(ref_out)
+    if "PCAMV_NO_ROW_STREAM" in env or "PCAMV_NO_PINNED" in env:
+        assert stats["t_row_wait"] == 0.0
+
+
 def test_payload_identical(pcamv, cuda_lib, tmp_path):
     """The hidden payload: per P frame the message bits (glibc rand() & 1 stream, encoder/encoder.c:1838-1840) and the stego
     LSB vector the STC embedder produced are identical to the reference's (EMBD records of the instrumented twin)."""

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_deblock(const DbFrame f, cons
                                                            int *progress, int *row_claim)
 {
     __shared__ int s_group;
+    __shared__ __align__(16) uint8_t s_stage[RC_WARPS][(DB_STAGE_BYTES + 15) & ~15];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (;;)
     {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_deblock(const DbFrame f, cons
                     if (ns < 1024) ns <<= 1;
                 }
             }
-            deblock_mb(f, rp, dp, x, row);
+            deblock_mb(f, rp, dp, x, row, s_stage[warp]);
             __syncwarp();
             if (lane == 0)
             {

@@ -39,9 +39,11 @@ struct DeblockParams
 #if defined(PCAMV_EMU)
   #define PCAMV_PX_LD(p) (*(p))
   #define PCAMV_PX_ST(p, v) (*(p) = (v))
+  #define PCAMV_STV(p, v) (*(p) = (v))
 #else
   #define PCAMV_PX_LD(p) __ldcg(p)
   #define PCAMV_PX_ST(p, v) __stcg((p), (v))
+  #define PCAMV_STV(p, v) __stcg((p), (v))
 #endif
 
 // ---- reconstruction of one macroblock in its final mode ------------------------------------------------------------
@@ -142,83 +144,58 @@ struct DbFrame               // what the filter reads of the frame's final motio
     int mb_w;
 };
 
-// bS of the four 4-pixel pieces of edge `e` of macroblock (mb_x, mb_y) in direction dir (0 = vertical edges), packed one byte
-// each (common/frame.c DEBLOCK_STRENGTH); inter macroblocks only
-PCAMV_DEV uint32_t db_strength(const DbFrame &f, int mb_x, int mb_y, int dir, int e, int no_sub8x8)
+// one line across a luma edge (deblock_luma_c): pix = q0, xs = step across the edge; works on the staged copy of the
+// macroblock's neighbourhood (plain loads and stores: team-private memory)
+PCAMV_DEV void db_luma_line(uint8_t *pix, int xs, int alpha, int beta, int tc0)
 {
-    const int mb_xy = mb_y * f.mb_w + mb_x;
-    const int mbn_xy = e ? mb_xy : (dir == 0 ? mb_xy - 1 : mb_xy - f.mb_w);
-    const int s8 = 2 * f.mb_w, s4 = 4 * f.mb_w;
-    const int nx = e ? mb_x : (dir == 0 ? mb_x - 1 : mb_x), ny = e ? mb_y : (dir == 0 ? mb_y : mb_y - 1);
-    const unsigned nz_p = f.nnz[mb_xy], nz_q = f.nnz[mbn_xy];
-    uint32_t out = 0;
-    int prev = 0;
-#pragma unroll 1
-    for (int i = 0; i < 4; i++)
-    {
-        const int x = dir == 0 ? e : i, y = dir == 0 ? i : e;
-        const int xn = dir == 0 ? (x - 1) & 3 : x, yn = dir == 0 ? y : (y - 1) & 3;
-        int bs = 0;
-        if (((nz_p >> (x + 4 * y)) & 1) || ((nz_q >> (xn + 4 * yn)) & 1))
-            bs = 2;
-        else if (!(e & no_sub8x8))
-        {
-            if ((i & no_sub8x8) && prev != 2)
-                bs = prev;
-            else
-            {
-                const int i8p = (2 * mb_y + (y >> 1)) * s8 + 2 * mb_x + (x >> 1), i8q = (2 * ny + (yn >> 1)) * s8 + 2 * nx + (xn >> 1);
-                const int i4p = (4 * mb_y + y) * s4 + 4 * mb_x + x, i4q = (4 * ny + yn) * s4 + 4 * nx + xn;
-                const uint32_t mp = PCAMV_LDV(f.mv4 + i4p), mq = PCAMV_LDV(f.mv4 + i4q);
-                if (PCAMV_LDV(f.ref8 + i8p) != PCAMV_LDV(f.ref8 + i8q) || iabs(mv_x(mp) - mv_x(mq)) >= 4 || iabs(mv_y(mp) - mv_y(mq)) >= 4)
-                    bs = 1;
-            }
-        }
-        prev = bs;
-        out |= (uint32_t)bs << (8 * i);
-    }
-    return out;
-}
-
-// one line across a luma edge (deblock_luma_c): pix = q0, xs = step across the edge
-PCAMV_DEV void db_luma_line(uint8_t *pix, ptrdiff_t xs, int alpha, int beta, int tc0)
-{
-    const int p2 = PCAMV_PX_LD(pix - 3 * xs), p1 = PCAMV_PX_LD(pix - 2 * xs), p0 = PCAMV_PX_LD(pix - xs);
-    const int q0 = PCAMV_PX_LD(pix), q1 = PCAMV_PX_LD(pix + xs), q2 = PCAMV_PX_LD(pix + 2 * xs);
+    const int p2 = pix[-3 * xs], p1 = pix[-2 * xs], p0 = pix[-xs];
+    const int q0 = pix[0], q1 = pix[xs], q2 = pix[2 * xs];
     if (iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta)
     {
         int tc = tc0;
         if (iabs(p2 - p0) < beta)
         {
-            PCAMV_PX_ST(pix - 2 * xs, (uint8_t)(p1 + clip3(((p2 + ((p0 + q0 + 1) >> 1)) >> 1) - p1, -tc0, tc0)));
+            pix[-2 * xs] = (uint8_t)(p1 + clip3(((p2 + ((p0 + q0 + 1) >> 1)) >> 1) - p1, -tc0, tc0));
             tc++;
         }
         if (iabs(q2 - q0) < beta)
         {
-            PCAMV_PX_ST(pix + xs, (uint8_t)(q1 + clip3(((q2 + ((p0 + q0 + 1) >> 1)) >> 1) - q1, -tc0, tc0)));
+            pix[xs] = (uint8_t)(q1 + clip3(((q2 + ((p0 + q0 + 1) >> 1)) >> 1) - q1, -tc0, tc0));
             tc++;
         }
         const int delta = clip3((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-        PCAMV_PX_ST(pix - xs, (uint8_t)clip_u8(p0 + delta));
-        PCAMV_PX_ST(pix, (uint8_t)clip_u8(q0 - delta));
+        pix[-xs] = (uint8_t)clip_u8(p0 + delta);
+        pix[0] = (uint8_t)clip_u8(q0 - delta);
     }
 }
-PCAMV_DEV void db_chroma_line(uint8_t *pix, ptrdiff_t xs, int alpha, int beta, int tc)
+PCAMV_DEV void db_chroma_line(uint8_t *pix, int xs, int alpha, int beta, int tc)
 {
-    const int p1 = PCAMV_PX_LD(pix - 2 * xs), p0 = PCAMV_PX_LD(pix - xs), q0 = PCAMV_PX_LD(pix), q1 = PCAMV_PX_LD(pix + xs);
+    const int p1 = pix[-2 * xs], p0 = pix[-xs], q0 = pix[0], q1 = pix[xs];
     if (iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta)
     {
         const int delta = clip3((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-        PCAMV_PX_ST(pix - xs, (uint8_t)clip_u8(p0 + delta));
-        PCAMV_PX_ST(pix, (uint8_t)clip_u8(q0 - delta));
+        pix[-xs] = (uint8_t)clip_u8(p0 + delta);
+        pix[0] = (uint8_t)clip_u8(q0 - delta);
     }
 }
 
+// Team-private staging of one macroblock's filter neighbourhood: luma rows -4..15 x columns -4..15 (stride 24), U and V rows
+// -4..7 x columns -4..7 (stride 16), and the 32 boundary strengths of its 2 x 4 edges x 4 pieces.
+#define DB_LS 24
+#define DB_CS 16
+#define DB_STAGE_Y 0
+#define DB_STAGE_C (20 * DB_LS)
+#define DB_STAGE_BS (DB_STAGE_C + 2 * 12 * DB_CS)
+#define DB_STAGE_BYTES (DB_STAGE_BS + 32)
+
 // All edges of macroblock (mb_x, mb_y), in the reference's order: vertical edges left to right (luma, and chroma on the even
 // ones), then horizontal edges top to bottom.  The caller guarantees that the left neighbour and the row above up to the
-// top-right neighbour are finished (their pixels are read and written here).
-// Team layout: lanes 0..15 = the 16 luma lines of an edge, lanes 16..23 / 24..31 = the 8 lines of U / V.
-PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockParams &dp, int mb_x, int mb_y)
+// top-right neighbour are finished (their pixels are read and written here) and that nobody else touches the macroblock's
+// neighbourhood until this call returns — which the wavefront order gives: the right neighbour and the row below start after it.
+// The neighbourhood is copied into team-private memory once (one global round trip instead of one per edge), the 32 boundary
+// strengths are computed one per lane, the edges are filtered in the copy and the copy is written back.
+// Team layout while filtering: lanes 0..15 = the 16 luma lines of an edge, lanes 16..23 / 24..31 = the 8 lines of U / V.
+PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockParams &dp, int mb_x, int mb_y, uint8_t *stage)
 {
     const int mb_xy = mb_y * f.mb_w + mb_x;
     const int type = PCAMV_LDV(f.type + mb_xy);
@@ -229,16 +206,89 @@ PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockP
     const int alpha_c = db_alpha(dp.qp_chroma + dp.alpha_c0_offset), beta_c = db_beta(dp.qp_chroma + dp.beta_offset);
     uint8_t *py = rp.y + (size_t)(16 * mb_y) * rp.stride_y + 16 * mb_x;
     uint8_t *pu = rp.u + (size_t)(8 * mb_y) * rp.stride_c + 8 * mb_x, *pv = rp.v + (size_t)(8 * mb_y) * rp.stride_c + 8 * mb_x;
+    uint8_t *sy = stage + DB_STAGE_Y + 4 * DB_LS + 4;                   // (0, 0) of the macroblock in the luma copy
+    uint8_t *sbs = stage + DB_STAGE_BS;
+
+    // (1) copy in: 20 luma rows of 20 bytes, 12 rows of 12 bytes per chroma plane (the planes are padded: rows / columns -4..-1
+    // exist in memory on the frame border too, and are not filtered there)
+    PCAMV_FOR_ITEMS(it, 32)
+    {
+        if (it < 20)
+        {
+            const uint32_t *src = (const uint32_t *)(py + (ptrdiff_t)(it - 4) * rp.stride_y - 4);
+            uint32_t *dst = (uint32_t *)(stage + DB_STAGE_Y + it * DB_LS);
+#pragma unroll
+            for (int k = 0; k < 5; k++) dst[k] = PCAMV_LDV(src + k);
+        }
+        else
+        {
+            const int r = it - 20;
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++)
+            {
+                const uint32_t *src = (const uint32_t *)((pl ? pv : pu) + (ptrdiff_t)(r - 4) * rp.stride_c - 4);
+                uint32_t *dst = (uint32_t *)(stage + DB_STAGE_C + pl * 12 * DB_CS + r * DB_CS);
+#pragma unroll
+                for (int k = 0; k < 3; k++) dst[k] = PCAMV_LDV(src + k);
+            }
+        }
+    }
+    // (2) boundary strengths, one piece per lane: it = 16 dir + 4 e + i  (common/frame.c DEBLOCK_STRENGTH; inter macroblocks only)
+    {
+        const int s8 = 2 * f.mb_w, s4 = 4 * f.mb_w;
+        PCAMV_FOR_ITEMS(it, 32)
+        {
+            const int dir = it >> 4, e = (it >> 2) & 3, i = it & 3;
+            int bs = 0;
+            const int on_border = e == 0 && (dir ? mb_y == 0 : mb_x == 0);
+            if (!on_border && !(e >= 1 && e >= edge_end))
+            {
+                const int mbn_xy = e ? mb_xy : (dir == 0 ? mb_xy - 1 : mb_xy - f.mb_w);
+                const int nx = e ? mb_x : (dir == 0 ? mb_x - 1 : mb_x), ny = e ? mb_y : (dir == 0 ? mb_y : mb_y - 1);
+                const unsigned nz_p = PCAMV_LDV(f.nnz + mb_xy), nz_q = PCAMV_LDV(f.nnz + mbn_xy);
+                const int x = dir == 0 ? e : i, y = dir == 0 ? i : e;
+                const int xn = dir == 0 ? (x - 1) & 3 : x, yn = dir == 0 ? y : (y - 1) & 3;
+                if (((nz_p >> (x + 4 * y)) & 1) || ((nz_q >> (xn + 4 * yn)) & 1))
+                    bs = 2;
+                else if (!(e & no_sub8x8))
+                {
+                    // (an odd piece of a macroblock without sub-8x8 partitions takes its left / upper neighbour piece's strength
+                    // unless that is 2: resolved below, 0x80 marks "would have been compared")
+                    const int i8p = (2 * mb_y + (y >> 1)) * s8 + 2 * mb_x + (x >> 1), i8q = (2 * ny + (yn >> 1)) * s8 + 2 * nx + (xn >> 1);
+                    const int i4p = (4 * mb_y + y) * s4 + 4 * mb_x + x, i4q = (4 * ny + yn) * s4 + 4 * nx + xn;
+                    const uint32_t mp = PCAMV_LDV(f.mv4 + i4p), mq = PCAMV_LDV(f.mv4 + i4q);
+                    if (PCAMV_LDV(f.ref8 + i8p) != PCAMV_LDV(f.ref8 + i8q) || iabs(mv_x(mp) - mv_x(mq)) >= 4 || iabs(mv_y(mp) - mv_y(mq)) >= 4)
+                        bs = 1;
+                    bs |= 0x80;
+                }
+            }
+            sbs[it] = (uint8_t)bs;
+        }
+        team_sync();
+        PCAMV_FOR_ITEMS(it, 32)
+        {
+            int bs = sbs[it];
+            if (bs & 0x80)
+            {
+                const int prev = sbs[it - ((it & 1) ? 1 : 0)] & 0x7f;       // (even pieces never copy: prev unused)
+                bs &= 0x7f;
+                if ((it & 1) && no_sub8x8 && prev != 2)
+                    bs = prev;
+            }
+            team_sync();                 // every lane has read its neighbour's raw value before anybody overwrites
+            sbs[it] = (uint8_t)bs;
+        }
+    }
+    // (3) the edges, in the copy
 #pragma unroll 1
     for (int dir = 0; dir < 2; dir++)
     {
-        team_sync();             // the horizontal edges read what the vertical edges of all lines wrote
-        // edge 0 is the macroblock boundary (not on the frame border); the inner edges 1..3 only up to edge_end
 #pragma unroll 1
-        for (int e = (dir ? mb_y == 0 : mb_x == 0) ? 1 : 0; e < 4; e++)
+        for (int e = 0; e < 4; e++)
         {
-            if (e >= 1 && e >= edge_end) break;
-            const uint32_t bS = db_strength(f, mb_x, mb_y, dir, e, no_sub8x8);
+            team_sync();             // an edge reads what the previous edge (and, for dir 1, the vertical edges of all lines) wrote
+            const uint32_t bS = (uint32_t)sbs[16 * dir + 4 * e] | ((uint32_t)sbs[16 * dir + 4 * e + 1] << 8) |
+                                ((uint32_t)sbs[16 * dir + 4 * e + 2] << 16) | ((uint32_t)sbs[16 * dir + 4 * e + 3] << 24);
             if (bS)
             {
                 PCAMV_FOR_ITEMS(it, 32)
@@ -248,8 +298,8 @@ PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockP
                         const int bs = (bS >> (8 * (it >> 2))) & 255;
                         if (bs && alpha && beta)
                         {
-                            uint8_t *q = dir == 0 ? py + (size_t)it * rp.stride_y + 4 * e : py + (size_t)(4 * e) * rp.stride_y + it;
-                            db_luma_line(q, dir == 0 ? 1 : rp.stride_y, alpha, beta, db_tc0(dp.qp + dp.alpha_c0_offset, bs));
+                            uint8_t *q = dir == 0 ? sy + it * DB_LS + 4 * e : sy + (4 * e) * DB_LS + it;
+                            db_luma_line(q, dir == 0 ? 1 : DB_LS, alpha, beta, db_tc0(dp.qp + dp.alpha_c0_offset, bs));
                         }
                     }
                     else if (!(e & 1))
@@ -258,12 +308,36 @@ PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockP
                         const int bs = (bS >> (8 * (line >> 1))) & 255;
                         if (bs && alpha_c && beta_c)
                         {
-                            uint8_t *base = pl ? pv : pu;
-                            uint8_t *q = dir == 0 ? base + (size_t)line * rp.stride_c + 2 * e : base + (size_t)(2 * e) * rp.stride_c + line;
-                            db_chroma_line(q, dir == 0 ? 1 : rp.stride_c, alpha_c, beta_c, db_tc0(dp.qp_chroma + dp.alpha_c0_offset, bs) + 1);
+                            uint8_t *base = stage + DB_STAGE_C + pl * 12 * DB_CS + 4 * DB_CS + 4;
+                            uint8_t *q = dir == 0 ? base + line * DB_CS + 2 * e : base + (2 * e) * DB_CS + line;
+                            db_chroma_line(q, dir == 0 ? 1 : DB_CS, alpha_c, beta_c, db_tc0(dp.qp_chroma + dp.alpha_c0_offset, bs) + 1);
                         }
                     }
                 }
+            }
+        }
+    }
+    team_sync();
+    // (4) copy out
+    PCAMV_FOR_ITEMS(it, 32)
+    {
+        if (it < 20)
+        {
+            uint32_t *dst = (uint32_t *)(py + (ptrdiff_t)(it - 4) * rp.stride_y - 4);
+            const uint32_t *src = (const uint32_t *)(stage + DB_STAGE_Y + it * DB_LS);
+#pragma unroll
+            for (int k = 0; k < 5; k++) PCAMV_STV(dst + k, src[k]);
+        }
+        else
+        {
+            const int r = it - 20;
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++)
+            {
+                uint32_t *dst = (uint32_t *)((pl ? pv : pu) + (ptrdiff_t)(r - 4) * rp.stride_c - 4);
+                const uint32_t *src = (const uint32_t *)(stage + DB_STAGE_C + pl * 12 * DB_CS + r * DB_CS);
+#pragma unroll
+                for (int k = 0; k < 3; k++) PCAMV_STV(dst + k, src[k]);
             }
         }
     }

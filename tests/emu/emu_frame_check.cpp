@@ -344,8 +344,11 @@ int main(int argc, char **argv)
             DeblockParams dp; memset(&dp, 0, sizeof(dp));
             dp.qp = fc.tab.qp; dp.qp_chroma = fc.tab.chroma_qp; dp.no_sub8x8_all = !(fc.analyse_inter & 0x20);
             alignas(16) uint8_t db_stage[(DB_STAGE_BYTES + 15) & ~15];
+            std::vector<uint32_t> db_bs(8 * (size_t)n_mb);             // strengths of the whole frame first, as k_deblock_bs does
+            for (int t = 0; t < 32 * n_mb; t++)
+                ((uint8_t *)db_bs.data())[t] = (uint8_t)db_strength_piece(df, dp, (t >> 5) % mb_w, (t >> 5) / mb_w, t & 31);
             for (int mb = 0; mb < n_mb; mb++)
-                deblock_mb(df, rp, dp, mb % mb_w, mb / mb_w, db_stage);
+                deblock_mb(rp, dp, mb % mb_w, mb / mb_w, (const uint8_t *)(db_bs.data() + 8 * (size_t)mb), db_stage);
             rec_frame = sp.hd.frame; rec_q1 = 0;
             for (int mb = 0; mb < n_mb; mb++) rec_q1 += results[mb].early_skip == 2;
             for (int mb = 0; mb < n_mb; mb++) { rec_type[mb] = results[mb].type; rec_mv0[mb] = results[mb].mv[0]; memcpy(&rec_ref[4 * mb], results[mb].ref, 4); }

@@ -85,8 +85,18 @@ __device__ __forceinline__ void rc_st_release(int *p, int v)
 }
 
 // progress[row] = macroblocks of the row finished; row_claim = next row to hand out
-__global__ void __launch_bounds__(RC_WARPS * 32) k_deblock(const DbFrame f, const ReconPlanes rp, const DeblockParams dp, int mb_h,
-                                                           int *progress, int *row_claim)
+// boundary strengths of the whole frame, one thread per 4-pixel piece (32 per macroblock): no dependence on filtered pixels
+__global__ void __launch_bounds__(256) k_deblock_bs(const DbFrame f, const DeblockParams dp, int n_mb, uint8_t *__restrict__ bs)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 32 * n_mb)
+        return;
+    const int mb = t >> 5;
+    bs[t] = (uint8_t)db_strength_piece(f, dp, mb % f.mb_w, mb / f.mb_w, t & 31);
+}
+
+__global__ void __launch_bounds__(RC_WARPS * 32) k_deblock(const ReconPlanes rp, const DeblockParams dp, int mb_w, int mb_h,
+                                                           const uint8_t *__restrict__ bs, int *progress, int *row_claim)
 {
     __shared__ int s_group;
     __shared__ __align__(16) uint8_t s_stage[RC_WARPS][(DB_STAGE_BYTES + 15) & ~15];
@@ -101,11 +111,11 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_deblock(const DbFrame f, cons
         const int row = s_group * RC_WARPS + warp;
         if (row >= mb_h)
             continue;
-        for (int x = 0; x < f.mb_w; x++)
+        for (int x = 0; x < mb_w; x++)
         {
             if (row > 0)
             {
-                const int need = min(x + 2, f.mb_w);
+                const int need = min(x + 2, mb_w);
                 unsigned ns = 32;
                 while (rc_ld_acquire(progress + row - 1) < need)
                 {
@@ -113,7 +123,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_deblock(const DbFrame f, cons
                     if (ns < 1024) ns <<= 1;
                 }
             }
-            deblock_mb(f, rp, dp, x, row, s_stage[warp]);
+            deblock_mb(rp, dp, x, row, bs + 32 * (size_t)(row * mb_w + x), s_stage[warp]);
             __syncwarp();
             if (lane == 0)
             {
@@ -148,7 +158,10 @@ extern "C" int pcamv_reconstruct_ref(pcamv_ctx *ctx, int slot, int poc, int pass
     for (int i = 0; i < fp.n_ref; i++)
         if (fp.ref_slot[i] == slot) return ctx_fail(ctx, "pcamv_reconstruct_ref: the target slot is one of the frame's references", cudaSuccess);
     const int n_mb = fc.mb_w * fc.mb_h;
-    if (!ctx->d_recon_nnz) CK(cudaMalloc(&ctx->d_recon_nnz, n_mb * sizeof(uint16_t)));
+    // one allocation: coefficient flags (uint16 per macroblock), then the 32 boundary strengths of every macroblock
+    const size_t nnz_bytes = ((size_t)n_mb * sizeof(uint16_t) + 255) & ~(size_t)255;
+    if (!ctx->d_recon_nnz) CK(cudaMalloc(&ctx->d_recon_nnz, nnz_bytes + (size_t)32 * n_mb));
+    uint8_t *d_bs = (uint8_t *)ctx->d_recon_nnz + nnz_bytes;
     DevRef &r = ctx->fc.ref[slot];
     r.valid = 0;
     ReconPlanes rp;
@@ -181,8 +194,9 @@ extern "C" int pcamv_reconstruct_ref(pcamv_ctx *ctx, int slot, int poc, int pass
         dp.no_sub8x8_all = !(fc.analyse_inter & 0x20);
         CK(cudaMemsetAsync(ctx->d_progress, 0, (2 * fc.mb_h + 2) * sizeof(int), ctx->stream));
         const int groups = (fc.mb_h + RC_WARPS - 1) / RC_WARPS;
-        k_deblock<<<groups, RC_WARPS * 32, 0, ctx->stream>>>(f, rp, dp, fc.mb_h, ctx->d_progress, ctx->d_progress + fc.mb_h);
-        ctx->launches += 1;
+        k_deblock_bs<<<(32 * n_mb + 255) / 256, 256, 0, ctx->stream>>>(f, dp, n_mb, d_bs);
+        k_deblock<<<groups, RC_WARPS * 32, 0, ctx->stream>>>(rp, dp, fc.mb_w, fc.mb_h, d_bs, ctx->d_progress, ctx->d_progress + fc.mb_h);
+        ctx->launches += 2;
     }
     if (filter_slot(ctx, slot)) return -1;
     CK(cudaStreamSynchronize(ctx->stream));

@@ -179,6 +179,55 @@ PCAMV_DEV void db_chroma_line(uint8_t *pix, int xs, int alpha, int beta, int tc)
     }
 }
 
+// Boundary strength of piece i (4 pixels) of edge e in direction dir (0 = vertical edges) of macroblock (mb_x, mb_y), it = 16 dir
+// + 4 e + i (common/frame.c DEBLOCK_STRENGTH; inter macroblocks only).  0 for an edge that is not filtered at all: the frame
+// border, the inner edges of a P_SKIP macroblock or of a slice whose QP is too low to change anything.  Depends on the frame's
+// final motion state and coefficient flags only — not on any filtered pixel — so the strengths of the whole frame are computed
+// ahead of the filter wavefront, one thread per piece.
+PCAMV_DEV int db_raw_strength(const DbFrame &f, int mb_x, int mb_y, int it, int edge_end, int no_sub8x8)
+{
+    const int mb_xy = mb_y * f.mb_w + mb_x;
+    const int dir = it >> 4, e = (it >> 2) & 3, i = it & 3;
+    if ((e == 0 && (dir ? mb_y == 0 : mb_x == 0)) || (e >= 1 && e >= edge_end))
+        return 0;
+    const int s8 = 2 * f.mb_w, s4 = 4 * f.mb_w;
+    const int mbn_xy = e ? mb_xy : (dir == 0 ? mb_xy - 1 : mb_xy - f.mb_w);
+    const int nx = e ? mb_x : (dir == 0 ? mb_x - 1 : mb_x), ny = e ? mb_y : (dir == 0 ? mb_y : mb_y - 1);
+    const unsigned nz_p = PCAMV_LDV(f.nnz + mb_xy), nz_q = PCAMV_LDV(f.nnz + mbn_xy);
+    const int x = dir == 0 ? e : i, y = dir == 0 ? i : e;
+    const int xn = dir == 0 ? (x - 1) & 3 : x, yn = dir == 0 ? y : (y - 1) & 3;
+    if (((nz_p >> (x + 4 * y)) & 1) || ((nz_q >> (xn + 4 * yn)) & 1))
+        return 2;
+    if (e & no_sub8x8)
+        return 0;
+    // 0x80: "the reference would compare here" — unless it copies the previous piece's strength (db_strength_piece)
+    const int i8p = (2 * mb_y + (y >> 1)) * s8 + 2 * mb_x + (x >> 1), i8q = (2 * ny + (yn >> 1)) * s8 + 2 * nx + (xn >> 1);
+    const int i4p = (4 * mb_y + y) * s4 + 4 * mb_x + x, i4q = (4 * ny + yn) * s4 + 4 * nx + xn;
+    const uint32_t mp = PCAMV_LDV(f.mv4 + i4p), mq = PCAMV_LDV(f.mv4 + i4q);
+    const int differ = PCAMV_LDV(f.ref8 + i8p) != PCAMV_LDV(f.ref8 + i8q) || iabs(mv_x(mp) - mv_x(mq)) >= 4 || iabs(mv_y(mp) - mv_y(mq)) >= 4;
+    return 0x80 | differ;
+}
+PCAMV_DEV int db_strength_piece(const DbFrame &f, const DeblockParams &dp, int mb_x, int mb_y, int it)
+{
+    const int type = PCAMV_LDV(f.type + mb_y * f.mb_w + mb_x);
+    const int qp_thresh = 15 - imin(dp.alpha_c0_offset, dp.beta_offset) - imax(0, dp.chroma_qp_offset);
+    const int edge_end = (type == MB_P_SKIP || dp.qp <= qp_thresh) ? 1 : 4;
+    const int no_sub8x8 = (type != MB_P_8x8 || dp.no_sub8x8_all) ? 1 : 0;
+    int bs = db_raw_strength(f, mb_x, mb_y, it, edge_end, no_sub8x8);
+    if (bs & 0x80)
+    {
+        bs &= 0x7f;
+        // an odd piece of a macroblock without sub-8x8 partitions takes the strength of the piece before it unless that is 2
+        // (the reference's loop carries `prev`; an even piece never copies)
+        if ((it & 1) && no_sub8x8)
+        {
+            const int prev = db_raw_strength(f, mb_x, mb_y, it - 1, edge_end, no_sub8x8) & 0x7f;
+            if (prev != 2) bs = prev;
+        }
+    }
+    return bs;
+}
+
 // Team-private staging of one macroblock's filter neighbourhood: luma rows -4..15 x columns -4..15 (stride 24), U and V rows
 // -4..7 x columns -4..7 (stride 16), and the 32 boundary strengths of its 2 x 4 edges x 4 pieces.
 #define DB_LS 24
@@ -192,16 +241,12 @@ PCAMV_DEV void db_chroma_line(uint8_t *pix, int xs, int alpha, int beta, int tc)
 // ones), then horizontal edges top to bottom.  The caller guarantees that the left neighbour and the row above up to the
 // top-right neighbour are finished (their pixels are read and written here) and that nobody else touches the macroblock's
 // neighbourhood until this call returns — which the wavefront order gives: the right neighbour and the row below start after it.
-// The neighbourhood is copied into team-private memory once (one global round trip instead of one per edge), the 32 boundary
-// strengths are computed one per lane, the edges are filtered in the copy and the copy is written back.
+// The neighbourhood and the macroblock's 32 boundary strengths (bs32, computed ahead: db_strength_piece) are copied into
+// team-private memory once (one global round trip instead of one per edge), the edges are filtered in the copy and the copy is
+// written back.
 // Team layout while filtering: lanes 0..15 = the 16 luma lines of an edge, lanes 16..23 / 24..31 = the 8 lines of U / V.
-PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockParams &dp, int mb_x, int mb_y, uint8_t *stage)
+PCAMV_FN void deblock_mb(const ReconPlanes &rp, const DeblockParams &dp, int mb_x, int mb_y, const uint8_t *bs32, uint8_t *stage)
 {
-    const int mb_xy = mb_y * f.mb_w + mb_x;
-    const int type = PCAMV_LDV(f.type + mb_xy);
-    const int qp_thresh = 15 - imin(dp.alpha_c0_offset, dp.beta_offset) - imax(0, dp.chroma_qp_offset);
-    const int edge_end = (type == MB_P_SKIP || dp.qp <= qp_thresh) ? 1 : 4;
-    const int no_sub8x8 = (type != MB_P_8x8 || dp.no_sub8x8_all) ? 1 : 0;
     const int alpha = db_alpha(dp.qp + dp.alpha_c0_offset), beta = db_beta(dp.qp + dp.beta_offset);
     const int alpha_c = db_alpha(dp.qp_chroma + dp.alpha_c0_offset), beta_c = db_beta(dp.qp_chroma + dp.beta_offset);
     uint8_t *py = rp.y + (size_t)(16 * mb_y) * rp.stride_y + 16 * mb_x;
@@ -213,6 +258,8 @@ PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockP
     // exist in memory on the frame border too, and are not filtered there)
     PCAMV_FOR_ITEMS(it, 32)
     {
+        if (it < 8)
+            ((uint32_t *)sbs)[it] = PCAMV_LDV((const uint32_t *)bs32 + it);
         if (it < 20)
         {
             const uint32_t *src = (const uint32_t *)(py + (ptrdiff_t)(it - 4) * rp.stride_y - 4);
@@ -231,52 +278,6 @@ PCAMV_FN void deblock_mb(const DbFrame &f, const ReconPlanes &rp, const DeblockP
 #pragma unroll
                 for (int k = 0; k < 3; k++) dst[k] = PCAMV_LDV(src + k);
             }
-        }
-    }
-    // (2) boundary strengths, one piece per lane: it = 16 dir + 4 e + i  (common/frame.c DEBLOCK_STRENGTH; inter macroblocks only)
-    {
-        const int s8 = 2 * f.mb_w, s4 = 4 * f.mb_w;
-        PCAMV_FOR_ITEMS(it, 32)
-        {
-            const int dir = it >> 4, e = (it >> 2) & 3, i = it & 3;
-            int bs = 0;
-            const int on_border = e == 0 && (dir ? mb_y == 0 : mb_x == 0);
-            if (!on_border && !(e >= 1 && e >= edge_end))
-            {
-                const int mbn_xy = e ? mb_xy : (dir == 0 ? mb_xy - 1 : mb_xy - f.mb_w);
-                const int nx = e ? mb_x : (dir == 0 ? mb_x - 1 : mb_x), ny = e ? mb_y : (dir == 0 ? mb_y : mb_y - 1);
-                const unsigned nz_p = PCAMV_LDV(f.nnz + mb_xy), nz_q = PCAMV_LDV(f.nnz + mbn_xy);
-                const int x = dir == 0 ? e : i, y = dir == 0 ? i : e;
-                const int xn = dir == 0 ? (x - 1) & 3 : x, yn = dir == 0 ? y : (y - 1) & 3;
-                if (((nz_p >> (x + 4 * y)) & 1) || ((nz_q >> (xn + 4 * yn)) & 1))
-                    bs = 2;
-                else if (!(e & no_sub8x8))
-                {
-                    // (an odd piece of a macroblock without sub-8x8 partitions takes its left / upper neighbour piece's strength
-                    // unless that is 2: resolved below, 0x80 marks "would have been compared")
-                    const int i8p = (2 * mb_y + (y >> 1)) * s8 + 2 * mb_x + (x >> 1), i8q = (2 * ny + (yn >> 1)) * s8 + 2 * nx + (xn >> 1);
-                    const int i4p = (4 * mb_y + y) * s4 + 4 * mb_x + x, i4q = (4 * ny + yn) * s4 + 4 * nx + xn;
-                    const uint32_t mp = PCAMV_LDV(f.mv4 + i4p), mq = PCAMV_LDV(f.mv4 + i4q);
-                    if (PCAMV_LDV(f.ref8 + i8p) != PCAMV_LDV(f.ref8 + i8q) || iabs(mv_x(mp) - mv_x(mq)) >= 4 || iabs(mv_y(mp) - mv_y(mq)) >= 4)
-                        bs = 1;
-                    bs |= 0x80;
-                }
-            }
-            sbs[it] = (uint8_t)bs;
-        }
-        team_sync();
-        PCAMV_FOR_ITEMS(it, 32)
-        {
-            int bs = sbs[it];
-            if (bs & 0x80)
-            {
-                const int prev = sbs[it - ((it & 1) ? 1 : 0)] & 0x7f;       // (even pieces never copy: prev unused)
-                bs &= 0x7f;
-                if ((it & 1) && no_sub8x8 && prev != 2)
-                    bs = prev;
-            }
-            team_sync();                 // every lane has read its neighbour's raw value before anybody overwrites
-            sbs[it] = (uint8_t)bs;
         }
     }
     // (3) the edges, in the copy

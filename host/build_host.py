@@ -26,7 +26,8 @@ HOOK_DECL = ("void pcamv_hook_open( x264_t *h ); void pcamv_hook_close( x264_t *
              "void pcamv_hook_slice_begin( x264_t *h ); void pcamv_hook_slice_end( x264_t *h );\n"
              "void pcamv_hook_analyse_begin( x264_t *h ); void pcamv_hook_analyse_end( x264_t *h );\n"
              "void pcamv_hook_embed( x264_t *h, int an ); void pcamv_hook_ih_satd( int i_pixel, int b_chroma_me );\n"
-             "void pcamv_hook_encoded( x264_t *h ); int pcamv_hook_pass1_on_device( x264_t *h );\n")
+             "void pcamv_hook_encoded( x264_t *h ); int pcamv_hook_pass1_on_device( x264_t *h );\n"
+             "int pcamv_hook_skip_hpel( x264_t *h );\n")
 # encoder/analyse.c additions: a way for the glue to have the lambda*bits tables built before the first macroblock
 # (the reference builds them lazily inside x264_mb_analyse_load_costs, analyse.c:193-229), and the replay version of
 # x264_ih_get_mv_cost — the cost comes from the GPU log, the host state ends up where the reference leaves it

@@ -46,6 +46,8 @@ typedef struct
     int cur_mb, cur_pos;            /* replay cursor */
     int qp_loaded;
     int elide, pass, pinned;                /* pass-2 elision on; pass of the slice being replayed */
+    int host_hpel;                  /* PCAMV_HOST_HPEL=1: the host filters its own half-pel planes even for frames the GPU rebuilds */
+    int skip_hpel_frame;            /* i_frame of the frame whose half-pel planes come back from the GPU instead of x264_frame_filter (-1: none) */
     int host_intra;                 /* PCAMV_HOST_INTRA=1: intra analysis of every P macroblock, as the reference does for its statistics */
     int stream_rows, rows_ready, mb_h;      /* the replayed pass is consumed row by row while the kernel runs (PCAMV_NO_ROW_STREAM=1: wait for its end) */
     double t_row_wait, t_pass1, t_embed;
@@ -56,7 +58,7 @@ typedef struct
      * deblocks the frame into a free slot, and the next frame finds it resident instead of uploading it */
     int recon_on, recon_check, cur_ref_slots[PCAMV_MAX_REFS], cur_n_ref;
     pcamv_recon_patch *patches; int n_patches, cap_patches;
-    long recon_frames, recon_mismatch, recon_patched_mbs;
+    long recon_frames, recon_mismatch, recon_patched_mbs, hpel_frames;
     int fenc_frame;                 /* h->fenc->i_frame currently on the GPU */
     /* reference slots: which frame each GPU slot holds */
     struct { x264_frame_t *fr; int i_frame, i_poc, age, device_built; } slot[PCAMV_MAX_REFS + 2];
@@ -186,6 +188,7 @@ void pcamv_hook_open( x264_t *h )
     g.h = h;
     g.t_total0 = now_s();
     g.fenc_frame = -1;
+    g.skip_hpel_frame = -1;
     if( h->param.i_threads > 1 )
         die_msg( "frame threads are not supported (the reference itself crashes with embedding on)" );
     if( h->param.rc.i_rc_method != X264_RC_CQP || h->param.rc.i_aq_mode )
@@ -245,6 +248,7 @@ void pcamv_hook_open( x264_t *h )
     g.direct = !( ( (s = getenv( "PCAMV_HOST_PASS1" )) && atoi( s ) ) || ( (s = getenv( "PCAMV_HOST_EMBED" )) && atoi( s ) ) ||
                   ( (s = getenv( "PCAMV_CHECK_EMBED" )) && atoi( s ) ) );
     g.host_intra = (s = getenv( "PCAMV_HOST_INTRA" )) && atoi( s );
+    g.host_hpel = (s = getenv( "PCAMV_HOST_HPEL" )) && atoi( s );
     g.mb_h = h->sps->i_mb_height;
     g.stream_rows = g.pinned && !( (s = getenv( "PCAMV_NO_ROW_STREAM" )) && atoi( s ) );
     g.recon_on = (s = getenv( "PCAMV_DEVICE_RECON" )) && atoi( s );
@@ -266,9 +270,9 @@ void pcamv_hook_close( x264_t *h )
         if( f )
         {
             fprintf( f, "{\"p_passes\": %ld, \"replayed_calls\": %ld, \"gpu_launches\": %lld, \"t_gpu_calls\": %.6f, \"t_open\": %.6f, \"t_total\": %.6f, "
-                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld, \"t_ref_upload\": %.6f, \"t_recon\": %.6f, \"direct_pass1\": %ld, \"stale_mismatch\": %ld, \"t_row_wait\": %.6f, \"t_pass1\": %.6f, \"t_embed\": %.6f}\n",
+                        "\"recon_frames\": %ld, \"recon_mismatch\": %ld, \"recon_patched_mbs\": %ld, \"t_ref_upload\": %.6f, \"t_recon\": %.6f, \"direct_pass1\": %ld, \"stale_mismatch\": %ld, \"t_row_wait\": %.6f, \"t_pass1\": %.6f, \"t_embed\": %.6f, \"hpel_frames\": %ld}\n",
                      g.n_passes, g.n_replayed, g.ctx ? pcamv_launch_count( g.ctx ) : 0LL, g.t_gpu, g.t_open, now_s() - g.t_total0,
-                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs, g.t_ref_upload, g.t_recon, g.n_direct, g.stale_mismatch, g.t_row_wait, g.t_pass1, g.t_embed );
+                     g.recon_frames, g.recon_mismatch, g.recon_patched_mbs, g.t_ref_upload, g.t_recon, g.n_direct, g.stale_mismatch, g.t_row_wait, g.t_pass1, g.t_embed, g.hpel_frames );
             fclose( f );
         }
     }
@@ -358,6 +362,9 @@ void pcamv_hook_slice_begin( x264_t *h )
         return;
     t0 = now_s();
     pass = !h->info.embed_flag ? 0 : h->info.firstTime ? 1 : 2;
+    /* a frame the GPU rebuilds as a reference (PCAMV_DEVICE_RECON) gets its half-pel planes from there too: the host skips
+     * x264_frame_filter for it (not in check mode, which compares the host's own planes with the GPU's) */
+    g.skip_hpel_frame = ( g.recon_on && !g.recon_check && !g.host_hpel && h->fdec->b_kept_as_ref ) ? h->fdec->i_frame : -1;
     if( qp != g.qp_loaded )
     {
         pcamv_qp_tables t;
@@ -480,6 +487,12 @@ void pcamv_hook_slice_begin( x264_t *h )
     g.t_gpu += now_s() - t0;
 }
 
+/* x264_fdec_filter_row: does the frame being coded get its half-pel planes from the GPU?  (tools/reftree.py) */
+int pcamv_hook_skip_hpel( x264_t *h )
+{
+    return g.skip_hpel_frame >= 0 && h->fdec->i_frame == g.skip_hpel_frame && h->sh.i_type == SLICE_TYPE_P;
+}
+
 /* P slices: is the intra analysis of this macroblock more than a statistic?  (host/build_host.py stats_only_intra) */
 int pcamv_hook_want_intra( x264_t *h )
 {
@@ -593,6 +606,19 @@ void pcamv_hook_slice_end( x264_t *h )
             die_msg( "no free reference slot" );
         if( pcamv_reconstruct_ref( g.ctx, best, h->fdec->i_poc, g.pass, g.patches, g.n_patches ) )
             die( "pcamv_reconstruct_ref" );
+        if( g.skip_hpel_frame == h->fdec->i_frame )
+        {
+            /* H, V and HV planes, borders included: the GPU's buffers have the host's layout (same stride and padding) */
+            for( k = 1; k < 4; k++ )
+            {
+                const int stride = pcamv_plane_stride( g.ctx, k );
+                if( stride != h->fdec->i_stride[0] )
+                    die_msg( "plane stride of the GPU differs from the host's" );
+                if( pcamv_get_ref_plane( g.ctx, best, k, h->fdec->filtered[k] - (size_t)32 * stride - 32 ) )
+                    die( "pcamv_get_ref_plane" );
+            }
+            g.hpel_frames++;
+        }
         g.slot[best].fr = h->fdec; g.slot[best].i_frame = h->fdec->i_frame; g.slot[best].i_poc = h->fdec->i_poc;
         g.slot[best].age = ++g.tick; g.slot[best].device_built = 1;
         g.recon_frames++;

@@ -111,5 +111,10 @@ def test_host_with_device_built_references(pcamv, cuda_lib, case, tmp_path):
     if case[0] == "cif_qp48_skips":
         assert stats["recon_patched_mbs"] > 0            # the q1 path was really exercised
     # and without the safety net: whatever the GPU built is what the next frames were searched in
+    # — including the half-pel planes the host's own motion compensation reads: they come back from the GPU, x264_frame_filter is
+    # skipped for these frames
     ref_out, out, stats = th.encode_pair(pcamv, *case, workdir=str(tmp_path), extra_env={"PCAMV_DEVICE_RECON": "1"})
     assert th.md5(out) == th.md5(ref_out)
+    assert stats["hpel_frames"] == stats["recon_frames"] >= 2, stats
+    ref_out, out, stats = th.encode_pair(pcamv, *case, workdir=str(tmp_path), extra_env={"PCAMV_DEVICE_RECON": "1", "PCAMV_HOST_HPEL": "1"})
+    assert th.md5(out) == th.md5(ref_out) and stats["hpel_frames"] == 0

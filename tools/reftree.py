@@ -122,6 +122,10 @@ def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra="", drop_rea
     t = sub_exact(t, r"(    /\* init stats \*/\n    memset\( &h->stat\.frame, 0, sizeof\(h->stat\.frame\) \);)",
                   r"\1 pcamv_hook_slice_begin( h );" + (" if( pcamv_hook_pass1_on_device( h ) ) return;" if pass1_on_device else ""), 1, "slice begin")
     if pass1_on_device:
+        # x264_fdec_filter_row (encoder/encoder.c:1041-1046): the half-pel planes of a frame the GPU rebuilds as a reference come
+        # back from the GPU (pcamv_hook_slice_end), the host does not filter them itself
+        t = sub_exact(t, r"(        if\( h->param\.analyse\.i_subpel_refine) \)\n(        \{\n[^\n]*\n            x264_frame_filter\( h, h->fdec, min_y, b_end \);)",
+                      r"\1 && !pcamv_hook_skip_hpel( h ) )\n\2", 1, "half-pel filter of fdec")
         t = sub_exact(t, r"i_frame_size = h->out\.nal\[h->out\.i_nal-1\]\.i_payload;",
                       "i_frame_size = h->out.i_nal ? h->out.nal[h->out.i_nal-1].i_payload : 0;", 1, "frame size of an empty pass")
     t = sub_exact(t, r"\n(\t\tx264_macroblock_analyse\( h \);)",

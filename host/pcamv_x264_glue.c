@@ -54,7 +54,7 @@ typedef struct
     int direct;                     /* pass 1 of an embedding frame never reaches the host's macroblock loop (pcamv_hook_pass1_on_device) */
     int16_t last_mv[16][2]; int have_last_mv; long stale_mismatch;
     int device_forced;              /* the embed stage of this frame ran on the device: pass 2 takes its forced decisions from HBM */
-    /* reference frames built on the device (PCAMV_DEVICE_RECON=1): after the final pass of a P frame the GPU reconstructs and
+    /* reference frames built on the device (default; PCAMV_DEVICE_RECON=0 uploads them instead): after the final pass of a P frame the GPU reconstructs and
      * deblocks the frame into a free slot, and the next frame finds it resident instead of uploading it */
     int recon_on, recon_check, cur_ref_slots[PCAMV_MAX_REFS], cur_n_ref;
     pcamv_recon_patch *patches; int n_patches, cap_patches;
@@ -251,7 +251,7 @@ void pcamv_hook_open( x264_t *h )
     g.host_hpel = (s = getenv( "PCAMV_HOST_HPEL" )) && atoi( s );
     g.mb_h = h->sps->i_mb_height;
     g.stream_rows = g.pinned && !( (s = getenv( "PCAMV_NO_ROW_STREAM" )) && atoi( s ) );
-    g.recon_on = (s = getenv( "PCAMV_DEVICE_RECON" )) && atoi( s );
+    g.recon_on = !( (s = getenv( "PCAMV_DEVICE_RECON" )) && !atoi( s ) );       /* default on; PCAMV_DEVICE_RECON=0: every reference is uploaded */
     g.recon_check = (s = getenv( "PCAMV_CHECK_RECON" )) && atoi( s );
     g.t_open = now_s() - g.t_total0;
 }

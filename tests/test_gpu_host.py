@@ -103,8 +103,8 @@ def test_bitstream_identical_with_full_pass2(pcamv, cuda_lib, case, tmp_path):
 
 
 @pytest.mark.parametrize("env", [{"PCAMV_NO_ROW_STREAM": "1"}, {"PCAMV_HOST_INTRA": "1"}, {"PCAMV_NO_PINNED": "1"},
-                                 {"PCAMV_ROWS_PER_CTA": "4"}, {"PCAMV_BLOCKING_SYNC": "1"}],
-                         ids=["no-row-stream", "host-intra", "no-pinned", "row-groups-4", "blocking-sync"])
+                                 {"PCAMV_ROWS_PER_CTA": "4"}, {"PCAMV_BLOCKING_SYNC": "1"}, {"PCAMV_DEVICE_RECON": "0"}],
+                         ids=["no-row-stream", "host-intra", "no-pinned", "row-groups-4", "blocking-sync", "uploaded-references"])
 @pytest.mark.parametrize("case", [CASES[1], CASES[10]], ids=[CASES[1][0], CASES[10][0]])
 def test_bitstream_identical_with_host_switches(pcamv, cuda_lib, case, env, tmp_path):
     """The switches of the bound host that change HOW it gets its results, never WHAT they are: waiting for the end of the replayed
@@ -115,6 +115,8 @@ def test_bitstream_identical_with_host_switches(pcamv, cuda_lib, case, env, tmp_
     assert md5(out) == md5(ref_out)
     if "PCAMV_NO_ROW_STREAM" in env or "PCAMV_NO_PINNED" in env:
         assert stats["t_row_wait"] == 0.0
+    # by default the P frames become references on the device (and hand their half-pel planes back); the switch uploads them
+    assert (stats["recon_frames"] == 0) == ("PCAMV_DEVICE_RECON" in env)
 
 
 def test_payload_identical(pcamv, cuda_lib, tmp_path):

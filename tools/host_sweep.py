@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """GPU box: whole-encoder md5 parity (host/_build/x264_pcamv vs oracle/_ref/x264_wide) over a random grid of options, sizes
 and seeds.  One line per case; exit code 1 if any case differs."""
-import hashlib, os, random, subprocess, sys, tempfile
+import hashlib, json, os, random, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
@@ -24,11 +24,19 @@ for case in range(n):
     clip = os.path.join(wd, "c.yuv")
     subprocess.check_call([synth, str(w), str(h), "6", "1", str(200 + case), clip, str(noise)])
     outs = []
+    # odd cases run in check mode: every reference picture the GPU builds is compared with the host's own planes before use
+    stats_file = os.path.join(wd, "stats.json")
+    env = dict(os.environ, PCAMV_STATS=stats_file, **({"PCAMV_CHECK_RECON": "1"} if case & 1 else {}))
+    if os.path.exists(stats_file):
+        os.remove(stats_file)
     for exe in (os.path.join(ROOT, "oracle", "_ref", "x264_wide"), os.path.join(ROOT, "host", "_build", "x264_pcamv")):
         o = os.path.join(wd, "o_%d.264" % len(outs))
-        p = subprocess.run([exe] + args + ["-o", o, clip, "%dx%d" % (w, h)], capture_output=True)
+        p = subprocess.run([exe] + args + ["-o", o, clip, "%dx%d" % (w, h)], capture_output=True, env=env)
         outs.append((p.returncode, hashlib.md5(open(o, "rb").read()).hexdigest() if os.path.exists(o) else None, p.stderr[-200:]))
     ok = outs[0][:2] == outs[1][:2]
+    st = json.load(open(stats_file)) if os.path.exists(stats_file) else {}
+    ok = ok and st.get("recon_mismatch", 0) == 0 and st.get("stale_mismatch", 0) == 0
     bad += not ok
-    print("%s | %dx%d noise %d | %s%s" % ("OK  " if ok else "DIFF", w, h, noise, " ".join(args), "" if ok else " | rc %s/%s %s" % (outs[0][0], outs[1][0], outs[1][2].decode("latin-1")[-160:])), flush=True)
+    print("%s | %dx%d noise %d | recon %s%s patched %s direct %s | %s%s" % ("OK  " if ok else "DIFF", w, h, noise, st.get("recon_frames"), " (checked)" if case & 1 else "",
+                                                                           st.get("recon_patched_mbs"), st.get("direct_pass1"), " ".join(args), "" if ok else " | rc %s/%s %s" % (outs[0][0], outs[1][0], outs[1][2].decode("latin-1")[-160:])), flush=True)
 sys.exit(1 if bad else 0)

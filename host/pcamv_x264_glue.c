@@ -290,17 +290,36 @@ void pcamv_hook_close( x264_t *h )
 /* returns 0 when the GPU's planes of slot `s` equal the host's planes of `fr`, else 1 + the first differing plane */
 static int check_device_ref( int s, x264_frame_t *fr )
 {
+    /* picture + borders, row by row: the luma strides of the two sides are equal by construction, the chroma strides are not
+     * for widths that are 16 mod 32 (the host halves its luma stride, common/frame.c:52-60; the GPU aligns to 16), and the
+     * alignment slack behind a row's right border belongs to nobody */
     int k, bad = 0;
     for( k = 0; k < 6 && !bad; k++ )
     {
         const size_t n = pcamv_plane_bytes( g.ctx, k );
         const int stride = pcamv_plane_stride( g.ctx, k ), padv = k < 4 ? 32 : 16, padh = k < 4 ? 32 : 16;
+        const int hstride = fr->i_stride[k < 4 ? 0 : 1];
+        const int width = ( 16 * g.h->sps->i_mb_width >> ( k >= 4 ) ) + 2 * padh, rows = (int)( n / stride );
         uint8_t *dev = malloc( n );
-        const uint8_t *host = ( k < 4 ? fr->filtered[k] : fr->plane[k - 3] ) - (size_t)padv * stride - padh;
+        const uint8_t *host = ( k < 4 ? fr->filtered[k] : fr->plane[k - 3] ) - (size_t)padv * hstride - padh;
+        size_t count = 0;
+        int y, x, fy = -1, fx = -1;
         if( !dev || pcamv_get_ref_plane( g.ctx, s, k, dev ) )
             die( "pcamv_get_ref_plane" );
-        if( stride != fr->i_stride[k < 4 ? 0 : 1] || memcmp( dev, host, n ) )
+        for( y = 0; y < rows; y++ )
+            if( memcmp( dev + (size_t)y * stride, host + (size_t)y * hstride, width ) )
+                for( x = 0; x < width; x++ )
+                    if( dev[(size_t)y * stride + x] != host[(size_t)y * hstride + x] )
+                    {
+                        if( !count ) { fy = y; fx = x; }
+                        count++;
+                    }
+        if( count )
+        {
             bad = k + 1;
+            fprintf( stderr, "x264 [pcamv]: plane %d: %zu bytes differ, the first at line %d column %d of the picture (GPU %d, host %d)\n", k, count,
+                     fy - padv, fx - padh, dev[(size_t)fy * stride + fx], host[(size_t)fy * hstride + fx] );
+        }
         free( dev );
     }
     return bad;

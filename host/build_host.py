@@ -55,6 +55,7 @@ typedef struct { x264_param_t param; cli_opt_t opt; int ret, index, gop; char ou
  * passed through with an = 0. */
 int pcamv_stc_extract( const uint8_t *stego, int n, uint8_t *message, int an, int matrixheight );
 int pcamv_stc_columns( int width, int height, uint32_t *out );
+int pcamv_bitstream_main( int argc, char **argv );
 static int pcamv_extract_main( int argc, char **argv )
 {
     const char *in = argv[2], *out = NULL;
@@ -103,6 +104,9 @@ int main( int argc, char **argv )
     FILE *fo;
     if( argc >= 3 && !strcmp( argv[1], "--extract" ) )
         return pcamv_extract_main( argc, argv );
+    /* the decoder side (host/pcamv_bitstream.c): motion vectors / payload from the .264 alone */
+    if( argc >= 3 && ( !strcmp( argv[1], "--parse-mv" ) || !strcmp( argv[1], "--extract-264" ) ) )
+        return pcamv_bitstream_main( argc, argv );
     if( argc == 4 && !strcmp( argv[1], "--stc-columns" ) )
     {
         uint32_t cols[64]; int w = atoi( argv[2] ), hh = atoi( argv[3] ), i;
@@ -238,7 +242,7 @@ def main():
     stats_only_intra(tree)
     exe = os.path.join(OUT, "x264_pcamv")
     reftree.compile_tree(tree, exe,
-                         extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c")],
+                         extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c"), os.path.join(HERE, "pcamv_bitstream.c")],
                          extra_cflags=["-I" + os.path.join(ROOT, "include")],
                          extra_ldflags=["-L" + PKG, "-lpcamv_cuda", "-Wl,-rpath,$ORIGIN/../../video-steganography-pcamv_b200"])
     print("build_host: built", exe)
@@ -246,7 +250,7 @@ def main():
         # gprof twin (same flags + -pg): where a single-stream encode spends its HOST time; writes gmon.out into the cwd
         exe_pg = os.path.join(OUT, "x264_pcamv_pg")
         reftree.compile_tree(tree, exe_pg,
-                             extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c")],
+                             extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c"), os.path.join(HERE, "pcamv_bitstream.c")],
                              extra_cflags=["-I" + os.path.join(ROOT, "include"), "-pg", "-fno-omit-frame-pointer"],
                              extra_ldflags=["-pg", "-L" + PKG, "-lpcamv_cuda", "-Wl,-rpath,$ORIGIN/../../video-steganography-pcamv_b200"])
         print("build_host: built", exe_pg)

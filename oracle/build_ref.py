@@ -8,6 +8,10 @@ Compiles the C sources where they lie under /root/reference (read-only) into ora
   x264_wide   same, with the CIF constants widened (396 -> MAX_MB, 6336 -> 16*MAX_MB,
               uint16 MV counters -> uint32) so 720p/1080p/4K run
   x264_dump   x264_wide + oracle/ref_hooks.c instrumentation (dumps, counters, timers)
+  x264_dump_conformant   x264_dump with tools/reftree.py::conformance_switch ON: the three statements of pass 2 that make the
+              reference's embedding streams unreadable for a standard decoder are corrected (straight vector copy,
+              i_partition of a forced P_8x8, vector cache of a forced P_SKIP).  NOT the parity reference — its bitstream
+              differs from the reference's by design; it is the checker for the decoder side (tests/test_bitstream.py)
 
 The reference does not link as shipped: the MSVC-only `sscanf_s`/`_strdup`
 are mapped with -D, and the un-vendored S-UNIWARD.lib symbol comes from oracle/ref_stub.c.
@@ -40,13 +44,15 @@ IH_WRAPPER = ("{ int r; pcamv_hook_ih_begin(); r = x264_ih_get_mv_cost_real( h, 
               "  pcamv_hook_ih_end(); return r; }\n")
 
 
-def compile_variant(name, wide, hooks, jobs=8):
+def compile_variant(name, wide, hooks, jobs=8, conformant=False):
     tree = os.path.join(OUT, "build", name)
     reftree.copy_tree(tree)
     if wide:
         reftree.widen(tree)
     if hooks:
         reftree.hook_call_sites(tree, HOOK_DECL, IH_WRAPPER)
+    if conformant:
+        reftree.conformance_switch(tree, "static inline int pcamv_conformant( void ) { return 1; }\n")
     extra = [os.path.join(HERE, "ref_stub.c")] + ([os.path.join(HERE, "ref_hooks.c")] if hooks else [])
     exe = os.path.join(OUT, name)
     # libx264-equivalent archive of the wide build, for leaf-level differential tests
@@ -61,9 +67,9 @@ def main():
         print("build_ref: %s not present; keeping prebuilt oracle/_ref/ as is" % REF)
         return 0
     os.makedirs(OUT, exist_ok=True)
-    want = sys.argv[1:] or ["x264_ref", "x264_wide", "x264_dump"]
+    want = sys.argv[1:] or ["x264_ref", "x264_wide", "x264_dump", "x264_dump_conformant"]
     for name in want:
-        exe = compile_variant(name, wide=name != "x264_ref", hooks=name == "x264_dump")
+        exe = compile_variant(name, wide=name != "x264_ref", hooks=name.startswith("x264_dump"), conformant=name.endswith("_conformant"))
         print("build_ref: built", exe)
     shutil.rmtree(os.path.join(OUT, "build"), ignore_errors=True)
     return 0

@@ -160,3 +160,30 @@ def hook_call_sites(tree, hook_decl, ih_wrapper_body, analyse_extra="", drop_rea
     idx = t.index("\nvoid x264_macroblock_analyse( x264_t *h )\n")
     t = t[:idx] + "\n" + analyse_extra + wrapper + t[idx:]
     write(p, t)
+
+
+def conformance_switch(tree, switch_def):
+    """Three anchored edits in encoder/analyse.c behind `int pcamv_conformant( void )` (`switch_def` declares or defines it).
+    With the switch OFF the code is the reference's, statement for statement.  With it ON pass 2 of an embedding P frame
+    writes a stream a standard H.264 decoder reads back to the encoder's own vectors, so the payload can be extracted from
+    the .264 alone (host/pcamv_bitstream.c; SURVEY.md 8(f) row 4 asks for "a documented fix/flag ... off by default"):
+      1. the copy of the macroblock's vectors into info.cache[].mv (analyse.c:3537-3543, 3626-3632) is a straight copy instead
+         of the unsequenced `idx++` one (SURVEY fact 3), so a partition's cover bit is the LSB of its own vector;
+      2. a macroblock pass 2 forces to P_8x8 also gets h->mb.i_partition = D_8x8 (analyse.c:2871-2875 sets it for P_L0 only;
+         x264_mb_predict_mv, common/macroblock.c:51-79, applies the 16x8 / 8x16 shortcuts to the 8x8 blocks of a macroblock
+         whose i_partition is still what pass 2's own analysis chose — the decoder predicts differently and reads other vectors);
+      3. a macroblock pass 2 forces to P_SKIP leaves through x264_analyse_update_cache like every other skip (analyse.c:2677-2680
+         returns with the vector cache of whatever was analysed last: the encoder then motion-compensates and predicts its
+         neighbours from a vector the decoder never sees — quirk q2)."""
+    p = os.path.join(tree, "encoder/analyse.c")
+    t = read(p)
+    t = sub_exact(t, r'(#include "common/common.h"\n)', r"\1" + switch_def.replace("\\", "\\\\"), 1, "analyse.c include (conformance)")
+    t = sub_exact(t, r"for \(int idx = 0; idx < 16;\) \{",
+                  "for (int idx = 0; idx < 16;) { if( pcamv_conformant() ) { *(uint32_t*)&h->info.cache[mb_xy].mv[idx][0] = "
+                  "*(uint32_t*)&h->mb.cache.mv[0][x264_scan8[idx]][0]; idx++; continue; }", 2, "unsequenced mv copy")
+    t = sub_exact(t, r"(\n\t\t\t\tif \(i_type==P_L0\)\n\t\t\t\t\{\n\t\t\t\t\th->mb\.i_partition = h->info\.cache\[mb_xy\]\.i_partition;)",
+                  r"\n\t\t\t\tif( i_type == P_8x8 && pcamv_conformant() ) h->mb.i_partition = D_8x8;\1", 1, "forced P_8x8 partition")
+    t = sub_exact(t, r"(\n\t\t\tif \(h->mb\.i_type == P_SKIP\)[^\n]*\n\t\t\t\{\n)(\t\t\t\treturn;)",
+                  r"\1\t\t\t\tif( pcamv_conformant() && h->info.embed_flag && !h->info.firstTime ) x264_analyse_update_cache( h, &analysis );\n\2",
+                  1, "forced P_SKIP cache")
+    write(p, t)

@@ -240,6 +240,7 @@ def main():
     reftree.hook_call_sites(tree, HOOK_DECL, IH_WRAPPER, analyse_extra=ANALYSE_EXTRA, drop_real=True, pass1_on_device=True)
     shard_driver(tree)
     stats_only_intra(tree)
+    reftree.conformance_switch(tree, "int pcamv_conformant( void );\n")      # PCAMV_CONFORMANT=1, host/pcamv_x264_glue.c
     exe = os.path.join(OUT, "x264_pcamv")
     reftree.compile_tree(tree, exe,
                          extra_sources=[os.path.join(HERE, "ref_stub.c"), os.path.join(HERE, "pcamv_x264_glue.c"), os.path.join(HERE, "pcamv_bitstream.c")],

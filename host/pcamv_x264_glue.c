@@ -180,6 +180,17 @@ static void die_msg( const char *msg )
 }
 
 /* ---- open / close ---------------------------------------------------------------------------- */
+/* PCAMV_CONFORMANT=1 (off by default: it changes the bitstream): the three statements of the reference's pass 2 that make its
+ * embedding streams unreadable for a standard decoder are corrected - on the host by tools/reftree.py::conformance_switch (the
+ * edits call this function), on the device by pcamv_set_conformant.  The parity reference of this mode is
+ * oracle/_ref/x264_dump_conformant; what it buys is extraction from the .264 alone (host/pcamv_bitstream.c). */
+int pcamv_conformant( void )
+{
+    static int on = -1;
+    if( on < 0 ) { const char *s = getenv( "PCAMV_CONFORMANT" ); on = s && atoi( s ); }
+    return on;
+}
+
 void pcamv_hook_open( x264_t *h )
 {
     pcamv_cfg cfg;
@@ -230,6 +241,8 @@ void pcamv_hook_open( x264_t *h )
     pthread_mutex_lock( &g_mu );
     if( pcamv_open( &g.ctx, &cfg ) )
         die( "pcamv_open" );
+    if( pcamv_conformant() && pcamv_set_conformant( g.ctx, 1 ) )
+        die( "pcamv_set_conformant" );
     /* the reference builds its lambda*bits tables lazily into function-static storage (analyse.c:193-229): do it here, once,
      * under the lock, so that concurrent encoders only ever read them */
     pcamv_glue_load_costs( h, h->param.rc.i_qp_constant );

@@ -236,6 +236,17 @@ typedef struct pcamv_frame_in
 /* Switch pcamv_cfg.pass2_elide of an open context (takes effect with the next launch). */
 int pcamv_set_pass2_elide(pcamv_ctx *ctx, int on);
 
+/* Conformance switch of an open context (0 by default = the reference's behaviour, bit for bit; takes effect with the next
+ * launch).  With it on, the two places where the DEVICE reproduces statements of the reference that make its embedding
+ * streams unreadable for a standard decoder are corrected: a macroblock that pass 2 forces to P_SKIP gets the skip
+ * predictor as its vector (the reference returns without x264_analyse_update_cache, encoder/analyse.c:2677-2680, quirk q2),
+ * and pcamv_embed_prepare copies a macroblock's vectors into the info.cache[] record straight (the reference's unsequenced
+ * `idx++` copy, analyse.c:3537-3543 / 3626-3632, SURVEY fact 3, hands slot k the vector of another block).  The host side
+ * of the same switch is tools/reftree.py::conformance_switch (PCAMV_CONFORMANT=1 in the bound host); with both on, the
+ * payload can be extracted from the .264 alone (host/pcamv_bitstream.c).  The bitstream then differs from the reference's
+ * by design; the parity reference for this mode is oracle/_ref/x264_dump_conformant. */
+int pcamv_set_conformant(pcamv_ctx *ctx, int on);
+
 /* Entries per macroblock in the log arrays of this context: the most its configuration can produce (14 -> 16 for one
  * reference frame), never more than PCAMV_LOG_MAX.  Entry k of macroblock mb is log[mb * pcamv_log_stride(ctx) + k]. */
 int pcamv_log_stride(const pcamv_ctx *ctx);

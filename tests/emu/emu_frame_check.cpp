@@ -57,6 +57,9 @@ int main(int argc, char **argv)
     std::vector<unsigned long long> mvsads((size_t)(2 * fc.me_range + 4) * (2 * fc.me_range + 1));
 
     // PCAMV_EMU_ASYNC=1: run the resumable (split wavefront) form of the analysis; not for configurations with sub-8x8 partitions
+    // PCAMV_EMU_CONFORMANT=1: the dump comes from oracle/_ref/x264_dump_conformant (tools/reftree.py::conformance_switch); the device
+    // logic runs with pcamv_set_conformant's switch on
+    fc.conformant = getenv("PCAMV_EMU_CONFORMANT") && atoi(getenv("PCAMV_EMU_CONFORMANT"));
     const bool async_mode = getenv("PCAMV_EMU_ASYNC") && atoi(getenv("PCAMV_EMU_ASYNC")) && !(fc.analyse_inter & 0x20);
     long n_yield = 0;
     // (4) reconstruction + deblocking of the frame's final pass (pcamv_recon.cuh) against the reference planes the NEXT frame was

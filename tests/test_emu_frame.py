@@ -16,9 +16,12 @@ def checker(pcamv):
     return pcamv.build.build_tool("emu_frame_check", os.path.join(ROOT, "tests", "emu", "emu_frame_check.cpp"))
 
 
-def run_checker(checker, dump, async_mode=False):
-    env = dict(os.environ, PCAMV_EMU_ASYNC="1") if async_mode else None
+def run_checker(checker, dump, async_mode=False, conformant=False, expect_bad=False):
+    env = dict(os.environ, PCAMV_EMU_ASYNC="1" if async_mode else "0", PCAMV_EMU_CONFORMANT="1" if conformant else "0")
     p = subprocess.run([checker, dump], capture_output=True, text=True, env=env)
+    if expect_bad:
+        out = dict(kv.split("=") for kv in p.stdout.split())
+        return {k: int(v) for k, v in out.items()}
     if async_mode:
         assert "searches handed out" in p.stderr and int(p.stderr.split("async:")[1].split()[0]) > 1000, p.stderr
     assert p.returncode == 0, p.stdout + p.stderr
@@ -70,3 +73,32 @@ def test_live_reference_frames(pcamv, checker, args, frames, noise, tmp_path):
     assert n["passes"] >= 2 and n["calls"] > 5000
     if "--partitions" not in args or "p4x4" not in args and "all" not in args:
         run_checker(checker, dump, async_mode=True)
+
+
+CONFORMANT = [
+    ("--me dia --subme 4 --ref 2 --qp 34", "1:4", 2),                      # skip-heavy: macroblocks forced to P_SKIP (quirk q2)
+    ("--me hex --subme 5 --ref 1 --partitions p8x8,p4x4 --qp 22", "1:3", 32),   # forced P_8x8 whose own pass-2 analysis chose 16x8 / 8x16
+    ("--me umh --subme 5 --ref 2 --partitions all", "2:4", 24),
+]
+
+
+@pytest.mark.skipif(not refrun.have_ref("x264_dump_conformant"), reason="oracle/_ref/x264_dump_conformant not built")
+@pytest.mark.parametrize("args,frames,noise", CONFORMANT)
+def test_live_conformant_frames(pcamv, checker, args, frames, noise, tmp_path):
+    """pcamv_set_conformant (include/pcamv.h): the device logic with the switch on against the reference with the same three
+    statements corrected (oracle/_ref/x264_dump_conformant, tools/reftree.py::conformance_switch) - searches, decisions of both
+    passes incl. the vectors of forced skips and the partition of forced P_8x8, cost table, reconstructed reference frame.
+    Negative controls: the switch off against that dump, and the switch on against the unmodified reference, must both differ."""
+    clip = refrun.synth_clip(pcamv, 352, 288, 5, config=1, stream=5, noise16=noise, workdir=str(tmp_path))
+    dump = str(tmp_path / "d.bin")
+    refrun.run_ref(clip, 352, 288, ("--qp 26 --keyint 250 --emrate 0.2 " + args).split(), binary="x264_dump_conformant", dump=dump, frames=frames)
+    n = run_checker(checker, dump, conformant=True)
+    assert n["passes"] >= 2 and n["calls"] > 5000
+    if "--partitions" not in args:
+        run_checker(checker, dump, async_mode=True, conformant=True)
+    off = run_checker(checker, dump, conformant=False, expect_bad=True)
+    assert off["bad_decisions"] > 0
+    refrun.run_ref(clip, 352, 288, ("--qp 26 --keyint 250 --emrate 0.2 " + args).split(), binary="x264_dump", dump=dump, frames=frames)
+    on = run_checker(checker, dump, conformant=True, expect_bad=True)
+    assert on["bad_decisions"] > 0
+    run_checker(checker, dump)          # and the default against the unmodified reference stays exact

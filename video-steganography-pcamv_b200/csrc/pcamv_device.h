@@ -42,6 +42,7 @@ struct DevFrameCtx
     int stride_y, stride_c;          // bytes per row of the padded luma / chroma planes
     int me_method, me_range, subme, chroma_me, mv_range;
     int max_refs, b_cabac, b_fast_pskip, b_dct_decimate, analyse_inter, pass2_elide;
+    int conformant;                  // pcamv_set_conformant: pass 2 without quirk q2, embed stage with a straight vector copy
     const uint8_t *fenc_y, *fenc_u, *fenc_v;   // source frame, pixel (0,0); strides = stride_y / stride_c
     DevRef ref[PCAMV_SLOTS];
     DevTables tab;

@@ -62,7 +62,7 @@ __device__ __forceinline__ int emb_iabs(int v) { return v < 0 ? -v : v; }
 
 // one thread per macroblock: info.cache[mb] as the reference leaves it after pass 1, cover bits and rho of its carriers
 __global__ void k_embed_fill(const MbResult *__restrict__ res, const LogEntry *__restrict__ log, int log_stride,
-                             const PartInfo *__restrict__ subparts, const int *__restrict__ offsets, int n_mb,
+                             const PartInfo *__restrict__ subparts, const int *__restrict__ offsets, int n_mb, int straight_copy,
                              Pass1Mb *__restrict__ p1, uint8_t *__restrict__ cover, float *__restrict__ rho)
 {
     const int mb = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,7 +83,7 @@ __global__ void k_embed_fill(const MbResult *__restrict__ res, const LogEntry *_
     uint32_t mvs[16];
     for (int k = 0; k < 16; k++)
     {
-        mvs[k] = r.mv[B[k]];
+        mvs[k] = r.mv[straight_copy ? k : B[k]];          // pcamv_set_conformant: entry k is the vector of block k
         p.mv[k][0] = (int16_t)emb_mvx(mvs[k]); p.mv[k][1] = (int16_t)emb_mvy(mvs[k]);
     }
     // carriers in the reference's order: slot in info.cache (mv / mv_stego / inter_stego_cost index), split kind per 8x8 block
@@ -242,7 +242,7 @@ extern "C" int pcamv_embed_prepare(pcamv_ctx *ctx, int *length)
     const int n_mb = ctx->fc.mb_w * ctx->fc.mb_h;
     k_embed_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_mb_results, n_mb, ctx->emb_offsets);
     k_embed_fill<<<(n_mb + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_mb_results, ctx->d_log, ctx->log_stride, ctx->d_subparts, ctx->emb_offsets,
-                                                              n_mb, (Pass1Mb *)ctx->emb_pass1, ctx->emb_cover, ctx->emb_rho);
+                                                              n_mb, ctx->fc.conformant, (Pass1Mb *)ctx->emb_pass1, ctx->emb_cover, ctx->emb_rho);
     ctx->launches += 2;
     int len = 0;
     CK(cudaMemcpyAsync(&len, ctx->emb_offsets + n_mb, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1397,7 +1397,9 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
     }
     if (type == MB_P_SKIP)
     {
-        if (!early_skip)
+        if (!early_skip && fc.conformant)
+            update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);    // pcamv_set_conformant: a forced skip leaves like every other skip
+        else if (!early_skip)
         {
             // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
             // and the refs are what the 16x16 search left (its best reference)
@@ -1480,6 +1482,7 @@ PCAMV_FN void analyse_p_mb(MbCtx &c, const uint32_t *prev_mv)
         // forces the sub-partition types and leaves h->mb.i_partition as this pass decided it (analyse.c:2872-2890)
         type = forced->type;
         if (type != MB_P_8x8) partition = forced->partition;
+        else if (fc.conformant) partition = PART_8x8;       // pcamv_set_conformant: a forced P_8x8 is 8x8 in h->mb.i_partition too
 #pragma unroll 1
         for (int i = 0; i < 4; i++)
             cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);
@@ -1566,7 +1569,9 @@ PCAMV_FN int analyse_p_mb_rs(MbCtx &c, const uint32_t *prev_mv)
             pt.type = forced->type;
         if (pt.type == MB_P_SKIP)
         {
-            if (!early_skip)
+            if (!early_skip && fc.conformant)
+                update_cache<SUB8>(c, a, MB_P_SKIP, PART_16x16);
+            else if (!early_skip)
             {
                 // forced to P_SKIP without x264_analyse_update_cache: the MV cache still holds the previous MB's vectors
                 // and the refs are what the 16x16 search left (its best reference)
@@ -1684,6 +1689,7 @@ PCAMV_FN int analyse_p_mb_rs(MbCtx &c, const uint32_t *prev_mv)
         // forces the sub-partition types and leaves h->mb.i_partition as this pass decided it (analyse.c:2872-2890)
         type = forced->type;
         if (type != MB_P_8x8) partition = forced->partition;
+        else if (fc.conformant) partition = PART_8x8;       // pcamv_set_conformant: a forced P_8x8 is 8x8 in h->mb.i_partition too
 #pragma unroll 1
         for (int i = 0; i < 4; i++)
             cache_fill_rect(c, 2 * (i & 1), 2 * (i >> 1), 2, 2, forced->ref[i], 0, 1, 0);

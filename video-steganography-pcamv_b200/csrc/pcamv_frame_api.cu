@@ -267,6 +267,13 @@ extern "C" int pcamv_set_pass2_elide(pcamv_ctx *ctx, int on)
     return 0;
 }
 
+extern "C" int pcamv_set_conformant(pcamv_ctx *ctx, int on)
+{
+    GUARD();
+    ctx->fc.conformant = on != 0;
+    return 0;
+}
+
 extern "C" int pcamv_log_stride(const pcamv_ctx *ctx) { return ctx ? ctx->log_stride : 0; }
 
 extern "C" int pcamv_frame_trace(pcamv_ctx *ctx, int enable, unsigned long long *out)

@@ -69,7 +69,7 @@ EXPORTS = ["pcamv_open", "pcamv_close", "pcamv_last_error", "pcamv_abi_version",
            "pcamv_plane_stride", "pcamv_me_search_batch", "pcamv_me_batch_upload", "pcamv_me_batch_run",
            "pcamv_me_batch_download", "pcamv_launch_count", "pcamv_int_peak",
            "pcamv_analyse_p", "pcamv_frame_upload", "pcamv_frame_run", "pcamv_frame_download", "pcamv_frame_trace", "pcamv_log_stride",
-           "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide",
+           "pcamv_analyse_p_batch", "pcamv_frame_run_batch", "pcamv_host_alloc", "pcamv_host_free", "pcamv_set_pass2_elide", "pcamv_set_conformant",
            "pcamv_group_create", "pcamv_group_destroy", "pcamv_group_analyse_p", "pcamv_group_leave", "pcamv_stc_embed",
            "pcamv_embed_prepare", "pcamv_embed_stc", "pcamv_embed_download", "pcamv_reconstruct_ref",
            "pcamv_analyse_p_begin", "pcamv_analyse_p_batch_begin", "pcamv_group_analyse_p_begin", "pcamv_analyse_p_rows"]
@@ -116,6 +116,7 @@ def load_library(path=None):
     lib.pcamv_frame_trace.argtypes = [vp, ip, vp]; lib.pcamv_frame_trace.restype = ip
     lib.pcamv_log_stride.argtypes = [vp]; lib.pcamv_log_stride.restype = ip
     lib.pcamv_set_pass2_elide.argtypes = [vp, ip]; lib.pcamv_set_pass2_elide.restype = ip
+    lib.pcamv_set_conformant.argtypes = [vp, ip]; lib.pcamv_set_conformant.restype = ip
     lib.pcamv_group_create.argtypes = [C.POINTER(vp), ip]; lib.pcamv_group_create.restype = ip
     lib.pcamv_group_destroy.argtypes = [vp]; lib.pcamv_group_destroy.restype = None
     lib.pcamv_group_analyse_p.argtypes = [vp, vp, C.POINTER(FrameIn), vp, vp]; lib.pcamv_group_analyse_p.restype = ip
@@ -415,6 +416,9 @@ class PcamvContext:
 
     def set_pass2_elide(self, on):
         self._check(self.lib.pcamv_set_pass2_elide(self.handle, int(bool(on))))
+
+    def set_conformant(self, on):
+        self._check(self.lib.pcamv_set_conformant(self.handle, int(bool(on))))
 
     def int_peak_gops(self):
         g = C.c_double()

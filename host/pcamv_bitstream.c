@@ -643,6 +643,7 @@ static void parse_sps( dec_t *d, bsr_t *b )
     s.log2_max_frame_num = br_ue( b ) + 4;
     s.poc_type = br_ue( b );
     if( s.poc_type == 0 ) s.log2_max_poc_lsb = br_ue( b ) + 4;
+    if( (unsigned)s.log2_max_frame_num > 16 || (unsigned)s.log2_max_poc_lsb > 16 ) return;
     else if( s.poc_type == 1 )
     {
         uint32_t n, i;
@@ -654,7 +655,7 @@ static void parse_sps( dec_t *d, bsr_t *b )
     s.mb_w = br_ue( b ) + 1;
     s.mb_h = br_ue( b ) + 1;
     s.frame_mbs_only = br_u( b, 1 );
-    s.valid = !b->err;
+    s.valid = !b->err && s.mb_w >= 1 && s.mb_w <= 1024 && s.mb_h >= 1 && s.mb_h <= 1024;     /* an untrusted stream sizes the arrays */
     d->sps[id] = s;
 }
 static void parse_pps( dec_t *d, bsr_t *b )
@@ -668,13 +669,13 @@ static void parse_pps( dec_t *d, bsr_t *b )
     p.cabac = br_u( b, 1 );
     p.pic_order = br_u( b, 1 );
     if( br_ue( b ) != 0 ) return;                 /* slice groups */
-    p.num_ref_l0 = br_ue( b ) + 1; br_ue( b );
+    p.num_ref_l0 = (int)( br_ue( b ) & 0xff ) + 1; br_ue( b );
     p.weighted_pred = br_u( b, 1 ); br_u( b, 2 );
     p.init_qp = 26 + br_se( b ); br_se( b ); br_se( b );
     p.deblock_control = br_u( b, 1 ); br_u( b, 1 );
     p.redundant = br_u( b, 1 );
     if( br_more_rbsp_data( b ) ) p.transform8x8 = br_u( b, 1 );
-    p.valid = !b->err && p.sps_id < 32;
+    p.valid = !b->err && (unsigned)p.sps_id < 32;
     d->pps[id] = p;
 }
 static void free_picture_arrays( dec_t *d )
@@ -732,7 +733,7 @@ static int parse_slice( dec_t *d, bsr_t *b, int nal_type, int nal_ref_idc, pcamv
     }
     if( p->redundant ) br_ue( b );
     d->num_ref = p->num_ref_l0;
-    if( br_u( b, 1 ) ) d->num_ref = br_ue( b ) + 1;
+    if( br_u( b, 1 ) ) d->num_ref = (int)( br_ue( b ) & 0xff ) + 1;
     if( d->num_ref < 1 || d->num_ref > 32 ) return fail( d, "num_ref_idx_active out of range" );
     if( br_u( b, 1 ) )                            /* ref_pic_list_reordering: only the order of the reference list, not its length */
         for( i = 0; i < 66; i++ )
@@ -841,6 +842,7 @@ static int pcamv_bitstream_walk( const uint8_t *data, size_t size, pcamv_picture
         else if( nal_type == 1 || nal_type == 5 )
         {
             pcamv_picture pic;
+            memset( &pic, 0, sizeof(pic) );
             rc = parse_slice( d, &b, nal_type, nal_ref_idc, &pic );
             if( rc == 1 )
             {
@@ -851,6 +853,7 @@ static int pcamv_bitstream_walk( const uint8_t *data, size_t size, pcamv_picture
             else if( rc < 0 )
             {
                 char where[64];
+                free( pic.mb );
                 snprintf( where, sizeof(where), " (picture %d, macroblock %d)", pictures, d->cur_mb );
                 strncat( d->err, where, sizeof(d->err) - strlen( d->err ) - 1 );
             }

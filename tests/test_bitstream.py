@@ -209,3 +209,13 @@ def test_parser_refuses_what_it_does_not_read(pcamv, tmp_path):
     # --extract-264 needs the rate
     p = subprocess.run([HOST, "--extract-264", stream, "-o", str(tmp_path / "m.bin")], capture_output=True, timeout=60)
     assert p.returncode != 0 and b"--emrate" in p.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("PCAMV_REFERENCE", "/root/reference")), reason="needs the reference's headers to build the sanitizer harness")
+def test_parser_survives_hostile_streams():
+    """The parser reads untrusted bytes: built with AddressSanitizer + UBSan and fed mutated streams (byte flips, truncations,
+    splices, garbage behind valid headers), it must parse or refuse with a message - no sanitizer report, no signal, no leak."""
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bitstream_fuzz.py"), "120", "7"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "0 sanitizer reports, 0 signals" in p.stdout

@@ -13,10 +13,13 @@
  *                                    4x4 arrays: a neighbour is unavailable when it lies outside the picture or has not
  *                                    been decoded yet, which is what the encoder's cache encodes with ref = -2
  *
- * No table of the reference is restated here: the context initialisation, the LPS ranges, the state transitions and the
- * CAVLC code tables are the encoder's own (x264_cabac_context_init, x264_cabac_range_lps, x264_cabac_transition,
- * x264_coeff_token, x264_total_zeros, x264_run_before - this file is linked with the reference's objects like the rest of the
- * bound host), read in the opposite direction.
+ * None of the reference's data tables is restated here: the context initialisation (460 x 4 models), the LPS ranges, the state
+ * transitions and the CAVLC code tables are the encoder's own objects (x264_cabac_context_init, x264_cabac_range_lps,
+ * x264_cabac_transition, x264_coeff_token, x264_total_zeros, x264_run_before - this file is linked with the reference's objects
+ * like the rest of the bound host), read in the opposite direction.  What IS written out below are the syntax-level constants of
+ * H.264 itself, which encoder and decoder necessarily share: the ctxIdxOffsets of the residual elements (Table 9-34: 85 / 105 /
+ * 166 / 227 + the per-category offsets), the bin-to-context maps of mvd and coeff_abs_level_minus1 (9.3.3.1.1.7, 9.3.3.1.3), the
+ * coded_block_pattern mapping of Table 9-4 and the CAVLC level arithmetic of 9.2.2.1.
  *
  * Scope = what the reference can emit on the PCAMV path: one slice per picture, frame macroblocks, P slices
  * whose macroblocks are P_L0 (16x16 / 16x8 / 8x16), P_8x8 (8x8 / 8x4 / 4x8 / 4x4) or P_SKIP, 4x4 transform.  I slices carry

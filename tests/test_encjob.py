@@ -7,6 +7,8 @@ import pytest
 
 import refrun
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 @pytest.mark.skipif(not refrun.have_ref("x264_wide"), reason="oracle/_ref/x264_wide not built")
 def test_job_clip_and_reference_side(pcamv, tmp_path, monkeypatch):
@@ -45,3 +47,18 @@ def test_sharded_job_matches_reference_side(pcamv, cuda_lib, tmp_path, monkeypat
         for r in recs:
             assert r["md5"] == ref["md5"][r["gop"]], "shard %d: bitstream differs" % r["gop"]
             assert r["payload_md5"] == ref["payload_md5"][r["gop"]] and r["n_bits"] == ref["payload_bits"][r["gop"]]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "x264_dump_conformant")) or not os.path.exists(os.path.join(ROOT, "host", "_build", "x264_pcamv")),
+                    reason="oracle/_ref/x264_dump_conformant or host/_build/x264_pcamv not built")
+def test_round_trip_job_through_the_bitstream_alone(tmp_path):
+    """tools/round_trip_job.py on the CPU-sized job, with the conformant reference as the encoder: every GOP's payload read back from
+    its .264 alone is the embedded message (the GPU run of the same tool encodes with x264_pcamv, PCAMV_CONFORMANT=1)."""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "round_trip_job.py"), "tiny", "--encoder", "reference"], capture_output=True, text=True,
+                       env=dict(os.environ, PCAMV_JOB_DIR=str(tmp_path)), timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["payload_equals_embedded_message"] and res["p_frames_extracted"] == 12 and res["payload_bits"] > 500 and res["frames_without_payload"] == 0

@@ -1,10 +1,13 @@
 #!/usr/bin/env python3
 """GPU box: whole-encoder md5 parity (host/_build/x264_pcamv vs oracle/_ref/x264_wide) over a random grid of options, sizes
-and seeds.  One line per case; exit code 1 if any case differs."""
+and seeds.  One line per case; exit code 1 if any case differs.
+    python tools/host_sweep.py [seed] [cases] [conformant]
+`conformant`: the same sweep for PCAMV_CONFORMANT=1 against oracle/_ref/x264_dump_conformant - embedding always on."""
 import hashlib, json, os, random, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+conformant = len(sys.argv) > 3 and sys.argv[3] == "conformant"
 wd = tempfile.mkdtemp(prefix="pcamv_hsweep_")
 synth = os.path.join(ROOT, "build", "pcamv_synth")
 bad = 0
@@ -18,6 +21,8 @@ for case in range(n):
     qp = rnd.choice([18, 26, 32, 38, 44, 50])
     merange = rnd.choice([4, 8, 12, 16]) if me in ("esa", "tesa") else rnd.choice([8, 16, 24])
     em = rnd.choice(["0.1", "0.3", "0.7", "20", "0"])
+    if conformant and em == "0":
+        em = "0.2"
     noise = rnd.choice([0, 2, 8, 32])
     args = ("--qp %d --ref %d --keyint 250 --me %s --merange %d --subme %d %s %s %s" % (
         qp, ref, me, merange, subme, ("--emrate " + em) if em != "0" else "", parts, extra)).split()
@@ -26,10 +31,10 @@ for case in range(n):
     outs = []
     # odd cases run in check mode: every reference picture the GPU builds is compared with the host's own planes before use
     stats_file = os.path.join(wd, "stats.json")
-    env = dict(os.environ, PCAMV_STATS=stats_file, **({"PCAMV_CHECK_RECON": "1"} if case & 1 else {}))
+    env = dict(os.environ, PCAMV_STATS=stats_file, **({"PCAMV_CHECK_RECON": "1"} if case & 1 else {}), **({"PCAMV_CONFORMANT": "1"} if conformant else {}))
     if os.path.exists(stats_file):
         os.remove(stats_file)
-    for exe in (os.path.join(ROOT, "oracle", "_ref", "x264_wide"), os.path.join(ROOT, "host", "_build", "x264_pcamv")):
+    for exe in (os.path.join(ROOT, "oracle", "_ref", "x264_dump_conformant" if conformant else "x264_wide"), os.path.join(ROOT, "host", "_build", "x264_pcamv")):
         o = os.path.join(wd, "o_%d.264" % len(outs))
         p = subprocess.run([exe] + args + ["-o", o, clip, "%dx%d" % (w, h)], capture_output=True, env=env)
         outs.append((p.returncode, hashlib.md5(open(o, "rb").read()).hexdigest() if os.path.exists(o) else None, p.stderr[-200:]))

@@ -25,8 +25,8 @@ def main():
         with tempfile.TemporaryDirectory() as wd:
             clip = refrun.synth_clip(pcamv, w, h, frames, config=synth, stream=1, workdir=wd)
             for cab in ("", "--no-cabac"):
-                for sub in (5, 6, 7):
-                    args = ("--qp 26 --ref 1 --keyint 250 --me umh --subme %d --emrate 0.2 %s" % (sub, cab)).split()
+                for sub, parts in ((5, ""), (6, ""), (7, ""), (5, "--partitions all")):
+                    args = ("--qp 26 --ref 1 --keyint 250 --me umh --subme %d --emrate 0.2 %s %s" % (sub, cab, parts)).split()
                     out = os.path.join(wd, "o.264")
                     t0 = time.perf_counter()
                     p = subprocess.run([exe] + args + ["-o", out, clip, "%dx%d" % (w, h)], capture_output=True)

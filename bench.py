@@ -631,10 +631,27 @@ def main():
             line["encoder_e2e"] = encoder_e2e(pcamv, workdir, local_rank)
             # BASELINE.json config 3 (exhaustive search, merange 32, 4 references): one stream, whole encoder
             line["encoder_e2e_esa"] = encoder_e2e(pcamv, workdir, local_rank, frames=6, ref_args=ESA_ARGS, config=3, tag="esa")
+            line["round_trip"] = round_trip_leg(local_rank)
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def round_trip_leg(device, job="config5-small"):
+    """BASELINE config 5's wording on a bounded job - embed + extract round trip - with nothing but the .264 on the extraction
+    side: tools/round_trip_job.py encodes the job's streams with x264_pcamv in conformant mode, reads every stream
+    back with `x264_pcamv --extract-264` and compares the payload with the embedded message.  A side leg (its own process, bounded
+    by a timeout); a failure is reported in the line, it never takes the bench down."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "round_trip_job.py"), job], capture_output=True, timeout=240,
+                           env=dict(os.environ, PCAMV_DEVICE=str(device)))
+        last = [ln for ln in p.stdout.decode("latin-1").splitlines() if ln.startswith("{")]
+        if not last:
+            return {"job": job, "error": ("rc %d: " % p.returncode) + p.stderr.decode("latin-1")[-300:]}
+        return json.loads(last[-1])
+    except Exception as e:                                     # noqa: BLE001 - a side leg
+        return {"job": job, "error": str(e)[:300]}
 
 
 def encoder_job_leg(pcamv, name, rank, world, local_rank, barrier):

@@ -117,6 +117,7 @@ SYNTAX_CASES = [
     pytest.param((352, 288), 3, "--qp 40 --ref 1 --keyint 250 --me dia --subme 2 --no-cabac", 4, id="cif-qp40-skips-cavlc"),
     pytest.param((208, 112), 6, "--qp 30 --ref 4 --keyint 3 --me hex --subme 4 --partitions all", 16, id="idr-gops-ref4-cabac"),
     pytest.param((208, 112), 6, "--qp 30 --ref 4 --keyint 3 --me hex --subme 4 --partitions all --no-cabac --nf", 16, id="idr-gops-ref4-cavlc"),
+    pytest.param((360, 270), 3, "--qp 26 --ref 2 --keyint 250 --me hex --subme 5", 32, id="non-mod16-size-cabac"),
     pytest.param((640, 368), 2, "--qp 51 --ref 1 --keyint 250 --me hex --subme 5", 32, id="qp51-cabac"),
     pytest.param((640, 368), 2, "--qp 1 --ref 1 --keyint 250 --me hex --subme 5", 32, id="qp1-escapes-cabac"),
     pytest.param((640, 368), 2, "--qp 1 --ref 1 --keyint 250 --me hex --subme 5 --no-cabac", 32, id="qp1-escapes-cavlc"),

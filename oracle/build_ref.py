@@ -12,6 +12,8 @@ Compiles the C sources where they lie under /root/reference (read-only) into ora
               reference's embedding streams unreadable for a standard decoder are corrected (straight vector copy,
               i_partition of a forced P_8x8, vector cache of a forced P_SKIP).  NOT the parity reference — its bitstream
               differs from the reference's by design; it is the checker for the decoder side (tests/test_bitstream.py)
+  x264_dump_rd   x264_dump + a report from x264_rd_cost_mb (encoder/rdo.c:139-172): what x264_macroblock_size_cavlc saw and returned
+              for every macroblock RD mode decision sized (--subme 6 --no-cabac); the checker of csrc/pcamv_cavlc.cuh
 
 The reference does not link as shipped: the MSVC-only `sscanf_s`/`_strdup`
 are mapped with -D, and the un-vendored S-UNIWARD.lib symbol comes from oracle/ref_stub.c.
@@ -44,7 +46,7 @@ IH_WRAPPER = ("{ int r; pcamv_hook_ih_begin(); r = x264_ih_get_mv_cost_real( h, 
               "  pcamv_hook_ih_end(); return r; }\n")
 
 
-def compile_variant(name, wide, hooks, jobs=8, conformant=False):
+def compile_variant(name, wide, hooks, jobs=8, conformant=False, rd=False):
     tree = os.path.join(OUT, "build", name)
     reftree.copy_tree(tree)
     if wide:
@@ -53,6 +55,8 @@ def compile_variant(name, wide, hooks, jobs=8, conformant=False):
         reftree.hook_call_sites(tree, HOOK_DECL, IH_WRAPPER)
     if conformant:
         reftree.conformance_switch(tree, "static inline int pcamv_conformant( void ) { return 1; }\n")
+    if rd:
+        reftree.rd_hook(tree)
     extra = [os.path.join(HERE, "ref_stub.c")] + ([os.path.join(HERE, "ref_hooks.c")] if hooks else [])
     exe = os.path.join(OUT, name)
     # libx264-equivalent archive of the wide build, for leaf-level differential tests
@@ -67,9 +71,10 @@ def main():
         print("build_ref: %s not present; keeping prebuilt oracle/_ref/ as is" % REF)
         return 0
     os.makedirs(OUT, exist_ok=True)
-    want = sys.argv[1:] or ["x264_ref", "x264_wide", "x264_dump", "x264_dump_conformant"]
+    want = sys.argv[1:] or ["x264_ref", "x264_wide", "x264_dump", "x264_dump_conformant", "x264_dump_rd"]
     for name in want:
-        exe = compile_variant(name, wide=name != "x264_ref", hooks=name.startswith("x264_dump"), conformant=name.endswith("_conformant"))
+        exe = compile_variant(name, wide=name != "x264_ref", hooks=name.startswith("x264_dump"), conformant=name.endswith("_conformant"),
+                              rd=name.endswith("_rd"))
         print("build_ref: built", exe)
     shutil.rmtree(os.path.join(OUT, "build"), ignore_errors=True)
     return 0

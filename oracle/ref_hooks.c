@@ -401,6 +401,66 @@ void pcamv_hook_analyse_end( x264_t *h )
     }
 }
 
+/* ---- RD mode decision (x264_dump_rd only: tools/reftree.py::rd_hook puts the call into x264_rd_cost_mb, encoder/rdo.c:139-172) ----
+ * 'RDMB': one record per x264_rd_cost_mb call that sized the macroblock with CAVLC: what x264_macroblock_size_cavlc saw and what it
+ * returned - the checker of csrc/pcamv_cavlc.cuh (tests/emu/emu_cavlc_check.cpp).  'VLC0' (once): the bit LENGTHS of the encoder's own
+ * CAVLC tables (common/vlc.c), the way 'CMV0' carries its lambda*bits tables: a product host would upload them the same way. */
+static int g_vlc_dumped;
+void pcamv_hook_rd_mb( x264_t *h, int i_ssd, int i_bits_encoded, int i_lambda2 )
+{
+    int i, j, n_mvd = 0;
+    int16_t mvd[16][2];
+    int16_t mvp[2];
+    if( !dump_on( h ) || h->sh.i_type != SLICE_TYPE_P )
+        return;
+    if( !g_vlc_dumped )
+    {
+        uint8_t z[5 + 5*64 + 15*16 + 3*4 + 7*16], *q = z;
+        for( i = 0; i < 5; i++ ) *q++ = x264_coeff0_token[i].i_size;
+        for( i = 0; i < 5; i++ ) for( j = 0; j < 64; j++ ) *q++ = x264_coeff_token[i][j].i_size;
+        for( i = 0; i < 15; i++ ) for( j = 0; j < 16; j++ ) *q++ = x264_total_zeros[i][j].i_size;
+        for( i = 0; i < 3; i++ ) for( j = 0; j < 4; j++ ) *q++ = x264_total_zeros_dc[i][j].i_size;
+        for( i = 0; i < 7; i++ ) for( j = 0; j < 16; j++ ) *q++ = x264_run_before[i][j].i_size;
+        rec_begin( "VLC0", sizeof(z) );
+        fwrite( z, 1, sizeof(z), g_dump );
+        g_vlc_dumped = 1;
+    }
+    memset( mvd, 0, sizeof(mvd) );
+#define RD_MVD( idx, width ) do { x264_mb_predict_mv( h, 0, idx, width, mvp ); \
+        mvd[n_mvd][0] = h->mb.cache.mv[0][x264_scan8[idx]][0] - mvp[0]; mvd[n_mvd][1] = h->mb.cache.mv[0][x264_scan8[idx]][1] - mvp[1]; n_mvd++; } while( 0 )
+    if( h->mb.i_type == P_L0 )
+    {
+        if( h->mb.i_partition == D_16x16 ) RD_MVD( 0, 4 );
+        else if( h->mb.i_partition == D_16x8 ) { RD_MVD( 0, 4 ); RD_MVD( 8, 4 ); }
+        else if( h->mb.i_partition == D_8x16 ) { RD_MVD( 0, 2 ); RD_MVD( 4, 2 ); }
+    }
+    else if( h->mb.i_type == P_8x8 )
+        for( i = 0; i < 4; i++ )
+            switch( h->mb.i_sub_partition[i] )
+            {
+                case D_L0_8x8: RD_MVD( 4*i, 2 ); break;
+                case D_L0_8x4: RD_MVD( 4*i, 2 ); RD_MVD( 4*i + 2, 2 ); break;
+                case D_L0_4x8: RD_MVD( 4*i, 1 ); RD_MVD( 4*i + 1, 1 ); break;
+                case D_L0_4x4: RD_MVD( 4*i, 1 ); RD_MVD( 4*i + 1, 1 ); RD_MVD( 4*i + 2, 1 ); RD_MVD( 4*i + 3, 1 ); break;
+            }
+#undef RD_MVD
+    {
+        int32_t hd[20] = { h->i_frame, g_pass, h->mb.i_mb_xy, h->mb.i_type, h->mb.i_partition,
+                           h->mb.i_sub_partition[0], h->mb.i_sub_partition[1], h->mb.i_sub_partition[2], h->mb.i_sub_partition[3],
+                           h->mb.pic.i_fref[0], !!( h->param.analyse.inter & X264_ANALYSE_PSUB8x8 ), h->mb.i_cbp_luma, h->mb.i_cbp_chroma,
+                           h->mb.i_qp - h->mb.i_last_qp, i_ssd, i_bits_encoded, i_lambda2, n_mvd, 0, 0 };
+        int8_t ref[4];
+        for( i = 0; i < 4; i++ ) ref[i] = h->mb.cache.ref[0][x264_scan8[4*i]];
+        rec_begin( "RDMB", sizeof(hd) + sizeof(ref) + sizeof(mvd) + 48 + 24*16*2 + 2*4*2 );
+        fwrite( hd, 1, sizeof(hd), g_dump );
+        fwrite( ref, 1, sizeof(ref), g_dump );
+        fwrite( mvd, 1, sizeof(mvd), g_dump );
+        fwrite( h->mb.cache.non_zero_count, 1, 48, g_dump );
+        fwrite( h->dct.luma4x4, 1, 24*16*2, g_dump );
+        fwrite( h->dct.chroma_dc, 1, 2*4*2, g_dump );
+    }
+}
+
 /* ---- embed stage -------------------------------------------------------------------------------- */
 void pcamv_hook_embed( x264_t *h, int an )
 {

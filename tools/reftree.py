@@ -187,3 +187,14 @@ def conformance_switch(tree, switch_def):
                   r"\1\t\t\t\tif( pcamv_conformant() && h->info.embed_flag && !h->info.firstTime ) x264_analyse_update_cache( h, &analysis );\n\2",
                   1, "forced P_SKIP cache")
     write(p, t)
+
+
+def rd_hook(tree):
+    """oracle variant x264_dump_rd: x264_rd_cost_mb (encoder/rdo.c:139-172, #included by encoder/analyse.c) reports every macroblock it
+    sizes with CAVLC to oracle/ref_hooks.c::pcamv_hook_rd_mb - the inputs and the result of x264_macroblock_size_cavlc."""
+    p = os.path.join(tree, "encoder/rdo.c")
+    t = read(p)
+    t = sub_exact(t, r"(        x264_macroblock_size_cavlc\( h, &bs_tmp \);\n)",
+                  r"\1        pcamv_hook_rd_mb( h, i_ssd, bs_tmp.i_bits_encoded, i_lambda2 );\n", 1, "rd_cost_mb cavlc size")
+    t = "void pcamv_hook_rd_mb( x264_t *h, int i_ssd, int i_bits_encoded, int i_lambda2 );\n" + t
+    write(p, t)

@@ -920,7 +920,7 @@ static int on_picture_extract( void *user, const pcamv_picture *pic )
 {
     cli_t *c = user;
     uint8_t *stego, *msg;
-    int n, an;
+    int n, an, zeros;
     int32_t oh[2], sh[3];
     if( !pic->is_p ) return 0;
     c->p_pictures++;
@@ -930,7 +930,16 @@ static int on_picture_extract( void *user, const pcamv_picture *pic )
      * above 1, bits per carrier vector otherwise */
     an = c->rate > 1 ? (int)c->rate : (int)( c->rate * n );
     msg = malloc( ( an > 0 ? an : 0 ) + 1 );
-    if( an < 1 || n < an || pcamv_stc_extract( stego, n, msg, an, 10 ) < 0 )
+    /* a frame the embedder gave up on (message longer than the cover, syndrome outside the code's range) is recognisable in the
+     * stream: its stego vector stays zeroed (embed.h:349-356) and pass 2 still flips every carrier whose cover bit is 1
+     * (encoder/encoder.c:1848-1855), so EVERY carrier of the written picture has LSB 0.  Such a picture carries nothing. */
+    for( zeros = 0; zeros < n && !stego[zeros]; zeros++ ) ;
+    if( an >= 1 && n >= an && n >= 16 && zeros == n )
+    {
+        fprintf( stderr, "x264 [warning]: picture %d: all %d carriers are even - the embedder gave up on this frame, nothing to extract\n", pic->picture, n );
+        an = 0; c->skipped++;
+    }
+    else if( an < 1 || n < an || pcamv_stc_extract( stego, n, msg, an, 10 ) < 0 )
     {
         if( an >= 1 ) fprintf( stderr, "x264 [warning]: picture %d: cannot extract %d bits from %d carriers, skipped\n", pic->picture, an, n );
         an = 0; c->skipped++;

@@ -220,3 +220,20 @@ def test_parser_survives_hostile_streams():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bitstream_fuzz.py"), "120", "7"], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert "0 sanitizer reports, 0 signals" in p.stdout
+
+
+def test_extractor_recognises_frames_the_embedder_gave_up_on(pcamv, tmp_path):
+    """Where stc_embed gives up (here: messages of a few bits on a 64x48 frame) the reference leaves the stego vector zeroed and pass
+    2 still flips every carrier whose cover bit is 1 - every carrier of the written picture is even.  The decoder side must report
+    such a picture as carrying nothing instead of inventing a payload."""
+    args = "--qp 38 --ref 3 --keyint 250 --me dia --subme 1 --no-dct-decimate"
+    stream, dump = encode(pcamv, "x264_dump_conformant", (64, 48), 4, args + " --emrate 0.1", 32, 461, str(tmp_path))
+    embeds = dump.embeds()
+    messages, stegos = extract_264(stream, "0.1", str(tmp_path))
+    gave_up = 0
+    for e, (_, an, _), (_, n, _, stego) in zip(embeds, messages, stegos):
+        assert n == e["length"] and np.array_equal(stego, e["stego"])
+        if 1 <= e["an"] <= e["length"] and e["length"] >= 16 and not e["stego"].any() and e["cover"].any():
+            gave_up += 1
+            assert an == 0
+    assert gave_up >= 1

@@ -3,7 +3,7 @@
  * SURVEY.md 8(f) row 4.  The reference is an encoder only (x264 build 66 has no decoder, its extractor include is commented
  * out, encoder/analyse.c:43).  This file is the mirror of what the reference WRITES for a P slice, read back:
  *
- *   NAL / SPS / PPS / slice header   encoder/set.c:196-330 (x264_sps_write), :420-470 (x264_pps_write),
+ *   NAL / SPS / PPS / slice header   encoder/set.c:215-355 (x264_sps_write), :429-470 (x264_pps_write),
  *                                    encoder/encoder.c:174-310 (x264_slice_header_write), common/common.c:658-695 (x264_nal_encode)
  *   CABAC macroblock layer           encoder/cabac.c:64-130 (mb_type), :233-330 (cbp, qp_delta, skip, sub partition),
  *                                    :375-505 (ref, mvd), :508-680 (coded_block_flag contexts, residual), :781-1030 (macroblock)
@@ -641,7 +641,7 @@ static void parse_sps( dec_t *d, bsr_t *b )
     {
         if( br_ue( b ) != 1 ) return;             /* chroma_format_idc: 4:2:0 only */
         br_ue( b ); br_ue( b ); br_u( b, 1 );
-        if( br_u( b, 1 ) ) return;                /* scaling matrices: not written for the flat matrix (encoder/set.c:213) */
+        if( br_u( b, 1 ) ) return;                /* scaling matrices: not written for the flat matrix (encoder/set.c:234) */
     }
     s.log2_max_frame_num = br_ue( b ) + 4;
     s.poc_type = br_ue( b );

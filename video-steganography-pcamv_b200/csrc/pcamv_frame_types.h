@@ -66,7 +66,7 @@ struct FrameParams
     MbResult *results;       // [n_mb]
     PartInfo *subparts;      // [n_mb][16], P_8x8 macroblocks only (X264_ANALYSE_PSUB8x8), else null: the up to 16 MV-carrying
                              // blocks of the final mode in the reference's cost-table order (device-internal, not in the ABI)
-    int *row_progress;       // [mb_h] wavefront counters
+    int *row_progress;       // [2*mb_h + 2]: [0, mb_h) wavefront counters (macroblocks finished per row) | [mb_h] group claim counter | [mb_h+1, 2*mb_h+1] row owners (row pool)
     unsigned long long *mvsads;  // --me tesa: [mb_h][mvsads_cap] candidate lists, one per macroblock row (= per lane team), else null
     int mvsads_cap;
     unsigned long long *trace;   // optional [n_mb][2]: globaltimer ns at the start / end of each macroblock (profiling aid)

@@ -487,8 +487,6 @@ static void skip_mb( dec_t *d )
 static int macroblock_layer( dec_t *d, int cabac )
 {
     static const int8_t golomb_to_sub[4] = { D_L0_8x8, D_L0_8x4, D_L0_4x8, D_L0_4x4 };    /* inverse of sub_mb_type_p_to_golomb (encoder/cavlc.c:55-58) */
-    static int8_t golomb_to_inter_cbp[48];
-    static int have_cbp_table = 0;
     int sub[4] = { D_L0_8x8, D_L0_8x8, D_L0_8x8, D_L0_8x8 };
     int type, partition, ref0_only = 0, i, cbp_luma, cbp_chroma;
     int32_t cbp;
@@ -585,21 +583,14 @@ static int macroblock_layer( dec_t *d, int cabac )
     }
     else
     {
-        uint32_t t;
-        if( !have_cbp_table )
-        {
-            /* the encoder's inter_cbp_to_golomb (encoder/cavlc.c:42-47) is Table 9-4 of H.264, inter column, cbp -> codeNum; a
-             * static of that file, so its inverse is built from the standard's own definition of the mapping instead: codeNum
-             * order of the inter column */
-            static const uint8_t inter_cbp_by_code[48] = {
-                0, 16, 1, 2, 4, 8, 32, 3, 5, 10, 12, 15, 47, 7, 11, 13, 14, 6, 9, 31, 35, 37, 42, 44,
-                33, 34, 36, 40, 39, 43, 45, 46, 17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41 };
-            for( i = 0; i < 48; i++ ) golomb_to_inter_cbp[i] = (int8_t)inter_cbp_by_code[i];
-            have_cbp_table = 1;
-        }
-        t = br_ue( d->br );
+        /* codeNum -> coded_block_pattern, inter column of H.264 table 9-4 (the encoder holds the opposite direction in a static
+         * of encoder/cavlc.c:42-47, inter_cbp_to_golomb) */
+        static const uint8_t inter_cbp_by_code[48] = {
+            0, 16, 1, 2, 4, 8, 32, 3, 5, 10, 12, 15, 47, 7, 11, 13, 14, 6, 9, 31, 35, 37, 42, 44,
+            33, 34, 36, 40, 39, 43, 45, 46, 17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41 };
+        const uint32_t t = br_ue( d->br );
         if( t > 47 ) return fail( d, "coded_block_pattern out of range" );
-        cbp_luma = golomb_to_inter_cbp[t] & 15; cbp_chroma = golomb_to_inter_cbp[t] >> 4;
+        cbp_luma = inter_cbp_by_code[t] & 15; cbp_chroma = inter_cbp_by_code[t] >> 4;
     }
     cbp = cbp_luma | ( cbp_chroma << 4 );
     d->cbp[d->cur_mb] = cbp;                      /* the chroma DC flags join below; the neighbours' entries are what the contexts read */

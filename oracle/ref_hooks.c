@@ -448,16 +448,25 @@ void pcamv_hook_rd_mb( x264_t *h, int i_ssd, int i_bits_encoded, int i_lambda2 )
         int32_t hd[20] = { h->i_frame, g_pass, h->mb.i_mb_xy, h->mb.i_type, h->mb.i_partition,
                            h->mb.i_sub_partition[0], h->mb.i_sub_partition[1], h->mb.i_sub_partition[2], h->mb.i_sub_partition[3],
                            h->mb.pic.i_fref[0], !!( h->param.analyse.inter & X264_ANALYSE_PSUB8x8 ), h->mb.i_cbp_luma, h->mb.i_cbp_chroma,
-                           h->mb.i_qp - h->mb.i_last_qp, i_ssd, i_bits_encoded, i_lambda2, n_mvd, 0, 0 };
+                           h->mb.i_qp - h->mb.i_last_qp, i_ssd, i_bits_encoded, i_lambda2, n_mvd, h->mb.i_psy_rd, x264_lambda_tab[h->mb.i_qp] };
         int8_t ref[4];
+        int16_t mv[16][2];
         for( i = 0; i < 4; i++ ) ref[i] = h->mb.cache.ref[0][x264_scan8[4*i]];
-        rec_begin( "RDMB", sizeof(hd) + sizeof(ref) + sizeof(mvd) + 48 + 24*16*2 + 2*4*2 );
+        for( i = 0; i < 16; i++ ) { mv[i][0] = h->mb.cache.mv[0][x264_scan8[i]][0]; mv[i][1] = h->mb.cache.mv[0][x264_scan8[i]][1]; }
+        rec_begin( "RDMB", sizeof(hd) + sizeof(ref) + sizeof(mvd) + 48 + 24*16*2 + 2*4*2 + sizeof(mv) + 4 );
         fwrite( hd, 1, sizeof(hd), g_dump );
         fwrite( ref, 1, sizeof(ref), g_dump );
         fwrite( mvd, 1, sizeof(mvd), g_dump );
         fwrite( h->mb.cache.non_zero_count, 1, 48, g_dump );
         fwrite( h->dct.luma4x4, 1, 24*16*2, g_dump );
         fwrite( h->dct.chroma_dc, 1, 2*4*2, g_dump );
+        fwrite( mv, 1, sizeof(mv), g_dump );              /* the candidate's vectors, block_idx order (for the distortion half) */
+        {
+            /* quirk q1: with b_skip_mc left set x264_macroblock_encode does not motion-compensate (encoder/macroblock.c:611-612) and
+             * the "candidate" is coded against whatever the last analysis left in fdec */
+            int32_t skip_mc = h->mb.b_skip_mc;
+            fwrite( &skip_mc, 4, 1, g_dump );
+        }
     }
 }
 

@@ -39,3 +39,33 @@ def test_cavlc_macroblock_size_equals_reference_rd(pcamv, checker, args, noise, 
     assert n["bad"] == 0 and n["inter"] > 2000 and n["coded"] > 100
     if "--partitions all" in args:
         assert n["sub8x8"] > 0 and n["multi_ref"] > 0
+
+
+RD_CASES = [
+    pytest.param("--qp 26 --ref 1 --me hex", 32, id="qp26"),
+    pytest.param("--qp 26 --ref 3 --me umh --partitions all", 24, id="ref3-sub8x8"),
+    pytest.param("--qp 14 --ref 1 --me hex --no-dct-decimate", 48, id="qp14-no-decimate"),
+    pytest.param("--qp 38 --ref 2 --me dia", 4, id="qp38-sparse"),
+    pytest.param("--qp 26 --ref 1 --me hex --psy-rd 0:0", 32, id="no-psy"),
+]
+
+
+@pytest.fixture(scope="module")
+def rd_checker(pcamv):
+    return pcamv.build.build_tool("emu_rd_check", os.path.join(ROOT, "tests", "emu", "emu_rd_check.cpp"))
+
+
+@pytest.mark.skipif(not refrun.have_ref("x264_dump_rd"), reason="oracle/_ref/x264_dump_rd not built")
+@pytest.mark.parametrize("args,noise", RD_CASES)
+def test_rd_cost_of_inter_candidates_equals_reference(pcamv, rd_checker, args, noise, tmp_path):
+    """Both halves of x264_rd_cost_mb (encoder/rdo.c:139-172) for every inter candidate RD mode decision costed: the distortion
+    (SSD + psy term, csrc/pcamv_rd.cuh) of the candidate as the PRODUCT's device code reconstructs it (recon_mb) and its CAVLC
+    size (csrc/pcamv_cavlc.cuh); also the set of luma blocks that keep coefficients."""
+    clip = refrun.synth_clip(pcamv, 352, 288, 4, config=1, stream=6, noise16=noise, workdir=str(tmp_path))
+    dump = str(tmp_path / "d.bin")
+    refrun.run_ref(clip, 352, 288, ("--keyint 250 --emrate 0.2 --subme 6 --no-cabac " + args).split(), binary="x264_dump_rd", dump=dump, frames="1:3")
+    p = subprocess.run([rd_checker, dump], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr[-1500:]
+    n = {k: int(v) for k, v in (kv.split("=") for kv in p.stdout.split())}
+    assert n["candidates"] > 1500 and n["bad_distortion"] == 0 and n["bad_bits"] == 0 and n["bad_kept_mask"] == 0
+    assert (n["with_psy"] == 0) == ("--psy-rd 0:0" in args)

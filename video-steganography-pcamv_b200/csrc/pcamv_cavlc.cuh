@@ -2,7 +2,7 @@
 // encoder/cavlc.c:61-198,285-600 compiled with RDO_SKIP_BS, "produces exactly the same bit count as a normal encode") returns
 // for a P_L0 / P_8x8 macroblock, as a host/device function.
 //
-// STATUS: the first parity-tested piece of RD mode decision (--subme 6 / 7), NOT on the product path: no kernel
+// STATUS: the first parity-tested piece of RD mode decision (the second is csrc/pcamv_rd.cuh) (--subme 6 / 7), NOT on the product path: no kernel
 // calls it yet and the bound host still refuses --subme >= 6.  Why this piece first: with --no-cabac the size of a macroblock
 // depends on nothing but the macroblock itself, the motion-vector predictors and the coefficient counts of its left / top
 // neighbours — all of which the wavefront already orders — whereas CABAC sizes depend on the live arithmetic-coder state

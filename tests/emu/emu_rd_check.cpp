@@ -48,7 +48,7 @@ int main(int argc, char **argv)
 
     MbWork work;
     std::vector<uint8_t> rec_y, rec_u, rec_v; std::vector<uint16_t> rec_nnz(n_mb);
-    long n = 0, bad_ssd = 0, bad_bits = 0, bad_nnz = 0, n_intra = 0, n_psy = 0, n_q1 = 0;
+    long n = 0, bad_ssd = 0, bad_bits = 0, bad_nnz = 0, n_intra = 0, n_psy = 0, n_q1 = 0, bad_device = 0;
     for (size_t ri = 0; ri < d.recs.size(); ri++)
     {
         if (strcmp(d.recs[ri].tag, "SLCB")) continue;
@@ -129,11 +129,48 @@ int main(int argc, char **argv)
             for (int i = 0; i < 16; i++)
                 if (m.coded[i]) want_mask |= 1 << (((i & 1) | ((i >> 1) & 2)) + 4 * (((i >> 1) & 1) | ((i >> 2) & 2)));
             if (want_mask != rec_nnz[mb]) { if (bad_nnz < 5) fprintf(stderr, "frame %d mb %d: kept-coefficient mask %04x, reference %04x\n", hd[0], mb, rec_nnz[mb], want_mask); bad_nnz++; }
-            // (3) size
+            // (3) size, from the reference's coefficient arrays
             const int got_bits = cavlc_mb_inter_bits(z, m);
             if (got_bits != want_bits) { if (bad_bits < 5) fprintf(stderr, "frame %d mb %d: %d bits, reference %d\n", hd[0], mb, got_bits, want_bits); bad_bits++; }
+            // (4) the same candidate once more, device-only: motion compensation, the device's OWN levels / kept flags / cbp, then the
+            //     residual path the product runs, distortion and size from nothing the reference computed but the vector differences
+            //     and the neighbours' coefficient counts
+            {
+                rd_mc_inter(c, res);
+                static RdLevels lv;
+                rd_levels_mb(c, lv);
+                encode_mb_residual(c);
+                const int ssd2 = rd_distortion_mb(work.fenc_y, work.pred_y, work.fenc_u, work.pred_u, work.fenc_v, work.pred_v, psy_rd, lambda);
+                CavlcMb m2 = m;
+                m2.coef = lv.coef; m2.chroma_dc = lv.chroma_dc; m2.cbp_luma = lv.cbp_luma; m2.cbp_chroma = lv.cbp_chroma;
+                memcpy(m2.coded, lv.coded, 26);
+                const int bits2 = cavlc_mb_inter_bits(z, m2);
+                const int cost = ssd2 + ((bits2 * hd[16] + 128) >> 8), want_cost = want_ssd + ((want_bits * hd[16] + 128) >> 8);
+                if (cost != want_cost || lv.cbp_luma != hd[11] || lv.cbp_chroma != hd[12])
+                {
+                    if (bad_device < 5)
+                        fprintf(stderr, "frame %d mb %d type %d: device-only RD cost %d (ssd %d, %d bits, cbp %x/%d), reference %d (ssd %d, %d bits, cbp %x/%d)\n",
+                                hd[0], mb, m.type, cost, ssd2, bits2, lv.cbp_luma, lv.cbp_chroma, want_cost, want_ssd, want_bits, hd[11], hd[12]);
+                    if (bad_device < 3 && getenv("PCAMV_EMU_RD_DEBUG"))
+                    {
+                        for (int pl = 0; pl < 2; pl++)
+                            fprintf(stderr, "   chroma dc %d: device %d %d %d %d (coded %d), reference %d %d %d %d (coded %d)\n", pl, lv.chroma_dc[pl][0], lv.chroma_dc[pl][1], lv.chroma_dc[pl][2], lv.chroma_dc[pl][3], lv.coded[24 + pl],
+                                    m.chroma_dc[pl][0], m.chroma_dc[pl][1], m.chroma_dc[pl][2], m.chroma_dc[pl][3], m.coded[24 + pl]);
+                        for (int i = 0; i < 24; i++)
+                            if (lv.coded[i] || m.coded[i])
+                            {
+                                fprintf(stderr, "   block %d coded %d/%d device:", i, lv.coded[i], m.coded[i]);
+                                for (int k = 0; k < 16; k++) fprintf(stderr, " %d", lv.coef[i][k]);
+                                fprintf(stderr, "  reference:");
+                                for (int k = 0; k < 16; k++) fprintf(stderr, " %d", m.coef[i][k]);
+                                fprintf(stderr, "\n");
+                            }
+                    }
+                    bad_device++;
+                }
+            }
         }
     }
-    printf("candidates=%ld bad_distortion=%ld bad_bits=%ld bad_kept_mask=%ld intra_skipped=%ld with_psy=%ld q1_skipped=%ld\n", n, bad_ssd, bad_bits, bad_nnz, n_intra, n_psy, n_q1);
-    return (bad_ssd || bad_bits || bad_nnz) ? 1 : 0;
+    printf("candidates=%ld bad_distortion=%ld bad_bits=%ld bad_kept_mask=%ld bad_device_only_cost=%ld intra_skipped=%ld with_psy=%ld q1_skipped=%ld\n", n, bad_ssd, bad_bits, bad_nnz, bad_device, n_intra, n_psy, n_q1);
+    return (bad_ssd || bad_bits || bad_nnz || bad_device) ? 1 : 0;
 }

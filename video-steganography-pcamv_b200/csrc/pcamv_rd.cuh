@@ -93,4 +93,105 @@ PCAMV_RD_HD static inline int rd_distortion_mb(const uint8_t *fenc_y, const uint
     return ssd + psy;
 }
 
+// ---- the quantised levels of a candidate, from the device's own residual path ---------------------------------------------------
+// Only when the frame-level device code is in the translation unit (pcamv_frame.cuh / pcamv_cost.cuh included first).
+#if defined(PCAMV_FN)
+struct RdLevels                      // what x264_macroblock_encode leaves in h->dct / h->mb for the entropy coder, inter macroblock
+{
+    int16_t coef[24][16];            // h->dct.luma4x4: zigzag-scanned levels, 16 luma blocks (block_idx order) + 8 chroma AC blocks ([0] = 0)
+    int16_t chroma_dc[2][4];         // h->dct.chroma_dc
+    uint8_t coded[26];               // non_zero_count != 0 of the 16 + 8 + 2 blocks (after decimation)
+    int cbp_luma, cbp_chroma;
+};
+
+// Call with the motion-compensated prediction staged in c.w.pred_* (before encode_mb_residual adds the residual to it).  Same
+// arithmetic and the same decisions as encode_mb_residual (csrc/pcamv_cost.cuh = encoder/macroblock.c:690-755 luma, :277-372
+// chroma), but it keeps what that function only passes through: the levels.  One lane (see the header comment).
+PCAMV_DEV void rd_levels_mb(MbCtx &c, RdLevels &o)
+{
+    const DevTables &t = c.fc.tab;
+    const unsigned long long zz = 0xfbeda7369c852140ull;      // zigzag position i lives at dct[x][y], flattened 4*x+y (decimate_score)
+    int score[24], nz[24];
+    int16_t dcs[8];
+    for (int it = 0; it < 24; it++)
+    {
+        const int ch = it >= 16;
+        int d[16], co[16];
+        if (!ch)
+        {
+            const int bx = (it & 1) | ((it >> 1) & 2), by = ((it >> 1) & 1) | ((it >> 2) & 2);
+            load_residual(c.w.fenc_y + 64 * by + 4 * bx, 16, c.w.pred_y + 64 * by + 4 * bx, 16, d);
+        }
+        else
+        {
+            const int pl = (it - 16) >> 2, blk = (it - 16) & 3;
+            const uint8_t *fe = pl ? c.w.fenc_v : c.w.fenc_u, *pr = pl ? c.w.pred_v : c.w.pred_u;
+            load_residual(fe + 32 * (blk >> 1) + 4 * (blk & 1), 8, pr + 32 * (blk >> 1) + 4 * (blk & 1), 8, d);
+        }
+        dct4x4<1>(d, co);
+        if (ch) { dcs[it - 16] = (int16_t)co[0]; co[0] = 0; }
+        nz[it] = quant4x4<1>(co, t.quant4_mf[ch], t.quant4_bias[ch]);
+        int16_t q[16];
+        for (int i = 0; i < 16; i++) q[i] = (int16_t)co[i];
+        score[it] = nz[it] ? decimate_score(q, ch) : 0;
+        for (int i = 0; i < 16; i++) o.coef[it][i] = q[(zz >> (4 * i)) & 15];
+    }
+    const int b_decimate = c.fc.b_dct_decimate;
+    int s8[4], any8[4], mb = 0;
+    for (int i = 0; i < 4; i++)
+    {
+        s8[i] = 0; any8[i] = 0;
+        for (int j = 0; j < 4; j++) { any8[i] |= nz[4 * i + j]; s8[i] += score[4 * i + j]; }
+        mb += s8[i];
+    }
+    o.cbp_luma = 0;
+    for (int i = 0; i < 4; i++)
+        if (b_decimate ? (mb >= 6 && s8[i] >= 4) : any8[i]) o.cbp_luma |= 1 << i;
+    for (int it = 0; it < 16; it++) o.coded[it] = (uint8_t)(((o.cbp_luma >> (it >> 2)) & 1) && nz[it]);
+    int any_ac = 0, any_dc = 0;
+    for (int pl = 0; pl < 2; pl++)
+    {
+        int nz_ac = 0, sc = 0;
+        for (int j = 0; j < 4; j++) { nz_ac |= nz[16 + 4 * pl + j]; sc += score[16 + 4 * pl + j]; }
+        const int b0 = dcs[4 * pl], b1 = dcs[4 * pl + 1], b2 = dcs[4 * pl + 2], b3 = dcs[4 * pl + 3];
+        const int D0 = b0 + b1, D1 = b2 + b3, D2 = b0 - b1, D3 = b2 - b3;
+        const int mf = t.quant4_mf[1][0] >> 1, bias = t.quant4_bias[1][0] << 1;
+        // dct2x2dc + quant_2x2_dc + zigzag_scan_2x2_dc (common/dct.c:87-105, quant.c:63-75); the reference's 2x2 array is indexed
+        // [x][y] of the 4x4 block inside the plane, so its scan order is: sum, horizontal difference, vertical difference, diagonal
+        o.chroma_dc[pl][0] = (int16_t)quant_one((int16_t)(D0 + D1), mf, bias);
+        o.chroma_dc[pl][1] = (int16_t)quant_one((int16_t)(D2 + D3), mf, bias);
+        o.chroma_dc[pl][2] = (int16_t)quant_one((int16_t)(D0 - D1), mf, bias);
+        o.chroma_dc[pl][3] = (int16_t)quant_one((int16_t)(D2 - D3), mf, bias);
+        const int nz_dc = (o.chroma_dc[pl][0] | o.chroma_dc[pl][1] | o.chroma_dc[pl][2] | o.chroma_dc[pl][3]) != 0;
+        const int keep_ac = !((b_decimate && sc < 7) || !nz_ac);
+        for (int j = 0; j < 4; j++) o.coded[16 + 4 * pl + j] = (uint8_t)(keep_ac && nz[16 + 4 * pl + j]);
+        o.coded[24 + pl] = (uint8_t)nz_dc;
+        any_ac |= keep_ac; any_dc |= nz_dc;
+    }
+    o.cbp_chroma = any_ac ? 2 : any_dc ? 1 : 0;
+}
+
+// the motion compensation of a candidate into c.w.pred_* (the first half of recon_mb, csrc/pcamv_recon.cuh, verbatim)
+PCAMV_FN void rd_mc_inter(MbCtx &c, const MbResult &r)
+{
+    init_limits(c);
+#pragma unroll 1
+    for (int i8 = 0; i8 < 4; i8++)
+    {
+        const int slot = c.fp.ref_slot[r.ref[i8]];
+        const uint32_t m0 = r.mv[4 * i8];
+        if (r.mv[4 * i8 + 1] == m0 && r.mv[4 * i8 + 2] == m0 && r.mv[4 * i8 + 3] == m0)
+            mc_rect(c, slot, 8 * (i8 & 1), 8 * (i8 >> 1), 8, 8, clip3(mv_x(m0), c.mv_min[0], c.mv_max[0]), clip3(mv_y(m0), c.mv_min[1], c.mv_max[1]));
+        else
+#pragma unroll 1
+            for (int j = 0; j < 4; j++)
+            {
+                const uint32_t m = r.mv[4 * i8 + j];
+                mc_rect(c, slot, 8 * (i8 & 1) + 4 * (j & 1), 8 * (i8 >> 1) + 4 * (j >> 1), 4, 4,
+                        clip3(mv_x(m), c.mv_min[0], c.mv_max[0]), clip3(mv_y(m), c.mv_min[1], c.mv_max[1]));
+            }
+    }
+}
+#endif
+
 } // namespace pcamv

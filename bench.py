@@ -238,7 +238,8 @@ def run_reference_arm(args, pcamv, rank, world):
     v = cand / t / 1e6
     sample = ("%d concurrent reference encoder processes (one per host core), each a whole %d-frame 1080p clip per step (%d P frames, both "
               "passes each, %d reference-counted candidates in total); time = the slowest process's seconds inside x264_macroblock_analyse "
-              "of the P slices" % (cores, CLIP_FRAMES, p_frames, cand))
+              "of the P slices (its border expansion and half-pel filter, x264_frame_filter, are NOT in this time although the GPU arm's "
+              "e2e includes them through pcamv_put_ref: the time base favours the reference)" % (cores, CLIP_FRAMES, p_frames, cand))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mcandidates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 / (p_frames / cores), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",

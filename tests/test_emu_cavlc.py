@@ -69,3 +69,16 @@ def test_rd_cost_of_inter_candidates_equals_reference(pcamv, rd_checker, args, n
     n = {k: int(v) for k, v in (kv.split("=") for kv in p.stdout.split())}
     assert n["candidates"] > 1500 and n["bad_distortion"] == 0 and n["bad_bits"] == 0 and n["bad_kept_mask"] == 0
     assert (n["with_psy"] == 0) == ("--psy-rd 0:0" in args)
+
+
+@pytest.mark.skipif(not os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")), reason="nvcc not present")
+def test_rd_pieces_compile_for_sm_100a(tmp_path):
+    """The RD pieces are host/device code: a kernel that runs a candidate through motion compensation, kept levels, the product's
+    residual path, distortion and CAVLC size compiles for sm_100a (tools/probes/rd_compile_probe.cu; compile only, nothing launches
+    it - the pieces are not on the product path)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    p = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xptxas", "-v", "-c",
+                        os.path.join(ROOT, "tools", "probes", "rd_compile_probe.cu"), "-o", str(tmp_path / "rd_probe.o")],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert "k_rd_cost_probe" in p.stderr and "sm_100a" in p.stderr

@@ -212,7 +212,8 @@ def test_parser_refuses_what_it_does_not_read(pcamv, tmp_path):
     assert p.returncode != 0 and b"--emrate" in p.stderr
 
 
-@pytest.mark.skipif(not os.path.isdir(os.environ.get("PCAMV_REFERENCE", "/root/reference")), reason="needs the reference's headers to build the sanitizer harness")
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("PCAMV_REFERENCE", "/root/reference")) or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libx264_wide.a")),
+                    reason="needs the reference's headers and oracle/_ref/libx264_wide.a to build the sanitizer harness")
 def test_parser_survives_hostile_streams():
     """The parser reads untrusted bytes: built with AddressSanitizer + UBSan and fed mutated streams (byte flips, truncations,
     splices, garbage behind valid headers), it must parse or refuse with a message - no sanitizer report, no signal, no leak."""

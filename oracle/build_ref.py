@@ -57,6 +57,7 @@ def compile_variant(name, wide, hooks, jobs=8, conformant=False, rd=False):
         reftree.conformance_switch(tree, "static inline int pcamv_conformant( void ) { return 1; }\n")
     if rd:
         reftree.rd_hook(tree)
+        reftree.intra_hook(tree)
     extra = [os.path.join(HERE, "ref_stub.c")] + ([os.path.join(HERE, "ref_hooks.c")] if hooks else [])
     exe = os.path.join(OUT, name)
     # libx264-equivalent archive of the wide build, for leaf-level differential tests

@@ -470,6 +470,62 @@ void pcamv_hook_rd_mb( x264_t *h, int i_ssd, int i_bits_encoded, int i_lambda2 )
     }
 }
 
+/* ---- intra analysis (x264_dump_rd only: tools/reftree.py::intra_hook wraps x264_mb_analyse_intra, encoder/analyse.c:628-879) ----------
+ * 'INTR': one record per call: what the 16x16 / chroma mode analysis saw (source macroblock, the reconstructed border pixels of the
+ * neighbours, which neighbours exist, lambda) and what it decided - the checker of csrc/pcamv_intra.cuh (tests/emu/emu_intra_check.cpp). */
+void pcamv_hook_intra( x264_t *h, int lambda, int i_satd_inter, int satd16, int pred16, const int *dir16, int satd_c, int pred_c, int satd4, const int *pred4,
+                       int i_qp, int i_mbrd, int b_fast_intra, int i_satd_i8x8 )
+{
+    int i, pl;
+    if( !dump_on( h ) )
+        return;
+    {
+        int32_t hd[20] = { h->i_frame, g_pass, h->mb.i_mb_xy, h->sh.i_type, !!( h->mb.i_neighbour & MB_LEFT ), !!( h->mb.i_neighbour & MB_TOP ),
+                           !!( h->mb.i_neighbour & MB_TOPLEFT ), lambda, i_satd_inter, satd16, pred16, dir16[0], dir16[1], dir16[2], dir16[3],
+                           satd_c, pred_c, satd4, h->mb.b_chroma_me, 0 };
+        uint8_t pix[256 + 2*64], border[33 + 2*17];
+        int32_t p4[16];
+        for( i = 0; i < 16; i++ ) memcpy( pix + 16*i, h->mb.pic.p_fenc[0] + i*FENC_STRIDE, 16 );
+        for( pl = 0; pl < 2; pl++ )
+            for( i = 0; i < 8; i++ ) memcpy( pix + 256 + 64*pl + 8*i, h->mb.pic.p_fenc[1 + pl] + i*FENC_STRIDE, 8 );
+        /* luma: topleft, top[16], left[16]; chroma: topleft, top[8], left[8] per plane */
+        border[0] = h->mb.pic.p_fdec[0][-FDEC_STRIDE - 1];
+        for( i = 0; i < 16; i++ ) { border[1 + i] = h->mb.pic.p_fdec[0][-FDEC_STRIDE + i]; border[17 + i] = h->mb.pic.p_fdec[0][i*FDEC_STRIDE - 1]; }
+        for( pl = 0; pl < 2; pl++ )
+        {
+            uint8_t *b = border + 33 + 17*pl, *f = h->mb.pic.p_fdec[1 + pl];
+            b[0] = f[-FDEC_STRIDE - 1];
+            for( i = 0; i < 8; i++ ) { b[1 + i] = f[-FDEC_STRIDE + i]; b[9 + i] = f[i*FDEC_STRIDE - 1]; }
+        }
+        for( i = 0; i < 16; i++ ) p4[i] = pred4[i];
+        {
+            /* for the 4x4 modes: qp and the analysis switches, which neighbours every 4x4 block has, the cached prediction modes of the
+             * blocks left of / above the macroblock, the four pixels right of the top row, the intra quantiser of this qp */
+            int32_t x4[4] = { i_qp, i_mbrd, b_fast_intra, i_satd_i8x8 };
+            uint8_t nb4[16], tr[4];
+            int8_t lm[4], tm[4];
+            static const int left_idx[4] = { 0, 2, 8, 10 }, top_idx[4] = { 0, 1, 4, 5 };
+            for( i = 0; i < 16; i++ ) nb4[i] = (uint8_t)h->mb.i_neighbour4[i];
+            for( i = 0; i < 4; i++ )
+            {
+                lm[i] = h->mb.cache.intra4x4_pred_mode[x264_scan8[left_idx[i]] - 1];
+                tm[i] = h->mb.cache.intra4x4_pred_mode[x264_scan8[top_idx[i]] - 8];
+                tr[i] = h->mb.pic.p_fdec[0][-FDEC_STRIDE + 16 + i];
+            }
+            rec_begin( "INTR", sizeof(hd) + sizeof(pix) + sizeof(border) + sizeof(p4) + sizeof(x4) + 16 + 4 + 4 + 4 + 32 + 32 + 6*16*4 );
+            fwrite( hd, 1, sizeof(hd), g_dump );
+            fwrite( pix, 1, sizeof(pix), g_dump );
+            fwrite( border, 1, sizeof(border), g_dump );
+            fwrite( p4, 1, sizeof(p4), g_dump );
+            fwrite( x4, 1, sizeof(x4), g_dump );
+            fwrite( nb4, 1, 16, g_dump ); fwrite( lm, 1, 4, g_dump ); fwrite( tm, 1, 4, g_dump ); fwrite( tr, 1, 4, g_dump );
+            fwrite( h->quant4_mf[CQM_4IY][i_qp], 2, 16, g_dump );
+            fwrite( h->quant4_bias[CQM_4IY][i_qp], 2, 16, g_dump );
+            fwrite( h->dequant4_mf[CQM_4IY], 4, 6*16, g_dump );
+        }
+    }
+}
+
 /* ---- embed stage -------------------------------------------------------------------------------- */
 void pcamv_hook_embed( x264_t *h, int an )
 {

@@ -81,4 +81,4 @@ def test_rd_pieces_compile_for_sm_100a(tmp_path):
                         os.path.join(ROOT, "tools", "probes", "rd_compile_probe.cu"), "-o", str(tmp_path / "rd_probe.o")],
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-3000:]
-    assert "k_rd_cost_probe" in p.stderr and "sm_100a" in p.stderr
+    assert "k_rd_cost_probe" in p.stderr and "k_intra_probe" in p.stderr and "sm_100a" in p.stderr

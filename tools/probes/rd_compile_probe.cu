@@ -1,4 +1,5 @@
-// rd_compile_probe.cu — compile-only evidence that the RD pieces (csrc/pcamv_cavlc.cuh, csrc/pcamv_rd.cuh) are device code:
+// rd_compile_probe.cu — compile-only evidence that the RD pieces (csrc/pcamv_cavlc.cuh, csrc/pcamv_rd.cuh) and the intra mode analysis
+// (csrc/pcamv_intra.cuh, second kernel) are device code:
 // one macroblock-per-team kernel that runs a candidate through motion compensation, the kept levels, the product's residual path,
 // the distortion and the CAVLC size, built for sm_100a by tests/test_emu_cavlc.py::test_rd_pieces_compile_for_sm_100a
 // (nvcc -c; nothing launches it — the pieces are not on the product path).
@@ -6,6 +7,7 @@
 #include "../../video-steganography-pcamv_b200/csrc/pcamv_recon.cuh"
 #include "../../video-steganography-pcamv_b200/csrc/pcamv_cavlc.cuh"
 #include "../../video-steganography-pcamv_b200/csrc/pcamv_rd.cuh"
+#include "../../video-steganography-pcamv_b200/csrc/pcamv_intra.cuh"
 
 using namespace pcamv;
 
@@ -42,4 +44,24 @@ __global__ void k_rd_cost_probe(DevFrameCtx fc, FrameParams fp, const CavlcSizes
         }
         team_sync();
     }
+}
+
+// the intra mode analysis of one macroblock per team (lane 0 does the work: the pieces are one-lane code so far)
+struct IntraJob { Intra4x4In in4; uint8_t fenc_u[64], fenc_v[64], border[33 + 34]; int has_left, has_top, has_topleft; };
+
+__global__ void k_intra_probe(const IntraJob *jobs, int n, IntraCosts *costs, int *cost4, int *modes4)
+{
+    for (int i = blockIdx.x; i < n; i += gridDim.x)
+        if (threadIdx.x == 0)
+        {
+            const IntraJob &j = jobs[i];
+            IntraCosts o;
+            intra_analyse_16x16(j.in4.fenc, j.has_left, j.has_top, j.has_topleft, j.border[0], j.border + 1, j.border + 17, j.in4.lambda, o);
+            const int tl[2] = { j.border[33], j.border[50] };
+            intra_analyse_chroma(j.fenc_u, j.fenc_v, j.has_left, j.has_top, j.has_topleft, tl, j.border + 34, j.border + 42, j.border + 51, j.border + 59, j.in4.lambda, o);
+            costs[i] = o;
+            int pred[16];
+            cost4[i] = intra_analyse_4x4(j.in4, pred);
+            for (int k = 0; k < 16; k++) modes4[16 * i + k] = pred[k];
+        }
 }

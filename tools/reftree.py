@@ -198,3 +198,20 @@ def rd_hook(tree):
                   r"\1        pcamv_hook_rd_mb( h, i_ssd, bs_tmp.i_bits_encoded, i_lambda2 );\n", 1, "rd_cost_mb cavlc size")
     t = "void pcamv_hook_rd_mb( x264_t *h, int i_ssd, int i_bits_encoded, int i_lambda2 );\n" + t
     write(p, t)
+
+
+def intra_hook(tree):
+    """oracle variant x264_dump_rd: x264_mb_analyse_intra (encoder/analyse.c:628-879) is wrapped; after every call the wrapper reports
+    what the analysis saw and decided to oracle/ref_hooks.c::pcamv_hook_intra."""
+    p = os.path.join(tree, "encoder/analyse.c")
+    t = read(p)
+    t = sub_exact(t, r"\nstatic void x264_mb_analyse_intra\( x264_t \*h, x264_mb_analysis_t \*a, int i_satd_inter \)\n\{",
+                  "\nstatic void x264_mb_analyse_intra_real( x264_t *h, x264_mb_analysis_t *a, int i_satd_inter )\n{", 1, "analyse_intra def")
+    wrapper = ("void pcamv_hook_intra( x264_t *h, int lambda, int i_satd_inter, int satd16, int pred16, const int *dir16, int satd_c, int pred_c, int satd4, const int *pred4,\n"
+               "                       int i_qp, int i_mbrd, int b_fast_intra, int i_satd_i8x8 );\n"
+               "static void x264_mb_analyse_intra( x264_t *h, x264_mb_analysis_t *a, int i_satd_inter )\n"
+               "{\n    x264_mb_analyse_intra_real( h, a, i_satd_inter );\n"
+               "    pcamv_hook_intra( h, a->i_lambda, i_satd_inter, a->i_satd_i16x16, a->i_predict16x16, a->i_satd_i16x16_dir, a->i_satd_i8x8chroma,\n"
+               "                      a->i_predict8x8chroma, a->i_satd_i4x4, a->i_predict4x4, a->i_qp, a->i_mbrd, a->b_fast_intra, a->i_satd_i8x8 );\n}\n\n")
+    t = sub_exact(t, r"\nstatic void x264_intra_rd\( x264_t \*h, x264_mb_analysis_t \*a, int i_satd_thresh \)\n", "\n" + wrapper.replace("\\", "\\\\") + "static void x264_intra_rd( x264_t *h, x264_mb_analysis_t *a, int i_satd_thresh )\n", 1, "intra wrapper")
+    write(p, t)

@@ -30,7 +30,8 @@
  * element per vector-carrying partition, LSB of mv_x + mv_y) and the payload (syndrome under the embedder's sub-matrices,
  * host/pcamv_stc_extract.c).  CLI (host/build_host.py):
  *
- *   x264_pcamv --parse-mv IN.264 -o MV.bin                      per P picture: int32 picture, n_mb, mb_w, mb_h, qp, cabac + n_mb records
+ *   x264_pcamv --parse-mv IN.264 -o MV.bin [--csv]              per P picture: int32 picture, n_mb, mb_w, mb_h, qp, cabac + n_mb records
+ *                                                               (--csv: one text line per macroblock instead)
  *   x264_pcamv --extract-264 IN.264 --emrate R -o MESSAGE.bin [--stego STEGO.bin]
  *
  * What bitstream-side extraction can and cannot give for the reference's own output is a property of the reference, measured
@@ -897,7 +898,7 @@ static int picture_stego( const pcamv_picture *pic, uint8_t *stego )
 }
 
 /* ---- CLI ------------------------------------------------------------------------------------------------------------------------ */
-typedef struct { FILE *mv, *msg, *stego; float rate; int frames, bits, skipped, carriers, p_pictures; } cli_t;
+typedef struct { FILE *mv, *msg, *stego; float rate; int frames, bits, skipped, carriers, p_pictures, csv; } cli_t;
 
 static int on_picture_mv( void *user, const pcamv_picture *pic )
 {
@@ -905,6 +906,21 @@ static int on_picture_mv( void *user, const pcamv_picture *pic )
     int32_t hd[6] = { pic->picture, pic->n_mb, pic->mb_w, pic->mb_h, pic->qp, pic->cabac };
     if( !pic->is_p ) return 0;
     c->p_pictures++;
+    if( c->csv )
+    {
+        /* one line per macroblock: picture, mb_x, mb_y, type, partition, the four sub-partition types, the four references, then the
+         * sixteen vectors (quarter-pel x, y) in block_idx order - the motion field as steganalysis tools want it */
+        int mb, i;
+        for( mb = 0; mb < pic->n_mb; mb++ )
+        {
+            const pcamv_mvrec *r = &pic->mb[mb];
+            fprintf( c->mv, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", pic->picture, mb % pic->mb_w, mb / pic->mb_w, r->type, r->partition,
+                     r->sub[0], r->sub[1], r->sub[2], r->sub[3], r->ref[0], r->ref[1], r->ref[2], r->ref[3] );
+            for( i = 0; i < 16; i++ ) fprintf( c->mv, ",%d,%d", r->mv[i][0], r->mv[i][1] );
+            fputc( '\n', c->mv );
+        }
+        return ferror( c->mv );
+    }
     return fwrite( hd, 4, 6, c->mv ) != 6 || (int)fwrite( pic->mb, sizeof(pcamv_mvrec), pic->n_mb, c->mv ) != pic->n_mb;
 }
 static int on_picture_extract( void *user, const pcamv_picture *pic )
@@ -959,7 +975,7 @@ static uint8_t *read_file( const char *path, size_t *size )
     *size = n;
     return buf;
 }
-/* `x264_pcamv --parse-mv IN.264 -o MV.bin` and `x264_pcamv --extract-264 IN.264 --emrate R -o MESSAGE.bin [--stego STEGO.bin]` */
+/* `x264_pcamv --parse-mv IN.264 -o MV.bin [--csv]` and `x264_pcamv --extract-264 IN.264 --emrate R -o MESSAGE.bin [--stego STEGO.bin]` */
 int pcamv_bitstream_main( int argc, char **argv )
 {
     const int extract = !strcmp( argv[1], "--extract-264" );
@@ -977,6 +993,8 @@ int pcamv_bitstream_main( int argc, char **argv )
         else if( !strcmp( argv[i], "--emrate" ) ) c.rate = atof( argv[i + 1] );      /* x264.c:522 */
         else if( !strcmp( argv[i], "--stego" ) ) stego = argv[i + 1];
     }
+    for( i = 3; i < argc; i++ )
+        if( !strcmp( argv[i], "--csv" ) ) c.csv = 1;
     if( !out ) { fprintf( stderr, "x264 [error]: %s needs -o\n", argv[1] ); return -1; }
     if( extract && !( c.rate > 0 ) ) { fprintf( stderr, "x264 [error]: --extract-264 needs the embedder's --emrate\n" ); return -1; }
     data = read_file( in, &size );

@@ -238,3 +238,21 @@ def test_extractor_recognises_frames_the_embedder_gave_up_on(pcamv, tmp_path):
             gave_up += 1
             assert an == 0
     assert gave_up >= 1
+
+
+def test_parse_mv_csv_is_the_same_motion_field(pcamv, tmp_path):
+    """`--parse-mv --csv`: the text form (one line per macroblock) carries exactly the binary records."""
+    stream, _ = encode(pcamv, "x264_dump_conformant", (176, 144), 3, "--qp 26 --ref 2 --keyint 250 --me hex --subme 5 --partitions all --emrate 0.2", 32, 15, str(tmp_path))
+    pics = parse_mv(stream, str(tmp_path))
+    out = str(tmp_path / "mv.csv")
+    p = subprocess.run([HOST, "--parse-mv", stream, "-o", out, "--csv"], capture_output=True, timeout=60)
+    assert p.returncode == 0, p.stderr[-1000:].decode("latin-1")
+    rows = np.loadtxt(out, delimiter=",", dtype=np.int64)
+    assert rows.shape == (sum(pc["n_mb"] for pc in pics), 13 + 32)
+    k = 0
+    for pc in pics:
+        for mb, r in enumerate(pc["mb"]):
+            row = rows[k]; k += 1
+            assert row[0] == pc["picture"] and row[1] == mb % pc["mb_w"] and row[2] == mb // pc["mb_w"]
+            assert row[3] == r["type"] and row[4] == r["partition"] and list(row[5:9]) == list(r["sub"]) and list(row[9:13]) == list(r["ref"])
+            assert np.array_equal(row[13:].reshape(16, 2), r["mv"])
